@@ -1,0 +1,173 @@
+/* rheo_gpu.h — C-ABI of the B200-native viscoelastic stress step (log-conformation models).
+ *
+ * One handle == one `Foam::constitutiveEq` object of the reference (or one `multiMode` wrapper with
+ * n_modes sub-models) living on one GPU / one MPI rank.  Each entry point cites the reference
+ * interface it replaces; paths are relative to of90/src/libs/constitutiveEquations/constitutiveEqs/.
+ *
+ *   rheo_gpu_create            <- XxxLog constructors (Oldroyd-B/Oldroyd-BLog/Oldroyd_BLog.C:43-122,
+ *                                 Giesekus/GiesekusLog/GiesekusLog.C:43-123, PTT/PTTLog/PTTLog.C:58-171,
+ *                                 FENE-P/FENE-PLog/FENE_PLog.C:43-123, multiMode/multiMode.C:41-92) and
+ *                                 the run-time selection call constitutiveEq/newConstitutiveEq.C:32-61
+ *   rheo_gpu_upload_state      <- MUST_READ tau/theta and READ_IF_PRESENT eigVals/eigVecs
+ *                                 (Oldroyd_BLog.C:52-113; defaults = identity)
+ *   rheo_gpu_upload_velocity   <- the const references U(), phi() the model holds
+ *                                 (constitutiveEq/constitutiveEq.H:72-75,285-295)
+ *   rheo_gpu_store_old_time    <- theta_.oldTime() bookkeeping done by OpenFOAM when runTime++
+ *                                 (fvm::ddt(theta_), Oldroyd_BLog.C:143)
+ *   rheo_gpu_step              <- constitutiveEq::correct() (constitutiveEq.H:346-350; bodies:
+ *                                 Oldroyd_BLog.C:127-179, GiesekusLog.C:128-176, PTTLog.C:176-268,
+ *                                 FENE_PLog.C:128-182, multiMode.C:247-260)
+ *   rheo_gpu_download          <- tau() (constitutiveEq.H:314; multiMode.C:216-226) and the AUTO_WRITE
+ *                                 of tau/theta/eigVals/eigVecs at write time (Oldroyd_BLog.C:52-113)
+ *   rheo_gpu_correct           <- correct() + tau() as a CPU momentum predictor uses them
+ *                                 (of90/src/solvers/rheoFoam/rheoFoam.C:147-153, UEqn.H:12)
+ *   rheo_gpu_last_error        <- FatalErrorInFunction text (newConstitutiveEq.C:47-58); every call
+ *                                 returns 0 on success, non-zero on error (the C++ shim turns that
+ *                                 into FatalError).
+ *
+ * Host arrays use OpenFOAM's AoS layouts (vector 3, symmTensor 6 = xx,xy,xz,yy,yz,zz, tensor 9
+ * row-major); on the device everything is FP64 structure-of-arrays in a colour-sorted numbering
+ * (see DESIGN.md).  There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef RHEO_GPU_H
+#define RHEO_GPU_H
+
+#include <stdint.h>
+#include "rheo_mesh.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* constitutive models (`type` in constitutiveProperties) */
+#define RHEO_MODEL_OLDROYD_B_LOG 0
+#define RHEO_MODEL_GIESEKUS_LOG  1
+#define RHEO_MODEL_PTT_LOG       2
+#define RHEO_MODEL_FENE_P_LOG    3
+
+/* PTTLog destructionFunctionType (PTT/PTTLog/PTTLog.C:41-50,190-237) */
+#define RHEO_PTT_LINEAR      0
+#define RHEO_PTT_EXPONENTIAL 1
+#define RHEO_PTT_GENERALIZED 2
+
+/* GaussDefCmpw limiter (gaussDefCmpwConvectionScheme/limiters.H:48-98) */
+#define RHEO_LIMITER_UPWIND   0
+#define RHEO_LIMITER_CUBISTA  1
+#define RHEO_LIMITER_MINMOD   2
+#define RHEO_LIMITER_SMART    3
+#define RHEO_LIMITER_WACEB    4
+#define RHEO_LIMITER_SUPERBEE 5
+#define RHEO_LIMITER_NONE     6   /* no convection */
+
+#define RHEO_DDT_EULER 0
+
+#define RHEO_SOLVER_PBICGSTAB 0
+#define RHEO_SOLVER_PBICG     1
+
+typedef struct RheoModelDesc {
+    int32_t model;          /* RHEO_MODEL_*                                   */
+    double  rho, etaS, etaP, lambda;
+    double  alpha;          /* GiesekusLog mobility                            */
+    double  epsilon, zeta;  /* PTTLog                                          */
+    int32_t ptt_function;   /* RHEO_PTT_*                                      */
+    double  ml_alpha, ml_beta, ml_rtol;  /* PTTLog generalized (Mittag-Leffler) */
+    int32_t ml_max_iter;
+    double  L2;             /* FENE-PLog extensibility                         */
+} RheoModelDesc;
+
+typedef struct RheoSchemeCtl {
+    int32_t limiter;        /* divSchemes div(phi,theta) GaussDefCmpw <limiter>          */
+    int32_t ddt;            /* ddtSchemes: RHEO_DDT_EULER                                */
+    int32_t solver;         /* fvSolution solvers.theta.solver                           */
+    double  tolerance;      /* fvSolution tolerance                                      */
+    double  rel_tol;        /* fvSolution relTol                                         */
+    int32_t min_iter;
+    int32_t max_iter;
+    double  relax;          /* relaxationFactors.equations.theta; <= 0 : relax() is a no-op */
+} RheoSchemeCtl;
+
+/* mirrors OpenFOAM SolverPerformance<symmTensor> per mode */
+typedef struct RheoStepStats {
+    double  initial_residual[6];
+    double  final_residual[6];
+    int32_t n_iterations[6];
+    int32_t converged[6];
+} RheoStepStats;
+
+typedef struct RheoGpu RheoGpu;
+
+/* what rheo_gpu_download / rheo_gpu_upload_field move */
+#define RHEO_FIELD_THETA      0  /* symmTensor, 6/cell */
+#define RHEO_FIELD_TAU        1  /* symmTensor, 6/cell */
+#define RHEO_FIELD_EIGVALS    2  /* tensor, 9/cell (diagonal = exp(eig)) */
+#define RHEO_FIELD_EIGVECS    3  /* tensor, 9/cell (columns = eigenvectors) */
+#define RHEO_FIELD_THETA_B    4  /* symmTensor, 6/boundary face */
+#define RHEO_FIELD_TAU_B      5  /* symmTensor, 6/boundary face */
+#define RHEO_FIELD_TAU_TOTAL  6  /* sum over modes of tau, 6/cell (multiMode::tau) */
+#define RHEO_FIELD_THETA_OLD  7
+
+int rheo_gpu_device_count(void);
+
+/* Build the device-resident model.  The mesh arrays are only read during the call. */
+int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_t n_modes,
+                    const RheoSchemeCtl* ctl, int32_t device, RheoGpu** out);
+void rheo_gpu_destroy(RheoGpu* h);
+
+/* Multi-GPU: one rank per GPU.  Rank 0 obtains an id (128 bytes), the host broadcasts it by any
+ * means (MPI_Bcast in the OpenFOAM shim, torch.distributed in bench.py), every rank then joins.
+ * Halo swaps of processor patches and Krylov reductions then go through NCCL on the model's stream. */
+int rheo_gpu_nccl_unique_id(void* id128);
+int rheo_gpu_comm_init(RheoGpu* h, int32_t rank, int32_t n_ranks, const void* id128);
+
+/* State.  NULL eigvals/eigvecs => identity (READ_IF_PRESENT default); NULL theta_b/tau_b => boundary
+ * values derived from the BC (fixedValue patches then hold 0). */
+int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const double* tau,
+                          const double* eigvals, const double* eigvecs,
+                          const double* theta_b, const double* tau_b);
+
+/* U [3*n_cells], U_b [3*n_boundary_faces] (values on processor/empty faces ignored),
+ * phi [n_faces] (internal then boundary).  Pageable or pinned host memory. */
+int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi);
+
+int rheo_gpu_store_old_time(RheoGpu* h);
+
+/* One constitutiveEq::correct() for all modes, inputs already resident in HBM.
+ * stats: array of n_modes entries or NULL (NULL avoids the final device->host read). */
+int rheo_gpu_step(RheoGpu* h, double dt, RheoStepStats* stats);
+
+int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst);
+
+/* Host-buffer convenience = upload_velocity + store_old_time (if new_time_step) + step +
+ * download(TAU_TOTAL) (+ TAU_B of mode 0 when tau_b != NULL): what the reference plugin call costs
+ * when the momentum predictor stays on the CPU. */
+int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const double* phi, double dt,
+                     int32_t new_time_step, double* tau_out, double* tau_b_out, RheoStepStats* stats);
+
+/* ---- introspection used by the parity tests and bench.py ---- */
+/* renumbering actually used on the device: perm[new] = old cell, n_colours, colour_start[n_colours+1] */
+int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int32_t* colour_start);
+/* ELL width K and the neighbour table nbr[K*n_cells] (slot-major, in NEW numbering: >=0 cell,
+ * >= n_cells ghost, -1 empty, <=-2 boundary face -(b+2)) and face table (face index, ~face when
+ * the cell is the face's neighbour) */
+int rheo_gpu_get_ell(RheoGpu* h, int32_t* K, int32_t* nbr, int32_t* face);
+/* kernels launched by this handle so far (all of them are this library's own) */
+int64_t rheo_gpu_launch_count(const RheoGpu* h);
+/* Krylov iterations (max over components and modes) of the last step */
+int rheo_gpu_last_iterations(const RheoGpu* h);
+/* per-phase device times of the last step measured with CUDA events when enabled (ms):
+ * [0] halo+bc  [1] grad(theta)  [2] assemble  [3] solve  [4] eig+tau  [5] tau bc  [6] total */
+int rheo_gpu_set_phase_timing(RheoGpu* h, int32_t enabled);
+int rheo_gpu_get_phase_times(RheoGpu* h, double* ms7);
+/* device buffers for callers that keep U/phi on the GPU (SoA, renumbered) */
+int rheo_gpu_stream(RheoGpu* h, void** cuda_stream);
+int rheo_gpu_synchronize(RheoGpu* h);
+
+/* stand-alone per-cell kernels on host arrays (n cells, AoS) — used by the unit parity tests */
+int rheo_gpu_eig_exp(int32_t device, int32_t n, const double* theta6, double* eigvals9, double* eigvecs9);
+
+const char* rheo_gpu_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHEO_GPU_H */

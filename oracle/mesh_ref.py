@@ -1,0 +1,232 @@
+"""numpy restatement of the INTEGER contracts of the GPU library.  TEST INFRASTRUCTURE ONLY.
+
+  * colour_renumber   greedy multi-colouring in cell order + colour-major stable sort (what
+                      rheo_gpu_create applies on the device; DESIGN.md "Renumbering")
+  * renumbered_mesh   the mesh after that permutation in OpenFOAM upper-triangular order — what
+                      `renumberMesh` would write — so the C++ oracle can run on it
+  * ell_tables        slot-major ELL neighbour / face tables in the new numbering
+  * simple_decomp     EXT-OF9 simpleGeomDecomp (decomposeParDict method simple)
+  * sub_mesh          EXT-OF9 domainDecomposition processor mesh (cells ascending, internal faces in
+                      global order, physical patches, processor patches by neighbour rank)
+Everything here must agree BIT-EXACTLY with the product's integer arrays (tests/test_mesh_integers.py).
+Written independently (numpy, different algorithmic route) from rheotool_b200/csrc/host/*.cpp.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+PATCH_EMPTY, PATCH_PROCESSOR = 2, 3
+
+
+@dataclass
+class RefMesh:
+    n_cells: int
+    owner: np.ndarray          # [n_faces] int32
+    neighbour: np.ndarray      # [n_internal] int32
+    Sf: np.ndarray
+    Cf: np.ndarray
+    C: np.ndarray
+    V: np.ndarray
+    weights: np.ndarray
+    nbr_C: np.ndarray
+    patches: list              # [(type, start, size, nbr_rank, theta_bc, tau_bc)]
+    solved: list
+    cell_addr: np.ndarray | None = None
+    face_addr: np.ndarray | None = None
+    _keep: list = field(default_factory=list)
+
+    @property
+    def n_faces(self):
+        return len(self.owner)
+
+    @property
+    def n_internal(self):
+        return len(self.neighbour)
+
+
+def from_host_mesh(m) -> RefMesh:
+    pat = [(p.type, p.start, p.size, p.nbr_rank, p.theta_bc, p.tau_bc) for p in m.patches]
+    return RefMesh(m.n_cells, m.owner.copy(), m.neighbour.copy(), m.Sf.copy(), m.Cf.copy(), m.C.copy(), m.V.copy(),
+                   m.weights.copy(), m.nbr_C.copy(), pat, list(m.solved))
+
+
+def to_desc(rm: RefMesh, abi):
+    """Build a RheoMeshDesc (ctypes) over contiguous copies kept alive inside rm."""
+    import ctypes as C
+    d = abi.RheoMeshDesc()
+    own = np.ascontiguousarray(rm.owner, dtype=np.int32)
+    nei = np.ascontiguousarray(rm.neighbour if len(rm.neighbour) else np.zeros(1), dtype=np.int32)
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (rm.Sf, rm.Cf, rm.C, rm.V, rm.weights,
+                                                                rm.nbr_C if len(rm.nbr_C) else np.zeros((1, 3)))]
+    pats = (abi.RheoPatchDesc * len(rm.patches))()
+    for i, p in enumerate(rm.patches):
+        pats[i].type, pats[i].start, pats[i].size, pats[i].nbr_rank, pats[i].theta_bc, pats[i].tau_bc = p
+    rm._keep = [own, nei, arrs, pats]
+    d.n_cells, d.n_faces, d.n_internal_faces, d.n_patches = rm.n_cells, rm.n_faces, rm.n_internal, len(rm.patches)
+    d.owner = own.ctypes.data_as(C.POINTER(C.c_int32))
+    d.neighbour = nei.ctypes.data_as(C.POINTER(C.c_int32))
+    dp = C.POINTER(C.c_double)
+    d.Sf, d.Cf, d.C, d.V, d.weights, d.nbr_C = [a.ctypes.data_as(dp) for a in arrs]
+    d.patches = pats
+    for q in range(6):
+        d.solved_components[q] = rm.solved[q]
+    return d
+
+
+# ------------------------------------------------------------------------------------------ colouring
+def colour_renumber(n_cells: int, owner: np.ndarray, neighbour: np.ndarray):
+    """Returns (perm[new]=old, colour[old], colour_start)."""
+    nint = len(neighbour)
+    lower = [[] for _ in range(n_cells)]   # already-coloured neighbours = neighbours with a smaller index
+    for f in range(nint):
+        o, n = int(owner[f]), int(neighbour[f])
+        if o < n:
+            lower[n].append(o)
+        else:
+            lower[o].append(n)
+    colour = np.zeros(n_cells, dtype=np.int32)
+    for c in range(n_cells):
+        used = {int(colour[q]) for q in lower[c]}
+        k = 0
+        while k in used:
+            k += 1
+        colour[c] = k
+    perm = np.argsort(colour, kind="stable").astype(np.int32)
+    ncol = int(colour.max()) + 1
+    cstart = np.zeros(ncol + 1, dtype=np.int32)
+    cstart[1:] = np.cumsum(np.bincount(colour, minlength=ncol))
+    return perm, colour, cstart
+
+
+def face_order(n_cells, owner, neighbour, perm):
+    """New internal-face order: signed old face ids (+(f+1), negative = flipped), new owner / neighbour."""
+    iperm = np.empty(n_cells, dtype=np.int64)
+    iperm[perm] = np.arange(n_cells)
+    nint = len(neighbour)
+    o = iperm[owner[:nint]]
+    n = iperm[neighbour]
+    flip = o > n
+    lo, hi = np.minimum(o, n), np.maximum(o, n)
+    order = np.lexsort((hi, lo))
+    signed = np.where(flip[order], -(order + 1), order + 1).astype(np.int32)
+    return signed, lo[order].astype(np.int32), hi[order].astype(np.int32), iperm
+
+
+def renumbered_mesh(rm: RefMesh, perm: np.ndarray) -> RefMesh:
+    signed, no, nn, iperm = face_order(rm.n_cells, rm.owner, rm.neighbour, perm)
+    nint = rm.n_internal
+    old = np.abs(signed) - 1
+    sg = np.sign(signed).astype(np.float64)
+    owner = np.concatenate([no, iperm[rm.owner[nint:]].astype(np.int32)])
+    Sf = np.concatenate([rm.Sf[old] * sg[:, None], rm.Sf[nint:]])
+    Cf = np.concatenate([rm.Cf[old], rm.Cf[nint:]])
+    w = np.concatenate([np.where(signed > 0, rm.weights[old], 1.0 - rm.weights[old]), rm.weights[nint:]])
+    out = RefMesh(rm.n_cells, owner, nn, Sf, Cf, rm.C[perm], rm.V[perm], w, rm.nbr_C.copy(), list(rm.patches), list(rm.solved))
+    out.face_addr = np.concatenate([signed, np.arange(nint, rm.n_faces, dtype=np.int32) + 1])
+    out.cell_addr = perm.copy()
+    return out
+
+
+def ell_tables(rm: RefMesh, perm: np.ndarray):
+    """(nbr[K,N], face[K,N]) as rheo_gpu_get_ell returns them."""
+    signed, no, nn, iperm = face_order(rm.n_cells, rm.owner, rm.neighbour, perm)
+    N, nint = rm.n_cells, rm.n_internal
+    rows = [[] for _ in range(N)]
+    for q in range(nint):
+        rows[no[q]].append((int(nn[q]), q))
+        rows[nn[q]].append((int(no[q]), ~q))
+    for c in range(N):
+        rows[c].sort(key=lambda t: t[0])
+    h = 0
+    for (ptype, start, size, _r, _a, _b) in rm.patches:
+        for f in range(start, start + size):
+            if ptype == PATCH_EMPTY:
+                continue
+            c = int(iperm[rm.owner[f]])
+            b = f - nint
+            if ptype == PATCH_PROCESSOR:
+                rows[c].append((N + h, f))
+                h += 1
+            else:
+                rows[c].append((-(b + 2), f))
+    K = max(len(r) for r in rows)
+    nbr = np.full((K, N), -1, dtype=np.int32)
+    face = np.zeros((K, N), dtype=np.int32)
+    for c, r in enumerate(rows):
+        for s, (nb, fq) in enumerate(r):
+            nbr[s, c] = nb
+            face[s, c] = fq
+    return nbr, face
+
+
+# ------------------------------------------------------------------------------------------ decomposition
+def simple_decomp(C: np.ndarray, n, delta=1e-3):
+    px, py, pz = n
+    d = 1 - 0.5 * delta * delta
+    d2, a, a2 = d * d, delta, delta * delta
+    R = np.array([[d2, -a * d, a], [a * d - a2 * d, a * a2 + d2, -2 * a * d], [a * d2 + a2, a * d - a2 * d, d2 - a2]])
+    rp = C @ R.T
+    ncell = len(C)
+    out = np.zeros(ncell, dtype=np.int32)
+    mult = [1, px, px * py]
+    for dirn, npd in enumerate((px, py, pz)):
+        order = np.argsort(rp[:, dirn], kind="stable")
+        per, rem = divmod(ncell, npd)
+        counts = [per + (1 if g < rem else 0) for g in range(npd)]
+        group = np.repeat(np.arange(npd), counts)
+        out[order] += (mult[dirn] * group).astype(np.int32)
+    return out
+
+
+def sub_mesh(rm: RefMesh, c2r: np.ndarray, n_ranks: int, rank: int) -> RefMesh:
+    nint = rm.n_internal
+    mine = np.nonzero(c2r == rank)[0]
+    g2l = -np.ones(rm.n_cells, dtype=np.int64)
+    g2l[mine] = np.arange(len(mine))
+    ro, rn = c2r[rm.owner[:nint]], c2r[rm.neighbour]
+    fin = np.nonzero((ro == rank) & (rn == rank))[0]
+    owner = [g2l[rm.owner[fin]]]
+    neigh = g2l[rm.neighbour[fin]]
+    faces = [fin + 1]
+    w = [rm.weights[fin]]
+    nbrC = []
+    patches = []
+    pos = len(fin)
+    for (ptype, start, size, _r, tb, ub) in rm.patches:
+        fs = np.arange(start, start + size)
+        fs = fs[c2r[rm.owner[fs]] == rank]
+        owner.append(g2l[rm.owner[fs]])
+        faces.append(fs + 1)
+        w.append(rm.weights[fs])
+        nbrC.append(np.zeros((len(fs), 3)))
+        patches.append((ptype, pos, len(fs), -1, tb, ub))
+        pos += len(fs)
+    for r in range(n_ranks):
+        if r == rank:
+            continue
+        a = np.nonzero((ro == rank) & (rn == r))[0]     # local cell is the global owner
+        b = np.nonzero((ro == r) & (rn == rank))[0]     # local cell is the global neighbour -> flipped
+        fs = np.concatenate([a, b])
+        if len(fs) == 0:
+            continue
+        flip = np.concatenate([np.zeros(len(a), bool), np.ones(len(b), bool)])
+        srt = np.argsort(fs, kind="stable")
+        fs, flip = fs[srt], flip[srt]
+        loc = np.where(flip, rm.neighbour[fs], rm.owner[fs])
+        oth = np.where(flip, rm.owner[fs], rm.neighbour[fs])
+        owner.append(g2l[loc])
+        faces.append(np.where(flip, -(fs + 1), fs + 1))
+        w.append(np.where(flip, 1.0 - rm.weights[fs], rm.weights[fs]))
+        nbrC.append(rm.C[oth])
+        patches.append((PATCH_PROCESSOR, pos, len(fs), r, 4, 4))
+        pos += len(fs)
+    faces = np.concatenate(faces).astype(np.int32)
+    of = np.abs(faces) - 1
+    sg = np.sign(faces).astype(np.float64)
+    out = RefMesh(len(mine), np.concatenate(owner).astype(np.int32), neigh.astype(np.int32), rm.Sf[of] * sg[:, None], rm.Cf[of],
+                  rm.C[mine], rm.V[mine], np.concatenate(w), np.concatenate(nbrC) if nbrC else np.zeros((0, 3)), patches, list(rm.solved))
+    out.cell_addr = mine.astype(np.int32)
+    out.face_addr = faces
+    return out

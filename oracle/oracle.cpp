@@ -1,0 +1,1109 @@
+// oracle.cpp — CPU restatement of rheoTool's log-conformation stress step.  TEST INFRASTRUCTURE ONLY.
+//
+// This file is the parity oracle and the timed CPU baseline.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load it; the product (rheotool_b200/)
+// never does.
+//
+// PARITY UNPINNED: the reference cannot be built here (needs OpenFOAM-9, Eigen 3.2.9, MPI; none is
+// installed, no network) and ships no golden vectors for this path.  The oracle
+// is therefore pinned only (a) line-by-line against the reference sources cited at each function,
+// (b) against analytic material functions and algebraic identities (tests/test_oracle_*.py).
+//
+// Conventions follow OpenFOAM: symmTensor = (xx,xy,xz,yy,yz,zz); tensor row-major; fields AoS;
+// face loops in face order; one scalar Krylov solve per valid component (segregated).
+// Paths below are relative to /root/reference/of90/src/libs/ ; CE = constitutiveEquations/constitutiveEqs.
+// "EXT-OF9" marks OpenFOAM-9 behaviour that is not in /root/reference and is restated from its
+// published semantics.
+//
+// Multi-rank runs are emulated in-process: a Case holds R sub-domain meshes with processor patches;
+// "messages" are copies; global reductions sum per-rank partial sums in rank order.  Each phase is an
+// OpenMP loop over ranks, which is also how the multi-core CPU baseline is timed.
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rheo_gpu.h"
+#include "rheo_mesh.h"
+
+namespace {
+
+typedef std::vector<double> dvec;
+
+std::string g_err;
+
+// ------------------------------------------------------------------ small tensor algebra (EXT-OF9)
+struct T9 { double v[9]; };
+inline T9 mul(const T9& a, const T9& b) {   // A & B
+    T9 r;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            r.v[3 * i + j] = a.v[3 * i] * b.v[j] + a.v[3 * i + 1] * b.v[3 + j] + a.v[3 * i + 2] * b.v[6 + j];
+    return r;
+}
+inline T9 transpose(const T9& a) { return T9{{a.v[0], a.v[3], a.v[6], a.v[1], a.v[4], a.v[7], a.v[2], a.v[5], a.v[8]}}; }
+inline T9 add(const T9& a, const T9& b) { T9 r; for (int i = 0; i < 9; ++i) r.v[i] = a.v[i] + b.v[i]; return r; }
+inline T9 sub(const T9& a, const T9& b) { T9 r; for (int i = 0; i < 9; ++i) r.v[i] = a.v[i] - b.v[i]; return r; }
+inline T9 scale(double s, const T9& a) { T9 r; for (int i = 0; i < 9; ++i) r.v[i] = s * a.v[i]; return r; }
+inline T9 identity() { return T9{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+inline T9 from_sym(const double* s) { return T9{{s[0], s[1], s[2], s[1], s[3], s[4], s[2], s[4], s[5]}}; }
+inline void symm(const T9& t, double* s) {   // EXT-OF9 symm(T) = 1/2 (T + T^T)
+    s[0] = t.v[0]; s[1] = 0.5 * (t.v[1] + t.v[3]); s[2] = 0.5 * (t.v[2] + t.v[6]);
+    s[3] = t.v[4]; s[4] = 0.5 * (t.v[5] + t.v[7]); s[5] = t.v[8];
+}
+inline double tr(const T9& t) { return t.v[0] + t.v[4] + t.v[8]; }
+inline T9 inv(const T9& t) {   // EXT-OF9 inv(tensor): cofactors / det (general formula, also for diagonal input)
+    const double xx = t.v[0], xy = t.v[1], xz = t.v[2], yx = t.v[3], yy = t.v[4], yz = t.v[5], zx = t.v[6], zy = t.v[7], zz = t.v[8];
+    const double det = xx * yy * zz + xy * yz * zx + xz * yx * zy - xx * yz * zy - xy * yx * zz - xz * yy * zx;
+    T9 r = {{yy * zz - zy * yz, xz * zy - xy * zz, xy * yz - xz * yy,
+             zx * yz - yx * zz, xx * zz - xz * zx, yx * xz - xx * yz,
+             yx * zy - yy * zx, xy * zx - xx * zy, xx * yy - yx * xy}};
+    for (int i = 0; i < 9; ++i) r.v[i] /= det;
+    return r;
+}
+// CE/constitutiveEq/constitutiveEq.C:471-518  innerP: (t1^T & t2) & t1  or  (t1 & t2) & t1^T
+inline T9 innerP(const T9& t1, const T9& t2, bool firstT) {
+    return firstT ? mul(mul(transpose(t1), t2), t1) : mul(mul(t1, t2), transpose(t1));
+}
+inline double pos(double x) { return x >= 0 ? 1.0 : 0.0; }
+
+// ------------------------------------------------------------------ mesh / state
+struct Patch { int type, start, size, nbr_rank, theta_bc, tau_bc, nbr_patch; };
+
+struct Mesh {
+    int nCells = 0, nFaces = 0, nInt = 0;
+    std::vector<int> own, nei, losort;
+    dvec Sf, Cf, C, V, w, nbrC;
+    std::vector<Patch> patches;
+    int solved[6];
+    int nB() const { return nFaces - nInt; }
+};
+
+struct Model {
+    RheoModelDesc d;
+    dvec gammaVals;   // CE/PTT/PTTLog/PTTLog.C:143-170
+    int mlMaxIter = 0;
+};
+
+struct Mode {
+    Model model;
+    dvec theta, thetaOld, tau, eigVals, eigVecs, thetaB, tauB;
+};
+
+struct Rank {
+    Mesh mesh;
+    std::vector<Mode> modes;
+    dvec U, Ub, phi;
+    // per-step work (one mode at a time, like the reference)
+    dvec L, rhs, fFene, diag, lower, upper, source, iC, bC, gradTheta;
+};
+
+struct Case {
+    std::vector<Rank> ranks;
+    RheoSchemeCtl ctl;
+    bool sortEig = true;   // order eigenpairs ascending like Eigen::SelfAdjointEigenSolver (CE/constitutiveEq/constitutiveEq.C:390-414)
+    int lastIters = 0;
+    bool finalized = false;
+};
+
+// patchNeighbourField of a cell field with nc components per cell (EXT-OF9 processorFvPatchField)
+template <class Get>
+void patch_neighbour(const Case& cs, int r, const Patch& p, int nc, Get get, double* out) {
+    const Rank& o = cs.ranks[p.nbr_rank];
+    const Patch& q = o.mesh.patches[p.nbr_patch];
+    const double* fld = get(p.nbr_rank);
+    for (int i = 0; i < p.size; ++i) {
+        const int cell = o.mesh.own[q.start + i];
+        for (int k = 0; k < nc; ++k) out[(size_t)nc * i + k] = fld[(size_t)nc * cell + k];
+    }
+    (void)r;
+}
+
+// ------------------------------------------------------------------ CE/utils/jacobi.H:7-158
+// Cyclic Jacobi, 50 fixed sweeps, thresholds exactly as in the reference (incl. tresh = 0.2*sm*sm
+// for the first three sweeps).  Returns V (columns = eigenvectors) and D (eigenvalues, unsorted).
+void jacobi_ref(const double* At, double* D, double* V) {
+    const int N = 3;
+    double A[3][3] = {{At[0], At[1], At[2]}, {At[1], At[3], At[4]}, {At[2], At[4], At[5]}};
+    double B[3], Z[3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) V[3 * i + j] = (i == j) ? 1.0 : 0.0;
+    for (int ip = 0; ip < N; ++ip) { B[ip] = A[ip][ip]; D[ip] = B[ip]; Z[ip] = 0; }
+    for (int i = 1; i <= 50; ++i) {
+        double sm = 0;
+        for (int ip = 0; ip < N - 1; ++ip)
+            for (int iq = ip + 1; iq <= N - 1; ++iq) sm = sm + std::fabs(A[ip][iq]);
+        double tresh = (i < 4) ? 0.2 * sm * sm : 0.0;
+        for (int ip = 0; ip < N - 1; ++ip) {
+            for (int iq = ip + 1; iq <= N - 1; ++iq) {
+                double g = 100 * std::fabs(A[ip][iq]);
+                if ((i > 4) && (std::fabs(D[ip]) + g == std::fabs(D[ip])) && (std::fabs(D[iq]) + g == std::fabs(D[iq])))
+                    A[ip][iq] = 0;
+                else if (std::fabs(A[ip][iq]) > tresh) {
+                    double h = D[iq] - D[ip], t;
+                    if (std::fabs(h) + g == std::fabs(h))
+                        t = A[ip][iq] / h;
+                    else {
+                        double theta = 0.5 * h / A[ip][iq];
+                        t = 1 / (std::fabs(theta) + std::sqrt(1.0 + theta * theta));
+                        if (theta < 0) t = -t;
+                    }
+                    double c = 1.0 / std::sqrt(1.0 + t * t), s = t * c, tau = s / (1.0 + c);
+                    h = t * A[ip][iq];
+                    Z[ip] -= h; Z[iq] += h; D[ip] -= h; D[iq] += h;
+                    A[ip][iq] = 0;
+                    for (int j = 0; j < ip; ++j) {
+                        g = A[j][ip]; h = A[j][iq];
+                        A[j][ip] = g - s * (h + g * tau); A[j][iq] = h + s * (g - h * tau);
+                    }
+                    for (int j = ip + 1; j < iq; ++j) {
+                        g = A[ip][j]; h = A[j][iq];
+                        A[ip][j] = g - s * (h + g * tau); A[j][iq] = h + s * (g - h * tau);
+                    }
+                    for (int j = iq + 1; j <= N - 1; ++j) {
+                        g = A[ip][j]; h = A[iq][j];
+                        A[ip][j] = g - s * (h + g * tau); A[iq][j] = h + s * (g - h * tau);
+                    }
+                    for (int j = 0; j <= N - 1; ++j) {
+                        g = V[3 * j + ip]; h = V[3 * j + iq];
+                        V[3 * j + ip] = g - s * (h + g * tau); V[3 * j + iq] = h + s * (g - h * tau);
+                    }
+                }
+            }
+        }
+        for (int ip = 0; ip <= N - 1; ++ip) { B[ip] += Z[ip]; D[ip] = B[ip]; Z[ip] = 0; }
+    }
+}
+
+// CE/constitutiveEq/constitutiveEq.C:360-416  calcEig: vecs columns = eigenvectors,
+// vals = diag(exp(eig)), off-diagonals zeroed.  Back-end = jacobi.H restatement (the in-tree
+// alternative, constitutiveEq.C:418-426); the active Eigen-3.2.9 QR back-end returns ascending
+// eigenvalues, which `sortEig` reproduces (tau, theta, Omega, B are invariant to order and sign).
+void calc_eig_cell(const double* theta6, double* vals9, double* vecs9, bool sortEig) {
+    double D[3], V[9];
+    jacobi_ref(theta6, D, V);
+    int idx[3] = {0, 1, 2};
+    if (sortEig) std::stable_sort(idx, idx + 3, [&](int a, int b) { return D[a] < D[b]; });
+    for (int i = 0; i < 9; ++i) vals9[i] = 0.0;
+    for (int c = 0; c < 3; ++c) {
+        vals9[4 * c] = std::exp(D[idx[c]]);
+        for (int r = 0; r < 3; ++r) vecs9[3 * r + c] = V[3 * r + idx[c]];
+    }
+}
+
+// ------------------------------------------------------------------ Gauss-linear gradient (EXT-OF9)
+// gaussGrad::gradf + linear interpolation; call sites CE/utils/boilerLog.H:1,
+// gaussDefCmpwConvectionScheme/gaussDefCmpwConvectionScheme.C:254,
+// boundaryConditions/linearExtrapolation/linearExtrapolationFvPatchField.C:130.
+// psi: nc components per cell; psiFaceB: face values on boundary faces (nc per boundary face);
+// out: 3*nc per cell, out[(3*k? )] layout: for component k, gradient d = out[cell*3*nc + 3*k + d]
+void gauss_grad(const Mesh& m, int nc, const double* psi, const double* psiFaceB, double* out) {
+    std::fill(out, out + (size_t)3 * nc * m.nCells, 0.0);
+    for (int f = 0; f < m.nInt; ++f) {
+        const int P = m.own[f], N = m.nei[f];
+        const double* S = &m.Sf[3 * (size_t)f];
+        for (int k = 0; k < nc; ++k) {
+            const double pf = m.w[f] * (psi[(size_t)nc * P + k] - psi[(size_t)nc * N + k]) + psi[(size_t)nc * N + k];
+            for (int d = 0; d < 3; ++d) {
+                const double sp = S[d] * pf;
+                out[(size_t)3 * nc * P + 3 * k + d] += sp;
+                out[(size_t)3 * nc * N + 3 * k + d] -= sp;
+            }
+        }
+    }
+    for (const Patch& p : m.patches) {
+        if (p.type == RHEO_PATCH_EMPTY) continue;
+        for (int f = p.start; f < p.start + p.size; ++f) {
+            const int P = m.own[f];
+            const double* S = &m.Sf[3 * (size_t)f];
+            const double* pb = &psiFaceB[(size_t)nc * (f - m.nInt)];
+            for (int k = 0; k < nc; ++k)
+                for (int d = 0; d < 3; ++d) out[(size_t)3 * nc * P + 3 * k + d] += S[d] * pb[k];
+        }
+    }
+    for (int c = 0; c < m.nCells; ++c)
+        for (int q = 0; q < 3 * nc; ++q) out[(size_t)3 * nc * c + q] /= m.V[c];
+}
+
+// boundary FACE values used by the linear scheme: non-coupled = patch value, coupled =
+// w*psi_P + (1-w)*psi_N (EXT-OF9 surfaceInterpolationScheme::interpolate).
+template <class Get>
+void face_values_boundary(const Case& cs, int r, int nc, Get get, const double* patchVals, double* out) {
+    const Mesh& m = cs.ranks[r].mesh;
+    const double* psi = get(r);
+    dvec nbr;
+    for (const Patch& p : m.patches) {
+        if (p.type == RHEO_PATCH_EMPTY) continue;
+        if (p.type == RHEO_PATCH_PROCESSOR) {
+            nbr.resize((size_t)nc * p.size);
+            patch_neighbour(cs, r, p, nc, get, nbr.data());
+            for (int i = 0; i < p.size; ++i) {
+                const int f = p.start + i, P = m.own[f];
+                for (int k = 0; k < nc; ++k)
+                    out[(size_t)nc * (f - m.nInt) + k] = m.w[f] * psi[(size_t)nc * P + k] + (1.0 - m.w[f]) * nbr[(size_t)nc * i + k];
+            }
+        } else {
+            for (int f = p.start; f < p.start + p.size; ++f)
+                for (int k = 0; k < nc; ++k) out[(size_t)nc * (f - m.nInt) + k] = patchVals[(size_t)nc * (f - m.nInt) + k];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ per-cell algebra
+// CE/utils/boilerLog.H:26-34 + CE/constitutiveEq/constitutiveEq.C:323-358 (decomposeGradU)
+void decompose_gradU_cell(const T9& L, const T9& R, const T9& Lam, double zeta, bool ptt, T9& omega, T9& B) {
+    T9 X = transpose(L);
+    if (ptt) {   // L.T() - zeta*symm(L)
+        double s[6];
+        symm(L, s);
+        X = sub(X, scale(zeta, from_sym(s)));
+    }
+    const T9 M = innerP(R, X, true);
+    T9 b = {{M.v[0], 0, 0, 0, M.v[4], 0, 0, 0, M.v[8]}};
+    T9 o = {{0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    const double lx = Lam.v[0], ly = Lam.v[4], lz = Lam.v[8];
+    o.v[1] = (ly * M.v[1] + lx * M.v[3]) / (ly - lx + 1e-16);
+    o.v[2] = (lz * M.v[2] + lx * M.v[6]) / (lz - lx + 1e-16);
+    o.v[5] = (lz * M.v[5] + ly * M.v[7]) / (lz - ly + 1e-16);
+    o.v[3] = -o.v[1]; o.v[6] = -o.v[2]; o.v[7] = -o.v[5];
+    omega = innerP(R, o, false);
+    B = innerP(R, b, false);
+}
+
+// Mittag-Leffler series, CE/PTT/PTTLog/PTTLog.C:202-236
+double mittag_leffler(const Model& mo, double zi) {
+    double sum = 0, sumOld = 0, error = 1;
+    int k = 0;
+    while (k < mo.mlMaxIter && error > mo.d.ml_rtol) {
+        double Eabk = std::pow(zi, k) / mo.gammaVals[k + 1];
+        sumOld = sum;
+        sum += Eabk;
+        error = std::fabs((sumOld - sum) / (sumOld + 1e-12));
+        k++;
+    }
+    return sum;
+}
+
+// right-hand side of the theta equation for one cell; returns FENE-P's f (else 0)
+//   Oldroyd_BLog.C:146-163, GiesekusLog.C:142-157, PTTLog.C:190-251, FENE_PLog.C:142-163
+double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const T9& R, const T9& Lam, double* rhs6) {
+    const RheoModelDesc& d = mo.d;
+    T9 omega, B;
+    decompose_gradU_cell(L, R, Lam, d.zeta, d.model == RHEO_MODEL_PTT_LOG, omega, B);
+    const T9 I = identity();
+    const T9 th = from_sym(theta6);
+    T9 acc = add(sub(mul(omega, th), mul(th, omega)), scale(2.0, B));
+    double f = 0;
+    switch (d.model) {
+        case RHEO_MODEL_OLDROYD_B_LOG:
+            acc = add(acc, scale(1.0 / d.lambda, innerP(R, sub(inv(Lam), I), false)));
+            break;
+        case RHEO_MODEL_GIESEKUS_LOG: {
+            const T9 trhs = mul(mul(R, sub(inv(Lam), I)), transpose(R));
+            const T9 A = mul(mul(R, Lam), transpose(R));
+            acc = add(acc, scale(1.0 / d.lambda, sub(trhs, scale(d.alpha, mul(A, mul(trhs, trhs))))));
+            break;
+        }
+        case RHEO_MODEL_PTT_LOG: {
+            T9 ext = scale(1.0 / d.lambda, mul(mul(R, sub(inv(Lam), I)), transpose(R)));
+            const T9 A = mul(mul(R, Lam), transpose(R));
+            const double z = (d.epsilon / (1 - d.zeta)) * (tr(A) - 3.);
+            if (d.ptt_function == RHEO_PTT_LINEAR) ext = scale(1. + z, ext);
+            else if (d.ptt_function == RHEO_PTT_EXPONENTIAL) ext = scale(std::exp(z), ext);
+            else ext = scale(mo.gammaVals[0] * mittag_leffler(mo, z), ext);
+            acc = add(acc, ext);
+            break;
+        }
+        case RHEO_MODEL_FENE_P_LOG: {
+            const T9 A = mul(mul(R, Lam), transpose(R));
+            f = d.L2 / (d.L2 - tr(A));
+            const double a = d.L2 / (d.L2 - 3.);
+            acc = add(acc, scale(1.0 / d.lambda, mul(mul(R, sub(scale(a, inv(Lam)), scale(f, I))), transpose(R))));
+            break;
+        }
+    }
+    symm(acc, rhs6);
+    return f;
+}
+
+// theta -> tau for one cell: Oldroyd_BLog.C:175, GiesekusLog.C:172, PTTLog.C:264, FENE_PLog.C:178
+void tau_cell(const Model& mo, const T9& R, const T9& Lam, double fOld, double* tau6) {
+    const RheoModelDesc& d = mo.d;
+    const T9 A = innerP(R, Lam, false);
+    const T9 I = identity();
+    double s[6];
+    double coef = d.etaP / d.lambda;
+    if (d.model == RHEO_MODEL_FENE_P_LOG) {
+        const double a = d.L2 / (d.L2 - 3.);
+        symm(sub(scale(fOld, A), scale(a, I)), s);
+    } else {
+        if (d.model == RHEO_MODEL_PTT_LOG) coef = d.etaP / (d.lambda * (1 - d.zeta));
+        symm(sub(A, I), s);
+    }
+    for (int q = 0; q < 6; ++q) tau6[q] = coef * s[q];
+}
+
+// ------------------------------------------------------------------ limiter table
+// gaussDefCmpwConvectionScheme/limiters.H:48-98
+bool limiter_table(int lim, double* alpha, double* beta, double* bounds) {
+    switch (lim) {
+        case RHEO_LIMITER_CUBISTA: alpha[0] = 7. / 4.; alpha[1] = 3. / 4.; alpha[2] = 1. / 4.; beta[0] = 0.; beta[1] = 3. / 8.; beta[2] = 3. / 4.; bounds[0] = 3. / 8.; bounds[1] = 3. / 4.; return true;
+        case RHEO_LIMITER_MINMOD: alpha[0] = 1.5; alpha[1] = .5; alpha[2] = .5; beta[0] = 0.; beta[1] = .5; beta[2] = .5; bounds[0] = .5; bounds[1] = 1.; return true;
+        case RHEO_LIMITER_SMART: alpha[0] = 3.; alpha[1] = 3. / 4.; alpha[2] = 0.; beta[0] = 0.; beta[1] = 3. / 8.; beta[2] = 1.; bounds[0] = 1. / 6.; bounds[1] = 5. / 6.; return true;
+        case RHEO_LIMITER_WACEB: alpha[0] = 2.; alpha[1] = 3. / 4.; alpha[2] = 0.; beta[0] = 0.; beta[1] = 3. / 8.; beta[2] = 1.; bounds[0] = 3. / 10.; bounds[1] = 5. / 6.; return true;
+        case RHEO_LIMITER_SUPERBEE: alpha[0] = 0.5; alpha[1] = 1.5; alpha[2] = 0.; beta[0] = 0.5; beta[1] = 0.; beta[2] = 1.; bounds[0] = 1. / 2.; bounds[1] = 2. / 3.; return true;
+        default: return false;
+    }
+}
+
+// deferred-correction face value, gaussDefCmpwConvectionScheme.C:259-274 (swit = 1) and :304-317
+inline double phif_defc(double vP, double vN, const double* gP, const double* gN, const double* dlt, double upw,
+                        const double* aL, const double* bL, const double* bnd) {
+    const double gd_up = (gP[0] * upw + (1.0 - upw) * gN[0]) * dlt[0] + (gP[1] * upw + (1.0 - upw) * gN[1]) * dlt[1] +
+                         (gP[2] * upw + (1.0 - upw) * gN[2]) * dlt[2];
+    const double phitc = 1.0 - ((vN - vP) / (2.0 * gd_up + 1e-18));
+    double alpha, beta;
+    if (phitc <= 0. || phitc >= 1.) { alpha = 1.; beta = 0.; }
+    else if (phitc < bnd[0]) { alpha = aL[0]; beta = bL[0]; }
+    else if (phitc < bnd[1]) { alpha = aL[1]; beta = bL[1]; }
+    else { alpha = aL[2]; beta = bL[2]; }
+    const double gPd = gP[0] * dlt[0] + gP[1] * dlt[1] + gP[2] * dlt[2];
+    const double gNd = gN[0] * dlt[0] + gN[1] * dlt[1] + gN[2] * dlt[2];
+    return (1.0 - alpha - beta) * (vN - 2.0 * gPd) * upw + (1.0 - alpha - beta) * (vP + 2.0 * gNd) * (1.0 - upw) +
+           ((alpha - 1.0) * upw + beta * (1.0 - upw)) * vP + (beta * upw + (alpha - 1.0) * (1.0 - upw)) * vN;
+}
+
+// ------------------------------------------------------------------ distributed vectors + LDU ops (EXT-OF9)
+struct DVec { std::vector<dvec> v; };
+
+struct Ldu {   // one scalar system per component on the shared LDU structure
+    Case* cs;
+    // per rank: diag (incl. internalCoeffs of this component), lower, upper, interface boundary coeffs
+    std::vector<const double*> lower, upper;
+    std::vector<dvec> diag;
+    std::vector<dvec> ifBou, ifInt;   // per boundary face (only processor faces used)
+};
+
+template <class F> void for_ranks(Case& cs, F f) {
+    const int R = (int)cs.ranks.size();
+#pragma omp parallel for schedule(static) if (R > 1)
+    for (int r = 0; r < R; ++r) f(r);
+}
+
+double gsum(Case& cs, const std::vector<double>& part) { double s = 0; for (size_t r = 0; r < cs.ranks.size(); ++r) s += part[r]; return s; }
+
+// lduMatrix::Amul / Tmul incl. processor interfaces (result -= coeff * psi_nbr)
+void amul(Ldu& A, DVec& y, const DVec& x, bool transposeA) {
+    Case& cs = *A.cs;
+    for_ranks(cs, [&](int r) {
+        const Mesh& m = cs.ranks[r].mesh;
+        double* yy = y.v[r].data();
+        const double* xx = x.v[r].data();
+        const double* lo = transposeA ? A.upper[r] : A.lower[r];
+        const double* up = transposeA ? A.lower[r] : A.upper[r];
+        for (int c = 0; c < m.nCells; ++c) yy[c] = A.diag[r][c] * xx[c];
+        for (int f = 0; f < m.nInt; ++f) {
+            yy[m.nei[f]] += lo[f] * xx[m.own[f]];
+            yy[m.own[f]] += up[f] * xx[m.nei[f]];
+        }
+        const dvec& co = transposeA ? A.ifInt[r] : A.ifBou[r];
+        for (const Patch& p : m.patches) {
+            if (p.type != RHEO_PATCH_PROCESSOR) continue;
+            const Rank& o = cs.ranks[p.nbr_rank];
+            const Patch& q = o.mesh.patches[p.nbr_patch];
+            const double* xo = x.v[p.nbr_rank].data();
+            for (int i = 0; i < p.size; ++i) {
+                const int f = p.start + i;
+                yy[m.own[f]] -= co[f - m.nInt] * xo[o.mesh.own[q.start + i]];
+            }
+        }
+    });
+}
+
+// lduMatrix::sumA
+void sum_a(Ldu& A, DVec& s) {
+    Case& cs = *A.cs;
+    for_ranks(cs, [&](int r) {
+        const Mesh& m = cs.ranks[r].mesh;
+        double* ss = s.v[r].data();
+        for (int c = 0; c < m.nCells; ++c) ss[c] = A.diag[r][c];
+        for (int f = 0; f < m.nInt; ++f) { ss[m.nei[f]] += A.lower[r][f]; ss[m.own[f]] += A.upper[r][f]; }
+        for (const Patch& p : m.patches)
+            if (p.type == RHEO_PATCH_PROCESSOR)
+                for (int f = p.start; f < p.start + p.size; ++f) ss[m.own[f]] -= A.ifBou[r][f - m.nInt];
+    });
+}
+
+// DILUPreconditioner (rank-local)
+struct Dilu {
+    std::vector<dvec> rD;
+    void init(Ldu& A) {
+        Case& cs = *A.cs;
+        rD.resize(cs.ranks.size());
+        for_ranks(cs, [&](int r) {
+            const Mesh& m = cs.ranks[r].mesh;
+            rD[r] = A.diag[r];
+            double* d = rD[r].data();
+            for (int f = 0; f < m.nInt; ++f) d[m.nei[f]] -= A.upper[r][f] * A.lower[r][f] / d[m.own[f]];
+            for (int c = 0; c < m.nCells; ++c) d[c] = 1.0 / d[c];
+        });
+    }
+    void precondition(Ldu& A, DVec& w, const DVec& rr, bool transposeA) {
+        Case& cs = *A.cs;
+        for_ranks(cs, [&](int r) {
+            const Mesh& m = cs.ranks[r].mesh;
+            const double* d = rD[r].data();
+            double* ww = w.v[r].data();
+            const double* rv = rr.v[r].data();
+            const double* lo = A.lower[r];
+            const double* up = A.upper[r];
+            for (int c = 0; c < m.nCells; ++c) ww[c] = d[c] * rv[c];
+            if (!transposeA) {
+                for (int q = 0; q < m.nInt; ++q) { const int f = m.losort[q]; ww[m.nei[f]] -= d[m.nei[f]] * lo[f] * ww[m.own[f]]; }
+                for (int f = m.nInt - 1; f >= 0; --f) ww[m.own[f]] -= d[m.own[f]] * up[f] * ww[m.nei[f]];
+            } else {
+                for (int f = 0; f < m.nInt; ++f) ww[m.nei[f]] -= d[m.nei[f]] * up[f] * ww[m.own[f]];
+                for (int q = m.nInt - 1; q >= 0; --q) { const int f = m.losort[q]; ww[m.own[f]] -= d[m.own[f]] * lo[f] * ww[m.nei[f]]; }
+            }
+        });
+    }
+};
+
+struct Perf { double init = 0, fin = 0; int iters = 0; bool conv = false; bool singular = false; };
+
+bool check_conv(const Perf& p, double tol, double relTol) {
+    return p.fin < tol || (relTol > 1e-20 && p.fin < relTol * p.init);
+}
+
+template <class F> double reduce_ranks(Case& cs, F f) {
+    std::vector<double> part(cs.ranks.size(), 0.0);
+    for_ranks(cs, [&](int r) { part[r] = f(r); });
+    return gsum(cs, part);
+}
+
+DVec make_vec(Case& cs) {
+    DVec v;
+    v.v.resize(cs.ranks.size());
+    for (size_t r = 0; r < cs.ranks.size(); ++r) v.v[r].assign(cs.ranks[r].mesh.nCells, 0.0);
+    return v;
+}
+
+// lduMatrix::solver::normFactor (restated in-repo: sparseMatrixSolvers/segregated/sparseSolver.C:152-179)
+double norm_factor(Ldu& A, const DVec& psi, const DVec& source, const DVec& Apsi, DVec& tmp) {
+    Case& cs = *A.cs;
+    sum_a(A, tmp);
+    double tot = reduce_ranks(cs, [&](int r) { double s = 0; for (double v : psi.v[r]) s += v; return s; });
+    long n = 0;
+    for (auto& rk : cs.ranks) n += rk.mesh.nCells;
+    const double xRef = tot / (double)n;   // gAverage
+    return reduce_ranks(cs, [&](int r) {
+               double s = 0;
+               const size_t nc = psi.v[r].size();
+               for (size_t c = 0; c < nc; ++c) {
+                   const double t = tmp.v[r][c] * xRef;
+                   s += std::fabs(Apsi.v[r][c] - t) + std::fabs(source.v[r][c] - t);
+               }
+               return s;
+           }) + 1e-20;
+}
+
+// EXT-OF9 PBiCGStab::solve (van der Vorst, right-preconditioned)
+Perf pbicgstab(Ldu& A, DVec& psi, const DVec& source, const RheoSchemeCtl& ctl) {
+    Case& cs = *A.cs;
+    Perf perf;
+    DVec yA = make_vec(cs), rA = make_vec(cs), pA = make_vec(cs);
+    amul(A, yA, psi, false);
+    for_ranks(cs, [&](int r) { for (size_t c = 0; c < rA.v[r].size(); ++c) rA.v[r][c] = source.v[r][c] - yA.v[r][c]; });
+    const double normFactor = norm_factor(A, psi, source, yA, pA);
+    auto sumMag = [&](const DVec& v) { return reduce_ranks(cs, [&](int r) { double s = 0; for (double x : v.v[r]) s += std::fabs(x); return s; }); };
+    auto sumProd = [&](const DVec& a, const DVec& b) { return reduce_ranks(cs, [&](int r) { double s = 0; for (size_t c = 0; c < a.v[r].size(); ++c) s += a.v[r][c] * b.v[r][c]; return s; }); };
+    perf.init = sumMag(rA) / normFactor;
+    perf.fin = perf.init;
+    if (ctl.min_iter > 0 || !check_conv(perf, ctl.tolerance, ctl.rel_tol)) {
+        DVec AyA = make_vec(cs), sA = make_vec(cs), zA = make_vec(cs), tA = make_vec(cs);
+        const DVec rA0 = rA;
+        double rA0rA = 0, alpha = 0, omega = 0;
+        Dilu pre;
+        pre.init(A);
+        do {
+            const double rA0rAold = rA0rA;
+            rA0rA = sumProd(rA0, rA);
+            if (!(std::fabs(rA0rA) > 1e-300)) { perf.singular = true; break; }
+            if (perf.iters == 0) {
+                pA = rA;
+            } else {
+                if (!(std::fabs(omega) > 1e-300)) { perf.singular = true; break; }
+                const double beta = (rA0rA / rA0rAold) * (alpha / omega);
+                for_ranks(cs, [&](int r) { for (size_t c = 0; c < pA.v[r].size(); ++c) pA.v[r][c] = rA.v[r][c] + beta * (pA.v[r][c] - omega * AyA.v[r][c]); });
+            }
+            pre.precondition(A, yA, pA, false);
+            amul(A, AyA, yA, false);
+            const double rA0AyA = sumProd(rA0, AyA);
+            alpha = rA0rA / rA0AyA;
+            for_ranks(cs, [&](int r) { for (size_t c = 0; c < sA.v[r].size(); ++c) sA.v[r][c] = rA.v[r][c] - alpha * AyA.v[r][c]; });
+            perf.fin = sumMag(sA) / normFactor;
+            if (check_conv(perf, ctl.tolerance, ctl.rel_tol)) {
+                for_ranks(cs, [&](int r) { for (size_t c = 0; c < psi.v[r].size(); ++c) psi.v[r][c] += alpha * yA.v[r][c]; });
+                perf.iters++;
+                perf.conv = true;
+                return perf;
+            }
+            pre.precondition(A, zA, sA, false);
+            amul(A, tA, zA, false);
+            const double tAtA = sumProd(tA, tA);
+            omega = sumProd(tA, sA) / tAtA;
+            for_ranks(cs, [&](int r) {
+                for (size_t c = 0; c < psi.v[r].size(); ++c) {
+                    psi.v[r][c] += alpha * yA.v[r][c] + omega * zA.v[r][c];
+                    rA.v[r][c] = sA.v[r][c] - omega * tA.v[r][c];
+                }
+            });
+            perf.fin = sumMag(rA) / normFactor;
+        } while ((perf.iters++ < ctl.max_iter && !check_conv(perf, ctl.tolerance, ctl.rel_tol)) || perf.iters < ctl.min_iter);
+    }
+    perf.conv = check_conv(perf, ctl.tolerance, ctl.rel_tol);
+    return perf;
+}
+
+// EXT-OF9 PBiCG::solve (the solver every theta tutorial selects, e.g.
+// of90/tutorials/rheoFoam/Cylinder/Oldroyd-BLog/system/fvSolution:32-45)
+Perf pbicg(Ldu& A, DVec& psi, const DVec& source, const RheoSchemeCtl& ctl) {
+    Case& cs = *A.cs;
+    Perf perf;
+    DVec pA = make_vec(cs), wA = make_vec(cs), pT = make_vec(cs), wT = make_vec(cs), rA = make_vec(cs), rT = make_vec(cs);
+    amul(A, wA, psi, false);
+    amul(A, wT, psi, true);
+    for_ranks(cs, [&](int r) {
+        for (size_t c = 0; c < rA.v[r].size(); ++c) { rA.v[r][c] = source.v[r][c] - wA.v[r][c]; rT.v[r][c] = source.v[r][c] - wT.v[r][c]; }
+    });
+    const double normFactor = norm_factor(A, psi, source, wA, pA);
+    auto sumMag = [&](const DVec& v) { return reduce_ranks(cs, [&](int r) { double s = 0; for (double x : v.v[r]) s += std::fabs(x); return s; }); };
+    auto sumProd = [&](const DVec& a, const DVec& b) { return reduce_ranks(cs, [&](int r) { double s = 0; for (size_t c = 0; c < a.v[r].size(); ++c) s += a.v[r][c] * b.v[r][c]; return s; }); };
+    perf.init = sumMag(rA) / normFactor;
+    perf.fin = perf.init;
+    if (ctl.min_iter > 0 || !check_conv(perf, ctl.tolerance, ctl.rel_tol)) {
+        Dilu pre;
+        pre.init(A);
+        double wArT = 1e300;   // solverPerf.great_
+        do {
+            const double wArTold = wArT;
+            pre.precondition(A, wA, rA, false);
+            pre.precondition(A, wT, rT, true);
+            wArT = sumProd(wA, rT);
+            if (perf.iters == 0) {
+                pA = wA; pT = wT;
+            } else {
+                const double beta = wArT / wArTold;
+                for_ranks(cs, [&](int r) {
+                    for (size_t c = 0; c < pA.v[r].size(); ++c) { pA.v[r][c] = wA.v[r][c] + beta * pA.v[r][c]; pT.v[r][c] = wT.v[r][c] + beta * pT.v[r][c]; }
+                });
+            }
+            amul(A, wA, pA, false);
+            amul(A, wT, pT, true);
+            const double wApT = sumProd(wA, pT);
+            if (!(std::fabs(wApT) / normFactor > 1e-300)) { perf.singular = true; break; }
+            const double alpha = wArT / wApT;
+            for_ranks(cs, [&](int r) {
+                for (size_t c = 0; c < psi.v[r].size(); ++c) {
+                    psi.v[r][c] += alpha * pA.v[r][c];
+                    rA.v[r][c] -= alpha * wA.v[r][c];
+                    rT.v[r][c] -= alpha * wT.v[r][c];
+                }
+            });
+            perf.fin = sumMag(rA) / normFactor;
+        } while ((perf.iters++ < ctl.max_iter && !check_conv(perf, ctl.tolerance, ctl.rel_tol)) || perf.iters < ctl.min_iter);
+    }
+    perf.conv = check_conv(perf, ctl.tolerance, ctl.rel_tol);
+    return perf;
+}
+
+// ------------------------------------------------------------------ one constitutiveEq::correct() of one mode
+int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
+    const int R = (int)cs.ranks.size();
+    const RheoSchemeCtl& ctl = cs.ctl;
+    if (ctl.ddt != RHEO_DDT_EULER) { g_err = "oracle: only the Euler ddt scheme is restated"; return 3; }
+    double aL[3] = {1, 1, 1}, bL[3] = {0, 0, 0}, bnd[2] = {1, 1};
+    const bool hrs = limiter_table(ctl.limiter, aL, bL, bnd);
+    const bool noConv = (ctl.limiter == RHEO_LIMITER_NONE);
+
+    // --- boilerLog.H:1  L = fvc::grad(U)   (EXT-OF9 Gauss linear; processor faces interpolate with the neighbour cell)
+    for_ranks(cs, [&](int r) {
+        Rank& rk = cs.ranks[r];
+        const Mesh& m = rk.mesh;
+        dvec fb((size_t)3 * m.nB(), 0.0);
+        face_values_boundary(cs, r, 3, [&](int q) { return cs.ranks[q].U.data(); }, rk.Ub.data(), fb.data());
+        rk.L.resize((size_t)9 * m.nCells);
+        gauss_grad(m, 3, rk.U.data(), fb.data(), rk.L.data());
+        // gauss_grad stores, for component k of U, gradient d at [3k+d]; OpenFOAM's L_ij = d_i U_j = [3i+j]
+        for (int c = 0; c < m.nCells; ++c) {
+            double* l = &rk.L[(size_t)9 * c];
+            std::swap(l[1], l[3]); std::swap(l[2], l[6]); std::swap(l[5], l[7]);
+        }
+    });
+
+    // --- per-cell: Omega/B split and model source (uses the eigen-pairs of the PREVIOUS theta)
+    for_ranks(cs, [&](int r) {
+        Rank& rk = cs.ranks[r];
+        Mode& mo = rk.modes[mi];
+        const int n = rk.mesh.nCells;
+        rk.rhs.resize((size_t)6 * n);
+        rk.fFene.assign(n, 0.0);
+        for (int c = 0; c < n; ++c) {
+            T9 L, Rm, Lam;
+            std::memcpy(L.v, &rk.L[(size_t)9 * c], 72);
+            std::memcpy(Rm.v, &mo.eigVecs[(size_t)9 * c], 72);
+            std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
+            rk.fFene[c] = model_rhs_cell(mo.model, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c]);
+        }
+    });
+
+    // --- fvm::ddt(theta) + fvm::div(phi,theta)  (EXT-OF9 EulerDdtScheme; gaussDefCmpwConvectionScheme.C:70-170)
+    const double rDeltaT = 1.0 / dt;
+    for_ranks(cs, [&](int r) {
+        Rank& rk = cs.ranks[r];
+        Mode& mo = rk.modes[mi];
+        const Mesh& m = rk.mesh;
+        const int n = m.nCells, nB = m.nB();
+        rk.diag.assign(n, 0.0);
+        rk.source.assign((size_t)6 * n, 0.0);
+        rk.lower.assign(m.nInt, 0.0);
+        rk.upper.assign(m.nInt, 0.0);
+        rk.iC.assign(nB, 0.0);
+        rk.bC.assign((size_t)6 * nB, 0.0);
+        for (int c = 0; c < n; ++c) {
+            rk.diag[c] = rDeltaT * m.V[c];
+            for (int q = 0; q < 6; ++q) rk.source[(size_t)6 * c + q] = rDeltaT * mo.thetaOld[(size_t)6 * c + q] * m.V[c];
+        }
+        if (!noConv) {
+            dvec ddiag(n, 0.0);
+            for (int f = 0; f < m.nInt; ++f) {
+                const double upw = pos(rk.phi[f]);
+                rk.lower[f] = -upw * rk.phi[f];
+                rk.upper[f] = (1.0 - upw) * rk.phi[f];
+            }
+            for (int f = 0; f < m.nInt; ++f) { ddiag[m.own[f]] -= rk.lower[f]; ddiag[m.nei[f]] -= rk.upper[f]; }   // negSumDiag
+            for (int c = 0; c < n; ++c) rk.diag[c] += ddiag[c];
+            for (const Patch& p : m.patches) {
+                if (p.type == RHEO_PATCH_EMPTY) continue;
+                for (int f = p.start; f < p.start + p.size; ++f) {
+                    const int b = f - m.nInt;
+                    const double ph = rk.phi[f];
+                    double vIC, vBC[6];
+                    if (p.theta_bc == RHEO_BC_PROCESSOR) {
+                        const double plim = pos(ph);
+                        vIC = plim;
+                        for (int q = 0; q < 6; ++q) vBC[q] = 1.0 - plim;
+                    } else if (p.theta_bc == RHEO_BC_ZERO_GRADIENT) {
+                        vIC = 1.0;
+                        for (int q = 0; q < 6; ++q) vBC[q] = 0.0;
+                    } else {   // fixedValue
+                        vIC = 0.0;
+                        for (int q = 0; q < 6; ++q) vBC[q] = mo.thetaB[(size_t)6 * b + q];
+                    }
+                    rk.iC[b] = ph * vIC;
+                    for (int q = 0; q < 6; ++q) rk.bC[(size_t)6 * b + q] = -ph * vBC[q];
+                }
+            }
+        }
+    });
+
+    if (hrs) {
+        // phifDefC (gaussDefCmpwConvectionScheme.C:195-328): one Gauss-linear gradient per component
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            Mode& mo = rk.modes[mi];
+            const Mesh& m = rk.mesh;
+            dvec fb((size_t)6 * m.nB(), 0.0);
+            face_values_boundary(cs, r, 6, [&](int q) { return cs.ranks[q].modes[mi].theta.data(); }, mo.thetaB.data(), fb.data());
+            rk.gradTheta.resize((size_t)18 * m.nCells);
+            gauss_grad(m, 6, mo.theta.data(), fb.data(), rk.gradTheta.data());
+        });
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            Mode& mo = rk.modes[mi];
+            const Mesh& m = rk.mesh;
+            dvec souT((size_t)6 * m.nCells, 0.0);
+            for (int f = 0; f < m.nInt; ++f) {
+                const int P = m.own[f], N = m.nei[f];
+                const double upw = pos(rk.phi[f]);
+                const double dl[3] = {m.C[3 * (size_t)N] - m.C[3 * (size_t)P], m.C[3 * (size_t)N + 1] - m.C[3 * (size_t)P + 1], m.C[3 * (size_t)N + 2] - m.C[3 * (size_t)P + 2]};
+                for (int q = 0; q < 6; ++q) {
+                    const double v = phif_defc(mo.theta[(size_t)6 * P + q], mo.theta[(size_t)6 * N + q], &rk.gradTheta[(size_t)18 * P + 3 * q],
+                                               &rk.gradTheta[(size_t)18 * N + 3 * q], dl, upw, aL, bL, bnd);
+                    souT[(size_t)6 * P + q] += v * rk.phi[f];
+                    souT[(size_t)6 * N + q] -= v * rk.phi[f];
+                }
+            }
+            dvec nTh, nGr;
+            for (const Patch& p : m.patches) {
+                if (p.type != RHEO_PATCH_PROCESSOR) continue;
+                nTh.resize((size_t)6 * p.size);
+                nGr.resize((size_t)18 * p.size);
+                patch_neighbour(cs, r, p, 6, [&](int q) { return cs.ranks[q].modes[mi].theta.data(); }, nTh.data());
+                patch_neighbour(cs, r, p, 18, [&](int q) { return cs.ranks[q].gradTheta.data(); }, nGr.data());
+                for (int i = 0; i < p.size; ++i) {
+                    const int f = p.start + i, P = m.own[f], b = f - m.nInt;
+                    const double upw = pos(rk.phi[f]);
+                    const double dl[3] = {m.nbrC[3 * (size_t)b] - m.C[3 * (size_t)P], m.nbrC[3 * (size_t)b + 1] - m.C[3 * (size_t)P + 1], m.nbrC[3 * (size_t)b + 2] - m.C[3 * (size_t)P + 2]};
+                    for (int q = 0; q < 6; ++q) {
+                        const double v = phif_defc(mo.theta[(size_t)6 * P + q], nTh[(size_t)6 * i + q], &rk.gradTheta[(size_t)18 * P + 3 * q],
+                                                   &nGr[(size_t)18 * i + 3 * q], dl, upw, aL, bL, bnd);
+                        souT[(size_t)6 * P + q] += v * rk.phi[f];   // only contributes once (to owner cell)
+                    }
+                }
+            }
+            for (size_t q = 0; q < souT.size(); ++q) rk.source[q] += -souT[q];
+        });
+    }
+
+    // --- `== symm(...)`  : source += V*rhs (EXT-OF9 fvMatrix operator==)
+    for_ranks(cs, [&](int r) {
+        Rank& rk = cs.ranks[r];
+        for (int c = 0; c < rk.mesh.nCells; ++c)
+            for (int q = 0; q < 6; ++q) rk.source[(size_t)6 * c + q] += rk.mesh.V[c] * rk.rhs[(size_t)6 * c + q];
+    });
+
+    // --- thetaEqn.relax()  (EXT-OF9 fvMatrix::relax; only with a relaxation factor in fvSolution)
+    if (ctl.relax > 0) {
+        const double alpha = ctl.relax;
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            Mode& mo = rk.modes[mi];
+            const Mesh& m = rk.mesh;
+            dvec D0 = rk.diag, sumOff(m.nCells, 0.0);
+            dvec& D = rk.diag;
+            for (int f = 0; f < m.nInt; ++f) { sumOff[m.nei[f]] += std::fabs(rk.lower[f]); sumOff[m.own[f]] += std::fabs(rk.upper[f]); }
+            for (const Patch& p : m.patches) {
+                if (p.type == RHEO_PATCH_EMPTY) continue;
+                for (int f = p.start; f < p.start + p.size; ++f) {
+                    const int b = f - m.nInt;
+                    if (p.type == RHEO_PATCH_PROCESSOR) { D[m.own[f]] += rk.iC[b]; sumOff[m.own[f]] += std::fabs(rk.bC[(size_t)6 * b]); }
+                    else D[m.own[f]] += std::fabs(rk.iC[b]);   // cmptMax(cmptMag(iCoeffs))
+                }
+            }
+            for (int c = 0; c < m.nCells; ++c) D[c] = std::max(std::fabs(D[c]), sumOff[c]);
+            for (int c = 0; c < m.nCells; ++c) D[c] /= alpha;
+            for (const Patch& p : m.patches) {
+                if (p.type == RHEO_PATCH_EMPTY) continue;
+                for (int f = p.start; f < p.start + p.size; ++f) D[m.own[f]] -= rk.iC[f - m.nInt];   // coupled: component 0; else cmptMin
+            }
+            for (int c = 0; c < m.nCells; ++c)
+                for (int q = 0; q < 6; ++q) rk.source[(size_t)6 * c + q] += (D[c] - D0[c]) * mo.theta[(size_t)6 * c + q];
+        });
+    }
+
+    // --- thetaEqn.solve()  (EXT-OF9 fvMatrix::solveSegregated; in-repo restatement
+    //     sparseMatrixSolvers/segregated/sparseSolver.C:72-127 and eigenSolver/eigenSolver.C:409-563)
+    for_ranks(cs, [&](int r) {   // addBoundarySource: non-coupled only (coupled part cancels)
+        Rank& rk = cs.ranks[r];
+        const Mesh& m = rk.mesh;
+        for (const Patch& p : m.patches) {
+            if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR) continue;
+            for (int f = p.start; f < p.start + p.size; ++f)
+                for (int q = 0; q < 6; ++q) rk.source[(size_t)6 * m.own[f] + q] += rk.bC[(size_t)6 * (f - m.nInt) + q];
+        }
+    });
+    int maxIters = 0;
+    for (int cmpt = 0; cmpt < 6; ++cmpt) {
+        if (st) { st->initial_residual[cmpt] = 0; st->final_residual[cmpt] = 0; st->n_iterations[cmpt] = 0; st->converged[cmpt] = 1; }
+        if (!cs.ranks[0].mesh.solved[cmpt]) continue;
+        Ldu A;
+        A.cs = &cs;
+        A.lower.resize(R); A.upper.resize(R); A.diag.resize(R); A.ifBou.resize(R); A.ifInt.resize(R);
+        DVec psi = make_vec(cs), src = make_vec(cs);
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            const Mesh& m = rk.mesh;
+            A.lower[r] = rk.lower.data();
+            A.upper[r] = rk.upper.data();
+            A.diag[r] = rk.diag;
+            A.ifBou[r].assign(m.nB(), 0.0);
+            A.ifInt[r] = rk.iC;
+            for (const Patch& p : m.patches) {   // addBoundaryDiag
+                if (p.type == RHEO_PATCH_EMPTY) continue;
+                for (int f = p.start; f < p.start + p.size; ++f) {
+                    A.diag[r][m.own[f]] += rk.iC[f - m.nInt];
+                    A.ifBou[r][f - m.nInt] = rk.bC[(size_t)6 * (f - m.nInt) + cmpt];
+                }
+            }
+            for (int c = 0; c < m.nCells; ++c) { psi.v[r][c] = rk.modes[mi].theta[(size_t)6 * c + cmpt]; src.v[r][c] = rk.source[(size_t)6 * c + cmpt]; }
+        });
+        Perf pf = (ctl.solver == RHEO_SOLVER_PBICG) ? pbicg(A, psi, src, ctl) : pbicgstab(A, psi, src, ctl);
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            for (int c = 0; c < rk.mesh.nCells; ++c) rk.modes[mi].theta[(size_t)6 * c + cmpt] = psi.v[r][c];
+        });
+        if (st) { st->initial_residual[cmpt] = pf.init; st->final_residual[cmpt] = pf.fin; st->n_iterations[cmpt] = pf.iters; st->converged[cmpt] = pf.conv ? 1 : 0; }
+        maxIters = std::max(maxIters, pf.iters);
+    }
+    cs.lastIters = std::max(cs.lastIters, maxIters);
+
+    // --- theta.correctBoundaryConditions(); calcEig; tau; tau.correctBoundaryConditions()
+    for_ranks(cs, [&](int r) {
+        Rank& rk = cs.ranks[r];
+        Mode& mo = rk.modes[mi];
+        const Mesh& m = rk.mesh;
+        for (const Patch& p : m.patches)
+            if (p.theta_bc == RHEO_BC_ZERO_GRADIENT && p.type != RHEO_PATCH_EMPTY)
+                for (int f = p.start; f < p.start + p.size; ++f)
+                    for (int q = 0; q < 6; ++q) mo.thetaB[(size_t)6 * (f - m.nInt) + q] = mo.theta[(size_t)6 * m.own[f] + q];
+        for (int c = 0; c < m.nCells; ++c) {
+            calc_eig_cell(&mo.theta[(size_t)6 * c], &mo.eigVals[(size_t)9 * c], &mo.eigVecs[(size_t)9 * c], cs.sortEig);
+            T9 Rm, Lam;
+            std::memcpy(Rm.v, &mo.eigVecs[(size_t)9 * c], 72);
+            std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
+            tau_cell(mo.model, Rm, Lam, rk.fFene[c], &mo.tau[(size_t)6 * c]);
+        }
+    });
+    // tau BCs: processor values first (all sends complete before any evaluate), then the physical
+    // patches in patch order; linearExtrapolation (linearExtrapolationFvPatchField.C:101-151) uses a
+    // full Gauss-linear gradient per component with the boundary values current at that moment.
+    for_ranks(cs, [&](int r) {
+        Rank& rk = cs.ranks[r];
+        Mode& mo = rk.modes[mi];
+        const Mesh& m = rk.mesh;
+        dvec fb((size_t)6 * m.nB()), g((size_t)18 * m.nCells);
+        for (const Patch& p : m.patches) {
+            if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR) continue;
+            if (p.tau_bc == RHEO_BC_ZERO_GRADIENT) {
+                for (int f = p.start; f < p.start + p.size; ++f)
+                    for (int q = 0; q < 6; ++q) mo.tauB[(size_t)6 * (f - m.nInt) + q] = mo.tau[(size_t)6 * m.own[f] + q];
+            } else if (p.tau_bc == RHEO_BC_LINEAR_EXTRAPOLATION) {
+                if (p.size == 0) continue;
+                face_values_boundary(cs, r, 6, [&](int q) { return cs.ranks[q].modes[mi].tau.data(); }, mo.tauB.data(), fb.data());
+                gauss_grad(m, 6, mo.tau.data(), fb.data(), g.data());
+                dvec varp((size_t)6 * p.size);
+                for (int i = 0; i < p.size; ++i) {
+                    const int f = p.start + i, cellA = m.own[f];
+                    const double CtoF[3] = {m.Cf[3 * (size_t)f] - m.C[3 * (size_t)cellA], m.Cf[3 * (size_t)f + 1] - m.C[3 * (size_t)cellA + 1], m.Cf[3 * (size_t)f + 2] - m.C[3 * (size_t)cellA + 2]};
+                    for (int q = 0; q < 6; ++q) {
+                        const double* gq = &g[(size_t)18 * cellA + 3 * q];
+                        varp[(size_t)6 * i + q] = mo.tau[(size_t)6 * cellA + q] + (gq[0] * CtoF[0] + gq[1] * CtoF[1] + gq[2] * CtoF[2]);
+                    }
+                }
+                std::copy(varp.begin(), varp.end(), mo.tauB.begin() + (size_t)6 * (p.start - m.nInt));
+            }   // fixedValue: unchanged
+        }
+    });
+    return 0;
+}
+
+void finalize(Case& cs) {
+    for (size_t r = 0; r < cs.ranks.size(); ++r) {
+        Mesh& m = cs.ranks[r].mesh;
+        for (Patch& p : m.patches) {
+            p.nbr_patch = -1;
+            if (p.type != RHEO_PATCH_PROCESSOR) continue;
+            const Mesh& o = cs.ranks[p.nbr_rank].mesh;
+            for (size_t q = 0; q < o.patches.size(); ++q)
+                if (o.patches[q].type == RHEO_PATCH_PROCESSOR && o.patches[q].nbr_rank == (int)r) p.nbr_patch = (int)q;
+        }
+        // lduAddressing::losort: faces ordered by neighbour (upper) cell, stable
+        m.losort.resize(m.nInt);
+        for (int f = 0; f < m.nInt; ++f) m.losort[f] = f;
+        std::stable_sort(m.losort.begin(), m.losort.end(), [&](int a, int b) { return m.nei[a] < m.nei[b]; });
+    }
+    cs.finalized = true;
+}
+
+void init_model(Model& mo) {
+    mo.mlMaxIter = mo.d.ml_max_iter;
+    mo.gammaVals.clear();
+    if (mo.d.model == RHEO_MODEL_PTT_LOG && mo.d.ptt_function == RHEO_PTT_GENERALIZED) {   // PTTLog.C:143-170
+        mo.gammaVals.push_back(std::tgamma(mo.d.ml_beta));
+        int k = 0;
+        while (k < mo.mlMaxIter && mo.gammaVals.back() < 1e+100) {
+            mo.gammaVals.push_back(std::tgamma(mo.d.ml_alpha * k + mo.d.ml_beta));
+            k++;
+        }
+        mo.mlMaxIter = k;
+    }
+}
+
+}  // namespace
+
+// ==================================================================== C API (ctypes)
+extern "C" {
+
+const char* orc_last_error(void) { return g_err.c_str(); }
+
+void* orc_create(int n_ranks) {
+    auto* cs = new Case();
+    cs->ranks.resize(n_ranks);
+    cs->ctl = RheoSchemeCtl{RHEO_LIMITER_CUBISTA, RHEO_DDT_EULER, RHEO_SOLVER_PBICG, 1e-10, 0.0, 0, 1000, 0.0};
+    return cs;
+}
+void orc_destroy(void* h) { delete (Case*)h; }
+
+int orc_set_mesh(void* h, int rank, const RheoMeshDesc* d) {
+    Case& cs = *(Case*)h;
+    if (rank < 0 || rank >= (int)cs.ranks.size()) { g_err = "orc_set_mesh: bad rank"; return 1; }
+    Mesh& m = cs.ranks[rank].mesh;
+    m.nCells = d->n_cells; m.nFaces = d->n_faces; m.nInt = d->n_internal_faces;
+    m.own.assign(d->owner, d->owner + d->n_faces);
+    m.nei.assign(d->neighbour, d->neighbour + d->n_internal_faces);
+    m.Sf.assign(d->Sf, d->Sf + 3 * (size_t)d->n_faces);
+    m.Cf.assign(d->Cf, d->Cf + 3 * (size_t)d->n_faces);
+    m.C.assign(d->C, d->C + 3 * (size_t)d->n_cells);
+    m.V.assign(d->V, d->V + d->n_cells);
+    m.w.assign(d->weights, d->weights + d->n_faces);
+    const size_t nb = (size_t)m.nB();
+    if (d->nbr_C) m.nbrC.assign(d->nbr_C, d->nbr_C + 3 * nb); else m.nbrC.assign(3 * nb, 0.0);
+    m.patches.clear();
+    for (int p = 0; p < d->n_patches; ++p) {
+        const RheoPatchDesc& q = d->patches[p];
+        m.patches.push_back(Patch{q.type, q.start, q.size, q.nbr_rank, q.theta_bc, q.tau_bc, -1});
+    }
+    for (int q = 0; q < 6; ++q) m.solved[q] = d->solved_components[q];
+    cs.finalized = false;
+    return 0;
+}
+
+int orc_add_mode(void* h, const RheoModelDesc* d) {
+    Case& cs = *(Case*)h;
+    for (Rank& rk : cs.ranks) {
+        Mode mo;
+        mo.model.d = *d;
+        init_model(mo.model);
+        const size_t n = rk.mesh.nCells, nb = rk.mesh.nB();
+        mo.theta.assign(6 * n, 0.0); mo.thetaOld.assign(6 * n, 0.0); mo.tau.assign(6 * n, 0.0);
+        mo.eigVals.assign(9 * n, 0.0); mo.eigVecs.assign(9 * n, 0.0);
+        for (size_t c = 0; c < n; ++c)
+            for (int q = 0; q < 3; ++q) { mo.eigVals[9 * c + 4 * q] = 1.0; mo.eigVecs[9 * c + 4 * q] = 1.0; }
+        mo.thetaB.assign(6 * nb, 0.0); mo.tauB.assign(6 * nb, 0.0);
+        rk.modes.push_back(std::move(mo));
+    }
+    return 0;
+}
+
+int orc_set_schemes(void* h, const RheoSchemeCtl* c) { ((Case*)h)->ctl = *c; return 0; }
+int orc_set_sort_eig(void* h, int on) { ((Case*)h)->sortEig = on != 0; return 0; }
+
+int orc_set_state(void* h, int rank, int mode, const double* theta, const double* tau, const double* eigvals,
+                  const double* eigvecs, const double* theta_b, const double* tau_b) {
+    Case& cs = *(Case*)h;
+    Rank& rk = cs.ranks[rank];
+    Mode& mo = rk.modes[mode];
+    const size_t n = rk.mesh.nCells, nb = rk.mesh.nB();
+    if (theta) { mo.theta.assign(theta, theta + 6 * n); mo.thetaOld = mo.theta; }
+    if (tau) mo.tau.assign(tau, tau + 6 * n);
+    if (eigvals) mo.eigVals.assign(eigvals, eigvals + 9 * n);
+    if (eigvecs) mo.eigVecs.assign(eigvecs, eigvecs + 9 * n);
+    if (theta_b) mo.thetaB.assign(theta_b, theta_b + 6 * nb);
+    else {
+        for (const Patch& p : rk.mesh.patches)
+            if (p.theta_bc == RHEO_BC_ZERO_GRADIENT && p.type != RHEO_PATCH_EMPTY)
+                for (int f = p.start; f < p.start + p.size; ++f)
+                    for (int q = 0; q < 6; ++q) mo.thetaB[6 * (size_t)(f - rk.mesh.nInt) + q] = mo.theta[6 * (size_t)rk.mesh.own[f] + q];
+    }
+    if (tau_b) mo.tauB.assign(tau_b, tau_b + 6 * nb);
+    else {
+        for (const Patch& p : rk.mesh.patches)
+            if (p.tau_bc == RHEO_BC_ZERO_GRADIENT && p.type != RHEO_PATCH_EMPTY)
+                for (int f = p.start; f < p.start + p.size; ++f)
+                    for (int q = 0; q < 6; ++q) mo.tauB[6 * (size_t)(f - rk.mesh.nInt) + q] = mo.tau[6 * (size_t)rk.mesh.own[f] + q];
+    }
+    return 0;
+}
+
+int orc_set_velocity(void* h, int rank, const double* U, const double* Ub, const double* phi) {
+    Case& cs = *(Case*)h;
+    Rank& rk = cs.ranks[rank];
+    rk.U.assign(U, U + 3 * (size_t)rk.mesh.nCells);
+    rk.Ub.assign(Ub, Ub + 3 * (size_t)rk.mesh.nB());
+    rk.phi.assign(phi, phi + rk.mesh.nFaces);
+    return 0;
+}
+
+int orc_store_old_time(void* h) {
+    Case& cs = *(Case*)h;
+    for (Rank& rk : cs.ranks)
+        for (Mode& mo : rk.modes) mo.thetaOld = mo.theta;
+    return 0;
+}
+
+// multiMode::correct (CE/multiMode/multiMode.C:247-260): modes one after the other
+int orc_step(void* h, double dt, RheoStepStats* stats) {
+    Case& cs = *(Case*)h;
+    if (!cs.finalized) finalize(cs);
+    cs.lastIters = 0;
+    const int nm = (int)cs.ranks[0].modes.size();
+    for (int mi = 0; mi < nm; ++mi) {
+        int rc = correct_mode(cs, mi, dt, stats ? &stats[mi] : nullptr);
+        if (rc) return rc;
+    }
+    return 0;
+}
+int orc_last_iterations(void* h) { return ((Case*)h)->lastIters; }
+
+int orc_get(void* h, int rank, int mode, int field, double* out) {
+    Case& cs = *(Case*)h;
+    Rank& rk = cs.ranks[rank];
+    const dvec* src = nullptr;
+    dvec tot;
+    switch (field) {
+        case RHEO_FIELD_THETA: src = &rk.modes[mode].theta; break;
+        case RHEO_FIELD_TAU: src = &rk.modes[mode].tau; break;
+        case RHEO_FIELD_EIGVALS: src = &rk.modes[mode].eigVals; break;
+        case RHEO_FIELD_EIGVECS: src = &rk.modes[mode].eigVecs; break;
+        case RHEO_FIELD_THETA_B: src = &rk.modes[mode].thetaB; break;
+        case RHEO_FIELD_TAU_B: src = &rk.modes[mode].tauB; break;
+        case RHEO_FIELD_THETA_OLD: src = &rk.modes[mode].thetaOld; break;
+        case RHEO_FIELD_TAU_TOTAL:   // multiMode::tau(), multiMode.C:216-226
+            tot.assign(rk.modes[0].tau.size(), 0.0);
+            for (Mode& mo : rk.modes) for (size_t q = 0; q < tot.size(); ++q) tot[q] += mo.tau[q];
+            src = &tot;
+            break;
+        default: g_err = "orc_get: unknown field"; return 1;
+    }
+    std::copy(src->begin(), src->end(), out);
+    return 0;
+}
+
+// ---- stand-alone pieces for unit tests
+void orc_jacobi(int n, const double* theta6, double* D3, double* V9) {
+    for (int c = 0; c < n; ++c) jacobi_ref(theta6 + 6 * (size_t)c, D3 + 3 * (size_t)c, V9 + 9 * (size_t)c);
+}
+void orc_calc_eig(int n, const double* theta6, double* vals9, double* vecs9, int sortEig) {
+    for (int c = 0; c < n; ++c) calc_eig_cell(theta6 + 6 * (size_t)c, vals9 + 9 * (size_t)c, vecs9 + 9 * (size_t)c, sortEig != 0);
+}
+// Omega and B of decomposeGradU for n cells
+void orc_decompose_gradU(int n, const double* L9, const double* R9, const double* Lam9, double zeta, int ptt, double* omega9, double* B9) {
+    for (int c = 0; c < n; ++c) {
+        T9 L, R, Lam, o, B;
+        std::memcpy(L.v, L9 + 9 * (size_t)c, 72); std::memcpy(R.v, R9 + 9 * (size_t)c, 72); std::memcpy(Lam.v, Lam9 + 9 * (size_t)c, 72);
+        decompose_gradU_cell(L, R, Lam, zeta, ptt != 0, o, B);
+        std::memcpy(omega9 + 9 * (size_t)c, o.v, 72); std::memcpy(B9 + 9 * (size_t)c, B.v, 72);
+    }
+}
+void orc_model_rhs(const RheoModelDesc* d, int n, const double* L9, const double* theta6, const double* R9, const double* Lam9, double* rhs6, double* f) {
+    Model mo;
+    mo.d = *d;
+    init_model(mo);
+    for (int c = 0; c < n; ++c) {
+        T9 L, R, Lam;
+        std::memcpy(L.v, L9 + 9 * (size_t)c, 72); std::memcpy(R.v, R9 + 9 * (size_t)c, 72); std::memcpy(Lam.v, Lam9 + 9 * (size_t)c, 72);
+        double ff = model_rhs_cell(mo, L, theta6 + 6 * (size_t)c, R, Lam, rhs6 + 6 * (size_t)c);
+        if (f) f[c] = ff;
+    }
+}
+void orc_tau(const RheoModelDesc* d, int n, const double* R9, const double* Lam9, const double* f, double* tau6) {
+    Model mo;
+    mo.d = *d;
+    init_model(mo);
+    for (int c = 0; c < n; ++c) {
+        T9 R, Lam;
+        std::memcpy(R.v, R9 + 9 * (size_t)c, 72); std::memcpy(Lam.v, Lam9 + 9 * (size_t)c, 72);
+        tau_cell(mo, R, Lam, f ? f[c] : 0.0, tau6 + 6 * (size_t)c);
+    }
+}
+// Gauss-linear gradient of a scalar cell field on rank 0's mesh with given boundary face values
+int orc_gauss_grad(void* h, int rank, int nc, const double* psi, const double* faceB, double* out) {
+    Case& cs = *(Case*)h;
+    gauss_grad(cs.ranks[rank].mesh, nc, psi, faceB, out);
+    return 0;
+}
+
+}  // extern "C"

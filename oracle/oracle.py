@@ -1,0 +1,149 @@
+"""ctypes front-end of the CPU oracle (oracle/oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs — never by the product package.  Mesh/model/scheme descriptors are the public C structs of
+include/*.h (passed by pointer), so a test feeds the same descriptors to both sides.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = _HERE / "_build" / "liboracle.so"
+_lib = None
+
+
+def build() -> Path:
+    subprocess.run(["make", "-s", "-C", str(_HERE)], check=True)
+    return _LIB
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB.exists():
+            build()
+        L = C.CDLL(str(_LIB))
+        P, I, D = C.c_void_p, C.c_int, C.c_double
+        sig = {
+            "orc_create": (P, [I]), "orc_destroy": (None, [P]), "orc_set_mesh": (I, [P, I, P]),
+            "orc_add_mode": (I, [P, P]), "orc_set_schemes": (I, [P, P]), "orc_set_sort_eig": (I, [P, I]),
+            "orc_set_state": (I, [P, I, I, P, P, P, P, P, P]), "orc_set_velocity": (I, [P, I, P, P, P]),
+            "orc_store_old_time": (I, [P]), "orc_step": (I, [P, D, P]), "orc_last_iterations": (I, [P]),
+            "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
+            "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
+            "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
+            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []),
+        }
+        for n, (r, a) in sig.items():
+            f = getattr(L, n)
+            f.restype, f.argtypes = r, a
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
+
+
+FIELD_WIDTH = {0: 6, 1: 6, 2: 9, 3: 9, 4: 6, 5: 6, 6: 6, 7: 6}
+
+
+class OracleCase:
+    """R sub-domain meshes + modes; step() = one constitutiveEq::correct() of every mode."""
+
+    def __init__(self, mesh_descs, models, schemes, sort_eig=True):
+        L = lib()
+        self._descs = list(mesh_descs)   # keep alive
+        self.n_ranks = len(self._descs)
+        self._h = L.orc_create(self.n_ranks)
+        self.sizes = []
+        for r, d in enumerate(self._descs):
+            if L.orc_set_mesh(self._h, r, C.byref(d)):
+                raise RuntimeError(L.orc_last_error().decode())
+            self.sizes.append((d.n_cells, d.n_faces - d.n_internal_faces))
+        for m in models:
+            L.orc_add_mode(self._h, C.byref(m))
+        self.n_modes = len(models)
+        L.orc_set_schemes(self._h, C.byref(schemes))
+        L.orc_set_sort_eig(self._h, 1 if sort_eig else 0)
+
+    def __del__(self):
+        try:
+            lib().orc_destroy(self._h)
+        except Exception:
+            pass
+
+    def set_state(self, rank, mode, theta=None, tau=None, eigvals=None, eigvecs=None, theta_b=None, tau_b=None):
+        keep = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (theta, tau, eigvals, eigvecs, theta_b, tau_b)]
+        lib().orc_set_state(self._h, rank, mode, *[_p(a) for a in keep])
+
+    def set_velocity(self, rank, U, Ub, phi):
+        keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (U, Ub, phi)]
+        lib().orc_set_velocity(self._h, rank, *[_p(a) for a in keep])
+
+    def store_old_time(self):
+        lib().orc_store_old_time(self._h)
+
+    def step(self, dt, stats=None):
+        rc = lib().orc_step(self._h, float(dt), None if stats is None else C.cast(stats, C.c_void_p))
+        if rc:
+            raise RuntimeError(lib().orc_last_error().decode())
+
+    def last_iterations(self):
+        return lib().orc_last_iterations(self._h)
+
+    def get(self, rank, mode, field):
+        n, nb = self.sizes[rank]
+        rows = nb if field in (4, 5) else n
+        out = np.zeros((rows, FIELD_WIDTH[field]))
+        if lib().orc_get(self._h, rank, mode, field, _p(out)):
+            raise RuntimeError(lib().orc_last_error().decode())
+        return out
+
+
+# ---- stand-alone per-cell pieces --------------------------------------------------------------------
+def jacobi(theta6):
+    t = np.ascontiguousarray(theta6, dtype=np.float64).reshape(-1, 6)
+    D = np.zeros((len(t), 3)); V = np.zeros((len(t), 9))
+    lib().orc_jacobi(len(t), _p(t), _p(D), _p(V))
+    return D, V.reshape(-1, 3, 3)
+
+
+def calc_eig(theta6, sort_eig=True):
+    t = np.ascontiguousarray(theta6, dtype=np.float64).reshape(-1, 6)
+    vals = np.zeros((len(t), 9)); vecs = np.zeros((len(t), 9))
+    lib().orc_calc_eig(len(t), _p(t), _p(vals), _p(vecs), 1 if sort_eig else 0)
+    return vals, vecs
+
+
+def decompose_gradU(L9, R9, Lam9, zeta=0.0, ptt=False):
+    L9 = np.ascontiguousarray(L9, dtype=np.float64).reshape(-1, 9)
+    R9 = np.ascontiguousarray(R9, dtype=np.float64).reshape(-1, 9)
+    Lam9 = np.ascontiguousarray(Lam9, dtype=np.float64).reshape(-1, 9)
+    om = np.zeros_like(L9); B = np.zeros_like(L9)
+    lib().orc_decompose_gradU(len(L9), _p(L9), _p(R9), _p(Lam9), float(zeta), 1 if ptt else 0, _p(om), _p(B))
+    return om, B
+
+
+def model_rhs(model, L9, theta6, R9, Lam9):
+    L9 = np.ascontiguousarray(L9, dtype=np.float64).reshape(-1, 9)
+    th = np.ascontiguousarray(theta6, dtype=np.float64).reshape(-1, 6)
+    R9 = np.ascontiguousarray(R9, dtype=np.float64).reshape(-1, 9)
+    Lam9 = np.ascontiguousarray(Lam9, dtype=np.float64).reshape(-1, 9)
+    rhs = np.zeros_like(th); f = np.zeros(len(th))
+    lib().orc_model_rhs(C.byref(model), len(th), _p(L9), _p(th), _p(R9), _p(Lam9), _p(rhs), _p(f))
+    return rhs, f
+
+
+def tau_from_eig(model, R9, Lam9, f=None):
+    R9 = np.ascontiguousarray(R9, dtype=np.float64).reshape(-1, 9)
+    Lam9 = np.ascontiguousarray(Lam9, dtype=np.float64).reshape(-1, 9)
+    tau = np.zeros((len(R9), 6))
+    ff = None if f is None else np.ascontiguousarray(f, dtype=np.float64)
+    lib().orc_tau(C.byref(model), len(R9), _p(R9), _p(Lam9), _p(ff), _p(tau))
+    return tau

@@ -1,0 +1,139 @@
+"""ctypes mirror of include/rheo_mesh.h and include/rheo_gpu.h, and the loader of librheo_b200.so.
+
+The product path fails loudly: there is no CPU fallback — if the shared library (or, for compute
+calls, a CUDA device) is missing, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_LIB_PATH = Path(__file__).resolve().parent / "librheo_b200.so"
+
+# ---- constants (keep in sync with include/*.h) ---------------------------------------------------
+PATCH_PATCH, PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2, 3
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSOR = 0, 1, 2, 3, 4
+MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG = 0, 1, 2, 3
+PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
+LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}
+DDT_EULER = 0
+SOLVER = {"PBiCGStab": 0, "PBiCG": 1}
+FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD = range(8)
+FLOW_CONTRACTION_2D, FLOW_VORTEX, FLOW_CONTRACTION_3D = 0, 1, 2
+
+MODEL_NAMES = {
+    "Oldroyd-BLog": MODEL_OLDROYD_B_LOG,
+    "GiesekusLog": MODEL_GIESEKUS_LOG,
+    "PTTLog": MODEL_PTT_LOG,
+    "FENE-PLog": MODEL_FENE_P_LOG,
+}
+
+
+class RheoPatchDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("start", C.c_int32), ("size", C.c_int32), ("nbr_rank", C.c_int32),
+                ("theta_bc", C.c_int32), ("tau_bc", C.c_int32)]
+
+
+class RheoMeshDesc(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("n_faces", C.c_int32), ("n_internal_faces", C.c_int32), ("n_patches", C.c_int32),
+                ("owner", C.POINTER(C.c_int32)), ("neighbour", C.POINTER(C.c_int32)),
+                ("Sf", C.POINTER(C.c_double)), ("Cf", C.POINTER(C.c_double)), ("C", C.POINTER(C.c_double)),
+                ("V", C.POINTER(C.c_double)), ("weights", C.POINTER(C.c_double)), ("nbr_C", C.POINTER(C.c_double)),
+                ("patches", C.POINTER(RheoPatchDesc)), ("solved_components", C.c_int32 * 6)]
+
+
+class RheoPatchRule(C.Structure):
+    _fields_ = [("patch", C.c_int32), ("lo", C.c_double * 3), ("hi", C.c_double * 3)]
+
+
+class RheoPatchSpec(C.Structure):
+    _fields_ = [("type", C.c_int32), ("theta_bc", C.c_int32), ("tau_bc", C.c_int32)]
+
+
+class RheoSynthSpec(C.Structure):
+    _fields_ = [("flow", C.c_int32), ("amplitude", C.c_double), ("h_up", C.c_double), ("h_down", C.c_double),
+                ("x_ramp", C.c_double), ("theta_amp", C.c_double), ("noise", C.c_double), ("seed", C.c_uint64)]
+
+
+class RheoModelDesc(C.Structure):
+    _fields_ = [("model", C.c_int32), ("rho", C.c_double), ("etaS", C.c_double), ("etaP", C.c_double),
+                ("lambda_", C.c_double), ("alpha", C.c_double), ("epsilon", C.c_double), ("zeta", C.c_double),
+                ("ptt_function", C.c_int32), ("ml_alpha", C.c_double), ("ml_beta", C.c_double), ("ml_rtol", C.c_double),
+                ("ml_max_iter", C.c_int32), ("L2", C.c_double)]
+
+
+class RheoSchemeCtl(C.Structure):
+    _fields_ = [("limiter", C.c_int32), ("ddt", C.c_int32), ("solver", C.c_int32), ("tolerance", C.c_double),
+                ("rel_tol", C.c_double), ("min_iter", C.c_int32), ("max_iter", C.c_int32), ("relax", C.c_double)]
+
+
+class RheoStepStats(C.Structure):
+    _fields_ = [("initial_residual", C.c_double * 6), ("final_residual", C.c_double * 6),
+                ("n_iterations", C.c_int32 * 6), ("converged", C.c_int32 * 6)]
+
+
+# every symbol include/*.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+_I = C.c_int32
+_D = C.c_double
+MESH_SYMBOLS = {
+    "rheo_mesh_tensor_grid": (_P, [_I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _D, _I]),
+    "rheo_mesh_tensor_grid_part": (_P, [_I, _I, _I, _P, _P, _P, _I, _P, _I, _P, _I, _P, _I, _D, _I, _I, _I, _I, _I]),
+    "rheo_mesh_from_desc": (_P, [_P]),
+    "rheo_mesh_free": (None, [_P]),
+    "rheo_mesh_desc": (C.c_int, [_P, _P]),
+    "rheo_mesh_n_boundary_faces": (C.c_int, [_P]),
+    "rheo_mesh_simple_decomp": (C.c_int, [_P, _I, _I, _I, _D, _P]),
+    "rheo_mesh_decompose": (_P, [_P, _P, _I, _I]),
+    "rheo_mesh_proc_addressing": (C.c_int, [_P, _P, _P]),
+    "rheo_mesh_colour_renumber": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_synth_fields": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "rheo_mesh_max_courant_rate": (_D, [_P, _P]),
+    "rheo_mesh_last_error": (C.c_char_p, []),
+}
+GPU_SYMBOLS = {
+    "rheo_gpu_device_count": (C.c_int, []),
+    "rheo_gpu_create": (C.c_int, [_P, _P, _I, _P, _I, _P]),
+    "rheo_gpu_destroy": (None, [_P]),
+    "rheo_gpu_nccl_unique_id": (C.c_int, [_P]),
+    "rheo_gpu_comm_init": (C.c_int, [_P, _I, _I, _P]),
+    "rheo_gpu_upload_state": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P]),
+    "rheo_gpu_upload_velocity": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_gpu_store_old_time": (C.c_int, [_P]),
+    "rheo_gpu_step": (C.c_int, [_P, _D, _P]),
+    "rheo_gpu_download": (C.c_int, [_P, _I, _I, _P]),
+    "rheo_gpu_correct": (C.c_int, [_P, _P, _P, _P, _D, _I, _P, _P, _P]),
+    "rheo_gpu_get_renumbering": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_gpu_get_ell": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_gpu_launch_count": (C.c_int64, [_P]),
+    "rheo_gpu_last_iterations": (C.c_int, [_P]),
+    "rheo_gpu_set_phase_timing": (C.c_int, [_P, _I]),
+    "rheo_gpu_get_phase_times": (C.c_int, [_P, _P]),
+    "rheo_gpu_stream": (C.c_int, [_P, _P]),
+    "rheo_gpu_synchronize": (C.c_int, [_P]),
+    "rheo_gpu_eig_exp": (C.c_int, [_I, _I, _P, _P, _P]),
+    "rheo_gpu_last_error": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load librheo_b200.so (building is the job of __graft_entry__.build / rheotool_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: run `python -m rheotool_b200.build` (or __graft_entry__.build()). "
+                "There is no CPU fallback for the stress step.")
+        L = C.CDLL(str(_LIB_PATH))
+        for name, (res, args) in {**MESH_SYMBOLS, **GPU_SYMBOLS}.items():
+            fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def lib_path() -> Path:
+    return _LIB_PATH

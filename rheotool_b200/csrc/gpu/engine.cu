@@ -1,0 +1,813 @@
+// engine.cu — device-resident stress step behind the C-ABI of include/rheo_gpu.h.
+//
+// One RheoGpu == one constitutiveEq object (or a multiMode set) on one GPU.  Layout in HBM: FP64 SoA
+// planes of stride NP, cells renumbered by colour (greedy multi-colouring, then colour-major order)
+// so that the DILU forward/backward substitutions of EXT-OF9 DILUPreconditioner become one fully
+// parallel kernel per colour; faces re-sorted to upper-triangular order of the new numbering;
+// connectivity as a slot-major ELL table; processor-patch neighbours appended as ghost cells
+// [N, N+H) that the halo exchange (NCCL send/recv) fills.  See DESIGN.md.
+//
+// There is no CPU fallback: every compute entry point needs a CUDA device and fails otherwise.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "rheo_gpu.h"
+
+using namespace rk;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            g_err = std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"; \
+            return 1;                                                                                \
+        }                                                                                            \
+    } while (0)
+
+inline int cdiv(long a, int b) { return (int)((a + b - 1) / b); }
+inline int round_up(long a, int b) { return (int)(((a + b - 1) / b) * b); }
+
+// ---------------------------------------------------------------- NCCL through dlopen (no link-time dependency)
+typedef struct { char internal[128]; } NcclId;
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) return false;
+#define LD(f) f = (decltype(f))dlsym(lib, "nccl" #f); if (!f) return false;
+        LD(GetUniqueId) LD(CommInitRank) LD(CommDestroy) LD(Send) LD(Recv) LD(AllReduce) LD(GroupStart) LD(GroupEnd) LD(GetErrorString)
+#undef LD
+        return true;
+    }
+} g_nccl;
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t b) {
+        bytes = b;
+        if (b == 0) { p = nullptr; return 0; }
+        CK(cudaMalloc(&p, b));
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct ModeDev {
+    RheoModelDesc desc;
+    ModelParams mp;
+    DevBuf theta, thetaOld, tau, lam, R, fFene, bsrc, thetaB, tauB, gammaVals;
+};
+
+struct HaloSeg { int nbrRank, h0, len; };
+
+}  // namespace
+
+struct RheoGpu {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    RheoSchemeCtl ctl;
+    Limiter lim;
+    // sizes
+    int N = 0, H = 0, NT = 0, NS = 0, NP = 0, K = 0, nInt = 0, nF = 0, nB = 0;
+    int nComp = 6;                 // solved components
+    int comps[6];                  // indices of solved components
+    int nColours = 0;
+    std::vector<int> colourStart;
+    long nGlobalCells = 0;
+    // host-side maps
+    std::vector<int> perm;         // perm[new] = old
+    std::vector<int> faceOld;      // device face -> (old face+1), negative if flipped
+    std::vector<int> h_nbr, h_fidx;
+    std::vector<RheoPatchDesc> patches;
+    std::vector<HaloSeg> segs;
+    // device mesh
+    DevBuf d_perm, d_faceOld, d_nbr, d_nbrA, d_fidx, d_Sf, d_w, d_C, d_V, d_rV, d_bcell, d_bkind, d_bthetaBC, d_btauBC, d_CfB;
+    DevBuf d_haloCell, d_segStart, d_segLen, d_send, d_recv;
+    MeshView mv;
+    // fields
+    DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_grad, d_stage, d_tmpB;
+    std::vector<ModeDev> modes;
+    // Krylov
+    DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ctl, d_partials, d_red, d_counter;
+    int* h_nActive = nullptr;      // pinned
+    KrylovCtl* h_ctl = nullptr;    // pinned
+    // comm
+    void* comm = nullptr;
+    int rank = 0, nRanks = 1;
+    // stats
+    long launches = 0;
+    int lastIters = 0;
+    bool timing = false;
+    cudaEvent_t ev[8];
+    double phaseMs[7] = {0, 0, 0, 0, 0, 0, 0};
+    size_t stageBytes = 0;
+};
+
+namespace {
+
+#define LAUNCH(h, kern, grid, block, ...)                         \
+    do {                                                          \
+        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);   \
+        (h)->launches++;                                          \
+    } while (0)
+
+Limiter make_limiter(int lim) {
+    Limiter L{0, 1, 1, 1, 0, 0, 0, 1, 1};
+    switch (lim) {   // gaussDefCmpwConvectionScheme/limiters.H:48-98
+        case RHEO_LIMITER_CUBISTA: L = {1, 7. / 4., 3. / 4., 1. / 4., 0., 3. / 8., 3. / 4., 3. / 8., 3. / 4.}; break;
+        case RHEO_LIMITER_MINMOD: L = {1, 1.5, .5, .5, 0., .5, .5, .5, 1.}; break;
+        case RHEO_LIMITER_SMART: L = {1, 3., 3. / 4., 0., 0., 3. / 8., 1., 1. / 6., 5. / 6.}; break;
+        case RHEO_LIMITER_WACEB: L = {1, 2., 3. / 4., 0., 0., 3. / 8., 1., 3. / 10., 5. / 6.}; break;
+        case RHEO_LIMITER_SUPERBEE: L = {1, 0.5, 1.5, 0., 0.5, 0., 1., 1. / 2., 2. / 3.}; break;
+        default: break;
+    }
+    return L;
+}
+
+// greedy colouring + colour-major permutation (the integer contract; restated independently in
+// oracle/renumber_ref.py and compared bit-exactly by the tests)
+int colour_renumber(int n, int nInt, const int32_t* own, const int32_t* nei, std::vector<int>& perm, std::vector<int>& colourStart) {
+    std::vector<int> start((size_t)n + 1, 0);
+    for (int f = 0; f < nInt; ++f) { start[own[f] + 1]++; start[nei[f] + 1]++; }
+    for (int c = 0; c < n; ++c) start[c + 1] += start[c];
+    std::vector<int> adj((size_t)start[n]), fill(start.begin(), start.end() - 1);
+    for (int f = 0; f < nInt; ++f) { adj[fill[own[f]]++] = nei[f]; adj[fill[nei[f]]++] = own[f]; }
+    std::vector<int> colour(n);
+    int nCol = 0;
+    for (int c = 0; c < n; ++c) {
+        uint64_t used = 0;
+        for (int q = start[c]; q < start[c + 1]; ++q)
+            if (adj[q] < c) used |= (uint64_t)1 << colour[adj[q]];
+        int col = 0;
+        while (used & ((uint64_t)1 << col)) ++col;
+        if (col >= 63) return -1;
+        colour[c] = col;
+        nCol = std::max(nCol, col + 1);
+    }
+    colourStart.assign(nCol + 1, 0);
+    for (int c = 0; c < n; ++c) colourStart[colour[c] + 1]++;
+    for (int q = 0; q < nCol; ++q) colourStart[q + 1] += colourStart[q];
+    std::vector<int> pos(colourStart.begin(), colourStart.end() - 1);
+    perm.resize(n);
+    for (int c = 0; c < n; ++c) perm[pos[colour[c]]++] = c;
+    return nCol;
+}
+
+template <class T> int upload(DevBuf& b, const std::vector<T>& v) {
+    if (b.alloc(v.size() * sizeof(T))) return 1;
+    if (!v.empty()) CK(cudaMemcpy(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
+    const int N = d->n_cells, nF = d->n_faces, nInt = d->n_internal_faces, nB = nF - nInt;
+    h->N = N; h->nF = nF; h->nInt = nInt; h->nB = nB;
+    h->patches.assign(d->patches, d->patches + d->n_patches);
+    h->nComp = 0;
+    for (int q = 0; q < 6; ++q) if (d->solved_components[q]) h->comps[h->nComp++] = q;
+    if (h->nComp != 6 && h->nComp != 4) return fail("rheo_gpu_create: solved_components must select 6 (3-D) or 4 (2-D) components");
+
+    // ---- renumbering
+    h->nColours = colour_renumber(N, nInt, d->owner, d->neighbour, h->perm, h->colourStart);
+    if (h->nColours < 1) return fail("rheo_gpu_create: colouring failed (more than 63 colours)");
+    std::vector<int> iperm(N);
+    for (int c = 0; c < N; ++c) iperm[h->perm[c]] = c;
+
+    // ---- internal faces in upper-triangular order of the new numbering (bucket by new owner)
+    std::vector<int> fo(nInt), fn(nInt);
+    std::vector<char> flip(nInt);
+    std::vector<int> cnt((size_t)N + 1, 0);
+    for (int f = 0; f < nInt; ++f) {
+        int o = iperm[d->owner[f]], n = iperm[d->neighbour[f]];
+        flip[f] = o > n;
+        if (o > n) std::swap(o, n);
+        fo[f] = o; fn[f] = n;
+        cnt[o + 1]++;
+    }
+    for (int c = 0; c < N; ++c) cnt[c + 1] += cnt[c];
+    std::vector<int> order(nInt), pos(cnt.begin(), cnt.end() - 1);
+    for (int f = 0; f < nInt; ++f) order[pos[fo[f]]++] = f;
+    for (int c = 0; c < N; ++c) std::sort(order.begin() + cnt[c], order.begin() + cnt[c + 1], [&](int a, int b) { return fn[a] < fn[b]; });
+    h->faceOld.resize(nF);
+    std::vector<int> newOwn(nF), newNei(nInt);
+    for (int q = 0; q < nInt; ++q) {
+        const int f = order[q];
+        h->faceOld[q] = flip[f] ? -(f + 1) : (f + 1);
+        newOwn[q] = fo[f]; newNei[q] = fn[f];
+    }
+    for (int f = nInt; f < nF; ++f) { h->faceOld[f] = f + 1; newOwn[f] = iperm[d->owner[f]]; }
+
+    // ---- ghosts: one per processor face, in patch order
+    std::vector<int> ghostOfB(nB, -1), haloCell, segStart, segLen;
+    std::vector<int> bkind(nB, RHEO_PATCH_EMPTY), bthetaBC(nB, RHEO_BC_EMPTY), btauBC(nB, RHEO_BC_EMPTY), bcell(nB);
+    int H = 0;
+    for (const RheoPatchDesc& p : h->patches) {
+        if (p.start < nInt || p.start + p.size > nF) return fail("rheo_gpu_create: patch range outside the boundary faces");
+        if (p.type == RHEO_PATCH_PROCESSOR) h->segs.push_back({p.nbr_rank, H, p.size});
+        for (int f = p.start; f < p.start + p.size; ++f) {
+            const int b = f - nInt;
+            bkind[b] = p.type; bthetaBC[b] = p.theta_bc; btauBC[b] = p.tau_bc;
+            if (p.type == RHEO_PATCH_PROCESSOR) {
+                ghostOfB[b] = H;
+                haloCell.push_back(newOwn[f]);
+                segStart.push_back(h->segs.back().h0);
+                segLen.push_back(p.size);
+                ++H;
+            } else if (p.type != RHEO_PATCH_EMPTY) {
+                if (p.theta_bc != RHEO_BC_FIXED_VALUE && p.theta_bc != RHEO_BC_ZERO_GRADIENT)
+                    return fail("rheo_gpu_create: theta BC must be fixedValue or zeroGradient on physical patches");
+                if (p.tau_bc != RHEO_BC_FIXED_VALUE && p.tau_bc != RHEO_BC_ZERO_GRADIENT && p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION)
+                    return fail("rheo_gpu_create: tau BC must be fixedValue, zeroGradient or linearExtrapolation on physical patches");
+            }
+        }
+    }
+    for (int b = 0; b < nB; ++b) bcell[b] = newOwn[nInt + b];
+    h->H = H; h->NT = N + H;
+    h->NS = round_up(N, 32);
+    h->NP = round_up(N + H, 32);
+
+    // ---- ELL (slot order: internal faces by ascending new neighbour, then boundary faces in face order)
+    std::vector<int> deg(N, 0);
+    for (int q = 0; q < nInt; ++q) { deg[newOwn[q]]++; deg[newNei[q]]++; }
+    for (int b = 0; b < nB; ++b) if (bkind[b] != RHEO_PATCH_EMPTY) deg[bcell[b]]++;
+    int K = 0;
+    for (int c = 0; c < N; ++c) K = std::max(K, deg[c]);
+    h->K = K;
+    const size_t ell = (size_t)K * h->NS;
+    h->h_nbr.assign(ell, -1);
+    h->h_fidx.assign(ell, 0);
+    std::vector<int> nbrA(ell);
+    std::fill(deg.begin(), deg.end(), 0);
+    for (int q = 0; q < nInt; ++q) {
+        const int o = newOwn[q], n = newNei[q];
+        h->h_nbr[(size_t)deg[o] * h->NS + o] = n; h->h_fidx[(size_t)deg[o] * h->NS + o] = q; deg[o]++;
+        h->h_nbr[(size_t)deg[n] * h->NS + n] = o; h->h_fidx[(size_t)deg[n] * h->NS + n] = ~q; deg[n]++;
+    }
+    for (int b = 0; b < nB; ++b) {
+        if (bkind[b] == RHEO_PATCH_EMPTY) continue;
+        const int c = bcell[b];
+        h->h_nbr[(size_t)deg[c] * h->NS + c] = (bkind[b] == RHEO_PATCH_PROCESSOR) ? N + ghostOfB[b] : -(b + 2);
+        h->h_fidx[(size_t)deg[c] * h->NS + c] = nInt + b;
+        deg[c]++;
+    }
+    for (int s = 0; s < K; ++s)
+        for (int c = 0; c < h->NS; ++c) {
+            const int v = h->h_nbr[(size_t)s * h->NS + c];
+            nbrA[(size_t)s * h->NS + c] = (v >= 0) ? v : std::min(c, N - 1);
+        }
+
+    // ---- geometry in device order
+    std::vector<double> Sf(3 * (size_t)nF), w(nF), C(3 * (size_t)h->NP, 0.0), V(N), rV(N), CfB(3 * (size_t)nB);
+    for (int q = 0; q < nF; ++q) {
+        const int o = h->faceOld[q];
+        const int f = (o > 0 ? o : -o) - 1;
+        const double sg = o > 0 ? 1.0 : -1.0;
+        for (int e = 0; e < 3; ++e) Sf[(size_t)e * nF + q] = sg * d->Sf[3 * (size_t)f + e];
+        w[q] = o > 0 ? d->weights[f] : 1.0 - d->weights[f];
+    }
+    for (int c = 0; c < N; ++c) {
+        const int o = h->perm[c];
+        for (int e = 0; e < 3; ++e) C[(size_t)e * h->NP + c] = d->C[3 * (size_t)o + e];
+        V[c] = d->V[o];
+        rV[c] = 1.0 / d->V[o];
+    }
+    for (int b = 0; b < nB; ++b) {
+        for (int e = 0; e < 3; ++e) CfB[(size_t)e * nB + b] = d->Cf[3 * (size_t)(nInt + b) + e];
+        if (ghostOfB[b] >= 0) {
+            if (!d->nbr_C) return fail("rheo_gpu_create: processor patches need nbr_C");
+            for (int e = 0; e < 3; ++e) C[(size_t)e * h->NP + N + ghostOfB[b]] = d->nbr_C[3 * (size_t)b + e];
+        }
+    }
+    if (upload(h->d_perm, h->perm) || upload(h->d_faceOld, h->faceOld) || upload(h->d_nbr, h->h_nbr) || upload(h->d_nbrA, nbrA) ||
+        upload(h->d_fidx, h->h_fidx) || upload(h->d_Sf, Sf) || upload(h->d_w, w) || upload(h->d_C, C) || upload(h->d_V, V) ||
+        upload(h->d_rV, rV) || upload(h->d_bcell, bcell) || upload(h->d_bkind, bkind) || upload(h->d_bthetaBC, bthetaBC) ||
+        upload(h->d_btauBC, btauBC) || upload(h->d_CfB, CfB) || upload(h->d_haloCell, haloCell) || upload(h->d_segStart, segStart) ||
+        upload(h->d_segLen, segLen))
+        return 1;
+    MeshView& m = h->mv;
+    m.N = N; m.H = H; m.NT = h->NT; m.NS = h->NS; m.NP = h->NP; m.K = K; m.nInt = nInt; m.nF = nF; m.nB = nB;
+    m.nbr = h->d_nbr.as<int>(); m.nbrA = h->d_nbrA.as<int>(); m.fidx = h->d_fidx.as<int>();
+    m.Sf = h->d_Sf.as<double>(); m.w = h->d_w.as<double>(); m.C = h->d_C.as<double>(); m.V = h->d_V.as<double>(); m.rV = h->d_rV.as<double>();
+    m.bcell = h->d_bcell.as<int>(); m.bkind = h->d_bkind.as<int>(); m.bthetaBC = h->d_bthetaBC.as<int>(); m.btauBC = h->d_btauBC.as<int>();
+    m.CfB = h->d_CfB.as<double>();
+    h->nGlobalCells = N;
+    return 0;
+}
+
+int zero(RheoGpu* h, DevBuf& b) {
+    if (b.bytes) CK(cudaMemsetAsync(b.p, 0, b.bytes, h->stream));
+    return 0;
+}
+
+int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
+    const size_t NP = h->NP, nB = std::max(h->nB, 1);
+    const size_t d8 = sizeof(double);
+    if (h->d_U.alloc(3 * NP * d8) || h->d_Ub.alloc(3 * nB * d8) || h->d_phi.alloc((size_t)std::max(h->nF, 1) * d8) ||
+        h->d_diag.alloc(NP * d8) || h->d_rD.alloc(NP * d8) || h->d_Fs.alloc((size_t)h->K * h->NS * d8) || h->d_grad.alloc(18 * NP * d8) ||
+        h->d_tmpB.alloc(6 * nB * d8))
+        return 1;
+    zero(h, h->d_U); zero(h, h->d_Ub); zero(h, h->d_phi); zero(h, h->d_grad); zero(h, h->d_Fs); zero(h, h->d_diag); zero(h, h->d_rD);
+    h->stageBytes = std::max<size_t>(9 * (size_t)h->N, std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;
+    if (h->d_stage.alloc(h->stageBytes)) return 1;
+    h->modes.resize(nModes);
+    for (int mi = 0; mi < nModes; ++mi) {
+        ModeDev& md = h->modes[mi];
+        md.desc = modes[mi];
+        const RheoModelDesc& q = modes[mi];
+        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_FENE_P_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
+        if (!(q.lambda > 0)) return fail("rheo_gpu_create: lambda must be positive");
+        ModelParams& mp = md.mp;
+        mp.model = q.model; mp.ptt_function = q.ptt_function; mp.ml_max_iter = q.ml_max_iter;
+        mp.etaP = q.etaP; mp.lambda = q.lambda; mp.alpha = q.alpha; mp.epsilon = q.epsilon; mp.zeta = q.zeta; mp.L2 = q.L2;
+        mp.ml_rtol = q.ml_rtol; mp.gamma_beta = 1.0; mp.gamma_vals = nullptr;
+        if (q.model == RHEO_MODEL_PTT_LOG && q.ptt_function == RHEO_PTT_GENERALIZED) {   // PTTLog.C:143-170
+            if (q.ml_alpha <= 0 || q.ml_beta <= 0) return fail("Both alpha and beta should be positive values for the Mittag-Leffler function to converge.");
+            std::vector<double> gv{std::tgamma(q.ml_beta)};
+            int k = 0;
+            while (k < q.ml_max_iter && gv.back() < 1e+100) { gv.push_back(std::tgamma(q.ml_alpha * k + q.ml_beta)); k++; }
+            mp.ml_max_iter = k;
+            mp.gamma_beta = gv[0];
+            if (upload(md.gammaVals, gv)) return 1;
+            mp.gamma_vals = md.gammaVals.as<double>();
+        }
+        if (md.theta.alloc(6 * NP * d8) || md.thetaOld.alloc(6 * NP * d8) || md.tau.alloc(6 * NP * d8) || md.lam.alloc(3 * NP * d8) ||
+            md.R.alloc(9 * NP * d8) || md.fFene.alloc(NP * d8) || md.bsrc.alloc(6 * NP * d8) || md.thetaB.alloc(6 * nB * d8) || md.tauB.alloc(6 * nB * d8))
+            return 1;
+        zero(h, md.theta); zero(h, md.thetaOld); zero(h, md.tau); zero(h, md.fFene); zero(h, md.bsrc); zero(h, md.thetaB); zero(h, md.tauB); zero(h, md.R);
+        // READ_IF_PRESENT defaults: eigVals = eigVecs = I (Oldroyd_BLog.C:76-113)
+        LAUNCH(h, k_fill, cdiv(3 * NP, BLOCK), BLOCK, 3 * NP, md.lam.as<double>(), 1.0);
+        for (int q9 : {0, 4, 8}) LAUNCH(h, k_fill, cdiv(NP, BLOCK), BLOCK, NP, md.R.as<double>() + (size_t)q9 * NP, 1.0);
+    }
+    const int nrhsMax = std::min(MAX_RHS, nModes * h->nComp);
+    const size_t kv = (size_t)nrhsMax * NP * d8;
+    if (h->d_r.alloc(kv) || h->d_r0.alloc(kv) || h->d_p.alloc(kv) || h->d_y.alloc(kv) || h->d_v.alloc(kv) || h->d_s.alloc(kv) ||
+        h->d_z.alloc(kv) || h->d_t.alloc(kv))
+        return 1;
+    for (DevBuf* b : {&h->d_r, &h->d_r0, &h->d_p, &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t}) zero(h, *b);
+    const int nBlocks = cdiv(h->N, BLOCK);
+    if (h->d_ctl.alloc(MAX_RHS * sizeof(KrylovCtl)) || h->d_partials.alloc((size_t)nBlocks * MAX_RED * d8) || h->d_red.alloc(4 * MAX_RED * d8) ||
+        h->d_counter.alloc(sizeof(unsigned)))
+        return 1;
+    zero(h, h->d_counter); zero(h, h->d_red); zero(h, h->d_ctl);
+    CK(cudaHostAlloc((void**)&h->h_nActive, sizeof(int), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&h->h_ctl, MAX_RHS * sizeof(KrylovCtl), cudaHostAllocDefault));
+    const size_t hb = (size_t)std::max(h->H, 1) * MAX_RHS * d8;
+    if (h->d_send.alloc(hb) || h->d_recv.alloc(hb)) return 1;
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// ---------------------------------------------------------------- halo exchange of a set of planes
+int halo_exchange(RheoGpu* h, const PlaneList& pl) {
+    if (h->H == 0) return 0;
+    if (!h->comm) return fail("mesh has processor patches but rheo_gpu_comm_init was not called");
+    LAUNCH(h, k_halo_pack, cdiv(h->H, BLOCK), BLOCK, h->H, pl, h->d_haloCell.as<int>(), h->d_segStart.as<int>(), h->d_segLen.as<int>(), h->d_send.as<double>());
+    g_nccl.GroupStart();
+    for (const HaloSeg& s : h->segs) {
+        const size_t off = (size_t)pl.n * s.h0, cnt = (size_t)pl.n * s.len;
+        int rc = g_nccl.Send(h->d_send.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
+        if (!rc) rc = g_nccl.Recv(h->d_recv.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
+        if (rc) { g_nccl.GroupEnd(); return fail(std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(rc)); }
+    }
+    int rc = g_nccl.GroupEnd();
+    if (rc) return fail(std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc));
+    LAUNCH(h, k_halo_unpack, cdiv(h->H, BLOCK), BLOCK, h->H, h->N, pl, h->d_segStart.as<int>(), h->d_segLen.as<int>(), h->d_recv.as<double>());
+    return 0;
+}
+int halo_planes(RheoGpu* h, double* base, int nPlanes) {
+    for (int p0 = 0; p0 < nPlanes; p0 += MAX_RHS) {
+        PlaneList pl;
+        pl.n = std::min(MAX_RHS, nPlanes - p0);
+        for (int p = 0; p < pl.n; ++p) pl.p[p] = base + (size_t)(p0 + p) * h->NP;
+        if (halo_exchange(h, pl)) return 1;
+    }
+    return 0;
+}
+int all_reduce(RheoGpu* h, double* buf, int n) {
+    if (h->nRanks <= 1) return 0;
+    int rc = g_nccl.AllReduce(buf, buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+    if (rc) return fail(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+    return 0;
+}
+
+// ---------------------------------------------------------------- batched PBiCGStab + colour-parallel DILU
+template <int CH>
+int precondition(RheoGpu* h, int nrhs, const double* rIn, double* w) {
+    const KrylovCtl* ctl = h->d_ctl.as<KrylovCtl>();
+    const int nc = h->nColours;
+    for (int k = 0; k < nc; ++k) {
+        const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
+        if (c1 > c0) LAUNCH(h, (k_sweep_fwd<CH>), cdiv(c1 - c0, BLOCK), BLOCK, h->mv, c0, c1, nrhs, ctl, 0, h->d_rD.as<double>(), h->d_Fs.as<double>(), rIn, w);
+    }
+    for (int k = nc - 2; k >= 0; --k) {
+        const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
+        if (c1 > c0) LAUNCH(h, (k_sweep_bwd<CH>), cdiv(c1 - c0, BLOCK), BLOCK, h->mv, c0, c1, nrhs, ctl, 0, h->d_rD.as<double>(), h->d_Fs.as<double>(), w);
+    }
+    return 0;
+}
+
+template <int CH>
+int solve_batch(RheoGpu* h, const RhsPtrs& rp, int* itersOut) {
+    const int nrhs = rp.n, N = h->N, NP = h->NP;
+    const int grid = cdiv(N, BLOCK);
+    KrylovCtl* ctl = h->d_ctl.as<KrylovCtl>();
+    double* part = h->d_partials.as<double>();
+    double* red = h->d_red.as<double>();
+    double *redA = red, *redB = red + MAX_RED, *redC = red + 2 * MAX_RED, *redD = red + 3 * MAX_RED;
+    unsigned* counter = h->d_counter.as<unsigned>();
+    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *p = h->d_p.as<double>(), *y = h->d_y.as<double>(), *v = h->d_v.as<double>(),
+           *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
+    const SolveCtl sc{h->ctl.tolerance, h->ctl.rel_tol, h->ctl.min_iter, h->ctl.max_iter};
+    const double* diag = h->d_diag.as<double>();
+    const double* Fs = h->d_Fs.as<double>();
+
+    // psi halo, gAverage(psi), initial residual + normFactor
+    {
+        PlaneList pl; pl.n = nrhs;
+        for (int q = 0; q < nrhs; ++q) pl.p[q] = rp.psi[q];
+        if (halo_exchange(h, pl)) return 1;
+    }
+    LAUNCH(h, (k_sum_psi<CH>), grid, BLOCK, N, rp, part, redA, counter);
+    if (all_reduce(h, redA, nrhs)) return 1;
+    LAUNCH(h, (k_krylov_init<CH>), grid, BLOCK, h->mv, rp, diag, Fs, redA, (double)h->nGlobalCells, r, r0, part, redB, counter);
+    if (all_reduce(h, redB, 3 * nrhs)) return 1;
+    LAUNCH(h, k_ctl_init, 1, 32, nrhs, ctl, redB, sc, h->h_nActive);
+    CK(cudaStreamSynchronize(h->stream));
+    int iters = 0;
+    while (*h->h_nActive > 0) {
+        LAUNCH(h, (k_update_p<CH>), grid, BLOCK, N, NP, nrhs, ctl, r, v, p);
+        if (precondition<CH>(h, nrhs, p, y)) return 1;
+        if (halo_planes(h, y, nrhs)) return 1;
+        LAUNCH(h, (k_spmv_dot<CH, 0>), grid, BLOCK, h->mv, nrhs, ctl, diag, Fs, y, v, r0, part, redA, counter);
+        if (all_reduce(h, redA, nrhs)) return 1;
+        LAUNCH(h, (k_make_s<CH>), grid, BLOCK, N, NP, nrhs, ctl, redA, r, v, sv, part, redB, counter);
+        if (all_reduce(h, redB, nrhs)) return 1;
+        LAUNCH(h, k_ctl_half, 1, 32, nrhs, ctl, redA, redB, sc);
+        if (precondition<CH>(h, nrhs, sv, z)) return 1;
+        if (halo_planes(h, z, nrhs)) return 1;
+        LAUNCH(h, (k_spmv_dot<CH, 1>), grid, BLOCK, h->mv, nrhs, ctl, diag, Fs, z, t, sv, part, redC, counter);
+        if (all_reduce(h, redC, 2 * nrhs)) return 1;
+        LAUNCH(h, (k_update_x_r<CH>), grid, BLOCK, N, NP, rp, ctl, redC, y, z, sv, t, r0, r, part, redD, counter);
+        if (all_reduce(h, redD, 2 * nrhs)) return 1;
+        LAUNCH(h, k_ctl_end, 1, 32, nrhs, ctl, redC, redD, sc, h->h_nActive);
+        CK(cudaStreamSynchronize(h->stream));
+        ++iters;
+        if (iters > h->ctl.max_iter + 2) break;
+    }
+    *itersOut = iters;
+    return 0;
+}
+
+int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
+    if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
+    if (h->ctl.ddt != RHEO_DDT_EULER) return fail("rheo_gpu_step: only the Euler ddt scheme is implemented");
+    if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB) return fail("rheo_gpu_step: only PBiCGStab is implemented on the device (PBiCG is available in the oracle)");
+    const int N = h->N, NP = h->NP, grid = cdiv(N, BLOCK);
+    const int nModes = (int)h->modes.size();
+    const double rDeltaT = 1.0 / dt;
+    const int noConv = h->ctl.limiter == RHEO_LIMITER_NONE;
+    if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+
+    // ---- halo of U (grad U) and of theta (deferred correction / SpMV of the first residual)
+    if (h->H) {
+        if (halo_planes(h, h->d_U.as<double>(), 3)) return 1;
+        for (ModeDev& md : h->modes) if (halo_planes(h, md.theta.as<double>(), 6)) return 1;
+    }
+    if (h->timing) cudaEventRecord(h->ev[1], h->stream);
+    // ---- assembly, mode by mode (the matrix is shared: same phi, same dt)
+    float msGrad = 0, msAsm = 0;
+    for (int mi = 0; mi < nModes; ++mi) {
+        ModeDev& md = h->modes[mi];
+        cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
+        if (h->lim.hrs && !noConv) {
+            if (h->timing) cudaEventRecord(e0, h->stream);
+            LAUNCH(h, k_grad_theta, grid, BLOCK, h->mv, md.theta.as<double>(), md.thetaB.as<double>(), h->d_grad.as<double>());
+            if (h->H && halo_planes(h, h->d_grad.as<double>(), 18)) return 1;
+            if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msGrad += ms; }
+        }
+        if (h->timing) cudaEventRecord(e0, h->stream);
+        LAUNCH(h, k_cell_source, grid, BLOCK, h->mv, md.mp, rDeltaT, h->d_U.as<double>(), h->d_Ub.as<double>(), md.theta.as<double>(),
+               md.thetaOld.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.bsrc.as<double>(), md.fFene.as<double>());
+        LAUNCH(h, k_convect, grid, BLOCK, h->mv, h->lim, noConv, rDeltaT, h->ctl.relax, mi == 0 ? 1 : 0, h->d_phi.as<double>(), md.theta.as<double>(),
+               md.thetaB.as<double>(), h->d_grad.as<double>(), md.bsrc.as<double>(), h->d_diag.as<double>(), h->d_rD.as<double>(), h->d_Fs.as<double>());
+        if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
+    }
+    if (h->timing) cudaEventRecord(h->ev[2], h->stream);
+
+    // ---- segregated solve: all valid components of all modes batched on the shared matrix
+    h->lastIters = 0;
+    const int perBatch = std::max(1, MAX_RHS / h->nComp);
+    for (int m0 = 0; m0 < nModes; m0 += perBatch) {
+        const int m1 = std::min(nModes, m0 + perBatch);
+        RhsPtrs rp;
+        rp.n = 0;
+        for (int mi = m0; mi < m1; ++mi)
+            for (int j = 0; j < h->nComp; ++j) {
+                rp.psi[rp.n] = h->modes[mi].theta.as<double>() + (size_t)h->comps[j] * NP;
+                rp.b[rp.n] = h->modes[mi].bsrc.as<double>() + (size_t)h->comps[j] * NP;
+                rp.n++;
+            }
+        int iters = 0;
+        int rc = (h->nComp == 6) ? solve_batch<6>(h, rp, &iters) : solve_batch<4>(h, rp, &iters);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl.p, rp.n * sizeof(KrylovCtl), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        int q = 0;
+        for (int mi = m0; mi < m1; ++mi) {
+            if (stats) std::memset(&stats[mi], 0, sizeof(RheoStepStats));
+            for (int j = 0; j < h->nComp; ++j, ++q) {
+                const KrylovCtl& k = h->h_ctl[q];
+                h->lastIters = std::max(h->lastIters, k.iters);
+                if (stats) {
+                    const int cmp = h->comps[j];
+                    stats[mi].initial_residual[cmp] = k.initRes;
+                    stats[mi].final_residual[cmp] = k.finRes;
+                    stats[mi].n_iterations[cmp] = k.iters;
+                    stats[mi].converged[cmp] = (k.finRes < h->ctl.tolerance || (h->ctl.rel_tol > 1e-20 && k.finRes < h->ctl.rel_tol * k.initRes)) ? 1 : 0;
+                }
+            }
+            if (stats) for (int cmp = 0; cmp < 6; ++cmp) if (std::find(h->comps, h->comps + h->nComp, cmp) == h->comps + h->nComp) stats[mi].converged[cmp] = 1;
+        }
+    }
+    if (h->timing) cudaEventRecord(h->ev[3], h->stream);
+
+    // ---- theta BCs, eig + exp + tau
+    for (ModeDev& md : h->modes) {
+        if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_bthetaBC.as<int>(), md.theta.as<double>(), md.thetaB.as<double>(), 6);
+        LAUNCH(h, k_eig_tau, grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>());
+    }
+    if (h->timing) cudaEventRecord(h->ev[4], h->stream);
+    // ---- tau.correctBoundaryConditions(): processor values first, then physical patches in order
+    for (ModeDev& md : h->modes) {
+        if (h->H && halo_planes(h, md.tau.as<double>(), 6)) return 1;
+        if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_btauBC.as<int>(), md.tau.as<double>(), md.tauB.as<double>(), 6);
+        for (const RheoPatchDesc& p : h->patches) {
+            if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR || p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION || p.size == 0) continue;
+            const int b0 = p.start - h->nInt;
+            LAUNCH(h, k_tau_bc_linext, cdiv(p.size, 128), 128, h->mv, b0, p.size, md.tau.as<double>(), md.tauB.as<double>(), h->d_tmpB.as<double>());
+            LAUNCH(h, k_tau_bc_commit, cdiv(p.size, 128), 128, h->nB, b0, p.size, h->d_tmpB.as<double>(), md.tauB.as<double>());
+        }
+    }
+    if (h->timing) {
+        cudaEventRecord(h->ev[5], h->stream);
+        cudaEventSynchronize(h->ev[5]);
+        float ms;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->phaseMs[0] = ms;
+        h->phaseMs[1] = msGrad; h->phaseMs[2] = msAsm;
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->phaseMs[3] = ms;
+        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->phaseMs[4] = ms;
+        cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->phaseMs[5] = ms;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->phaseMs[6] = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string("rheo_gpu_step: ") + cudaGetErrorString(e));
+    return 0;
+}
+
+// host AoS -> device SoA through the staging buffer
+int put_cells(RheoGpu* h, const double* src, int nc, double* dstPlanes) {
+    CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->N * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(h, k_aos_to_soa, cdiv(h->N, BLOCK), BLOCK, h->N, nc, h->d_perm.as<int>(), h->d_stage.as<double>(), dstPlanes, h->NP);
+    return 0;
+}
+int put_bfaces(RheoGpu* h, const double* src, int nc, double* dstPlanes) {
+    if (!h->nB) return 0;
+    CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->nB * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(h, k_aos_to_soa, cdiv(h->nB, BLOCK), BLOCK, h->nB, nc, (const int*)nullptr, h->d_stage.as<double>(), dstPlanes, h->nB);
+    return 0;
+}
+
+}  // namespace
+
+// ==================================================================== C-ABI
+extern "C" {
+
+const char* rheo_gpu_last_error(void) { return g_err.c_str(); }
+
+int rheo_gpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_t n_modes, const RheoSchemeCtl* ctl, int32_t device, RheoGpu** out) {
+    if (!mesh || !modes || !ctl || !out || n_modes < 1) return fail("rheo_gpu_create: null/invalid argument");
+    if (rheo_gpu_device_count() <= device) return fail("rheo_gpu_create: no CUDA device " + std::to_string(device) + " (this library has no CPU fallback)");
+    CK(cudaSetDevice(device));
+    RheoGpu* h = new RheoGpu();
+    h->device = device;
+    h->ctl = *ctl;
+    h->lim = make_limiter(ctl->limiter);
+    if (ctl->limiter < RHEO_LIMITER_UPWIND || ctl->limiter > RHEO_LIMITER_NONE) { delete h; return fail("The deferred limited scheme is not specified or does not exist. Valid schemes are: upwind cubista minmod smart waceb superbee none"); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("cudaStreamCreate failed"); }
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    if (build_mesh(h, mesh) || alloc_fields(h, modes, n_modes)) { rheo_gpu_destroy(h); return 1; }
+    *out = h;
+    return 0;
+}
+
+void rheo_gpu_destroy(RheoGpu* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
+                      &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
+                      &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_grad, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
+                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ctl, &h->d_partials, &h->d_red, &h->d_counter})
+        b->release();
+    for (ModeDev& md : h->modes)
+        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals}) b->release();
+    if (h->h_nActive) cudaFreeHost(h->h_nActive);
+    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    for (auto& e : h->ev) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int rheo_gpu_nccl_unique_id(void* id128) {
+    if (!g_nccl.load()) return fail("rheo_gpu_nccl_unique_id: cannot load libnccl.so.2");
+    NcclId id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc) return fail(std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc));
+    std::memcpy(id128, &id, 128);
+    return 0;
+}
+
+int rheo_gpu_comm_init(RheoGpu* h, int32_t rank, int32_t n_ranks, const void* id128) {
+    if (!h) return fail("rheo_gpu_comm_init: null handle");
+    if (!g_nccl.load()) return fail("rheo_gpu_comm_init: cannot load libnccl.so.2");
+    CK(cudaSetDevice(h->device));
+    NcclId id;
+    std::memcpy(&id, id128, 128);
+    int rc = g_nccl.CommInitRank(&h->comm, n_ranks, id, rank);
+    if (rc) return fail(std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc));
+    h->rank = rank; h->nRanks = n_ranks;
+    // global cell count for gAverage
+    double* tmp = h->d_red.as<double>();
+    double n = (double)h->N;
+    CK(cudaMemcpyAsync(tmp, &n, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (all_reduce(h, tmp, 1)) return 1;
+    CK(cudaMemcpyAsync(&n, tmp, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->nGlobalCells = (long)(n + 0.5);
+    return 0;
+}
+
+int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const double* tau, const double* eigvals, const double* eigvecs,
+                          const double* theta_b, const double* tau_b) {
+    if (!h || mode < 0 || mode >= (int)h->modes.size()) return fail("rheo_gpu_upload_state: bad handle/mode");
+    CK(cudaSetDevice(h->device));
+    ModeDev& md = h->modes[mode];
+    if (theta) {
+        if (put_cells(h, theta, 6, md.theta.as<double>())) return 1;
+        CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (tau && put_cells(h, tau, 6, md.tau.as<double>())) return 1;
+    if (eigvals) {
+        CK(cudaMemcpyAsync(h->d_stage.p, eigvals, (size_t)h->N * 9 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        LAUNCH(h, k_lam_from_tensor, cdiv(h->N, BLOCK), BLOCK, h->N, h->d_perm.as<int>(), h->d_stage.as<double>(), md.lam.as<double>(), h->NP);
+    }
+    if (eigvecs && put_cells(h, eigvecs, 9, md.R.as<double>())) return 1;
+    if (theta_b) { if (put_bfaces(h, theta_b, 6, md.thetaB.as<double>())) return 1; }
+    if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_bthetaBC.as<int>(), md.theta.as<double>(), md.thetaB.as<double>(), 6);
+    if (tau_b) { if (put_bfaces(h, tau_b, 6, md.tauB.as<double>())) return 1; }
+    else if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_btauBC.as<int>(), md.tau.as<double>(), md.tauB.as<double>(), 6);
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi) {
+    if (!h || !U || !phi) return fail("rheo_gpu_upload_velocity: null argument");
+    CK(cudaSetDevice(h->device));
+    if (put_cells(h, U, 3, h->d_U.as<double>())) return 1;
+    if (h->nB && U_b && put_bfaces(h, U_b, 3, h->d_Ub.as<double>())) return 1;
+    CK(cudaMemcpyAsync(h->d_stage.p, phi, (size_t)h->nF * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    LAUNCH(h, k_phi_in, cdiv(h->nF, BLOCK), BLOCK, h->nF, h->d_faceOld.as<int>(), h->d_stage.as<double>(), h->d_phi.as<double>());
+    return 0;
+}
+
+int rheo_gpu_store_old_time(RheoGpu* h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    for (ModeDev& md : h->modes) CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int rheo_gpu_step(RheoGpu* h, double dt, RheoStepStats* stats) {
+    if (!h) return fail("rheo_gpu_step: null handle");
+    CK(cudaSetDevice(h->device));
+    return do_step(h, dt, stats);
+}
+
+int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
+    if (!h || !dst || mode < 0 || mode >= (int)h->modes.size()) return fail("rheo_gpu_download: bad argument");
+    CK(cudaSetDevice(h->device));
+    ModeDev& md = h->modes[mode];
+    const int N = h->N, NP = h->NP, nB = h->nB;
+    double* stage = h->d_stage.as<double>();
+    size_t bytes = 0;
+    switch (field) {
+        case RHEO_FIELD_THETA: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), md.theta.as<double>(), stage, NP); bytes = (size_t)N * 6; break;
+        case RHEO_FIELD_THETA_OLD: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), md.thetaOld.as<double>(), stage, NP); bytes = (size_t)N * 6; break;
+        case RHEO_FIELD_TAU: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), md.tau.as<double>(), stage, NP); bytes = (size_t)N * 6; break;
+        case RHEO_FIELD_TAU_TOTAL:
+            for (size_t mi = 0; mi < h->modes.size(); ++mi) {
+                if (mi == 0) LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), h->modes[mi].tau.as<double>(), stage, NP);
+                else LAUNCH(h, k_soa_to_aos_acc, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), h->modes[mi].tau.as<double>(), stage, NP);
+            }
+            bytes = (size_t)N * 6;
+            break;
+        case RHEO_FIELD_EIGVALS: LAUNCH(h, k_lam_to_tensor, cdiv(N, BLOCK), BLOCK, N, h->d_perm.as<int>(), md.lam.as<double>(), stage, NP); bytes = (size_t)N * 9; break;
+        case RHEO_FIELD_EIGVECS: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 9, h->d_perm.as<int>(), md.R.as<double>(), stage, NP); bytes = (size_t)N * 9; break;
+        case RHEO_FIELD_THETA_B: if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, md.thetaB.as<double>(), stage, nB); bytes = (size_t)nB * 6; break;
+        case RHEO_FIELD_TAU_B: if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, md.tauB.as<double>(), stage, nB); bytes = (size_t)nB * 6; break;
+        default: return fail("rheo_gpu_download: unknown field");
+    }
+    if (bytes) CK(cudaMemcpyAsync(dst, stage, bytes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const double* phi, double dt, int32_t new_time_step, double* tau_out,
+                     double* tau_b_out, RheoStepStats* stats) {
+    if (rheo_gpu_upload_velocity(h, U, U_b, phi)) return 1;
+    if (new_time_step && rheo_gpu_store_old_time(h)) return 1;
+    if (rheo_gpu_step(h, dt, stats)) return 1;
+    if (tau_out && rheo_gpu_download(h, 0, RHEO_FIELD_TAU_TOTAL, tau_out)) return 1;
+    if (tau_b_out && rheo_gpu_download(h, 0, RHEO_FIELD_TAU_B, tau_b_out)) return 1;
+    return 0;
+}
+
+int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int32_t* colour_start) {
+    if (!h) return fail("null handle");
+    if (perm) std::copy(h->perm.begin(), h->perm.end(), perm);
+    if (n_colours) *n_colours = h->nColours;
+    if (colour_start) std::copy(h->colourStart.begin(), h->colourStart.end(), colour_start);
+    return 0;
+}
+
+int rheo_gpu_get_ell(RheoGpu* h, int32_t* K, int32_t* nbr, int32_t* face) {
+    if (!h) return fail("null handle");
+    if (K) *K = h->K;
+    for (int s = 0; s < h->K; ++s)
+        for (int c = 0; c < h->N; ++c) {
+            if (nbr) nbr[(size_t)s * h->N + c] = h->h_nbr[(size_t)s * h->NS + c];
+            if (face) face[(size_t)s * h->N + c] = h->h_fidx[(size_t)s * h->NS + c];
+        }
+    return 0;
+}
+
+int64_t rheo_gpu_launch_count(const RheoGpu* h) { return h ? h->launches : 0; }
+int rheo_gpu_last_iterations(const RheoGpu* h) { return h ? h->lastIters : -1; }
+int rheo_gpu_set_phase_timing(RheoGpu* h, int32_t enabled) { if (!h) return 1; h->timing = enabled != 0; return 0; }
+int rheo_gpu_get_phase_times(RheoGpu* h, double* ms7) { if (!h || !ms7) return 1; std::copy(h->phaseMs, h->phaseMs + 7, ms7); return 0; }
+int rheo_gpu_stream(RheoGpu* h, void** s) { if (!h || !s) return 1; *s = (void*)h->stream; return 0; }
+int rheo_gpu_synchronize(RheoGpu* h) {
+    if (!h) return fail("null handle");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int rheo_gpu_eig_exp(int32_t device, int32_t n, const double* theta6, double* eigvals9, double* eigvecs9) {
+    if (rheo_gpu_device_count() <= device) return fail("rheo_gpu_eig_exp: no CUDA device (no CPU fallback)");
+    CK(cudaSetDevice(device));
+    double *a = nullptr, *b = nullptr, *c = nullptr;
+    CK(cudaMalloc(&a, (size_t)n * 6 * 8)); CK(cudaMalloc(&b, (size_t)n * 9 * 8)); CK(cudaMalloc(&c, (size_t)n * 9 * 8));
+    CK(cudaMemcpy(a, theta6, (size_t)n * 6 * 8, cudaMemcpyHostToDevice));
+    k_eig_exp_aos<<<cdiv(n, BLOCK), BLOCK>>>(n, a, b, c);
+    CK(cudaMemcpy(eigvals9, b, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(eigvecs9, c, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost));
+    cudaFree(a); cudaFree(b); cudaFree(c);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,676 @@
+// kernels.cuh — sm_100a kernels of the stress step.  All of them are HBM-bound FP64 streaming /
+// gather kernels (no dense contraction anywhere => no tensor cores): one thread per cell, SoA planes,
+// slot-major ELL connectivity so that every warp-level load is a contiguous 256-byte segment, cell
+// numbering sorted by colour so that the DILU sweeps are a few fully parallel phases.
+//
+// Reference loops restated (of90/src/libs/...):
+//   k_grad_theta      gaussDefCmpwConvectionScheme/gaussDefCmpwConvectionScheme.C:242-254 (6 x fvc::grad)
+//   k_cell_source     constitutiveEquations/constitutiveEqs/utils/boilerLog.H:1-36 + the model sources
+//   k_convect         gaussDefCmpwConvectionScheme.C:93-167 (upwind LDU, boundary coeffs, deferred HRS)
+//                     and :257-319 (phifDefC face loop, coupled patches), EXT-OF9 fvMatrix::relax,
+//                     addBoundaryDiag/addBoundarySource
+//   k_spmv*, k_sweep* EXT-OF9 lduMatrix::Amul, DILUPreconditioner::precondition
+//   k_eig_tau         constitutiveEq.C:360-416 (calcEig) + theta->tau maps
+//   k_tau_bc_linext   boundaryConditions/linearExtrapolation/linearExtrapolationFvPatchField.C:101-151
+#pragma once
+#include <cstdint>
+#include "cell_algebra.cuh"
+
+namespace rk {
+
+constexpr int BLOCK = 256;
+constexpr int MAX_RHS = 24;
+constexpr int MAX_RED = 3 * MAX_RHS;
+
+// ---------------------------------------------------------------- device views
+struct MeshView {
+    int N, H, NT, NS, NP, K, nInt, nF, nB;
+    const int* nbr;    // [K*NS] topological: >=0 cell/ghost, -1 empty, <=-2 boundary face -(b+2)
+    const int* nbrA;   // [K*NS] algebraic: neighbour cell/ghost, self for empty/boundary slots
+    const int* fidx;   // [K*NS] face id, ~face when this cell is the face's neighbour
+    const double* Sf;  // [3*nF] planes (x|y|z), stride nF, orientation of the (renumbered) owner
+    const double* w;   // [nF]
+    const double* C;   // [3*NP] planes, incl. ghost cell centres
+    const double* V;   // [N]
+    const double* rV;  // [N] 1/V
+    const int* bcell;  // [nB] owner cell of boundary face
+    const int* bkind;  // [nB] patch type
+    const int* bthetaBC;  // [nB]
+    const int* btauBC;    // [nB]
+    const double* CfB;    // [3*nB] planes
+};
+
+struct RhsPtrs {      // one batch of right-hand sides sharing the matrix
+    int n;
+    double* psi[MAX_RHS];       // theta planes (solution, in place)
+    const double* b[MAX_RHS];   // source planes
+};
+
+// ---------------------------------------------------------------- reductions
+// Block-reduce NV per-thread values and store the block partials; the last block to finish sums
+// the partials of all blocks in a fixed order (deterministic) into out[].
+template <int NV>
+__device__ __forceinline__ void block_reduce_to_partials(double (&v)[NV], double* partials, int slotBase, int nSlots) {
+    __shared__ double sm[BLOCK / 32][NV];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double x = v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[warp][i] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double x = 0;
+#pragma unroll
+        for (int wv = 0; wv < BLOCK / 32; ++wv) x += sm[wv][threadIdx.x];
+        partials[(size_t)blockIdx.x * nSlots + slotBase + threadIdx.x] = x;
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void finalize_partials(const double* partials, int nSlots, double* out, unsigned* counter) {
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(counter, 1u);
+        isLast = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = warp; s < nSlots; s += BLOCK / 32) {
+        double x = 0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) x += partials[(size_t)b * nSlots + s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) out[s] = x;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+// ---------------------------------------------------------------- layout transforms (upload / download)
+// AoS in the caller's numbering -> SoA planes in device numbering
+__global__ void k_aos_to_soa(int n, int nc, const int* __restrict__ perm, const double* __restrict__ aos, double* __restrict__ soa, int stride) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int o = perm ? perm[c] : c;
+    for (int k = 0; k < nc; ++k) soa[(size_t)k * stride + c] = aos[(size_t)o * nc + k];
+}
+__global__ void k_soa_to_aos(int n, int nc, const int* __restrict__ perm, const double* __restrict__ soa, double* __restrict__ aos, int stride) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int o = perm ? perm[c] : c;
+    for (int k = 0; k < nc; ++k) aos[(size_t)o * nc + k] = soa[(size_t)k * stride + c];
+}
+// eigVals tensor (9, diagonal used) <-> Lam[3]; accum != 0 adds instead of overwriting (sum over modes)
+__global__ void k_soa_to_aos_acc(int n, int nc, const int* __restrict__ perm, const double* __restrict__ soa, double* __restrict__ aos, int stride) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int o = perm ? perm[c] : c;
+    for (int k = 0; k < nc; ++k) aos[(size_t)o * nc + k] += soa[(size_t)k * stride + c];
+}
+__global__ void k_lam_from_tensor(int n, const int* __restrict__ perm, const double* __restrict__ aos9, double* __restrict__ lam, int stride) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int o = perm[c];
+    lam[c] = aos9[(size_t)o * 9]; lam[stride + c] = aos9[(size_t)o * 9 + 4]; lam[2 * (size_t)stride + c] = aos9[(size_t)o * 9 + 8];
+}
+__global__ void k_lam_to_tensor(int n, const int* __restrict__ perm, const double* __restrict__ lam, double* __restrict__ aos9, int stride) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const int o = perm[c];
+    double* t = aos9 + (size_t)o * 9;
+    t[0] = lam[c]; t[1] = 0; t[2] = 0; t[3] = 0; t[4] = lam[stride + c]; t[5] = 0; t[6] = 0; t[7] = 0; t[8] = lam[2 * (size_t)stride + c];
+}
+// phi: caller's face order -> device face order (flip sign where the renumbered owner changed)
+__global__ void k_phi_in(int nF, const int* __restrict__ faceOld, const double* __restrict__ src, double* __restrict__ dst) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nF) return;
+    const int o = faceOld[f];   // old face + 1, negative if flipped
+    dst[f] = o > 0 ? src[o - 1] : -src[-o - 1];
+}
+__global__ void k_fill(size_t n, double* p, double v) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_copy(size_t n, const double* __restrict__ s, double* __restrict__ d) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = s[i];
+}
+
+// ---------------------------------------------------------------- halo pack / unpack
+// segment layout: for neighbour j with ghosts [h0,h1): buf[np*h0 + p*(h1-h0) + (h-h0)]
+struct PlaneList { int n; double* p[MAX_RHS]; };
+__global__ void k_halo_pack(int H, PlaneList pl, const int* __restrict__ haloCell, const int* __restrict__ segStart, const int* __restrict__ segLen, double* __restrict__ buf) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const int c = haloCell[h], h0 = segStart[h], len = segLen[h];
+    for (int p = 0; p < pl.n; ++p) buf[(size_t)pl.n * h0 + (size_t)p * len + (h - h0)] = pl.p[p][c];
+}
+__global__ void k_halo_unpack(int H, int N, PlaneList pl, const int* __restrict__ segStart, const int* __restrict__ segLen, const double* __restrict__ buf) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const int h0 = segStart[h], len = segLen[h];
+    for (int p = 0; p < pl.n; ++p) pl.p[p][N + h] = buf[(size_t)pl.n * h0 + (size_t)p * len + (h - h0)];
+}
+
+// ---------------------------------------------------------------- boundary values
+// theta.correctBoundaryConditions(): zeroGradient patch value = internal value
+__global__ void k_bc_zero_gradient(MeshView m, const int* __restrict__ bc, const double* __restrict__ fld, double* __restrict__ fldB, int nc) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.nB) return;
+    if (bc[b] != RHEO_BC_ZERO_GRADIENT || m.bkind[b] == RHEO_PATCH_EMPTY) return;
+    const int c = m.bcell[b];
+    for (int k = 0; k < nc; ++k) fldB[(size_t)k * m.nB + b] = fld[(size_t)k * m.NP + c];
+}
+
+// ---------------------------------------------------------------- Gauss-linear gradient of NC fields
+// face value: internal w(P-N)+N in the face's owner/neighbour frame; processor wP+(1-w)N; boundary = patch value
+template <int NC>
+__device__ __forceinline__ void gauss_grad_cell(const MeshView& m, int c, const double* __restrict__ fld, const double* __restrict__ fldB,
+                                                const double* own, double* g /*[3*NC]: g[3k+d]*/) {
+#pragma unroll
+    for (int i = 0; i < 3 * NC; ++i) g[i] = 0.0;
+    for (int s = 0; s < m.K; ++s) {
+        const int nb = m.nbr[(size_t)s * m.NS + c];
+        if (nb == -1) continue;
+        const int fi = m.fidx[(size_t)s * m.NS + c];
+        const int f = fi >= 0 ? fi : ~fi;
+        const double sg = fi >= 0 ? 1.0 : -1.0;
+        const double Sx = sg * m.Sf[f], Sy = sg * m.Sf[(size_t)m.nF + f], Sz = sg * m.Sf[2 * (size_t)m.nF + f];
+        if (nb >= 0) {
+            const double w = m.w[f];
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const double vn = fld[(size_t)k * m.NP + nb];
+                double vf;
+                if (nb >= m.N) vf = w * own[k] + (1.0 - w) * vn;
+                else vf = fi >= 0 ? w * (own[k] - vn) + vn : w * (vn - own[k]) + own[k];
+                g[3 * k] += Sx * vf; g[3 * k + 1] += Sy * vf; g[3 * k + 2] += Sz * vf;
+            }
+        } else {
+            const int b = -nb - 2;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+                const double vf = fldB[(size_t)k * m.nB + b];
+                g[3 * k] += Sx * vf; g[3 * k + 1] += Sy * vf; g[3 * k + 2] += Sz * vf;
+            }
+        }
+    }
+    const double rv = m.rV[c];
+#pragma unroll
+    for (int i = 0; i < 3 * NC; ++i) g[i] *= rv;
+}
+
+__global__ void __launch_bounds__(BLOCK) k_grad_theta(MeshView m, const double* __restrict__ theta, const double* __restrict__ thetaB, double* __restrict__ grad) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.N) return;
+    double own[6], g[18];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) own[k] = theta[(size_t)k * m.NP + c];
+    gauss_grad_cell<6>(m, c, theta, thetaB, own, g);
+#pragma unroll
+    for (int i = 0; i < 18; ++i) grad[(size_t)i * m.NP + c] = g[i];
+}
+
+// ---------------------------------------------------------------- per-cell source: grad(U), Omega/B split, model term, Euler ddt
+__global__ void __launch_bounds__(BLOCK) k_cell_source(MeshView m, ModelParams mp, double rDeltaT, const double* __restrict__ U, const double* __restrict__ Ub,
+                                                        const double* __restrict__ theta, const double* __restrict__ thetaOld, const double* __restrict__ lam,
+                                                        const double* __restrict__ R, double* __restrict__ bsrc, double* __restrict__ fFene) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.N) return;
+    double own[3], g[9];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) own[k] = U[(size_t)k * m.NP + c];
+    gauss_grad_cell<3>(m, c, U, Ub, own, g);
+    // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
+    const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
+    double th[6], Rm[9], lm[3], rhs[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) th[k] = theta[(size_t)k * m.NP + c];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Rm[k] = R[(size_t)k * m.NP + c];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) lm[k] = lam[(size_t)k * m.NP + c];
+    const double f = model_rhs(mp, L, th, Rm, lm, rhs);
+    fFene[c] = f;
+    const double V = m.V[c];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bsrc[(size_t)k * m.NP + c] = rDeltaT * thetaOld[(size_t)k * m.NP + c] * V + V * rhs[k];
+}
+
+// ---------------------------------------------------------------- convection: upwind LDU + deferred HRS + boundary folding + relax
+struct Limiter { int hrs; double a0, a1, a2, b0, b1, b2, bnd0, bnd1; };
+
+__device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, double gNd, double upw, const Limiter& lm) {
+    const double gd_up = gPd * upw + (1.0 - upw) * gNd;
+    const double phitc = 1.0 - ((vN - vP) / (2.0 * gd_up + 1e-18));
+    double alpha, beta;
+    if (phitc <= 0. || phitc >= 1.) { alpha = 1.; beta = 0.; }
+    else if (phitc < lm.bnd0) { alpha = lm.a0; beta = lm.b0; }
+    else if (phitc < lm.bnd1) { alpha = lm.a1; beta = lm.b1; }
+    else { alpha = lm.a2; beta = lm.b2; }
+    return (1.0 - alpha - beta) * (vN - 2.0 * gPd) * upw + (1.0 - alpha - beta) * (vP + 2.0 * gNd) * (1.0 - upw) +
+           ((alpha - 1.0) * upw + beta * (1.0 - upw)) * vP + (beta * upw + (alpha - 1.0) * (1.0 - upw)) * vN;
+}
+
+// writeMatrix: first mode of a batch writes Fs / diag (identical for all modes: same phi, same dt)
+__global__ void __launch_bounds__(BLOCK) k_convect(MeshView m, Limiter lim, int noConv, double rDeltaT, double relax, int writeMatrix,
+                                                    const double* __restrict__ phi, const double* __restrict__ theta, const double* __restrict__ thetaB,
+                                                    const double* __restrict__ grad, double* __restrict__ bsrc, double* __restrict__ diag,
+                                                    double* __restrict__ rD, double* __restrict__ Fs) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m.N) return;
+    double thP[6], sou[6] = {0, 0, 0, 0, 0, 0}, bnd[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 6; ++k) thP[k] = theta[(size_t)k * m.NP + c];
+    const double Cx = m.C[c], Cy = m.C[(size_t)m.NP + c], Cz = m.C[2 * (size_t)m.NP + c];
+    double D = rDeltaT * m.V[c];   // ddt diag + negSumDiag
+    double sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0;
+    for (int s = 0; s < m.K; ++s) {
+        const int nb = m.nbr[(size_t)s * m.NS + c];
+        double F = 0.0;   // signed outflow flux stored for the Krylov kernels
+        if (nb != -1 && !noConv) {
+            const int fi = m.fidx[(size_t)s * m.NS + c];
+            const int f = fi >= 0 ? fi : ~fi;
+            const double ph = phi[f];
+            if (nb >= 0) {
+                F = fi >= 0 ? ph : -ph;
+                if (nb < m.N) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
+                else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
+                if (lim.hrs) {
+                    // owner/neighbour frame of the face (identical arithmetic on both sides => conservative)
+                    const bool own = fi >= 0;
+                    const double dx = own ? m.C[nb] - Cx : Cx - m.C[nb];
+                    const double dy = own ? m.C[(size_t)m.NP + nb] - Cy : Cy - m.C[(size_t)m.NP + nb];
+                    const double dz = own ? m.C[2 * (size_t)m.NP + nb] - Cz : Cz - m.C[2 * (size_t)m.NP + nb];
+                    const double upw = ph >= 0 ? 1.0 : 0.0;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const double gcx = grad[(size_t)(3 * k) * m.NP + c], gcy = grad[(size_t)(3 * k + 1) * m.NP + c], gcz = grad[(size_t)(3 * k + 2) * m.NP + c];
+                        const double gnx = grad[(size_t)(3 * k) * m.NP + nb], gny = grad[(size_t)(3 * k + 1) * m.NP + nb], gnz = grad[(size_t)(3 * k + 2) * m.NP + nb];
+                        const double gc = gcx * dx + gcy * dy + gcz * dz, gn = gnx * dx + gny * dy + gnz * dz;
+                        const double vn = theta[(size_t)k * m.NP + nb];
+                        const double v = own ? phif_defc(thP[k], vn, gc, gn, upw, lim) : phif_defc(vn, thP[k], gn, gc, upw, lim);
+                        sou[k] += v * F;   // souT[own] += v*phi ; souT[nei] -= v*phi
+                    }
+                }
+            } else {
+                const int b = -nb - 2;
+                if (m.bthetaBC[b] == RHEO_BC_ZERO_GRADIENT) { iCplain += ph; iCplainAbs += fabs(ph); }
+                else {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) bnd[k] += -ph * thetaB[(size_t)k * m.nB + b];
+                }
+                F = 0.0;
+            }
+        }
+        if (writeMatrix) Fs[(size_t)s * m.NS + c] = (nb >= 0) ? F : 0.0;
+    }
+    double add[6] = {0, 0, 0, 0, 0, 0};
+    if (relax > 0) {   // EXT-OF9 fvMatrix::relax
+        const double D0 = D;
+        double Dn = D + iCcoupled + iCplainAbs;
+        Dn = fmax(fabs(Dn), sumOff);
+        Dn /= relax;
+        Dn -= iCcoupled;
+        Dn -= iCplain;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) add[k] = (Dn - D0) * thP[k];
+        D = Dn;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) bsrc[(size_t)k * m.NP + c] += (-sou[k] + add[k]) + bnd[k];
+    if (writeMatrix) {
+        const double Dfull = D + iCcoupled + iCplain;   // addBoundaryDiag
+        diag[c] = Dfull;
+        rD[c] = 1.0 / Dfull;   // DILU: upper*lower == 0 on every face of an upwind matrix
+    }
+}
+
+// ---------------------------------------------------------------- Krylov building blocks (batched RHS, one shared matrix)
+// row c of A:  diag[c] x[c] + sum_slots min(Fs,0) x[nbrA]      (lduMatrix::Amul incl. processor interfaces via ghosts)
+struct VecSet { double* v; };   // [nrhs][NP] contiguous planes
+
+struct KrylovCtl {   // one per RHS, device resident
+    double rho, rhoOld, alpha, omega, beta, normFactor, initRes, finRes;
+    int state;   // 0 active, 1 converged at the half step (needs psi += alpha y), 2 done
+    int iters;
+    int singular;
+    int pad;
+};
+
+// sum of psi (for gAverage) ---------------------------------------------------
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_sum_psi(int N, RhsPtrs rp, double* partials, double* out, unsigned* counter) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int r0 = 0; r0 < rp.n; r0 += CH) {
+        double v[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) v[j] = (c < N) ? rp.psi[r0 + j][c] : 0.0;
+        block_reduce_to_partials<CH>(v, partials, r0, rp.n);
+    }
+    finalize_partials(partials, rp.n, out, counter);
+}
+
+// initial residual: v = A psi, r = b - v, r0 = r; sums: [0] normFactor terms, [1] |r|, [2] r0.r
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ Fs,
+                                                        const double* __restrict__ sumPsi, double nGlobal, double* __restrict__ r, double* __restrict__ r0v,
+                                                        double* partials, double* out, unsigned* counter) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = c < m.N;
+    double d = 0, rowsum = 0;
+    if (act) {
+        d = diag[c];
+        rowsum = d;
+        for (int s = 0; s < m.K; ++s) rowsum += fmin(Fs[(size_t)s * m.NS + c], 0.0);
+    }
+    for (int q0 = 0; q0 < rp.n; q0 += CH) {
+        double red[3 * CH];
+#pragma unroll
+        for (int j = 0; j < 3 * CH; ++j) red[j] = 0.0;
+        if (act) {
+            double acc[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) acc[j] = d * rp.psi[q0 + j][c];
+            for (int s = 0; s < m.K; ++s) {
+                const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
+                const int nb = m.nbrA[(size_t)s * m.NS + c];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) acc[j] += a * rp.psi[q0 + j][nb];
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                const double bb = rp.b[q0 + j][c];
+                const double rr = bb - acc[j];
+                r[(size_t)(q0 + j) * m.NP + c] = rr;
+                r0v[(size_t)(q0 + j) * m.NP + c] = rr;
+                const double t = rowsum * (sumPsi[q0 + j] / nGlobal);
+                red[3 * j] = fabs(acc[j] - t) + fabs(bb - t);
+                red[3 * j + 1] = fabs(rr);
+                red[3 * j + 2] = rr * rr;
+            }
+        }
+        block_reduce_to_partials<3 * CH>(red, partials, 3 * q0, 3 * rp.n);
+    }
+    finalize_partials(partials, 3 * rp.n, out, counter);
+}
+
+// p = r + beta (p - omega v)   (first iteration p = r)
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nrhs, const KrylovCtl* __restrict__ ctl, const double* __restrict__ r,
+                                                     const double* __restrict__ v, double* __restrict__ p) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    for (int q = 0; q < nrhs; ++q) {
+        const KrylovCtl k = ctl[q];
+        if (k.state != 0) continue;
+        const size_t i = (size_t)q * NP + c;
+        p[i] = (k.iters == 0) ? r[i] : r[i] + k.beta * (p[i] - k.omega * v[i]);
+    }
+}
+
+// DILU forward phase for the cells of one colour: w = rD (r - sum_{lower} A[c][l] w[l])
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_sweep_fwd(MeshView m, int c0, int c1, int nrhs, const KrylovCtl* __restrict__ ctl, int needState,
+                                                      const double* __restrict__ rD, const double* __restrict__ Fs, const double* __restrict__ r, double* __restrict__ w) {
+    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const double d = rD[c];
+    for (int q0 = 0; q0 < nrhs; q0 += CH) {
+        double acc[CH];
+        bool on[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { on[j] = ctl[q0 + j].state == needState; acc[j] = on[j] ? r[(size_t)(q0 + j) * m.NP + c] : 0.0; }
+        if (c0 > 0) {
+            for (int s = 0; s < m.K; ++s) {
+                const int nb = m.nbrA[(size_t)s * m.NS + c];
+                if (nb >= c) continue;
+                const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
+#pragma unroll
+                for (int j = 0; j < CH; ++j) if (on[j]) acc[j] -= a * w[(size_t)(q0 + j) * m.NP + nb];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) if (on[j]) w[(size_t)(q0 + j) * m.NP + c] = d * acc[j];
+    }
+}
+// DILU backward phase: w[c] -= rD[c] sum_{upper, local} A[c][u] w[u]
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_sweep_bwd(MeshView m, int c0, int c1, int nrhs, const KrylovCtl* __restrict__ ctl, int needState,
+                                                      const double* __restrict__ rD, const double* __restrict__ Fs, double* __restrict__ w) {
+    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    const double d = rD[c];
+    for (int q0 = 0; q0 < nrhs; q0 += CH) {
+        double acc[CH];
+        bool on[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) { on[j] = ctl[q0 + j].state == needState; acc[j] = 0.0; }
+        for (int s = 0; s < m.K; ++s) {
+            const int nb = m.nbrA[(size_t)s * m.NS + c];
+            if (nb <= c || nb >= m.N) continue;
+            const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
+#pragma unroll
+            for (int j = 0; j < CH; ++j) if (on[j]) acc[j] += a * w[(size_t)(q0 + j) * m.NP + nb];
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) if (on[j]) w[(size_t)(q0 + j) * m.NP + c] -= d * acc[j];
+    }
+}
+
+// y = A x with NDOT fused dot products per RHS:
+//   mode 0: out[q]       = r0 . y                         (rA0AyA)
+//   mode 1: out[2q],[2q+1] = y . y , y . s                (tAtA, tAsA)
+template <int CH, int MODE>
+__global__ void __launch_bounds__(BLOCK) k_spmv_dot(MeshView m, int nrhs, const KrylovCtl* __restrict__ ctl, const double* __restrict__ diag, const double* __restrict__ Fs,
+                                                     const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ other,
+                                                     double* partials, double* out, unsigned* counter) {
+    constexpr int ND = MODE == 0 ? 1 : 2;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = c < m.N;
+    const double d = act ? diag[c] : 0.0;
+    for (int q0 = 0; q0 < nrhs; q0 += CH) {
+        double red[ND * CH];
+#pragma unroll
+        for (int j = 0; j < ND * CH; ++j) red[j] = 0.0;
+        if (act) {
+            double acc[CH];
+            bool on[CH];
+#pragma unroll
+            for (int j = 0; j < CH; ++j) { on[j] = ctl[q0 + j].state == 0; acc[j] = on[j] ? d * x[(size_t)(q0 + j) * m.NP + c] : 0.0; }
+            for (int s = 0; s < m.K; ++s) {
+                const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
+                const int nb = m.nbrA[(size_t)s * m.NS + c];
+#pragma unroll
+                for (int j = 0; j < CH; ++j) if (on[j]) acc[j] += a * x[(size_t)(q0 + j) * m.NP + nb];
+            }
+#pragma unroll
+            for (int j = 0; j < CH; ++j) {
+                if (!on[j]) continue;
+                const size_t i = (size_t)(q0 + j) * m.NP + c;
+                y[i] = acc[j];
+                const double o = other[i];
+                if (MODE == 0) red[j] = o * acc[j];
+                else { red[2 * j] = acc[j] * acc[j]; red[2 * j + 1] = acc[j] * o; }
+            }
+        }
+        block_reduce_to_partials<ND * CH>(red, partials, ND * q0, ND * nrhs);
+    }
+    finalize_partials(partials, ND * nrhs, out, counter);
+}
+
+// s = r - alpha v ; out[q] = sum |s|        (alpha = rho / (r0.v) computed here, stored by thread 0 of block 0)
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_make_s(int N, int NP, int nrhs, KrylovCtl* __restrict__ ctl, const double* __restrict__ dots, const double* __restrict__ r,
+                                                   const double* __restrict__ v, double* __restrict__ sv, double* partials, double* out, unsigned* counter) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int q0 = 0; q0 < nrhs; q0 += CH) {
+        double red[CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            red[j] = 0.0;
+            const KrylovCtl k = ctl[q0 + j];
+            if (k.state != 0) continue;
+            const double alpha = k.rho / dots[q0 + j];
+            if (c < N) {
+                const size_t i = (size_t)(q0 + j) * NP + c;
+                const double x = r[i] - alpha * v[i];
+                sv[i] = x;
+                red[j] = fabs(x);
+            }
+        }
+        block_reduce_to_partials<CH>(red, partials, q0, nrhs);
+    }
+    finalize_partials(partials, nrhs, out, counter);
+}
+
+// psi += alpha y + omega z ; r = s - omega t ; out[2q] = sum|r| , out[2q+1] = r0.r      (state 0)
+// psi += alpha y                                                                        (state 1)
+template <int CH>
+__global__ void __launch_bounds__(BLOCK) k_update_x_r(int N, int NP, RhsPtrs rp, const KrylovCtl* __restrict__ ctl, const double* __restrict__ dots2,
+                                                       const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ sv,
+                                                       const double* __restrict__ t, const double* __restrict__ r0v, double* __restrict__ r,
+                                                       double* partials, double* out, unsigned* counter) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int q0 = 0; q0 < rp.n; q0 += CH) {
+        double red[2 * CH];
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+            red[2 * j] = 0.0; red[2 * j + 1] = 0.0;
+            const KrylovCtl k = ctl[q0 + j];
+            if (k.state == 2 || c >= N) continue;
+            const size_t i = (size_t)(q0 + j) * NP + c;
+            if (k.state == 1) { rp.psi[q0 + j][c] += k.alpha * y[i]; continue; }
+            const double omega = dots2[2 * (q0 + j) + 1] / dots2[2 * (q0 + j)];
+            rp.psi[q0 + j][c] += k.alpha * y[i] + omega * z[i];
+            const double rr = sv[i] - omega * t[i];
+            r[i] = rr;
+            red[2 * j] = fabs(rr);
+            red[2 * j + 1] = r0v[i] * rr;
+        }
+        block_reduce_to_partials<2 * CH>(red, partials, 2 * q0, 2 * rp.n);
+    }
+    finalize_partials(partials, 2 * rp.n, out, counter);
+}
+
+// ---- control kernels (one small block; mirror EXT-OF9 PBiCGStab's scalar logic per component)
+struct SolveCtl { double tol, relTol; int minIter, maxIter; };
+__device__ __forceinline__ bool conv_check(double fin, double init, const SolveCtl& sc) {
+    return fin < sc.tol || (sc.relTol > 1e-20 && fin < sc.relTol * init);
+}
+__global__ void k_ctl_init(int nrhs, KrylovCtl* ctl, const double* red3, SolveCtl sc, int* nActiveOut) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int q = threadIdx.x;
+    if (q < nrhs) {
+        KrylovCtl k;
+        k.normFactor = red3[3 * q] + 1e-20;
+        k.initRes = red3[3 * q + 1] / k.normFactor;
+        k.finRes = k.initRes;
+        k.rho = red3[3 * q + 2];
+        k.rhoOld = 0; k.alpha = 0; k.omega = 0; k.beta = 0; k.iters = 0; k.singular = 0; k.pad = 0;
+        k.state = (sc.minIter > 0 || !conv_check(k.finRes, k.initRes, sc)) ? 0 : 2;
+        if (k.state == 0 && !(fabs(k.rho) > 1e-300)) { k.state = 2; k.singular = 1; }
+        ctl[q] = k;
+        if (k.state == 0) atomicAdd(&cnt, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nActiveOut = cnt;
+}
+// after s: alpha, half-step convergence
+__global__ void k_ctl_half(int nrhs, KrylovCtl* ctl, const double* dotsV, const double* sumS, SolveCtl sc) {
+    const int q = threadIdx.x;
+    if (q >= nrhs) return;
+    KrylovCtl k = ctl[q];
+    if (k.state != 0) return;
+    k.alpha = k.rho / dotsV[q];
+    k.finRes = sumS[q] / k.normFactor;
+    if (conv_check(k.finRes, k.initRes, sc)) k.state = 1;
+    ctl[q] = k;
+}
+// end of iteration
+__global__ void k_ctl_end(int nrhs, KrylovCtl* ctl, const double* dots2, const double* red2, SolveCtl sc, int* nActiveOut) {
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
+    __syncthreads();
+    const int q = threadIdx.x;
+    if (q < nrhs) {
+        KrylovCtl k = ctl[q];
+        if (k.state == 1) { k.iters++; k.state = 2; }
+        else if (k.state == 0) {
+            k.omega = dots2[2 * q + 1] / dots2[2 * q];
+            k.finRes = red2[2 * q] / k.normFactor;
+            k.rhoOld = k.rho;
+            k.rho = red2[2 * q + 1];
+            const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
+            if (!cont) k.state = 2;
+            else if (!(fabs(k.rho) > 1e-300) || !(fabs(k.omega) > 1e-300)) { k.state = 2; k.singular = 1; }
+            else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);
+        }
+        ctl[q] = k;
+        if (k.state == 0) atomicAdd(&cnt, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *nActiveOut = cnt;
+}
+
+// ---------------------------------------------------------------- eig + exp + tau
+__global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp, const double* __restrict__ theta, const double* __restrict__ fFene,
+                                                    double* __restrict__ lam, double* __restrict__ R, double* __restrict__ tau) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    double th[6], d[3], V[9], l[3], t6[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) th[k] = theta[(size_t)k * NP + c];
+    jacobi_eig(th, d, V);
+    l[0] = exp(d[0]); l[1] = exp(d[1]); l[2] = exp(d[2]);
+    tau_from_eig(mp, V, l, fFene[c], t6);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) lam[(size_t)k * NP + c] = l[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[(size_t)k * NP + c] = V[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tau[(size_t)k * NP + c] = t6[k];
+}
+// stand-alone calcEig on AoS host-layout arrays (unit parity test entry point)
+__global__ void k_eig_exp_aos(int n, const double* __restrict__ th6, double* __restrict__ vals9, double* __restrict__ vecs9) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double th[6], d[3], V[9];
+    for (int k = 0; k < 6; ++k) th[k] = th6[(size_t)c * 6 + k];
+    jacobi_eig(th, d, V);
+    double* o = vals9 + (size_t)c * 9;
+    for (int k = 0; k < 9; ++k) o[k] = 0.0;
+    o[0] = exp(d[0]); o[4] = exp(d[1]); o[8] = exp(d[2]);
+    for (int k = 0; k < 9; ++k) vecs9[(size_t)c * 9 + k] = V[k];
+}
+
+// ---------------------------------------------------------------- tau wall BC: linearExtrapolation on one patch
+// one thread per patch face; gradient of the 6 tau components at the wall-adjacent cell only
+__global__ void k_tau_bc_linext(MeshView m, int start, int size, const double* __restrict__ tau, const double* __restrict__ tauB, double* __restrict__ tmp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const int b = start + i;
+    const int c = m.bcell[b];
+    double own[6], g[18];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) own[k] = tau[(size_t)k * m.NP + c];
+    gauss_grad_cell<6>(m, c, tau, tauB, own, g);
+    const double dx = m.CfB[b] - m.C[c], dy = m.CfB[(size_t)m.nB + b] - m.C[(size_t)m.NP + c], dz = m.CfB[2 * (size_t)m.nB + b] - m.C[2 * (size_t)m.NP + c];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) tmp[(size_t)k * size + i] = own[k] + (g[3 * k] * dx + g[3 * k + 1] * dy + g[3 * k + 2] * dz);
+}
+__global__ void k_tau_bc_commit(int nB, int start, int size, const double* __restrict__ tmp, double* __restrict__ tauB) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    for (int k = 0; k < 6; ++k) tauB[(size_t)k * nB + start + i] = tmp[(size_t)k * size + i];
+}
+
+}  // namespace rk

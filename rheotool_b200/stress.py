@@ -1,0 +1,201 @@
+"""Python mirror of the reference's plugin surface for the stress step, on top of the C-ABI.
+
+`GpuStressModel` plays the role of one `Foam::constitutiveEq` object (constitutiveEq.H:62-351): it is
+constructed from (mesh, U/phi providers, dictionary-like model description), owns theta/tau/eigVals/
+eigVecs on the device, and exposes `correct()` and `tau()`.  `constitutive_model()` mirrors
+`constitutiveModel` + `constitutiveEq::New` (constitutiveModel.C:47-58, newConstitutiveEq.C:32-61):
+it selects by the `type` keyword, including `multiMode` (multiMode.C:73-92).
+
+Everything here calls librheo_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .cases import model_desc, scheme_ctl
+from .mesh import HostMesh
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+class RheoError(RuntimeError):
+    """The C++ shim turns a non-zero status into FatalError; here it is an exception."""
+
+
+def _check(rc):
+    if rc:
+        raise RheoError(abi.lib().rheo_gpu_last_error().decode())
+
+
+class GpuStressModel:
+    def __init__(self, mesh: HostMesh, models, schemes: abi.RheoSchemeCtl, device: int = 0):
+        self.mesh = mesh
+        self.n_modes = len(models)
+        self._models = (abi.RheoModelDesc * len(models))(*models)
+        self._schemes = schemes
+        self._h = C.c_void_p()
+        _check(abi.lib().rheo_gpu_create(mesh.desc_ptr(), C.cast(self._models, C.c_void_p), len(models), C.byref(schemes), device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            abi.lib().rheo_gpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(abi.lib().rheo_gpu_nccl_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, n_ranks: int, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        _check(abi.lib().rheo_gpu_comm_init(self._h, rank, n_ranks, buf))
+
+    # ---- state ----
+    def upload_state(self, mode=0, theta=None, tau=None, eigvals=None, eigvecs=None, theta_b=None, tau_b=None):
+        arrs = [_c(a) for a in (theta, tau, eigvals, eigvecs, theta_b, tau_b)]
+        _check(abi.lib().rheo_gpu_upload_state(self._h, mode, *[_p(a) for a in arrs]))
+
+    def upload_velocity(self, U, U_b, phi):
+        U, U_b, phi = _c(U), _c(U_b), _c(phi)
+        _check(abi.lib().rheo_gpu_upload_velocity(self._h, _p(U), _p(U_b), _p(phi)))
+        self.synchronize()
+
+    def upload_velocity_ptrs(self, U_ptr, Ub_ptr, phi_ptr):
+        """Raw host pointers (e.g. pinned torch tensors); asynchronous on the model's stream."""
+        _check(abi.lib().rheo_gpu_upload_velocity(self._h, U_ptr, Ub_ptr, phi_ptr))
+
+    def store_old_time(self):
+        _check(abi.lib().rheo_gpu_store_old_time(self._h))
+
+    def correct(self, dt: float, want_stats: bool = False):
+        """constitutiveEq::correct() with U/phi already resident on the device."""
+        stats = (abi.RheoStepStats * self.n_modes)() if want_stats else None
+        _check(abi.lib().rheo_gpu_step(self._h, float(dt), None if stats is None else C.cast(stats, C.c_void_p)))
+        return stats
+
+    def correct_host(self, U_ptr, Ub_ptr, phi_ptr, dt, new_time_step, tau_out_ptr, tau_b_out_ptr=None):
+        """upload + correct + tau download through the one-call C entry point (host buffers)."""
+        _check(abi.lib().rheo_gpu_correct(self._h, U_ptr, Ub_ptr, phi_ptr, float(dt), 1 if new_time_step else 0, tau_out_ptr, tau_b_out_ptr, None))
+
+    def download(self, field: int, mode: int = 0) -> np.ndarray:
+        n = self.mesh.n_boundary if field in (abi.FIELD_THETA_B, abi.FIELD_TAU_B) else self.mesh.n_cells
+        w = 9 if field in (abi.FIELD_EIGVALS, abi.FIELD_EIGVECS) else 6
+        out = np.zeros((n, w))
+        _check(abi.lib().rheo_gpu_download(self._h, mode, field, _p(out)))
+        return out
+
+    def theta(self, mode=0):
+        return self.download(abi.FIELD_THETA, mode)
+
+    def tau(self, mode=None):
+        """tau() of the reference: the mode's tau, or the sum over modes (multiMode::tau)."""
+        return self.download(abi.FIELD_TAU_TOTAL, 0) if mode is None else self.download(abi.FIELD_TAU, mode)
+
+    # ---- introspection ----
+    def renumbering(self):
+        perm = np.zeros(self.mesh.n_cells, dtype=np.int32)
+        nc = C.c_int32()
+        cs = np.zeros(65, dtype=np.int32)
+        _check(abi.lib().rheo_gpu_get_renumbering(self._h, _p(perm), C.byref(nc), _p(cs)))
+        return perm, cs[: nc.value + 1].copy()
+
+    def ell(self):
+        K = C.c_int32()
+        _check(abi.lib().rheo_gpu_get_ell(self._h, C.byref(K), None, None))
+        nbr = np.zeros((K.value, self.mesh.n_cells), dtype=np.int32)
+        face = np.zeros((K.value, self.mesh.n_cells), dtype=np.int32)
+        _check(abi.lib().rheo_gpu_get_ell(self._h, C.byref(K), _p(nbr), _p(face)))
+        return nbr, face
+
+    def launch_count(self) -> int:
+        return int(abi.lib().rheo_gpu_launch_count(self._h))
+
+    def last_iterations(self) -> int:
+        return int(abi.lib().rheo_gpu_last_iterations(self._h))
+
+    def set_phase_timing(self, on: bool):
+        _check(abi.lib().rheo_gpu_set_phase_timing(self._h, 1 if on else 0))
+
+    def phase_times(self):
+        out = np.zeros(7)
+        _check(abi.lib().rheo_gpu_get_phase_times(self._h, _p(out)))
+        return dict(zip(["halo_bc", "grad_theta", "assemble", "solve", "eig_tau", "tau_bc", "total"], out.tolist()))
+
+    def synchronize(self):
+        _check(abi.lib().rheo_gpu_synchronize(self._h))
+
+
+def eig_exp(theta6: np.ndarray, device: int = 0):
+    """calcEig on the GPU for an AoS symmTensor array (constitutiveEq.C:360-416)."""
+    t = np.ascontiguousarray(theta6, dtype=np.float64).reshape(-1, 6)
+    vals = np.zeros((len(t), 9))
+    vecs = np.zeros((len(t), 9))
+    _check(abi.lib().rheo_gpu_eig_exp(device, len(t), _p(t), _p(vals), _p(vecs)))
+    return vals, vecs
+
+
+# ---- run-time selection mirror -----------------------------------------------------------------------
+def models_from_dict(params: dict) -> list:
+    """`parameters` dictionary of constant/constitutiveProperties -> list of RheoModelDesc.
+    `type multiMode` expands `models` ( M1 {...} M2 {...} ) like multiMode.C:73-92."""
+    t = params.get("type")
+    if t is None:
+        raise RheoError("keyword type is undefined in dictionary parameters")
+    if t == "multiMode":
+        out = []
+        for _name, sub in params["models"]:
+            out.extend(models_from_dict(sub))
+        return out
+    if t not in abi.MODEL_NAMES:
+        raise RheoError(f"Unknown constitutiveEq type {t}\n\nValid constitutiveEq types on the GPU path are :\n{sorted(abi.MODEL_NAMES) + ['multiMode']}")
+    kw = {}
+    for src, dst in (("rho", "rho"), ("etaS", "etaS"), ("etaP", "etaP"), ("lambda", "lambda_"), ("alpha", "alpha"),
+                     ("epsilon", "epsilon"), ("zeta", "zeta"), ("L2", "L2")):
+        if src in params:
+            kw[dst] = float(params[src])
+    if t == "PTTLog":
+        kw["ptt_function"] = params.get("destructionFunctionType", "linear")
+        if kw["ptt_function"] == "generalized":
+            kw["ml_alpha"], kw["ml_beta"] = float(params["alpha"]), float(params["beta"])
+            kw.pop("alpha", None)
+            kw["ml_rtol"] = float(params.get("rTolMittagLeffler", 1e-12))
+            kw["ml_max_iter"] = int(params.get("maxIterMittagLeffler", 200))
+    return [model_desc(t, **kw)]
+
+
+def constitutive_model(mesh: HostMesh, constitutive_properties: dict, fv_schemes: dict | None = None,
+                       fv_solution: dict | None = None, device: int = 0) -> GpuStressModel:
+    """constitutiveModel constEq(U, phi): select the model(s) from `parameters.type`, the limiter from
+    divSchemes `div(phi,theta)` ("GaussDefCmpw cubista"), the solver controls from fvSolution."""
+    models = models_from_dict(constitutive_properties["parameters"])
+    fv_schemes = fv_schemes or {}
+    fv_solution = fv_solution or {}
+    div = fv_schemes.get("div(phi,theta)", "GaussDefCmpw cubista").split()
+    if div[0] == "bounded":
+        raise RheoError("bounded GaussDefCmpw is not implemented on the GPU path")
+    if div[0] != "GaussDefCmpw":
+        raise RheoError(f"div(phi,theta) must use GaussDefCmpw, got {div[0]}")
+    if fv_schemes.get("ddt", "Euler") != "Euler":
+        raise RheoError("only ddtSchemes Euler is implemented on the GPU path")
+    sol = fv_solution.get("theta", {})
+    ctl = scheme_ctl(limiter=div[1], solver=sol.get("solver", "PBiCGStab"), tolerance=float(sol.get("tolerance", 1e-10)),
+                     rel_tol=float(sol.get("relTol", 0.0)), min_iter=int(sol.get("minIter", 0)), max_iter=int(sol.get("maxIter", 1000)),
+                     relax=float(fv_solution.get("relaxationFactors", {}).get("theta", 0.0)))
+    return GpuStressModel(mesh, models, ctl, device)
