@@ -158,6 +158,10 @@ int rheo_gpu_last_iterations(const RheoGpu* h);
  * [0] halo+bc  [1] grad(theta)  [2] assemble  [3] solve  [4] eig+tau  [5] tau bc  [6] total */
 int rheo_gpu_set_phase_timing(RheoGpu* h, int32_t enabled);
 int rheo_gpu_get_phase_times(RheoGpu* h, double* ms7);
+/* per-kernel CUDA-event timing (serialises the launches; used by bench.py's roofline pass only).
+ * get: text lines "<kernel> <launches> <total ms>" */
+int rheo_gpu_set_kernel_timing(RheoGpu* h, int32_t enabled);
+int rheo_gpu_get_kernel_times(RheoGpu* h, char* buf, int32_t buflen);
 /* device buffers for callers that keep U/phi on the GPU (SoA, renumbered) */
 int rheo_gpu_stream(RheoGpu* h, void** cuda_stream);
 int rheo_gpu_synchronize(RheoGpu* h);

@@ -109,6 +109,8 @@ GPU_SYMBOLS = {
     "rheo_gpu_last_iterations": (C.c_int, [_P]),
     "rheo_gpu_set_phase_timing": (C.c_int, [_P, _I]),
     "rheo_gpu_get_phase_times": (C.c_int, [_P, _P]),
+    "rheo_gpu_set_kernel_timing": (C.c_int, [_P, _I]),
+    "rheo_gpu_get_kernel_times": (C.c_int, [_P, _P, _I]),
     "rheo_gpu_stream": (C.c_int, [_P, _P]),
     "rheo_gpu_synchronize": (C.c_int, [_P]),
     "rheo_gpu_eig_exp": (C.c_int, [_I, _I, _P, _P, _P]),

@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <map>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -125,6 +126,9 @@ struct RheoGpu {
     long launches = 0;
     int lastIters = 0;
     bool timing = false;
+    bool ktiming = false;          // per-kernel CUDA-event timing (bench.py roofline pass; serialises launches)
+    cudaEvent_t kev0 = nullptr, kev1 = nullptr;
+    std::map<std::string, std::pair<double, long>> ktimes;
     cudaEvent_t ev[8];
     double phaseMs[7] = {0, 0, 0, 0, 0, 0, 0};
     size_t stageBytes = 0;
@@ -132,10 +136,20 @@ struct RheoGpu {
 
 namespace {
 
-#define LAUNCH(h, kern, grid, block, ...)                         \
-    do {                                                          \
-        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);   \
-        (h)->launches++;                                          \
+#define LAUNCH(h, kern, grid, block, ...)                                      \
+    do {                                                                       \
+        if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
+        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                \
+        (h)->launches++;                                                       \
+        if ((h)->ktiming) {                                                    \
+            cudaEventRecord((h)->kev1, (h)->stream);                           \
+            cudaEventSynchronize((h)->kev1);                                   \
+            float ms_ = 0;                                                     \
+            cudaEventElapsedTime(&ms_, (h)->kev0, (h)->kev1);                  \
+            auto& kt_ = (h)->ktimes[#kern];                                    \
+            kt_.first += ms_;                                                  \
+            kt_.second += 1;                                                   \
+        }                                                                      \
     } while (0)
 
 Limiter make_limiter(int lim) {
@@ -628,6 +642,7 @@ int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_
     if (ctl->limiter < RHEO_LIMITER_UPWIND || ctl->limiter > RHEO_LIMITER_NONE) { delete h; return fail("The deferred limited scheme is not specified or does not exist. Valid schemes are: upwind cubista minmod smart waceb superbee none"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("cudaStreamCreate failed"); }
     for (auto& e : h->ev) cudaEventCreate(&e);
+    cudaEventCreate(&h->kev0); cudaEventCreate(&h->kev1);
     if (build_mesh(h, mesh) || alloc_fields(h, modes, n_modes)) { rheo_gpu_destroy(h); return 1; }
     *out = h;
     return 0;
@@ -789,6 +804,23 @@ int64_t rheo_gpu_launch_count(const RheoGpu* h) { return h ? h->launches : 0; }
 int rheo_gpu_last_iterations(const RheoGpu* h) { return h ? h->lastIters : -1; }
 int rheo_gpu_set_phase_timing(RheoGpu* h, int32_t enabled) { if (!h) return 1; h->timing = enabled != 0; return 0; }
 int rheo_gpu_get_phase_times(RheoGpu* h, double* ms7) { if (!h || !ms7) return 1; std::copy(h->phaseMs, h->phaseMs + 7, ms7); return 0; }
+int rheo_gpu_set_kernel_timing(RheoGpu* h, int32_t enabled) {
+    if (!h) return 1;
+    h->ktiming = enabled != 0;
+    h->ktimes.clear();
+    return 0;
+}
+int rheo_gpu_get_kernel_times(RheoGpu* h, char* buf, int32_t buflen) {
+    if (!h || !buf || buflen < 1) return 1;
+    std::string out;
+    for (auto& kv : h->ktimes) {
+        char line[256];
+        snprintf(line, sizeof line, "%s %ld %.6f\n", kv.first.c_str(), kv.second.second, kv.second.first);
+        out += line;
+    }
+    snprintf(buf, (size_t)buflen, "%s", out.c_str());
+    return 0;
+}
 int rheo_gpu_stream(RheoGpu* h, void** s) { if (!h || !s) return 1; *s = (void*)h->stream; return 0; }
 int rheo_gpu_synchronize(RheoGpu* h) {
     if (!h) return fail("null handle");

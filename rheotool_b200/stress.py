@@ -138,6 +138,24 @@ class GpuStressModel:
         _check(abi.lib().rheo_gpu_get_phase_times(self._h, _p(out)))
         return dict(zip(["halo_bc", "grad_theta", "assemble", "solve", "eig_tau", "tau_bc", "total"], out.tolist()))
 
+    def set_kernel_timing(self, on: bool):
+        _check(abi.lib().rheo_gpu_set_kernel_timing(self._h, 1 if on else 0))
+
+    def kernel_times(self) -> dict:
+        """{kernel: (launches, total_ms)} accumulated since set_kernel_timing(True)."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(abi.lib().rheo_gpu_get_kernel_times(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.rsplit(" ", 2)
+            out[name.strip("()")] = (int(cnt), float(ms))
+        return out
+
+    def stream_ptr(self) -> int:
+        s = C.c_void_p()
+        _check(abi.lib().rheo_gpu_stream(self._h, C.byref(s)))
+        return int(s.value or 0)
+
     def synchronize(self):
         _check(abi.lib().rheo_gpu_synchronize(self._h))
 

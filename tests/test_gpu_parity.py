@@ -1,0 +1,201 @@
+"""GPU parity tests proper: the CUDA path (through the C-ABI) against the CPU oracle on identical
+seeded inputs.  Tolerances are BASELINE.json's: theta/tau relative L2 <= 1e-10 after one step,
+<= 1e-6 after 100 steps (FP64)."""
+import numpy as np
+import pytest
+
+from helpers import Setup, rel_l2, tight
+from oracle import mesh_ref
+from oracle import oracle as orc
+from rheotool_b200 import abi, cases
+
+pytestmark = pytest.mark.gpu
+
+TOL_1 = 1e-10
+TOL_100 = 1e-6
+
+
+def _a_of(vals, vecs):
+    R = vecs.reshape(-1, 3, 3)
+    L = vals.reshape(-1, 3, 3)
+    return R @ L @ np.transpose(R, (0, 2, 1))
+
+
+def test_eig_exp_kernel_matches_oracle():
+    """calcEig (constitutiveEq.C:360-416): eigenvalues ascending, exp on the diagonal, A = R L R^T."""
+    from rheotool_b200.stress import eig_exp
+    rng = np.random.default_rng(0)
+    n = 20000
+    th = rng.standard_normal((n, 6)) * np.array([1.0, 0.5, 0.3, 1.0, 0.4, 1.0])
+    th[:100] = 0.0                               # isotropic theta = 0 (t = 0 of every tutorial)
+    th[100:200, [1, 2, 4]] = 0.0                 # diagonal
+    th[200:300] = np.array([0.3, 0, 0, 0.3, 0, -0.2])   # two equal eigenvalues
+    th[300:400, [2, 4]] = 0.0                    # 2-D tensors
+    gv, gV = eig_exp(th)
+    ov, oV = orc.calc_eig(th)
+    assert np.abs(gv - ov).max() <= 1e-12 * np.abs(ov).max()
+    assert rel_l2(_a_of(gv, gV), _a_of(ov, oV)) < 1e-13
+    R = gV.reshape(-1, 3, 3)
+    assert np.abs(R @ np.transpose(R, (0, 2, 1)) - np.eye(3)).max() < 1e-13
+    d = np.stack([gv[:, 0], gv[:, 4], gv[:, 8]], 1)
+    assert (np.diff(d, axis=1) >= 0).all()       # ascending, like Eigen::SelfAdjointEigenSolver
+    assert np.abs(gv[:, [1, 2, 3, 5, 6, 7]]).max() == 0.0
+
+
+def _one_step(spec, cold=False, schemes=None, steps=1):
+    s = Setup(spec, cold_start=cold)
+    sc = schemes or tight(spec.schemes)
+    oc = s.oracle(sc)
+    g = s.gpu(sc)
+    for _ in range(steps):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    return s, oc, g
+
+
+CASES = {
+    "C1-OldroydB-2D": lambda: cases.by_name("C1", 0.25),
+    "C2-PTT-contraction-2D": lambda: cases.by_name("C2", 1 / 9),
+    "C3-Giesekus-contraction-3D": lambda: cases.by_name("C3", 3 / 19),
+    "C4-multimode-Giesekus": lambda: cases.by_name("C4", 14 / 252),
+    "C5-FENEP-cavity": lambda: cases.by_name("C5", 18 / 400),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_one_step_parity(name):
+    spec = CASES[name]()
+    s, oc, g = _one_step(spec)
+    for mi in range(len(spec.models)):
+        for fld, label in ((abi.FIELD_THETA, "theta"), (abi.FIELD_TAU, "tau")):
+            err = rel_l2(g.download(fld, mi), oc.get(0, mi, fld))
+            assert err <= TOL_1, f"{name} mode {mi} {label}: rel L2 {err:.3e}"
+        # conformation tensor from the stored eigen-pairs (R itself is only defined up to sign/order)
+        err = rel_l2(_a_of(g.download(abi.FIELD_EIGVALS, mi), g.download(abi.FIELD_EIGVECS, mi)),
+                     _a_of(oc.get(0, mi, abi.FIELD_EIGVALS), oc.get(0, mi, abi.FIELD_EIGVECS)))
+        assert err <= TOL_1
+        tb_g, tb_o = g.download(abi.FIELD_TAU_B, mi), oc.get(0, mi, abi.FIELD_TAU_B)
+        assert rel_l2(tb_g, tb_o) <= TOL_1, "tau boundary (linearExtrapolation / zeroGradient)"
+        assert rel_l2(g.download(abi.FIELD_THETA_B, mi), oc.get(0, mi, abi.FIELD_THETA_B)) <= TOL_1
+    assert rel_l2(g.tau(), oc.get(0, 0, abi.FIELD_TAU_TOTAL)) <= TOL_1   # multiMode::tau()
+
+
+def test_theta_zero_start():
+    """Cold start of every tutorial: theta = 0 and no eigVals/eigVecs files, so READ_IF_PRESENT gives
+    R = Lambda = I (Oldroyd_BLog.C:76-113).  Isotropic cells: omega ~ 1/1e-16 times theta = 0 must stay
+    finite.  (With theta0 != 0 and identity eigen-pairs the reference algorithm
+    itself overflows, so that combination is not a parity case.)"""
+    spec = cases.by_name("C2", 1 / 9)
+    s = Setup(spec, cold_start=True)
+    s.theta0[:] = 0.0
+    sc = tight(spec.schemes)
+    oc, g = s.oracle(sc), s.gpu(sc)
+    for _ in range(3):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    th_g, th_o = g.theta(), oc.get(0, 0, abi.FIELD_THETA)
+    assert np.isfinite(th_g).all()
+    assert rel_l2(th_g, th_o) <= 1e-9
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-9
+
+
+@pytest.mark.parametrize("limiter", ["upwind", "minmod", "smart", "waceb", "superbee", "none"])
+def test_limiter_table(limiter):
+    """every row of limiters.H:48-98"""
+    spec = cases.by_name("C3", 2 / 19)
+    sc = tight(spec.schemes)
+    sc.limiter = abi.LIMITER[limiter]
+    s, oc, g = _one_step(spec, schemes=sc)
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
+
+
+def test_tutorial_tolerance_same_iterations_as_oracle_on_renumbered_mesh():
+    """With the tutorial tolerance (1e-10) the GPU's colour-parallel DILU is exactly the sequential
+    DILU of the oracle run on the renumbered mesh: same iteration counts, same residual histories."""
+    spec = cases.by_name("C3", 3 / 19)
+    s = Setup(spec, cfl=2.0)   # larger CFL so that several Krylov iterations are needed
+    g = s.gpu()
+    perm, cstart = g.renumbering()
+    rm = mesh_ref.renumbered_mesh(mesh_ref.from_host_mesh(s.mesh), perm)
+    desc = mesh_ref.to_desc(rm, abi)
+    oc = orc.OracleCase([desc], spec.models, spec.schemes)
+    oc.set_state(0, 0, s.theta0[perm], s.tau0[perm], s.eigvals[perm], s.eigvecs[perm])
+    fa = rm.face_addr
+    phi_r = np.where(fa > 0, s.phi[np.abs(fa) - 1], -s.phi[np.abs(fa) - 1])
+    oc.set_velocity(0, s.U[perm], s.Ub, phi_r)
+    so = (abi.RheoStepStats * 1)()
+    oc.store_old_time(); oc.step(s.dt, so)
+    g.store_old_time(); sg = g.correct(s.dt, want_stats=True)
+    assert list(sg[0].n_iterations) == list(so[0].n_iterations)
+    assert max(so[0].n_iterations) >= 2
+    np.testing.assert_allclose(list(sg[0].initial_residual), list(so[0].initial_residual), rtol=1e-9)
+    th_o = np.empty_like(s.theta0); th_o[perm] = oc.get(0, 0, abi.FIELD_THETA)
+    assert rel_l2(g.theta(), th_o) <= 1e-12
+    # and against the oracle on the ORIGINAL numbering the converged fields agree to the solver tolerance
+    oc0 = s.oracle(); oc0.store_old_time(); oc0.step(s.dt)
+    assert rel_l2(g.theta(), oc0.get(0, 0, abi.FIELD_THETA)) <= 1e-8
+
+
+def test_hundred_steps():
+    spec = cases.by_name("C2", 1 / 9)
+    s, oc, g = _one_step(spec, steps=100, schemes=tight(spec.schemes, 1e-13))
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_100
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_100
+
+
+def test_inner_iterations_keep_old_time():
+    """nInIter > 1: correct() twice per time step with the same theta.oldTime() (rheoFoam.C:97-154)."""
+    spec = cases.by_name("C3", 2 / 19)
+    s = Setup(spec)
+    sc = tight(spec.schemes)
+    oc, g = s.oracle(sc), s.gpu(sc)
+    oc.store_old_time(); g.store_old_time()
+    for _ in range(2):
+        oc.step(s.dt); g.correct(s.dt)
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
+    assert rel_l2(g.download(abi.FIELD_THETA_OLD), s.theta0) == 0.0
+
+
+def test_relax_factor_one_is_folded():
+    """relaxationFactors.equations.theta 1 (Contraction41/Cavity tutorials): fvMatrix::relax path."""
+    spec = cases.by_name("C2", 1 / 9)
+    assert spec.schemes.relax == 1.0
+    sc = tight(spec.schemes); sc.relax = 0.7
+    s, oc, g = _one_step(spec, schemes=sc)
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
+
+
+def test_renumbering_and_ell_bit_exact():
+    """integer mesh renumbering / addressing must be bit-exact (BASELINE.json)."""
+    spec = cases.by_name("C2", 1 / 9)
+    s = Setup(spec)
+    g = s.gpu()
+    perm, cstart = g.renumbering()
+    rm = mesh_ref.from_host_mesh(s.mesh)
+    perm_ref, colour_ref, cstart_ref = mesh_ref.colour_renumber(rm.n_cells, rm.owner, rm.neighbour)
+    assert np.array_equal(perm, perm_ref) and np.array_equal(cstart, cstart_ref)
+    nbr, face = g.ell()
+    nbr_ref, face_ref = mesh_ref.ell_tables(rm, perm_ref)
+    assert np.array_equal(nbr, nbr_ref) and np.array_equal(face, face_ref)
+
+
+def test_upload_download_round_trip_is_exact():
+    spec = cases.by_name("C3", 2 / 19)
+    s = Setup(spec)
+    g = s.gpu()
+    assert np.array_equal(g.theta(), s.theta0)
+    assert np.array_equal(g.download(abi.FIELD_EIGVECS), s.eigvecs)
+    assert np.array_equal(g.download(abi.FIELD_EIGVALS), s.eigvals)
+
+
+def test_errors_are_reported_not_swallowed():
+    from rheotool_b200.stress import GpuStressModel, RheoError
+    spec = cases.by_name("C3", 2 / 19)
+    s = Setup(spec)
+    bad = tight(spec.schemes); bad.limiter = 99
+    with pytest.raises(RheoError, match="deferred limited scheme"):
+        GpuStressModel(s.mesh, spec.models, bad)
+    g = s.gpu()
+    with pytest.raises(RheoError):
+        g.correct(-1.0)
