@@ -19,7 +19,7 @@
 #include <string>
 #include <vector>
 
-#include "kernels.cuh"
+#include "krylov.cuh"
 #include "rheo_gpu.h"
 
 using namespace rk;
@@ -116,9 +116,11 @@ struct RheoGpu {
     DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_grad, d_stage, d_tmpB;
     std::vector<ModeDev> modes;
     // Krylov
-    DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ctl, d_partials, d_red, d_counter;
-    int* h_nActive = nullptr;      // pinned
-    KrylovCtl* h_ctl = nullptr;    // pinned
+    DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ks, d_partials, d_red, d_counter, d_bcells;
+    KrylovShared* h_ks = nullptr;  // pinned mirror of the device control block
+    int specIters = 1;             // Krylov iterations launched speculatively per batch (= last step's count)
+    int maxBlocks = 148 * 6;       // SM count x resident CTAs (set at create)
+    int nBcells = 0;               // cells that own at least one ghost (processor) slot
     // comm
     void* comm = nullptr;
     int rank = 0, nRanks = 1;
@@ -297,6 +299,16 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
             nbrA[(size_t)s * h->NS + c] = (v >= 0) ? v : std::min(c, N - 1);
         }
 
+    {   // cells owning ghost slots (k_ghost)
+        std::vector<int> bc;
+        for (int c = 0; c < N; ++c) {
+            bool g = false;
+            for (int s = 0; s < K; ++s) if (h->h_nbr[(size_t)s * h->NS + c] >= N) g = true;
+            if (g) bc.push_back(c);
+        }
+        h->nBcells = (int)bc.size();
+        if (upload(h->d_bcells, bc)) return 1;
+    }
     // ---- geometry in device order
     std::vector<double> Sf(3 * (size_t)nF), w(nF), C(3 * (size_t)h->NP, 0.0), V(N), rV(N), CfB(3 * (size_t)nB);
     for (int q = 0; q < nF; ++q) {
@@ -386,12 +398,11 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         return 1;
     for (DevBuf* b : {&h->d_r, &h->d_r0, &h->d_p, &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t}) zero(h, *b);
     const int nBlocks = cdiv(h->N, BLOCK);
-    if (h->d_ctl.alloc(MAX_RHS * sizeof(KrylovCtl)) || h->d_partials.alloc((size_t)nBlocks * MAX_RED * d8) || h->d_red.alloc(4 * MAX_RED * d8) ||
+    if (h->d_ks.alloc(sizeof(KrylovShared)) || h->d_partials.alloc((size_t)nBlocks * MAX_RED * d8) || h->d_red.alloc(4 * MAX_RED * d8) ||
         h->d_counter.alloc(sizeof(unsigned)))
         return 1;
-    zero(h, h->d_counter); zero(h, h->d_red); zero(h, h->d_ctl);
-    CK(cudaHostAlloc((void**)&h->h_nActive, sizeof(int), cudaHostAllocDefault));
-    CK(cudaHostAlloc((void**)&h->h_ctl, MAX_RHS * sizeof(KrylovCtl), cudaHostAllocDefault));
+    zero(h, h->d_counter); zero(h, h->d_red); zero(h, h->d_ks);
+    CK(cudaHostAlloc((void**)&h->h_ks, sizeof(KrylovShared), cudaHostAllocDefault));
     const size_t hb = (size_t)std::max(h->H, 1) * MAX_RHS * d8;
     if (h->d_send.alloc(hb) || h->d_recv.alloc(hb)) return 1;
     CK(cudaStreamSynchronize(h->stream));
@@ -431,73 +442,10 @@ int all_reduce(RheoGpu* h, double* buf, int n) {
     return 0;
 }
 
-// ---------------------------------------------------------------- batched PBiCGStab + colour-parallel DILU
-template <int CH>
-int precondition(RheoGpu* h, int nrhs, const double* rIn, double* w) {
-    const KrylovCtl* ctl = h->d_ctl.as<KrylovCtl>();
-    const int nc = h->nColours;
-    for (int k = 0; k < nc; ++k) {
-        const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
-        if (c1 > c0) LAUNCH(h, (k_sweep_fwd<CH>), cdiv(c1 - c0, BLOCK), BLOCK, h->mv, c0, c1, nrhs, ctl, 0, h->d_rD.as<double>(), h->d_Fs.as<double>(), rIn, w);
-    }
-    for (int k = nc - 2; k >= 0; --k) {
-        const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
-        if (c1 > c0) LAUNCH(h, (k_sweep_bwd<CH>), cdiv(c1 - c0, BLOCK), BLOCK, h->mv, c0, c1, nrhs, ctl, 0, h->d_rD.as<double>(), h->d_Fs.as<double>(), w);
-    }
-    return 0;
-}
+// persistent-style grids: at most `ctasPerSm` CTAs per SM, each striding over the cells
+inline int grid_for(RheoGpu* h, long n) { return std::max(1, std::min(cdiv(n, BLOCK), h->maxBlocks)); }
 
-template <int CH>
-int solve_batch(RheoGpu* h, const RhsPtrs& rp, int* itersOut) {
-    const int nrhs = rp.n, N = h->N, NP = h->NP;
-    const int grid = cdiv(N, BLOCK);
-    KrylovCtl* ctl = h->d_ctl.as<KrylovCtl>();
-    double* part = h->d_partials.as<double>();
-    double* red = h->d_red.as<double>();
-    double *redA = red, *redB = red + MAX_RED, *redC = red + 2 * MAX_RED, *redD = red + 3 * MAX_RED;
-    unsigned* counter = h->d_counter.as<unsigned>();
-    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *p = h->d_p.as<double>(), *y = h->d_y.as<double>(), *v = h->d_v.as<double>(),
-           *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
-    const SolveCtl sc{h->ctl.tolerance, h->ctl.rel_tol, h->ctl.min_iter, h->ctl.max_iter};
-    const double* diag = h->d_diag.as<double>();
-    const double* Fs = h->d_Fs.as<double>();
-
-    // psi halo, gAverage(psi), initial residual + normFactor
-    {
-        PlaneList pl; pl.n = nrhs;
-        for (int q = 0; q < nrhs; ++q) pl.p[q] = rp.psi[q];
-        if (halo_exchange(h, pl)) return 1;
-    }
-    LAUNCH(h, (k_sum_psi<CH>), grid, BLOCK, N, rp, part, redA, counter);
-    if (all_reduce(h, redA, nrhs)) return 1;
-    LAUNCH(h, (k_krylov_init<CH>), grid, BLOCK, h->mv, rp, diag, Fs, redA, (double)h->nGlobalCells, r, r0, part, redB, counter);
-    if (all_reduce(h, redB, 3 * nrhs)) return 1;
-    LAUNCH(h, k_ctl_init, 1, 32, nrhs, ctl, redB, sc, h->h_nActive);
-    CK(cudaStreamSynchronize(h->stream));
-    int iters = 0;
-    while (*h->h_nActive > 0) {
-        LAUNCH(h, (k_update_p<CH>), grid, BLOCK, N, NP, nrhs, ctl, r, v, p);
-        if (precondition<CH>(h, nrhs, p, y)) return 1;
-        if (halo_planes(h, y, nrhs)) return 1;
-        LAUNCH(h, (k_spmv_dot<CH, 0>), grid, BLOCK, h->mv, nrhs, ctl, diag, Fs, y, v, r0, part, redA, counter);
-        if (all_reduce(h, redA, nrhs)) return 1;
-        LAUNCH(h, (k_make_s<CH>), grid, BLOCK, N, NP, nrhs, ctl, redA, r, v, sv, part, redB, counter);
-        if (all_reduce(h, redB, nrhs)) return 1;
-        LAUNCH(h, k_ctl_half, 1, 32, nrhs, ctl, redA, redB, sc);
-        if (precondition<CH>(h, nrhs, sv, z)) return 1;
-        if (halo_planes(h, z, nrhs)) return 1;
-        LAUNCH(h, (k_spmv_dot<CH, 1>), grid, BLOCK, h->mv, nrhs, ctl, diag, Fs, z, t, sv, part, redC, counter);
-        if (all_reduce(h, redC, 2 * nrhs)) return 1;
-        LAUNCH(h, (k_update_x_r<CH>), grid, BLOCK, N, NP, rp, ctl, redC, y, z, sv, t, r0, r, part, redD, counter);
-        if (all_reduce(h, redD, 2 * nrhs)) return 1;
-        LAUNCH(h, k_ctl_end, 1, 32, nrhs, ctl, redC, redD, sc, h->h_nActive);
-        CK(cudaStreamSynchronize(h->stream));
-        ++iters;
-        if (iters > h->ctl.max_iter + 2) break;
-    }
-    *itersOut = iters;
-    return 0;
-}
+#include "solve.inl"
 
 int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
@@ -549,15 +497,14 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 rp.n++;
             }
         int iters = 0;
-        int rc = (h->nComp == 6) ? solve_batch<6>(h, rp, &iters) : solve_batch<4>(h, rp, &iters);
+        int rc = (h->nComp == 6) ? solve_batch<6>(h, rp, m1 - m0, &iters) : solve_batch<4>(h, rp, m1 - m0, &iters);
         if (rc) return rc;
-        CK(cudaMemcpyAsync(h->h_ctl, h->d_ctl.p, rp.n * sizeof(KrylovCtl), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        h->specIters = std::max(1, iters);
         int q = 0;
         for (int mi = m0; mi < m1; ++mi) {
             if (stats) std::memset(&stats[mi], 0, sizeof(RheoStepStats));
             for (int j = 0; j < h->nComp; ++j, ++q) {
-                const KrylovCtl& k = h->h_ctl[q];
+                const KrylovCtl& k = h->h_ks->ctl[q];
                 h->lastIters = std::max(h->lastIters, k.iters);
                 if (stats) {
                     const int cmp = h->comps[j];
@@ -641,6 +588,7 @@ int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_
     h->lim = make_limiter(ctl->limiter);
     if (ctl->limiter < RHEO_LIMITER_UPWIND || ctl->limiter > RHEO_LIMITER_NONE) { delete h; return fail("The deferred limited scheme is not specified or does not exist. Valid schemes are: upwind cubista minmod smart waceb superbee none"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("cudaStreamCreate failed"); }
+    { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->maxBlocks = sms * 6; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     cudaEventCreate(&h->kev0); cudaEventCreate(&h->kev1);
     if (build_mesh(h, mesh) || alloc_fields(h, modes, n_modes)) { rheo_gpu_destroy(h); return 1; }
@@ -656,12 +604,11 @@ void rheo_gpu_destroy(RheoGpu* h) {
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_grad, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
-                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ctl, &h->d_partials, &h->d_red, &h->d_counter})
+                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
     for (ModeDev& md : h->modes)
         for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals}) b->release();
-    if (h->h_nActive) cudaFreeHost(h->h_nActive);
-    if (h->h_ctl) cudaFreeHost(h->h_ctl);
+    if (h->h_ks) cudaFreeHost(h->h_ks);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;

@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(BLOCK) k_convect(MeshView m, Limiter lim, int 
                 F = 0.0;
             }
         }
-        if (writeMatrix) Fs[(size_t)s * m.NS + c] = (nb >= 0) ? F : 0.0;
+        if (writeMatrix) Fs[(size_t)s * m.NS + c] = (nb >= 0) ? fmin(F, 0.0) : 0.0;   // row coefficient A[c][nb]
     }
     double add[6] = {0, 0, 0, 0, 0, 0};
     if (relax > 0) {   // EXT-OF9 fvMatrix::relax
@@ -332,10 +332,7 @@ __global__ void __launch_bounds__(BLOCK) k_convect(MeshView m, Limiter lim, int 
     }
 }
 
-// ---------------------------------------------------------------- Krylov building blocks (batched RHS, one shared matrix)
-// row c of A:  diag[c] x[c] + sum_slots min(Fs,0) x[nbrA]      (lduMatrix::Amul incl. processor interfaces via ghosts)
-struct VecSet { double* v; };   // [nrhs][NP] contiguous planes
-
+// ---------------------------------------------------------------- Krylov control block (kernels in krylov.cuh)
 struct KrylovCtl {   // one per RHS, device resident
     double rho, rhoOld, alpha, omega, beta, normFactor, initRes, finRes;
     int state;   // 0 active, 1 converged at the half step (needs psi += alpha y), 2 done
@@ -343,283 +340,6 @@ struct KrylovCtl {   // one per RHS, device resident
     int singular;
     int pad;
 };
-
-// sum of psi (for gAverage) ---------------------------------------------------
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_sum_psi(int N, RhsPtrs rp, double* partials, double* out, unsigned* counter) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int r0 = 0; r0 < rp.n; r0 += CH) {
-        double v[CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) v[j] = (c < N) ? rp.psi[r0 + j][c] : 0.0;
-        block_reduce_to_partials<CH>(v, partials, r0, rp.n);
-    }
-    finalize_partials(partials, rp.n, out, counter);
-}
-
-// initial residual: v = A psi, r = b - v, r0 = r; sums: [0] normFactor terms, [1] |r|, [2] r0.r
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ Fs,
-                                                        const double* __restrict__ sumPsi, double nGlobal, double* __restrict__ r, double* __restrict__ r0v,
-                                                        double* partials, double* out, unsigned* counter) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = c < m.N;
-    double d = 0, rowsum = 0;
-    if (act) {
-        d = diag[c];
-        rowsum = d;
-        for (int s = 0; s < m.K; ++s) rowsum += fmin(Fs[(size_t)s * m.NS + c], 0.0);
-    }
-    for (int q0 = 0; q0 < rp.n; q0 += CH) {
-        double red[3 * CH];
-#pragma unroll
-        for (int j = 0; j < 3 * CH; ++j) red[j] = 0.0;
-        if (act) {
-            double acc[CH];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) acc[j] = d * rp.psi[q0 + j][c];
-            for (int s = 0; s < m.K; ++s) {
-                const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
-                const int nb = m.nbrA[(size_t)s * m.NS + c];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) acc[j] += a * rp.psi[q0 + j][nb];
-            }
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const double bb = rp.b[q0 + j][c];
-                const double rr = bb - acc[j];
-                r[(size_t)(q0 + j) * m.NP + c] = rr;
-                r0v[(size_t)(q0 + j) * m.NP + c] = rr;
-                const double t = rowsum * (sumPsi[q0 + j] / nGlobal);
-                red[3 * j] = fabs(acc[j] - t) + fabs(bb - t);
-                red[3 * j + 1] = fabs(rr);
-                red[3 * j + 2] = rr * rr;
-            }
-        }
-        block_reduce_to_partials<3 * CH>(red, partials, 3 * q0, 3 * rp.n);
-    }
-    finalize_partials(partials, 3 * rp.n, out, counter);
-}
-
-// p = r + beta (p - omega v)   (first iteration p = r)
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nrhs, const KrylovCtl* __restrict__ ctl, const double* __restrict__ r,
-                                                     const double* __restrict__ v, double* __restrict__ p) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    for (int q = 0; q < nrhs; ++q) {
-        const KrylovCtl k = ctl[q];
-        if (k.state != 0) continue;
-        const size_t i = (size_t)q * NP + c;
-        p[i] = (k.iters == 0) ? r[i] : r[i] + k.beta * (p[i] - k.omega * v[i]);
-    }
-}
-
-// DILU forward phase for the cells of one colour: w = rD (r - sum_{lower} A[c][l] w[l])
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_sweep_fwd(MeshView m, int c0, int c1, int nrhs, const KrylovCtl* __restrict__ ctl, int needState,
-                                                      const double* __restrict__ rD, const double* __restrict__ Fs, const double* __restrict__ r, double* __restrict__ w) {
-    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c1) return;
-    const double d = rD[c];
-    for (int q0 = 0; q0 < nrhs; q0 += CH) {
-        double acc[CH];
-        bool on[CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) { on[j] = ctl[q0 + j].state == needState; acc[j] = on[j] ? r[(size_t)(q0 + j) * m.NP + c] : 0.0; }
-        if (c0 > 0) {
-            for (int s = 0; s < m.K; ++s) {
-                const int nb = m.nbrA[(size_t)s * m.NS + c];
-                if (nb >= c) continue;
-                const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
-#pragma unroll
-                for (int j = 0; j < CH; ++j) if (on[j]) acc[j] -= a * w[(size_t)(q0 + j) * m.NP + nb];
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < CH; ++j) if (on[j]) w[(size_t)(q0 + j) * m.NP + c] = d * acc[j];
-    }
-}
-// DILU backward phase: w[c] -= rD[c] sum_{upper, local} A[c][u] w[u]
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_sweep_bwd(MeshView m, int c0, int c1, int nrhs, const KrylovCtl* __restrict__ ctl, int needState,
-                                                      const double* __restrict__ rD, const double* __restrict__ Fs, double* __restrict__ w) {
-    const int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= c1) return;
-    const double d = rD[c];
-    for (int q0 = 0; q0 < nrhs; q0 += CH) {
-        double acc[CH];
-        bool on[CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) { on[j] = ctl[q0 + j].state == needState; acc[j] = 0.0; }
-        for (int s = 0; s < m.K; ++s) {
-            const int nb = m.nbrA[(size_t)s * m.NS + c];
-            if (nb <= c || nb >= m.N) continue;
-            const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
-#pragma unroll
-            for (int j = 0; j < CH; ++j) if (on[j]) acc[j] += a * w[(size_t)(q0 + j) * m.NP + nb];
-        }
-#pragma unroll
-        for (int j = 0; j < CH; ++j) if (on[j]) w[(size_t)(q0 + j) * m.NP + c] -= d * acc[j];
-    }
-}
-
-// y = A x with NDOT fused dot products per RHS:
-//   mode 0: out[q]       = r0 . y                         (rA0AyA)
-//   mode 1: out[2q],[2q+1] = y . y , y . s                (tAtA, tAsA)
-template <int CH, int MODE>
-__global__ void __launch_bounds__(BLOCK) k_spmv_dot(MeshView m, int nrhs, const KrylovCtl* __restrict__ ctl, const double* __restrict__ diag, const double* __restrict__ Fs,
-                                                     const double* __restrict__ x, double* __restrict__ y, const double* __restrict__ other,
-                                                     double* partials, double* out, unsigned* counter) {
-    constexpr int ND = MODE == 0 ? 1 : 2;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = c < m.N;
-    const double d = act ? diag[c] : 0.0;
-    for (int q0 = 0; q0 < nrhs; q0 += CH) {
-        double red[ND * CH];
-#pragma unroll
-        for (int j = 0; j < ND * CH; ++j) red[j] = 0.0;
-        if (act) {
-            double acc[CH];
-            bool on[CH];
-#pragma unroll
-            for (int j = 0; j < CH; ++j) { on[j] = ctl[q0 + j].state == 0; acc[j] = on[j] ? d * x[(size_t)(q0 + j) * m.NP + c] : 0.0; }
-            for (int s = 0; s < m.K; ++s) {
-                const double a = fmin(Fs[(size_t)s * m.NS + c], 0.0);
-                const int nb = m.nbrA[(size_t)s * m.NS + c];
-#pragma unroll
-                for (int j = 0; j < CH; ++j) if (on[j]) acc[j] += a * x[(size_t)(q0 + j) * m.NP + nb];
-            }
-#pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                if (!on[j]) continue;
-                const size_t i = (size_t)(q0 + j) * m.NP + c;
-                y[i] = acc[j];
-                const double o = other[i];
-                if (MODE == 0) red[j] = o * acc[j];
-                else { red[2 * j] = acc[j] * acc[j]; red[2 * j + 1] = acc[j] * o; }
-            }
-        }
-        block_reduce_to_partials<ND * CH>(red, partials, ND * q0, ND * nrhs);
-    }
-    finalize_partials(partials, ND * nrhs, out, counter);
-}
-
-// s = r - alpha v ; out[q] = sum |s|        (alpha = rho / (r0.v) computed here, stored by thread 0 of block 0)
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_make_s(int N, int NP, int nrhs, KrylovCtl* __restrict__ ctl, const double* __restrict__ dots, const double* __restrict__ r,
-                                                   const double* __restrict__ v, double* __restrict__ sv, double* partials, double* out, unsigned* counter) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int q0 = 0; q0 < nrhs; q0 += CH) {
-        double red[CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            red[j] = 0.0;
-            const KrylovCtl k = ctl[q0 + j];
-            if (k.state != 0) continue;
-            const double alpha = k.rho / dots[q0 + j];
-            if (c < N) {
-                const size_t i = (size_t)(q0 + j) * NP + c;
-                const double x = r[i] - alpha * v[i];
-                sv[i] = x;
-                red[j] = fabs(x);
-            }
-        }
-        block_reduce_to_partials<CH>(red, partials, q0, nrhs);
-    }
-    finalize_partials(partials, nrhs, out, counter);
-}
-
-// psi += alpha y + omega z ; r = s - omega t ; out[2q] = sum|r| , out[2q+1] = r0.r      (state 0)
-// psi += alpha y                                                                        (state 1)
-template <int CH>
-__global__ void __launch_bounds__(BLOCK) k_update_x_r(int N, int NP, RhsPtrs rp, const KrylovCtl* __restrict__ ctl, const double* __restrict__ dots2,
-                                                       const double* __restrict__ y, const double* __restrict__ z, const double* __restrict__ sv,
-                                                       const double* __restrict__ t, const double* __restrict__ r0v, double* __restrict__ r,
-                                                       double* partials, double* out, unsigned* counter) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    for (int q0 = 0; q0 < rp.n; q0 += CH) {
-        double red[2 * CH];
-#pragma unroll
-        for (int j = 0; j < CH; ++j) {
-            red[2 * j] = 0.0; red[2 * j + 1] = 0.0;
-            const KrylovCtl k = ctl[q0 + j];
-            if (k.state == 2 || c >= N) continue;
-            const size_t i = (size_t)(q0 + j) * NP + c;
-            if (k.state == 1) { rp.psi[q0 + j][c] += k.alpha * y[i]; continue; }
-            const double omega = dots2[2 * (q0 + j) + 1] / dots2[2 * (q0 + j)];
-            rp.psi[q0 + j][c] += k.alpha * y[i] + omega * z[i];
-            const double rr = sv[i] - omega * t[i];
-            r[i] = rr;
-            red[2 * j] = fabs(rr);
-            red[2 * j + 1] = r0v[i] * rr;
-        }
-        block_reduce_to_partials<2 * CH>(red, partials, 2 * q0, 2 * rp.n);
-    }
-    finalize_partials(partials, 2 * rp.n, out, counter);
-}
-
-// ---- control kernels (one small block; mirror EXT-OF9 PBiCGStab's scalar logic per component)
-struct SolveCtl { double tol, relTol; int minIter, maxIter; };
-__device__ __forceinline__ bool conv_check(double fin, double init, const SolveCtl& sc) {
-    return fin < sc.tol || (sc.relTol > 1e-20 && fin < sc.relTol * init);
-}
-__global__ void k_ctl_init(int nrhs, KrylovCtl* ctl, const double* red3, SolveCtl sc, int* nActiveOut) {
-    __shared__ int cnt;
-    if (threadIdx.x == 0) cnt = 0;
-    __syncthreads();
-    const int q = threadIdx.x;
-    if (q < nrhs) {
-        KrylovCtl k;
-        k.normFactor = red3[3 * q] + 1e-20;
-        k.initRes = red3[3 * q + 1] / k.normFactor;
-        k.finRes = k.initRes;
-        k.rho = red3[3 * q + 2];
-        k.rhoOld = 0; k.alpha = 0; k.omega = 0; k.beta = 0; k.iters = 0; k.singular = 0; k.pad = 0;
-        k.state = (sc.minIter > 0 || !conv_check(k.finRes, k.initRes, sc)) ? 0 : 2;
-        if (k.state == 0 && !(fabs(k.rho) > 1e-300)) { k.state = 2; k.singular = 1; }
-        ctl[q] = k;
-        if (k.state == 0) atomicAdd(&cnt, 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *nActiveOut = cnt;
-}
-// after s: alpha, half-step convergence
-__global__ void k_ctl_half(int nrhs, KrylovCtl* ctl, const double* dotsV, const double* sumS, SolveCtl sc) {
-    const int q = threadIdx.x;
-    if (q >= nrhs) return;
-    KrylovCtl k = ctl[q];
-    if (k.state != 0) return;
-    k.alpha = k.rho / dotsV[q];
-    k.finRes = sumS[q] / k.normFactor;
-    if (conv_check(k.finRes, k.initRes, sc)) k.state = 1;
-    ctl[q] = k;
-}
-// end of iteration
-__global__ void k_ctl_end(int nrhs, KrylovCtl* ctl, const double* dots2, const double* red2, SolveCtl sc, int* nActiveOut) {
-    __shared__ int cnt;
-    if (threadIdx.x == 0) cnt = 0;
-    __syncthreads();
-    const int q = threadIdx.x;
-    if (q < nrhs) {
-        KrylovCtl k = ctl[q];
-        if (k.state == 1) { k.iters++; k.state = 2; }
-        else if (k.state == 0) {
-            k.omega = dots2[2 * q + 1] / dots2[2 * q];
-            k.finRes = red2[2 * q] / k.normFactor;
-            k.rhoOld = k.rho;
-            k.rho = red2[2 * q + 1];
-            const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
-            if (!cont) k.state = 2;
-            else if (!(fabs(k.rho) > 1e-300) || !(fabs(k.omega) > 1e-300)) { k.state = 2; k.singular = 1; }
-            else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);
-        }
-        ctl[q] = k;
-        if (k.state == 0) atomicAdd(&cnt, 1);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *nActiveOut = cnt;
-}
 
 // ---------------------------------------------------------------- eig + exp + tau
 __global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp, const double* __restrict__ theta, const double* __restrict__ fFene,

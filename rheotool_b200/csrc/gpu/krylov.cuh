@@ -1,0 +1,446 @@
+// krylov.cuh — batched multi-RHS PBiCGStab with colour-parallel DILU, fused for HBM traffic.
+//
+// EXT-OF9 semantics restated: PBiCGStab::solve, DILUPreconditioner::precondition, lduMatrix::Amul /
+// sumA / normFactor (in-repo restatement of the residual norm:
+// of90/src/libs/sparseMatrixSolvers/segregated/sparseSolver.C:152-179).
+//
+// Layout: the NR right-hand sides of one mode (NR = 4 in 2-D, 6 in 3-D: the valid components of
+// theta) are INTERLEAVED per cell, X[(mode*NP + cell)*NR + j], so one 16-byte load fetches two RHS
+// and a neighbour gather uses whole 32-byte sectors.  theta itself (psi) stays in SoA planes.
+// Matrix: diag[c], rD[c] = 1/diag[c] (DILU of an upwind matrix: upper*lower == 0 on every face),
+// A[s][c] = min(signed outflow flux, 0) in slot-major ELL with neighbour table nbrA.
+//
+// Cells are numbered colour by colour.  One preconditioned product v = A M^-1 p is
+//     y = rD p                                  (written by the kernel that produced p)
+//     k_fwd   colours 1..nc-1 :  y[c] -= rD[c] sum_{nb<c} A y[nb]
+//     k_bwd   colours nc-2..1 :  y[c] -= rD[c] sum_{c<nb<N} A y[nb]
+//     k_spmv<FUSE=1> colour 0 :  S = sum_{local nb} A y[nb]; y[c] -= rD[c] S; v[c] = diag[c] y[c] + S
+//     k_spmv<FUSE=0> the rest :  v[c] = diag[c] y[c] + sum A y[nb]
+// (for the 2 colours of a hex mesh: 3 half-size launches).  Ghost (processor) neighbours are added by
+// k_ghost after the halo exchange so that the interior work never waits for NCCL.
+// Scalar control (alpha, omega, beta, convergence per RHS) runs in the last-block epilogue of the
+// reductions on one GPU, or in k_ctl after the all-reduce on several.
+#pragma once
+#include "kernels.cuh"
+
+namespace rk {
+
+struct KrylovShared {      // device resident
+    KrylovCtl ctl[MAX_RHS];
+    int nActive;
+    int pad[3];
+};
+
+struct SolveCtl { double tol, relTol; int minIter, maxIter; };
+
+__device__ __forceinline__ bool conv_check(double fin, double init, const SolveCtl& sc) {
+    return fin < sc.tol || (sc.relTol > 1e-20 && fin < sc.relTol * init);
+}
+
+template <int NR> __device__ __forceinline__ void ldv(const double* __restrict__ p, size_t cell, double (&o)[NR]) {
+    const double2* q = reinterpret_cast<const double2*>(p + cell * NR);
+#pragma unroll
+    for (int j = 0; j < NR / 2; ++j) { const double2 t = q[j]; o[2 * j] = t.x; o[2 * j + 1] = t.y; }
+}
+template <int NR> __device__ __forceinline__ void stv(double* __restrict__ p, size_t cell, const double (&o)[NR]) {
+    double2* q = reinterpret_cast<double2*>(p + cell * NR);
+#pragma unroll
+    for (int j = 0; j < NR / 2; ++j) q[j] = make_double2(o[2 * j], o[2 * j + 1]);
+}
+
+// ---- scalar control, shared by the epilogues (1 GPU) and k_ctl (after all-reduce)
+__device__ __forceinline__ void ctl_init(KrylovShared* ks, int nrhs, const double* red3, const SolveCtl& sc) {
+    int cnt = 0;
+    for (int q = 0; q < nrhs; ++q) {
+        KrylovCtl k;
+        k.normFactor = red3[3 * q] + 1e-20;
+        k.initRes = red3[3 * q + 1] / k.normFactor;
+        k.finRes = k.initRes;
+        k.rho = red3[3 * q + 2];
+        k.rhoOld = 0; k.alpha = 0; k.omega = 0; k.beta = 0; k.iters = 0; k.singular = 0; k.pad = 0;
+        k.state = (sc.minIter > 0 || !conv_check(k.finRes, k.initRes, sc)) ? 0 : 2;
+        if (k.state == 0 && !(fabs(k.rho) > 1e-300)) { k.state = 2; k.singular = 1; }
+        ks->ctl[q] = k;
+        cnt += (k.state == 0);
+    }
+    ks->nActive = cnt;
+}
+// after r0.v : alpha
+__device__ __forceinline__ void ctl_alpha(KrylovShared* ks, int nrhs, const double* dotsV) {
+    for (int q = 0; q < nrhs; ++q)
+        if (ks->ctl[q].state == 0) ks->ctl[q].alpha = ks->ctl[q].rho / dotsV[q];
+}
+// after sum|s| : half-step convergence
+__device__ __forceinline__ void ctl_half(KrylovShared* ks, int nrhs, const double* sumS, const SolveCtl& sc) {
+    for (int q = 0; q < nrhs; ++q) {
+        KrylovCtl& k = ks->ctl[q];
+        if (k.state != 0) continue;
+        k.finRes = sumS[q] / k.normFactor;
+        if (conv_check(k.finRes, k.initRes, sc)) k.state = 1;
+    }
+}
+// after t.t, t.s : omega
+__device__ __forceinline__ void ctl_omega(KrylovShared* ks, int nrhs, const double* dots2) {
+    for (int q = 0; q < nrhs; ++q)
+        if (ks->ctl[q].state == 0) ks->ctl[q].omega = dots2[2 * q + 1] / dots2[2 * q];
+}
+// end of iteration
+__device__ __forceinline__ void ctl_end(KrylovShared* ks, int nrhs, const double* red2, const SolveCtl& sc) {
+    int cnt = 0;
+    for (int q = 0; q < nrhs; ++q) {
+        KrylovCtl& k = ks->ctl[q];
+        if (k.state == 1) { k.iters++; k.state = 2; }
+        else if (k.state == 0) {
+            k.finRes = red2[2 * q] / k.normFactor;
+            k.rhoOld = k.rho;
+            k.rho = red2[2 * q + 1];
+            const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
+            if (!cont) k.state = 2;
+            else if (!(fabs(k.rho) > 1e-300) || !(fabs(k.omega) > 1e-300)) { k.state = 2; k.singular = 1; }
+            else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);
+        }
+        cnt += (k.state == 0);
+    }
+    ks->nActive = cnt;
+}
+enum { CTL_NONE = 0, CTL_INIT = 1, CTL_ALPHA = 2, CTL_HALF = 3, CTL_OMEGA = 4, CTL_END = 5 };
+__device__ __forceinline__ void ctl_dispatch(int what, KrylovShared* ks, int nrhs, const double* red, const SolveCtl& sc) {
+    switch (what) {
+        case CTL_INIT: ctl_init(ks, nrhs, red, sc); break;
+        case CTL_ALPHA: ctl_alpha(ks, nrhs, red); break;
+        case CTL_HALF: ctl_half(ks, nrhs, red, sc); break;
+        case CTL_OMEGA: ctl_omega(ks, nrhs, red); break;
+        case CTL_END: ctl_end(ks, nrhs, red, sc); break;
+        default: break;
+    }
+}
+__global__ void k_ctl(int what, KrylovShared* ks, int nrhs, const double* red, SolveCtl sc) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctl_dispatch(what, ks, nrhs, red, sc);
+}
+
+// Reduction epilogue: the last block (of `expected` participating blocks, possibly spread over several
+// launches that share partials/counter) sums the partials in a fixed order and optionally runs the
+// scalar control step.
+__device__ __forceinline__ void finalize_ctl(const double* partials, int nBlocksTotal, int nSlots, double* out, unsigned* counter,
+                                             unsigned expected, int what, KrylovShared* ks, int nrhs, const SolveCtl& sc) {
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = atomicAdd(counter, 1u);
+        isLast = (t == expected - 1);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int s = warp; s < nSlots; s += BLOCK / 32) {
+        double x = 0;
+        for (int b = lane; b < nBlocksTotal; b += 32) x += partials[(size_t)b * nSlots + s];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) out[s] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *counter = 0;
+        __threadfence();
+        if (what != CTL_NONE) ctl_dispatch(what, ks, nrhs, out, sc);
+    }
+}
+
+// All kernels below are persistent-style: a bounded grid (a few CTAs per SM) strides over the cells, so the
+// block reduction / last-block epilogue is paid once per CTA instead of once per 256 cells.
+
+// ---------------------------------------------------------------- sum(psi) for gAverage
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_sum_psi(int N, int nModes, RhsPtrs rp, double* partials, double* out, unsigned* counter) {
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        double v[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) v[j] = 0.0;
+        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) v[j] += rp.psi[md * NR + j][c];
+        }
+        block_reduce_to_partials<NR>(v, partials, md * NR, nModes * NR);
+    }
+    SolveCtl sc{};
+    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, CTL_NONE, nullptr, 0, sc);
+}
+
+// ---------------------------------------------------------------- initial residual
+// v = A psi (ghost columns included: psi halos are exchanged before), r = b - v, r0 = r
+// sums per RHS: [0] |v - xRef rowsum| + |b - xRef rowsum|, [1] |r|, [2] r.r
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ A,
+                                                        const double* __restrict__ sumPsi, double nGlobal, double* __restrict__ r, double* __restrict__ r0v,
+                                                        double* partials, double* out, unsigned* counter, int ctlWhat, KrylovShared* ks, SolveCtl sc) {
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        double red[3 * NR];
+#pragma unroll
+        for (int j = 0; j < 3 * NR; ++j) red[j] = 0.0;
+        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < m.N; c += stride) {
+            const double d = diag[c];
+            double rowsum = d;
+            double acc[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] = d * rp.psi[md * NR + j][c];
+            for (int s = 0; s < m.K; ++s) {
+                const double a = A[(size_t)s * m.NS + c];
+                const int nb = m.nbrA[(size_t)s * m.NS + c];
+                rowsum += a;
+#pragma unroll
+                for (int j = 0; j < NR; ++j) acc[j] += a * rp.psi[md * NR + j][nb];
+            }
+            double rr[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                const double bb = rp.b[md * NR + j][c];
+                rr[j] = bb - acc[j];
+                const double t = rowsum * (sumPsi[md * NR + j] / nGlobal);
+                red[3 * j] += fabs(acc[j] - t) + fabs(bb - t);
+                red[3 * j + 1] += fabs(rr[j]);
+                red[3 * j + 2] += rr[j] * rr[j];
+            }
+            stv<NR>(r, (size_t)md * m.NP + c, rr);
+            stv<NR>(r0v, (size_t)md * m.NP + c, rr);
+        }
+        block_reduce_to_partials<3 * NR>(red, partials, 3 * md * NR, 3 * nModes * NR);
+    }
+    finalize_ctl(partials, gridDim.x, 3 * nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);
+}
+
+// ---------------------------------------------------------------- p = r + beta (p - omega v);  y = rD p
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
+                                                     const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p, double* __restrict__ y) {
+    if (ks->nActive == 0) return;
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        double beta[NR], omega[NR];
+        bool on[NR], first[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            const KrylovCtl& k = ks->ctl[md * NR + j];
+            on[j] = k.state == 0; first[j] = k.iters == 0; beta[j] = k.beta; omega[j] = k.omega;
+        }
+        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
+            const double d = rD[c];
+            const size_t i = (size_t)md * NP + c;
+            double rr[NR], pp[NR], vv[NR], yy[NR];
+            ldv<NR>(r, i, rr); ldv<NR>(p, i, pp); ldv<NR>(v, i, vv);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                yy[j] = 0.0;   // y of a finished RHS is never read again
+                if (!on[j]) continue;
+                pp[j] = first[j] ? rr[j] : rr[j] + beta[j] * (pp[j] - omega[j] * vv[j]);
+                yy[j] = d * pp[j];
+            }
+            stv<NR>(p, i, pp); stv<NR>(y, i, yy);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- DILU forward / backward phases on a cell range
+template <int NR, int FWD>
+__global__ void __launch_bounds__(BLOCK) k_sweep(MeshView m, int c0, int c1, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
+                                                  const double* __restrict__ A, double* __restrict__ y) {
+    if (ks->nActive == 0) return;
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        bool on[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) on[j] = ks->ctl[md * NR + j].state == 0;
+        for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
+            const double d = rD[c];
+            double acc[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+            for (int s = 0; s < m.K; ++s) {
+                const int nb = m.nbrA[(size_t)s * m.NS + c];
+                if (FWD ? (nb >= c) : (nb <= c || nb >= m.N)) continue;
+                const double a = A[(size_t)s * m.NS + c];
+                double yn[NR];
+                ldv<NR>(y, (size_t)md * m.NP + nb, yn);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+            }
+            double yy[NR];
+            const size_t i = (size_t)md * m.NP + c;
+            ldv<NR>(y, i, yy);
+#pragma unroll
+            for (int j = 0; j < NR; ++j)
+                if (on[j]) yy[j] -= d * acc[j];
+            stv<NR>(y, i, yy);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- v = A y (local columns) with fused dots
+//   FUSE = 1 : the range is colour 0 — first finish the backward substitution of these cells
+//   MODE 0   : dot[q]            = other . v   (other = r0)
+//   MODE 1   : dot[2q], [2q+1]   = v . v , v . other   (other = s)
+// Several launches (cell ranges) share partials; the last launched range finalises (blockBase/totalBlocks).
+template <int NR, int MODE, int FUSE>
+__global__ void __launch_bounds__(BLOCK) k_spmv(MeshView m, int c0, int c1, int nModes, KrylovShared* ks, const double* __restrict__ diag,
+                                                 const double* __restrict__ rD, const double* __restrict__ A, double* __restrict__ y, double* __restrict__ v,
+                                                 const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
+                                                 int totalBlocks, int ctlWhat, SolveCtl sc) {
+    if (ks->nActive == 0) return;
+    constexpr int ND = MODE == 0 ? 1 : 2;
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        double red[ND * NR];
+        bool on[NR];
+#pragma unroll
+        for (int j = 0; j < ND * NR; ++j) red[j] = 0.0;
+#pragma unroll
+        for (int j = 0; j < NR; ++j) on[j] = ks->ctl[md * NR + j].state == 0;
+        for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
+            const double d = diag[c], rd = rD[c];
+            double acc[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+            for (int s = 0; s < m.K; ++s) {
+                const int nb = m.nbrA[(size_t)s * m.NS + c];
+                if (nb == c || nb >= m.N) continue;
+                const double a = A[(size_t)s * m.NS + c];
+                double yn[NR];
+                ldv<NR>(y, (size_t)md * m.NP + nb, yn);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+            }
+            const size_t i = (size_t)md * m.NP + c;
+            double yy[NR], vv[NR], oo[NR];
+            ldv<NR>(y, i, yy); ldv<NR>(other, i, oo);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                vv[j] = 0.0;   // v of a finished RHS is never read again
+                if (!on[j]) continue;
+                if (FUSE) yy[j] -= rd * acc[j];
+                vv[j] = d * yy[j] + acc[j];
+                if (MODE == 0) red[j] += oo[j] * vv[j];
+                else { red[2 * j] += vv[j] * vv[j]; red[2 * j + 1] += vv[j] * oo[j]; }
+            }
+            if (FUSE) stv<NR>(y, i, yy);
+            stv<NR>(v, i, vv);
+        }
+        block_reduce_to_partials<ND * NR>(red, partials + (size_t)blockBase * ND * nModes * NR, ND * md * NR, ND * nModes * NR);
+    }
+    finalize_ctl(partials, totalBlocks, ND * nModes * NR, out, counter, (unsigned)totalBlocks, ctlWhat, ks, nModes * NR, sc);
+}
+
+// ghost (processor-patch) columns, after the halo exchange of y: one thread per cell that owns ghost slots
+//   v[c] += sum_{ghost slots} A y[ghost]; the dots are corrected for the change of v
+template <int NR, int MODE>
+__global__ void __launch_bounds__(BLOCK) k_ghost(MeshView m, int nBcells, const int* __restrict__ bcells, int nModes, const KrylovShared* __restrict__ ks,
+                                                  const double* __restrict__ A, const double* __restrict__ y, double* __restrict__ v,
+                                                  const double* __restrict__ other, double* dots) {
+    if (ks->nActive == 0) return;
+    constexpr int ND = MODE == 0 ? 1 : 2;
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= nBcells) return;
+    const int c = bcells[i0];
+    for (int md = 0; md < nModes; ++md) {
+        double acc[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+        for (int s = 0; s < m.K; ++s) {
+            const int nb = m.nbrA[(size_t)s * m.NS + c];
+            if (nb < m.N) continue;
+            const double a = A[(size_t)s * m.NS + c];
+            double yn[NR];
+            ldv<NR>(y, (size_t)md * m.NP + nb, yn);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+        }
+        const size_t i = (size_t)md * m.NP + c;
+        double vv[NR], oo[NR];
+        ldv<NR>(v, i, vv); ldv<NR>(other, i, oo);
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            if (ks->ctl[md * NR + j].state != 0) continue;
+            const double vn = vv[j] + acc[j];
+            if (MODE == 0) atomicAdd(&dots[md * NR + j], oo[j] * acc[j]);
+            else { atomicAdd(&dots[ND * (md * NR + j)], vn * vn - vv[j] * vv[j]); atomicAdd(&dots[ND * (md * NR + j) + 1], acc[j] * oo[j]); }
+            vv[j] = vn;
+        }
+        stv<NR>(v, i, vv);
+    }
+}
+
+// ---------------------------------------------------------------- s = r - alpha v ; z = rD s ; sum|s|
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_make_s(int N, int NP, int nModes, KrylovShared* ks, const double* __restrict__ rD, const double* __restrict__ r,
+                                                   const double* __restrict__ v, double* __restrict__ sv, double* __restrict__ z, double* partials,
+                                                   double* out, unsigned* counter, int ctlWhat, SolveCtl sc) {
+    if (ks->nActive == 0) return;
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        double red[NR], alpha[NR];
+        bool on[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) { red[j] = 0.0; const KrylovCtl& k = ks->ctl[md * NR + j]; on[j] = k.state == 0; alpha[j] = k.alpha; }
+        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
+            const double d = rD[c];
+            const size_t i = (size_t)md * NP + c;
+            double rr[NR], vv[NR], ss[NR], zz[NR];
+            ldv<NR>(r, i, rr); ldv<NR>(v, i, vv);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                ss[j] = 0.0; zz[j] = 0.0;
+                if (!on[j]) continue;
+                ss[j] = rr[j] - alpha[j] * vv[j];
+                zz[j] = d * ss[j];
+                red[j] += fabs(ss[j]);
+            }
+            stv<NR>(sv, i, ss); stv<NR>(z, i, zz);
+        }
+        block_reduce_to_partials<NR>(red, partials, md * NR, nModes * NR);
+    }
+    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);
+}
+
+// ---------------------------------------------------------------- psi += alpha y + omega z ; r = s - omega t ; sum|r| , r0.r
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_update_x_r(int N, int NP, int nModes, RhsPtrs rp, KrylovShared* ks, const double* __restrict__ y,
+                                                       const double* __restrict__ z, const double* __restrict__ sv, const double* __restrict__ t,
+                                                       const double* __restrict__ r0v, double* __restrict__ r, double* partials, double* out,
+                                                       unsigned* counter, int ctlWhat, SolveCtl sc) {
+    if (ks->nActive == 0) return;
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md) {
+        double red[2 * NR], alpha[NR], omega[NR];
+        int st[NR];
+#pragma unroll
+        for (int j = 0; j < NR; ++j) {
+            red[2 * j] = 0.0; red[2 * j + 1] = 0.0;
+            const KrylovCtl& k = ks->ctl[md * NR + j];
+            st[j] = k.state; alpha[j] = k.alpha; omega[j] = k.omega;
+        }
+        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
+            const size_t i = (size_t)md * NP + c;
+            double yy[NR], zz[NR], ss[NR], tt[NR], r0[NR], rr[NR];
+            ldv<NR>(y, i, yy); ldv<NR>(z, i, zz); ldv<NR>(sv, i, ss); ldv<NR>(t, i, tt); ldv<NR>(r0v, i, r0);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                rr[j] = 0.0;
+                if (st[j] == 2) continue;
+                double* psi = rp.psi[md * NR + j];
+                if (st[j] == 1) { psi[c] += alpha[j] * yy[j]; continue; }
+                psi[c] += alpha[j] * yy[j] + omega[j] * zz[j];
+                rr[j] = ss[j] - omega[j] * tt[j];
+                red[2 * j] += fabs(rr[j]);
+                red[2 * j + 1] += r0[j] * rr[j];
+            }
+            stv<NR>(r, i, rr);
+        }
+        block_reduce_to_partials<2 * NR>(red, partials, 2 * md * NR, 2 * nModes * NR);
+    }
+    finalize_ctl(partials, gridDim.x, 2 * nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);
+}
+
+}  // namespace rk

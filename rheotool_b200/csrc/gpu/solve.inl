@@ -1,0 +1,146 @@
+// solve.inl — host orchestration of the batched PBiCGStab/DILU solve (included by engine.cu).
+//
+// One call solves the NR valid components of `nModes` modes on the shared LDU matrix.  Iterations are
+// launched in speculative batches (as many as the previous step needed) with no host synchronisation
+// inside a batch: every kernel returns immediately once the device-side nActive counter is 0.
+
+// interleaved halo records: buf[(nModes*NR)*h + md*NR + j]
+template <int NR>
+__global__ void k_halo_pack_il(int H, int NP, int nModes, const int* __restrict__ haloCell, const double* __restrict__ x, double* __restrict__ buf) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    const int c = haloCell[h];
+    for (int md = 0; md < nModes; ++md) {
+        double v[NR];
+        ldv<NR>(x, (size_t)md * NP + c, v);
+        stv<NR>(buf, (size_t)h * nModes + md, v);
+    }
+}
+template <int NR>
+__global__ void k_halo_unpack_il(int H, int N, int NP, int nModes, const double* __restrict__ buf, double* __restrict__ x) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= H) return;
+    for (int md = 0; md < nModes; ++md) {
+        double v[NR];
+        ldv<NR>(buf, (size_t)h * nModes + md, v);
+        stv<NR>(x, (size_t)md * NP + N + h, v);
+    }
+}
+
+template <int NR>
+int halo_interleaved(RheoGpu* h, int nModes, double* x) {
+    if (h->H == 0) return 0;
+    if (!h->comm) return fail("mesh has processor patches but rheo_gpu_comm_init was not called");
+    const int rec = nModes * NR;
+    LAUNCH(h, (k_halo_pack_il<NR>), cdiv(h->H, BLOCK), BLOCK, h->H, h->NP, nModes, h->d_haloCell.as<int>(), x, h->d_send.as<double>());
+    g_nccl.GroupStart();
+    for (const HaloSeg& s : h->segs) {
+        const size_t off = (size_t)rec * s.h0, cnt = (size_t)rec * s.len;
+        int rc = g_nccl.Send(h->d_send.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
+        if (!rc) rc = g_nccl.Recv(h->d_recv.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
+        if (rc) { g_nccl.GroupEnd(); return fail(std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(rc)); }
+    }
+    int rc = g_nccl.GroupEnd();
+    if (rc) return fail(std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc));
+    LAUNCH(h, (k_halo_unpack_il<NR>), cdiv(h->H, BLOCK), BLOCK, h->H, h->N, h->NP, nModes, h->d_recv.as<double>(), x);
+    return 0;
+}
+
+// v = A M^-1 (rhs), where x already holds rD*rhs.  MODE 0: dots r0.v -> alpha; MODE 1: t.t, t.s -> omega
+template <int NR, int MODE>
+int precond_spmv(RheoGpu* h, int nModes, double* x, double* v, const double* other, double* redOut, const SolveCtl& sc) {
+    KrylovShared* ks = h->d_ks.as<KrylovShared>();
+    const double* diag = h->d_diag.as<double>();
+    const double* rD = h->d_rD.as<double>();
+    const double* A = h->d_Fs.as<double>();
+    double* part = h->d_partials.as<double>();
+    unsigned* counter = h->d_counter.as<unsigned>();
+    const int nc = h->nColours;
+    const bool multi = h->nRanks > 1;
+    const int what = multi ? CTL_NONE : (MODE == 0 ? CTL_ALPHA : CTL_OMEGA);
+    for (int k = 1; k < nc; ++k) {
+        const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
+        if (c1 > c0) LAUNCH(h, (k_sweep<NR, 1>), grid_for(h, c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
+    }
+    for (int k = nc - 2; k >= 1; --k) {
+        const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
+        if (c1 > c0) LAUNCH(h, (k_sweep<NR, 0>), grid_for(h, c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
+    }
+    const int n0 = h->colourStart[1];
+    const int g0 = grid_for(h, n0), g1 = (h->N > n0) ? grid_for(h, h->N - n0) : 0;
+    if (nc >= 2) {
+        LAUNCH(h, (k_spmv<NR, MODE, 1>), g0, BLOCK, h->mv, 0, n0, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0 + g1, what, sc);
+        if (g1) LAUNCH(h, (k_spmv<NR, MODE, 0>), g1, BLOCK, h->mv, n0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, g0, g0 + g1, what, sc);
+    } else {
+        LAUNCH(h, (k_spmv<NR, MODE, 0>), g0, BLOCK, h->mv, 0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0, what, sc);
+    }
+    if (multi) {
+        const int nd = (MODE == 0 ? 1 : 2) * nModes * NR;
+        if (halo_interleaved<NR>(h, nModes, x)) return 1;
+        if (h->nBcells) LAUNCH(h, (k_ghost<NR, MODE>), cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, A, x, v, other, redOut);
+        if (all_reduce(h, redOut, nd)) return 1;
+        LAUNCH(h, k_ctl, 1, 32, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, ks, nModes * NR, redOut, sc);
+    }
+    return 0;
+}
+
+template <int NR>
+int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
+    const int nrhs = nModes * NR, N = h->N, NP = h->NP;
+    const int grid = grid_for(h, N);
+    KrylovShared* ks = h->d_ks.as<KrylovShared>();
+    double* part = h->d_partials.as<double>();
+    double* red = h->d_red.as<double>();
+    double *redA = red, *redB = red + MAX_RED, *redC = red + 2 * MAX_RED, *redD = red + 3 * MAX_RED;
+    unsigned* counter = h->d_counter.as<unsigned>();
+    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *p = h->d_p.as<double>(), *y = h->d_y.as<double>(), *v = h->d_v.as<double>(),
+           *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
+    const SolveCtl sc{h->ctl.tolerance, h->ctl.rel_tol, h->ctl.min_iter, h->ctl.max_iter};
+    const double* diag = h->d_diag.as<double>();
+    const double* rD = h->d_rD.as<double>();
+    const double* A = h->d_Fs.as<double>();
+    const bool multi = h->nRanks > 1;
+
+    // psi halo, gAverage(psi), initial residual + normFactor
+    if (h->H) {
+        PlaneList pl; pl.n = nrhs;
+        for (int q = 0; q < nrhs; ++q) pl.p[q] = rp.psi[q];
+        if (halo_exchange(h, pl)) return 1;
+    }
+    LAUNCH(h, (k_sum_psi<NR>), grid, BLOCK, N, nModes, rp, part, redA, counter);
+    if (all_reduce(h, redA, nrhs)) return 1;
+    LAUNCH(h, (k_krylov_init<NR>), grid, BLOCK, h->mv, nModes, rp, diag, A, redA, (double)h->nGlobalCells, r, r0, part, redB, counter,
+           multi ? CTL_NONE : CTL_INIT, ks, sc);
+    if (multi) {
+        if (all_reduce(h, redB, 3 * nrhs)) return 1;
+        LAUNCH(h, k_ctl, 1, 32, CTL_INIT, ks, nrhs, redB, sc);
+    }
+    int launched = 0;
+    int spec = std::max(1, h->specIters);
+    for (;;) {
+        for (int it = 0; it < spec; ++it) {
+            LAUNCH(h, (k_update_p<NR>), grid, BLOCK, N, NP, nModes, ks, rD, r, v, p, y);
+            if (precond_spmv<NR, 0>(h, nModes, y, v, r0, redA, sc)) return 1;
+            LAUNCH(h, (k_make_s<NR>), grid, BLOCK, N, NP, nModes, ks, rD, r, v, sv, z, part, redB, counter, multi ? CTL_NONE : CTL_HALF, sc);
+            if (multi) {
+                if (all_reduce(h, redB, nrhs)) return 1;
+                LAUNCH(h, k_ctl, 1, 32, CTL_HALF, ks, nrhs, redB, sc);
+            }
+            if (precond_spmv<NR, 1>(h, nModes, z, t, sv, redC, sc)) return 1;
+            LAUNCH(h, (k_update_x_r<NR>), grid, BLOCK, N, NP, nModes, rp, ks, y, z, sv, t, r0, r, part, redD, counter, multi ? CTL_NONE : CTL_END, sc);
+            if (multi) {
+                if (all_reduce(h, redD, 2 * nrhs)) return 1;
+                LAUNCH(h, k_ctl, 1, 32, CTL_END, ks, nrhs, redD, sc);
+            }
+            ++launched;
+        }
+        CK(cudaMemcpyAsync(h->h_ks, ks, sizeof(KrylovShared), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        if (h->h_ks->nActive == 0 || launched > h->ctl.max_iter + 2) break;
+        spec = 1;
+    }
+    int iters = 0;
+    for (int q = 0; q < nrhs; ++q) iters = std::max(iters, h->h_ks->ctl[q].iters);
+    *itersOut = iters;
+    return 0;
+}
