@@ -119,7 +119,8 @@ struct RheoGpu {
     DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ks, d_partials, d_red, d_counter, d_bcells;
     KrylovShared* h_ks = nullptr;  // pinned mirror of the device control block
     int specIters = 1;             // Krylov iterations launched speculatively per batch (= last step's count)
-    int maxBlocks = 148 * 6;       // SM count x resident CTAs (set at create)
+    int nSms = 148;                // SM count (set at create)
+    std::map<const void*, int> residentBlocks;   // kernel -> SM count x resident CTAs per SM
     int nBcells = 0;               // cells that own at least one ghost (processor) slot
     // comm
     void* comm = nullptr;
@@ -142,6 +143,22 @@ namespace {
     do {                                                                       \
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
         kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                \
+        (h)->launches++;                                                       \
+        if ((h)->ktiming) {                                                    \
+            cudaEventRecord((h)->kev1, (h)->stream);                           \
+            cudaEventSynchronize((h)->kev1);                                   \
+            float ms_ = 0;                                                     \
+            cudaEventElapsedTime(&ms_, (h)->kev0, (h)->kev1);                  \
+            auto& kt_ = (h)->ktimes[#kern];                                    \
+            kt_.first += ms_;                                                  \
+            kt_.second += 1;                                                   \
+        }                                                                      \
+    } while (0)
+
+#define LAUNCH_SM(h, kern, grid, block, smem, ...)                             \
+    do {                                                                       \
+        if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
+        kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);           \
         (h)->launches++;                                                       \
         if ((h)->ktiming) {                                                    \
             cudaEventRecord((h)->kev1, (h)->stream);                           \
@@ -276,6 +293,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     int K = 0;
     for (int c = 0; c < N; ++c) K = std::max(K, deg[c]);
     h->K = K;
+    if (K > 32) return fail("rheo_gpu_create: a cell has more than 32 faces (tile kernels stage 40 B per slot and cell in shared memory)");
     const size_t ell = (size_t)K * h->NS;
     h->h_nbr.assign(ell, -1);
     h->h_fidx.assign(ell, 0);
@@ -442,8 +460,28 @@ int all_reduce(RheoGpu* h, double* buf, int n) {
     return 0;
 }
 
-// persistent-style grids: at most `ctasPerSm` CTAs per SM, each striding over the cells
-inline int grid_for(RheoGpu* h, long n) { return std::max(1, std::min(cdiv(n, BLOCK), h->maxBlocks)); }
+// persistent-style grids: exactly one wave of resident CTAs (SM count x occupancy of that kernel), each
+// striding over the cells — no partial second wave, and the block reductions are paid once per CTA.
+template <class Kern> int resident_grid(RheoGpu* h, Kern kern, long n) {
+    auto it = h->residentBlocks.find((const void*)kern);
+    int blocks;
+    if (it == h->residentBlocks.end()) {
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, BLOCK, 0) != cudaSuccess || perSm < 1) { cudaGetLastError(); perSm = 2; }
+        blocks = perSm * h->nSms;
+        h->residentBlocks[(const void*)kern] = blocks;
+    } else blocks = it->second;
+    return std::max(1, std::min(cdiv(n, BLOCK), blocks));
+}
+#define GRID(h, kern, n) resident_grid(h, kern, n)
+#define LAUNCH_K(h, kern, grid, block, ...)                                                  \
+    do {                                                                                     \
+        switch ((h)->K) {                                                                    \
+            case 4: LAUNCH(h, (kern<4>), grid, block, __VA_ARGS__); break;                   \
+            case 6: LAUNCH(h, (kern<6>), grid, block, __VA_ARGS__); break;                   \
+            default: LAUNCH(h, (kern<0>), grid, block, __VA_ARGS__); break;                  \
+        }                                                                                    \
+    } while (0)
 
 #include "solve.inl"
 
@@ -455,6 +493,11 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     const int nModes = (int)h->modes.size();
     const double rDeltaT = 1.0 / dt;
     const int noConv = h->ctl.limiter == RHEO_LIMITER_NONE;
+    CompList cl;
+    cl.n = h->nComp;
+    for (int j = 0; j < 6; ++j) cl.c[j] = j < h->nComp ? h->comps[j] : 0;
+    const int tileGrid = cdiv(N, TILE);
+    const size_t tileSmem = (size_t)h->K * TILE * (4 * sizeof(double) + 2 * sizeof(int));
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
 
     // ---- halo of U (grad U) and of theta (deferred correction / SpMV of the first residual)
@@ -470,14 +513,14 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
         if (h->lim.hrs && !noConv) {
             if (h->timing) cudaEventRecord(e0, h->stream);
-            LAUNCH(h, k_grad_theta, grid, BLOCK, h->mv, md.theta.as<double>(), md.thetaB.as<double>(), h->d_grad.as<double>());
+            LAUNCH_SM(h, k_grad_theta, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, md.theta.as<double>(), md.thetaB.as<double>(), h->d_grad.as<double>());
             if (h->H && halo_planes(h, h->d_grad.as<double>(), 18)) return 1;
             if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msGrad += ms; }
         }
         if (h->timing) cudaEventRecord(e0, h->stream);
-        LAUNCH(h, k_cell_source, grid, BLOCK, h->mv, md.mp, rDeltaT, h->d_U.as<double>(), h->d_Ub.as<double>(), md.theta.as<double>(),
+        LAUNCH_K(h, k_cell_source, grid, BLOCK, h->mv, md.mp, rDeltaT, h->d_U.as<double>(), h->d_Ub.as<double>(), md.theta.as<double>(),
                md.thetaOld.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.bsrc.as<double>(), md.fFene.as<double>());
-        LAUNCH(h, k_convect, grid, BLOCK, h->mv, h->lim, noConv, rDeltaT, h->ctl.relax, mi == 0 ? 1 : 0, h->d_phi.as<double>(), md.theta.as<double>(),
+        LAUNCH_SM(h, k_convect, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, h->lim, noConv, rDeltaT, h->ctl.relax, mi == 0 ? 1 : 0, h->d_phi.as<double>(), md.theta.as<double>(),
                md.thetaB.as<double>(), h->d_grad.as<double>(), md.bsrc.as<double>(), h->d_diag.as<double>(), h->d_rD.as<double>(), h->d_Fs.as<double>());
         if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
     }
@@ -497,7 +540,9 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 rp.n++;
             }
         int iters = 0;
-        int rc = (h->nComp == 6) ? solve_batch<6>(h, rp, m1 - m0, &iters) : solve_batch<4>(h, rp, m1 - m0, &iters);
+        int rc;
+        if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m1 - m0, &iters) : solve_batch<6, 0>(h, rp, m1 - m0, &iters);
+        else rc = (h->K == 4) ? solve_batch<4, 4>(h, rp, m1 - m0, &iters) : solve_batch<4, 0>(h, rp, m1 - m0, &iters);
         if (rc) return rc;
         h->specIters = std::max(1, iters);
         int q = 0;
@@ -588,7 +633,7 @@ int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_
     h->lim = make_limiter(ctl->limiter);
     if (ctl->limiter < RHEO_LIMITER_UPWIND || ctl->limiter > RHEO_LIMITER_NONE) { delete h; return fail("The deferred limited scheme is not specified or does not exist. Valid schemes are: upwind cubista minmod smart waceb superbee none"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("cudaStreamCreate failed"); }
-    { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->maxBlocks = sms * 6; }
+    { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->nSms = sms; }
     for (auto& e : h->ev) cudaEventCreate(&e);
     cudaEventCreate(&h->kev0); cudaEventCreate(&h->kev1);
     if (build_mesh(h, mesh) || alloc_fields(h, modes, n_modes)) { rheo_gpu_destroy(h); return 1; }

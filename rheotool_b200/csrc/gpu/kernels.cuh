@@ -170,34 +170,69 @@ __global__ void k_bc_zero_gradient(MeshView m, const int* __restrict__ bc, const
 
 // ---------------------------------------------------------------- Gauss-linear gradient of NC fields
 // face value: internal w(P-N)+N in the face's owner/neighbour frame; processor wP+(1-w)N; boundary = patch value
-template <int NC>
+// KT = compile-time slot count (4: 2-D hex, 6: 3-D hex) so that all index / geometry loads of a cell are issued
+// together and then all field gathers (two dependent memory latencies per cell instead of 2*K);
+// KT = 0: run-time K (unstructured meshes).  Slot order and arithmetic are identical in both paths.
+template <int NC, int KT>
 __device__ __forceinline__ void gauss_grad_cell(const MeshView& m, int c, const double* __restrict__ fld, const double* __restrict__ fldB,
                                                 const double* own, double* g /*[3*NC]: g[3k+d]*/) {
 #pragma unroll
     for (int i = 0; i < 3 * NC; ++i) g[i] = 0.0;
-    for (int s = 0; s < m.K; ++s) {
-        const int nb = m.nbr[(size_t)s * m.NS + c];
-        if (nb == -1) continue;
-        const int fi = m.fidx[(size_t)s * m.NS + c];
-        const int f = fi >= 0 ? fi : ~fi;
-        const double sg = fi >= 0 ? 1.0 : -1.0;
-        const double Sx = sg * m.Sf[f], Sy = sg * m.Sf[(size_t)m.nF + f], Sz = sg * m.Sf[2 * (size_t)m.nF + f];
-        if (nb >= 0) {
-            const double w = m.w[f];
+    if constexpr (KT == 0) {
+        for (int s = 0; s < m.K; ++s) {
+            const int nb = m.nbr[(size_t)s * m.NS + c];
+            if (nb == -1) continue;
+            const int fi = m.fidx[(size_t)s * m.NS + c];
+            const int f = fi >= 0 ? fi : ~fi;
+            const double sg = fi >= 0 ? 1.0 : -1.0;
+            const double Sx = sg * m.Sf[f], Sy = sg * m.Sf[(size_t)m.nF + f], Sz = sg * m.Sf[2 * (size_t)m.nF + f];
+            if (nb >= 0) {
+                const double w = m.w[f];
 #pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                const double vn = fld[(size_t)k * m.NP + nb];
-                double vf;
-                if (nb >= m.N) vf = w * own[k] + (1.0 - w) * vn;
-                else vf = fi >= 0 ? w * (own[k] - vn) + vn : w * (vn - own[k]) + own[k];
-                g[3 * k] += Sx * vf; g[3 * k + 1] += Sy * vf; g[3 * k + 2] += Sz * vf;
+                for (int k = 0; k < NC; ++k) {
+                    const double vn = fld[(size_t)k * m.NP + nb];
+                    double vf;
+                    if (nb >= m.N) vf = w * own[k] + (1.0 - w) * vn;
+                    else vf = fi >= 0 ? w * (own[k] - vn) + vn : w * (vn - own[k]) + own[k];
+                    g[3 * k] += Sx * vf; g[3 * k + 1] += Sy * vf; g[3 * k + 2] += Sz * vf;
+                }
+            } else {
+                const int b = -nb - 2;
+#pragma unroll
+                for (int k = 0; k < NC; ++k) {
+                    const double vf = fldB[(size_t)k * m.nB + b];
+                    g[3 * k] += Sx * vf; g[3 * k + 1] += Sy * vf; g[3 * k + 2] += Sz * vf;
+                }
             }
-        } else {
-            const int b = -nb - 2;
+        }
+    } else {
+        int nb[KT], fi[KT];
 #pragma unroll
-            for (int k = 0; k < NC; ++k) {
-                const double vf = fldB[(size_t)k * m.nB + b];
-                g[3 * k] += Sx * vf; g[3 * k + 1] += Sy * vf; g[3 * k + 2] += Sz * vf;
+        for (int s = 0; s < KT; ++s) { nb[s] = m.nbr[(size_t)s * m.NS + c]; fi[s] = m.fidx[(size_t)s * m.NS + c]; }
+        double Sx[KT], Sy[KT], Sz[KT], w[KT];
+#pragma unroll
+        for (int s = 0; s < KT; ++s) {
+            const bool used = nb[s] != -1;
+            const int f = used ? (fi[s] >= 0 ? fi[s] : ~fi[s]) : 0;
+            const double sg = used ? (fi[s] >= 0 ? 1.0 : -1.0) : 0.0;   // unused slot: contributes S = 0
+            Sx[s] = sg * m.Sf[f]; Sy[s] = sg * m.Sf[(size_t)m.nF + f]; Sz[s] = sg * m.Sf[2 * (size_t)m.nF + f];
+            w[s] = m.w[f];
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+            double v[KT];
+#pragma unroll
+            for (int s = 0; s < KT; ++s) {   // one load per slot through a selected pointer: cell / ghost / patch value / (unused: own)
+                const double* src = nb[s] >= 0 ? fld + (size_t)k * m.NP + nb[s]
+                                  : (nb[s] == -1 ? fld + (size_t)k * m.NP + c : fldB + (size_t)k * m.nB + (-nb[s] - 2));
+                v[s] = *src;
+            }
+#pragma unroll
+            for (int s = 0; s < KT; ++s) {
+                double vf = v[s];
+                if (nb[s] >= m.N) vf = w[s] * own[k] + (1.0 - w[s]) * v[s];
+                else if (nb[s] >= 0) vf = fi[s] >= 0 ? w[s] * (own[k] - v[s]) + v[s] : w[s] * (v[s] - own[k]) + own[k];
+                g[3 * k] += Sx[s] * vf; g[3 * k + 1] += Sy[s] * vf; g[3 * k + 2] += Sz[s] * vf;
             }
         }
     }
@@ -206,18 +241,73 @@ __device__ __forceinline__ void gauss_grad_cell(const MeshView& m, int c, const 
     for (int i = 0; i < 3 * NC; ++i) g[i] *= rv;
 }
 
-__global__ void __launch_bounds__(BLOCK) k_grad_theta(MeshView m, const double* __restrict__ theta, const double* __restrict__ thetaB, double* __restrict__ grad) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.N) return;
-    double own[6], g[18];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) own[k] = theta[(size_t)k * m.NP + c];
-    gauss_grad_cell<6>(m, c, theta, thetaB, own, g);
-#pragma unroll
-    for (int i = 0; i < 18; ++i) grad[(size_t)i * m.NP + c] = g[i];
+// ---------------------------------------------------------------- tile kernels: one warp per (32 cells, component)
+// Face kernels of the assembly (grad(theta) and the convection operator) are latency-bound when one
+// thread owns a whole cell (6 slots x 6 components of dependent gathers, >130 registers).  Here a CTA is
+// a tile of 32 consecutive cells times the n solved components: threadIdx = comp_group*32 + cell.
+//   phase 1  the warps share the slots: warp g stages slot g, g+n, ... of the 32 cells (neighbour index,
+//            face geometry / flux) in shared memory — every connectivity and geometry word is loaded once;
+//   phase 2  warp g accumulates component comps[g] over the slots: per slot a handful of coalesced gathers,
+//            ~50 registers, so 30-40 warps per SM keep enough loads in flight to cover HBM latency.
+// Unsolved components (xz, yz in 2-D: theta stays 0 there) are skipped altogether.
+struct CompList { int n; int c[6]; };
+constexpr int TILE = 32;
+
+__global__ void __launch_bounds__(TILE * 6) k_grad_theta(MeshView m, CompList cl, const double* __restrict__ theta, const double* __restrict__ thetaB,
+                                                          double* __restrict__ grad) {
+    extern __shared__ double smem[];
+    const int K = m.K;
+    double* sS = smem;                         // [3][K][TILE]  signed face area vector (0 for unused slots)
+    double* sW = smem + 3 * K * TILE;          // [K][TILE]
+    int* sNb = (int*)(smem + 4 * K * TILE);    // [K][TILE]
+    int* sOwn = sNb + K * TILE;                // [K][TILE] 1 if this cell is the face's owner
+    const int lane = threadIdx.x & (TILE - 1), grp = threadIdx.x / TILE, nGrp = blockDim.x / TILE;
+    const int c = blockIdx.x * TILE + lane;
+    const bool active = c < m.N;
+    for (int s = grp; s < K; s += nGrp) {
+        int nb = -1, own = 1;
+        double Sx = 0, Sy = 0, Sz = 0, w = 0;
+        if (active) {
+            nb = m.nbr[(size_t)s * m.NS + c];
+            if (nb != -1) {
+                const int fi = m.fidx[(size_t)s * m.NS + c];
+                own = fi >= 0;
+                const int f = own ? fi : ~fi;
+                const double sg = own ? 1.0 : -1.0;
+                Sx = sg * m.Sf[f]; Sy = sg * m.Sf[(size_t)m.nF + f]; Sz = sg * m.Sf[2 * (size_t)m.nF + f];
+                w = m.w[f];
+            }
+        }
+        const int i = s * TILE + lane;
+        sS[i] = Sx; sS[K * TILE + i] = Sy; sS[2 * K * TILE + i] = Sz; sW[i] = w; sNb[i] = nb; sOwn[i] = own;
+    }
+    __syncthreads();
+    if (!active) return;
+    const int k = cl.c[grp];
+    const double* fk = theta + (size_t)k * m.NP;
+    const double own = fk[c];
+    double gx = 0, gy = 0, gz = 0;
+#pragma unroll 2
+    for (int s = 0; s < K; ++s) {
+        const int i = s * TILE + lane;
+        const int nb = sNb[i];
+        if (nb == -1) continue;
+        double vf;
+        if (nb >= 0) {
+            const double vn = fk[nb], w = sW[i];
+            if (nb >= m.N) vf = w * own + (1.0 - w) * vn;
+            else vf = sOwn[i] ? w * (own - vn) + vn : w * (vn - own) + own;
+        } else vf = thetaB[(size_t)k * m.nB + (-nb - 2)];
+        gx += sS[i] * vf; gy += sS[K * TILE + i] * vf; gz += sS[2 * K * TILE + i] * vf;
+    }
+    const double rv = m.rV[c];
+    grad[(size_t)(3 * k) * m.NP + c] = gx * rv;
+    grad[(size_t)(3 * k + 1) * m.NP + c] = gy * rv;
+    grad[(size_t)(3 * k + 2) * m.NP + c] = gz * rv;
 }
 
 // ---------------------------------------------------------------- per-cell source: grad(U), Omega/B split, model term, Euler ddt
+template <int KT>
 __global__ void __launch_bounds__(BLOCK) k_cell_source(MeshView m, ModelParams mp, double rDeltaT, const double* __restrict__ U, const double* __restrict__ Ub,
                                                         const double* __restrict__ theta, const double* __restrict__ thetaOld, const double* __restrict__ lam,
                                                         const double* __restrict__ R, double* __restrict__ bsrc, double* __restrict__ fFene) {
@@ -226,7 +316,7 @@ __global__ void __launch_bounds__(BLOCK) k_cell_source(MeshView m, ModelParams m
     double own[3], g[9];
 #pragma unroll
     for (int k = 0; k < 3; ++k) own[k] = U[(size_t)k * m.NP + c];
-    gauss_grad_cell<3>(m, c, U, Ub, own, g);
+    gauss_grad_cell<3, KT>(m, c, U, Ub, own, g);
     // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
     const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
     double th[6], Rm[9], lm[3], rhs[6];
@@ -258,60 +348,92 @@ __device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, do
            ((alpha - 1.0) * upw + beta * (1.0 - upw)) * vP + (beta * upw + (alpha - 1.0) * (1.0 - upw)) * vN;
 }
 
-// writeMatrix: first mode of a batch writes Fs / diag (identical for all modes: same phi, same dt)
-__global__ void __launch_bounds__(BLOCK) k_convect(MeshView m, Limiter lim, int noConv, double rDeltaT, double relax, int writeMatrix,
-                                                    const double* __restrict__ phi, const double* __restrict__ theta, const double* __restrict__ thetaB,
-                                                    const double* __restrict__ grad, double* __restrict__ bsrc, double* __restrict__ diag,
-                                                    double* __restrict__ rD, double* __restrict__ Fs) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.N) return;
-    double thP[6], sou[6] = {0, 0, 0, 0, 0, 0}, bnd[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int k = 0; k < 6; ++k) thP[k] = theta[(size_t)k * m.NP + c];
-    const double Cx = m.C[c], Cy = m.C[(size_t)m.NP + c], Cz = m.C[2 * (size_t)m.NP + c];
-    double D = rDeltaT * m.V[c];   // ddt diag + negSumDiag
-    double sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0;
-    for (int s = 0; s < m.K; ++s) {
-        const int nb = m.nbr[(size_t)s * m.NS + c];
-        double F = 0.0;   // signed outflow flux stored for the Krylov kernels
-        if (nb != -1 && !noConv) {
-            const int fi = m.fidx[(size_t)s * m.NS + c];
-            const int f = fi >= 0 ? fi : ~fi;
-            const double ph = phi[f];
-            if (nb >= 0) {
-                F = fi >= 0 ? ph : -ph;
-                if (nb < m.N) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
-                else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
-                if (lim.hrs) {
-                    // owner/neighbour frame of the face (identical arithmetic on both sides => conservative)
-                    const bool own = fi >= 0;
-                    const double dx = own ? m.C[nb] - Cx : Cx - m.C[nb];
-                    const double dy = own ? m.C[(size_t)m.NP + nb] - Cy : Cy - m.C[(size_t)m.NP + nb];
-                    const double dz = own ? m.C[2 * (size_t)m.NP + nb] - Cz : Cz - m.C[2 * (size_t)m.NP + nb];
-                    const double upw = ph >= 0 ? 1.0 : 0.0;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        const double gcx = grad[(size_t)(3 * k) * m.NP + c], gcy = grad[(size_t)(3 * k + 1) * m.NP + c], gcz = grad[(size_t)(3 * k + 2) * m.NP + c];
-                        const double gnx = grad[(size_t)(3 * k) * m.NP + nb], gny = grad[(size_t)(3 * k + 1) * m.NP + nb], gnz = grad[(size_t)(3 * k + 2) * m.NP + nb];
-                        const double gc = gcx * dx + gcy * dy + gcz * dz, gn = gnx * dx + gny * dy + gnz * dz;
-                        const double vn = theta[(size_t)k * m.NP + nb];
-                        const double v = own ? phif_defc(thP[k], vn, gc, gn, upw, lim) : phif_defc(vn, thP[k], gn, gc, upw, lim);
-                        sou[k] += v * F;   // souT[own] += v*phi ; souT[nei] -= v*phi
+// Convection operator (tile kernel, see above).  Phase 1 stages per slot: neighbour, flags, the signed
+// outflow flux F (patch faces: phi_b), the centre-to-centre vector d in the face's owner->neighbour frame, and
+// writes the off-diagonal row coefficients min(F,0) (writeMatrix: first mode of a batch; identical for all
+// modes — same phi, same dt).  Phase 2, per component: diagonal (ddt + upwind + boundary coefficients +
+// relax), the deferred high-resolution correction, boundary source.
+enum { SLOT_CELL = 1, SLOT_OWNER = 2, SLOT_UPW = 4, SLOT_GHOST = 8, SLOT_PATCH = 16, SLOT_PATCH_ZG = 32 };
+
+__global__ void __launch_bounds__(TILE * 6) k_convect(MeshView m, CompList cl, Limiter lim, int noConv, double rDeltaT, double relax, int writeMatrix,
+                                                       const double* __restrict__ phi, const double* __restrict__ theta, const double* __restrict__ thetaB,
+                                                       const double* __restrict__ grad, double* __restrict__ bsrc, double* __restrict__ diag,
+                                                       double* __restrict__ rD, double* __restrict__ Fs) {
+    extern __shared__ double smem[];
+    const int K = m.K;
+    double* sD = smem;                         // [3][K][TILE]
+    double* sF = smem + 3 * K * TILE;          // [K][TILE]
+    int* sNb = (int*)(smem + 4 * K * TILE);    // [K][TILE]
+    int* sFlag = sNb + K * TILE;               // [K][TILE]
+    const int lane = threadIdx.x & (TILE - 1), grp = threadIdx.x / TILE, nGrp = blockDim.x / TILE;
+    const int c = blockIdx.x * TILE + lane;
+    const bool active = c < m.N;
+    const bool hrs = lim.hrs && !noConv;
+    for (int s = grp; s < K; s += nGrp) {
+        int nb = -1, flag = 0;
+        double F = 0, dx = 0, dy = 0, dz = 0;
+        if (active) {
+            nb = m.nbr[(size_t)s * m.NS + c];
+            if (nb != -1 && !noConv) {
+                const int fi = m.fidx[(size_t)s * m.NS + c];
+                const bool own = fi >= 0;
+                const double ph = phi[own ? fi : ~fi];
+                if (nb >= 0) {
+                    F = own ? ph : -ph;
+                    flag = SLOT_CELL | (own ? SLOT_OWNER : 0) | (ph >= 0 ? SLOT_UPW : 0) | (nb >= m.N ? SLOT_GHOST : 0);
+                    if (hrs) {   // owner/neighbour frame of the face (identical arithmetic on both sides => conservative)
+                        const double Cx = m.C[c], Cy = m.C[(size_t)m.NP + c], Cz = m.C[2 * (size_t)m.NP + c];
+                        const double nx = m.C[nb], ny = m.C[(size_t)m.NP + nb], nz = m.C[2 * (size_t)m.NP + nb];
+                        dx = own ? nx - Cx : Cx - nx; dy = own ? ny - Cy : Cy - ny; dz = own ? nz - Cz : Cz - nz;
                     }
+                } else {
+                    F = ph;
+                    flag = SLOT_PATCH | (m.bthetaBC[-nb - 2] == RHEO_BC_ZERO_GRADIENT ? SLOT_PATCH_ZG : 0);
                 }
-            } else {
-                const int b = -nb - 2;
-                if (m.bthetaBC[b] == RHEO_BC_ZERO_GRADIENT) { iCplain += ph; iCplainAbs += fabs(ph); }
-                else {
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) bnd[k] += -ph * thetaB[(size_t)k * m.nB + b];
-                }
-                F = 0.0;
             }
+            if (writeMatrix) Fs[(size_t)s * m.NS + c] = (flag & SLOT_CELL) ? fmin(F, 0.0) : 0.0;   // row coefficient A[c][nb]
         }
-        if (writeMatrix) Fs[(size_t)s * m.NS + c] = (nb >= 0) ? fmin(F, 0.0) : 0.0;   // row coefficient A[c][nb]
+        const int i = s * TILE + lane;
+        sD[i] = dx; sD[K * TILE + i] = dy; sD[2 * K * TILE + i] = dz; sF[i] = F; sNb[i] = nb; sFlag[i] = flag;
     }
-    double add[6] = {0, 0, 0, 0, 0, 0};
+    __syncthreads();
+    if (!active) return;
+    const int k = cl.c[grp];
+    const double* tk = theta + (size_t)k * m.NP;
+    const double tP = tk[c];
+    double D = rDeltaT * m.V[c];   // ddt diag + negSumDiag
+    double sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0, bnd = 0;
+    for (int s = 0; s < K; ++s) {
+        const int i = s * TILE + lane;
+        const int flag = sFlag[i];
+        const double F = sF[i];
+        if (flag & SLOT_CELL) {
+            if (!(flag & SLOT_GHOST)) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
+            else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
+        } else if (flag & SLOT_PATCH) {
+            if (flag & SLOT_PATCH_ZG) { iCplain += F; iCplainAbs += fabs(F); }
+            else bnd += -F * thetaB[(size_t)k * m.nB + (-sNb[i] - 2)];
+        }
+    }
+    double sou = 0;
+    if (hrs) {
+        const double* gk = grad + (size_t)(3 * k) * m.NP;
+        const double gcx = gk[c], gcy = gk[(size_t)m.NP + c], gcz = gk[2 * (size_t)m.NP + c];
+#pragma unroll 2
+        for (int s = 0; s < K; ++s) {
+            const int i = s * TILE + lane;
+            const int flag = sFlag[i];
+            if (!(flag & SLOT_CELL)) continue;
+            const int nb = sNb[i];
+            const double gnx = gk[nb], gny = gk[(size_t)m.NP + nb], gnz = gk[2 * (size_t)m.NP + nb], vn = tk[nb];
+            const double dx = sD[i], dy = sD[K * TILE + i], dz = sD[2 * K * TILE + i];
+            const double gc = gcx * dx + gcy * dy + gcz * dz, gn = gnx * dx + gny * dy + gnz * dz;
+            const double upw = (flag & SLOT_UPW) ? 1.0 : 0.0;
+            const double v = (flag & SLOT_OWNER) ? phif_defc(tP, vn, gc, gn, upw, lim) : phif_defc(vn, tP, gn, gc, upw, lim);
+            sou += v * sF[i];   // souT[own] += v*phi ; souT[nei] -= v*phi
+        }
+    }
+    double add = 0;
     if (relax > 0) {   // EXT-OF9 fvMatrix::relax
         const double D0 = D;
         double Dn = D + iCcoupled + iCplainAbs;
@@ -319,13 +441,11 @@ __global__ void __launch_bounds__(BLOCK) k_convect(MeshView m, Limiter lim, int 
         Dn /= relax;
         Dn -= iCcoupled;
         Dn -= iCplain;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) add[k] = (Dn - D0) * thP[k];
+        add = (Dn - D0) * tP;
         D = Dn;
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) bsrc[(size_t)k * m.NP + c] += (-sou[k] + add[k]) + bnd[k];
-    if (writeMatrix) {
+    bsrc[(size_t)k * m.NP + c] += (-sou + add) + bnd;
+    if (writeMatrix && grp == 0) {
         const double Dfull = D + iCcoupled + iCplain;   // addBoundaryDiag
         diag[c] = Dfull;
         rD[c] = 1.0 / Dfull;   // DILU: upper*lower == 0 on every face of an upwind matrix
@@ -382,7 +502,7 @@ __global__ void k_tau_bc_linext(MeshView m, int start, int size, const double* _
     double own[6], g[18];
 #pragma unroll
     for (int k = 0; k < 6; ++k) own[k] = tau[(size_t)k * m.NP + c];
-    gauss_grad_cell<6>(m, c, tau, tauB, own, g);
+    gauss_grad_cell<6, 0>(m, c, tau, tauB, own, g);
     const double dx = m.CfB[b] - m.C[c], dy = m.CfB[(size_t)m.nB + b] - m.C[(size_t)m.NP + c], dz = m.CfB[2 * (size_t)m.nB + b] - m.C[2 * (size_t)m.NP + c];
 #pragma unroll
     for (int k = 0; k < 6; ++k) tmp[(size_t)k * size + i] = own[k] + (g[3 * k] * dx + g[3 * k + 1] * dy + g[3 * k + 2] * dz);

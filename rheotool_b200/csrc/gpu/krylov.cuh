@@ -48,6 +48,48 @@ template <int NR> __device__ __forceinline__ void stv(double* __restrict__ p, si
     for (int j = 0; j < NR / 2; ++j) q[j] = make_double2(o[2 * j], o[2 * j + 1]);
 }
 
+
+// Row gather  acc[j] = sum_s A[s][c] * y[nb(s)][j]  over the slots selected by SEL:
+//   SEL 0: forward substitution (nb < c)   1: backward (c < nb < N)   2: all local columns (nb != c, nb < N)
+// KT > 0: compile-time slot count — the K index/coefficient loads are issued together, then the K gathers
+// (excluded slots read the cell's own row with coefficient 0, so there is no divergent control flow);
+// KT = 0: run-time K.  Slot order and arithmetic are the same in both.
+template <int SEL> __device__ __forceinline__ bool slot_selected(int nb, int c, int N) {
+    return SEL == 0 ? (nb < c) : (SEL == 1 ? (nb > c && nb < N) : (nb != c && nb < N));
+}
+template <int NR, int KT, int SEL>
+__device__ __forceinline__ void row_gather(const MeshView& m, int c, const double* __restrict__ A, const double* __restrict__ y, size_t base,
+                                           double (&acc)[NR]) {
+#pragma unroll
+    for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+    if constexpr (KT == 0) {
+        for (int s = 0; s < m.K; ++s) {
+            const int nb = m.nbrA[(size_t)s * m.NS + c];
+            if (!slot_selected<SEL>(nb, c, m.N)) continue;
+            const double a = A[(size_t)s * m.NS + c];
+            double yn[NR];
+            ldv<NR>(y, base + nb, yn);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+        }
+    } else {
+        int nb[KT];
+        double a[KT];
+#pragma unroll
+        for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[(size_t)s * m.NS + c]; a[s] = A[(size_t)s * m.NS + c]; }
+#pragma unroll
+        for (int s = 0; s < KT; ++s)
+            if (!slot_selected<SEL>(nb[s], c, m.N)) { nb[s] = c; a[s] = 0.0; }
+#pragma unroll
+        for (int s = 0; s < KT; ++s) {
+            double yn[NR];
+            ldv<NR>(y, base + nb[s], yn);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] += a[s] * yn[j];
+        }
+    }
+}
+
 // ---- scalar control, shared by the epilogues (1 GPU) and k_ctl (after all-reduce)
 __device__ __forceinline__ void ctl_init(KrylovShared* ks, int nrhs, const double* red3, const SolveCtl& sc) {
     int cnt = 0;
@@ -173,7 +215,7 @@ __global__ void __launch_bounds__(BLOCK) k_sum_psi(int N, int nModes, RhsPtrs rp
 // ---------------------------------------------------------------- initial residual
 // v = A psi (ghost columns included: psi halos are exchanged before), r = b - v, r0 = r
 // sums per RHS: [0] |v - xRef rowsum| + |b - xRef rowsum|, [1] |r|, [2] r.r
-template <int NR>
+template <int NR, int KT>
 __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ A,
                                                         const double* __restrict__ sumPsi, double nGlobal, double* __restrict__ r, double* __restrict__ r0v,
                                                         double* partials, double* out, unsigned* counter, int ctlWhat, KrylovShared* ks, SolveCtl sc) {
@@ -188,12 +230,30 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
             double acc[NR];
 #pragma unroll
             for (int j = 0; j < NR; ++j) acc[j] = d * rp.psi[md * NR + j][c];
-            for (int s = 0; s < m.K; ++s) {
-                const double a = A[(size_t)s * m.NS + c];
-                const int nb = m.nbrA[(size_t)s * m.NS + c];
-                rowsum += a;
+            if constexpr (KT == 0) {
+                for (int s = 0; s < m.K; ++s) {
+                    const double a = A[(size_t)s * m.NS + c];
+                    const int nb = m.nbrA[(size_t)s * m.NS + c];
+                    rowsum += a;
 #pragma unroll
-                for (int j = 0; j < NR; ++j) acc[j] += a * rp.psi[md * NR + j][nb];
+                    for (int j = 0; j < NR; ++j) acc[j] += a * rp.psi[md * NR + j][nb];
+                }
+            } else {
+                int nb[KT];
+                double a[KT];
+#pragma unroll
+                for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[(size_t)s * m.NS + c]; a[s] = A[(size_t)s * m.NS + c]; }
+#pragma unroll
+                for (int s = 0; s < KT; ++s) rowsum += a[s];
+#pragma unroll
+                for (int j = 0; j < NR; ++j) {
+                    const double* pj = rp.psi[md * NR + j];
+                    double pn[KT];
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) pn[s] = pj[nb[s]];
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) acc[j] += a[s] * pn[s];
+                }
             }
             double rr[NR];
 #pragma unroll
@@ -245,7 +305,7 @@ __global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nModes, c
 }
 
 // ---------------------------------------------------------------- DILU forward / backward phases on a cell range
-template <int NR, int FWD>
+template <int NR, int KT, int FWD>
 __global__ void __launch_bounds__(BLOCK) k_sweep(MeshView m, int c0, int c1, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
                                                   const double* __restrict__ A, double* __restrict__ y) {
     if (ks->nActive == 0) return;
@@ -257,17 +317,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(MeshView m, int c0, int c1, int
         for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
             const double d = rD[c];
             double acc[NR];
-#pragma unroll
-            for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-            for (int s = 0; s < m.K; ++s) {
-                const int nb = m.nbrA[(size_t)s * m.NS + c];
-                if (FWD ? (nb >= c) : (nb <= c || nb >= m.N)) continue;
-                const double a = A[(size_t)s * m.NS + c];
-                double yn[NR];
-                ldv<NR>(y, (size_t)md * m.NP + nb, yn);
-#pragma unroll
-                for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
-            }
+            row_gather<NR, KT, FWD ? 0 : 1>(m, c, A, y, (size_t)md * m.NP, acc);
             double yy[NR];
             const size_t i = (size_t)md * m.NP + c;
             ldv<NR>(y, i, yy);
@@ -284,7 +334,7 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(MeshView m, int c0, int c1, int
 //   MODE 0   : dot[q]            = other . v   (other = r0)
 //   MODE 1   : dot[2q], [2q+1]   = v . v , v . other   (other = s)
 // Several launches (cell ranges) share partials; the last launched range finalises (blockBase/totalBlocks).
-template <int NR, int MODE, int FUSE>
+template <int NR, int KT, int MODE, int FUSE>
 __global__ void __launch_bounds__(BLOCK) k_spmv(MeshView m, int c0, int c1, int nModes, KrylovShared* ks, const double* __restrict__ diag,
                                                  const double* __restrict__ rD, const double* __restrict__ A, double* __restrict__ y, double* __restrict__ v,
                                                  const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
@@ -302,17 +352,7 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(MeshView m, int c0, int c1, int 
         for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
             const double d = diag[c], rd = rD[c];
             double acc[NR];
-#pragma unroll
-            for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-            for (int s = 0; s < m.K; ++s) {
-                const int nb = m.nbrA[(size_t)s * m.NS + c];
-                if (nb == c || nb >= m.N) continue;
-                const double a = A[(size_t)s * m.NS + c];
-                double yn[NR];
-                ldv<NR>(y, (size_t)md * m.NP + nb, yn);
-#pragma unroll
-                for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
-            }
+            row_gather<NR, KT, 2>(m, c, A, y, (size_t)md * m.NP, acc);
             const size_t i = (size_t)md * m.NP + c;
             double yy[NR], vv[NR], oo[NR];
             ldv<NR>(y, i, yy); ldv<NR>(other, i, oo);

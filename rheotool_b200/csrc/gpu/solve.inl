@@ -47,7 +47,7 @@ int halo_interleaved(RheoGpu* h, int nModes, double* x) {
 }
 
 // v = A M^-1 (rhs), where x already holds rD*rhs.  MODE 0: dots r0.v -> alpha; MODE 1: t.t, t.s -> omega
-template <int NR, int MODE>
+template <int NR, int KT, int MODE>
 int precond_spmv(RheoGpu* h, int nModes, double* x, double* v, const double* other, double* redOut, const SolveCtl& sc) {
     KrylovShared* ks = h->d_ks.as<KrylovShared>();
     const double* diag = h->d_diag.as<double>();
@@ -60,19 +60,20 @@ int precond_spmv(RheoGpu* h, int nModes, double* x, double* v, const double* oth
     const int what = multi ? CTL_NONE : (MODE == 0 ? CTL_ALPHA : CTL_OMEGA);
     for (int k = 1; k < nc; ++k) {
         const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
-        if (c1 > c0) LAUNCH(h, (k_sweep<NR, 1>), grid_for(h, c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
+        if (c1 > c0) LAUNCH(h, (k_sweep<NR, KT, 1>), GRID(h, (k_sweep<NR, KT, 1>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
     }
     for (int k = nc - 2; k >= 1; --k) {
         const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
-        if (c1 > c0) LAUNCH(h, (k_sweep<NR, 0>), grid_for(h, c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
+        if (c1 > c0) LAUNCH(h, (k_sweep<NR, KT, 0>), GRID(h, (k_sweep<NR, KT, 0>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
     }
     const int n0 = h->colourStart[1];
-    const int g0 = grid_for(h, n0), g1 = (h->N > n0) ? grid_for(h, h->N - n0) : 0;
+    const int g0 = (nc >= 2) ? GRID(h, (k_spmv<NR, KT, MODE, 1>), n0) : GRID(h, (k_spmv<NR, KT, MODE, 0>), n0);
+    const int g1 = (h->N > n0) ? GRID(h, (k_spmv<NR, KT, MODE, 0>), h->N - n0) : 0;
     if (nc >= 2) {
-        LAUNCH(h, (k_spmv<NR, MODE, 1>), g0, BLOCK, h->mv, 0, n0, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0 + g1, what, sc);
-        if (g1) LAUNCH(h, (k_spmv<NR, MODE, 0>), g1, BLOCK, h->mv, n0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, g0, g0 + g1, what, sc);
+        LAUNCH(h, (k_spmv<NR, KT, MODE, 1>), g0, BLOCK, h->mv, 0, n0, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0 + g1, what, sc);
+        if (g1) LAUNCH(h, (k_spmv<NR, KT, MODE, 0>), g1, BLOCK, h->mv, n0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, g0, g0 + g1, what, sc);
     } else {
-        LAUNCH(h, (k_spmv<NR, MODE, 0>), g0, BLOCK, h->mv, 0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0, what, sc);
+        LAUNCH(h, (k_spmv<NR, KT, MODE, 0>), g0, BLOCK, h->mv, 0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0, what, sc);
     }
     if (multi) {
         const int nd = (MODE == 0 ? 1 : 2) * nModes * NR;
@@ -84,10 +85,9 @@ int precond_spmv(RheoGpu* h, int nModes, double* x, double* v, const double* oth
     return 0;
 }
 
-template <int NR>
+template <int NR, int KT>
 int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
     const int nrhs = nModes * NR, N = h->N, NP = h->NP;
-    const int grid = grid_for(h, N);
     KrylovShared* ks = h->d_ks.as<KrylovShared>();
     double* part = h->d_partials.as<double>();
     double* red = h->d_red.as<double>();
@@ -107,9 +107,9 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
         for (int q = 0; q < nrhs; ++q) pl.p[q] = rp.psi[q];
         if (halo_exchange(h, pl)) return 1;
     }
-    LAUNCH(h, (k_sum_psi<NR>), grid, BLOCK, N, nModes, rp, part, redA, counter);
+    LAUNCH(h, (k_sum_psi<NR>), GRID(h, (k_sum_psi<NR>), N), BLOCK, N, nModes, rp, part, redA, counter);
     if (all_reduce(h, redA, nrhs)) return 1;
-    LAUNCH(h, (k_krylov_init<NR>), grid, BLOCK, h->mv, nModes, rp, diag, A, redA, (double)h->nGlobalCells, r, r0, part, redB, counter,
+    LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, redA, (double)h->nGlobalCells, r, r0, part, redB, counter,
            multi ? CTL_NONE : CTL_INIT, ks, sc);
     if (multi) {
         if (all_reduce(h, redB, 3 * nrhs)) return 1;
@@ -119,15 +119,15 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
     int spec = std::max(1, h->specIters);
     for (;;) {
         for (int it = 0; it < spec; ++it) {
-            LAUNCH(h, (k_update_p<NR>), grid, BLOCK, N, NP, nModes, ks, rD, r, v, p, y);
-            if (precond_spmv<NR, 0>(h, nModes, y, v, r0, redA, sc)) return 1;
-            LAUNCH(h, (k_make_s<NR>), grid, BLOCK, N, NP, nModes, ks, rD, r, v, sv, z, part, redB, counter, multi ? CTL_NONE : CTL_HALF, sc);
+            LAUNCH(h, (k_update_p<NR>), GRID(h, (k_update_p<NR>), N), BLOCK, N, NP, nModes, ks, rD, r, v, p, y);
+            if (precond_spmv<NR, KT, 0>(h, nModes, y, v, r0, redA, sc)) return 1;
+            LAUNCH(h, (k_make_s<NR>), GRID(h, (k_make_s<NR>), N), BLOCK, N, NP, nModes, ks, rD, r, v, sv, z, part, redB, counter, multi ? CTL_NONE : CTL_HALF, sc);
             if (multi) {
                 if (all_reduce(h, redB, nrhs)) return 1;
                 LAUNCH(h, k_ctl, 1, 32, CTL_HALF, ks, nrhs, redB, sc);
             }
-            if (precond_spmv<NR, 1>(h, nModes, z, t, sv, redC, sc)) return 1;
-            LAUNCH(h, (k_update_x_r<NR>), grid, BLOCK, N, NP, nModes, rp, ks, y, z, sv, t, r0, r, part, redD, counter, multi ? CTL_NONE : CTL_END, sc);
+            if (precond_spmv<NR, KT, 1>(h, nModes, z, t, sv, redC, sc)) return 1;
+            LAUNCH(h, (k_update_x_r<NR>), GRID(h, (k_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, y, z, sv, t, r0, r, part, redD, counter, multi ? CTL_NONE : CTL_END, sc);
             if (multi) {
                 if (all_reduce(h, redD, 2 * nrhs)) return 1;
                 LAUNCH(h, k_ctl, 1, 32, CTL_END, ks, nrhs, redD, sc);
