@@ -336,16 +336,21 @@ __global__ void __launch_bounds__(BLOCK) k_cell_source(MeshView m, ModelParams m
 // ---------------------------------------------------------------- convection: upwind LDU + deferred HRS + boundary folding + relax
 struct Limiter { int hrs; double a0, a1, a2, b0, b1, b2, bnd0, bnd1; };
 
-__device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, double gNd, double upw, const Limiter& lm) {
-    const double gd_up = gPd * upw + (1.0 - upw) * gNd;
+// Deferred-correction face value of gaussDefCmpwConvectionScheme.C:259-274 (swit = 1) for one face and
+// component, in the face's owner(P) -> neighbour(N) frame.  upw in {0,1} makes the reference's blend
+//   (1-a-b)(vN - 2gPd) upw + (1-a-b)(vP + 2gNd)(1-upw) + ((a-1)upw + b(1-upw)) vP + (b upw + (a-1)(1-upw)) vN
+// a selection (x*1 = x, y*0 = 0 exactly), which is how it is evaluated here — no divergent branches.
+__device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, double gNd, bool upw, const Limiter& lm) {
+    const double gd_up = upw ? gPd : gNd;
     const double phitc = 1.0 - ((vN - vP) / (2.0 * gd_up + 1e-18));
-    double alpha, beta;
-    if (phitc <= 0. || phitc >= 1.) { alpha = 1.; beta = 0.; }
-    else if (phitc < lm.bnd0) { alpha = lm.a0; beta = lm.b0; }
-    else if (phitc < lm.bnd1) { alpha = lm.a1; beta = lm.b1; }
-    else { alpha = lm.a2; beta = lm.b2; }
-    return (1.0 - alpha - beta) * (vN - 2.0 * gPd) * upw + (1.0 - alpha - beta) * (vP + 2.0 * gNd) * (1.0 - upw) +
-           ((alpha - 1.0) * upw + beta * (1.0 - upw)) * vP + (beta * upw + (alpha - 1.0) * (1.0 - upw)) * vN;
+    const bool out = (phitc <= 0.) || (phitc >= 1.);
+    const bool s0 = phitc < lm.bnd0, s1 = phitc < lm.bnd1;
+    const double alpha = out ? 1.0 : (s0 ? lm.a0 : (s1 ? lm.a1 : lm.a2));
+    const double beta = out ? 0.0 : (s0 ? lm.b0 : (s1 ? lm.b1 : lm.b2));
+    const double oab = 1.0 - alpha - beta;
+    const double far = upw ? (vN - 2.0 * gPd) : (vP + 2.0 * gNd);
+    const double cP = upw ? (alpha - 1.0) : beta, cN = upw ? beta : (alpha - 1.0);
+    return oab * far + cP * vP + cN * vN;
 }
 
 // Convection operator (tile kernel, see above).  Phase 1 stages per slot: neighbour, flags, the signed
@@ -355,7 +360,7 @@ __device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, do
 // relax), the deferred high-resolution correction, boundary source.
 enum { SLOT_CELL = 1, SLOT_OWNER = 2, SLOT_UPW = 4, SLOT_GHOST = 8, SLOT_PATCH = 16, SLOT_PATCH_ZG = 32 };
 
-__global__ void __launch_bounds__(TILE * 6) k_convect(MeshView m, CompList cl, Limiter lim, int noConv, double rDeltaT, double relax, int writeMatrix,
+__global__ void __launch_bounds__(TILE * 6, 7) k_convect(MeshView m, CompList cl, Limiter lim, int noConv, double rDeltaT, double relax, int writeMatrix,
                                                        const double* __restrict__ phi, const double* __restrict__ theta, const double* __restrict__ thetaB,
                                                        const double* __restrict__ grad, double* __restrict__ bsrc, double* __restrict__ diag,
                                                        double* __restrict__ rD, double* __restrict__ Fs) {
@@ -401,36 +406,46 @@ __global__ void __launch_bounds__(TILE * 6) k_convect(MeshView m, CompList cl, L
     const int k = cl.c[grp];
     const double* tk = theta + (size_t)k * m.NP;
     const double tP = tk[c];
-    double D = rDeltaT * m.V[c];   // ddt diag + negSumDiag
-    double sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0, bnd = 0;
-    for (int s = 0; s < K; ++s) {
-        const int i = s * TILE + lane;
-        const int flag = sFlag[i];
-        const double F = sF[i];
-        if (flag & SLOT_CELL) {
-            if (!(flag & SLOT_GHOST)) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
-            else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
-        } else if (flag & SLOT_PATCH) {
-            if (flag & SLOT_PATCH_ZG) { iCplain += F; iCplainAbs += fabs(F); }
-            else bnd += -F * thetaB[(size_t)k * m.nB + (-sNb[i] - 2)];
+    const int KT_ = K * TILE;
+    const double *pF = sF + lane, *pDx = sD + lane, *pDy = pDx + KT_, *pDz = pDy + KT_;
+    const int *pNb = sNb + lane, *pFlag = sFlag + lane;
+    // ---- diagonal: only needed by the warp that writes it, or by every component when relax() is active
+    double D = 0, sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0;
+    if (relax > 0 || (writeMatrix && grp == 0)) {
+        D = rDeltaT * m.V[c];   // ddt diag + negSumDiag
+        for (int s = 0; s < K; ++s) {
+            const int flag = pFlag[s * TILE];
+            const double F = pF[s * TILE];
+            if (flag & SLOT_CELL) {
+                if (!(flag & SLOT_GHOST)) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
+                else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
+            } else if (flag & SLOT_PATCH_ZG) { iCplain += F; iCplainAbs += fabs(F); }
         }
     }
-    double sou = 0;
-    if (hrs) {
-        const double* gk = grad + (size_t)(3 * k) * m.NP;
-        const double gcx = gk[c], gcy = gk[(size_t)m.NP + c], gcz = gk[2 * (size_t)m.NP + c];
+    // ---- deferred high-resolution correction + fixedValue patch source
+    double sou = 0, bnd = 0;
+    {
+        const double* gx = grad + (size_t)(3 * k) * m.NP;
+        const double* gy = gx + m.NP;
+        const double* gz = gy + m.NP;
+        double gcx = 0, gcy = 0, gcz = 0;
+        if (hrs) { gcx = gx[c]; gcy = gy[c]; gcz = gz[c]; }
+        const Limiter L = lim;
 #pragma unroll 2
         for (int s = 0; s < K; ++s) {
-            const int i = s * TILE + lane;
-            const int flag = sFlag[i];
-            if (!(flag & SLOT_CELL)) continue;
-            const int nb = sNb[i];
-            const double gnx = gk[nb], gny = gk[(size_t)m.NP + nb], gnz = gk[2 * (size_t)m.NP + nb], vn = tk[nb];
-            const double dx = sD[i], dy = sD[K * TILE + i], dz = sD[2 * K * TILE + i];
-            const double gc = gcx * dx + gcy * dy + gcz * dz, gn = gnx * dx + gny * dy + gnz * dz;
-            const double upw = (flag & SLOT_UPW) ? 1.0 : 0.0;
-            const double v = (flag & SLOT_OWNER) ? phif_defc(tP, vn, gc, gn, upw, lim) : phif_defc(vn, tP, gn, gc, upw, lim);
-            sou += v * sF[i];   // souT[own] += v*phi ; souT[nei] -= v*phi
+            const int flag = pFlag[s * TILE];
+            if (flag & SLOT_CELL) {
+                if (!hrs) continue;
+                const int nb = pNb[s * TILE];
+                const double gnx = gx[nb], gny = gy[nb], gnz = gz[nb], vn = tk[nb];
+                const double dx = pDx[s * TILE], dy = pDy[s * TILE], dz = pDz[s * TILE];
+                const double gc = gcx * dx + gcy * dy + gcz * dz, gn = gnx * dx + gny * dy + gnz * dz;
+                const bool own = flag & SLOT_OWNER;
+                const double v = phif_defc(own ? tP : vn, own ? vn : tP, own ? gc : gn, own ? gn : gc, (flag & SLOT_UPW) != 0, L);
+                sou += v * pF[s * TILE];   // souT[own] += v*phi ; souT[nei] -= v*phi
+            } else if ((flag & (SLOT_PATCH | SLOT_PATCH_ZG)) == SLOT_PATCH) {
+                bnd += -pF[s * TILE] * thetaB[(size_t)k * m.nB + (-pNb[s * TILE] - 2)];
+            }
         }
     }
     double add = 0;
