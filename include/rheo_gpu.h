@@ -171,6 +171,11 @@ int rheo_gpu_eig_exp(int32_t device, int32_t n, const double* theta6, double* ei
 
 const char* rheo_gpu_last_error(void);
 
+/* sizeof() of the public structs as compiled into the library, in the order RheoPatchDesc, RheoMeshDesc,
+ * RheoModelDesc, RheoSchemeCtl, RheoStepStats, RheoSynthSpec, RheoPatchRule, RheoPatchSpec — lets a binding
+ * (ctypes here, cgo/JNI elsewhere) verify its mirror of the layouts before the first call. */
+int rheo_gpu_abi_sizes(int32_t* out8);
+
 #ifdef __cplusplus
 }
 #endif

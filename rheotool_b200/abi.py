@@ -115,6 +115,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_synchronize": (C.c_int, [_P]),
     "rheo_gpu_eig_exp": (C.c_int, [_I, _I, _P, _P, _P]),
     "rheo_gpu_last_error": (C.c_char_p, []),
+    "rheo_gpu_abi_sizes": (C.c_int, [_P]),
 }
 
 _lib = None

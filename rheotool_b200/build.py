@@ -73,12 +73,5 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
-def build_oracle() -> Path:
-    """Build the CPU oracle (test infrastructure) with its own Makefile."""
-    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
-    return ROOT / "oracle" / "_build" / "liboracle.so"
-
-
 if __name__ == "__main__":
     print(build_library(force="--force" in sys.argv, verbose=True))
-    print(build_oracle())

@@ -185,7 +185,7 @@ Limiter make_limiter(int lim) {
 }
 
 // greedy colouring + colour-major permutation (the integer contract; restated independently in
-// oracle/renumber_ref.py and compared bit-exactly by the tests)
+// tests' numpy mesh reference and compared bit-exactly)
 int colour_renumber(int n, int nInt, const int32_t* own, const int32_t* nei, std::vector<int>& perm, std::vector<int>& colourStart) {
     std::vector<int> start((size_t)n + 1, 0);
     for (int f = 0; f < nInt; ++f) { start[own[f] + 1]++; start[nei[f] + 1]++; }
@@ -488,7 +488,7 @@ template <class Kern> int resident_grid(RheoGpu* h, Kern kern, long n) {
 int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
     if (h->ctl.ddt != RHEO_DDT_EULER) return fail("rheo_gpu_step: only the Euler ddt scheme is implemented");
-    if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB) return fail("rheo_gpu_step: only PBiCGStab is implemented on the device (PBiCG is available in the oracle)");
+    if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB) return fail("rheo_gpu_step: only PBiCGStab is implemented on the device (fvSolution solver PBiCGStab)");
     const int N = h->N, NP = h->NP, grid = cdiv(N, BLOCK);
     const int nModes = (int)h->modes.size();
     const double rDeltaT = 1.0 / dt;
@@ -831,6 +831,14 @@ int rheo_gpu_eig_exp(int32_t device, int32_t n, const double* theta6, double* ei
     CK(cudaMemcpy(eigvals9, b, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(eigvecs9, c, (size_t)n * 9 * 8, cudaMemcpyDeviceToHost));
     cudaFree(a); cudaFree(b); cudaFree(c);
+    return 0;
+}
+
+int rheo_gpu_abi_sizes(int32_t* out8) {
+    if (!out8) return fail("rheo_gpu_abi_sizes: null argument");
+    const size_t sz[8] = {sizeof(RheoPatchDesc), sizeof(RheoMeshDesc), sizeof(RheoModelDesc), sizeof(RheoSchemeCtl),
+                          sizeof(RheoStepStats), sizeof(RheoSynthSpec), sizeof(RheoPatchRule), sizeof(RheoPatchSpec)};
+    for (int i = 0; i < 8; ++i) out8[i] = (int32_t)sz[i];
     return 0;
 }
 

@@ -68,13 +68,13 @@ class HostMesh:
         self.n_boundary = self.n_faces - self.n_internal
         as_np = np.ctypeslib.as_array
         self.owner = as_np(d.owner, (self.n_faces,))
-        self.neighbour = as_np(d.neighbour, (max(self.n_internal, 1),))[: self.n_internal]
+        self.neighbour = as_np(d.neighbour, (self.n_internal,)) if self.n_internal else np.zeros(0, dtype=np.int32)
         self.Sf = as_np(d.Sf, (self.n_faces, 3))
         self.Cf = as_np(d.Cf, (self.n_faces, 3))
         self.C = as_np(d.C, (self.n_cells, 3))
         self.V = as_np(d.V, (self.n_cells,))
         self.weights = as_np(d.weights, (self.n_faces,))
-        self.nbr_C = as_np(d.nbr_C, (max(self.n_boundary, 1), 3))[: self.n_boundary]
+        self.nbr_C = as_np(d.nbr_C, (self.n_boundary, 3)) if self.n_boundary else np.zeros((0, 3))
         self.patches = [d.patches[i] for i in range(d.n_patches)]
         self.solved = [int(v) for v in d.solved_components]
         self.patch_names = list(patch_names) if patch_names else []

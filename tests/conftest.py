@@ -19,7 +19,8 @@ def _built_libraries():
     if not abi.lib_path().exists():
         build.build_library()
     if not (ROOT / "oracle" / "_build" / "liboracle.so").exists():
-        build.build_oracle()
+        from oracle import oracle as orc
+        orc.build()
     yield
 
 

@@ -1,0 +1,57 @@
+"""N > 1: one rank per GPU (processor patches + NCCL halo swaps + all-reduced Krylov scalars) against the
+oracle on ONE rank, i.e. decomposePar + mpirun must not change the answer.
+Needs >= 2 CUDA devices (gpurun --gpus 2); skipped otherwise."""
+import socket
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import Setup, rel_l2, tight
+from rheotool_b200 import abi, cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    return abi.lib().rheo_gpu_device_count()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("case,scale,decomp,steps", [
+    ("C3", 4 / 19, (2, 1, 1), 2),
+    ("C2", 1 / 9, (2, 1, 1), 2),
+    ("C4", 14 / 252, (2, 1, 1), 1),
+    ("C5", 20 / 400, (2, 2, 1), 2),
+    ("C5", 20 / 400, (2, 2, 2), 1),
+])
+def test_decomposed_gpu_run_matches_single_rank_oracle(case, scale, decomp, steps):
+    world = decomp[0] * decomp[1] * decomp[2]
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs, have {_n_gpus()}")
+    import torch.multiprocessing as mp
+    from mp_worker import gpu_rank
+    tol = 1e-15
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(gpu_rank, args=(world, _free_port(), case, scale, decomp, steps, td, tol), nprocs=world, join=True)
+        ranks = [dict(np.load(Path(td) / f"gpu_rank{r}.npz")) for r in range(world)]
+    spec = cases.by_name(case, scale)
+    s = Setup(spec)
+    assert float(ranks[0]["dt"]) == pytest.approx(s.dt, rel=1e-12)
+    oc = s.oracle(tight(spec.schemes, tol))
+    for _ in range(steps):
+        oc.store_old_time(); oc.step(s.dt)
+    for mi in range(len(spec.models)):
+        for name, fld in (("theta", abi.FIELD_THETA), ("tau", abi.FIELD_TAU)):
+            ref = oc.get(0, mi, fld)
+            got = np.full_like(ref, np.nan)
+            for d in ranks:
+                got[d["cells"]] = d[f"{name}{mi}"]
+            err = rel_l2(got, ref)
+            assert err <= 1e-10, f"{case} {decomp} mode {mi} {name}: rel L2 {err:.3e}"
