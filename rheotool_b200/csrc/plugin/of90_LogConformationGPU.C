@@ -1,0 +1,369 @@
+/*---------------------------------------------------------------------------*\
+  of90_LogConformationGPU.C — see the header.  OpenFOAM-9 + rheoTool only.
+
+  Registered type names (constant/constitutiveProperties -> parameters -> type):
+      Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  multiModeLogGPU
+  Dictionary keys are those of the CPU models (Oldroyd_BLog.C:114-119,
+  GiesekusLog.C:117, PTTLog.C:129-139, FENE_PLog.C:114-119, multiMode.C:73-92);
+  fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler,
+  fvSolution solvers.theta<name> supplies tolerance/relTol/minIter/maxIter.
+\*---------------------------------------------------------------------------*/
+#include "of90_LogConformationGPU.H"
+#include "addToRunTimeSelectionTable.H"
+#include "processorFvPatch.H"
+#include "emptyFvPatch.H"
+#include "wallFvPatch.H"
+#include "fixedValueFvPatchFields.H"
+#include "zeroGradientFvPatchFields.H"
+#include "linearExtrapolationFvPatchField.H"
+#include "extrapolatedCalculatedFvPatchFields.H"
+#include "Pstream.H"
+
+namespace Foam
+{
+namespace constitutiveEqs
+{
+    defineTypeNameAndDebug(LogConformationGPU, 0);
+
+    // the same class under the five user-facing names
+    #define RHEO_GPU_REGISTER(ClassAlias, UserName)                                              \
+        class ClassAlias : public LogConformationGPU                                             \
+        {                                                                                        \
+        public:                                                                                  \
+            TypeName(UserName);                                                                  \
+            ClassAlias(const word& n, const volVectorField& U, const surfaceScalarField& phi,    \
+                       const dictionary& d) : LogConformationGPU(n, U, phi, d) {}                \
+        };                                                                                       \
+        defineTypeNameAndDebug(ClassAlias, 0);                                                   \
+        addToRunTimeSelectionTable(constitutiveEq, ClassAlias, dictionary);
+
+    RHEO_GPU_REGISTER(Oldroyd_BLogGPU, "Oldroyd-BLogGPU")
+    RHEO_GPU_REGISTER(GiesekusLogGPU, "GiesekusLogGPU")
+    RHEO_GPU_REGISTER(PTTLogGPU, "PTTLogGPU")
+    RHEO_GPU_REGISTER(FENE_PLogGPU, "FENE-PLogGPU")
+    RHEO_GPU_REGISTER(multiModeLogGPU, "multiModeLogGPU")
+}
+}
+
+using namespace Foam;
+using namespace Foam::constitutiveEqs;
+
+// * * * * * * * * * * * * * * * helpers * * * * * * * * * * * * * * * * * * //
+
+void LogConformationGPU::check(int rc, const char* where) const
+{
+    if (rc)
+    {
+        // newConstitutiveEq.C:47-58 convention: fatal, no return codes above the C layer
+        FatalErrorInFunction << where << ": " << rheo_gpu_last_error() << exit(FatalError);
+    }
+}
+
+void LogConformationGPU::readMode(const word& type, const dictionary& dict, RheoModelDesc& m) const
+{
+    std::memset(&m, 0, sizeof(m));
+    m.rho    = dimensionedScalar(dict.lookup("rho")).value();
+    m.etaS   = dimensionedScalar(dict.lookup("etaS")).value();
+    m.etaP   = dimensionedScalar(dict.lookup("etaP")).value();
+    m.lambda = dimensionedScalar(dict.lookup("lambda")).value();
+    m.L2 = 100; m.ml_alpha = 1; m.ml_beta = 1; m.ml_rtol = 1e-12; m.ml_max_iter = 200;
+    if (type == "Oldroyd-BLogGPU" || type == "Oldroyd-BLog") m.model = RHEO_MODEL_OLDROYD_B_LOG;
+    else if (type == "GiesekusLogGPU" || type == "GiesekusLog")
+    {
+        m.model = RHEO_MODEL_GIESEKUS_LOG;
+        m.alpha = dimensionedScalar(dict.lookup("alpha")).value();
+    }
+    else if (type == "PTTLogGPU" || type == "PTTLog")
+    {
+        m.model   = RHEO_MODEL_PTT_LOG;
+        m.epsilon = dimensionedScalar(dict.lookup("epsilon")).value();
+        m.zeta    = dimensionedScalar(dict.lookup("zeta")).value();
+        const word f(dict.lookup("destructionFunctionType"));      // PTTLog.C:41-50
+        m.ptt_function = (f == "linear") ? RHEO_PTT_LINEAR : (f == "exponential") ? RHEO_PTT_EXPONENTIAL : RHEO_PTT_GENERALIZED;
+        if (m.ptt_function == RHEO_PTT_GENERALIZED)                 // PTTLog.C:143-170
+        {
+            m.ml_alpha = dimensionedScalar(dict.lookup("alpha")).value();
+            m.ml_beta  = dimensionedScalar(dict.lookup("beta")).value();
+        }
+    }
+    else if (type == "FENE-PLogGPU" || type == "FENE-PLog")
+    {
+        m.model = RHEO_MODEL_FENE_P_LOG;
+        m.L2 = dimensionedScalar(dict.lookup("L2")).value();
+    }
+    else
+    {
+        FatalErrorInFunction << "Unknown GPU constitutiveEq type " << type << exit(FatalError);
+    }
+    // thermoLambda / thermoEta sub-dictionaries: only the Constant function (the default when absent,
+    // thermo/thermoFunctions/thermoFunction/newThermoFunction.C:39-41) is supported on the device
+    if (dict.found("thermoLambda") || dict.found("thermoEta"))
+    {
+        FatalErrorInFunction << "temperature-dependent lambda/etaP are not available on the GPU path" << exit(FatalError);
+    }
+}
+
+void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
+{
+    std::memset(&ctl_, 0, sizeof(ctl_));
+    ITstream& div = mesh.divScheme("div(phi," + thetaName + ")");
+    word w(div);
+    if (w == "bounded") FatalErrorInFunction << "bounded GaussDefCmpw is not available on the GPU path" << exit(FatalError);
+    if (w != "GaussDefCmpw") FatalErrorInFunction << "div(phi," << thetaName << ") must be GaussDefCmpw" << exit(FatalError);
+    const word lim(div);
+    const char* names[] = {"upwind", "cubista", "minmod", "smart", "waceb", "superbee", "none"};   // limiters.H:48-98
+    ctl_.limiter = -1;
+    for (int i = 0; i < 7; ++i) if (lim == names[i]) ctl_.limiter = i;
+    if (word(mesh.ddtScheme("ddt(" + thetaName + ")")) != "Euler")
+        FatalErrorInFunction << "only ddtSchemes Euler is available on the GPU path" << exit(FatalError);
+    ctl_.ddt = RHEO_DDT_EULER;
+    const dictionary& sol = mesh.solverDict(thetaName);
+    const word solver(sol.lookup("solver"));
+    // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs PBiCGStab
+    ctl_.solver    = RHEO_SOLVER_PBICGSTAB;
+    ctl_.tolerance = sol.lookupOrDefault<scalar>("tolerance", 1e-6);
+    ctl_.rel_tol   = sol.lookupOrDefault<scalar>("relTol", 0);
+    ctl_.min_iter  = sol.lookupOrDefault<label>("minIter", 0);
+    ctl_.max_iter  = sol.lookupOrDefault<label>("maxIter", 1000);
+    ctl_.relax     = mesh.relaxEquation(thetaName) ? mesh.equationRelaxationFactor(thetaName) : 0;
+}
+
+void LogConformationGPU::buildMeshDesc
+(
+    const fvMesh& mesh,
+    List<int32_t>& owner, List<int32_t>& neighbour,
+    List<RheoPatchDesc>& patches, vectorField& nbrC, scalarField& weights,
+    RheoMeshDesc& d
+) const
+{
+    const label nF = mesh.nFaces(), nI = mesh.nInternalFaces();
+    owner.setSize(nF); neighbour.setSize(nI);
+    forAll(owner, f) owner[f] = mesh.faceOwner()[f];
+    forAll(neighbour, f) neighbour[f] = mesh.faceNeighbour()[f];
+    weights.setSize(nF, 1.0);
+    nbrC.setSize(nF - nI, vector::zero);
+    const surfaceScalarField& w = mesh.weights();
+    forAll(w, f) weights[f] = w[f];
+    const volSymmTensorField& th = theta_[0];
+    const volSymmTensorField& ta = tau_[0];
+    patches.setSize(mesh.boundary().size());
+    forAll(mesh.boundary(), pI)
+    {
+        const fvPatch& p = mesh.boundary()[pI];
+        RheoPatchDesc& q = patches[pI];
+        q.start = p.start(); q.size = p.size(); q.nbr_rank = -1;
+        if (isA<processorFvPatch>(p))
+        {
+            q.type = RHEO_PATCH_PROCESSOR; q.theta_bc = q.tau_bc = RHEO_BC_PROCESSOR;
+            q.nbr_rank = refCast<const processorFvPatch>(p).neighbProcNo();
+            const vectorField nc(mesh.C().boundaryField()[pI].patchNeighbourField());
+            forAll(nc, i) { nbrC[p.start() - nI + i] = nc[i]; weights[p.start() + i] = w.boundaryField()[pI][i]; }
+        }
+        else if (isA<emptyFvPatch>(p)) { q.type = RHEO_PATCH_EMPTY; q.theta_bc = q.tau_bc = RHEO_BC_EMPTY; }
+        else
+        {
+            q.type = isA<wallFvPatch>(p) ? RHEO_PATCH_WALL : RHEO_PATCH_PATCH;
+            const fvPatchSymmTensorField& tb = th.boundaryField()[pI];
+            const fvPatchSymmTensorField& ub = ta.boundaryField()[pI];
+            q.theta_bc = isA<zeroGradientFvPatchSymmTensorField>(tb) ? RHEO_BC_ZERO_GRADIENT : RHEO_BC_FIXED_VALUE;
+            q.tau_bc = isA<linearExtrapolationFvPatchField<symmTensor>>(ub) ? RHEO_BC_LINEAR_EXTRAPOLATION
+                     : isA<zeroGradientFvPatchSymmTensorField>(ub) ? RHEO_BC_ZERO_GRADIENT : RHEO_BC_FIXED_VALUE;
+        }
+    }
+    d.n_cells = mesh.nCells(); d.n_faces = nF; d.n_internal_faces = nI; d.n_patches = patches.size();
+    d.owner = owner.begin(); d.neighbour = neighbour.begin();
+    d.Sf = reinterpret_cast<const double*>(mesh.faceAreas().begin());      // vector == 3 contiguous doubles
+    d.Cf = reinterpret_cast<const double*>(mesh.faceCentres().begin());
+    d.C  = reinterpret_cast<const double*>(mesh.cellCentres().begin());
+    d.V  = mesh.cellVolumes().begin();
+    d.weights = weights.begin();
+    d.nbr_C = reinterpret_cast<const double*>(nbrC.begin());
+    d.patches = patches.begin();
+    const Vector<label>& sd = mesh.solutionD();                            // validComponents<symmTensor>
+    const int valid[6] = {sd.x() > 0, sd.x() > 0 && sd.y() > 0, sd.x() > 0 && sd.z() > 0, sd.y() > 0, sd.y() > 0 && sd.z() > 0, 1};
+    for (int c = 0; c < 6; ++c) d.solved_components[c] = valid[c];
+    // 2-D in (x,y): XX XY YY ZZ solved
+    if (sd.z() < 0) { d.solved_components[2] = 0; d.solved_components[4] = 0; d.solved_components[5] = 1; }
+}
+
+// * * * * * * * * * * * * * * * * Constructor * * * * * * * * * * * * * * * * //
+
+LogConformationGPU::LogConformationGPU
+(
+    const word& name,
+    const volVectorField& U,
+    const surfaceScalarField& phi,
+    const dictionary& dict
+)
+:
+    constitutiveEq(name, U, phi),
+    tauTotal_
+    (
+        IOobject("tauGPUTotal" + name, U.time().timeName(), U.mesh(), IOobject::NO_READ, IOobject::NO_WRITE),
+        U.mesh(),
+        dimensionedSymmTensor("zero", dimensionSet(1, -1, -2, 0, 0, 0, 0), symmTensor::zero),
+        extrapolatedCalculatedFvPatchField<symmTensor>::typeName
+    ),
+    rho_("rho", dimDensity, 0), etaS_("etaS", dimPressure*dimTime, 0), etaP_("etaP", dimPressure*dimTime, 0),
+    gpu_(nullptr),
+    lastTimeIndex_(-1)
+{
+    const fvMesh& mesh = U.mesh();
+    const word type(dict.lookup("type"));
+    wordList suffix;
+    List<const dictionary*> dicts;
+    PtrList<entry> modelEntries;
+    if (type == "multiModeLogGPU")                                           // multiMode.C:73-92
+    {
+        modelEntries.transfer(PtrList<entry>(dict.lookup("models"))());
+        forAll(modelEntries, i) { suffix.append(name + modelEntries[i].keyword()); dicts.append(&modelEntries[i].dict()); }
+    }
+    else { suffix.append(name); dicts.append(&dict); }
+
+    modes_.setSize(suffix.size());
+    forAll(suffix, i)
+    {
+        const word sub = (type == "multiModeLogGPU") ? word(dicts[i]->lookup("type")) : type;
+        readMode(sub, *dicts[i], modes_[i]);
+        etaS_.value() += modes_[i].etaS; etaP_.value() += modes_[i].etaP; rho_.value() += modes_[i].rho/suffix.size();
+        // same IOobjects as the CPU models (Oldroyd_BLog.C:52-113)
+        tau_.append(new volSymmTensorField(IOobject("tau" + suffix[i], U.time().timeName(), mesh, IOobject::MUST_READ, IOobject::AUTO_WRITE), mesh));
+        theta_.append(new volSymmTensorField(IOobject("theta" + suffix[i], U.time().timeName(), mesh, IOobject::MUST_READ, IOobject::AUTO_WRITE), mesh));
+        eigVals_.append(new volTensorField(IOobject("eigVals" + suffix[i], U.time().timeName(), mesh, IOobject::READ_IF_PRESENT, IOobject::AUTO_WRITE),
+                                           mesh, dimensionedTensor("I", dimless, pTraits<tensor>::I), extrapolatedCalculatedFvPatchField<tensor>::typeName));
+        eigVecs_.append(new volTensorField(IOobject("eigVecs" + suffix[i], U.time().timeName(), mesh, IOobject::READ_IF_PRESENT, IOobject::AUTO_WRITE),
+                                           mesh, dimensionedTensor("I", dimless, pTraits<tensor>::I), extrapolatedCalculatedFvPatchField<tensor>::typeName));
+    }
+    checkForStab(dict);                                                     // constitutiveEq.C:430-439
+    readSchemes(mesh, "theta" + suffix[0]);
+
+    List<int32_t> owner, neighbour; List<RheoPatchDesc> patches; vectorField nbrC; scalarField weights;
+    RheoMeshDesc d;
+    buildMeshDesc(mesh, owner, neighbour, patches, nbrC, weights, d);
+    // one rank <-> one GPU: ranks of a node take the node's devices round-robin
+    const int nDev = rheo_gpu_device_count();
+    if (nDev < 1) FatalErrorInFunction << "no CUDA device: the GPU stress step has no CPU fallback" << exit(FatalError);
+    check(rheo_gpu_create(&d, modes_.begin(), modes_.size(), &ctl_, Pstream::myProcNo() % nDev, &gpu_), "rheo_gpu_create");
+    if (Pstream::parRun())
+    {
+        List<char> id(128, 0);
+        if (Pstream::master()) check(rheo_gpu_nccl_unique_id(id.begin()), "rheo_gpu_nccl_unique_id");
+        Pstream::scatter(id);                                               // MPI_Bcast of the NCCL unique id
+        check(rheo_gpu_comm_init(gpu_, Pstream::myProcNo(), Pstream::nProcs(), id.begin()), "rheo_gpu_comm_init");
+    }
+    uploadState();
+}
+
+LogConformationGPU::~LogConformationGPU()
+{
+    rheo_gpu_destroy(gpu_);
+}
+
+// * * * * * * * * * * * * * * * Member Functions  * * * * * * * * * * * * * //
+
+static void gatherBoundary(const GeometricField<symmTensor, fvPatchField, volMesh>& f, symmTensorField& out, label nI)
+{
+    out.setSize(f.mesh().nFaces() - nI, symmTensor::zero);
+    forAll(f.boundaryField(), pI)
+    {
+        const fvPatchSymmTensorField& pf = f.boundaryField()[pI];
+        if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
+        forAll(pf, i) out[pf.patch().start() - nI + i] = pf[i];
+    }
+}
+
+void LogConformationGPU::uploadState()
+{
+    const label nI = U().mesh().nInternalFaces();
+    forAll(theta_, i)
+    {
+        symmTensorField thB, tauB;
+        gatherBoundary(theta_[i], thB, nI);
+        gatherBoundary(tau_[i], tauB, nI);
+        // symmTensor / tensor are 6 / 9 contiguous doubles in OpenFOAM's component order = the C-ABI's AoS order
+        check(rheo_gpu_upload_state(gpu_, i,
+              reinterpret_cast<const double*>(theta_[i].primitiveField().begin()),
+              reinterpret_cast<const double*>(tau_[i].primitiveField().begin()),
+              reinterpret_cast<const double*>(eigVals_[i].primitiveField().begin()),
+              reinterpret_cast<const double*>(eigVecs_[i].primitiveField().begin()),
+              reinterpret_cast<const double*>(thB.begin()), reinterpret_cast<const double*>(tauB.begin())),
+              "rheo_gpu_upload_state");
+    }
+}
+
+void LogConformationGPU::downloadAll()
+{
+    forAll(theta_, i)
+    {
+        check(rheo_gpu_download(gpu_, i, RHEO_FIELD_THETA,   reinterpret_cast<double*>(theta_[i].primitiveFieldRef().begin())), "download theta");
+        check(rheo_gpu_download(gpu_, i, RHEO_FIELD_EIGVALS, reinterpret_cast<double*>(eigVals_[i].primitiveFieldRef().begin())), "download eigVals");
+        check(rheo_gpu_download(gpu_, i, RHEO_FIELD_EIGVECS, reinterpret_cast<double*>(eigVecs_[i].primitiveFieldRef().begin())), "download eigVecs");
+        theta_[i].correctBoundaryConditions();
+        eigVals_[i].correctBoundaryConditions();
+        eigVecs_[i].correctBoundaryConditions();
+    }
+}
+
+void LogConformationGPU::correct(const volScalarField* alpha, const volTensorField* gradU)
+{
+    if (alpha || gradU)
+    {
+        FatalErrorInFunction << "two-phase (alpha) and caller-supplied gradU (filmModel.C:408) are not available on the GPU path"
+                             << exit(FatalError);
+    }
+    const fvMesh& mesh = U().mesh();
+    const label nI = mesh.nInternalFaces();
+    // U boundary values and phi (internal + boundary) in face order
+    vectorField Ub(mesh.nFaces() - nI, vector::zero);
+    scalarField ph(mesh.nFaces(), 0.0);
+    forAll(phi(), f) ph[f] = phi()[f];
+    forAll(U().boundaryField(), pI)
+    {
+        const fvPatch& p = mesh.boundary()[pI];
+        if (!p.size() || isA<emptyFvPatch>(p)) continue;
+        forAll(p, i)
+        {
+            if (!p.coupled()) Ub[p.start() - nI + i] = U().boundaryField()[pI][i];
+            ph[p.start() + i] = phi().boundaryField()[pI][i];
+        }
+    }
+    // theta_.oldTime() bookkeeping of fvm::ddt (Oldroyd_BLog.C:143): once per time step, not per inner iteration
+    const bool newStep = U().time().timeIndex() != lastTimeIndex_;
+    lastTimeIndex_ = U().time().timeIndex();
+
+    symmTensorField tauB(mesh.nFaces() - nI);
+    List<RheoStepStats> stats(modes_.size());
+    check(rheo_gpu_correct(gpu_,
+          reinterpret_cast<const double*>(U().primitiveField().begin()), reinterpret_cast<const double*>(Ub.begin()), ph.begin(),
+          U().time().deltaTValue(), newStep ? 1 : 0,
+          reinterpret_cast<double*>(tauTotal_.primitiveFieldRef().begin()), reinterpret_cast<double*>(tauB.begin()), stats.begin()),
+          "rheo_gpu_correct");
+
+    // OpenFOAM-style solver report (SolverPerformance<symmTensor>)
+    static const char* cmpt[6] = {"XX", "XY", "XZ", "YY", "YZ", "ZZ"};
+    forAll(stats, i) for (int c = 0; c < 6; ++c) if (stats[i].n_iterations[c] || stats[i].initial_residual[c] > 0)
+        Info<< "B200-PBiCGStab:  Solving for " << theta_[i].name() << cmpt[c] << ", Initial residual = " << stats[i].initial_residual[c]
+            << ", Final residual = " << stats[i].final_residual[c] << ", No Iterations " << stats[i].n_iterations[c] << endl;
+
+    // boundary values of tau for the momentum predictor (single mode: patch values from the device;
+    // multi-mode: extrapolated, as multiMode::tau() rebuilds them from the sum)
+    if (modes_.size() == 1)
+    {
+        forAll(tauTotal_.boundaryField(), pI)
+        {
+            fvPatchSymmTensorField& pf = tauTotal_.boundaryFieldRef()[pI];
+            if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
+            forAll(pf, i) pf[i] = tauB[pf.patch().start() - nI + i];
+        }
+        tau_[0].primitiveFieldRef() = tauTotal_.primitiveField();
+        tau_[0].boundaryFieldRef() = tauTotal_.boundaryField();
+    }
+    else tauTotal_.correctBoundaryConditions();
+
+    if (U().time().writeTime())
+    {
+        downloadAll();
+        if (modes_.size() > 1) forAll(tau_, i)
+            check(rheo_gpu_download(gpu_, i, RHEO_FIELD_TAU, reinterpret_cast<double*>(tau_[i].primitiveFieldRef().begin())), "download tau");
+    }
+}
