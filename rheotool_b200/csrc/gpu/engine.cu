@@ -108,6 +108,9 @@ struct RheoGpu {
     std::vector<int> h_nbr, h_fidx;
     std::vector<RheoPatchDesc> patches;
     std::vector<HaloSeg> segs;
+    // boundary-face ranges (b0, len) whose host values are read at upload: U_b skips empty and processor patches,
+    // phi skips empty patches (OpenFOAM's emptyFvPatchField has size 0: there is nothing to send)
+    std::vector<std::pair<int, int>> ubRanges, phiBRanges;
     // device mesh
     DevBuf d_perm, d_faceOld, d_nbr, d_nbrA, d_fidx, d_Sf, d_w, d_C, d_V, d_rV, d_bcell, d_bkind, d_bthetaBC, d_btauBC, d_CfB;
     DevBuf d_haloCell, d_segStart, d_segLen, d_send, d_recv;
@@ -282,6 +285,20 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
         }
     }
     for (int b = 0; b < nB; ++b) bcell[b] = newOwn[nInt + b];
+    {   // merged upload ranges, in face order
+        std::vector<RheoPatchDesc> ps(h->patches);
+        std::sort(ps.begin(), ps.end(), [](const RheoPatchDesc& a, const RheoPatchDesc& b) { return a.start < b.start; });
+        auto add = [](std::vector<std::pair<int, int>>& r, int b0, int len) {
+            if (len <= 0) return;
+            if (!r.empty() && r.back().first + r.back().second == b0) r.back().second += len;
+            else r.push_back({b0, len});
+        };
+        for (const RheoPatchDesc& p : ps) {
+            if (p.type == RHEO_PATCH_EMPTY) continue;
+            add(h->phiBRanges, p.start - nInt, p.size);
+            if (p.type != RHEO_PATCH_PROCESSOR) add(h->ubRanges, p.start - nInt, p.size);
+        }
+    }
     h->H = H; h->NT = N + H;
     h->NS = round_up(N, 32);
     h->NP = round_up(N + H, 32);
@@ -603,9 +620,13 @@ int put_cells(RheoGpu* h, const double* src, int nc, double* dstPlanes) {
     LAUNCH(h, k_aos_to_soa, cdiv(h->N, BLOCK), BLOCK, h->N, nc, h->d_perm.as<int>(), h->d_stage.as<double>(), dstPlanes, h->NP);
     return 0;
 }
-int put_bfaces(RheoGpu* h, const double* src, int nc, double* dstPlanes) {
+int put_bfaces(RheoGpu* h, const double* src, int nc, double* dstPlanes, const std::vector<std::pair<int, int>>* ranges = nullptr) {
     if (!h->nB) return 0;
-    CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->nB * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!ranges) CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->nB * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else
+        for (const auto& r : *ranges)   // faces outside the ranges keep stale staging values; no kernel reads them
+            CK(cudaMemcpyAsync(h->d_stage.as<double>() + (size_t)r.first * nc, src + (size_t)r.first * nc, (size_t)r.second * nc * sizeof(double),
+                               cudaMemcpyHostToDevice, h->stream));
     LAUNCH(h, k_aos_to_soa, cdiv(h->nB, BLOCK), BLOCK, h->nB, nc, (const int*)nullptr, h->d_stage.as<double>(), dstPlanes, h->nB);
     return 0;
 }
@@ -715,8 +736,10 @@ int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, con
     if (!h || !U || !phi) return fail("rheo_gpu_upload_velocity: null argument");
     CK(cudaSetDevice(h->device));
     if (put_cells(h, U, 3, h->d_U.as<double>())) return 1;
-    if (h->nB && U_b && put_bfaces(h, U_b, 3, h->d_Ub.as<double>())) return 1;
-    CK(cudaMemcpyAsync(h->d_stage.p, phi, (size_t)h->nF * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (h->nB && U_b && put_bfaces(h, U_b, 3, h->d_Ub.as<double>(), &h->ubRanges)) return 1;
+    CK(cudaMemcpyAsync(h->d_stage.p, phi, (size_t)h->nInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    for (const auto& r : h->phiBRanges)
+        CK(cudaMemcpyAsync(h->d_stage.as<double>() + h->nInt + r.first, phi + h->nInt + r.first, (size_t)r.second * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     LAUNCH(h, k_phi_in, cdiv(h->nF, BLOCK), BLOCK, h->nF, h->d_faceOld.as<int>(), h->d_stage.as<double>(), h->d_phi.as<double>());
     return 0;
 }
