@@ -57,9 +57,15 @@ def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int) 
     """Algorithmic bytes one launch moves per cell it processes (d=8, i=4,
     f = internal faces per cell (3 in 3-D, 2 in 2-D), c = solved components x modes)."""
     f = 3 if dims == 3 else 2
-    c = (6 if dims == 3 else 4) * n_modes
-    k = kernel.split("<")[0]
+    c1 = 6 if dims == 3 else 4          # solved components of one mode
+    K = 2 * f                           # slots per cell
+    c = c1 * n_modes
+    k = kernel.strip("()").split("<")[0]
     table = {
+        # theta, U, nbr, rslot, gS, gW, Fell, C, rV+V | A, diag+rD, bsrc, corr (one value per face and component), gradU
+        "k_flux_assemble": (c1 + 3) * 8 + K * 4 + K + 3 * K * 8 + K * 8 + K * 8 + 24 + 16 + K * 8 + 16 + c1 * 8 + f * c1 * 8 + 72,
+        # gradU, theta, thetaOld, lam, R, V, A, corr (inflow faces), bsrc read | bsrc, fFene
+        "k_cell_source2": (9 + 6 + 6 + 3 + 9 + 1) * 8 + K * 8 + f * c1 * 8 + c1 * 8 + 6 * 8 + 8,
         "k_grad_theta": 6 * 8 + f * (4 * 8 + 2 * 4) + 8 + 18 * 8,
         "k_cell_source": (3 + 3 + 9 + 6 + 6 + 1) * 8 + f * (4 * 8 + 2 * 4) + (6 + 1) * 8,
         "k_convect": (6 + 18 + 3 + 12 + 1 + 2) * 8 + f * (8 + 2 * 4) + 2 * f * 8,
@@ -216,6 +222,7 @@ def run_ours(args):
     for _ in range(2):
         g.correct_host(hU.data_ptr(), hUb.data_ptr(), hphi.data_ptr(), dt, True, htau.data_ptr())
     barrier()
+    tb0 = g.transfer_bytes()
     t0 = time.perf_counter()
     e0.record(ext)
     for _ in range(e2e_steps):
@@ -227,8 +234,9 @@ def run_ours(args):
     if n > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_value = n_cells_total * e2e_steps / (float(ms2.item()) * 1e-3) / 1e6
-    h2d = 8 * (U.size + Ub.size + phi.size)
-    d2h = 8 * htau.numel()
+    tb1 = g.transfer_bytes()
+    h2d = (tb1[0] - tb0[0]) // e2e_steps   # counted inside the library from the copies it issued
+    d2h = (tb1[1] - tb0[1]) // e2e_steps
 
     # ---- roofline of the dominant kernel: per-kernel CUDA-event timing pass (serialised launches)
     roof = None

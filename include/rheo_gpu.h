@@ -125,8 +125,9 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
                           const double* eigvals, const double* eigvecs,
                           const double* theta_b, const double* tau_b);
 
-/* U [3*n_cells], U_b [3*n_boundary_faces] (values on processor/empty faces ignored),
- * phi [n_faces] (internal then boundary).  Pageable or pinned host memory. */
+/* U [3*n_cells], U_b [3*n_boundary_faces] (faces of processor/empty patches are neither read nor copied),
+ * phi [n_faces] (internal then boundary; faces of empty patches are neither read nor copied — OpenFOAM's
+ * emptyFvPatchField has size 0, so the shim has nothing to put there).  Pageable or pinned host memory. */
 int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi);
 
 int rheo_gpu_store_old_time(RheoGpu* h);
@@ -154,6 +155,8 @@ int rheo_gpu_get_ell(RheoGpu* h, int32_t* K, int32_t* nbr, int32_t* face);
 int64_t rheo_gpu_launch_count(const RheoGpu* h);
 /* Krylov iterations (max over components and modes) of the last step */
 int rheo_gpu_last_iterations(const RheoGpu* h);
+/* bytes copied host->device / device->host by the upload/download/correct entry points of this handle so far */
+int rheo_gpu_transfer_bytes(const RheoGpu* h, int64_t* h2d, int64_t* d2h);
 /* per-phase device times of the last step measured with CUDA events when enabled (ms):
  * [0] halo+bc  [1] grad(theta)  [2] assemble  [3] solve  [4] eig+tau  [5] tau bc  [6] total */
 int rheo_gpu_set_phase_timing(RheoGpu* h, int32_t enabled);

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "krylov.cuh"
+#include "assembly.cuh"
 #include "rheo_gpu.h"
 
 using namespace rk;
@@ -114,9 +115,13 @@ struct RheoGpu {
     // device mesh
     DevBuf d_perm, d_faceOld, d_nbr, d_nbrA, d_fidx, d_Sf, d_w, d_C, d_V, d_rV, d_bcell, d_bkind, d_bthetaBC, d_btauBC, d_CfB;
     DevBuf d_haloCell, d_segStart, d_segLen, d_send, d_recv;
+    DevBuf d_tileRec;              // per-tile mesh records streamed by k_flux_assemble (assembly.cuh)
+    int nTiles = 0;
     MeshView mv;
     // fields
     DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_grad, d_stage, d_tmpB;
+    DevBuf d_Fell, d_corr, d_gradU;
+    bool assemblyV1 = false;       // RHEO_ASSEMBLY_V1=1: first-version assembly (k_grad_theta + k_cell_source + k_convect), for A/B runs
     std::vector<ModeDev> modes;
     // Krylov
     DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ks, d_partials, d_red, d_counter, d_bcells;
@@ -124,12 +129,14 @@ struct RheoGpu {
     int specIters = 1;             // Krylov iterations launched speculatively per batch (= last step's count)
     int nSms = 148;                // SM count (set at create)
     std::map<const void*, int> residentBlocks;   // kernel -> SM count x resident CTAs per SM
+    std::map<std::pair<const void*, long>, int> fluxBlocks;
     int nBcells = 0;               // cells that own at least one ghost (processor) slot
     // comm
     void* comm = nullptr;
     int rank = 0, nRanks = 1;
     // stats
     long launches = 0;
+    long long h2dBytes = 0, d2hBytes = 0;   // host<->device bytes copied by the upload/download entry points
     int lastIters = 0;
     bool timing = false;
     bool ktiming = false;          // per-kernel CUDA-event timing (bench.py roofline pass; serialises launches)
@@ -366,6 +373,64 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
             for (int e = 0; e < 3; ++e) C[(size_t)e * h->NP + N + ghostOfB[b]] = d->nbr_C[3 * (size_t)b + e];
         }
     }
+    {   // tile records streamed by k_flux_assemble (layout: assembly.cuh, tile_record_bytes)
+        const int nTiles = h->NS / TILE;
+        const size_t recBytes = tile_record_bytes(K);
+        std::vector<unsigned char> rec((size_t)nTiles * recBytes, 0);
+        std::vector<int> slotOfOwner(nInt, 0);
+        for (int s = 0; s < K; ++s)
+            for (int c = 0; c < N; ++c) {
+                const size_t e = (size_t)s * h->NS + c;
+                const int fi = h->h_fidx[e];
+                if (h->h_nbr[e] >= 0 && h->h_nbr[e] < N && fi >= 0) slotOfOwner[fi] = s;
+            }
+        for (int t = 0; t < nTiles; ++t) {
+            unsigned char* base = rec.data() + (size_t)t * recBytes;
+            int* rNb = (int*)base;
+            int* rMeta = rNb + K * TILE;
+            double* rS = (double*)(base + (size_t)2 * K * TILE * sizeof(int));
+            double* rW = rS + 3 * K * TILE;
+            double* rD = rW + K * TILE;
+            double* rRV = rD + 3 * K * TILE;
+            for (int l = 0; l < TILE; ++l) {
+                const int c = t * TILE + l;
+                rRV[l] = c < N ? rV[c] : 0.0;
+                rRV[TILE + l] = c < N ? V[c] : 0.0;
+                for (int s = 0; s < K; ++s) {
+                    const int i = s * TILE + l;
+                    rNb[i] = -1; rMeta[i] = 0;
+                    if (c >= N) continue;
+                    const size_t e = (size_t)s * h->NS + c;
+                    const int nb = h->h_nbr[e];
+                    rNb[i] = nb;
+                    if (nb == -1) continue;
+                    const int fi = h->h_fidx[e];
+                    const int f = fi >= 0 ? fi : ~fi;
+                    const double sg = fi >= 0 ? 1.0 : -1.0;
+                    for (int x = 0; x < 3; ++x) rS[x * K * TILE + i] = sg * Sf[(size_t)x * nF + f];
+                    rW[i] = w[f];
+                    if (nb >= 0) {
+                        const bool own = fi >= 0;   // == (nb > c): faces are in upper-triangular order
+                        int rs = 0;
+                        if (nb < N) {
+                            if (own) {   // find our face in the neighbour's row
+                                for (int s2 = 0; s2 < K; ++s2) if (h->h_nbr[(size_t)s2 * h->NS + nb] == c && h->h_fidx[(size_t)s2 * h->NS + nb] == ~f) rs = s2;
+                            } else rs = slotOfOwner[f];
+                        }
+                        rMeta[i] = SLOT_CELL | (own ? SLOT_OWNER : 0) | (nb >= N ? SLOT_GHOST : 0) | (rs << 8);
+                        for (int x = 0; x < 3; ++x) {   // d = C_N - C_P in the face's owner -> neighbour frame
+                            const double Cc = C[(size_t)x * h->NP + c], Cn = C[(size_t)x * h->NP + nb];
+                            rD[x * K * TILE + i] = own ? Cn - Cc : Cc - Cn;
+                        }
+                    } else {
+                        rMeta[i] = SLOT_PATCH | (bthetaBC[-nb - 2] == RHEO_BC_ZERO_GRADIENT ? SLOT_PATCH_ZG : 0);
+                    }
+                }
+            }
+        }
+        h->nTiles = nTiles;
+        if (upload(h->d_tileRec, rec)) return 1;
+    }
     if (upload(h->d_perm, h->perm) || upload(h->d_faceOld, h->faceOld) || upload(h->d_nbr, h->h_nbr) || upload(h->d_nbrA, nbrA) ||
         upload(h->d_fidx, h->h_fidx) || upload(h->d_Sf, Sf) || upload(h->d_w, w) || upload(h->d_C, C) || upload(h->d_V, V) ||
         upload(h->d_rV, rV) || upload(h->d_bcell, bcell) || upload(h->d_bkind, bkind) || upload(h->d_bthetaBC, bthetaBC) ||
@@ -391,10 +456,12 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
     const size_t NP = h->NP, nB = std::max(h->nB, 1);
     const size_t d8 = sizeof(double);
     if (h->d_U.alloc(3 * NP * d8) || h->d_Ub.alloc(3 * nB * d8) || h->d_phi.alloc((size_t)std::max(h->nF, 1) * d8) ||
-        h->d_diag.alloc(NP * d8) || h->d_rD.alloc(NP * d8) || h->d_Fs.alloc((size_t)h->K * h->NS * d8) || h->d_grad.alloc(18 * NP * d8) ||
-        h->d_tmpB.alloc(6 * nB * d8))
+        h->d_diag.alloc(NP * d8) || h->d_rD.alloc(NP * d8) || h->d_Fs.alloc((size_t)h->K * h->NS * d8) ||
+        h->d_grad.alloc(h->assemblyV1 ? 18 * NP * d8 : 0) || h->d_Fell.alloc((size_t)h->K * h->NS * d8) ||
+        h->d_corr.alloc((size_t)h->nComp * h->K * h->NS * d8) || h->d_gradU.alloc(9 * NP * d8) || h->d_tmpB.alloc(6 * nB * d8))
         return 1;
     zero(h, h->d_U); zero(h, h->d_Ub); zero(h, h->d_phi); zero(h, h->d_grad); zero(h, h->d_Fs); zero(h, h->d_diag); zero(h, h->d_rD);
+    zero(h, h->d_Fell); zero(h, h->d_corr); zero(h, h->d_gradU);
     h->stageBytes = std::max<size_t>(9 * (size_t)h->N, std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;
     if (h->d_stage.alloc(h->stageBytes)) return 1;
     h->modes.resize(nModes);
@@ -470,6 +537,21 @@ int halo_planes(RheoGpu* h, double* base, int nPlanes) {
     }
     return 0;
 }
+// exchange records already laid out in d_send as [h][rec] (rec doubles per processor face) -> d_recv
+int halo_sendrecv(RheoGpu* h, int rec) {
+    if (h->H == 0) return 0;
+    if (!h->comm) return fail("mesh has processor patches but rheo_gpu_comm_init was not called");
+    g_nccl.GroupStart();
+    for (const HaloSeg& s : h->segs) {
+        const size_t off = (size_t)rec * s.h0, cnt = (size_t)rec * s.len;
+        int rc = g_nccl.Send(h->d_send.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
+        if (!rc) rc = g_nccl.Recv(h->d_recv.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
+        if (rc) { g_nccl.GroupEnd(); return fail(std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(rc)); }
+    }
+    int rc = g_nccl.GroupEnd();
+    if (rc) return fail(std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc));
+    return 0;
+}
 int all_reduce(RheoGpu* h, double* buf, int n) {
     if (h->nRanks <= 1) return 0;
     int rc = g_nccl.AllReduce(buf, buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
@@ -500,6 +582,21 @@ template <class Kern> int resident_grid(RheoGpu* h, Kern kern, long n) {
         }                                                                                    \
     } while (0)
 
+// persistent grid of the TMA-fed assembly kernel: one resident wave for this block size / dynamic shared memory
+template <class Kern> int flux_grid(RheoGpu* h, Kern kern, int threads, size_t smem) {
+    const long key = ((long)threads << 32) ^ (long)smem;
+    auto it = h->fluxBlocks.find({(const void*)kern, key});
+    int blocks;
+    if (it == h->fluxBlocks.end()) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, threads, smem) != cudaSuccess || perSm < 1) { cudaGetLastError(); perSm = 1; }
+        blocks = perSm * h->nSms;
+        h->fluxBlocks[{(const void*)kern, key}] = blocks;
+    } else blocks = it->second;
+    return std::max(1, std::min(h->nTiles, blocks));
+}
+
 #include "solve.inl"
 
 int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
@@ -525,20 +622,68 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (h->timing) cudaEventRecord(h->ev[1], h->stream);
     // ---- assembly, mode by mode (the matrix is shared: same phi, same dt)
     float msGrad = 0, msAsm = 0;
-    for (int mi = 0; mi < nModes; ++mi) {
-        ModeDev& md = h->modes[mi];
-        cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
-        if (h->lim.hrs && !noConv) {
+    if (h->assemblyV1) {
+        for (int mi = 0; mi < nModes; ++mi) {
+            ModeDev& md = h->modes[mi];
+            cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
+            if (h->lim.hrs && !noConv) {
+                if (h->timing) cudaEventRecord(e0, h->stream);
+                LAUNCH_SM(h, k_grad_theta, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, md.theta.as<double>(), md.thetaB.as<double>(), h->d_grad.as<double>());
+                if (h->H && halo_planes(h, h->d_grad.as<double>(), 18)) return 1;
+                if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msGrad += ms; }
+            }
             if (h->timing) cudaEventRecord(e0, h->stream);
-            LAUNCH_SM(h, k_grad_theta, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, md.theta.as<double>(), md.thetaB.as<double>(), h->d_grad.as<double>());
-            if (h->H && halo_planes(h, h->d_grad.as<double>(), 18)) return 1;
-            if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msGrad += ms; }
+            LAUNCH_K(h, k_cell_source, grid, BLOCK, h->mv, md.mp, rDeltaT, h->d_U.as<double>(), h->d_Ub.as<double>(), md.theta.as<double>(),
+                   md.thetaOld.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.bsrc.as<double>(), md.fFene.as<double>());
+            LAUNCH_SM(h, k_convect, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, h->lim, noConv, rDeltaT, h->ctl.relax, mi == 0 ? 1 : 0, h->d_phi.as<double>(), md.theta.as<double>(),
+                   md.thetaB.as<double>(), h->d_grad.as<double>(), md.bsrc.as<double>(), h->d_diag.as<double>(), h->d_rD.as<double>(), h->d_Fs.as<double>());
+            if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
         }
+    } else {
+        // k_flux_assemble (upwind cell computes each deferred face value once; grad(U) with the first mode) then
+        // k_cell_source2 (model source + ddt + inflow faces).  Processor faces: the face values of a group of modes
+        // travel in one message per neighbour, then k_ghost_corr adds them on the receiving side.
+        const bool hrs = h->lim.hrs && !noConv;
+        const size_t fluxSmem = 2 * (tile_record_bytes(h->K) + tile_flux_bytes(h->K));   // two stages
+        const int perGroup = std::max(1, MAX_RHS / h->nComp);
+        cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
         if (h->timing) cudaEventRecord(e0, h->stream);
-        LAUNCH_K(h, k_cell_source, grid, BLOCK, h->mv, md.mp, rDeltaT, h->d_U.as<double>(), h->d_Ub.as<double>(), md.theta.as<double>(),
-               md.thetaOld.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.bsrc.as<double>(), md.fFene.as<double>());
-        LAUNCH_SM(h, k_convect, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, h->lim, noConv, rDeltaT, h->ctl.relax, mi == 0 ? 1 : 0, h->d_phi.as<double>(), md.theta.as<double>(),
-               md.thetaB.as<double>(), h->d_grad.as<double>(), md.bsrc.as<double>(), h->d_diag.as<double>(), h->d_rD.as<double>(), h->d_Fs.as<double>());
+        for (int g0 = 0; g0 < nModes; g0 += perGroup) {
+            const int g1 = std::min(nModes, g0 + perGroup);
+            const int stride = (g1 - g0) * h->nComp;
+            for (int mi = g0; mi < g1; ++mi) {
+                ModeDev& md = h->modes[mi];
+                FluxArgs fa;
+                fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = rDeltaT; fa.relax = h->ctl.relax;
+                fa.writeMatrix = mi == 0 ? 1 : 0;
+                fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
+                fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
+                fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>();
+                fa.corr = h->d_corr.as<double>(); fa.ghostCorr = h->d_send.as<double>(); fa.ghostStride = stride; fa.ghostOffset = (mi - g0) * h->nComp;
+                fa.gradU = h->d_gradU.as<double>();
+                const int threads = TILE * (cl.n + fa.nU);
+                const unsigned char* rec = h->d_tileRec.as<unsigned char>();
+                switch (h->K) {
+                    case 4: LAUNCH_SM(h, (k_flux_assemble<4>), flux_grid(h, k_flux_assemble<4>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                    case 6: LAUNCH_SM(h, (k_flux_assemble<6>), flux_grid(h, k_flux_assemble<6>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                    default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                }
+                SourceArgs sa;
+                sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.useCorr = hrs ? 1 : 0;
+                for (int q = 0; q < 6; ++q) sa.solvedIdx[q] = -1;
+                for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
+                sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
+                sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>(); sa.Fs = h->d_Fs.as<double>(); sa.corr = h->d_corr.as<double>();
+                sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>();
+                LAUNCH_K(h, k_cell_source2, grid, BLOCK, h->mv, sa);
+            }
+            if (h->H && hrs) {
+                if (halo_sendrecv(h, stride)) return 1;
+                for (int mi = g0; mi < g1; ++mi)
+                    if (h->nBcells) LAUNCH(h, k_ghost_corr, cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), cl, h->d_Fs.as<double>(),
+                                           h->d_recv.as<double>(), stride, (mi - g0) * h->nComp, h->modes[mi].bsrc.as<double>());
+            }
+        }
         if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
     }
     if (h->timing) cudaEventRecord(h->ev[2], h->stream);
@@ -617,16 +762,21 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
 // host AoS -> device SoA through the staging buffer
 int put_cells(RheoGpu* h, const double* src, int nc, double* dstPlanes) {
     CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->N * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    h->h2dBytes += (long long)h->N * nc * sizeof(double);
     LAUNCH(h, k_aos_to_soa, cdiv(h->N, BLOCK), BLOCK, h->N, nc, h->d_perm.as<int>(), h->d_stage.as<double>(), dstPlanes, h->NP);
     return 0;
 }
 int put_bfaces(RheoGpu* h, const double* src, int nc, double* dstPlanes, const std::vector<std::pair<int, int>>* ranges = nullptr) {
     if (!h->nB) return 0;
-    if (!ranges) CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->nB * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    else
-        for (const auto& r : *ranges)   // faces outside the ranges keep stale staging values; no kernel reads them
+    if (!ranges) {
+        CK(cudaMemcpyAsync(h->d_stage.p, src, (size_t)h->nB * nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->h2dBytes += (long long)h->nB * nc * sizeof(double);
+    } else
+        for (const auto& r : *ranges) {   // faces outside the ranges keep stale staging values; no kernel reads them
             CK(cudaMemcpyAsync(h->d_stage.as<double>() + (size_t)r.first * nc, src + (size_t)r.first * nc, (size_t)r.second * nc * sizeof(double),
                                cudaMemcpyHostToDevice, h->stream));
+            h->h2dBytes += (long long)r.second * nc * sizeof(double);
+        }
     LAUNCH(h, k_aos_to_soa, cdiv(h->nB, BLOCK), BLOCK, h->nB, nc, (const int*)nullptr, h->d_stage.as<double>(), dstPlanes, h->nB);
     return 0;
 }
@@ -652,6 +802,7 @@ int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_
     h->device = device;
     h->ctl = *ctl;
     h->lim = make_limiter(ctl->limiter);
+    { const char* e = getenv("RHEO_ASSEMBLY_V1"); h->assemblyV1 = e && e[0] == '1'; }
     if (ctl->limiter < RHEO_LIMITER_UPWIND || ctl->limiter > RHEO_LIMITER_NONE) { delete h; return fail("The deferred limited scheme is not specified or does not exist. Valid schemes are: upwind cubista minmod smart waceb superbee none"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("cudaStreamCreate failed"); }
     { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->nSms = sms; }
@@ -669,6 +820,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
+                      &h->d_tileRec, &h->d_Fell, &h->d_corr, &h->d_gradU,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_grad, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
@@ -738,9 +890,13 @@ int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, con
     if (put_cells(h, U, 3, h->d_U.as<double>())) return 1;
     if (h->nB && U_b && put_bfaces(h, U_b, 3, h->d_Ub.as<double>(), &h->ubRanges)) return 1;
     CK(cudaMemcpyAsync(h->d_stage.p, phi, (size_t)h->nInt * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    for (const auto& r : h->phiBRanges)
+    h->h2dBytes += (long long)h->nInt * sizeof(double);
+    for (const auto& r : h->phiBRanges) {
         CK(cudaMemcpyAsync(h->d_stage.as<double>() + h->nInt + r.first, phi + h->nInt + r.first, (size_t)r.second * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        h->h2dBytes += (long long)r.second * sizeof(double);
+    }
     LAUNCH(h, k_phi_in, cdiv(h->nF, BLOCK), BLOCK, h->nF, h->d_faceOld.as<int>(), h->d_stage.as<double>(), h->d_phi.as<double>());
+    LAUNCH(h, k_flux_ell, cdiv(h->N, BLOCK), BLOCK, h->mv, h->d_phi.as<double>(), h->d_Fell.as<double>());
     return 0;
 }
 
@@ -782,6 +938,7 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
         default: return fail("rheo_gpu_download: unknown field");
     }
     if (bytes) CK(cudaMemcpyAsync(dst, stage, bytes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->d2hBytes += (long long)bytes * sizeof(double);
     CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -817,6 +974,12 @@ int rheo_gpu_get_ell(RheoGpu* h, int32_t* K, int32_t* nbr, int32_t* face) {
 
 int64_t rheo_gpu_launch_count(const RheoGpu* h) { return h ? h->launches : 0; }
 int rheo_gpu_last_iterations(const RheoGpu* h) { return h ? h->lastIters : -1; }
+int rheo_gpu_transfer_bytes(const RheoGpu* h, int64_t* h2d, int64_t* d2h) {
+    if (!h) return 1;
+    if (h2d) *h2d = h->h2dBytes;
+    if (d2h) *d2h = h->d2hBytes;
+    return 0;
+}
 int rheo_gpu_set_phase_timing(RheoGpu* h, int32_t enabled) { if (!h) return 1; h->timing = enabled != 0; return 0; }
 int rheo_gpu_get_phase_times(RheoGpu* h, double* ms7) { if (!h || !ms7) return 1; std::copy(h->phaseMs, h->phaseMs + 7, ms7); return 0; }
 int rheo_gpu_set_kernel_timing(RheoGpu* h, int32_t enabled) {

@@ -127,6 +127,12 @@ class GpuStressModel:
     def launch_count(self) -> int:
         return int(abi.lib().rheo_gpu_launch_count(self._h))
 
+    def transfer_bytes(self) -> tuple[int, int]:
+        """(host->device, device->host) bytes copied by this handle so far."""
+        a, b = C.c_int64(0), C.c_int64(0)
+        abi.lib().rheo_gpu_transfer_bytes(self._h, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
+
     def last_iterations(self) -> int:
         return int(abi.lib().rheo_gpu_last_iterations(self._h))
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU check: parity tests + C2/C3 bench lines (tag = $1)
 tag=${1:-x}
-/usr/local/graft/bin/gpurun --timeout 900 -- "python -m pytest tests -m gpu -x -q 2>&1 | tail -5; python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_C2.json; python bench.py --config C3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_C3.json; python - <<PYEOF
+/usr/local/graft/bin/gpurun --timeout 900 -- "python -m pytest tests -m gpu -x -q 2>&1 | tail -15; python bench.py --steps 20 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_C2.json; python bench.py --config C3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_C3.json; python - <<PYEOF
 import json
 for c in ('C2','C3'):
     d=json.load(open('gpurun_out/${tag}_bench_'+c+'.json'))
