@@ -11,8 +11,8 @@
 // upwind cell of a face therefore has everything in registers right after it has computed its own Gauss gradient
 // (which gathers theta of all neighbours anyway): grad(theta) never goes to memory.  Each face value is computed ONCE,
 // by its upwind cell, which adds v*F to its own deferred source and hands v to the downwind cell through `corr`, an
-// ELL-shaped array indexed by the downwind cell's own (slot, cell) — the downwind cell (k_cell_source) later reads its
-// row of `corr` with coalesced loads.  Processor faces: v goes to the send buffer of the halo exchange instead (the
+// ELL-shaped array indexed by the downwind cell's own (slot, cell) — the downwind cell reads its row of `corr` with
+// coalesced loads when the first Krylov residual is formed (k_krylov_init folds  b -= sum_inflow A * corr).  Processor faces: v goes to the send buffer of the halo exchange instead (the
 // former halo of the 18 grad(theta) planes becomes one value per face and component).
 //
 // Compared with the first version (k_grad_theta -> 18 planes -> k_convect gathering theta + 3 gradient planes from all
@@ -132,17 +132,30 @@ __global__ void __launch_bounds__(TILE * 9, 3) k_flux_assemble(MeshView m, FluxA
                 const int u = grp - a.cl.n;
                 const double* fk = a.U + (size_t)u * m.NP;
                 const double own = fk[c];
+                const double* uB = a.Ub + (size_t)u * m.nB;
                 double gx = 0, gy = 0, gz = 0;
+                double un[KT > 0 ? KT : 1];
+                if constexpr (KT > 0) {
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) {   // all neighbour gathers in flight before the first use
+                        const int nb = pNb[s * TILE];
+                        const double* src = nb >= 0 ? fk + nb : (nb == -1 ? fk + c : uB + (-nb - 2));
+                        un[s] = *src;
+                    }
+                }
 #pragma unroll
                 for (int s = 0; s < K; ++s) {
                     const int nb = pNb[s * TILE];
                     if (nb == -1) continue;
-                    double vf;
+                    double v;
+                    if constexpr (KT > 0) v = un[s];
+                    else v = nb >= 0 ? fk[nb] : uB[-nb - 2];
+                    double vf = v;
                     if (nb >= 0) {
-                        const double vn = fk[nb], w = pW[s * TILE];
-                        if (nb >= m.N) vf = w * own + (1.0 - w) * vn;
-                        else vf = nb > c ? w * (own - vn) + vn : w * (vn - own) + own;
-                    } else vf = a.Ub[(size_t)u * m.nB + (-nb - 2)];
+                        const double w = pW[s * TILE];
+                        if (nb >= m.N) vf = w * own + (1.0 - w) * v;
+                        else vf = nb > c ? w * (own - v) + v : w * (v - own) + own;
+                    }
                     gx += pS[s * TILE] * vf; gy += pS[KTL + s * TILE] * vf; gz += pS[2 * KTL + s * TILE] * vf;
                 }
                 const double rv = pRV[0];
@@ -154,6 +167,7 @@ __global__ void __launch_bounds__(TILE * 9, 3) k_flux_assemble(MeshView m, FluxA
                 const double* tk = a.theta + (size_t)k * m.NP;
                 const double* tB = a.thetaB + (size_t)k * m.nB;
                 const double tP = tk[c];
+                double* corrRow = a.corr + (size_t)grp * m.K * m.NS;
                 // neighbour values first: K independent gathers in flight before anything else is computed
                 double vn[KT > 0 ? KT : 1];
                 if constexpr (KT > 0) {
@@ -218,13 +232,13 @@ __global__ void __launch_bounds__(TILE * 9, 3) k_flux_assemble(MeshView m, FluxA
                                 const double gd = gx * pD[s * TILE] + gy * pD[KTL + s * TILE] + gz * pD[2 * KTL + s * TILE];
                                 v = phif_defc(own ? tP : tn, own ? tn : tP, gd, gd, upwFace, L);
                                 sou += v * F;   // souT[own] += v*phi ; souT[nei] -= v*phi
-                                if (!(meta & SLOT_GHOST)) a.corr[((size_t)grp * m.K + (meta >> 8)) * m.NS + nb] = v;
+                                if (!(meta & SLOT_GHOST)) corrRow[(unsigned)(meta >> 8) * (unsigned)m.NS + (unsigned)nb] = v;   // K*NS < 2^31 (checked at create)
                             }
                             if (meta & SLOT_GHOST) {
                                 // processor face: the value travels with the halo exchange (0 where the other side is upwind, so
                                 // that the receiver never reads an unwritten word); my own ghost slot of `corr` is cleared
                                 a.ghostCorr[(size_t)(nb - m.N) * a.ghostStride + a.ghostOffset + grp] = v;
-                                a.corr[((size_t)grp * m.K + s) * m.NS + c] = 0.0;
+                                corrRow[(unsigned)s * (unsigned)m.NS + (unsigned)c] = 0.0;
                             }
                         } else if ((meta & (SLOT_PATCH | SLOT_PATCH_ZG)) == SLOT_PATCH) {
                             bnd += -pF[s * TILE] * tB[-pNb[s * TILE] - 2];
@@ -259,69 +273,42 @@ __global__ void __launch_bounds__(TILE * 9, 3) k_flux_assemble(MeshView m, FluxA
     }
 }
 
-// ---------------------------------------------------------------- per-cell source: Omega/B split, model term, Euler ddt, inflow faces
-// One thread per cell.  L comes from gradU (k_flux_assemble), the deferred values of the faces this cell is DOWNWIND of
-// from its own row of `corr` (coalesced): b -= sum_{inflow slots} F * v  with F = A[s][c] = min(F,0).
+// ---------------------------------------------------------------- per-cell source: Omega/B split, model term, Euler ddt
+// One thread per cell, pure streaming (no gathers): L comes from gradU (k_flux_assemble); the result is added to the
+// own-face part k_flux_assemble left in bsrc.  The faces the cell is DOWNWIND of are folded in by k_krylov_init, which
+// reads the cell's matrix row anyway: b -= sum_{inflow slots} A * corr  (krylov.cuh).
 struct SourceArgs {
     ModelParams mp;
     double rDeltaT;
-    int useCorr;            // high-resolution scheme active
     int solvedIdx[6];       // component -> index among the solved components, -1 if not solved (2-D: xz, yz)
     const double* gradU; const double* theta; const double* thetaOld; const double* lam; const double* R;
-    const double* Fs; const double* corr;
     double* bsrc; double* fFene;
 };
 
-template <int KT>
-__global__ void __launch_bounds__(BLOCK) k_cell_source2(MeshView m, SourceArgs a) {
+__global__ void __launch_bounds__(128, 4) k_cell_source2(MeshView m, SourceArgs a) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m.N) return;
-    const int K = KT > 0 ? KT : m.K;
-    // inflow faces first: the A -> corr load chain is in flight while the 3x3 algebra below runs
-    double inflow[6] = {0, 0, 0, 0, 0, 0};
-    if (a.useCorr) {
-        double A[KT > 0 ? KT : 1];
-        if constexpr (KT > 0) {
-#pragma unroll
-            for (int s = 0; s < KT; ++s) A[s] = a.Fs[(size_t)s * m.NS + c];
-        }
-#pragma unroll
-        for (int s = 0; s < K; ++s) {
-            const size_t e = (size_t)s * m.NS + c;
-            double As;
-            if constexpr (KT > 0) As = A[s];
-            else As = a.Fs[e];
-            if (As < 0.0) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int j = a.solvedIdx[k];
-                    if (j >= 0) inflow[k] += As * a.corr[(size_t)j * m.K * m.NS + e];
-                }
-            }
-        }
-    }
-    double g[9];
+    double g[9], thO[6], own6[6], th[6], Rm[9], lm[3], rhs[6];
 #pragma unroll
     for (int i = 0; i < 9; ++i) g[i] = a.gradU[(size_t)i * m.NP + c];
-    // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
-    const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
-    double th[6], Rm[9], lm[3], rhs[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) th[k] = a.theta[(size_t)k * m.NP + c];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rm[k] = a.R[(size_t)k * m.NP + c];
 #pragma unroll
     for (int k = 0; k < 3; ++k) lm[k] = a.lam[(size_t)k * m.NP + c];
-    const double f = model_rhs(a.mp, L, th, Rm, lm, rhs);
-    a.fFene[c] = f;
-    const double V = m.V[c];
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const double val = a.rDeltaT * a.thetaOld[(size_t)k * m.NP + c] * V + V * rhs[k];
-        double* dst = a.bsrc + (size_t)k * m.NP + c;
-        if (a.solvedIdx[k] >= 0) *dst = (val + *dst) - inflow[k];
-        else *dst = val;
+        thO[k] = a.thetaOld[(size_t)k * m.NP + c];
+        own6[k] = a.solvedIdx[k] >= 0 ? a.bsrc[(size_t)k * m.NP + c] : 0.0;
     }
+    const double V = m.V[c];
+    // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
+    const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
+    const double f = model_rhs(a.mp, L, th, Rm, lm, rhs);
+    a.fFene[c] = f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.bsrc[(size_t)k * m.NP + c] = (a.rDeltaT * thO[k] * V + V * rhs[k]) + own6[k];
 }
 
 // processor faces: deferred values received from the upwind side, for the cells that own ghost slots

@@ -85,6 +85,7 @@ struct ModeDev {
     RheoModelDesc desc;
     ModelParams mp;
     DevBuf theta, thetaOld, tau, lam, R, fFene, bsrc, thetaB, tauB, gammaVals;
+    DevBuf corr;   // [nComp][K*NS] deferred face values received from the upwind neighbours (assembly.cuh)
 };
 
 struct HaloSeg { int nbrRank, h0, len; };
@@ -120,7 +121,7 @@ struct RheoGpu {
     MeshView mv;
     // fields
     DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_grad, d_stage, d_tmpB;
-    DevBuf d_Fell, d_corr, d_gradU;
+    DevBuf d_Fell, d_gradU;
     bool assemblyV1 = false;       // RHEO_ASSEMBLY_V1=1: first-version assembly (k_grad_theta + k_cell_source + k_convect), for A/B runs
     std::vector<ModeDev> modes;
     // Krylov
@@ -317,6 +318,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     int K = 0;
     for (int c = 0; c < N; ++c) K = std::max(K, deg[c]);
     h->K = K;
+    if ((long)K * round_up(N, 32) >= (1L << 31)) return fail("rheo_gpu_create: K x cells exceeds 2^31 (32-bit slot indexing)");
     if (K > 32) return fail("rheo_gpu_create: a cell has more than 32 faces (tile kernels stage 40 B per slot and cell in shared memory)");
     const size_t ell = (size_t)K * h->NS;
     h->h_nbr.assign(ell, -1);
@@ -458,10 +460,10 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
     if (h->d_U.alloc(3 * NP * d8) || h->d_Ub.alloc(3 * nB * d8) || h->d_phi.alloc((size_t)std::max(h->nF, 1) * d8) ||
         h->d_diag.alloc(NP * d8) || h->d_rD.alloc(NP * d8) || h->d_Fs.alloc((size_t)h->K * h->NS * d8) ||
         h->d_grad.alloc(h->assemblyV1 ? 18 * NP * d8 : 0) || h->d_Fell.alloc((size_t)h->K * h->NS * d8) ||
-        h->d_corr.alloc((size_t)h->nComp * h->K * h->NS * d8) || h->d_gradU.alloc(9 * NP * d8) || h->d_tmpB.alloc(6 * nB * d8))
+        h->d_gradU.alloc(9 * NP * d8) || h->d_tmpB.alloc(6 * nB * d8))
         return 1;
     zero(h, h->d_U); zero(h, h->d_Ub); zero(h, h->d_phi); zero(h, h->d_grad); zero(h, h->d_Fs); zero(h, h->d_diag); zero(h, h->d_rD);
-    zero(h, h->d_Fell); zero(h, h->d_corr); zero(h, h->d_gradU);
+    zero(h, h->d_Fell); zero(h, h->d_gradU);
     h->stageBytes = std::max<size_t>(9 * (size_t)h->N, std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;
     if (h->d_stage.alloc(h->stageBytes)) return 1;
     h->modes.resize(nModes);
@@ -486,8 +488,10 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
             mp.gamma_vals = md.gammaVals.as<double>();
         }
         if (md.theta.alloc(6 * NP * d8) || md.thetaOld.alloc(6 * NP * d8) || md.tau.alloc(6 * NP * d8) || md.lam.alloc(3 * NP * d8) ||
-            md.R.alloc(9 * NP * d8) || md.fFene.alloc(NP * d8) || md.bsrc.alloc(6 * NP * d8) || md.thetaB.alloc(6 * nB * d8) || md.tauB.alloc(6 * nB * d8))
+            md.R.alloc(9 * NP * d8) || md.fFene.alloc(NP * d8) || md.bsrc.alloc(6 * NP * d8) || md.thetaB.alloc(6 * nB * d8) || md.tauB.alloc(6 * nB * d8) ||
+            md.corr.alloc(h->assemblyV1 ? 0 : (size_t)h->nComp * h->K * h->NS * d8))
             return 1;
+        zero(h, md.corr);
         zero(h, md.theta); zero(h, md.thetaOld); zero(h, md.tau); zero(h, md.fFene); zero(h, md.bsrc); zero(h, md.thetaB); zero(h, md.tauB); zero(h, md.R);
         // READ_IF_PRESENT defaults: eigVals = eigVecs = I (Oldroyd_BLog.C:76-113)
         LAUNCH(h, k_fill, cdiv(3 * NP, BLOCK), BLOCK, 3 * NP, md.lam.as<double>(), 1.0);
@@ -659,7 +663,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
                 fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
                 fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>();
-                fa.corr = h->d_corr.as<double>(); fa.ghostCorr = h->d_send.as<double>(); fa.ghostStride = stride; fa.ghostOffset = (mi - g0) * h->nComp;
+                fa.corr = md.corr.as<double>(); fa.ghostCorr = h->d_send.as<double>(); fa.ghostStride = stride; fa.ghostOffset = (mi - g0) * h->nComp;
                 fa.gradU = h->d_gradU.as<double>();
                 const int threads = TILE * (cl.n + fa.nU);
                 const unsigned char* rec = h->d_tileRec.as<unsigned char>();
@@ -669,13 +673,13 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                     default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
                 }
                 SourceArgs sa;
-                sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.useCorr = hrs ? 1 : 0;
+                sa.mp = md.mp; sa.rDeltaT = rDeltaT;
                 for (int q = 0; q < 6; ++q) sa.solvedIdx[q] = -1;
                 for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
                 sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
-                sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>(); sa.Fs = h->d_Fs.as<double>(); sa.corr = h->d_corr.as<double>();
+                sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
                 sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>();
-                LAUNCH_K(h, k_cell_source2, grid, BLOCK, h->mv, sa);
+                LAUNCH(h, k_cell_source2, cdiv(N, 128), 128, h->mv, sa);
             }
             if (h->H && hrs) {
                 if (halo_sendrecv(h, stride)) return 1;
@@ -699,6 +703,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             for (int j = 0; j < h->nComp; ++j) {
                 rp.psi[rp.n] = h->modes[mi].theta.as<double>() + (size_t)h->comps[j] * NP;
                 rp.b[rp.n] = h->modes[mi].bsrc.as<double>() + (size_t)h->comps[j] * NP;
+                rp.corr[rp.n] = (!h->assemblyV1 && h->lim.hrs && !noConv) ? h->modes[mi].corr.as<double>() + (size_t)j * h->K * h->NS : nullptr;
                 rp.n++;
             }
         int iters = 0;
@@ -820,12 +825,12 @@ void rheo_gpu_destroy(RheoGpu* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
-                      &h->d_tileRec, &h->d_Fell, &h->d_corr, &h->d_gradU,
+                      &h->d_tileRec, &h->d_Fell, &h->d_gradU,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_grad, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
     for (ModeDev& md : h->modes)
-        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals}) b->release();
+        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr}) b->release();
     if (h->h_ks) cudaFreeHost(h->h_ks);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -44,6 +44,7 @@ struct RhsPtrs {      // one batch of right-hand sides sharing the matrix
     int n;
     double* psi[MAX_RHS];       // theta planes (solution, in place)
     const double* b[MAX_RHS];   // source planes
+    const double* corr[MAX_RHS];   // [K*NS] deferred face values handed over by the upwind neighbours (assembly.cuh), or null
 };
 
 // ---------------------------------------------------------------- reductions

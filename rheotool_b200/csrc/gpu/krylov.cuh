@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
             const double d = diag[c];
             double rowsum = d;
             double acc[NR];
+            double aRow[KT > 0 ? KT : 1];
 #pragma unroll
             for (int j = 0; j < NR; ++j) acc[j] = d * rp.psi[md * NR + j][c];
             if constexpr (KT == 0) {
@@ -240,11 +241,10 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
                 }
             } else {
                 int nb[KT];
-                double a[KT];
 #pragma unroll
-                for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[(size_t)s * m.NS + c]; a[s] = A[(size_t)s * m.NS + c]; }
+                for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[(size_t)s * m.NS + c]; aRow[s] = A[(size_t)s * m.NS + c]; }
 #pragma unroll
-                for (int s = 0; s < KT; ++s) rowsum += a[s];
+                for (int s = 0; s < KT; ++s) rowsum += aRow[s];
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
                     const double* pj = rp.psi[md * NR + j];
@@ -252,16 +252,38 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
 #pragma unroll
                     for (int s = 0; s < KT; ++s) pn[s] = pj[nb[s]];
 #pragma unroll
-                    for (int s = 0; s < KT; ++s) acc[j] += a[s] * pn[s];
+                    for (int s = 0; s < KT; ++s) acc[j] += aRow[s] * pn[s];
+                }
+            }
+            // source: own part + the deferred values of the faces this cell is downwind of (A = min(F,0) < 0 marks them)
+            double bb[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) bb[j] = rp.b[md * NR + j][c];
+            if (rp.corr[md * NR] != nullptr) {
+                if constexpr (KT == 0) {
+                    for (int s = 0; s < m.K; ++s) {
+                        const double as = A[(size_t)s * m.NS + c];
+                        if (as < 0.0) {
+#pragma unroll
+                            for (int j = 0; j < NR; ++j) bb[j] -= as * rp.corr[md * NR + j][(size_t)s * m.NS + c];
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int s = 0; s < KT; ++s) {
+                        if (aRow[s] < 0.0) {
+#pragma unroll
+                            for (int j = 0; j < NR; ++j) bb[j] -= aRow[s] * rp.corr[md * NR + j][(size_t)s * m.NS + c];
+                        }
+                    }
                 }
             }
             double rr[NR];
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
-                const double bb = rp.b[md * NR + j][c];
-                rr[j] = bb - acc[j];
+                rr[j] = bb[j] - acc[j];
                 const double t = rowsum * (sumPsi[md * NR + j] / nGlobal);
-                red[3 * j] += fabs(acc[j] - t) + fabs(bb - t);
+                red[3 * j] += fabs(acc[j] - t) + fabs(bb[j] - t);
                 red[3 * j + 1] += fabs(rr[j]);
                 red[3 * j + 2] += rr[j] * rr[j];
             }
