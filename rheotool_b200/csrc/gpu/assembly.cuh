@@ -20,6 +20,7 @@
 // gathers per (cell, component), half the limiter evaluations (ncu r1c: k_convect was L1-throughput bound at 87 %).
 #pragma once
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace rk {
 
@@ -35,34 +36,12 @@ struct FluxArgs {
     const double* theta; const double* thetaB;
     const double* U; const double* Ub;
     double* bsrc;         // [6*NP] own part of the source (ddt and model terms are added by k_cell_source)
-    double* diag; double* rD; double* Fs;
+    double* diag; double* rD; double* Fs;   // Fs = A, tile-major (ell_t)
     double* corr;         // [nComp][K*NS] face values handed to the downwind cell
     double* ghostCorr;    // send buffer: [(h * ghostStride) + ghostOffset + comp]
     int ghostStride, ghostOffset;
     double* gradU;        // [9*NP] g[3k+d] = d_d U_k
 };
-
-// ---------------------------------------------------------------- TMA / mbarrier helpers (sm_100a)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// 1-D bulk copy global -> shared through the TMA unit; completion is signalled on `bar` (complete_tx)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
-                 "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    const uint32_t addr = smem_u32(bar);
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    } while (!ok);
-}
 
 // Tile record of the mesh (static, built once per mesh; one contiguous block per 32 consecutive cells so that ONE bulk copy
 // brings everything the tile needs): for K slots and 32 lanes
@@ -127,7 +106,7 @@ __global__ void __launch_bounds__(TILE * 9, 3) k_flux_assemble(MeshView m, FluxA
         if (active) {
             if (a.writeMatrix)   // row coefficients A[c][nb] = min(F,0), slot-major for the Krylov kernels
                 for (int s = grp; s < K; s += nGrp)
-                    a.Fs[(size_t)s * m.NS + c] = ((pMeta[s * TILE] & SLOT_CELL) && !a.noConv) ? fmin(pF[s * TILE], 0.0) : 0.0;
+                    a.Fs[ell_t(m.K, s, c)] = ((pMeta[s * TILE] & SLOT_CELL) && !a.noConv) ? fmin(pF[s * TILE], 0.0) : 0.0;
             if (grp >= a.cl.n) {   // ---------------- velocity warp: grad(U_u)
                 const int u = grp - a.cl.n;
                 const double* fk = a.U + (size_t)u * m.NP;
@@ -319,9 +298,9 @@ __global__ void k_ghost_corr(MeshView m, int nBcells, const int* __restrict__ bc
     if (i0 >= nBcells) return;
     const int c = bcells[i0];
     for (int s = 0; s < m.K; ++s) {
-        const int nb = m.nbrA[(size_t)s * m.NS + c];
+        const int nb = m.nbrA[ell_t(m.K, s, c)];
         if (nb < m.N) continue;
-        const double A = Fs[(size_t)s * m.NS + c];
+        const double A = Fs[ell_t(m.K, s, c)];
         if (!(A < 0.0)) continue;
         for (int j = 0; j < cl.n; ++j) bsrc[(size_t)cl.c[j] * m.NP + c] -= A * recv[(size_t)(nb - m.N) * stride + offset + j];
     }

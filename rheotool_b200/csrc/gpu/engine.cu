@@ -120,9 +120,8 @@ struct RheoGpu {
     int nTiles = 0;
     MeshView mv;
     // fields
-    DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_grad, d_stage, d_tmpB;
+    DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_stage, d_tmpB;
     DevBuf d_Fell, d_gradU;
-    bool assemblyV1 = false;       // RHEO_ASSEMBLY_V1=1: first-version assembly (k_grad_theta + k_cell_source + k_convect), for A/B runs
     std::vector<ModeDev> modes;
     // Krylov
     DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ks, d_partials, d_red, d_counter, d_bcells;
@@ -308,7 +307,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
         }
     }
     h->H = H; h->NT = N + H;
-    h->NS = round_up(N, 32);
+    h->NS = round_up(N, RT);   // row tiles of 256 cells (krylov.cuh); also a multiple of the assembly tile (32)
     h->NP = round_up(N + H, 32);
 
     // ---- ELL (slot order: internal faces by ascending new neighbour, then boundary faces in face order)
@@ -340,7 +339,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     for (int s = 0; s < K; ++s)
         for (int c = 0; c < h->NS; ++c) {
             const int v = h->h_nbr[(size_t)s * h->NS + c];
-            nbrA[(size_t)s * h->NS + c] = (v >= 0) ? v : std::min(c, N - 1);
+            nbrA[ell_t(K, s, c)] = (v >= 0) ? v : std::min(c, N - 1);   // tile-major (kernels.cuh: ell_t)
         }
 
     {   // cells owning ghost slots (k_ghost)
@@ -458,11 +457,11 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
     const size_t NP = h->NP, nB = std::max(h->nB, 1);
     const size_t d8 = sizeof(double);
     if (h->d_U.alloc(3 * NP * d8) || h->d_Ub.alloc(3 * nB * d8) || h->d_phi.alloc((size_t)std::max(h->nF, 1) * d8) ||
-        h->d_diag.alloc(NP * d8) || h->d_rD.alloc(NP * d8) || h->d_Fs.alloc((size_t)h->K * h->NS * d8) ||
-        h->d_grad.alloc(h->assemblyV1 ? 18 * NP * d8 : 0) || h->d_Fell.alloc((size_t)h->K * h->NS * d8) ||
+        h->d_diag.alloc(std::max<size_t>(NP, h->NS) * d8) || h->d_rD.alloc(std::max<size_t>(NP, h->NS) * d8) || h->d_Fs.alloc((size_t)h->K * h->NS * d8) ||
+        h->d_Fell.alloc((size_t)h->K * h->NS * d8) ||
         h->d_gradU.alloc(9 * NP * d8) || h->d_tmpB.alloc(6 * nB * d8))
         return 1;
-    zero(h, h->d_U); zero(h, h->d_Ub); zero(h, h->d_phi); zero(h, h->d_grad); zero(h, h->d_Fs); zero(h, h->d_diag); zero(h, h->d_rD);
+    zero(h, h->d_U); zero(h, h->d_Ub); zero(h, h->d_phi); zero(h, h->d_Fs); zero(h, h->d_diag); zero(h, h->d_rD);
     zero(h, h->d_Fell); zero(h, h->d_gradU);
     h->stageBytes = std::max<size_t>(9 * (size_t)h->N, std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;
     if (h->d_stage.alloc(h->stageBytes)) return 1;
@@ -489,7 +488,7 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         }
         if (md.theta.alloc(6 * NP * d8) || md.thetaOld.alloc(6 * NP * d8) || md.tau.alloc(6 * NP * d8) || md.lam.alloc(3 * NP * d8) ||
             md.R.alloc(9 * NP * d8) || md.fFene.alloc(NP * d8) || md.bsrc.alloc(6 * NP * d8) || md.thetaB.alloc(6 * nB * d8) || md.tauB.alloc(6 * nB * d8) ||
-            md.corr.alloc(h->assemblyV1 ? 0 : (size_t)h->nComp * h->K * h->NS * d8))
+            md.corr.alloc((size_t)h->nComp * h->K * h->NS * d8))
             return 1;
         zero(h, md.corr);
         zero(h, md.theta); zero(h, md.thetaOld); zero(h, md.tau); zero(h, md.fFene); zero(h, md.bsrc); zero(h, md.thetaB); zero(h, md.tauB); zero(h, md.R);
@@ -615,7 +614,6 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     cl.n = h->nComp;
     for (int j = 0; j < 6; ++j) cl.c[j] = j < h->nComp ? h->comps[j] : 0;
     const int tileGrid = cdiv(N, TILE);
-    const size_t tileSmem = (size_t)h->K * TILE * (4 * sizeof(double) + 2 * sizeof(int));
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
 
     // ---- halo of U (grad U) and of theta (deferred correction / SpMV of the first residual)
@@ -626,24 +624,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (h->timing) cudaEventRecord(h->ev[1], h->stream);
     // ---- assembly, mode by mode (the matrix is shared: same phi, same dt)
     float msGrad = 0, msAsm = 0;
-    if (h->assemblyV1) {
-        for (int mi = 0; mi < nModes; ++mi) {
-            ModeDev& md = h->modes[mi];
-            cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
-            if (h->lim.hrs && !noConv) {
-                if (h->timing) cudaEventRecord(e0, h->stream);
-                LAUNCH_SM(h, k_grad_theta, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, md.theta.as<double>(), md.thetaB.as<double>(), h->d_grad.as<double>());
-                if (h->H && halo_planes(h, h->d_grad.as<double>(), 18)) return 1;
-                if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msGrad += ms; }
-            }
-            if (h->timing) cudaEventRecord(e0, h->stream);
-            LAUNCH_K(h, k_cell_source, grid, BLOCK, h->mv, md.mp, rDeltaT, h->d_U.as<double>(), h->d_Ub.as<double>(), md.theta.as<double>(),
-                   md.thetaOld.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.bsrc.as<double>(), md.fFene.as<double>());
-            LAUNCH_SM(h, k_convect, tileGrid, TILE * cl.n, tileSmem, h->mv, cl, h->lim, noConv, rDeltaT, h->ctl.relax, mi == 0 ? 1 : 0, h->d_phi.as<double>(), md.theta.as<double>(),
-                   md.thetaB.as<double>(), h->d_grad.as<double>(), md.bsrc.as<double>(), h->d_diag.as<double>(), h->d_rD.as<double>(), h->d_Fs.as<double>());
-            if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
-        }
-    } else {
+    {
         // k_flux_assemble (upwind cell computes each deferred face value once; grad(U) with the first mode) then
         // k_cell_source2 (model source + ddt + inflow faces).  Processor faces: the face values of a group of modes
         // travel in one message per neighbour, then k_ghost_corr adds them on the receiving side.
@@ -703,7 +684,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             for (int j = 0; j < h->nComp; ++j) {
                 rp.psi[rp.n] = h->modes[mi].theta.as<double>() + (size_t)h->comps[j] * NP;
                 rp.b[rp.n] = h->modes[mi].bsrc.as<double>() + (size_t)h->comps[j] * NP;
-                rp.corr[rp.n] = (!h->assemblyV1 && h->lim.hrs && !noConv) ? h->modes[mi].corr.as<double>() + (size_t)j * h->K * h->NS : nullptr;
+                rp.corr[rp.n] = (h->lim.hrs && !noConv) ? h->modes[mi].corr.as<double>() + (size_t)j * h->K * h->NS : nullptr;
                 rp.n++;
             }
         int iters = 0;
@@ -807,7 +788,6 @@ int rheo_gpu_create(const RheoMeshDesc* mesh, const RheoModelDesc* modes, int32_
     h->device = device;
     h->ctl = *ctl;
     h->lim = make_limiter(ctl->limiter);
-    { const char* e = getenv("RHEO_ASSEMBLY_V1"); h->assemblyV1 = e && e[0] == '1'; }
     if (ctl->limiter < RHEO_LIMITER_UPWIND || ctl->limiter > RHEO_LIMITER_NONE) { delete h; return fail("The deferred limited scheme is not specified or does not exist. Valid schemes are: upwind cubista minmod smart waceb superbee none"); }
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return fail("cudaStreamCreate failed"); }
     { int sms = 148; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device); h->nSms = sms; }
@@ -826,7 +806,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU,
-                      &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_grad, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
+                      &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
     for (ModeDev& md : h->modes)

@@ -4,11 +4,8 @@
 // numbering sorted by colour so that the DILU sweeps are a few fully parallel phases.
 //
 // Reference loops restated (of90/src/libs/...):
-//   k_grad_theta      gaussDefCmpwConvectionScheme/gaussDefCmpwConvectionScheme.C:242-254 (6 x fvc::grad)
-//   k_cell_source     constitutiveEquations/constitutiveEqs/utils/boilerLog.H:1-36 + the model sources
-//   k_convect         gaussDefCmpwConvectionScheme.C:93-167 (upwind LDU, boundary coeffs, deferred HRS)
-//                     and :257-319 (phifDefC face loop, coupled patches), EXT-OF9 fvMatrix::relax,
-//                     addBoundaryDiag/addBoundarySource
+//   k_flux_assemble, k_cell_source2 (assembly.cuh)   gaussDefCmpwConvectionScheme.C:93-167, :242-319, boilerLog.H:1-36,
+//                     the model sources, EXT-OF9 fvMatrix::relax, addBoundaryDiag/addBoundarySource
 //   k_spmv*, k_sweep* EXT-OF9 lduMatrix::Amul, DILUPreconditioner::precondition
 //   k_eig_tau         constitutiveEq.C:360-416 (calcEig) + theta->tau maps
 //   k_tau_bc_linext   boundaryConditions/linearExtrapolation/linearExtrapolationFvPatchField.C:101-151
@@ -26,7 +23,7 @@ constexpr int MAX_RED = 3 * MAX_RHS;
 struct MeshView {
     int N, H, NT, NS, NP, K, nInt, nF, nB;
     const int* nbr;    // [K*NS] topological: >=0 cell/ghost, -1 empty, <=-2 boundary face -(b+2)
-    const int* nbrA;   // [K*NS] algebraic: neighbour cell/ghost, self for empty/boundary slots
+    const int* nbrA;   // [K*NS] algebraic: neighbour cell/ghost, self for empty/boundary slots; TILE-MAJOR, index ell_t(K, s, c)
     const int* fidx;   // [K*NS] face id, ~face when this cell is the face's neighbour
     const double* Sf;  // [3*nF] planes (x|y|z), stride nF, orientation of the (renumbered) owner
     const double* w;   // [nF]
@@ -242,97 +239,18 @@ __device__ __forceinline__ void gauss_grad_cell(const MeshView& m, int c, const 
     for (int i = 0; i < 3 * NC; ++i) g[i] *= rv;
 }
 
-// ---------------------------------------------------------------- tile kernels: one warp per (32 cells, component)
-// Face kernels of the assembly (grad(theta) and the convection operator) are latency-bound when one
-// thread owns a whole cell (6 slots x 6 components of dependent gathers, >130 registers).  Here a CTA is
-// a tile of 32 consecutive cells times the n solved components: threadIdx = comp_group*32 + cell.
-//   phase 1  the warps share the slots: warp g stages slot g, g+n, ... of the 32 cells (neighbour index,
-//            face geometry / flux) in shared memory — every connectivity and geometry word is loaded once;
-//   phase 2  warp g accumulates component comps[g] over the slots: per slot a handful of coalesced gathers,
-//            ~50 registers, so 30-40 warps per SM keep enough loads in flight to cover HBM latency.
-// Unsolved components (xz, yz in 2-D: theta stays 0 there) are skipped altogether.
+// ---------------------------------------------------------------- tiles
+// assembly (assembly.cuh): 32 consecutive cells x (solved components + velocity components), one warp each;
+// Krylov gather kernels (krylov.cuh): 256 consecutive cells, one thread each.  Unsolved components (xz, yz in 2-D: theta
+// stays 0 there) are skipped altogether.
 struct CompList { int n; int c[6]; };
 constexpr int TILE = 32;
+constexpr int RT = 256;   // cells per row tile of the matrix
 
-__global__ void __launch_bounds__(TILE * 6) k_grad_theta(MeshView m, CompList cl, const double* __restrict__ theta, const double* __restrict__ thetaB,
-                                                          double* __restrict__ grad) {
-    extern __shared__ double smem[];
-    const int K = m.K;
-    double* sS = smem;                         // [3][K][TILE]  signed face area vector (0 for unused slots)
-    double* sW = smem + 3 * K * TILE;          // [K][TILE]
-    int* sNb = (int*)(smem + 4 * K * TILE);    // [K][TILE]
-    int* sOwn = sNb + K * TILE;                // [K][TILE] 1 if this cell is the face's owner
-    const int lane = threadIdx.x & (TILE - 1), grp = threadIdx.x / TILE, nGrp = blockDim.x / TILE;
-    const int c = blockIdx.x * TILE + lane;
-    const bool active = c < m.N;
-    for (int s = grp; s < K; s += nGrp) {
-        int nb = -1, own = 1;
-        double Sx = 0, Sy = 0, Sz = 0, w = 0;
-        if (active) {
-            nb = m.nbr[(size_t)s * m.NS + c];
-            if (nb != -1) {
-                const int fi = m.fidx[(size_t)s * m.NS + c];
-                own = fi >= 0;
-                const int f = own ? fi : ~fi;
-                const double sg = own ? 1.0 : -1.0;
-                Sx = sg * m.Sf[f]; Sy = sg * m.Sf[(size_t)m.nF + f]; Sz = sg * m.Sf[2 * (size_t)m.nF + f];
-                w = m.w[f];
-            }
-        }
-        const int i = s * TILE + lane;
-        sS[i] = Sx; sS[K * TILE + i] = Sy; sS[2 * K * TILE + i] = Sz; sW[i] = w; sNb[i] = nb; sOwn[i] = own;
-    }
-    __syncthreads();
-    if (!active) return;
-    const int k = cl.c[grp];
-    const double* fk = theta + (size_t)k * m.NP;
-    const double own = fk[c];
-    double gx = 0, gy = 0, gz = 0;
-#pragma unroll 2
-    for (int s = 0; s < K; ++s) {
-        const int i = s * TILE + lane;
-        const int nb = sNb[i];
-        if (nb == -1) continue;
-        double vf;
-        if (nb >= 0) {
-            const double vn = fk[nb], w = sW[i];
-            if (nb >= m.N) vf = w * own + (1.0 - w) * vn;
-            else vf = sOwn[i] ? w * (own - vn) + vn : w * (vn - own) + own;
-        } else vf = thetaB[(size_t)k * m.nB + (-nb - 2)];
-        gx += sS[i] * vf; gy += sS[K * TILE + i] * vf; gz += sS[2 * K * TILE + i] * vf;
-    }
-    const double rv = m.rV[c];
-    grad[(size_t)(3 * k) * m.NP + c] = gx * rv;
-    grad[(size_t)(3 * k + 1) * m.NP + c] = gy * rv;
-    grad[(size_t)(3 * k + 2) * m.NP + c] = gz * rv;
-}
-
-// ---------------------------------------------------------------- per-cell source: grad(U), Omega/B split, model term, Euler ddt
-template <int KT>
-__global__ void __launch_bounds__(BLOCK) k_cell_source(MeshView m, ModelParams mp, double rDeltaT, const double* __restrict__ U, const double* __restrict__ Ub,
-                                                        const double* __restrict__ theta, const double* __restrict__ thetaOld, const double* __restrict__ lam,
-                                                        const double* __restrict__ R, double* __restrict__ bsrc, double* __restrict__ fFene) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.N) return;
-    double own[3], g[9];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) own[k] = U[(size_t)k * m.NP + c];
-    gauss_grad_cell<3, KT>(m, c, U, Ub, own, g);
-    // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
-    const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
-    double th[6], Rm[9], lm[3], rhs[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) th[k] = theta[(size_t)k * m.NP + c];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Rm[k] = R[(size_t)k * m.NP + c];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) lm[k] = lam[(size_t)k * m.NP + c];
-    const double f = model_rhs(mp, L, th, Rm, lm, rhs);
-    fFene[c] = f;
-    const double V = m.V[c];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) bsrc[(size_t)k * m.NP + c] = rDeltaT * thetaOld[(size_t)k * m.NP + c] * V + V * rhs[k];
-}
+// Matrix rows (neighbour table nbrA and coefficients A) are stored tile-major: the K x 256 words of the 256 consecutive
+// cells of a row tile are contiguous, so that one cp.async.bulk brings the tile's rows (krylov.cuh); a warp still reads
+// 32 consecutive words per slot.  NS is a multiple of 256.
+__host__ __device__ __forceinline__ size_t ell_t(int K, int s, int c) { return ((size_t)(c >> 8) * K + s) * RT + (c & (RT - 1)); }
 
 // ---------------------------------------------------------------- convection: upwind LDU + deferred HRS + boundary folding + relax
 struct Limiter { int hrs; double a0, a1, a2, b0, b1, b2, bnd0, bnd1; };
@@ -354,119 +272,7 @@ __device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, do
     return oab * far + cP * vP + cN * vN;
 }
 
-// Convection operator (tile kernel, see above).  Phase 1 stages per slot: neighbour, flags, the signed
-// outflow flux F (patch faces: phi_b), the centre-to-centre vector d in the face's owner->neighbour frame, and
-// writes the off-diagonal row coefficients min(F,0) (writeMatrix: first mode of a batch; identical for all
-// modes — same phi, same dt).  Phase 2, per component: diagonal (ddt + upwind + boundary coefficients +
-// relax), the deferred high-resolution correction, boundary source.
-enum { SLOT_CELL = 1, SLOT_OWNER = 2, SLOT_UPW = 4, SLOT_GHOST = 8, SLOT_PATCH = 16, SLOT_PATCH_ZG = 32 };
-
-__global__ void __launch_bounds__(TILE * 6, 7) k_convect(MeshView m, CompList cl, Limiter lim, int noConv, double rDeltaT, double relax, int writeMatrix,
-                                                       const double* __restrict__ phi, const double* __restrict__ theta, const double* __restrict__ thetaB,
-                                                       const double* __restrict__ grad, double* __restrict__ bsrc, double* __restrict__ diag,
-                                                       double* __restrict__ rD, double* __restrict__ Fs) {
-    extern __shared__ double smem[];
-    const int K = m.K;
-    double* sD = smem;                         // [3][K][TILE]
-    double* sF = smem + 3 * K * TILE;          // [K][TILE]
-    int* sNb = (int*)(smem + 4 * K * TILE);    // [K][TILE]
-    int* sFlag = sNb + K * TILE;               // [K][TILE]
-    const int lane = threadIdx.x & (TILE - 1), grp = threadIdx.x / TILE, nGrp = blockDim.x / TILE;
-    const int c = blockIdx.x * TILE + lane;
-    const bool active = c < m.N;
-    const bool hrs = lim.hrs && !noConv;
-    for (int s = grp; s < K; s += nGrp) {
-        int nb = -1, flag = 0;
-        double F = 0, dx = 0, dy = 0, dz = 0;
-        if (active) {
-            nb = m.nbr[(size_t)s * m.NS + c];
-            if (nb != -1 && !noConv) {
-                const int fi = m.fidx[(size_t)s * m.NS + c];
-                const bool own = fi >= 0;
-                const double ph = phi[own ? fi : ~fi];
-                if (nb >= 0) {
-                    F = own ? ph : -ph;
-                    flag = SLOT_CELL | (own ? SLOT_OWNER : 0) | (ph >= 0 ? SLOT_UPW : 0) | (nb >= m.N ? SLOT_GHOST : 0);
-                    if (hrs) {   // owner/neighbour frame of the face (identical arithmetic on both sides => conservative)
-                        const double Cx = m.C[c], Cy = m.C[(size_t)m.NP + c], Cz = m.C[2 * (size_t)m.NP + c];
-                        const double nx = m.C[nb], ny = m.C[(size_t)m.NP + nb], nz = m.C[2 * (size_t)m.NP + nb];
-                        dx = own ? nx - Cx : Cx - nx; dy = own ? ny - Cy : Cy - ny; dz = own ? nz - Cz : Cz - nz;
-                    }
-                } else {
-                    F = ph;
-                    flag = SLOT_PATCH | (m.bthetaBC[-nb - 2] == RHEO_BC_ZERO_GRADIENT ? SLOT_PATCH_ZG : 0);
-                }
-            }
-            if (writeMatrix) Fs[(size_t)s * m.NS + c] = (flag & SLOT_CELL) ? fmin(F, 0.0) : 0.0;   // row coefficient A[c][nb]
-        }
-        const int i = s * TILE + lane;
-        sD[i] = dx; sD[K * TILE + i] = dy; sD[2 * K * TILE + i] = dz; sF[i] = F; sNb[i] = nb; sFlag[i] = flag;
-    }
-    __syncthreads();
-    if (!active) return;
-    const int k = cl.c[grp];
-    const double* tk = theta + (size_t)k * m.NP;
-    const double tP = tk[c];
-    const int KT_ = K * TILE;
-    const double *pF = sF + lane, *pDx = sD + lane, *pDy = pDx + KT_, *pDz = pDy + KT_;
-    const int *pNb = sNb + lane, *pFlag = sFlag + lane;
-    // ---- diagonal: only needed by the warp that writes it, or by every component when relax() is active
-    double D = 0, sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0;
-    if (relax > 0 || (writeMatrix && grp == 0)) {
-        D = rDeltaT * m.V[c];   // ddt diag + negSumDiag
-        for (int s = 0; s < K; ++s) {
-            const int flag = pFlag[s * TILE];
-            const double F = pF[s * TILE];
-            if (flag & SLOT_CELL) {
-                if (!(flag & SLOT_GHOST)) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
-                else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
-            } else if (flag & SLOT_PATCH_ZG) { iCplain += F; iCplainAbs += fabs(F); }
-        }
-    }
-    // ---- deferred high-resolution correction + fixedValue patch source
-    double sou = 0, bnd = 0;
-    {
-        const double* gx = grad + (size_t)(3 * k) * m.NP;
-        const double* gy = gx + m.NP;
-        const double* gz = gy + m.NP;
-        double gcx = 0, gcy = 0, gcz = 0;
-        if (hrs) { gcx = gx[c]; gcy = gy[c]; gcz = gz[c]; }
-        const Limiter L = lim;
-#pragma unroll 2
-        for (int s = 0; s < K; ++s) {
-            const int flag = pFlag[s * TILE];
-            if (flag & SLOT_CELL) {
-                if (!hrs) continue;
-                const int nb = pNb[s * TILE];
-                const double gnx = gx[nb], gny = gy[nb], gnz = gz[nb], vn = tk[nb];
-                const double dx = pDx[s * TILE], dy = pDy[s * TILE], dz = pDz[s * TILE];
-                const double gc = gcx * dx + gcy * dy + gcz * dz, gn = gnx * dx + gny * dy + gnz * dz;
-                const bool own = flag & SLOT_OWNER;
-                const double v = phif_defc(own ? tP : vn, own ? vn : tP, own ? gc : gn, own ? gn : gc, (flag & SLOT_UPW) != 0, L);
-                sou += v * pF[s * TILE];   // souT[own] += v*phi ; souT[nei] -= v*phi
-            } else if ((flag & (SLOT_PATCH | SLOT_PATCH_ZG)) == SLOT_PATCH) {
-                bnd += -pF[s * TILE] * thetaB[(size_t)k * m.nB + (-pNb[s * TILE] - 2)];
-            }
-        }
-    }
-    double add = 0;
-    if (relax > 0) {   // EXT-OF9 fvMatrix::relax
-        const double D0 = D;
-        double Dn = D + iCcoupled + iCplainAbs;
-        Dn = fmax(fabs(Dn), sumOff);
-        Dn /= relax;
-        Dn -= iCcoupled;
-        Dn -= iCplain;
-        add = (Dn - D0) * tP;
-        D = Dn;
-    }
-    bsrc[(size_t)k * m.NP + c] += (-sou + add) + bnd;
-    if (writeMatrix && grp == 0) {
-        const double Dfull = D + iCcoupled + iCplain;   // addBoundaryDiag
-        diag[c] = Dfull;
-        rD[c] = 1.0 / Dfull;   // DILU: upper*lower == 0 on every face of an upwind matrix
-    }
-}
+enum { SLOT_CELL = 1, SLOT_OWNER = 2, SLOT_GHOST = 8, SLOT_PATCH = 16, SLOT_PATCH_ZG = 32 };   // static slot kinds (tile records, assembly.cuh)
 
 // ---------------------------------------------------------------- Krylov control block (kernels in krylov.cuh)
 struct KrylovCtl {   // one per RHS, device resident

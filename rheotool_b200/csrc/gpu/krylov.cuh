@@ -11,17 +11,21 @@
 // A[s][c] = min(signed outflow flux, 0) in slot-major ELL with neighbour table nbrA.
 //
 // Cells are numbered colour by colour.  One preconditioned product v = A M^-1 p is
-//     y = rD p                                  (written by the kernel that produced p)
-//     k_fwd   colours 1..nc-1 :  y[c] -= rD[c] sum_{nb<c} A y[nb]
-//     k_bwd   colours nc-2..1 :  y[c] -= rD[c] sum_{c<nb<N} A y[nb]
+//     colour 0           :  p = r + beta (p - omega v), y = rD p         (k_update_p / k_make_s on the colour-0 range)
+//     k_sweep<UPD, fwd>  colours 1..nc-1 :  the same vector update of the cell, then y[c] -= rD[c] sum_{nb<c} A y[nb]
+//     k_sweep<0, bwd>    colours nc-2..1 :  y[c] -= rD[c] sum_{c<nb<N} A y[nb]
 //     k_spmv<FUSE=1> colour 0 :  S = sum_{local nb} A y[nb]; y[c] -= rD[c] S; v[c] = diag[c] y[c] + S
 //     k_spmv<FUSE=0> the rest :  v[c] = diag[c] y[c] + sum A y[nb]
-// (for the 2 colours of a hex mesh: 3 half-size launches).  Ghost (processor) neighbours are added by
+// (for the 2 colours of a hex mesh: 3 half-size gather launches).  Ghost (processor) neighbours are added by
 // k_ghost after the halo exchange so that the interior work never waits for NCCL.
+// The gather kernels are persistent over row tiles of 256 cells: one thread streams the NEXT tile's matrix rows (nbrA, A,
+// rD, diag: contiguous blocks) into the other shared-memory stage with cp.async.bulk + mbarrier while the CTA gathers for
+// the current tile, so the only exposed memory latency is the gather itself.
 // Scalar control (alpha, omega, beta, convergence per RHS) runs in the last-block epilogue of the
 // reductions on one GPU, or in k_ctl after the all-reduce on several.
 #pragma once
 #include "kernels.cuh"
+#include "tma.cuh"
 
 namespace rk {
 
@@ -49,24 +53,57 @@ template <int NR> __device__ __forceinline__ void stv(double* __restrict__ p, si
 }
 
 
+// ---------------------------------------------------------------- row-tile pipeline (TMA bulk copies, 2 stages)
+struct RowSrc { const int* nbrT; const double* A; const double* rD; const double* diag; };   // tile-major nbrA / A, per-cell rD / diag
+__host__ __device__ __forceinline__ size_t row_stage_bytes(int K) { return (size_t)K * RT * (sizeof(int) + sizeof(double)) + 2 * RT * sizeof(double); }
+
+__device__ __forceinline__ void row_issue(unsigned char* dst, uint64_t* bar, const RowSrc& rs, int K, int tile) {
+    const uint32_t nbB = (uint32_t)K * RT * sizeof(int), aB = (uint32_t)K * RT * sizeof(double), vB = RT * sizeof(double);
+    mbar_expect_tx(bar, nbB + aB + 2 * vB);
+    bulk_g2s(dst, rs.nbrT + (size_t)tile * K * RT, nbB, bar);
+    bulk_g2s(dst + nbB, rs.A + (size_t)tile * K * RT, aB, bar);
+    bulk_g2s(dst + nbB + aB, rs.rD + (size_t)tile * RT, vB, bar);
+    bulk_g2s(dst + nbB + aB + vB, rs.diag + (size_t)tile * RT, vB, bar);
+}
+struct RowView {   // this thread's row in the current stage
+    const int* nb;      // nb[s * RT]
+    const double* a;    // a[s * RT]
+    double rd, dg;
+};
+__device__ __forceinline__ RowView row_view(const unsigned char* stage, int K) {
+    RowView v;
+    v.nb = (const int*)stage + threadIdx.x;
+    const double* d = (const double*)(stage + (size_t)K * RT * sizeof(int));
+    v.a = d + threadIdx.x;
+    v.rd = d[(size_t)K * RT + threadIdx.x];
+    v.dg = d[(size_t)K * RT + RT + threadIdx.x];
+    return v;
+}
+__device__ __forceinline__ void row_pipe_init(uint64_t* full) {
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+}
+
 // Row gather  acc[j] = sum_s A[s][c] * y[nb(s)][j]  over the slots selected by SEL:
 //   SEL 0: forward substitution (nb < c)   1: backward (c < nb < N)   2: all local columns (nb != c, nb < N)
-// KT > 0: compile-time slot count — the K index/coefficient loads are issued together, then the K gathers
-// (excluded slots read the cell's own row with coefficient 0, so there is no divergent control flow);
-// KT = 0: run-time K.  Slot order and arithmetic are the same in both.
+// KT > 0: compile-time slot count — the K gathers are issued together (excluded slots read the cell's own row with
+// coefficient 0, so there is no divergent control flow); KT = 0: run-time K.  Slot order and arithmetic are the same in both.
 template <int SEL> __device__ __forceinline__ bool slot_selected(int nb, int c, int N) {
     return SEL == 0 ? (nb < c) : (SEL == 1 ? (nb > c && nb < N) : (nb != c && nb < N));
 }
 template <int NR, int KT, int SEL>
-__device__ __forceinline__ void row_gather(const MeshView& m, int c, const double* __restrict__ A, const double* __restrict__ y, size_t base,
-                                           double (&acc)[NR]) {
+__device__ __forceinline__ void row_gather(const RowView& rv, int K, int c, int N, const double* __restrict__ y, size_t base, double (&acc)[NR]) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) acc[j] = 0.0;
     if constexpr (KT == 0) {
-        for (int s = 0; s < m.K; ++s) {
-            const int nb = m.nbrA[(size_t)s * m.NS + c];
-            if (!slot_selected<SEL>(nb, c, m.N)) continue;
-            const double a = A[(size_t)s * m.NS + c];
+        for (int s = 0; s < K; ++s) {
+            const int nb = rv.nb[s * RT];
+            if (!slot_selected<SEL>(nb, c, N)) continue;
+            const double a = rv.a[s * RT];
             double yn[NR];
             ldv<NR>(y, base + nb, yn);
 #pragma unroll
@@ -76,10 +113,10 @@ __device__ __forceinline__ void row_gather(const MeshView& m, int c, const doubl
         int nb[KT];
         double a[KT];
 #pragma unroll
-        for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[(size_t)s * m.NS + c]; a[s] = A[(size_t)s * m.NS + c]; }
+        for (int s = 0; s < KT; ++s) { nb[s] = rv.nb[s * RT]; a[s] = rv.a[s * RT]; }
 #pragma unroll
         for (int s = 0; s < KT; ++s)
-            if (!slot_selected<SEL>(nb[s], c, m.N)) { nb[s] = c; a[s] = 0.0; }
+            if (!slot_selected<SEL>(nb[s], c, N)) { nb[s] = c; a[s] = 0.0; }
 #pragma unroll
         for (int s = 0; s < KT; ++s) {
             double yn[NR];
@@ -233,8 +270,8 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
             for (int j = 0; j < NR; ++j) acc[j] = d * rp.psi[md * NR + j][c];
             if constexpr (KT == 0) {
                 for (int s = 0; s < m.K; ++s) {
-                    const double a = A[(size_t)s * m.NS + c];
-                    const int nb = m.nbrA[(size_t)s * m.NS + c];
+                    const double a = A[ell_t(m.K, s, c)];
+                    const int nb = m.nbrA[ell_t(m.K, s, c)];
                     rowsum += a;
 #pragma unroll
                     for (int j = 0; j < NR; ++j) acc[j] += a * rp.psi[md * NR + j][nb];
@@ -242,7 +279,7 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
             } else {
                 int nb[KT];
 #pragma unroll
-                for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[(size_t)s * m.NS + c]; aRow[s] = A[(size_t)s * m.NS + c]; }
+                for (int s = 0; s < KT; ++s) { nb[s] = m.nbrA[ell_t(KT, s, c)]; aRow[s] = A[ell_t(KT, s, c)]; }
 #pragma unroll
                 for (int s = 0; s < KT; ++s) rowsum += aRow[s];
 #pragma unroll
@@ -262,7 +299,7 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
             if (rp.corr[md * NR] != nullptr) {
                 if constexpr (KT == 0) {
                     for (int s = 0; s < m.K; ++s) {
-                        const double as = A[(size_t)s * m.NS + c];
+                        const double as = A[ell_t(m.K, s, c)];
                         if (as < 0.0) {
 #pragma unroll
                             for (int j = 0; j < NR; ++j) bb[j] -= as * rp.corr[md * NR + j][(size_t)s * m.NS + c];
@@ -295,9 +332,9 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
     finalize_ctl(partials, gridDim.x, 3 * nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);
 }
 
-// ---------------------------------------------------------------- p = r + beta (p - omega v);  y = rD p
+// ---------------------------------------------------------------- p = r + beta (p - omega v);  y = rD p   on cells [c0, c1)
 template <int NR>
-__global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
+__global__ void __launch_bounds__(BLOCK) k_update_p(int c0, int c1, int NP, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
                                                      const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p, double* __restrict__ y) {
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
@@ -309,7 +346,7 @@ __global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nModes, c
             const KrylovCtl& k = ks->ctl[md * NR + j];
             on[j] = k.state == 0; first[j] = k.iters == 0; beta[j] = k.beta; omega[j] = k.omega;
         }
-        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
+        for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
             const double d = rD[c];
             const size_t i = (size_t)md * NP + c;
             double rr[NR], pp[NR], vv[NR], yy[NR];
@@ -327,28 +364,91 @@ __global__ void __launch_bounds__(BLOCK) k_update_p(int N, int NP, int nModes, c
 }
 
 // ---------------------------------------------------------------- DILU forward / backward phases on a cell range
-template <int NR, int KT, int FWD>
-__global__ void __launch_bounds__(BLOCK) k_sweep(MeshView m, int c0, int c1, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
-                                                  const double* __restrict__ A, double* __restrict__ y) {
+// UPD (forward sweeps only) fuses the vector update that produces the right-hand side of the substitution, so that the
+// freshly computed y = rD p (or z = rD s) of the cell never makes a round trip through HBM:
+//   UPD 0 : y holds rD*rhs already             UPD 1 : p = r + beta (p - omega v), y = rD p   (k_update_p of this cell)
+//   UPD 2 : s = r - alpha v, z = rD s, sum|s|  (k_make_s of this cell; y is z, the partial sums share partials/counter
+//           with the colour-0 launch of k_make_s and the other sweeps: blockBase / totalBlocks)
+struct SweepUpd {
+    const double* r; const double* v; double* p; double* sv;
+    double* partials; double* out; unsigned* counter; int blockBase, totalBlocks, ctlWhat;
+    SolveCtl sc;
+};
+template <int NR, int KT, int FWD, int UPD>
+__global__ void __launch_bounds__(RT) k_sweep(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, SweepUpd u) {
     if (ks->nActive == 0) return;
-    const int stride = gridDim.x * BLOCK;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ uint64_t full[2];
+    const int K = KT > 0 ? KT : m.K;
+    const size_t stageBytes = row_stage_bytes(K);
+    const int tBeg = c0 / RT, tEnd = (c1 - 1) / RT;
+    row_pipe_init(full);
+    int it = 0;
     for (int md = 0; md < nModes; ++md) {
         bool on[NR];
+        double ca[NR], cb[NR];   // UPD 1: beta, omega;  UPD 2: alpha
+        bool first[NR];
+        double red[NR];
 #pragma unroll
-        for (int j = 0; j < NR; ++j) on[j] = ks->ctl[md * NR + j].state == 0;
-        for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
-            const double d = rD[c];
-            double acc[NR];
-            row_gather<NR, KT, FWD ? 0 : 1>(m, c, A, y, (size_t)md * m.NP, acc);
-            double yy[NR];
-            const size_t i = (size_t)md * m.NP + c;
-            ldv<NR>(y, i, yy);
-#pragma unroll
-            for (int j = 0; j < NR; ++j)
-                if (on[j]) yy[j] -= d * acc[j];
-            stv<NR>(y, i, yy);
+        for (int j = 0; j < NR; ++j) {
+            const KrylovCtl& k = ks->ctl[md * NR + j];
+            on[j] = k.state == 0; first[j] = k.iters == 0;
+            ca[j] = UPD == 1 ? k.beta : k.alpha; cb[j] = k.omega;
         }
+        if (UPD == 2) {
+#pragma unroll
+            for (int j = 0; j < NR; ++j) red[j] = 0.0;
+        }
+        int tile = tBeg + blockIdx.x;
+        if (threadIdx.x == 0 && tile <= tEnd) row_issue(smemRaw + (size_t)(it & 1) * stageBytes, &full[it & 1], rs, K, tile);
+        for (; tile <= tEnd; tile += gridDim.x, ++it) {
+            const int st = it & 1, next = tile + gridDim.x;
+            if (threadIdx.x == 0 && next <= tEnd) row_issue(smemRaw + (size_t)(st ^ 1) * stageBytes, &full[st ^ 1], rs, K, next);
+            const int c = tile * RT + threadIdx.x;
+            const bool valid = c >= c0 && c < c1;
+            const size_t i = (size_t)md * m.NP + c;
+            // own-cell vectors do not depend on the row: issue their loads before waiting for the stage
+            double yy[NR], rr[NR], vv[NR], pp[NR];
+            if (valid) {
+                if (UPD == 0) ldv<NR>(y, i, yy);
+                else { ldv<NR>(u.r, i, rr); ldv<NR>(u.v, i, vv); if (UPD == 1) ldv<NR>(u.p, i, pp); }
+            }
+            mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
+            if (valid) {
+                const RowView rv = row_view(smemRaw + (size_t)st * stageBytes, K);
+                double acc[NR];
+                row_gather<NR, KT, FWD ? 0 : 1>(rv, K, c, m.N, y, (size_t)md * m.NP, acc);
+                if (UPD == 1) {
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) {
+                        yy[j] = 0.0;
+                        if (!on[j]) continue;
+                        pp[j] = first[j] ? rr[j] : rr[j] + ca[j] * (pp[j] - cb[j] * vv[j]);
+                        yy[j] = rv.rd * pp[j];
+                    }
+                    stv<NR>(u.p, i, pp);
+                } else if (UPD == 2) {
+                    double ss[NR];
+#pragma unroll
+                    for (int j = 0; j < NR; ++j) {
+                        ss[j] = 0.0; yy[j] = 0.0;
+                        if (!on[j]) continue;
+                        ss[j] = rr[j] - ca[j] * vv[j];
+                        yy[j] = rv.rd * ss[j];
+                        red[j] += fabs(ss[j]);
+                    }
+                    stv<NR>(u.sv, i, ss);
+                }
+#pragma unroll
+                for (int j = 0; j < NR; ++j)
+                    if (on[j]) yy[j] -= rv.rd * acc[j];
+                stv<NR>(y, i, yy);
+            }
+            __syncthreads();   // stage st is free for the prefetch issued in the next iteration
+        }
+        if constexpr (UPD == 2) block_reduce_to_partials<NR>(red, u.partials + (size_t)u.blockBase * nModes * NR, md * NR, nModes * NR);
     }
+    if constexpr (UPD == 2) finalize_ctl(u.partials, u.totalBlocks, nModes * NR, u.out, u.counter, (unsigned)u.totalBlocks, u.ctlWhat, ks, nModes * NR, u.sc);
 }
 
 // ---------------------------------------------------------------- v = A y (local columns) with fused dots
@@ -357,13 +457,18 @@ __global__ void __launch_bounds__(BLOCK) k_sweep(MeshView m, int c0, int c1, int
 //   MODE 1   : dot[2q], [2q+1]   = v . v , v . other   (other = s)
 // Several launches (cell ranges) share partials; the last launched range finalises (blockBase/totalBlocks).
 template <int NR, int KT, int MODE, int FUSE>
-__global__ void __launch_bounds__(BLOCK) k_spmv(MeshView m, int c0, int c1, int nModes, KrylovShared* ks, const double* __restrict__ diag,
-                                                 const double* __restrict__ rD, const double* __restrict__ A, double* __restrict__ y, double* __restrict__ v,
-                                                 const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
-                                                 int totalBlocks, int ctlWhat, SolveCtl sc) {
+__global__ void __launch_bounds__(RT) k_spmv(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, double* __restrict__ v,
+                                              const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
+                                              int totalBlocks, int ctlWhat, SolveCtl sc) {
     if (ks->nActive == 0) return;
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    __shared__ uint64_t full[2];
     constexpr int ND = MODE == 0 ? 1 : 2;
-    const int stride = gridDim.x * BLOCK;
+    const int K = KT > 0 ? KT : m.K;
+    const size_t stageBytes = row_stage_bytes(K);
+    const int tBeg = c0 / RT, tEnd = (c1 - 1) / RT;
+    row_pipe_init(full);
+    int it = 0;
     for (int md = 0; md < nModes; ++md) {
         double red[ND * NR];
         bool on[NR];
@@ -371,24 +476,34 @@ __global__ void __launch_bounds__(BLOCK) k_spmv(MeshView m, int c0, int c1, int 
         for (int j = 0; j < ND * NR; ++j) red[j] = 0.0;
 #pragma unroll
         for (int j = 0; j < NR; ++j) on[j] = ks->ctl[md * NR + j].state == 0;
-        for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
-            const double d = diag[c], rd = rD[c];
-            double acc[NR];
-            row_gather<NR, KT, 2>(m, c, A, y, (size_t)md * m.NP, acc);
+        int tile = tBeg + blockIdx.x;
+        if (threadIdx.x == 0 && tile <= tEnd) row_issue(smemRaw + (size_t)(it & 1) * stageBytes, &full[it & 1], rs, K, tile);
+        for (; tile <= tEnd; tile += gridDim.x, ++it) {
+            const int st = it & 1, next = tile + gridDim.x;
+            if (threadIdx.x == 0 && next <= tEnd) row_issue(smemRaw + (size_t)(st ^ 1) * stageBytes, &full[st ^ 1], rs, K, next);
+            const int c = tile * RT + threadIdx.x;
+            const bool valid = c >= c0 && c < c1;
             const size_t i = (size_t)md * m.NP + c;
-            double yy[NR], vv[NR], oo[NR];
-            ldv<NR>(y, i, yy); ldv<NR>(other, i, oo);
+            double yy[NR], oo[NR];
+            if (valid) { ldv<NR>(y, i, yy); ldv<NR>(other, i, oo); }
+            mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
+            if (valid) {
+                const RowView rv = row_view(smemRaw + (size_t)st * stageBytes, K);
+                double acc[NR], vv[NR];
+                row_gather<NR, KT, 2>(rv, K, c, m.N, y, (size_t)md * m.NP, acc);
 #pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                vv[j] = 0.0;   // v of a finished RHS is never read again
-                if (!on[j]) continue;
-                if (FUSE) yy[j] -= rd * acc[j];
-                vv[j] = d * yy[j] + acc[j];
-                if (MODE == 0) red[j] += oo[j] * vv[j];
-                else { red[2 * j] += vv[j] * vv[j]; red[2 * j + 1] += vv[j] * oo[j]; }
+                for (int j = 0; j < NR; ++j) {
+                    vv[j] = 0.0;   // v of a finished RHS is never read again
+                    if (!on[j]) continue;
+                    if (FUSE) yy[j] -= rv.rd * acc[j];
+                    vv[j] = rv.dg * yy[j] + acc[j];
+                    if (MODE == 0) red[j] += oo[j] * vv[j];
+                    else { red[2 * j] += vv[j] * vv[j]; red[2 * j + 1] += vv[j] * oo[j]; }
+                }
+                if (FUSE) stv<NR>(y, i, yy);
+                stv<NR>(v, i, vv);
             }
-            if (FUSE) stv<NR>(y, i, yy);
-            stv<NR>(v, i, vv);
+            __syncthreads();
         }
         block_reduce_to_partials<ND * NR>(red, partials + (size_t)blockBase * ND * nModes * NR, ND * md * NR, ND * nModes * NR);
     }
@@ -411,9 +526,9 @@ __global__ void __launch_bounds__(BLOCK) k_ghost(MeshView m, int nBcells, const 
 #pragma unroll
         for (int j = 0; j < NR; ++j) acc[j] = 0.0;
         for (int s = 0; s < m.K; ++s) {
-            const int nb = m.nbrA[(size_t)s * m.NS + c];
+            const int nb = m.nbrA[ell_t(m.K, s, c)];
             if (nb < m.N) continue;
-            const double a = A[(size_t)s * m.NS + c];
+            const double a = A[ell_t(m.K, s, c)];
             double yn[NR];
             ldv<NR>(y, (size_t)md * m.NP + nb, yn);
 #pragma unroll
@@ -434,11 +549,12 @@ __global__ void __launch_bounds__(BLOCK) k_ghost(MeshView m, int nBcells, const 
     }
 }
 
-// ---------------------------------------------------------------- s = r - alpha v ; z = rD s ; sum|s|
+// ---------------------------------------------------------------- s = r - alpha v ; z = rD s ; sum|s|   on cells [c0, c1)
+// (the colour-0 range; the other colours do this inside k_sweep<UPD = 2> and share partials / counter: totalBlocks)
 template <int NR>
-__global__ void __launch_bounds__(BLOCK) k_make_s(int N, int NP, int nModes, KrylovShared* ks, const double* __restrict__ rD, const double* __restrict__ r,
+__global__ void __launch_bounds__(BLOCK) k_make_s(int c0, int c1, int NP, int nModes, KrylovShared* ks, const double* __restrict__ rD, const double* __restrict__ r,
                                                    const double* __restrict__ v, double* __restrict__ sv, double* __restrict__ z, double* partials,
-                                                   double* out, unsigned* counter, int ctlWhat, SolveCtl sc) {
+                                                   double* out, unsigned* counter, int totalBlocks, int ctlWhat, SolveCtl sc) {
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
     for (int md = 0; md < nModes; ++md) {
@@ -446,7 +562,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_s(int N, int NP, int nModes, Kry
         bool on[NR];
 #pragma unroll
         for (int j = 0; j < NR; ++j) { red[j] = 0.0; const KrylovCtl& k = ks->ctl[md * NR + j]; on[j] = k.state == 0; alpha[j] = k.alpha; }
-        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
+        for (int c = c0 + blockIdx.x * BLOCK + threadIdx.x; c < c1; c += stride) {
             const double d = rD[c];
             const size_t i = (size_t)md * NP + c;
             double rr[NR], vv[NR], ss[NR], zz[NR];
@@ -463,7 +579,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_s(int N, int NP, int nModes, Kry
         }
         block_reduce_to_partials<NR>(red, partials, md * NR, nModes * NR);
     }
-    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);
+    finalize_ctl(partials, totalBlocks, nModes * NR, out, counter, (unsigned)totalBlocks, ctlWhat, ks, nModes * NR, sc);
 }
 
 // ---------------------------------------------------------------- psi += alpha y + omega z ; r = s - omega t ; sum|r| , r0.r

@@ -46,41 +46,95 @@ int halo_interleaved(RheoGpu* h, int nModes, double* x) {
     return 0;
 }
 
-// v = A M^-1 (rhs), where x already holds rD*rhs.  MODE 0: dots r0.v -> alpha; MODE 1: t.t, t.s -> omega
-template <int NR, int KT, int MODE>
-int precond_spmv(RheoGpu* h, int nModes, double* x, double* v, const double* other, double* redOut, const SolveCtl& sc) {
+// persistent grid of a row-tile kernel over `cells` cells: one resident wave for its dynamic shared memory
+template <class Kern> int row_grid(RheoGpu* h, Kern kern, long cells, size_t smem) {
+    auto it = h->residentBlocks.find((const void*)kern);
+    int blocks;
+    if (it == h->residentBlocks.end()) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int perSm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, RT, smem) != cudaSuccess || perSm < 1) { cudaGetLastError(); perSm = 1; }
+        blocks = perSm * h->nSms;
+        h->residentBlocks[(const void*)kern] = blocks;
+    } else blocks = it->second;
+    return std::max(1, std::min(cdiv(cells, RT) + 1, blocks));   // + 1: a range that starts mid-tile touches one more tile
+}
+
+// One preconditioned product of the PBiCGStab iteration:
+//   WHICH 0 :  p = r + beta (p - omega v);  y = M^-1 p;  v = A y;  dots r0.v -> alpha            (x = y, w = v)
+//   WHICH 1 :  s = r - alpha v (sum|s| -> half-step convergence);  z = M^-1 s;  t = A z;  dots t.t, t.s -> omega   (x = z, w = t)
+// The vector update runs inside the first pass over each cell (colour 0: streaming kernel; other colours: fused into the
+// forward substitution).
+template <int NR, int KT, int WHICH>
+int precond_spmv(RheoGpu* h, int nModes, const SolveCtl& sc) {
     KrylovShared* ks = h->d_ks.as<KrylovShared>();
-    const double* diag = h->d_diag.as<double>();
     const double* rD = h->d_rD.as<double>();
-    const double* A = h->d_Fs.as<double>();
+    const RowSrc rs{h->d_nbrA.as<int>(), h->d_Fs.as<double>(), rD, h->d_diag.as<double>()};
     double* part = h->d_partials.as<double>();
+    double* red = h->d_red.as<double>();
     unsigned* counter = h->d_counter.as<unsigned>();
-    const int nc = h->nColours;
+    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *p = h->d_p.as<double>(), *y = h->d_y.as<double>(), *v = h->d_v.as<double>(),
+           *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
+    double* x = WHICH == 0 ? y : z;
+    double* w = WHICH == 0 ? v : t;
+    const double* other = WHICH == 0 ? r0 : sv;
+    double* redDots = WHICH == 0 ? red : red + 2 * MAX_RED;   // redA / redC
+    double* redHalf = red + MAX_RED;                           // redB
+    const int nc = h->nColours, N = h->N, NP = h->NP;
     const bool multi = h->nRanks > 1;
-    const int what = multi ? CTL_NONE : (MODE == 0 ? CTL_ALPHA : CTL_OMEGA);
+    const size_t smem = 2 * row_stage_bytes(h->K);
+    constexpr int UPD = WHICH == 0 ? 1 : 2;
+    const int n0 = h->colourStart[1];
+
+    // ---- vector update + forward substitution
+    std::vector<int> grids(nc, 0);
+    int totalBlocks = 0;
+    grids[0] = WHICH == 0 ? GRID(h, (k_update_p<NR>), n0) : GRID(h, (k_make_s<NR>), n0);
+    totalBlocks = grids[0];
+    for (int k = 1; k < nc; ++k) {
+        const int cells = h->colourStart[k + 1] - h->colourStart[k];
+        grids[k] = cells > 0 ? row_grid(h, (k_sweep<NR, KT, 1, UPD>), cells, smem) : 0;
+        totalBlocks += grids[k];
+    }
+    const int halfWhat = multi ? CTL_NONE : CTL_HALF;
+    if (WHICH == 0) LAUNCH(h, (k_update_p<NR>), grids[0], BLOCK, 0, n0, NP, nModes, ks, rD, r, v, p, y);
+    else LAUNCH(h, (k_make_s<NR>), grids[0], BLOCK, 0, n0, NP, nModes, ks, rD, r, v, sv, z, part, redHalf, counter, totalBlocks, halfWhat, sc);
+    int base = grids[0];
     for (int k = 1; k < nc; ++k) {
         const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
-        if (c1 > c0) LAUNCH(h, (k_sweep<NR, KT, 1>), GRID(h, (k_sweep<NR, KT, 1>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
+        if (c1 <= c0) continue;
+        SweepUpd u{r, v, p, sv, part, redHalf, counter, base, totalBlocks, halfWhat, sc};
+        LAUNCH_SM(h, (k_sweep<NR, KT, 1, UPD>), grids[k], RT, smem, h->mv, rs, c0, c1, nModes, ks, x, u);
+        base += grids[k];
     }
+    if (WHICH == 1 && multi) {
+        if (all_reduce(h, redHalf, nModes * NR)) return 1;
+        LAUNCH(h, k_ctl, 1, 32, CTL_HALF, ks, nModes * NR, redHalf, sc);
+    }
+    // ---- backward substitution of the middle colours
     for (int k = nc - 2; k >= 1; --k) {
         const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
-        if (c1 > c0) LAUNCH(h, (k_sweep<NR, KT, 0>), GRID(h, (k_sweep<NR, KT, 0>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, x);
+        if (c1 <= c0) continue;
+        SweepUpd u{};
+        LAUNCH_SM(h, (k_sweep<NR, KT, 0, 0>), row_grid(h, (k_sweep<NR, KT, 0, 0>), c1 - c0, smem), RT, smem, h->mv, rs, c0, c1, nModes, ks, x, u);
     }
-    const int n0 = h->colourStart[1];
-    const int g0 = (nc >= 2) ? GRID(h, (k_spmv<NR, KT, MODE, 1>), n0) : GRID(h, (k_spmv<NR, KT, MODE, 0>), n0);
-    const int g1 = (h->N > n0) ? GRID(h, (k_spmv<NR, KT, MODE, 0>), h->N - n0) : 0;
+    // ---- colour 0: last backward substitution fused into the SpMV; the rest: SpMV
+    constexpr int MODE = WHICH;
+    const int what = multi ? CTL_NONE : (MODE == 0 ? CTL_ALPHA : CTL_OMEGA);
+    const int g0 = (nc >= 2) ? row_grid(h, (k_spmv<NR, KT, MODE, 1>), n0, smem) : row_grid(h, (k_spmv<NR, KT, MODE, 0>), n0, smem);
+    const int g1 = (N > n0) ? row_grid(h, (k_spmv<NR, KT, MODE, 0>), N - n0, smem) : 0;
     if (nc >= 2) {
-        LAUNCH(h, (k_spmv<NR, KT, MODE, 1>), g0, BLOCK, h->mv, 0, n0, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0 + g1, what, sc);
-        if (g1) LAUNCH(h, (k_spmv<NR, KT, MODE, 0>), g1, BLOCK, h->mv, n0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, g0, g0 + g1, what, sc);
+        LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 1>), g0, RT, smem, h->mv, rs, 0, n0, nModes, ks, x, w, other, part, redDots, counter, 0, g0 + g1, what, sc);
+        if (g1) LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g1, RT, smem, h->mv, rs, n0, N, nModes, ks, x, w, other, part, redDots, counter, g0, g0 + g1, what, sc);
     } else {
-        LAUNCH(h, (k_spmv<NR, KT, MODE, 0>), g0, BLOCK, h->mv, 0, h->N, nModes, ks, diag, rD, A, x, v, other, part, redOut, counter, 0, g0, what, sc);
+        LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g0, RT, smem, h->mv, rs, 0, N, nModes, ks, x, w, other, part, redDots, counter, 0, g0, what, sc);
     }
     if (multi) {
         const int nd = (MODE == 0 ? 1 : 2) * nModes * NR;
         if (halo_interleaved<NR>(h, nModes, x)) return 1;
-        if (h->nBcells) LAUNCH(h, (k_ghost<NR, MODE>), cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, A, x, v, other, redOut);
-        if (all_reduce(h, redOut, nd)) return 1;
-        LAUNCH(h, k_ctl, 1, 32, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, ks, nModes * NR, redOut, sc);
+        if (h->nBcells) LAUNCH(h, (k_ghost<NR, MODE>), cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, h->d_Fs.as<double>(), x, w, other, redDots);
+        if (all_reduce(h, redDots, nd)) return 1;
+        LAUNCH(h, k_ctl, 1, 32, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, ks, nModes * NR, redDots, sc);
     }
     return 0;
 }
@@ -91,13 +145,12 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
     KrylovShared* ks = h->d_ks.as<KrylovShared>();
     double* part = h->d_partials.as<double>();
     double* red = h->d_red.as<double>();
-    double *redA = red, *redB = red + MAX_RED, *redC = red + 2 * MAX_RED, *redD = red + 3 * MAX_RED;
+    double *redA = red, *redB = red + MAX_RED, *redD = red + 3 * MAX_RED;
     unsigned* counter = h->d_counter.as<unsigned>();
-    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *p = h->d_p.as<double>(), *y = h->d_y.as<double>(), *v = h->d_v.as<double>(),
+    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *y = h->d_y.as<double>(),
            *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
     const SolveCtl sc{h->ctl.tolerance, h->ctl.rel_tol, h->ctl.min_iter, h->ctl.max_iter};
     const double* diag = h->d_diag.as<double>();
-    const double* rD = h->d_rD.as<double>();
     const double* A = h->d_Fs.as<double>();
     const bool multi = h->nRanks > 1;
 
@@ -119,14 +172,8 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
     int spec = std::max(1, h->specIters);
     for (;;) {
         for (int it = 0; it < spec; ++it) {
-            LAUNCH(h, (k_update_p<NR>), GRID(h, (k_update_p<NR>), N), BLOCK, N, NP, nModes, ks, rD, r, v, p, y);
-            if (precond_spmv<NR, KT, 0>(h, nModes, y, v, r0, redA, sc)) return 1;
-            LAUNCH(h, (k_make_s<NR>), GRID(h, (k_make_s<NR>), N), BLOCK, N, NP, nModes, ks, rD, r, v, sv, z, part, redB, counter, multi ? CTL_NONE : CTL_HALF, sc);
-            if (multi) {
-                if (all_reduce(h, redB, nrhs)) return 1;
-                LAUNCH(h, k_ctl, 1, 32, CTL_HALF, ks, nrhs, redB, sc);
-            }
-            if (precond_spmv<NR, KT, 1>(h, nModes, z, t, sv, redC, sc)) return 1;
+            if (precond_spmv<NR, KT, 0>(h, nModes, sc)) return 1;
+            if (precond_spmv<NR, KT, 1>(h, nModes, sc)) return 1;
             LAUNCH(h, (k_update_x_r<NR>), GRID(h, (k_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, y, z, sv, t, r0, r, part, redD, counter, multi ? CTL_NONE : CTL_END, sc);
             if (multi) {
                 if (all_reduce(h, redD, 2 * nrhs)) return 1;

@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """Per-source-line hot spots of one kernel from an .ncu-rep captured with --import-source on (and -lineinfo).
-usage: ncu_lines.py rep kernel-regex [top-n]"""
+usage: ncu_lines.py rep kernel-regex [top-n] [substring the demangled function name must contain]"""
 import csv, io, subprocess, sys, collections
 rep, rx = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
+need = sys.argv[4] if len(sys.argv) > 4 else ""
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv", "--kernel-name", "regex:" + rx],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 agg = collections.OrderedDict()
 hdr = None
 cur_file = None
+cur_fn = ""
 for r in rows:
     if len(r) == 2 and r[0] == "File Path":
         cur_file = r[1].split("/")[-1]; continue
+    if len(r) == 2 and r[0] == "Function Name":
+        cur_fn = r[1]; continue
     if r and r[0] == "Line No":
         hdr = r; continue
+    if need and need not in cur_fn:
+        continue
     if hdr is None or len(r) < len(hdr) or not r[0].isdigit():
         continue
     d = dict(zip(hdr[2:], r[2:]))   # sass-level columns (the 2nd "Source" is the SASS text)
