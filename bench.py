@@ -53,33 +53,46 @@ def peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int) -> float | None:
-    """Algorithmic bytes one launch moves per cell it processes (d=8, i=4,
-    f = internal faces per cell (3 in 3-D, 2 in 2-D), c = solved components x modes)."""
+def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int):
+    """(algorithmic bytes one launch moves per cell it processes, fraction of the mesh one launch processes).
+    DESIGN.md §3; d=8, i=4, f = internal faces per cell (3 in 3-D, 2 in 2-D), K = 2f slots, c1 = solved components of one
+    mode, c = c1 x modes.  Gathers from neighbours count once per distinct neighbour cell (they are L2/L1 hits otherwise)."""
     f = 3 if dims == 3 else 2
-    c1 = 6 if dims == 3 else 4          # solved components of one mode
-    K = 2 * f                           # slots per cell
+    c1 = 6 if dims == 3 else 4
+    K = 2 * f
     c = c1 * n_modes
-    k = kernel.strip("()").split("<")[0]
-    table = {
-        # theta, U, nbr, rslot, gS, gW, Fell, C, rV+V | A, diag+rD, bsrc, corr (one value per face and component), gradU
-        "k_flux_assemble": (c1 + 3) * 8 + K * 4 + K + 3 * K * 8 + K * 8 + K * 8 + 24 + 16 + K * 8 + 16 + c1 * 8 + f * c1 * 8 + 72,
-        # gradU, theta, thetaOld, lam, R, V, A, corr (inflow faces), bsrc read | bsrc, fFene
-        "k_cell_source2": (9 + 6 + 6 + 3 + 9 + 1) * 8 + K * 8 + f * c1 * 8 + c1 * 8 + 6 * 8 + 8,
-        "k_grad_theta": 6 * 8 + f * (4 * 8 + 2 * 4) + 8 + 18 * 8,
-        "k_cell_source": (3 + 3 + 9 + 6 + 6 + 1) * 8 + f * (4 * 8 + 2 * 4) + (6 + 1) * 8,
-        "k_convect": (6 + 18 + 3 + 12 + 1 + 2) * 8 + f * (8 + 2 * 4) + 2 * f * 8,
-        "k_eig_tau": (6 + 1) * 8 + (3 + 9 + 6) * 8,
-        "k_spmv_dot": 8 + 2 * f * (8 + 4) + c * 24,
-        "k_krylov_init": 8 + 2 * f * (8 + 4) + c * 32,
-        "k_sweep_fwd": 8 + 2 * f * (8 + 4) + c * 16,
-        "k_sweep_bwd": 8 + 2 * f * (8 + 4) + c * 16,
-        "k_update_x_r": c * 8 * 8,
-        "k_make_s": c * 8 * 3,
-        "k_update_p": c * 8 * 4,
-        "k_sum_psi": c * 8,
-    }
-    return table.get(k)
+    k = kernel.strip("()")
+    base = k.split("<")[0]
+    half = 1.0 / max(1, n_colours)      # kernels launched per colour (hex meshes: 2 colours -> half the mesh per launch)
+    row = K * (4 + 8)                   # matrix row: neighbour table + coefficients
+    if base == "k_flux_assemble":
+        # theta, U, tile record (nbr, meta, S, W, D, rV, V), flux tile | A, diag+rD, bsrc, corr (one value per face and component), gradU
+        return (c1 + 3) * 8 + K * (4 + 4 + 7 * 8) + 16 + K * 8 + K * 8 + 16 + c1 * 8 + f * c1 * 8 + 72, 1.0
+    if base == "k_cell_source2":
+        # gradU, theta, thetaOld, lam, R, V, bsrc read | bsrc, fFene
+        return (9 + 6 + 6 + 3 + 9 + 1) * 8 + c1 * 8 + 6 * 8 + 8, 1.0
+    if base == "k_eig_tau":
+        return (6 + 1) * 8 + (3 + 9 + 6) * 8, 1.0
+    if base == "k_krylov_init":
+        # diag, row, psi own + gathered, b, corr (inflow faces) | r, r0
+        return 8 + row + c * 8 * 2 + c * 8 + f * c * 8 + 2 * c * 8, 1.0
+    if base == "k_sweep":
+        # rD, row, gathered y | UPD 1: r, p, v -> p, y;  UPD 2: r, v -> s, z  (average 4.5 vectors); plain: y -> y
+        fused = "UPD" in k or k.rstrip(">").endswith(("1", "2"))
+        return 8 + row + c * 8 + (4.5 if fused else 2) * c * 8, half
+    if base == "k_spmv":
+        # diag, rD, row, gathered y, y own, other | v (+ y when the backward substitution is fused: colour 0)
+        fuse = k.rstrip(">").rstrip().endswith("1")
+        return 16 + row + c * 8 * 4 + (c * 8 if fuse else 0), half
+    if base == "k_update_p":
+        return 8 + 5 * c * 8, half
+    if base == "k_make_s":
+        return 8 + 4 * c * 8, half
+    if base == "k_update_x_r":
+        return 8 * c * 8, 1.0
+    if base == "k_sum_psi":
+        return c * 8, 1.0
+    return None, 1.0
 
 
 class ClockSampler:
@@ -138,6 +151,8 @@ def initial_state(m, spec):
 
 
 def run_ours(args):
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # NCCL prints its version banner on stdout; stdout carries the one JSON line
     import torch
     import torch.distributed as dist
     from rheotool_b200.stress import GpuStressModel, eig_exp
@@ -257,10 +272,8 @@ def run_ours(args):
             name, (cnt, tms) = top
             peak, peak_src = peaks()
             _, cstart = g.renumbering()
-            bpc = kernel_bytes_per_cell(name, spec.dims, len(spec.models), len(cstart) - 1)
-            cells_per_launch = m.n_cells
-            if name.startswith("k_sweep"):
-                cells_per_launch = m.n_cells / max(1, len(cstart) - 1)   # one colour per launch
+            bpc, frac_cells = kernel_bytes_per_cell(name, spec.dims, len(spec.models), len(cstart) - 1)
+            cells_per_launch = m.n_cells * frac_cells
             achieved = (bpc * cells_per_launch / (tms / cnt * 1e-3) / 1e9) if bpc else None
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,

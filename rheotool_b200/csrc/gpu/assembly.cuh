@@ -262,32 +262,87 @@ struct SourceArgs {
     int solvedIdx[6];       // component -> index among the solved components, -1 if not solved (2-D: xz, yz)
     const double* gradU; const double* theta; const double* thetaOld; const double* lam; const double* R;
     double* bsrc; double* fFene;
+    // sum of theta over the cells per solved component (gAverage(psi) of the solver's normFactor): theta is in registers
+    // here anyway, so the reduction rides along instead of being a kernel of its own
+    double* sumPartials; double* sumOut; unsigned* counter;
 };
 
-__global__ void __launch_bounds__(128, 4) k_cell_source2(MeshView m, SourceArgs a) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= m.N) return;
-    double g[9], thO[6], own6[6], th[6], Rm[9], lm[3], rhs[6];
+constexpr int SRC_BLOCK = 128;
+__global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, SourceArgs a) {
+    double sum[6] = {0, 0, 0, 0, 0, 0};
+    // persistent grid (one resident wave): the reduction epilogue is paid once per CTA, not once per 128 cells
+    for (int c = blockIdx.x * SRC_BLOCK + threadIdx.x; c < m.N; c += gridDim.x * SRC_BLOCK) {
+        double g[9], thO[6], own6[6], th[6], Rm[9], lm[3], rhs[6];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) g[i] = a.gradU[(size_t)i * m.NP + c];
+        for (int i = 0; i < 9; ++i) g[i] = a.gradU[(size_t)i * m.NP + c];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) th[k] = a.theta[(size_t)k * m.NP + c];
+        for (int k = 0; k < 6; ++k) th[k] = a.theta[(size_t)k * m.NP + c];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Rm[k] = a.R[(size_t)k * m.NP + c];
+        for (int k = 0; k < 9; ++k) Rm[k] = a.R[(size_t)k * m.NP + c];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) lm[k] = a.lam[(size_t)k * m.NP + c];
+        for (int k = 0; k < 3; ++k) lm[k] = a.lam[(size_t)k * m.NP + c];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            thO[k] = a.thetaOld[(size_t)k * m.NP + c];
+            own6[k] = a.solvedIdx[k] >= 0 ? a.bsrc[(size_t)k * m.NP + c] : 0.0;
+        }
+        const double V = m.V[c];
+        // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
+        const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
+        const double f = model_rhs(a.mp, L, th, Rm, lm, rhs);
+        a.fFene[c] = f;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            a.bsrc[(size_t)k * m.NP + c] = (a.rDeltaT * thO[k] * V + V * rhs[k]) + own6[k];
+            sum[k] += th[k];
+        }
+    }
+    // ---- sum(theta) per component: warp shuffle, block partials, last block sums the partials in block order
+    __shared__ double sm[SRC_BLOCK / 32][6];
+    __shared__ bool isLast;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        thO[k] = a.thetaOld[(size_t)k * m.NP + c];
-        own6[k] = a.solvedIdx[k] >= 0 ? a.bsrc[(size_t)k * m.NP + c] : 0.0;
-    }
-    const double V = m.V[c];
-    // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
-    const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
-    const double f = model_rhs(a.mp, L, th, Rm, lm, rhs);
-    a.fFene[c] = f;
+        double x = sum[k];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) a.bsrc[(size_t)k * m.NP + c] = (a.rDeltaT * thO[k] * V + V * rhs[k]) + own6[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0) sm[warp][k] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double x = 0;
+#pragma unroll
+        for (int wv = 0; wv < SRC_BLOCK / 32; ++wv) x += sm[wv][threadIdx.x];
+        a.sumPartials[(size_t)blockIdx.x * 6 + threadIdx.x] = x;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) isLast = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    for (int k = warp; k < 6; k += SRC_BLOCK / 32) {
+        double x = 0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) x += a.sumPartials[(size_t)b * 6 + k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if (lane == 0 && a.solvedIdx[k] >= 0) a.sumOut[a.solvedIdx[k]] = x;
+    }
+    if (threadIdx.x == 0) *a.counter = 0;
+}
+
+// theta.correctBoundaryConditions() and the zeroGradient part of tau.correctBoundaryConditions() in one launch:
+// zeroGradient patch value = internal value
+__global__ void k_bc_zero_gradient2(MeshView m, const double* __restrict__ theta, double* __restrict__ thetaB, const double* __restrict__ tau,
+                                    double* __restrict__ tauB) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.nB) return;
+    if (m.bkind[b] == RHEO_PATCH_EMPTY) return;
+    const int c = m.bcell[b];
+    if (m.bthetaBC[b] == RHEO_BC_ZERO_GRADIENT)
+        for (int k = 0; k < 6; ++k) thetaB[(size_t)k * m.nB + b] = theta[(size_t)k * m.NP + c];
+    if (m.btauBC[b] == RHEO_BC_ZERO_GRADIENT)
+        for (int k = 0; k < 6; ++k) tauB[(size_t)k * m.nB + b] = tau[(size_t)k * m.NP + c];
 }
 
 // processor faces: deferred values received from the upwind side, for the cells that own ghost slots

@@ -121,7 +121,7 @@ struct RheoGpu {
     MeshView mv;
     // fields
     DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_stage, d_tmpB;
-    DevBuf d_Fell, d_gradU;
+    DevBuf d_Fell, d_gradU, d_sumPsi;   // d_sumPsi: sum of theta per (mode, solved component), written by k_cell_source2
     std::vector<ModeDev> modes;
     // Krylov
     DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ks, d_partials, d_red, d_counter, d_bcells;
@@ -409,7 +409,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
                     const int f = fi >= 0 ? fi : ~fi;
                     const double sg = fi >= 0 ? 1.0 : -1.0;
                     for (int x = 0; x < 3; ++x) rS[x * K * TILE + i] = sg * Sf[(size_t)x * nF + f];
-                    rW[i] = w[f];
+                    rW[i] = nb >= 0 ? w[f] : 0.0;   // patch slots: w = 0 makes the branch-free face value w (P - N) + N the patch value
                     if (nb >= 0) {
                         const bool own = fi >= 0;   // == (nb > c): faces are in upper-triangular order
                         int rs = 0;
@@ -504,7 +504,7 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
     for (DevBuf* b : {&h->d_r, &h->d_r0, &h->d_p, &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t}) zero(h, *b);
     const int nBlocks = cdiv(h->N, BLOCK);
     if (h->d_ks.alloc(sizeof(KrylovShared)) || h->d_partials.alloc((size_t)nBlocks * MAX_RED * d8) || h->d_red.alloc(4 * MAX_RED * d8) ||
-        h->d_counter.alloc(sizeof(unsigned)))
+        h->d_counter.alloc(sizeof(unsigned)) || h->d_sumPsi.alloc((size_t)nModes * 6 * d8))
         return 1;
     zero(h, h->d_counter); zero(h, h->d_red); zero(h, h->d_ks);
     CK(cudaHostAlloc((void**)&h->h_ks, sizeof(KrylovShared), cudaHostAllocDefault));
@@ -660,7 +660,8 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
                 sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
                 sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>();
-                LAUNCH(h, k_cell_source2, cdiv(N, 128), 128, h->mv, sa);
+                sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
+                LAUNCH(h, k_cell_source2, std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms), SRC_BLOCK, h->mv, sa);
             }
             if (h->H && hrs) {
                 if (halo_sendrecv(h, stride)) return 1;
@@ -689,8 +690,8 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             }
         int iters = 0;
         int rc;
-        if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m1 - m0, &iters) : solve_batch<6, 0>(h, rp, m1 - m0, &iters);
-        else rc = (h->K == 4) ? solve_batch<4, 4>(h, rp, m1 - m0, &iters) : solve_batch<4, 0>(h, rp, m1 - m0, &iters);
+        if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m0, m1 - m0, &iters) : solve_batch<6, 0>(h, rp, m0, m1 - m0, &iters);
+        else rc = (h->K == 4) ? solve_batch<4, 4>(h, rp, m0, m1 - m0, &iters) : solve_batch<4, 0>(h, rp, m0, m1 - m0, &iters);
         if (rc) return rc;
         h->specIters = std::max(1, iters);
         int q = 0;
@@ -712,16 +713,14 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     }
     if (h->timing) cudaEventRecord(h->ev[3], h->stream);
 
-    // ---- theta BCs, eig + exp + tau
-    for (ModeDev& md : h->modes) {
-        if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_bthetaBC.as<int>(), md.theta.as<double>(), md.thetaB.as<double>(), 6);
+    // ---- eig + exp + tau
+    for (ModeDev& md : h->modes)
         LAUNCH(h, k_eig_tau, grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>());
-    }
     if (h->timing) cudaEventRecord(h->ev[4], h->stream);
-    // ---- tau.correctBoundaryConditions(): processor values first, then physical patches in order
+    // ---- theta BCs; tau.correctBoundaryConditions(): processor values first, then physical patches in order
     for (ModeDev& md : h->modes) {
         if (h->H && halo_planes(h, md.tau.as<double>(), 6)) return 1;
-        if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_btauBC.as<int>(), md.tau.as<double>(), md.tauB.as<double>(), 6);
+        if (h->nB) LAUNCH(h, k_bc_zero_gradient2, cdiv(h->nB, BLOCK), BLOCK, h->mv, md.theta.as<double>(), md.thetaB.as<double>(), md.tau.as<double>(), md.tauB.as<double>());
         for (const RheoPatchDesc& p : h->patches) {
             if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR || p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION || p.size == 0) continue;
             const int b0 = p.start - h->nInt;
@@ -805,7 +804,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
-                      &h->d_tileRec, &h->d_Fell, &h->d_gradU,
+                      &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();

@@ -53,6 +53,9 @@ template <int NR> __device__ __forceinline__ void stv(double* __restrict__ p, si
 }
 
 
+#ifndef RK_ROW_MINB
+#define RK_ROW_MINB 2   // resident CTAs per SM the row-tile kernels are compiled for (register cap 65536 / (256 * MINB))
+#endif
 // ---------------------------------------------------------------- row-tile pipeline (TMA bulk copies, 2 stages)
 struct RowSrc { const int* nbrT; const double* A; const double* rD; const double* diag; };   // tile-major nbrA / A, per-cell rD / diag
 __host__ __device__ __forceinline__ size_t row_stage_bytes(int K) { return (size_t)K * RT * (sizeof(int) + sizeof(double)) + 2 * RT * sizeof(double); }
@@ -375,7 +378,7 @@ struct SweepUpd {
     SolveCtl sc;
 };
 template <int NR, int KT, int FWD, int UPD>
-__global__ void __launch_bounds__(RT) k_sweep(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, SweepUpd u) {
+__global__ void __launch_bounds__(RT, RK_ROW_MINB) k_sweep(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, SweepUpd u) {
     if (ks->nActive == 0) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     __shared__ uint64_t full[2];
@@ -457,7 +460,7 @@ __global__ void __launch_bounds__(RT) k_sweep(MeshView m, RowSrc rs, int c0, int
 //   MODE 1   : dot[2q], [2q+1]   = v . v , v . other   (other = s)
 // Several launches (cell ranges) share partials; the last launched range finalises (blockBase/totalBlocks).
 template <int NR, int KT, int MODE, int FUSE>
-__global__ void __launch_bounds__(RT) k_spmv(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, double* __restrict__ v,
+__global__ void __launch_bounds__(RT, RK_ROW_MINB) k_spmv(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, double* __restrict__ v,
                                               const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
                                               int totalBlocks, int ctlWhat, SolveCtl sc) {
     if (ks->nActive == 0) return;

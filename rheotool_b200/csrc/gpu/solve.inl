@@ -140,12 +140,12 @@ int precond_spmv(RheoGpu* h, int nModes, const SolveCtl& sc) {
 }
 
 template <int NR, int KT>
-int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
+int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* itersOut) {
     const int nrhs = nModes * NR, N = h->N, NP = h->NP;
     KrylovShared* ks = h->d_ks.as<KrylovShared>();
     double* part = h->d_partials.as<double>();
     double* red = h->d_red.as<double>();
-    double *redA = red, *redB = red + MAX_RED, *redD = red + 3 * MAX_RED;
+    double *redB = red + MAX_RED, *redD = red + 3 * MAX_RED;
     unsigned* counter = h->d_counter.as<unsigned>();
     double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *y = h->d_y.as<double>(),
            *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
@@ -160,9 +160,10 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int nModes, int* itersOut) {
         for (int q = 0; q < nrhs; ++q) pl.p[q] = rp.psi[q];
         if (halo_exchange(h, pl)) return 1;
     }
-    LAUNCH(h, (k_sum_psi<NR>), GRID(h, (k_sum_psi<NR>), N), BLOCK, N, nModes, rp, part, redA, counter);
-    if (all_reduce(h, redA, nrhs)) return 1;
-    LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, redA, (double)h->nGlobalCells, r, r0, part, redB, counter,
+    // gAverage(psi): the per-component sums were accumulated by k_cell_source2 while it had theta in registers
+    double* sumPsi = h->d_sumPsi.as<double>() + (size_t)firstMode * NR;
+    if (all_reduce(h, sumPsi, nrhs)) return 1;
+    LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, r, r0, part, redB, counter,
            multi ? CTL_NONE : CTL_INIT, ks, sc);
     if (multi) {
         if (all_reduce(h, redB, 3 * nrhs)) return 1;
