@@ -216,12 +216,14 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = []
     barrier()
+    cs0 = g.comm_stats()
     e0.record(ext)
     for _ in range(args.steps):
         one_step()
         iters.append(g.last_iterations())
     e1.record(ext)
     barrier()
+    cs1 = g.comm_stats()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if n > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -300,6 +302,11 @@ def run_ours(args):
                        "l2": "working set (~1.0 kB/cell) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": launches,
+            "comm": {"mode": cs1["mode"],
+                     "halo_wait_ms_per_step": (cs1["halo_wait_ms"] - cs0["halo_wait_ms"]) / args.steps,
+                     "reduce_wait_ms_per_step": (cs1["reduce_wait_ms"] - cs0["reduce_wait_ms"]) / args.steps,
+                     "halo_swaps_per_step": (cs1["halo_waits"] - cs0["halo_waits"]) / args.steps,
+                     "reductions_per_step": (cs1["reduce_waits"] - cs0["reduce_waits"]) / args.steps},
             "clocks": clocks,
             "roofline": roof,
             "phase_ms": phase,

@@ -155,6 +155,10 @@ int rheo_gpu_get_ell(RheoGpu* h, int32_t* K, int32_t* nbr, int32_t* face);
 int64_t rheo_gpu_launch_count(const RheoGpu* h);
 /* Krylov iterations (max over components and modes) of the last step */
 int rheo_gpu_last_iterations(const RheoGpu* h);
+/* multi-GPU path in use: mode 0 single rank, 1 NCCL send/recv + all-reduce, 2 NVLink peer-memory mailboxes (peer.cuh);
+ * for mode 2 the device time rank-local thread 0 has spent waiting for [0] neighbours' halo records and [1] the other
+ * ranks' partial sums since comm_init (ms), and the number of such waits — the synchronisation cost of the decomposition */
+int rheo_gpu_comm_stats(RheoGpu* h, int32_t* mode, double* wait_ms2, int64_t* waits2);
 /* bytes copied host->device / device->host by the upload/download/correct entry points of this handle so far */
 int rheo_gpu_transfer_bytes(const RheoGpu* h, int64_t* h2d, int64_t* d2h);
 /* per-phase device times of the last step measured with CUDA events when enabled (ms):

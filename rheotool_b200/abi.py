@@ -108,6 +108,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_launch_count": (C.c_int64, [_P]),
     "rheo_gpu_last_iterations": (C.c_int, [_P]),
     "rheo_gpu_transfer_bytes": (C.c_int, [_P, _P, _P]),
+    "rheo_gpu_comm_stats": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_set_phase_timing": (C.c_int, [_P, _I]),
     "rheo_gpu_get_phase_times": (C.c_int, [_P, _P]),
     "rheo_gpu_set_kernel_timing": (C.c_int, [_P, _I]),

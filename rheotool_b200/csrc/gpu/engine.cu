@@ -21,6 +21,7 @@
 
 #include "krylov.cuh"
 #include "assembly.cuh"
+#include "peer.cuh"
 #include "rheo_gpu.h"
 
 using namespace rk;
@@ -66,7 +67,7 @@ struct Nccl {
         return true;
     }
 } g_nccl;
-constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;
+constexpr int NCCL_FLOAT64 = 8, NCCL_UINT8 = 1, NCCL_SUM = 0;
 
 struct DevBuf {
     void* p = nullptr;
@@ -134,6 +135,12 @@ struct RheoGpu {
     // comm
     void* comm = nullptr;
     int rank = 0, nRanks = 1;
+    // NVLink peer-memory path (peer.cuh); NCCL is the bootstrap and the fallback
+    bool p2p = false;
+    PeerView pv{};
+    DevBuf d_mailbox, d_peerSegs, d_segOfGhost, d_peerMisc;
+    void* peerBase[MAX_RANKS] = {};
+    unsigned long long haloSeq = 0, arSeq = 0;
     // stats
     long launches = 0;
     long long h2dBytes = 0, d2hBytes = 0;   // host<->device bytes copied by the upload/download entry points
@@ -514,36 +521,20 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
     return 0;
 }
 
-// ---------------------------------------------------------------- halo exchange of a set of planes
-int halo_exchange(RheoGpu* h, const PlaneList& pl) {
+// ---------------------------------------------------------------- halo exchange
+// records already laid out in d_send as [h][rec] (rec doubles per processor face, my ghost order) -> *recvOut points at the
+// records of my ghosts (same layout): the peer-memory mailbox (peer.cuh) or d_recv (NCCL send/recv group)
+int halo_sendrecv(RheoGpu* h, int rec, const double** recvOut) {
+    *recvOut = h->d_recv.as<double>();
     if (h->H == 0) return 0;
     if (!h->comm) return fail("mesh has processor patches but rheo_gpu_comm_init was not called");
-    LAUNCH(h, k_halo_pack, cdiv(h->H, BLOCK), BLOCK, h->H, pl, h->d_haloCell.as<int>(), h->d_segStart.as<int>(), h->d_segLen.as<int>(), h->d_send.as<double>());
-    g_nccl.GroupStart();
-    for (const HaloSeg& s : h->segs) {
-        const size_t off = (size_t)pl.n * s.h0, cnt = (size_t)pl.n * s.len;
-        int rc = g_nccl.Send(h->d_send.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
-        if (!rc) rc = g_nccl.Recv(h->d_recv.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
-        if (rc) { g_nccl.GroupEnd(); return fail(std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(rc)); }
+    if (h->p2p) {
+        const unsigned long long seq = ++h->haloSeq;
+        const int grid = std::max(1, std::min(cdiv((long)h->H * rec, BLOCK), h->nSms));
+        LAUNCH(h, k_peer_halo, grid, BLOCK, h->pv, rec, seq, h->d_send.as<double>());
+        *recvOut = h->pv.haloData + (seq & 1ull) * h->pv.haloCap;
+        return 0;
     }
-    int rc = g_nccl.GroupEnd();
-    if (rc) return fail(std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc));
-    LAUNCH(h, k_halo_unpack, cdiv(h->H, BLOCK), BLOCK, h->H, h->N, pl, h->d_segStart.as<int>(), h->d_segLen.as<int>(), h->d_recv.as<double>());
-    return 0;
-}
-int halo_planes(RheoGpu* h, double* base, int nPlanes) {
-    for (int p0 = 0; p0 < nPlanes; p0 += MAX_RHS) {
-        PlaneList pl;
-        pl.n = std::min(MAX_RHS, nPlanes - p0);
-        for (int p = 0; p < pl.n; ++p) pl.p[p] = base + (size_t)(p0 + p) * h->NP;
-        if (halo_exchange(h, pl)) return 1;
-    }
-    return 0;
-}
-// exchange records already laid out in d_send as [h][rec] (rec doubles per processor face) -> d_recv
-int halo_sendrecv(RheoGpu* h, int rec) {
-    if (h->H == 0) return 0;
-    if (!h->comm) return fail("mesh has processor patches but rheo_gpu_comm_init was not called");
     g_nccl.GroupStart();
     for (const HaloSeg& s : h->segs) {
         const size_t off = (size_t)rec * s.h0, cnt = (size_t)rec * s.len;
@@ -555,10 +546,140 @@ int halo_sendrecv(RheoGpu* h, int rec) {
     if (rc) return fail(std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc));
     return 0;
 }
-int all_reduce(RheoGpu* h, double* buf, int n) {
+// halo exchange of a set of planes (pack: buf[h * n + p])
+int halo_exchange(RheoGpu* h, const PlaneList& pl) {
+    if (h->H == 0) return 0;
+    if (h->p2p) {   // pack + swap + unpack in one kernel over peer memory
+        const int grid = std::max(1, std::min(cdiv(h->H, BLOCK), h->nSms));
+        LAUNCH(h, k_peer_halo_planes, grid, BLOCK, h->pv, ++h->haloSeq, h->N, pl, h->d_haloCell.as<int>());
+        return 0;
+    }
+    LAUNCH(h, k_halo_pack, cdiv(h->H, BLOCK), BLOCK, h->H, pl, h->d_haloCell.as<int>(), h->d_send.as<double>());
+    const double* recv;
+    if (halo_sendrecv(h, pl.n, &recv)) return 1;
+    LAUNCH(h, k_halo_unpack, cdiv(h->H, BLOCK), BLOCK, h->H, h->N, pl, recv);
+    return 0;
+}
+int halo_planes(RheoGpu* h, double* base, int nPlanes) {
+    for (int p0 = 0; p0 < nPlanes; p0 += MAX_RHS) {
+        PlaneList pl;
+        pl.n = std::min(MAX_RHS, nPlanes - p0);
+        for (int p = 0; p < pl.n; ++p) pl.p[p] = base + (size_t)(p0 + p) * h->NP;
+        if (halo_exchange(h, pl)) return 1;
+    }
+    return 0;
+}
+// sum over the ranks of buf[0..n), then the scalar control step `what` (CTL_NONE: none).  One kernel on the peer-memory
+// path; ncclAllReduce + k_ctl otherwise.  Single rank: only the control step (when the producing kernel did not run it).
+int all_reduce_ctl(RheoGpu* h, double* buf, int n, int what, int nrhs, const SolveCtl& sc) {
+    KrylovShared* ks = h->d_ks.as<KrylovShared>();
     if (h->nRanks <= 1) return 0;
+    if (h->p2p) {
+        LAUNCH(h, k_peer_allreduce_ctl, 1, 128, h->pv, buf, n, ++h->arSeq, what, ks, nrhs, sc);
+        return 0;
+    }
     int rc = g_nccl.AllReduce(buf, buf, (size_t)n, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
     if (rc) return fail(std::string("ncclAllReduce: ") + g_nccl.GetErrorString(rc));
+    if (what != CTL_NONE) LAUNCH(h, k_ctl, 1, 32, what, ks, nrhs, buf, sc);
+    return 0;
+}
+int all_reduce(RheoGpu* h, double* buf, int n) { return all_reduce_ctl(h, buf, n, CTL_NONE, 0, SolveCtl{}); }
+
+// ---------------------------------------------------------------- peer-memory set-up (collective; called by rheo_gpu_comm_init)
+struct PeerRec {   // what every rank publishes
+    cudaIpcMemHandle_t handle;
+    int ok, H;
+    int h0For[MAX_RANKS];   // first ghost of my segment facing rank j, -1 if none
+};
+int setup_peer(RheoGpu* h) {
+    const int R = h->nRanks, me = h->rank;
+    const char* env = getenv("RHEO_P2P");
+    const bool wanted = !(env && env[0] == '0') && R > 1 && R <= MAX_RANKS;
+    // mailbox: flags | all-reduce slots | halo slots (2 parities each)
+    const size_t flagBytes = (size_t)2 * R * sizeof(unsigned long long);
+    const size_t offArFlag = 256 * ((flagBytes + 255) / 256), offArData = 2 * offArFlag;
+    const size_t arBytes = (size_t)2 * R * AR_MAX * sizeof(double);
+    const size_t offHalo = offArData + 256 * ((arBytes + 255) / 256);
+    const long haloCap = (long)std::max(h->H, 1) * MAX_RHS;
+    const size_t total = offHalo + (size_t)2 * haloCap * sizeof(double);
+    PeerRec mine{};
+    mine.ok = 0; mine.H = h->H;
+    for (int j = 0; j < MAX_RANKS; ++j) mine.h0For[j] = -1;
+    if (wanted) {
+        bool dup = false;
+        for (const HaloSeg& sg : h->segs) {
+            if (sg.nbrRank < 0 || sg.nbrRank >= R || mine.h0For[sg.nbrRank] >= 0) dup = true;   // two patches towards the same rank: keep NCCL
+            else mine.h0For[sg.nbrRank] = sg.h0;
+        }
+        if (!dup && h->d_mailbox.alloc(total) == 0 && cudaMemsetAsync(h->d_mailbox.p, 0, total, h->stream) == cudaSuccess &&
+            cudaIpcGetMemHandle(&mine.handle, h->d_mailbox.p) == cudaSuccess)
+            mine.ok = 1;
+        cudaGetLastError();
+    }
+    // gather the records: sum of byte arrays in which only the owner's slot is non-zero
+    std::vector<PeerRec> all(R);
+    DevBuf g;
+    if (g.alloc(sizeof(PeerRec) * R)) return 1;
+    CK(cudaMemsetAsync(g.p, 0, g.bytes, h->stream));
+    CK(cudaMemcpyAsync((char*)g.p + sizeof(PeerRec) * me, &mine, sizeof(PeerRec), cudaMemcpyHostToDevice, h->stream));
+    int rc = g_nccl.AllReduce(g.p, g.p, g.bytes, NCCL_UINT8, NCCL_SUM, h->comm, h->stream);
+    if (rc) return fail(std::string("ncclAllReduce (peer records): ") + g_nccl.GetErrorString(rc));
+    CK(cudaMemcpyAsync(all.data(), g.p, g.bytes, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    g.release();
+    bool ok = wanted;
+    for (int r = 0; r < R; ++r) ok = ok && all[r].ok;
+    // map the peers
+    double opened = 0.0;
+    if (ok) {
+        opened = 1.0;
+        for (int r = 0; r < R && opened > 0; ++r) {
+            if (r == me) { h->peerBase[r] = h->d_mailbox.p; continue; }
+            if (cudaIpcOpenMemHandle(&h->peerBase[r], all[r].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); h->peerBase[r] = nullptr; opened = 0.0; }
+        }
+    }
+    // consensus: every rank must have mapped every peer
+    double* tmp = h->d_red.as<double>();
+    CK(cudaMemcpyAsync(tmp, &opened, sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    rc = g_nccl.AllReduce(tmp, tmp, 1, NCCL_FLOAT64, NCCL_SUM, h->comm, h->stream);
+    if (rc) return fail(std::string("ncclAllReduce (peer consensus): ") + g_nccl.GetErrorString(rc));
+    double sum = 0;
+    CK(cudaMemcpyAsync(&sum, tmp, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    if (!(sum > R - 0.5)) {
+        for (int r = 0; r < R; ++r) if (r != me && h->peerBase[r]) { cudaIpcCloseMemHandle(h->peerBase[r]); h->peerBase[r] = nullptr; }
+        h->p2p = false;
+        return 0;
+    }
+    // device-side tables
+    std::vector<PeerSeg> ps;
+    std::vector<int> segOf(std::max(h->H, 1), 0);
+    for (size_t q = 0; q < h->segs.size(); ++q) {
+        const HaloSeg& sg = h->segs[q];
+        const int nbrH0 = all[sg.nbrRank].h0For[me];
+        if (nbrH0 < 0) return fail("rheo_gpu_comm_init: processor patch without a matching patch on the neighbour rank");
+        ps.push_back({sg.nbrRank, sg.h0, sg.len, nbrH0});
+        for (int i = 0; i < sg.len; ++i) segOf[sg.h0 + i] = (int)q;
+    }
+    if (ps.empty()) ps.push_back({me, 0, 0, 0});
+    if (upload(h->d_peerSegs, ps) || upload(h->d_segOfGhost, segOf) || h->d_peerMisc.alloc(256)) return 1;
+    CK(cudaMemsetAsync(h->d_peerMisc.p, 0, 256, h->stream));
+    PeerView& pv = h->pv;
+    pv.rank = me; pv.nRanks = R; pv.nSegs = (int)h->segs.size(); pv.H = h->H;
+    auto view = [&](void* base, unsigned long long** hf, unsigned long long** af, double** ad, double** hd) {
+        char* b = (char*)base;
+        *hf = (unsigned long long*)b; *af = (unsigned long long*)(b + offArFlag); *ad = (double*)(b + offArData); *hd = (double*)(b + offHalo);
+    };
+    view(h->d_mailbox.p, &pv.haloFlag, &pv.arFlag, &pv.arData, &pv.haloData);
+    pv.haloCap = haloCap;
+    for (int r = 0; r < R; ++r) {
+        view(h->peerBase[r], &pv.pHaloFlag[r], &pv.pArFlag[r], &pv.pArData[r], &pv.pHaloData[r]);
+        pv.pHaloCap[r] = (long)std::max(all[r].H, 1) * MAX_RHS;
+    }
+    pv.segs = h->d_peerSegs.as<PeerSeg>(); pv.segOfGhost = h->d_segOfGhost.as<int>();
+    pv.blockCounter = h->d_peerMisc.as<unsigned>(); pv.err = (int*)((char*)h->d_peerMisc.p + 128); pv.stat = (unsigned long long*)((char*)h->d_peerMisc.p + 192);
+    CK(cudaStreamSynchronize(h->stream));
+    h->p2p = true;
     return 0;
 }
 
@@ -664,10 +785,11 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 LAUNCH(h, k_cell_source2, std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms), SRC_BLOCK, h->mv, sa);
             }
             if (h->H && hrs) {
-                if (halo_sendrecv(h, stride)) return 1;
+                const double* recv;
+                if (halo_sendrecv(h, stride, &recv)) return 1;
                 for (int mi = g0; mi < g1; ++mi)
                     if (h->nBcells) LAUNCH(h, k_ghost_corr, cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), cl, h->d_Fs.as<double>(),
-                                           h->d_recv.as<double>(), stride, (mi - g0) * h->nComp, h->modes[mi].bsrc.as<double>());
+                                           recv, stride, (mi - g0) * h->nComp, h->modes[mi].bsrc.as<double>());
             }
         }
         if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
@@ -801,10 +923,11 @@ void rheo_gpu_destroy(RheoGpu* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    for (int r = 0; r < MAX_RANKS; ++r) if (r != h->rank && h->peerBase[r]) cudaIpcCloseMemHandle(h->peerBase[r]);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
-                      &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi,
+                      &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
@@ -842,7 +965,7 @@ int rheo_gpu_comm_init(RheoGpu* h, int32_t rank, int32_t n_ranks, const void* id
     CK(cudaMemcpyAsync(&n, tmp, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->nGlobalCells = (long)(n + 0.5);
-    return 0;
+    return setup_peer(h);
 }
 
 int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const double* tau, const double* eigvals, const double* eigvecs,
@@ -958,6 +1081,19 @@ int rheo_gpu_get_ell(RheoGpu* h, int32_t* K, int32_t* nbr, int32_t* face) {
 
 int64_t rheo_gpu_launch_count(const RheoGpu* h) { return h ? h->launches : 0; }
 int rheo_gpu_last_iterations(const RheoGpu* h) { return h ? h->lastIters : -1; }
+int rheo_gpu_comm_stats(RheoGpu* h, int32_t* mode, double* wait_ms2, int64_t* waits2) {
+    if (!h) return 1;
+    if (mode) *mode = h->nRanks <= 1 ? 0 : (h->p2p ? 2 : 1);
+    unsigned long long st[4] = {0, 0, 0, 0};
+    if (h->p2p) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(st, h->pv.stat, sizeof st, cudaMemcpyDeviceToHost));
+    }
+    if (wait_ms2) { wait_ms2[0] = st[0] * 1e-6; wait_ms2[1] = st[1] * 1e-6; }
+    if (waits2) { waits2[0] = (int64_t)st[2]; waits2[1] = (int64_t)st[3]; }
+    return 0;
+}
 int rheo_gpu_transfer_bytes(const RheoGpu* h, int64_t* h2d, int64_t* d2h) {
     if (!h) return 1;
     if (h2d) *h2d = h->h2dBytes;

@@ -141,19 +141,18 @@ __global__ void k_copy(size_t n, const double* __restrict__ s, double* __restric
 }
 
 // ---------------------------------------------------------------- halo pack / unpack
-// segment layout: for neighbour j with ghosts [h0,h1): buf[np*h0 + p*(h1-h0) + (h-h0)]
+// record layout: buf[h * n + p] for ghost h and plane p (a neighbour's segment is a contiguous range of h)
 struct PlaneList { int n; double* p[MAX_RHS]; };
-__global__ void k_halo_pack(int H, PlaneList pl, const int* __restrict__ haloCell, const int* __restrict__ segStart, const int* __restrict__ segLen, double* __restrict__ buf) {
+__global__ void k_halo_pack(int H, PlaneList pl, const int* __restrict__ haloCell, double* __restrict__ buf) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
-    const int c = haloCell[h], h0 = segStart[h], len = segLen[h];
-    for (int p = 0; p < pl.n; ++p) buf[(size_t)pl.n * h0 + (size_t)p * len + (h - h0)] = pl.p[p][c];
+    const int c = haloCell[h];
+    for (int p = 0; p < pl.n; ++p) buf[(size_t)h * pl.n + p] = pl.p[p][c];
 }
-__global__ void k_halo_unpack(int H, int N, PlaneList pl, const int* __restrict__ segStart, const int* __restrict__ segLen, const double* __restrict__ buf) {
+__global__ void k_halo_unpack(int H, int N, PlaneList pl, const double* __restrict__ buf) {
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
-    const int h0 = segStart[h], len = segLen[h];
-    for (int p = 0; p < pl.n; ++p) pl.p[p][N + h] = buf[(size_t)pl.n * h0 + (size_t)p * len + (h - h0)];
+    for (int p = 0; p < pl.n; ++p) pl.p[p][N + h] = buf[(size_t)h * pl.n + p];
 }
 
 // ---------------------------------------------------------------- boundary values

@@ -30,19 +30,10 @@ __global__ void k_halo_unpack_il(int H, int N, int NP, int nModes, const double*
 template <int NR>
 int halo_interleaved(RheoGpu* h, int nModes, double* x) {
     if (h->H == 0) return 0;
-    if (!h->comm) return fail("mesh has processor patches but rheo_gpu_comm_init was not called");
-    const int rec = nModes * NR;
     LAUNCH(h, (k_halo_pack_il<NR>), cdiv(h->H, BLOCK), BLOCK, h->H, h->NP, nModes, h->d_haloCell.as<int>(), x, h->d_send.as<double>());
-    g_nccl.GroupStart();
-    for (const HaloSeg& s : h->segs) {
-        const size_t off = (size_t)rec * s.h0, cnt = (size_t)rec * s.len;
-        int rc = g_nccl.Send(h->d_send.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
-        if (!rc) rc = g_nccl.Recv(h->d_recv.as<double>() + off, cnt, NCCL_FLOAT64, s.nbrRank, h->comm, h->stream);
-        if (rc) { g_nccl.GroupEnd(); return fail(std::string("ncclSend/Recv: ") + g_nccl.GetErrorString(rc)); }
-    }
-    int rc = g_nccl.GroupEnd();
-    if (rc) return fail(std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(rc));
-    LAUNCH(h, (k_halo_unpack_il<NR>), cdiv(h->H, BLOCK), BLOCK, h->H, h->N, h->NP, nModes, h->d_recv.as<double>(), x);
+    const double* recv;
+    if (halo_sendrecv(h, nModes * NR, &recv)) return 1;
+    LAUNCH(h, (k_halo_unpack_il<NR>), cdiv(h->H, BLOCK), BLOCK, h->H, h->N, h->NP, nModes, recv, x);
     return 0;
 }
 
@@ -107,10 +98,8 @@ int precond_spmv(RheoGpu* h, int nModes, const SolveCtl& sc) {
         LAUNCH_SM(h, (k_sweep<NR, KT, 1, UPD>), grids[k], RT, smem, h->mv, rs, c0, c1, nModes, ks, x, u);
         base += grids[k];
     }
-    if (WHICH == 1 && multi) {
-        if (all_reduce(h, redHalf, nModes * NR)) return 1;
-        LAUNCH(h, k_ctl, 1, 32, CTL_HALF, ks, nModes * NR, redHalf, sc);
-    }
+    // (peer-memory path: the half-step sums are reduced together with the dots of this product, see k_peer_ghost_reduce)
+    if (WHICH == 1 && multi && !h->p2p && all_reduce_ctl(h, redHalf, nModes * NR, CTL_HALF, nModes * NR, sc)) return 1;
     // ---- backward substitution of the middle colours
     for (int k = nc - 2; k >= 1; --k) {
         const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
@@ -129,12 +118,15 @@ int precond_spmv(RheoGpu* h, int nModes, const SolveCtl& sc) {
     } else {
         LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g0, RT, smem, h->mv, rs, 0, N, nModes, ks, x, w, other, part, redDots, counter, 0, g0, what, sc);
     }
-    if (multi) {
+    if (multi && h->p2p) {
+        const unsigned long long sh = ++h->haloSeq, sa = ++h->arSeq;
+        LAUNCH(h, (k_peer_ghost_reduce<NR, MODE>), 1, PEER_CTA, h->pv, sh, sa, h->mv, h->nBcells, h->d_bcells.as<int>(), h->d_haloCell.as<int>(), nModes, ks,
+               h->d_Fs.as<double>(), x, w, other, redDots, redHalf, sc);
+    } else if (multi) {
         const int nd = (MODE == 0 ? 1 : 2) * nModes * NR;
         if (halo_interleaved<NR>(h, nModes, x)) return 1;
         if (h->nBcells) LAUNCH(h, (k_ghost<NR, MODE>), cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, h->d_Fs.as<double>(), x, w, other, redDots);
-        if (all_reduce(h, redDots, nd)) return 1;
-        LAUNCH(h, k_ctl, 1, 32, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, ks, nModes * NR, redDots, sc);
+        if (all_reduce_ctl(h, redDots, nd, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, nModes * NR, sc)) return 1;
     }
     return 0;
 }
@@ -165,10 +157,7 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* i
     if (all_reduce(h, sumPsi, nrhs)) return 1;
     LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, r, r0, part, redB, counter,
            multi ? CTL_NONE : CTL_INIT, ks, sc);
-    if (multi) {
-        if (all_reduce(h, redB, 3 * nrhs)) return 1;
-        LAUNCH(h, k_ctl, 1, 32, CTL_INIT, ks, nrhs, redB, sc);
-    }
+    if (multi && all_reduce_ctl(h, redB, 3 * nrhs, CTL_INIT, nrhs, sc)) return 1;
     int launched = 0;
     int spec = std::max(1, h->specIters);
     for (;;) {
@@ -176,14 +165,12 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* i
             if (precond_spmv<NR, KT, 0>(h, nModes, sc)) return 1;
             if (precond_spmv<NR, KT, 1>(h, nModes, sc)) return 1;
             LAUNCH(h, (k_update_x_r<NR>), GRID(h, (k_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, y, z, sv, t, r0, r, part, redD, counter, multi ? CTL_NONE : CTL_END, sc);
-            if (multi) {
-                if (all_reduce(h, redD, 2 * nrhs)) return 1;
-                LAUNCH(h, k_ctl, 1, 32, CTL_END, ks, nrhs, redD, sc);
-            }
+            if (multi && all_reduce_ctl(h, redD, 2 * nrhs, CTL_END, nrhs, sc)) return 1;
             ++launched;
         }
         CK(cudaMemcpyAsync(h->h_ks, ks, sizeof(KrylovShared), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        if (h->h_ks->pad[0]) return fail("peer-memory wait expired: a neighbour rank did not reach the halo swap / reduction (peer.cuh)");
         if (h->h_ks->nActive == 0 || launched > h->ctl.max_iter + 2) break;
         spec = 1;
     }

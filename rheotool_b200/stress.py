@@ -127,6 +127,15 @@ class GpuStressModel:
     def launch_count(self) -> int:
         return int(abi.lib().rheo_gpu_launch_count(self._h))
 
+    def comm_stats(self) -> dict:
+        """Multi-GPU path in use and, on the peer-memory path, the time spent waiting for the other ranks."""
+        mode = C.c_int32(0)
+        wait = (C.c_double * 2)()
+        n = (C.c_int64 * 2)()
+        _check(abi.lib().rheo_gpu_comm_stats(self._h, C.byref(mode), wait, n))
+        return {"mode": {0: "single", 1: "nccl", 2: "nvlink-peer-memory"}[mode.value], "halo_wait_ms": wait[0], "reduce_wait_ms": wait[1],
+                "halo_waits": int(n[0]), "reduce_waits": int(n[1])}
+
     def transfer_bytes(self) -> tuple[int, int]:
         """(host->device, device->host) bytes copied by this handle so far."""
         a, b = C.c_int64(0), C.c_int64(0)
