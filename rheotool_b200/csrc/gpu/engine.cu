@@ -1084,7 +1084,7 @@ int rheo_gpu_last_iterations(const RheoGpu* h) { return h ? h->lastIters : -1; }
 int rheo_gpu_comm_stats(RheoGpu* h, int32_t* mode, double* wait_ms2, int64_t* waits2) {
     if (!h) return 1;
     if (mode) *mode = h->nRanks <= 1 ? 0 : (h->p2p ? 2 : 1);
-    unsigned long long st[4] = {0, 0, 0, 0};
+    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (h->p2p) {
         CK(cudaSetDevice(h->device));
         CK(cudaStreamSynchronize(h->stream));
@@ -1092,6 +1092,7 @@ int rheo_gpu_comm_stats(RheoGpu* h, int32_t* mode, double* wait_ms2, int64_t* wa
     }
     if (wait_ms2) { wait_ms2[0] = st[0] * 1e-6; wait_ms2[1] = st[1] * 1e-6; }
     if (waits2) { waits2[0] = (int64_t)st[2]; waits2[1] = (int64_t)st[3]; }
+    if (getenv("RHEO_PEER_TRACE")) fprintf(stderr, "peer halo_planes phases (ms total): store %.3f fence %.3f publish+wait %.3f unpack %.3f\n", st[4] * 1e-6, st[5] * 1e-6, st[6] * 1e-6, st[7] * 1e-6);
     return 0;
 }
 int rheo_gpu_transfer_bytes(const RheoGpu* h, int64_t* h2d, int64_t* d2h) {

@@ -130,74 +130,69 @@ __device__ __forceinline__ void row_gather(const RowView& rv, int K, int c, int 
     }
 }
 
-// ---- scalar control, shared by the epilogues (1 GPU) and k_ctl (after all-reduce)
-__device__ __forceinline__ void ctl_init(KrylovShared* ks, int nrhs, const double* red3, const SolveCtl& sc) {
-    int cnt = 0;
-    for (int q = 0; q < nrhs; ++q) {
-        KrylovCtl k;
-        k.normFactor = red3[3 * q] + 1e-20;
-        k.initRes = red3[3 * q + 1] / k.normFactor;
-        k.finRes = k.initRes;
-        k.rho = red3[3 * q + 2];
-        k.rhoOld = 0; k.alpha = 0; k.omega = 0; k.beta = 0; k.iters = 0; k.singular = 0; k.pad = 0;
-        k.state = (sc.minIter > 0 || !conv_check(k.finRes, k.initRes, sc)) ? 0 : 2;
-        if (k.state == 0 && !(fabs(k.rho) > 1e-300)) { k.state = 2; k.singular = 1; }
-        ks->ctl[q] = k;
-        cnt += (k.state == 0);
-    }
-    ks->nActive = cnt;
+// ---- scalar control, shared by the epilogues (1 GPU), k_ctl (after ncclAllReduce) and the peer-memory kernels.
+// One lane per right-hand side (the RHS are independent; MAX_RHS <= 32): ctl_dispatch is called by ALL 32 lanes of one warp.
+__device__ __forceinline__ void ctl_init_one(KrylovCtl& k, const double* red3, const SolveCtl& sc) {
+    k.normFactor = red3[0] + 1e-20;
+    k.initRes = red3[1] / k.normFactor;
+    k.finRes = k.initRes;
+    k.rho = red3[2];
+    k.rhoOld = 0; k.alpha = 0; k.omega = 0; k.beta = 0; k.iters = 0; k.singular = 0; k.pad = 0;
+    k.state = (sc.minIter > 0 || !conv_check(k.finRes, k.initRes, sc)) ? 0 : 2;
+    if (k.state == 0 && !(fabs(k.rho) > 1e-300)) { k.state = 2; k.singular = 1; }
 }
 // after r0.v : alpha
-__device__ __forceinline__ void ctl_alpha(KrylovShared* ks, int nrhs, const double* dotsV) {
-    for (int q = 0; q < nrhs; ++q)
-        if (ks->ctl[q].state == 0) ks->ctl[q].alpha = ks->ctl[q].rho / dotsV[q];
+__device__ __forceinline__ void ctl_alpha_one(KrylovCtl& k, double dotV) {
+    if (k.state == 0) k.alpha = k.rho / dotV;
 }
 // after sum|s| : half-step convergence
-__device__ __forceinline__ void ctl_half(KrylovShared* ks, int nrhs, const double* sumS, const SolveCtl& sc) {
-    for (int q = 0; q < nrhs; ++q) {
-        KrylovCtl& k = ks->ctl[q];
-        if (k.state != 0) continue;
-        k.finRes = sumS[q] / k.normFactor;
-        if (conv_check(k.finRes, k.initRes, sc)) k.state = 1;
-    }
+__device__ __forceinline__ void ctl_half_one(KrylovCtl& k, double sumS, const SolveCtl& sc) {
+    if (k.state != 0) return;
+    k.finRes = sumS / k.normFactor;
+    if (conv_check(k.finRes, k.initRes, sc)) k.state = 1;
 }
 // after t.t, t.s : omega
-__device__ __forceinline__ void ctl_omega(KrylovShared* ks, int nrhs, const double* dots2) {
-    for (int q = 0; q < nrhs; ++q)
-        if (ks->ctl[q].state == 0) ks->ctl[q].omega = dots2[2 * q + 1] / dots2[2 * q];
+__device__ __forceinline__ void ctl_omega_one(KrylovCtl& k, double tt, double ts) {
+    if (k.state == 0) k.omega = ts / tt;
 }
 // end of iteration
-__device__ __forceinline__ void ctl_end(KrylovShared* ks, int nrhs, const double* red2, const SolveCtl& sc) {
-    int cnt = 0;
-    for (int q = 0; q < nrhs; ++q) {
-        KrylovCtl& k = ks->ctl[q];
-        if (k.state == 1) { k.iters++; k.state = 2; }
-        else if (k.state == 0) {
-            k.finRes = red2[2 * q] / k.normFactor;
-            k.rhoOld = k.rho;
-            k.rho = red2[2 * q + 1];
-            const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
-            if (!cont) k.state = 2;
-            else if (!(fabs(k.rho) > 1e-300) || !(fabs(k.omega) > 1e-300)) { k.state = 2; k.singular = 1; }
-            else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);
-        }
-        cnt += (k.state == 0);
+__device__ __forceinline__ void ctl_end_one(KrylovCtl& k, double sumR, double r0r, const SolveCtl& sc) {
+    if (k.state == 1) { k.iters++; k.state = 2; }
+    else if (k.state == 0) {
+        k.finRes = sumR / k.normFactor;
+        k.rhoOld = k.rho;
+        k.rho = r0r;
+        const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
+        if (!cont) k.state = 2;
+        else if (!(fabs(k.rho) > 1e-300) || !(fabs(k.omega) > 1e-300)) { k.state = 2; k.singular = 1; }
+        else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);
     }
-    ks->nActive = cnt;
 }
-enum { CTL_NONE = 0, CTL_INIT = 1, CTL_ALPHA = 2, CTL_HALF = 3, CTL_OMEGA = 4, CTL_END = 5 };
-__device__ __forceinline__ void ctl_dispatch(int what, KrylovShared* ks, int nrhs, const double* red, const SolveCtl& sc) {
-    switch (what) {
-        case CTL_INIT: ctl_init(ks, nrhs, red, sc); break;
-        case CTL_ALPHA: ctl_alpha(ks, nrhs, red); break;
-        case CTL_HALF: ctl_half(ks, nrhs, red, sc); break;
-        case CTL_OMEGA: ctl_omega(ks, nrhs, red); break;
-        case CTL_END: ctl_end(ks, nrhs, red, sc); break;
-        default: break;
+enum { CTL_NONE = 0, CTL_INIT = 1, CTL_ALPHA = 2, CTL_HALF = 3, CTL_OMEGA = 4, CTL_END = 5, CTL_HALF_OMEGA = 6 };
+// CTL_HALF_OMEGA: red = [t.t, t.s per RHS (2 nrhs) | sum|s| per RHS (nrhs)] — the half-step check deferred to the end of the
+// second preconditioned product (peer-memory path)
+__device__ __noinline__ void ctl_dispatch(int what, KrylovShared* ks, int nrhs, const double* red, const SolveCtl& sc) {
+    const int q = threadIdx.x & 31;
+    bool active = false;
+    if (q < nrhs && what != CTL_NONE) {
+        KrylovCtl k = ks->ctl[q];
+        switch (what) {
+            case CTL_INIT: ctl_init_one(k, red + 3 * q, sc); break;
+            case CTL_ALPHA: ctl_alpha_one(k, red[q]); break;
+            case CTL_HALF: ctl_half_one(k, red[q], sc); break;
+            case CTL_OMEGA: ctl_omega_one(k, red[2 * q], red[2 * q + 1]); break;
+            case CTL_HALF_OMEGA: ctl_half_one(k, red[2 * nrhs + q], sc); ctl_omega_one(k, red[2 * q], red[2 * q + 1]); break;
+            case CTL_END: ctl_end_one(k, red[2 * q], red[2 * q + 1], sc); break;
+            default: break;
+        }
+        ks->ctl[q] = k;
+        active = k.state == 0;
     }
+    const unsigned m = __ballot_sync(0xffffffffu, active);
+    if (q == 0 && (what == CTL_INIT || what == CTL_END)) ks->nActive = __popc(m);
 }
 __global__ void k_ctl(int what, KrylovShared* ks, int nrhs, const double* red, SolveCtl sc) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) ctl_dispatch(what, ks, nrhs, red, sc);
+    if (blockIdx.x == 0 && threadIdx.x < 32) ctl_dispatch(what, ks, nrhs, red, sc);
 }
 
 // Reduction epilogue: the last block (of `expected` participating blocks, possibly spread over several
@@ -224,10 +219,10 @@ __device__ __forceinline__ void finalize_ctl(const double* partials, int nBlocks
         if (lane == 0) out[s] = x;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        *counter = 0;
+    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x < 32 && what != CTL_NONE) {   // `what` is uniform: the whole first warp takes part (one lane per RHS)
         __threadfence();
-        if (what != CTL_NONE) ctl_dispatch(what, ks, nrhs, out, sc);
+        ctl_dispatch(what, ks, nrhs, out, sc);
     }
 }
 
@@ -587,7 +582,7 @@ __global__ void __launch_bounds__(BLOCK) k_make_s(int c0, int c1, int NP, int nM
 
 // ---------------------------------------------------------------- psi += alpha y + omega z ; r = s - omega t ; sum|r| , r0.r
 template <int NR>
-__global__ void __launch_bounds__(BLOCK) k_update_x_r(int N, int NP, int nModes, RhsPtrs rp, KrylovShared* ks, const double* __restrict__ y,
+__global__ void __launch_bounds__(BLOCK, 2) k_update_x_r(int N, int NP, int nModes, RhsPtrs rp, KrylovShared* ks, const double* __restrict__ y,
                                                        const double* __restrict__ z, const double* __restrict__ sv, const double* __restrict__ t,
                                                        const double* __restrict__ r0v, double* __restrict__ r, double* partials, double* out,
                                                        unsigned* counter, int ctlWhat, SolveCtl sc) {

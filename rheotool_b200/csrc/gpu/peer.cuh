@@ -119,10 +119,8 @@ __global__ void __launch_bounds__(128) k_peer_allreduce_ctl(PeerView pv, double*
         buf[q] = s;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        if (*pv.err) ks->pad[0] = 1;
-        if (what != CTL_NONE) ctl_dispatch(what, ks, nrhs, buf, sc);
-    }
+    if (threadIdx.x == 0 && *pv.err) ks->pad[0] = 1;
+    if (threadIdx.x < 32) ctl_dispatch(what, ks, nrhs, buf, sc);
 }
 
 
@@ -233,16 +231,12 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
     for (int q = threadIdx.x; q < nd; q += PEER_CTA) {
         double t = 0.0;
         for (int r = 0; r < R; ++r) t += __ldcg(&pv.arData[((long)parA * R + r) * AR_MAX + q]);
-        if (q < ndDots) dots[q] = t;
-        else sCorr[q - ndDots] = t;   // reduced half-step sums
+        dots[q] = t;   // MODE 1: [t.t, t.s per RHS | reduced half-step sums]  (dots has room for 3 nrhs values)
     }
     __syncthreads();
-    // ---- 4. control
-    if (threadIdx.x == 0) {
-        if (*pv.err) ks->pad[0] = 1;
-        if (MODE == 0) ctl_alpha(ks, nrhs, dots);
-        else { ctl_half(ks, nrhs, sCorr, sc); ctl_omega(ks, nrhs, dots); }
-    }
+    // ---- 4. control (one lane per RHS)
+    if (threadIdx.x == 0 && *pv.err) ks->pad[0] = 1;
+    if (threadIdx.x < 32) ctl_dispatch(MODE == 0 ? CTL_ALPHA : CTL_HALF_OMEGA, ks, nrhs, dots, sc);
 }
 
 // ---------------------------------------------------------------- fused: pack planes + halo swap + unpack into the ghost cells
@@ -251,14 +245,17 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
 __global__ void __launch_bounds__(BLOCK) k_peer_halo_planes(PeerView pv, unsigned long long seq, int N, PlaneList pl, const int* __restrict__ haloCell) {
     __shared__ bool isLast;
     const int par = (int)(seq & 1ull), rec = pl.n;
+    const unsigned long long tA = global_ns();
     for (int hh = blockIdx.x * BLOCK + threadIdx.x; hh < pv.H; hh += gridDim.x * BLOCK) {
         const PeerSeg sg = pv.segs[pv.segOfGhost[hh]];
         double* dst = pv.pHaloData[sg.nbrRank] + (long)par * pv.pHaloCap[sg.nbrRank] + (long)(sg.nbrH0 + (hh - sg.h0)) * rec;
         const int c = haloCell[hh];
         for (int p = 0; p < rec; ++p) dst[p] = pl.p[p][c];
     }
+    const unsigned long long tB = global_ns();
     __threadfence_system();
     __syncthreads();
+    const unsigned long long tC = global_ns();
     if (threadIdx.x == 0) isLast = atomicAdd(pv.blockCounter, 1u) == gridDim.x - 1;
     __syncthreads();
     if (isLast) {
@@ -268,9 +265,13 @@ __global__ void __launch_bounds__(BLOCK) k_peer_halo_planes(PeerView pv, unsigne
     }
     if (threadIdx.x < pv.nSegs) peer_wait(&pv.haloFlag[par * pv.nRanks + pv.segs[threadIdx.x].nbrRank], seq, pv, 0);
     __syncthreads();
+    const unsigned long long tD = global_ns();
     const double* box = pv.haloData + (long)par * pv.haloCap;
     for (int hh = blockIdx.x * BLOCK + threadIdx.x; hh < pv.H; hh += gridDim.x * BLOCK)
         for (int p = 0; p < rec; ++p) pl.p[p][N + hh] = __ldcg(box + (long)hh * rec + p);
+    if (threadIdx.x == 0 && blockIdx.x == 0) {   // phase timeline of this kernel (statistics)
+        pv.stat[4] += tB - tA; pv.stat[5] += tC - tB; pv.stat[6] += tD - tC; pv.stat[7] += global_ns() - tD;
+    }
 }
 
 }  // namespace rk
