@@ -62,7 +62,7 @@ __host__ __device__ constexpr size_t tile_flux_bytes(int K) { return (size_t)K *
 // KT = compile-time slot count (neighbour values stay in registers between the gradient and the face pass); KT = 0:
 // run-time K, the face pass re-reads the neighbour value (L1 hit).
 template <int KT>
-__global__ void __launch_bounds__(TILE * 9, 3) k_flux_assemble(MeshView m, FluxArgs a, const unsigned char* __restrict__ tileRec, int nTiles) {
+__global__ void __launch_bounds__(TILE * 9, 4) k_flux_assemble(MeshView m, FluxArgs a, const unsigned char* __restrict__ tileRec, int nTiles) {
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int K = KT > 0 ? KT : m.K;
     const int KTL = K * TILE;

@@ -738,9 +738,15 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
 
     // ---- halo of U (grad U) and of theta (deferred correction / SpMV of the first residual)
-    if (h->H) {
-        if (halo_planes(h, h->d_U.as<double>(), 3)) return 1;
-        for (ModeDev& md : h->modes) if (halo_planes(h, md.theta.as<double>(), 6)) return 1;
+    if (h->H) {   // one swap for the 3 planes of U and the 6 planes of theta of as many modes as fit one record
+        PlaneList pl;
+        pl.n = 0;
+        for (int p = 0; p < 3; ++p) pl.p[pl.n++] = h->d_U.as<double>() + (size_t)p * NP;
+        for (ModeDev& md : h->modes) {
+            if (pl.n + 6 > MAX_RHS) { if (halo_exchange(h, pl)) return 1; pl.n = 0; }
+            for (int p = 0; p < 6; ++p) pl.p[pl.n++] = md.theta.as<double>() + (size_t)p * NP;
+        }
+        if (pl.n && halo_exchange(h, pl)) return 1;
     }
     if (h->timing) cudaEventRecord(h->ev[1], h->stream);
     // ---- assembly, mode by mode (the matrix is shared: same phi, same dt)

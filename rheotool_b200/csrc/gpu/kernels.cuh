@@ -258,11 +258,21 @@ struct Limiter { int hrs; double a0, a1, a2, b0, b1, b2, bnd0, bnd1; };
 // component, in the face's owner(P) -> neighbour(N) frame.  upw in {0,1} makes the reference's blend
 //   (1-a-b)(vN - 2gPd) upw + (1-a-b)(vP + 2gNd)(1-upw) + ((a-1)upw + b(1-upw)) vP + (b upw + (a-1)(1-upw)) vN
 // a selection (x*1 = x, y*0 = 0 exactly), which is how it is evaluated here — no divergent branches.
+// The normalised variable phi~_C = 1 - r, r = (vN - vP) / (2 g.d + 1e-18), only SELECTS the (alpha, beta) row, so the FP64
+// division of the reference is replaced by sign-corrected comparisons of the numerator with multiples of the denominator:
+//   phi~ <= 0  <=>  r >= 1 ;   phi~ >= 1  <=>  r <= 0 ;   phi~ < b  <=>  r > 1 - b .
+// The selected row can differ from the reference's only when phi~ is within rounding of a breakpoint, where the limiters are
+// continuous (except the reference's superbee row at 0, see tests/test_gpu_parity.py); 0/0 keeps the reference's
+// "every comparison false" outcome.
 __device__ __forceinline__ double phif_defc(double vP, double vN, double gPd, double gNd, bool upw, const Limiter& lm) {
     const double gd_up = upw ? gPd : gNd;
-    const double phitc = 1.0 - ((vN - vP) / (2.0 * gd_up + 1e-18));
-    const bool out = (phitc <= 0.) || (phitc >= 1.);
-    const bool s0 = phitc < lm.bnd0, s1 = phitc < lm.bnd1;
+    const double den = 2.0 * gd_up + 1e-18;
+    const double num = vN - vP;
+    const bool neg = den < 0.0;
+    const double n = neg ? -num : num, d = fabs(den);
+    const bool nan = (d == 0.0) && (n == 0.0);
+    const bool out = !nan && ((n >= d) || (n <= 0.0));
+    const bool s0 = !nan && (n > (1.0 - lm.bnd0) * d), s1 = !nan && (n > (1.0 - lm.bnd1) * d);
     const double alpha = out ? 1.0 : (s0 ? lm.a0 : (s1 ? lm.a1 : lm.a2));
     const double beta = out ? 0.0 : (s0 ? lm.b0 : (s1 ? lm.b1 : lm.b2));
     const double oab = 1.0 - alpha - beta;

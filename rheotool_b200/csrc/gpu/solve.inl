@@ -146,12 +146,8 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* i
     const double* A = h->d_Fs.as<double>();
     const bool multi = h->nRanks > 1;
 
-    // psi halo, gAverage(psi), initial residual + normFactor
-    if (h->H) {
-        PlaneList pl; pl.n = nrhs;
-        for (int q = 0; q < nrhs; ++q) pl.p[q] = rp.psi[q];
-        if (halo_exchange(h, pl)) return 1;
-    }
+    // gAverage(psi), initial residual + normFactor.  (psi = theta: its processor-patch values were swapped at the start of
+    // the step and nothing has written theta since, so the ghost cells are current.)
     // gAverage(psi): the per-component sums were accumulated by k_cell_source2 while it had theta in registers
     double* sumPsi = h->d_sumPsi.as<double>() + (size_t)firstMode * NR;
     if (all_reduce(h, sumPsi, nrhs)) return 1;
