@@ -53,6 +53,19 @@ def peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
+def measured_traffic(config: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of this
+    config (profiles/r1_traffic.json), or None when the capture does not hold this kernel / configuration."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if not p.exists():
+        return None, None
+    t = json.loads(p.read_text())
+    k = t.get("configs", {}).get(config, {}).get(kernel.strip("()"))
+    if not k:
+        return None, None
+    return k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"], "profiles/r1_traffic.json (" + t.get("source", "") + ")"
+
+
 def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int):
     """(algorithmic bytes one launch moves per cell it processes, fraction of the mesh one launch processes).
     DESIGN.md §3; d=8, i=4, f = internal faces per cell (3 in 3-D, 2 in 2-D), K = 2f slots, c1 = solved components of one
@@ -277,8 +290,10 @@ def run_ours(args):
             bpc, frac_cells = kernel_bytes_per_cell(name, spec.dims, len(spec.models), len(cstart) - 1)
             cells_per_launch = m.n_cells * frac_cells
             achieved = (bpc * cells_per_launch / (tms / cnt * 1e-3) / 1e9) if bpc else None
+            traffic, traffic_src = measured_traffic(args.config, name)
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                    "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                    "algorithmic_bytes_per_launch": (bpc * cells_per_launch) if bpc else None, "peak_source": peak_src,
                     "kernel_share_of_step": tms / tot, "avg_launch_ms": tms / cnt,
                     "bytes_per_cell_launch": bpc,
                     "kernels_ms_per_step": {k: round(v[1] / 3, 4) for k, v in sorted(kt.items(), key=lambda kv: -kv[1][1])}}

@@ -217,3 +217,35 @@ def test_errors_are_reported_not_swallowed():
     g = s.gpu()
     with pytest.raises(RheoError):
         g.correct(-1.0)
+
+
+def test_host_buffer_call_matches_resident_call_and_skips_empty_patches():
+    """rheo_gpu_correct (host buffers: what the OpenFOAM shim calls) == upload + store_old_time + step + download; the
+    values a caller leaves on the faces of `empty` patches are never read (OpenFOAM's emptyFvPatchField has size 0), and
+    the bytes the library reports are the bytes it copied."""
+    spec = cases.by_name("C2", 1 / 9)   # 2-D: the front/back patches are `empty`
+    s = Setup(spec)
+    sc = tight(spec.schemes)
+    g1, g2 = s.gpu(sc), s.gpu(sc)
+    g1.store_old_time(); g1.correct(s.dt)
+    # poison everything that belongs to an empty patch
+    Ub, phi = s.Ub.copy(), s.phi.copy()
+    nint = s.mesh.n_internal
+    n_empty = 0
+    for p in s.mesh.patches:
+        if p.type == abi.PATCH_EMPTY:
+            Ub[p.start - nint:p.start - nint + p.size] = np.nan
+            phi[p.start:p.start + p.size] = np.nan
+            n_empty += p.size
+    assert n_empty > 0
+    U = np.ascontiguousarray(s.U)
+    tau = np.zeros((s.mesh.n_cells, 6))
+    h0, d0 = g2.transfer_bytes()
+    g2.correct_host(U.ctypes.data, Ub.ctypes.data, phi.ctypes.data, s.dt, True, tau.ctypes.data)
+    h1, d1 = g2.transfer_bytes()
+    assert np.array_equal(tau, g1.tau(0))
+    assert np.array_equal(g2.theta(), g1.theta())
+    n_faces = s.mesh.n_internal + s.mesh.n_boundary
+    assert h1 - h0 == 8 * (3 * s.mesh.n_cells + 3 * (s.mesh.n_boundary - n_empty) + (n_faces - n_empty))
+    assert d1 - d0 == 8 * 6 * s.mesh.n_cells
+    assert g2.comm_stats()["mode"] == "single"
