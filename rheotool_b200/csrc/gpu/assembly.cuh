@@ -63,6 +63,7 @@ __host__ __device__ constexpr size_t tile_flux_bytes(int K) { return (size_t)K *
 // run-time K, the face pass re-reads the neighbour value (L1 hit).
 template <int KT>
 __global__ void __launch_bounds__(TILE * 9, 4) k_flux_assemble(MeshView m, FluxArgs a, const unsigned char* __restrict__ tileRec, int nTiles) {
+    pdl_sync();
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int K = KT > 0 ? KT : m.K;
     const int KTL = K * TILE;
@@ -269,6 +270,7 @@ struct SourceArgs {
 
 constexpr int SRC_BLOCK = 128;
 __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, SourceArgs a) {
+    pdl_sync();
     double sum[6] = {0, 0, 0, 0, 0, 0};
     // persistent grid (one resident wave): the reduction epilogue is paid once per CTA, not once per 128 cells
     for (int c = blockIdx.x * SRC_BLOCK + threadIdx.x; c < m.N; c += gridDim.x * SRC_BLOCK) {
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, Sourc
 // zeroGradient patch value = internal value
 __global__ void k_bc_zero_gradient2(MeshView m, const double* __restrict__ theta, double* __restrict__ thetaB, const double* __restrict__ tau,
                                     double* __restrict__ tauB) {
+    pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= m.nB) return;
     if (m.bkind[b] == RHEO_PATCH_EMPTY) return;
@@ -349,6 +352,7 @@ __global__ void k_bc_zero_gradient2(MeshView m, const double* __restrict__ theta
 //   b[c] -= F * v  for inflow ghost slots;  recv layout: [(h * stride) + offset + comp]
 __global__ void k_ghost_corr(MeshView m, int nBcells, const int* __restrict__ bcells, CompList cl, const double* __restrict__ Fs,
                              const double* __restrict__ recv, int stride, int offset, double* __restrict__ bsrc) {
+    pdl_sync();
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
     if (i0 >= nBcells) return;
     const int c = bcells[i0];
@@ -364,6 +368,7 @@ __global__ void k_ghost_corr(MeshView m, int nBcells, const int* __restrict__ bc
 // phi in device face order -> signed outflow flux per (tile, slot, lane), the layout k_flux_assemble streams;
 // patch slots hold phi_b, unused slots 0
 __global__ void k_flux_ell(MeshView m, const double* __restrict__ phi, double* __restrict__ Fell) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= m.NS) return;
     const int tile = c / TILE, lane = c % TILE;

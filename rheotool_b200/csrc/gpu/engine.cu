@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <utility>
 #include <map>
 #include <cstring>
 #include <string>
@@ -29,6 +31,7 @@ using namespace rk;
 namespace {
 
 thread_local std::string g_err;
+const bool g_pdl = !(getenv("RHEO_PDL") && getenv("RHEO_PDL")[0] == '0');   // programmatic dependent launch (RHEO_PDL=0 disables)
 int fail(const std::string& m) { g_err = m; return 1; }
 
 #define CK(call)                                                                                     \
@@ -156,10 +159,22 @@ struct RheoGpu {
 
 namespace {
 
+// kernel launch with programmatic dependent launch enabled (kernels.cuh: pdl_sync)
+template <class... KArgs, class... Args>
+inline void launch_pdl(cudaStream_t stream, int grid, int block, size_t smem, void (*kern)(KArgs...), Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
 #define LAUNCH(h, kern, grid, block, ...)                                      \
     do {                                                                       \
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
-        kern<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);                \
+        launch_pdl((h)->stream, (grid), (block), 0, kern, __VA_ARGS__);       \
         (h)->launches++;                                                       \
         if ((h)->ktiming) {                                                    \
             cudaEventRecord((h)->kev1, (h)->stream);                           \
@@ -175,7 +190,7 @@ namespace {
 #define LAUNCH_SM(h, kern, grid, block, smem, ...)                             \
     do {                                                                       \
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
-        kern<<<(grid), (block), (smem), (h)->stream>>>(__VA_ARGS__);           \
+        launch_pdl((h)->stream, (grid), (block), (smem), kern, __VA_ARGS__);  \
         (h)->launches++;                                                       \
         if ((h)->ktiming) {                                                    \
             cudaEventRecord((h)->kev1, (h)->stream);                           \

@@ -15,6 +15,15 @@
 
 namespace rk {
 
+// Programmatic dependent launch (sm_90+): every kernel of this library is launched with the programmatic-stream-
+// serialization attribute and starts with this pair.  `wait` blocks until the previous kernel in the stream has completed
+// and its memory is visible (a no-op without the attribute); `launch_dependents` lets the NEXT kernel's CTAs become
+// resident as soon as every CTA of this one has started, so launch latency and ramp-up overlap this kernel's tail.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 constexpr int BLOCK = 256;
 constexpr int MAX_RHS = 24;
 constexpr int MAX_RED = 3 * MAX_RHS;
@@ -93,12 +102,14 @@ __device__ __forceinline__ void finalize_partials(const double* partials, int nS
 // ---------------------------------------------------------------- layout transforms (upload / download)
 // AoS in the caller's numbering -> SoA planes in device numbering
 __global__ void k_aos_to_soa(int n, int nc, const int* __restrict__ perm, const double* __restrict__ aos, double* __restrict__ soa, int stride) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int o = perm ? perm[c] : c;
     for (int k = 0; k < nc; ++k) soa[(size_t)k * stride + c] = aos[(size_t)o * nc + k];
 }
 __global__ void k_soa_to_aos(int n, int nc, const int* __restrict__ perm, const double* __restrict__ soa, double* __restrict__ aos, int stride) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int o = perm ? perm[c] : c;
@@ -106,18 +117,21 @@ __global__ void k_soa_to_aos(int n, int nc, const int* __restrict__ perm, const 
 }
 // eigVals tensor (9, diagonal used) <-> Lam[3]; accum != 0 adds instead of overwriting (sum over modes)
 __global__ void k_soa_to_aos_acc(int n, int nc, const int* __restrict__ perm, const double* __restrict__ soa, double* __restrict__ aos, int stride) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int o = perm ? perm[c] : c;
     for (int k = 0; k < nc; ++k) aos[(size_t)o * nc + k] += soa[(size_t)k * stride + c];
 }
 __global__ void k_lam_from_tensor(int n, const int* __restrict__ perm, const double* __restrict__ aos9, double* __restrict__ lam, int stride) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int o = perm[c];
     lam[c] = aos9[(size_t)o * 9]; lam[stride + c] = aos9[(size_t)o * 9 + 4]; lam[2 * (size_t)stride + c] = aos9[(size_t)o * 9 + 8];
 }
 __global__ void k_lam_to_tensor(int n, const int* __restrict__ perm, const double* __restrict__ lam, double* __restrict__ aos9, int stride) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     const int o = perm[c];
@@ -126,16 +140,19 @@ __global__ void k_lam_to_tensor(int n, const int* __restrict__ perm, const doubl
 }
 // phi: caller's face order -> device face order (flip sign where the renumbered owner changed)
 __global__ void k_phi_in(int nF, const int* __restrict__ faceOld, const double* __restrict__ src, double* __restrict__ dst) {
+    pdl_sync();
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= nF) return;
     const int o = faceOld[f];   // old face + 1, negative if flipped
     dst[f] = o > 0 ? src[o - 1] : -src[-o - 1];
 }
 __global__ void k_fill(size_t n, double* p, double v) {
+    pdl_sync();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
 __global__ void k_copy(size_t n, const double* __restrict__ s, double* __restrict__ d) {
+    pdl_sync();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = s[i];
 }
@@ -144,12 +161,14 @@ __global__ void k_copy(size_t n, const double* __restrict__ s, double* __restric
 // record layout: buf[h * n + p] for ghost h and plane p (a neighbour's segment is a contiguous range of h)
 struct PlaneList { int n; double* p[MAX_RHS]; };
 __global__ void k_halo_pack(int H, PlaneList pl, const int* __restrict__ haloCell, double* __restrict__ buf) {
+    pdl_sync();
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     const int c = haloCell[h];
     for (int p = 0; p < pl.n; ++p) buf[(size_t)h * pl.n + p] = pl.p[p][c];
 }
 __global__ void k_halo_unpack(int H, int N, PlaneList pl, const double* __restrict__ buf) {
+    pdl_sync();
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     for (int p = 0; p < pl.n; ++p) pl.p[p][N + h] = buf[(size_t)h * pl.n + p];
@@ -158,6 +177,7 @@ __global__ void k_halo_unpack(int H, int N, PlaneList pl, const double* __restri
 // ---------------------------------------------------------------- boundary values
 // theta.correctBoundaryConditions(): zeroGradient patch value = internal value
 __global__ void k_bc_zero_gradient(MeshView m, const int* __restrict__ bc, const double* __restrict__ fld, double* __restrict__ fldB, int nc) {
+    pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= m.nB) return;
     if (bc[b] != RHEO_BC_ZERO_GRADIENT || m.bkind[b] == RHEO_PATCH_EMPTY) return;
@@ -295,6 +315,7 @@ struct KrylovCtl {   // one per RHS, device resident
 // ---------------------------------------------------------------- eig + exp + tau
 __global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp, const double* __restrict__ theta, const double* __restrict__ fFene,
                                                     double* __restrict__ lam, double* __restrict__ R, double* __restrict__ tau) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
     double th[6], d[3], V[9], l[3], t6[6];
@@ -312,6 +333,7 @@ __global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp
 }
 // stand-alone calcEig on AoS host-layout arrays (unit parity test entry point)
 __global__ void k_eig_exp_aos(int n, const double* __restrict__ th6, double* __restrict__ vals9, double* __restrict__ vecs9) {
+    pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     double th[6], d[3], V[9];
@@ -326,6 +348,7 @@ __global__ void k_eig_exp_aos(int n, const double* __restrict__ th6, double* __r
 // ---------------------------------------------------------------- tau wall BC: linearExtrapolation on one patch
 // one thread per patch face; gradient of the 6 tau components at the wall-adjacent cell only
 __global__ void k_tau_bc_linext(MeshView m, int start, int size, const double* __restrict__ tau, const double* __restrict__ tauB, double* __restrict__ tmp) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= size) return;
     const int b = start + i;
@@ -339,6 +362,7 @@ __global__ void k_tau_bc_linext(MeshView m, int start, int size, const double* _
     for (int k = 0; k < 6; ++k) tmp[(size_t)k * size + i] = own[k] + (g[3 * k] * dx + g[3 * k + 1] * dy + g[3 * k + 2] * dz);
 }
 __global__ void k_tau_bc_commit(int nB, int start, int size, const double* __restrict__ tmp, double* __restrict__ tauB) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= size) return;
     for (int k = 0; k < 6; ++k) tauB[(size_t)k * nB + start + i] = tmp[(size_t)k * size + i];

@@ -192,6 +192,7 @@ __device__ __noinline__ void ctl_dispatch(int what, KrylovShared* ks, int nrhs, 
     if (q == 0 && (what == CTL_INIT || what == CTL_END)) ks->nActive = __popc(m);
 }
 __global__ void k_ctl(int what, KrylovShared* ks, int nrhs, const double* red, SolveCtl sc) {
+    pdl_sync();
     if (blockIdx.x == 0 && threadIdx.x < 32) ctl_dispatch(what, ks, nrhs, red, sc);
 }
 
@@ -232,6 +233,7 @@ __device__ __forceinline__ void finalize_ctl(const double* partials, int nBlocks
 // ---------------------------------------------------------------- sum(psi) for gAverage
 template <int NR>
 __global__ void __launch_bounds__(BLOCK) k_sum_psi(int N, int nModes, RhsPtrs rp, double* partials, double* out, unsigned* counter) {
+    pdl_sync();
     const int stride = gridDim.x * BLOCK;
     for (int md = 0; md < nModes; ++md) {
         double v[NR];
@@ -254,6 +256,7 @@ template <int NR, int KT>
 __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ A,
                                                         const double* __restrict__ sumPsi, double nGlobal, double* __restrict__ r, double* __restrict__ r0v,
                                                         double* partials, double* out, unsigned* counter, int ctlWhat, KrylovShared* ks, SolveCtl sc) {
+    pdl_sync();
     const int stride = gridDim.x * BLOCK;
     for (int md = 0; md < nModes; ++md) {
         double red[3 * NR];
@@ -334,6 +337,7 @@ __global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, R
 template <int NR>
 __global__ void __launch_bounds__(BLOCK) k_update_p(int c0, int c1, int NP, int nModes, const KrylovShared* __restrict__ ks, const double* __restrict__ rD,
                                                      const double* __restrict__ r, const double* __restrict__ v, double* __restrict__ p, double* __restrict__ y) {
+    pdl_sync();
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
     for (int md = 0; md < nModes; ++md) {
@@ -374,6 +378,7 @@ struct SweepUpd {
 };
 template <int NR, int KT, int FWD, int UPD>
 __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_sweep(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, SweepUpd u) {
+    pdl_sync();
     if (ks->nActive == 0) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     __shared__ uint64_t full[2];
@@ -458,6 +463,7 @@ template <int NR, int KT, int MODE, int FUSE>
 __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_spmv(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, double* __restrict__ v,
                                               const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
                                               int totalBlocks, int ctlWhat, SolveCtl sc) {
+    pdl_sync();
     if (ks->nActive == 0) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
     __shared__ uint64_t full[2];
@@ -514,6 +520,7 @@ template <int NR, int MODE>
 __global__ void __launch_bounds__(BLOCK) k_ghost(MeshView m, int nBcells, const int* __restrict__ bcells, int nModes, const KrylovShared* __restrict__ ks,
                                                   const double* __restrict__ A, const double* __restrict__ y, double* __restrict__ v,
                                                   const double* __restrict__ other, double* dots) {
+    pdl_sync();
     if (ks->nActive == 0) return;
     constexpr int ND = MODE == 0 ? 1 : 2;
     const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,6 +560,7 @@ template <int NR>
 __global__ void __launch_bounds__(BLOCK) k_make_s(int c0, int c1, int NP, int nModes, KrylovShared* ks, const double* __restrict__ rD, const double* __restrict__ r,
                                                    const double* __restrict__ v, double* __restrict__ sv, double* __restrict__ z, double* partials,
                                                    double* out, unsigned* counter, int totalBlocks, int ctlWhat, SolveCtl sc) {
+    pdl_sync();
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
     for (int md = 0; md < nModes; ++md) {
@@ -586,6 +594,7 @@ __global__ void __launch_bounds__(BLOCK, 2) k_update_x_r(int N, int NP, int nMod
                                                        const double* __restrict__ z, const double* __restrict__ sv, const double* __restrict__ t,
                                                        const double* __restrict__ r0v, double* __restrict__ r, double* partials, double* out,
                                                        unsigned* counter, int ctlWhat, SolveCtl sc) {
+    pdl_sync();
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
     for (int md = 0; md < nModes; ++md) {

@@ -77,6 +77,7 @@ __device__ __forceinline__ void peer_wait(const unsigned long long* flag, unsign
 // order); on return of the kernel my mailbox [parity] holds the records of MY ghosts, laid out like `send`.
 // grid <= SM count (all CTAs co-resident: a CTA that waits for a peer can never keep one of its own rank's CTAs from storing).
 __global__ void __launch_bounds__(BLOCK) k_peer_halo(PeerView pv, int rec, unsigned long long seq, const double* __restrict__ send) {
+    pdl_sync();
     __shared__ bool isLast;
     const int par = (int)(seq & 1ull);
     const long total = (long)pv.H * rec;
@@ -101,6 +102,7 @@ __global__ void __launch_bounds__(BLOCK) k_peer_halo(PeerView pv, int rec, unsig
 // All-reduce (sum) of buf[0..nd) over the ranks + the scalar control step `what` (CTL_NONE: reduction only).
 __global__ void __launch_bounds__(128) k_peer_allreduce_ctl(PeerView pv, double* buf, int nd, unsigned long long seq, int what, KrylovShared* ks, int nrhs,
                                                              SolveCtl sc) {
+    pdl_sync();
     const int par = (int)(seq & 1ull), R = pv.nRanks;
     for (int q = threadIdx.x; q < nd; q += blockDim.x) {
         const double v = buf[q];
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
                                                                  const int* __restrict__ bcells, const int* __restrict__ haloCell, int nModes, KrylovShared* ks,
                                                                  const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ v,
                                                                  const double* __restrict__ other, double* dots, const double* half, SolveCtl sc) {
+    pdl_sync();
     // no early exit when every RHS has converged (speculative iterations): the sequence numbers must advance by one per
     // executed operation on every rank, or the two-parity mailboxes would lose their ordering guarantee
     constexpr int ND = MODE == 0 ? 1 : 2;
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
 // (U, theta, tau, psi before the first residual): boundary-cell values of the planes in `pl` go straight into the
 // neighbours' mailboxes; after the wait my ghosts [N, N+H) of every plane are filled from my mailbox.
 __global__ void __launch_bounds__(BLOCK) k_peer_halo_planes(PeerView pv, unsigned long long seq, int N, PlaneList pl, const int* __restrict__ haloCell) {
+    pdl_sync();
     __shared__ bool isLast;
     const int par = (int)(seq & 1ull), rec = pl.n;
     const unsigned long long tA = global_ns();

@@ -7,6 +7,7 @@
 // interleaved halo records: buf[(nModes*NR)*h + md*NR + j]
 template <int NR>
 __global__ void k_halo_pack_il(int H, int NP, int nModes, const int* __restrict__ haloCell, const double* __restrict__ x, double* __restrict__ buf) {
+    pdl_sync();
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     const int c = haloCell[h];
@@ -18,6 +19,7 @@ __global__ void k_halo_pack_il(int H, int NP, int nModes, const int* __restrict_
 }
 template <int NR>
 __global__ void k_halo_unpack_il(int H, int N, int NP, int nModes, const double* __restrict__ buf, double* __restrict__ x) {
+    pdl_sync();
     const int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= H) return;
     for (int md = 0; md < nModes; ++md) {
