@@ -44,6 +44,8 @@ extern "C" {
 #define RHEO_MODEL_GIESEKUS_LOG  1
 #define RHEO_MODEL_PTT_LOG       2
 #define RHEO_MODEL_FENE_P_LOG    3
+#define RHEO_MODEL_FENE_CR_LOG   4   /* FENE-CR/FENE-CRLog/FENE_CRLog.C:128-182 (further Log models) */
+#define RHEO_MODEL_WM_CY_LOG     5   /* WhiteMetznerCY/WhiteMetznerCYLog/WhiteMetznerCYLog.C:145-211 */
 
 /* PTTLog destructionFunctionType (PTT/PTTLog/PTTLog.C:41-50,190-237) */
 #define RHEO_PTT_LINEAR      0
@@ -72,7 +74,9 @@ typedef struct RheoModelDesc {
     int32_t ptt_function;   /* RHEO_PTT_*                                      */
     double  ml_alpha, ml_beta, ml_rtol;  /* PTTLog generalized (Mittag-Leffler) */
     int32_t ml_max_iter;
-    double  L2;             /* FENE-PLog extensibility                         */
+    double  L2;             /* FENE-PLog / FENE-CRLog extensibility            */
+    double  wm_K, wm_n, wm_a; /* WhiteMetznerCYLog: eta, lambda *= (1 + (K gdot)^a)^((n-1)/a); the Log version requires
+                               m = n, L = K, b = a (WhiteMetznerCYLog.C:132-140: the caller checks and passes one set) */
 } RheoModelDesc;
 
 typedef struct RheoSchemeCtl {

@@ -286,8 +286,8 @@ double mittag_leffler(const Model& mo, double zi) {
     return sum;
 }
 
-// right-hand side of the theta equation for one cell; returns FENE-P's f (else 0)
-//   Oldroyd_BLog.C:146-163, GiesekusLog.C:142-157, PTTLog.C:190-251, FENE_PLog.C:142-163
+// right-hand side of the theta equation for one cell; returns the FENE-P / FENE-CR f (else 0)
+//   Oldroyd_BLog.C:146-163, GiesekusLog.C:142-157, PTTLog.C:190-251, FENE_PLog.C:142-163, FENE_CRLog.C:141-163
 double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const T9& R, const T9& Lam, double* rhs6) {
     const RheoModelDesc& d = mo.d;
     T9 omega, B;
@@ -297,6 +297,16 @@ double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const 
     T9 acc = add(sub(mul(omega, th), mul(th, omega)), scale(2.0, B));
     double f = 0;
     switch (d.model) {
+        case RHEO_MODEL_WM_CY_LOG: {   // WhiteMetznerCYLog.C:155-196
+            double s6[6];
+            symm(L, s6);
+            const double magD = std::sqrt(s6[0] * s6[0] + s6[3] * s6[3] + s6[5] * s6[5] + 2.0 * (s6[1] * s6[1] + s6[2] * s6[2] + s6[4] * s6[4]));
+            const double cy = std::pow(1.0 + std::pow(d.wm_K * std::sqrt(2.0) * magD, d.wm_a), (d.wm_n - 1.0) / d.wm_a);
+            const double lamC = d.lambda * cy, etaC = d.etaP * cy;
+            f = etaC / lamC;   // carried to theta -> tau (etaP/lambda fields of before the solve, :207)
+            acc = add(acc, scale(1.0 / lamC, innerP(R, sub(inv(Lam), I), false)));
+            break;
+        }
         case RHEO_MODEL_OLDROYD_B_LOG:
             acc = add(acc, scale(1.0 / d.lambda, innerP(R, sub(inv(Lam), I), false)));
             break;
@@ -323,6 +333,12 @@ double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const 
             acc = add(acc, scale(1.0 / d.lambda, mul(mul(R, sub(scale(a, inv(Lam)), scale(f, I))), transpose(R))));
             break;
         }
+        case RHEO_MODEL_FENE_CR_LOG: {   // FENE_CRLog.C:141-163
+            const T9 A = mul(mul(R, Lam), transpose(R));
+            f = d.L2 / (d.L2 - tr(A));
+            acc = add(acc, scale((1.0 / d.lambda) * f, mul(mul(R, sub(inv(Lam), I)), transpose(R))));
+            break;
+        }
     }
     symm(acc, rhs6);
     return f;
@@ -340,6 +356,8 @@ void tau_cell(const Model& mo, const T9& R, const T9& Lam, double fOld, double* 
         symm(sub(scale(fOld, A), scale(a, I)), s);
     } else {
         if (d.model == RHEO_MODEL_PTT_LOG) coef = d.etaP / (d.lambda * (1 - d.zeta));
+        if (d.model == RHEO_MODEL_FENE_CR_LOG) coef = (d.etaP / d.lambda) * fOld;   // FENE_CRLog.C:174 (f of before the solve)
+        if (d.model == RHEO_MODEL_WM_CY_LOG) coef = fOld;                            // WhiteMetznerCYLog.C:207
         symm(sub(A, I), s);
     }
     for (int q = 0; q < 6; ++q) tau6[q] = coef * s[q];

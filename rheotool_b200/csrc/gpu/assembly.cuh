@@ -269,6 +269,7 @@ struct SourceArgs {
 };
 
 constexpr int SRC_BLOCK = 128;
+template <int MODEL>
 __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, SourceArgs a) {
     pdl_sync();
     double sum[6] = {0, 0, 0, 0, 0, 0};
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, Sourc
         const double V = m.V[c];
         // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
         const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
-        const double f = model_rhs(a.mp, L, th, Rm, lm, rhs);
+        const double f = model_rhs<MODEL>(a.mp, L, th, Rm, lm, rhs);
         a.fFene[c] = f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {

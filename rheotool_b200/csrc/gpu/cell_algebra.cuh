@@ -15,7 +15,7 @@ namespace rk {
 
 struct ModelParams {
     int model, ptt_function, ml_max_iter;
-    double etaP, lambda, alpha, epsilon, zeta, L2, ml_rtol, gamma_beta;
+    double etaP, lambda, alpha, epsilon, zeta, L2, ml_rtol, gamma_beta, wmK, wmN, wmA;
     const double* gamma_vals;   // device table Gamma(alpha k + beta), PTTLog.C:143-170
 };
 
@@ -65,13 +65,15 @@ __device__ __forceinline__ double mittag_leffler(const ModelParams& mp, double z
     return sum;
 }
 
-// rhs6 = symm(Omega.theta - theta.Omega + 2B + G);  returns FENE-P's f (0 otherwise).
+// rhs6 = symm(Omega.theta - theta.Omega + 2B + G);  returns the FENE-P / FENE-CR f (0 otherwise).
+// MODEL is a compile-time constant: every model gets its own instance of the source kernel (no dead code, fewer registers).
 // L: grad(U), L_ij = d_i U_j.  R: eigenvectors in columns.  lam: exp(eigenvalues).
+template <int MODEL>
 __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double* L, const double* th6, const double* R,
                                             const double* lam, double* rhs6) {
     // X = L^T (- zeta symm(L) for PTT)          boilerLog.H:26-32
     double X[9] = {L[0], L[3], L[6], L[1], L[4], L[7], L[2], L[5], L[8]};
-    if (mp.model == RHEO_MODEL_PTT_LOG) {
+    if (MODEL == RHEO_MODEL_PTT_LOG) {
         const double z = mp.zeta;
         const double sxy = 0.5 * (L[1] + L[3]), sxz = 0.5 * (L[2] + L[6]), syz = 0.5 * (L[5] + L[7]);
         X[0] -= z * L[0]; X[4] -= z * L[4]; X[8] -= z * L[8];
@@ -98,20 +100,29 @@ __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double*
     // model term G (symmetric): eigen-frame diagonal g_k, G = R diag(g) R^T, except Giesekus' quadratic term
     double f = 0.0;
     double g0, g1, g2;
-    const double il = 1.0 / mp.lambda;
+    double il = 1.0 / mp.lambda;
+    if (MODEL == RHEO_MODEL_WM_CY_LOG) {
+        // WhiteMetznerCYLog.C:155-163: etaP, lambda *= (1 + (K sqrt(2) |symm L|)^a)^((n-1)/a); f carries etaP/lambda to theta->tau
+        const double sxy = 0.5 * (L[1] + L[3]), sxz = 0.5 * (L[2] + L[6]), syz = 0.5 * (L[5] + L[7]);
+        const double magD = sqrt(L[0] * L[0] + L[4] * L[4] + L[8] * L[8] + 2.0 * (sxy * sxy + sxz * sxz + syz * syz));
+        const double cy = pow(1.0 + pow(mp.wmK * sqrt(2.0) * magD, mp.wmA), (mp.wmN - 1.0) / mp.wmA);
+        const double lamC = mp.lambda * cy, etaC = mp.etaP * cy;
+        il = 1.0 / lamC;
+        f = etaC / lamC;
+    }
     const double i0 = 1.0 / lx, i1 = 1.0 / ly, i2 = 1.0 / lz;
     double G6[6];
-    if (mp.model == RHEO_MODEL_OLDROYD_B_LOG) {
+    if (MODEL == RHEO_MODEL_OLDROYD_B_LOG || MODEL == RHEO_MODEL_WM_CY_LOG) {
         g0 = il * (i0 - 1.0); g1 = il * (i1 - 1.0); g2 = il * (i2 - 1.0);
         rdrt_sym(R, g0, g1, g2, G6);
-    } else if (mp.model == RHEO_MODEL_GIESEKUS_LOG) {
+    } else if (MODEL == RHEO_MODEL_GIESEKUS_LOG) {
         // trhs - alpha A trhs^2 with A, trhs co-diagonal in R:  (1/L-1) - alpha L (1/L-1)^2
         const double t0 = i0 - 1.0, t1 = i1 - 1.0, t2 = i2 - 1.0;
         g0 = il * (t0 - mp.alpha * (lx * (t0 * t0)));
         g1 = il * (t1 - mp.alpha * (ly * (t1 * t1)));
         g2 = il * (t2 - mp.alpha * (lz * (t2 * t2)));
         rdrt_sym(R, g0, g1, g2, G6);
-    } else if (mp.model == RHEO_MODEL_PTT_LOG) {
+    } else if (MODEL == RHEO_MODEL_PTT_LOG) {
         double A6[6];
         rdrt_sym(R, lx, ly, lz, A6);
         const double z = (mp.epsilon / (1.0 - mp.zeta)) * ((A6[0] + A6[3] + A6[5]) - 3.0);
@@ -120,6 +131,12 @@ __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double*
         else if (mp.ptt_function == RHEO_PTT_EXPONENTIAL) Y = exp(z);
         else Y = mp.gamma_beta * mittag_leffler(mp, z);
         g0 = il * (i0 - 1.0) * Y; g1 = il * (i1 - 1.0) * Y; g2 = il * (i2 - 1.0) * Y;
+        rdrt_sym(R, g0, g1, g2, G6);
+    } else if (MODEL == RHEO_MODEL_FENE_CR_LOG) {   // FENE_CRLog.C:143-163: (f/lambda) R (1/Lambda - I) R^T
+        double A6[6];
+        rdrt_sym(R, lx, ly, lz, A6);
+        f = mp.L2 / (mp.L2 - (A6[0] + A6[3] + A6[5]));
+        g0 = il * f * (i0 - 1.0); g1 = il * f * (i1 - 1.0); g2 = il * f * (i2 - 1.0);
         rdrt_sym(R, g0, g1, g2, G6);
     } else {   // FENE-P
         double A6[6];
@@ -197,7 +214,7 @@ __device__ __forceinline__ void jacobi_eig(const double* th6, double* d, double*
     V[0] = c00; V[1] = c01; V[2] = c02; V[3] = c10; V[4] = c11; V[5] = c12; V[6] = c20; V[7] = c21; V[8] = c22;
 }
 
-// tau from (R, Lambda); fOld = FENE-P f computed before the solve (FENE_PLog.C:142,178)
+// tau from (R, Lambda); fOld = FENE-P / FENE-CR f computed before the solve (FENE_PLog.C:142,178; FENE_CRLog.C:141,174)
 __device__ __forceinline__ void tau_from_eig(const ModelParams& mp, const double* R, const double* lam, double fOld, double* tau6) {
     double A6[6];
     rdrt_sym(R, lam[0], lam[1], lam[2], A6);
@@ -208,6 +225,8 @@ __device__ __forceinline__ void tau_from_eig(const ModelParams& mp, const double
         tau6[3] = coef * (fOld * A6[3] - a); tau6[4] = coef * (fOld * A6[4]); tau6[5] = coef * (fOld * A6[5] - a);
     } else {
         if (mp.model == RHEO_MODEL_PTT_LOG) coef = mp.etaP / (mp.lambda * (1.0 - mp.zeta));
+        if (mp.model == RHEO_MODEL_FENE_CR_LOG) coef = (mp.etaP / mp.lambda) * fOld;   // FENE_CRLog.C:174: f of BEFORE the solve
+        if (mp.model == RHEO_MODEL_WM_CY_LOG) coef = fOld;                              // WhiteMetznerCYLog.C:207: etaP/lambda of BEFORE the solve
         tau6[0] = coef * (A6[0] - 1.0); tau6[1] = coef * A6[1]; tau6[2] = coef * A6[2];
         tau6[3] = coef * (A6[3] - 1.0); tau6[4] = coef * A6[4]; tau6[5] = coef * (A6[5] - 1.0);
     }

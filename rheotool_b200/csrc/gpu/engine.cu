@@ -492,12 +492,14 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         ModeDev& md = h->modes[mi];
         md.desc = modes[mi];
         const RheoModelDesc& q = modes[mi];
-        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_FENE_P_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
+        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_WM_CY_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
         if (!(q.lambda > 0)) return fail("rheo_gpu_create: lambda must be positive");
         ModelParams& mp = md.mp;
         mp.model = q.model; mp.ptt_function = q.ptt_function; mp.ml_max_iter = q.ml_max_iter;
         mp.etaP = q.etaP; mp.lambda = q.lambda; mp.alpha = q.alpha; mp.epsilon = q.epsilon; mp.zeta = q.zeta; mp.L2 = q.L2;
         mp.ml_rtol = q.ml_rtol; mp.gamma_beta = 1.0; mp.gamma_vals = nullptr;
+        mp.wmK = q.wm_K; mp.wmN = q.wm_n; mp.wmA = q.wm_a;
+        if (q.model == RHEO_MODEL_WM_CY_LOG && !(q.wm_a > 0)) return fail("rheo_gpu_create: WhiteMetznerCYLog needs a > 0");
         if (q.model == RHEO_MODEL_PTT_LOG && q.ptt_function == RHEO_PTT_GENERALIZED) {   // PTTLog.C:143-170
             if (q.ml_alpha <= 0 || q.ml_beta <= 0) return fail("Both alpha and beta should be positive values for the Mittag-Leffler function to converge.");
             std::vector<double> gv{std::tgamma(q.ml_beta)};
@@ -803,7 +805,15 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
                 sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>();
                 sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
-                LAUNCH(h, k_cell_source2, std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms), SRC_BLOCK, h->mv, sa);
+                const int srcGrid = std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms);
+                switch (md.mp.model) {
+                    case RHEO_MODEL_OLDROYD_B_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_OLDROYD_B_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_GIESEKUS_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_GIESEKUS_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_PTT_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_PTT_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_FENE_P_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_P_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_FENE_CR_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_CR_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                }
             }
             if (h->H && hrs) {
                 const double* recv;

@@ -2,7 +2,7 @@
   of90_LogConformationGPU.C — see the header.  OpenFOAM-9 + rheoTool only.
 
   Registered type names (constant/constitutiveProperties -> parameters -> type):
-      Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  multiModeLogGPU
+      Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  FENE-CRLogGPU  multiModeLogGPU
   Dictionary keys are those of the CPU models (Oldroyd_BLog.C:114-119,
   GiesekusLog.C:117, PTTLog.C:129-139, FENE_PLog.C:114-119, multiMode.C:73-92);
   fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler,
@@ -41,6 +41,8 @@ namespace constitutiveEqs
     RHEO_GPU_REGISTER(GiesekusLogGPU, "GiesekusLogGPU")
     RHEO_GPU_REGISTER(PTTLogGPU, "PTTLogGPU")
     RHEO_GPU_REGISTER(FENE_PLogGPU, "FENE-PLogGPU")
+    RHEO_GPU_REGISTER(FENE_CRLogGPU, "FENE-CRLogGPU")
+    RHEO_GPU_REGISTER(WhiteMetznerCYLogGPU, "WhiteMetznerCYLogGPU")
     RHEO_GPU_REGISTER(multiModeLogGPU, "multiModeLogGPU")
 }
 }
@@ -90,6 +92,24 @@ void LogConformationGPU::readMode(const word& type, const dictionary& dict, Rheo
     {
         m.model = RHEO_MODEL_FENE_P_LOG;
         m.L2 = dimensionedScalar(dict.lookup("L2")).value();
+    }
+    else if (type == "FENE-CRLogGPU" || type == "FENE-CRLog")      // FENE_CRLog.C:114-119
+    {
+        m.model = RHEO_MODEL_FENE_CR_LOG;
+        m.L2 = dimensionedScalar(dict.lookup("L2")).value();
+    }
+    else if (type == "WhiteMetznerCYLogGPU" || type == "WhiteMetznerCYLog")
+    {
+        m.model = RHEO_MODEL_WM_CY_LOG;
+        const scalar K = dimensionedScalar(dict.lookup("K")).value(), Lp = dimensionedScalar(dict.lookup("L")).value();
+        const scalar n = dimensionedScalar(dict.lookup("n")).value(), mm = dimensionedScalar(dict.lookup("m")).value();
+        const scalar a = dimensionedScalar(dict.lookup("a")).value(), b = dimensionedScalar(dict.lookup("b")).value();
+        if (mm != n || K != Lp || a != b)                         // WhiteMetznerCYLog.C:132-140
+        {
+            FatalErrorInFunction << "The Log version of the WhiteMetznerCY model can only be used if:\n"
+                << "\n   m=n   and   K=L   and   a=b\n" << abort(FatalError);
+        }
+        m.wm_K = K; m.wm_n = n; m.wm_a = a;
     }
     else
     {

@@ -249,3 +249,29 @@ def test_host_buffer_call_matches_resident_call_and_skips_empty_patches():
     assert h1 - h0 == 8 * (3 * s.mesh.n_cells + 3 * (s.mesh.n_boundary - n_empty) + (n_faces - n_empty))
     assert d1 - d0 == 8 * 6 * s.mesh.n_cells
     assert g2.comm_stats()["mode"] == "single"
+
+
+def test_fene_cr_log_one_step_and_ten_steps():
+    """FENE-CRLog (FENE_CRLog.C:128-182): same kernels, its own source / theta->tau functor."""
+    spec = cases.by_name("C5", 16 / 400)
+    spec.models[:] = [cases.model_desc("FENE-CRLog", rho=1.0, etaS=0.01, etaP=0.99, lambda_=0.1, L2=100.0)]
+    s, oc, g = _one_step(spec)
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
+    for _ in range(9):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
+
+
+def test_white_metzner_cy_log_one_step_and_ten_steps():
+    """WhiteMetznerCYLog (WhiteMetznerCYLog.C:145-211): shear-rate dependent eta_p, lambda per cell."""
+    spec = cases.by_name("C3", 3 / 19)
+    spec.models[:] = [cases.model_desc("WhiteMetznerCYLog", rho=1.0, etaS=0.01, etaP=0.99, lambda_=0.1, wm_K=0.8, wm_n=0.5, wm_a=2.0)]
+    s, oc, g = _one_step(spec)
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
+    for _ in range(9):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8

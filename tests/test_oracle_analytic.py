@@ -72,6 +72,8 @@ def H_of(model, A):
         Y = 1 + z if model.ptt_function == abi.PTT_LINEAR else np.exp(z)
         return Y * (A - I)
     f = model.L2 / (model.L2 - np.trace(A))
+    if model.model == abi.MODEL_FENE_CR_LOG:   # FENE_CR.C: f (A - I)
+        return f * (A - I)
     a = model.L2 / (model.L2 - 3)
     return f * A - a * I
 
@@ -87,6 +89,7 @@ MODELS = {
     "PTTLog-linear": dict(etaS=0.11, etaP=0.89, lambda_=0.6, epsilon=0.25, zeta=0.0, ptt_function="linear"),
     "PTTLog-exponential": dict(etaS=0.11, etaP=0.89, lambda_=0.6, epsilon=0.1, zeta=0.1, ptt_function="exponential"),
     "FENE-PLog": dict(etaS=0.01, etaP=0.99, lambda_=0.4, L2=50.0),
+    "FENE-CRLog": dict(etaS=0.01, etaP=0.99, lambda_=0.4, L2=50.0),
 }
 
 
@@ -108,11 +111,41 @@ def test_steady_state_satisfies_original_constitutive_equation(mname, flow):
     if model.model == abi.MODEL_FENE_P_LOG:
         f = model.L2 / (model.L2 - np.trace(A)); a = model.L2 / (model.L2 - 3)
         expect = coef * (f * A - a * np.eye(3))
+    elif model.model == abi.MODEL_FENE_CR_LOG:
+        expect = coef * model.L2 / (model.L2 - np.trace(A)) * (A - np.eye(3))
     elif model.model == abi.MODEL_PTT_LOG:
         expect = coef / (1 - model.zeta) * (A - np.eye(3))
     else:
         expect = coef * (A - np.eye(3))
     assert np.abs(tau - expect).max() < 1e-8 * max(1.0, np.abs(expect).max())
+
+
+def test_fene_cr_simple_shear_material_functions():
+    """FENE-CR in steady simple shear (closed form): constant shear viscosity  tau_xy = etaP*gdot  and
+    N1 = 2 etaP lambda gdot^2 / f  with f the positive root of (L2-3) f^2 - L2 f - 2 (lambda gdot)^2 = 0."""
+    etaP, lam, gd, L2 = 0.8, 0.5, 1.7, 30.0
+    model = cases.model_desc("FENE-CRLog", etaS=0.2, etaP=etaP, lambda_=lam, L2=L2)
+    kappa = np.zeros((3, 3)); kappa[0, 1] = gd
+    oc, _ = homogeneous_case(model, kappa)
+    tau = sym6(oc.get(0, 0, abi.FIELD_TAU)[0])
+    f = (L2 + np.sqrt(L2 ** 2 + 8 * (L2 - 3) * (lam * gd) ** 2)) / (2 * (L2 - 3))
+    assert tau[0, 1] == pytest.approx(etaP * gd, rel=1e-8)
+    assert tau[0, 0] - tau[1, 1] == pytest.approx(2 * etaP * lam * gd ** 2 / f, rel=1e-8)
+    assert abs(tau[1, 1]) < 1e-8 and abs(tau[2, 2]) < 1e-8
+
+
+def test_white_metzner_cy_simple_shear_material_functions():
+    """White-Metzner with Carreau-Yasuda functions (Log version: m = n, L = K, b = a) in steady simple shear behaves like
+    Oldroyd-B with the rate-dependent eta(gdot), lambda(gdot):  tau_xy = eta gdot,  N1 = 2 eta lambda gdot^2."""
+    etaP, lam, gd, K, n, a = 0.9, 0.4, 2.3, 1.5, 0.6, 1.8
+    model = cases.model_desc("WhiteMetznerCYLog", etaS=0.1, etaP=etaP, lambda_=lam, wm_K=K, wm_n=n, wm_a=a)
+    kappa = np.zeros((3, 3)); kappa[0, 1] = gd
+    oc, _ = homogeneous_case(model, kappa)
+    tau = sym6(oc.get(0, 0, abi.FIELD_TAU)[0])
+    cy = (1 + (K * gd) ** a) ** ((n - 1) / a)
+    assert tau[0, 1] == pytest.approx(etaP * cy * gd, rel=1e-8)
+    assert tau[0, 0] - tau[1, 1] == pytest.approx(2 * (etaP * cy) * (lam * cy) * gd ** 2, rel=1e-8)
+    assert abs(tau[1, 1]) < 1e-8 and abs(tau[2, 2]) < 1e-8
 
 
 def test_ptt_generalized_reduces_to_exponential_for_alpha_beta_one():
