@@ -46,6 +46,8 @@ extern "C" {
 #define RHEO_MODEL_FENE_P_LOG    3
 #define RHEO_MODEL_FENE_CR_LOG   4   /* FENE-CR/FENE-CRLog/FENE_CRLog.C:128-182 (further Log models) */
 #define RHEO_MODEL_WM_CY_LOG     5   /* WhiteMetznerCY/WhiteMetznerCYLog/WhiteMetznerCYLog.C:145-211 */
+#define RHEO_MODEL_ROLIE_POLY_LOG 6  /* Rolie-Poly/Rolie-PolyLog/RoliePolyLog.C:130-215 (lambda = lambdaD) */
+#define RHEO_MODEL_XPOMPOM_LOG   7   /* XPomPom/XPomPomLog/XPomPomLog.C:130-198 (lambda = lambdaB, alpha = anisotropy) */
 
 /* PTTLog destructionFunctionType (PTT/PTTLog/PTTLog.C:41-50,190-237) */
 #define RHEO_PTT_LINEAR      0
@@ -77,6 +79,8 @@ typedef struct RheoModelDesc {
     double  L2;             /* FENE-PLog / FENE-CRLog extensibility            */
     double  wm_K, wm_n, wm_a; /* WhiteMetznerCYLog: eta, lambda *= (1 + (K gdot)^a)^((n-1)/a); the Log version requires
                                m = n, L = K, b = a (WhiteMetznerCYLog.C:132-140: the caller checks and passes one set) */
+    double  rp_lambdaR, rp_beta, rp_delta, rp_chiMax;   /* Rolie-PolyLog (RoliePolyLog.C:114-121)            */
+    double  xpp_lambdaS, xpp_q, xpp_n;                  /* XPomPomLog   (XPomPomLog.C:115-122)               */
 } RheoModelDesc;
 
 typedef struct RheoSchemeCtl {

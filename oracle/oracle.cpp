@@ -333,6 +333,34 @@ double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const 
             acc = add(acc, scale(1.0 / d.lambda, mul(mul(R, sub(scale(a, inv(Lam)), scale(f, I))), transpose(R))));
             break;
         }
+        case RHEO_MODEL_ROLIE_POLY_LOG: {   // RoliePolyLog.C:144-186
+            double a6[6];
+            symm(mul(mul(R, Lam), transpose(R)), a6);
+            const T9 A = from_sym(a6);
+            const double trA = tr(A);
+            double M1 = 2. * (1. - std::sqrt(3. / trA)) / d.rp_lambdaR;
+            if (d.rp_chiMax > 1.) {
+                const double c2 = d.rp_chiMax * d.rp_chiMax;
+                M1 *= ((3. - (trA / 3.) / c2) * (1. - 1. / c2)) / ((1. - (trA / 3.) / c2) * (3. - 1. / c2));
+            }
+            const T9 inner = add(sub(A, I), scale(M1 * d.lambda, add(A, scale(d.rp_beta * std::pow(trA / 3., d.rp_delta), sub(A, I)))));
+            acc = sub(acc, scale(1.0 / d.lambda, mul(mul(mul(R, inv(Lam)), transpose(R)), inner)));
+            break;
+        }
+        case RHEO_MODEL_XPOMPOM_LOG: {   // XPomPomLog.C:148-183
+            double a6[6];
+            symm(mul(mul(R, Lam), transpose(R)), a6);
+            const T9 A = from_sym(a6);
+            const double trA = tr(A);
+            const double ls = std::sqrt(trA / 3.);
+            const T9 AA = mul(A, A);
+            const double stretch = d.xpp_n == 0 ? (1. - 1. / ls) : (1. - 1. / std::pow(ls, d.xpp_n + 1.));
+            const double fx = 2. * (d.lambda / d.xpp_lambdaS) * std::exp((2. / d.xpp_q) * (ls - 1.)) * stretch +
+                              (1. / (ls * ls)) * (1. - d.alpha - (d.alpha / 3.) * (tr(AA) - 2. * trA));
+            const T9 inner = add(add(scale(fx - 2. * d.alpha, A), scale(d.alpha, AA)), scale(d.alpha - 1., I));
+            acc = sub(acc, scale(1.0 / d.lambda, mul(mul(mul(R, inv(Lam)), transpose(R)), inner)));
+            break;
+        }
         case RHEO_MODEL_FENE_CR_LOG: {   // FENE_CRLog.C:141-163
             const T9 A = mul(mul(R, Lam), transpose(R));
             f = d.L2 / (d.L2 - tr(A));
@@ -358,6 +386,12 @@ void tau_cell(const Model& mo, const T9& R, const T9& Lam, double fOld, double* 
         if (d.model == RHEO_MODEL_PTT_LOG) coef = d.etaP / (d.lambda * (1 - d.zeta));
         if (d.model == RHEO_MODEL_FENE_CR_LOG) coef = (d.etaP / d.lambda) * fOld;   // FENE_CRLog.C:174 (f of before the solve)
         if (d.model == RHEO_MODEL_WM_CY_LOG) coef = fOld;                            // WhiteMetznerCYLog.C:207
+        if (d.model == RHEO_MODEL_ROLIE_POLY_LOG && d.rp_chiMax > 1.) {              // RoliePolyLog.C:203-212 (updated tr A)
+            double a6[6];
+            symm(A, a6);
+            const double trA = a6[0] + a6[3] + a6[5], c2 = d.rp_chiMax * d.rp_chiMax;
+            coef *= ((3. - (trA / 3.) / c2) * (1. - 1. / c2)) / ((1. - (trA / 3.) / c2) * (3. - 1. / c2));
+        }
         symm(sub(A, I), s);
     }
     for (int q = 0; q < 6; ++q) tau6[q] = coef * s[q];

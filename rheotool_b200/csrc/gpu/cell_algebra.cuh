@@ -15,7 +15,8 @@ namespace rk {
 
 struct ModelParams {
     int model, ptt_function, ml_max_iter;
-    double etaP, lambda, alpha, epsilon, zeta, L2, ml_rtol, gamma_beta, wmK, wmN, wmA;
+    double etaP, lambda, alpha, epsilon, zeta, L2, ml_rtol, gamma_beta, wmK, wmN, wmA,
+        rpLambdaR, rpBeta, rpDelta, rpChiMax, xppLambdaS, xppQ, xppN;
     const double* gamma_vals;   // device table Gamma(alpha k + beta), PTTLog.C:143-170
 };
 
@@ -138,6 +139,37 @@ __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double*
         f = mp.L2 / (mp.L2 - (A6[0] + A6[3] + A6[5]));
         g0 = il * f * (i0 - 1.0); g1 = il * f * (i1 - 1.0); g2 = il * f * (i2 - 1.0);
         rdrt_sym(R, g0, g1, g2, G6);
+    } else if (MODEL == RHEO_MODEL_ROLIE_POLY_LOG) {
+        // RoliePolyLog.C:144-186: -(1/lambdaD) A^-1 ((A - I) + M1 lambdaD (A + beta (trA/3)^delta (A - I))); every factor is
+        // a function of A, so the product is R diag(g) R^T with the scalar expression per eigenvalue
+        double A6[6];
+        rdrt_sym(R, lx, ly, lz, A6);
+        const double trA = A6[0] + A6[3] + A6[5];
+        double M1 = 2.0 * (1.0 - sqrt(3.0 / trA)) / mp.rpLambdaR;
+        if (mp.rpChiMax > 1.0) {
+            const double c2 = mp.rpChiMax * mp.rpChiMax;
+            M1 *= ((3.0 - (trA / 3.0) / c2) * (1.0 - 1.0 / c2)) / ((1.0 - (trA / 3.0) / c2) * (3.0 - 1.0 / c2));
+        }
+        const double bt = mp.rpBeta * pow(trA / 3.0, mp.rpDelta);
+        const double m1l = M1 * mp.lambda;
+        g0 = -il * i0 * ((lx - 1.0) + m1l * (lx + bt * (lx - 1.0)));
+        g1 = -il * i1 * ((ly - 1.0) + m1l * (ly + bt * (ly - 1.0)));
+        g2 = -il * i2 * ((lz - 1.0) + m1l * (lz + bt * (lz - 1.0)));
+        rdrt_sym(R, g0, g1, g2, G6);
+    } else if (MODEL == RHEO_MODEL_XPOMPOM_LOG) {
+        // XPomPomLog.C:148-183: -(1/lambdaB) A^-1 (A (f - 2 alpha) + alpha A.A + (alpha - 1) I)
+        double A6[6];
+        rdrt_sym(R, lx, ly, lz, A6);
+        const double trA = A6[0] + A6[3] + A6[5];
+        const double trAA = A6[0] * A6[0] + A6[3] * A6[3] + A6[5] * A6[5] + 2.0 * (A6[1] * A6[1] + A6[2] * A6[2] + A6[4] * A6[4]);
+        const double ls = sqrt(trA / 3.0);
+        const double stretch = mp.xppN == 0.0 ? (1.0 - 1.0 / ls) : (1.0 - 1.0 / pow(ls, mp.xppN + 1.0));
+        const double fx = 2.0 * (mp.lambda / mp.xppLambdaS) * exp((2.0 / mp.xppQ) * (ls - 1.0)) * stretch +
+                          (1.0 / (ls * ls)) * (1.0 - mp.alpha - (mp.alpha / 3.0) * (trAA - 2.0 * trA));
+        g0 = -il * i0 * (lx * (fx - 2.0 * mp.alpha) + mp.alpha * (lx * lx) + (mp.alpha - 1.0));
+        g1 = -il * i1 * (ly * (fx - 2.0 * mp.alpha) + mp.alpha * (ly * ly) + (mp.alpha - 1.0));
+        g2 = -il * i2 * (lz * (fx - 2.0 * mp.alpha) + mp.alpha * (lz * lz) + (mp.alpha - 1.0));
+        rdrt_sym(R, g0, g1, g2, G6);
     } else {   // FENE-P
         double A6[6];
         rdrt_sym(R, lx, ly, lz, A6);
@@ -227,6 +259,10 @@ __device__ __forceinline__ void tau_from_eig(const ModelParams& mp, const double
         if (mp.model == RHEO_MODEL_PTT_LOG) coef = mp.etaP / (mp.lambda * (1.0 - mp.zeta));
         if (mp.model == RHEO_MODEL_FENE_CR_LOG) coef = (mp.etaP / mp.lambda) * fOld;   // FENE_CRLog.C:174: f of BEFORE the solve
         if (mp.model == RHEO_MODEL_WM_CY_LOG) coef = fOld;                              // WhiteMetznerCYLog.C:207: etaP/lambda of BEFORE the solve
+        if (mp.model == RHEO_MODEL_ROLIE_POLY_LOG && mp.rpChiMax > 1.0) {               // RoliePolyLog.C:203-212: finite extensibility, NEW tr(A)
+            const double trA = A6[0] + A6[3] + A6[5], c2 = mp.rpChiMax * mp.rpChiMax;
+            coef *= ((3.0 - (trA / 3.0) / c2) * (1.0 - 1.0 / c2)) / ((1.0 - (trA / 3.0) / c2) * (3.0 - 1.0 / c2));
+        }
         tau6[0] = coef * (A6[0] - 1.0); tau6[1] = coef * A6[1]; tau6[2] = coef * A6[2];
         tau6[3] = coef * (A6[3] - 1.0); tau6[4] = coef * A6[4]; tau6[5] = coef * (A6[5] - 1.0);
     }

@@ -492,13 +492,17 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         ModeDev& md = h->modes[mi];
         md.desc = modes[mi];
         const RheoModelDesc& q = modes[mi];
-        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_WM_CY_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
+        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_XPOMPOM_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
         if (!(q.lambda > 0)) return fail("rheo_gpu_create: lambda must be positive");
         ModelParams& mp = md.mp;
         mp.model = q.model; mp.ptt_function = q.ptt_function; mp.ml_max_iter = q.ml_max_iter;
         mp.etaP = q.etaP; mp.lambda = q.lambda; mp.alpha = q.alpha; mp.epsilon = q.epsilon; mp.zeta = q.zeta; mp.L2 = q.L2;
         mp.ml_rtol = q.ml_rtol; mp.gamma_beta = 1.0; mp.gamma_vals = nullptr;
         mp.wmK = q.wm_K; mp.wmN = q.wm_n; mp.wmA = q.wm_a;
+        mp.rpLambdaR = q.rp_lambdaR; mp.rpBeta = q.rp_beta; mp.rpDelta = q.rp_delta; mp.rpChiMax = q.rp_chiMax;
+        mp.xppLambdaS = q.xpp_lambdaS; mp.xppQ = q.xpp_q; mp.xppN = q.xpp_n;
+        if (q.model == RHEO_MODEL_ROLIE_POLY_LOG && !(q.rp_lambdaR > 0)) return fail("rheo_gpu_create: Rolie-PolyLog needs lambdaR > 0");
+        if (q.model == RHEO_MODEL_XPOMPOM_LOG && !(q.xpp_lambdaS > 0 && q.xpp_q > 0)) return fail("rheo_gpu_create: XPomPomLog needs lambdaS > 0 and q > 0");
         if (q.model == RHEO_MODEL_WM_CY_LOG && !(q.wm_a > 0)) return fail("rheo_gpu_create: WhiteMetznerCYLog needs a > 0");
         if (q.model == RHEO_MODEL_PTT_LOG && q.ptt_function == RHEO_PTT_GENERALIZED) {   // PTTLog.C:143-170
             if (q.ml_alpha <= 0 || q.ml_beta <= 0) return fail("Both alpha and beta should be positive values for the Mittag-Leffler function to converge.");
@@ -812,7 +816,9 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                     case RHEO_MODEL_PTT_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_PTT_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                     case RHEO_MODEL_FENE_P_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_P_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                     case RHEO_MODEL_FENE_CR_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_CR_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_WM_CY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_ROLIE_POLY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_ROLIE_POLY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_XPOMPOM_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                 }
             }
             if (h->H && hrs) {

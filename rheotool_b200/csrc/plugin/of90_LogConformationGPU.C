@@ -2,7 +2,8 @@
   of90_LogConformationGPU.C — see the header.  OpenFOAM-9 + rheoTool only.
 
   Registered type names (constant/constitutiveProperties -> parameters -> type):
-      Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  FENE-CRLogGPU  multiModeLogGPU
+      Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  FENE-CRLogGPU
+      WhiteMetznerCYLogGPU  Rolie-PolyLogGPU  XPomPomLogGPU  multiModeLogGPU
   Dictionary keys are those of the CPU models (Oldroyd_BLog.C:114-119,
   GiesekusLog.C:117, PTTLog.C:129-139, FENE_PLog.C:114-119, multiMode.C:73-92);
   fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler,
@@ -43,6 +44,8 @@ namespace constitutiveEqs
     RHEO_GPU_REGISTER(FENE_PLogGPU, "FENE-PLogGPU")
     RHEO_GPU_REGISTER(FENE_CRLogGPU, "FENE-CRLogGPU")
     RHEO_GPU_REGISTER(WhiteMetznerCYLogGPU, "WhiteMetznerCYLogGPU")
+    RHEO_GPU_REGISTER(RoliePolyLogGPU, "Rolie-PolyLogGPU")
+    RHEO_GPU_REGISTER(XPomPomLogGPU, "XPomPomLogGPU")
     RHEO_GPU_REGISTER(multiModeLogGPU, "multiModeLogGPU")
 }
 }
@@ -67,7 +70,7 @@ void LogConformationGPU::readMode(const word& type, const dictionary& dict, Rheo
     m.rho    = dimensionedScalar(dict.lookup("rho")).value();
     m.etaS   = dimensionedScalar(dict.lookup("etaS")).value();
     m.etaP   = dimensionedScalar(dict.lookup("etaP")).value();
-    m.lambda = dimensionedScalar(dict.lookup("lambda")).value();
+    m.lambda = dict.found("lambda") ? dimensionedScalar(dict.lookup("lambda")).value() : 1;   // Rolie-Poly / XPomPom name theirs lambdaD / lambdaB
     m.L2 = 100; m.ml_alpha = 1; m.ml_beta = 1; m.ml_rtol = 1e-12; m.ml_max_iter = 200;
     if (type == "Oldroyd-BLogGPU" || type == "Oldroyd-BLog") m.model = RHEO_MODEL_OLDROYD_B_LOG;
     else if (type == "GiesekusLogGPU" || type == "GiesekusLog")
@@ -110,6 +113,24 @@ void LogConformationGPU::readMode(const word& type, const dictionary& dict, Rheo
                 << "\n   m=n   and   K=L   and   a=b\n" << abort(FatalError);
         }
         m.wm_K = K; m.wm_n = n; m.wm_a = a;
+    }
+    else if (type == "Rolie-PolyLogGPU" || type == "Rolie-PolyLog")      // RoliePolyLog.C:114-121
+    {
+        m.model = RHEO_MODEL_ROLIE_POLY_LOG;
+        m.lambda     = dimensionedScalar(dict.lookup("lambdaD")).value();
+        m.rp_lambdaR = dimensionedScalar(dict.lookup("lambdaR")).value();
+        m.rp_beta    = dimensionedScalar(dict.lookup("beta")).value();
+        m.rp_delta   = dimensionedScalar(dict.lookup("delta")).value();
+        m.rp_chiMax  = dimensionedScalar(dict.lookup("chiMax")).value();
+    }
+    else if (type == "XPomPomLogGPU" || type == "XPomPomLog")            // XPomPomLog.C:115-122
+    {
+        m.model = RHEO_MODEL_XPOMPOM_LOG;
+        m.lambda      = dimensionedScalar(dict.lookup("lambdaB")).value();
+        m.xpp_lambdaS = dimensionedScalar(dict.lookup("lambdaS")).value();
+        m.alpha       = dimensionedScalar(dict.lookup("alpha")).value();
+        m.xpp_q       = dimensionedScalar(dict.lookup("q")).value();
+        m.xpp_n       = dimensionedScalar(dict.lookup("n")).value();
     }
     else
     {

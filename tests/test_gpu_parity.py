@@ -275,3 +275,20 @@ def test_white_metzner_cy_log_one_step_and_ten_steps():
         oc.store_old_time(); oc.step(s.dt)
         g.store_old_time(); g.correct(s.dt)
     assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
+
+
+@pytest.mark.parametrize("mname,kw", [
+    ("Rolie-PolyLog", dict(lambda_=0.1, rp_lambdaR=0.03, rp_beta=0.3, rp_delta=-0.5, rp_chiMax=5.0)),
+    ("XPomPomLog", dict(lambda_=0.1, alpha=0.1, xpp_lambdaS=0.04, xpp_q=3.0, xpp_n=1.0)),
+])
+def test_tube_models_one_step_and_ten_steps(mname, kw):
+    """Rolie-PolyLog / XPomPomLog (RoliePolyLog.C:130-215, XPomPomLog.C:130-198)."""
+    spec = cases.by_name("C3", 3 / 19)
+    spec.models[:] = [cases.model_desc(mname, rho=1.0, etaS=0.01, etaP=0.99, **kw)]
+    s, oc, g = _one_step(spec)
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
+    for _ in range(9):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8

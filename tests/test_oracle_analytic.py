@@ -148,6 +148,55 @@ def test_white_metzner_cy_simple_shear_material_functions():
     assert abs(tau[1, 1]) < 1e-8 and abs(tau[2, 2]) < 1e-8
 
 
+def _chi_factor(trA, chi):
+    c2 = chi * chi
+    return ((3 - (trA / 3) / c2) * (1 - 1 / c2)) / ((1 - (trA / 3) / c2) * (3 - 1 / c2))
+
+
+@pytest.mark.parametrize("flow", sorted(FLOWS))
+@pytest.mark.parametrize("chi", [0.0, 4.0])
+def test_rolie_poly_log_steady_state_satisfies_the_conformation_form(flow, chi):
+    """Cross-file pin: the steady A reached by the LOG oracle (RoliePolyLog.C) must satisfy the NON-log conformation
+    equation of RoliePoly.C:139-150:  A.L + L^T.A - (A - I)/lambdaD - M1 (A + beta (trA/3)^delta (A - I)) = 0."""
+    lamD, lamR, beta, delta, etaP = 0.8, 0.2, 0.3, -0.5, 0.9
+    model = cases.model_desc("Rolie-PolyLog", etaS=0.1, etaP=etaP, lambda_=lamD, rp_lambdaR=lamR, rp_beta=beta, rp_delta=delta, rp_chiMax=chi)
+    kappa = FLOWS[flow]
+    oc, _ = homogeneous_case(model, kappa, n_steps=3000)
+    A = conformation(oc)
+    trA = np.trace(A)
+    M1 = 2 * (1 - np.sqrt(3 / trA)) / lamR
+    if chi > 1:
+        M1 *= _chi_factor(trA, chi)
+    I = np.eye(3)
+    res = kappa @ A + A @ kappa.T - (A - I) / lamD - M1 * (A + beta * (trA / 3) ** delta * (A - I))
+    assert np.abs(res).max() < 1e-8 * max(1.0, np.abs(A).max()), res
+    tau = sym6(oc.get(0, 0, abi.FIELD_TAU)[0])
+    expect = etaP / lamD * (A - I) * (_chi_factor(trA, chi) if chi > 1 else 1.0)   # RoliePoly.C:155-166
+    assert np.abs(tau - expect).max() < 1e-8 * max(1.0, np.abs(expect).max())
+
+
+@pytest.mark.parametrize("flow", sorted(FLOWS))
+@pytest.mark.parametrize("n", [0.0, 1.0])
+def test_xpompom_log_steady_state_satisfies_the_stress_form(flow, n):
+    """Cross-file pin: tau reached by the LOG oracle (XPomPomLog.C) must satisfy the steady STRESS equation of
+    XPomPom.C:108-141:  tau.L + L^T.tau + G 2D - (f/lambdaB) tau - (alpha/etaP) tau.tau - (G/lambdaB)(f - 1) I = 0,
+    G = etaP/lambdaB, with lambda and f evaluated from tau as that file does."""
+    lamB, lamS, alpha, q, etaP = 0.6, 0.3, 0.15, 3.0, 0.85
+    model = cases.model_desc("XPomPomLog", etaS=0.15, etaP=etaP, lambda_=lamB, alpha=alpha, xpp_lambdaS=lamS, xpp_q=q, xpp_n=n)
+    kappa = FLOWS[flow]
+    oc, _ = homogeneous_case(model, kappa, n_steps=3000)
+    tau = sym6(oc.get(0, 0, abi.FIELD_TAU)[0])
+    G = etaP / lamB
+    lam = np.sqrt(1 + np.trace(tau) / (3 * G))
+    stretch = (1 - 1 / lam) if n == 0 else (1 - 1 / lam ** (n + 1))
+    f = 2 * (lamB / lamS) * np.exp((2 / q) * (lam - 1)) * stretch + (1 / lam ** 2) * (1 - (alpha / 3) * np.trace(tau @ tau) / G ** 2)
+    L = kappa.T                                   # L_ij = d_i U_j
+    res = tau @ L + L.T @ tau + G * (L + L.T) - (f / lamB) * tau - (alpha / etaP) * (tau @ tau) - (G / lamB) * (f - 1) * np.eye(3)
+    assert np.abs(res).max() < 1e-8 * max(1.0, np.abs(tau).max() / lamB), res
+    A = conformation(oc)
+    assert np.abs(tau - G * (A - np.eye(3))).max() < 1e-8 * max(1.0, np.abs(tau).max())
+
+
 def test_ptt_generalized_reduces_to_exponential_for_alpha_beta_one():
     """Mittag-Leffler E_{1,1}(z) = exp(z) (PTTLog.C:202-236 with alpha = beta = 1)."""
     rng = np.random.default_rng(3)
