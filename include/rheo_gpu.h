@@ -63,7 +63,8 @@ extern "C" {
 #define RHEO_LIMITER_SUPERBEE 5
 #define RHEO_LIMITER_NONE     6   /* no convection */
 
-#define RHEO_DDT_EULER 0
+#define RHEO_DDT_EULER    0
+#define RHEO_DDT_BACKWARD 1   /* EXT-OF9 backwardDdtScheme: Euler until the field has two old times, variable-step coefficients after */
 
 #define RHEO_SOLVER_PBICGSTAB 0
 #define RHEO_SOLVER_PBICG     1
@@ -85,7 +86,7 @@ typedef struct RheoModelDesc {
 
 typedef struct RheoSchemeCtl {
     int32_t limiter;        /* divSchemes div(phi,theta) GaussDefCmpw <limiter>          */
-    int32_t ddt;            /* ddtSchemes: RHEO_DDT_EULER                                */
+    int32_t ddt;            /* ddtSchemes: RHEO_DDT_EULER | RHEO_DDT_BACKWARD            */
     int32_t solver;         /* fvSolution solvers.theta.solver                           */
     double  tolerance;      /* fvSolution tolerance                                      */
     double  rel_tol;        /* fvSolution relTol                                         */

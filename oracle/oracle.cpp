@@ -89,7 +89,7 @@ struct Model {
 
 struct Mode {
     Model model;
-    dvec theta, thetaOld, tau, eigVals, eigVecs, thetaB, tauB;
+    dvec theta, thetaOld, thetaOldOld, tau, eigVals, eigVecs, thetaB, tauB;
 };
 
 struct Rank {
@@ -106,6 +106,9 @@ struct Case {
     bool sortEig = true;   // order eigenpairs ascending like Eigen::SelfAdjointEigenSolver (CE/constitutiveEq/constitutiveEq.C:390-414)
     int lastIters = 0;
     bool finalized = false;
+    // time levels (EXT-OF9 Time::deltaT0Value, GeometricField::nOldTimes): set by orc_store_old_time / orc_step
+    int nOldTimes = 0;       // store_old_time calls since the state was set
+    double dtNow = 0, dt0 = 0;
 };
 
 // patchNeighbourField of a cell field with nc components per cell (EXT-OF9 processorFvPatchField)
@@ -675,7 +678,7 @@ Perf pbicg(Ldu& A, DVec& psi, const DVec& source, const RheoSchemeCtl& ctl) {
 int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
     const int R = (int)cs.ranks.size();
     const RheoSchemeCtl& ctl = cs.ctl;
-    if (ctl.ddt != RHEO_DDT_EULER) { g_err = "oracle: only the Euler ddt scheme is restated"; return 3; }
+    if (ctl.ddt != RHEO_DDT_EULER && ctl.ddt != RHEO_DDT_BACKWARD) { g_err = "oracle: only the Euler and backward ddt schemes are restated"; return 3; }
     double aL[3] = {1, 1, 1}, bL[3] = {0, 0, 0}, bnd[2] = {1, 1};
     const bool hrs = limiter_table(ctl.limiter, aL, bL, bnd);
     const bool noConv = (ctl.limiter == RHEO_LIMITER_NONE);
@@ -724,6 +727,19 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
         rk.upper.assign(m.nInt, 0.0);
         rk.iC.assign(nB, 0.0);
         rk.bC.assign((size_t)6 * nB, 0.0);
+        if (ctl.ddt == RHEO_DDT_BACKWARD) {
+            // EXT-OF9 backwardDdtScheme<Type>::fvmDdt (static mesh): deltaT0 = great while the field has < 2 old times
+            const double deltaT0 = cs.nOldTimes < 2 ? 1e15 : cs.dt0;
+            const double coefft = 1 + dt / (dt + deltaT0);
+            const double coefft00 = dt * dt / (deltaT0 * (dt + deltaT0));
+            const double coefft0 = coefft + coefft00;
+            const dvec& oo = mo.thetaOldOld.empty() ? mo.thetaOld : mo.thetaOldOld;
+            for (int c = 0; c < n; ++c) {
+                rk.diag[c] = (coefft * rDeltaT) * m.V[c];
+                for (int q = 0; q < 6; ++q)
+                    rk.source[(size_t)6 * c + q] = rDeltaT * m.V[c] * (coefft0 * mo.thetaOld[(size_t)6 * c + q] - coefft00 * oo[(size_t)6 * c + q]);
+            }
+        } else
         for (int c = 0; c < n; ++c) {
             rk.diag[c] = rDeltaT * m.V[c];
             for (int q = 0; q < 6; ++q) rk.source[(size_t)6 * c + q] = rDeltaT * mo.thetaOld[(size_t)6 * c + q] * m.V[c];
@@ -1039,7 +1055,7 @@ int orc_set_state(void* h, int rank, int mode, const double* theta, const double
     Rank& rk = cs.ranks[rank];
     Mode& mo = rk.modes[mode];
     const size_t n = rk.mesh.nCells, nb = rk.mesh.nB();
-    if (theta) { mo.theta.assign(theta, theta + 6 * n); mo.thetaOld = mo.theta; }
+    if (theta) { mo.theta.assign(theta, theta + 6 * n); mo.thetaOld = mo.theta; mo.thetaOldOld = mo.theta; cs.nOldTimes = 0; }
     if (tau) mo.tau.assign(tau, tau + 6 * n);
     if (eigvals) mo.eigVals.assign(eigvals, eigvals + 9 * n);
     if (eigvecs) mo.eigVecs.assign(eigvecs, eigvecs + 9 * n);
@@ -1072,7 +1088,9 @@ int orc_set_velocity(void* h, int rank, const double* U, const double* Ub, const
 int orc_store_old_time(void* h) {
     Case& cs = *(Case*)h;
     for (Rank& rk : cs.ranks)
-        for (Mode& mo : rk.modes) mo.thetaOld = mo.theta;
+        for (Mode& mo : rk.modes) { mo.thetaOldOld = mo.thetaOld; mo.thetaOld = mo.theta; }
+    cs.nOldTimes++;
+    cs.dt0 = cs.dtNow;   // Time::operator++: deltaT0_ = deltaT_
     return 0;
 }
 
@@ -1081,6 +1099,7 @@ int orc_step(void* h, double dt, RheoStepStats* stats) {
     Case& cs = *(Case*)h;
     if (!cs.finalized) finalize(cs);
     cs.lastIters = 0;
+    cs.dtNow = dt;
     const int nm = (int)cs.ranks[0].modes.size();
     for (int mi = 0; mi < nm; ++mi) {
         int rc = correct_mode(cs, mi, dt, stats ? &stats[mi] : nullptr);

@@ -30,7 +30,7 @@ struct FluxArgs {
     int nU;               // 3: also compute grad(U) (first mode of a step), 0: not
     Limiter lim;
     int noConv;           // limiter `none`: no convection term at all
-    double rDeltaT, relax;
+    double rDeltaT, relax;   // rDeltaT: ddt diagonal coefficient per unit volume (Euler 1/dt; backward coefft/dt)
     int writeMatrix;      // first mode: write A, diag, rD
     const double* Fell;   // [nTiles][K][32] signed outflow flux per slot (patch slots: phi_b)
     const double* theta; const double* thetaB;
@@ -263,6 +263,8 @@ struct SourceArgs {
     int solvedIdx[6];       // component -> index among the solved components, -1 if not solved (2-D: xz, yz)
     const double* gradU; const double* theta; const double* thetaOld; const double* lam; const double* R;
     double* bsrc; double* fFene;
+    // EXT-OF9 backwardDdtScheme: source = (1/dt) V (c0 theta_old - c00 theta_oldold); Euler: (1/dt) theta_old V
+    int backward; double c0, c00; const double* thetaOldOld;
     // sum of theta over the cells per solved component (gAverage(psi) of the solver's normFactor): theta is in registers
     // here anyway, so the reduction rides along instead of being a kernel of its own
     double* sumPartials; double* sumOut; unsigned* counter;
@@ -296,7 +298,10 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, Sourc
         a.fFene[c] = f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {
-            a.bsrc[(size_t)k * m.NP + c] = (a.rDeltaT * thO[k] * V + V * rhs[k]) + own6[k];
+            double ddtSrc;
+            if (a.backward) ddtSrc = a.rDeltaT * V * (a.c0 * thO[k] - a.c00 * a.thetaOldOld[(size_t)k * m.NP + c]);
+            else ddtSrc = a.rDeltaT * thO[k] * V;
+            a.bsrc[(size_t)k * m.NP + c] = (ddtSrc + V * rhs[k]) + own6[k];
             sum[k] += th[k];
         }
     }

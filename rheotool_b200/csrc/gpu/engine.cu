@@ -88,7 +88,7 @@ struct DevBuf {
 struct ModeDev {
     RheoModelDesc desc;
     ModelParams mp;
-    DevBuf theta, thetaOld, tau, lam, R, fFene, bsrc, thetaB, tauB, gammaVals;
+    DevBuf theta, thetaOld, thetaOldOld, tau, lam, R, fFene, bsrc, thetaB, tauB, gammaVals;   // thetaOldOld: backward ddt only
     DevBuf corr;   // [nComp][K*NS] deferred face values received from the upwind neighbours (assembly.cuh)
 };
 
@@ -145,6 +145,9 @@ struct RheoGpu {
     void* peerBase[MAX_RANKS] = {};
     unsigned long long haloSeq = 0, arSeq = 0;
     // stats
+    // time levels (EXT-OF9 Time::deltaT0Value / GeometricField::nOldTimes), for the backward ddt scheme
+    int nOldTimes = 0;
+    double dtNow = 0, dt0 = 0;
     long launches = 0;
     long long h2dBytes = 0, d2hBytes = 0;   // host<->device bytes copied by the upload/download entry points
     int lastIters = 0;
@@ -516,9 +519,9 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         }
         if (md.theta.alloc(6 * NP * d8) || md.thetaOld.alloc(6 * NP * d8) || md.tau.alloc(6 * NP * d8) || md.lam.alloc(3 * NP * d8) ||
             md.R.alloc(9 * NP * d8) || md.fFene.alloc(NP * d8) || md.bsrc.alloc(6 * NP * d8) || md.thetaB.alloc(6 * nB * d8) || md.tauB.alloc(6 * nB * d8) ||
-            md.corr.alloc((size_t)h->nComp * h->K * h->NS * d8))
+            md.corr.alloc((size_t)h->nComp * h->K * h->NS * d8) || md.thetaOldOld.alloc(h->ctl.ddt == RHEO_DDT_BACKWARD ? 6 * NP * d8 : 0))
             return 1;
-        zero(h, md.corr);
+        zero(h, md.corr); zero(h, md.thetaOldOld);
         zero(h, md.theta); zero(h, md.thetaOld); zero(h, md.tau); zero(h, md.fFene); zero(h, md.bsrc); zero(h, md.thetaB); zero(h, md.tauB); zero(h, md.R);
         // READ_IF_PRESENT defaults: eigVals = eigVecs = I (Oldroyd_BLog.C:76-113)
         LAUNCH(h, k_fill, cdiv(3 * NP, BLOCK), BLOCK, 3 * NP, md.lam.as<double>(), 1.0);
@@ -746,7 +749,18 @@ template <class Kern> int flux_grid(RheoGpu* h, Kern kern, int threads, size_t s
 
 int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
-    if (h->ctl.ddt != RHEO_DDT_EULER) return fail("rheo_gpu_step: only the Euler ddt scheme is implemented");
+    if (h->ctl.ddt != RHEO_DDT_EULER && h->ctl.ddt != RHEO_DDT_BACKWARD) return fail("rheo_gpu_step: only the Euler and backward ddt schemes are implemented");
+    // EXT-OF9 backwardDdtScheme::fvmDdt: deltaT0 = great while the field has < 2 old times (first step = Euler)
+    h->dtNow = dt;
+    double ddtDiag = 1.0 / dt, c0 = 1.0, c00 = 0.0;
+    const bool backward = h->ctl.ddt == RHEO_DDT_BACKWARD;
+    if (backward) {
+        const double deltaT0 = h->nOldTimes < 2 ? 1e15 : h->dt0;
+        const double coefft = 1 + dt / (dt + deltaT0);
+        c00 = dt * dt / (deltaT0 * (dt + deltaT0));
+        c0 = coefft + c00;
+        ddtDiag = coefft * (1.0 / dt);
+    }
     if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB) return fail("rheo_gpu_step: only PBiCGStab is implemented on the device (fvSolution solver PBiCGStab)");
     const int N = h->N, NP = h->NP, grid = cdiv(N, BLOCK);
     const int nModes = (int)h->modes.size();
@@ -787,7 +801,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             for (int mi = g0; mi < g1; ++mi) {
                 ModeDev& md = h->modes[mi];
                 FluxArgs fa;
-                fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = rDeltaT; fa.relax = h->ctl.relax;
+                fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = ddtDiag; fa.relax = h->ctl.relax;
                 fa.writeMatrix = mi == 0 ? 1 : 0;
                 fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
                 fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
@@ -802,7 +816,8 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                     default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
                 }
                 SourceArgs sa;
-                sa.mp = md.mp; sa.rDeltaT = rDeltaT;
+                sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.backward = backward ? 1 : 0; sa.c0 = c0; sa.c00 = c00;
+                sa.thetaOldOld = backward ? md.thetaOldOld.as<double>() : md.thetaOld.as<double>();
                 for (int q = 0; q < 6; ++q) sa.solvedIdx[q] = -1;
                 for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
                 sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
@@ -969,7 +984,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
     for (ModeDev& md : h->modes)
-        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr}) b->release();
+        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld}) b->release();
     if (h->h_ks) cudaFreeHost(h->h_ks);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1013,6 +1028,8 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
     if (theta) {
         if (put_cells(h, theta, 6, md.theta.as<double>())) return 1;
         CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+        if (md.thetaOldOld.p) CK(cudaMemcpyAsync(md.thetaOldOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+        h->nOldTimes = 0;
     }
     if (tau && put_cells(h, tau, 6, md.tau.as<double>())) return 1;
     if (eigvals) {
@@ -1047,7 +1064,12 @@ int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, con
 int rheo_gpu_store_old_time(RheoGpu* h) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
-    for (ModeDev& md : h->modes) CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    for (ModeDev& md : h->modes) {
+        if (md.thetaOldOld.p) CK(cudaMemcpyAsync(md.thetaOldOld.p, md.thetaOld.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    h->nOldTimes++;
+    h->dt0 = h->dtNow;   // Time::operator++: deltaT0_ = deltaT_
     return 0;
 }
 
