@@ -247,19 +247,20 @@ __device__ __forceinline__ void jacobi_eig(const double* th6, double* d, double*
 }
 
 // tau from (R, Lambda); fOld = FENE-P / FENE-CR f computed before the solve (FENE_PLog.C:142,178; FENE_CRLog.C:141,174)
+template <int MODEL>
 __device__ __forceinline__ void tau_from_eig(const ModelParams& mp, const double* R, const double* lam, double fOld, double* tau6) {
     double A6[6];
     rdrt_sym(R, lam[0], lam[1], lam[2], A6);
     double coef = mp.etaP / mp.lambda;
-    if (mp.model == RHEO_MODEL_FENE_P_LOG) {
+    if (MODEL == RHEO_MODEL_FENE_P_LOG) {
         const double a = mp.L2 / (mp.L2 - 3.0);
         tau6[0] = coef * (fOld * A6[0] - a); tau6[1] = coef * (fOld * A6[1]); tau6[2] = coef * (fOld * A6[2]);
         tau6[3] = coef * (fOld * A6[3] - a); tau6[4] = coef * (fOld * A6[4]); tau6[5] = coef * (fOld * A6[5] - a);
     } else {
-        if (mp.model == RHEO_MODEL_PTT_LOG) coef = mp.etaP / (mp.lambda * (1.0 - mp.zeta));
-        if (mp.model == RHEO_MODEL_FENE_CR_LOG) coef = (mp.etaP / mp.lambda) * fOld;   // FENE_CRLog.C:174: f of BEFORE the solve
-        if (mp.model == RHEO_MODEL_WM_CY_LOG) coef = fOld;                              // WhiteMetznerCYLog.C:207: etaP/lambda of BEFORE the solve
-        if (mp.model == RHEO_MODEL_ROLIE_POLY_LOG && mp.rpChiMax > 1.0) {               // RoliePolyLog.C:203-212: finite extensibility, NEW tr(A)
+        if (MODEL == RHEO_MODEL_PTT_LOG) coef = mp.etaP / (mp.lambda * (1.0 - mp.zeta));
+        if (MODEL == RHEO_MODEL_FENE_CR_LOG) coef = (mp.etaP / mp.lambda) * fOld;   // FENE_CRLog.C:174: f of BEFORE the solve
+        if (MODEL == RHEO_MODEL_WM_CY_LOG) coef = fOld;                              // WhiteMetznerCYLog.C:207: etaP/lambda of BEFORE the solve
+        if (MODEL == RHEO_MODEL_ROLIE_POLY_LOG && mp.rpChiMax > 1.0) {               // RoliePolyLog.C:203-212: finite extensibility, NEW tr(A)
             const double trA = A6[0] + A6[3] + A6[5], c2 = mp.rpChiMax * mp.rpChiMax;
             coef *= ((3.0 - (trA / 3.0) / c2) * (1.0 - 1.0 / c2)) / ((1.0 - (trA / 3.0) / c2) * (3.0 - 1.0 / c2));
         }

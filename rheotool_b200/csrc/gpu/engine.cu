@@ -889,7 +889,20 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
 
     // ---- eig + exp + tau
     for (ModeDev& md : h->modes)
-        LAUNCH(h, k_eig_tau, grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>());
+    {
+#define RK_EIG(M) LAUNCH(h, (k_eig_tau<M>), grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>())
+        switch (md.mp.model) {
+            case RHEO_MODEL_OLDROYD_B_LOG: RK_EIG(RHEO_MODEL_OLDROYD_B_LOG); break;
+            case RHEO_MODEL_GIESEKUS_LOG: RK_EIG(RHEO_MODEL_GIESEKUS_LOG); break;
+            case RHEO_MODEL_PTT_LOG: RK_EIG(RHEO_MODEL_PTT_LOG); break;
+            case RHEO_MODEL_FENE_P_LOG: RK_EIG(RHEO_MODEL_FENE_P_LOG); break;
+            case RHEO_MODEL_FENE_CR_LOG: RK_EIG(RHEO_MODEL_FENE_CR_LOG); break;
+            case RHEO_MODEL_WM_CY_LOG: RK_EIG(RHEO_MODEL_WM_CY_LOG); break;
+            case RHEO_MODEL_ROLIE_POLY_LOG: RK_EIG(RHEO_MODEL_ROLIE_POLY_LOG); break;
+            default: RK_EIG(RHEO_MODEL_XPOMPOM_LOG); break;
+        }
+#undef RK_EIG
+    }
     if (h->timing) cudaEventRecord(h->ev[4], h->stream);
     // ---- theta BCs; tau.correctBoundaryConditions(): processor values first, then physical patches in order
     for (ModeDev& md : h->modes) {

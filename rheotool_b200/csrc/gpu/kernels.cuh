@@ -313,6 +313,7 @@ struct KrylovCtl {   // one per RHS, device resident
 };
 
 // ---------------------------------------------------------------- eig + exp + tau
+template <int MODEL>
 __global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp, const double* __restrict__ theta, const double* __restrict__ fFene,
                                                     double* __restrict__ lam, double* __restrict__ R, double* __restrict__ tau) {
     pdl_sync();
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp
     for (int k = 0; k < 6; ++k) th[k] = theta[(size_t)k * NP + c];
     jacobi_eig(th, d, V);
     l[0] = exp(d[0]); l[1] = exp(d[1]); l[2] = exp(d[2]);
-    tau_from_eig(mp, V, l, fFene[c], t6);
+    tau_from_eig<MODEL>(mp, V, l, fFene[c], t6);
 #pragma unroll
     for (int k = 0; k < 3; ++k) lam[(size_t)k * NP + c] = l[k];
 #pragma unroll

@@ -6,7 +6,7 @@
       WhiteMetznerCYLogGPU  Rolie-PolyLogGPU  XPomPomLogGPU  multiModeLogGPU
   Dictionary keys are those of the CPU models (Oldroyd_BLog.C:114-119,
   GiesekusLog.C:117, PTTLog.C:129-139, FENE_PLog.C:114-119, multiMode.C:73-92);
-  fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler,
+  fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler or backward,
   fvSolution solvers.theta<name> supplies tolerance/relTol/minIter/maxIter.
 \*---------------------------------------------------------------------------*/
 #include "of90_LogConformationGPU.H"
@@ -155,9 +155,10 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     const char* names[] = {"upwind", "cubista", "minmod", "smart", "waceb", "superbee", "none"};   // limiters.H:48-98
     ctl_.limiter = -1;
     for (int i = 0; i < 7; ++i) if (lim == names[i]) ctl_.limiter = i;
-    if (word(mesh.ddtScheme("ddt(" + thetaName + ")")) != "Euler")
-        FatalErrorInFunction << "only ddtSchemes Euler is available on the GPU path" << exit(FatalError);
-    ctl_.ddt = RHEO_DDT_EULER;
+    const word ddtName(mesh.ddtScheme("ddt(" + thetaName + ")"));
+    if (ddtName == "Euler") ctl_.ddt = RHEO_DDT_EULER;
+    else if (ddtName == "backward") ctl_.ddt = RHEO_DDT_BACKWARD;
+    else FatalErrorInFunction << "ddtSchemes Euler and backward are available on the GPU path, not " << ddtName << exit(FatalError);
     const dictionary& sol = mesh.solverDict(thetaName);
     const word solver(sol.lookup("solver"));
     // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs PBiCGStab
