@@ -127,6 +127,21 @@ GPU_SYMBOLS = {
     "rheo_gpu_abi_sizes": (C.c_int, [_P]),
 }
 
+IO_SYMBOLS = {
+    "rheo_io_read_polymesh": (_P, [C.c_char_p]),
+    "rheo_io_write_polymesh": (C.c_int, [_P, C.c_char_p, _I]),
+    "rheo_io_mesh_counts": (C.c_int, [_P, _P, _P]),
+    "rheo_io_patch_name": (C.c_int, [_P, _I, _P, _I]),
+    "rheo_io_set_patch_name": (C.c_int, [_P, _I, C.c_char_p]),
+    "rheo_io_read_field": (_P, [C.c_char_p]),
+    "rheo_io_field_free": (None, [_P]),
+    "rheo_io_field_info": (C.c_int, [_P, _P, _I, _P, _I, _P, _P, _P]),
+    "rheo_io_field_internal": (C.c_int, [_P, C.c_int64, _P]),
+    "rheo_io_field_patch": (C.c_int, [_P, C.c_char_p, _I, _P, _I, _P, _P]),
+    "rheo_io_apply_field_bcs": (C.c_int, [_P, _P, _I]),
+    "rheo_io_write_field": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _I, C.c_int64, _P, _I, _P, _P, _P, _P, _I]),
+}
+
 _lib = None
 
 
@@ -139,7 +154,7 @@ def lib() -> C.CDLL:
                 f"{_LIB_PATH} is missing: run `python -m rheotool_b200.build` (or __graft_entry__.build()). "
                 "There is no CPU fallback for the stress step.")
         L = C.CDLL(str(_LIB_PATH))
-        for name, (res, args) in {**MESH_SYMBOLS, **GPU_SYMBOLS}.items():
+        for name, (res, args) in {**MESH_SYMBOLS, **GPU_SYMBOLS, **IO_SYMBOLS}.items():
             fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

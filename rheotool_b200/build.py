@@ -66,7 +66,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
                 print(" ".join(cmd))
             _run(cmd)
     if force or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in objs):
-        cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl", "-lpthread"]
+        cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl", "-lpthread", "-lz"]
         if verbose:
             print(" ".join(cmd))
         _run(cmd)

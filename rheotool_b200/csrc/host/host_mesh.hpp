@@ -21,6 +21,12 @@ struct RheoHostMesh {
     std::vector<int8_t>  face_dir;      // per face: 0..5 = -x,+x,-y,+y,-z,+z seen from the owner
     std::vector<int32_t> global_cell;   // global cell id of each local cell (identity for whole mesh)
 
+    // --- polyMesh provenance (meshes read from disk; generated on demand for tensor grids): include/rheo_io.h ---
+    std::vector<double> points;            // 3 per point
+    std::vector<int32_t> face_start;       // n_faces + 1 offsets into face_pts
+    std::vector<int32_t> face_pts;
+    std::vector<std::string> patch_names;  // may be shorter than patches (unnamed: patch<i>)
+
     // --- decomposition provenance (EXT-OF9 cellProcAddressing / faceProcAddressing) ---
     std::vector<int32_t> cell_addr, face_addr;
 

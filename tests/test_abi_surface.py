@@ -28,7 +28,7 @@ def test_every_declared_symbol_is_exported_and_bound():
     out = subprocess.run(["nm", "-D", "--defined-only", str(abi.lib_path())], capture_output=True, text=True, check=True).stdout
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
     assert decl <= exported, f"declared but not exported: {sorted(decl - exported)}"
-    bound = set(abi.MESH_SYMBOLS) | set(abi.GPU_SYMBOLS)
+    bound = set(abi.MESH_SYMBOLS) | set(abi.GPU_SYMBOLS) | set(abi.IO_SYMBOLS)
     assert decl == bound, f"header / ctypes mismatch: {sorted(decl ^ bound)}"
     lib = abi.lib()
     for n in decl:

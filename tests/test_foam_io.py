@@ -1,0 +1,178 @@
+"""OpenFOAM on-disk formats (include/rheo_io.h).  Pins: the polyMesh the reference ships
+(tutorials/rheoFoam/Aneurysm/.../polyMesh.org: 4 files gzip + boundary) and every tau*/theta* field file of its tutorials —
+read in this container only (/root/reference does not exist on the GPU box: those tests skip there) — plus write/read
+round trips of generated meshes and fields, which run everywhere."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from rheotool_b200 import abi, cases, foamio, mesh
+
+REF = Path("/root/reference/of90/tutorials")
+ANEURYSM = REF / "rheoFoam/Aneurysm/HerschelBulkley/constant/polyMesh.org"
+GOLD = Path(__file__).parent / "golden" / "aneurysm_geometry.json"
+needs_ref = pytest.mark.skipif(not REF.exists(), reason="reference tree not present (GPU box)")
+
+
+def _geometry_summary(m):
+    nint = m.n_internal
+    # closedness: sum of outward face area vectors per cell
+    acc = np.zeros((m.n_cells, 3))
+    np.add.at(acc, m.owner, m.Sf)
+    np.subtract.at(acc, m.neighbour, m.Sf[:nint])
+    bnd = m.Sf[nint:]
+    return {
+        "n_cells": int(m.n_cells), "n_faces": int(m.n_faces), "n_internal_faces": int(nint),
+        "patches": [[n, int(p.type), int(p.start), int(p.size)] for n, p in zip(m.patch_names, m.patches)],
+        "volume": float(m.V.sum()),
+        "volume_by_divergence": float((m.Cf[nint:] * bnd).sum() / 3.0),
+        "min_volume": float(m.V.min()),
+        "max_open": float(np.abs(acc).max()),
+        "patch_area": [float(np.linalg.norm(m.Sf[p.start:p.start + p.size], axis=1).sum()) for p in m.patches],
+        "min_weight": float(m.weights[:nint].min()), "max_weight": float(m.weights[:nint].max()),
+    }
+
+
+@needs_ref
+def test_reference_aneurysm_polymesh_reads_and_is_a_valid_finite_volume_mesh():
+    m = foamio.read_polymesh(ANEURYSM)
+    s = _geometry_summary(m)
+    # the counts OpenFOAM itself recorded in the owner file header (note "nPoints:... nCells:...")
+    import gzip, re
+    head = gzip.open(ANEURYSM / "owner.gz", "rt").read(2000)
+    note = {k: int(v) for k, v in re.findall(r"(nPoints|nCells|nFaces|nInternalFaces):\s*(\d+)", head)}
+    assert (s["n_cells"], s["n_faces"], s["n_internal_faces"]) == (note["nCells"], note["nFaces"], note["nInternalFaces"])
+    assert foamio.mesh_counts(m)[0] == note["nPoints"]
+    assert s["patches"][0][0] == "walls" and [p[0] for p in s["patches"]] == ["walls", "out1", "in1", "out2"]
+    assert s["min_volume"] > 0
+    assert s["max_open"] < 1e-12 * s["patch_area"][0]                    # every cell is closed
+    assert s["volume"] == pytest.approx(s["volume_by_divergence"], rel=1e-10)   # Gauss: V = 1/3 sum Cf.Sf over the boundary
+    assert 0 < s["min_weight"] and s["max_weight"] < 1
+    gold = json.loads(GOLD.read_text())
+    for k in ("n_cells", "n_faces", "n_internal_faces", "patches"):
+        assert s[k] == gold[k]
+    for k in ("volume", "min_volume"):
+        assert s[k] == pytest.approx(gold[k], rel=1e-12)
+    assert s["patch_area"] == pytest.approx(gold["patch_area"], rel=1e-12)
+
+
+@needs_ref
+def test_every_tau_and_theta_file_of_the_reference_tutorials_parses():
+    files = sorted(p for p in REF.rglob("*") if p.is_file() and p.parent.name in ("0", "fluid") and (p.name.startswith("tau") or p.name.startswith("theta")))
+    assert len(files) >= 60
+    known = {"fixedValue", "zeroGradient", "linearExtrapolation", "empty", "symmetryPlane", "wedge", "symmetry", "cyclic", "calculated"}
+    n_regex = 0
+    for p in files:
+        f = foamio.FoamField(p)
+        assert f.cls in ("volSymmTensorField", "volTensorField", "volScalarField"), (p, f.cls)
+        v = f.internal(3)
+        assert v.shape == (3, f.n_comp) and np.isfinite(v).all()
+        txt = p.read_text()
+        # every boundaryField keyword resolves, regular-expression keys included
+        import re
+        body = txt[txt.index("boundaryField"):]
+        for key in re.findall(r'^\s*("[^"]+"|[A-Za-z_][\w.]*)\s*\n?\s*\{', body, flags=re.M):
+            if key == "boundaryField":
+                continue
+            if key.startswith('"'):
+                n_regex += 1
+                inner = key.strip('"').strip("()")
+                name = inner.split("|")[0].replace(".*", "x")
+            else:
+                name = key
+            ty, _ = f.patch(name, 2)
+            assert ty in known, (p, key, ty)
+    assert n_regex > 0
+
+
+def test_polymesh_write_read_round_trip_of_a_generated_mesh(tmp_path):
+    spec = cases.by_name("C3", 2 / 19)
+    m = mesh.tensor_grid(spec.grid)
+    foamio.write_polymesh(m, tmp_path / "polyMesh", gz=True)
+    assert (tmp_path / "polyMesh" / "points.gz").exists() and (tmp_path / "polyMesh" / "boundary").exists()
+    r = foamio.read_polymesh(tmp_path / "polyMesh")
+    assert (r.n_cells, r.n_faces, r.n_internal) == (m.n_cells, m.n_faces, m.n_internal)
+    assert np.array_equal(r.owner, m.owner) and np.array_equal(r.neighbour, m.neighbour)
+    assert r.patch_names == m.patch_names[: len(m.patches)]
+    assert [(p.type, p.start, p.size) for p in r.patches] == [(p.type, p.start, p.size) for p in m.patches]
+    # geometry recomputed from the points agrees with the generator's analytic geometry
+    for a, b in ((r.Sf, m.Sf), (r.Cf, m.Cf), (r.C, m.C)):
+        assert np.abs(a - b).max() < 1e-12
+    assert np.abs(r.V - m.V).max() < 1e-15 and np.abs(r.weights - m.weights).max() < 1e-12
+    # and a second write of the mesh that was READ reproduces the files bit for bit
+    foamio.write_polymesh(r, tmp_path / "again", gz=False)
+    foamio.write_polymesh(m, tmp_path / "first", gz=False)
+    for name in ("points", "faces", "owner", "neighbour", "boundary"):
+        assert (tmp_path / "again" / name).read_bytes() == (tmp_path / "first" / name).read_bytes(), name
+
+
+def test_field_write_read_round_trip_is_bit_exact_and_bcs_reach_the_mesh(tmp_path):
+    spec = cases.by_name("C2", 1 / 9)
+    m = mesh.tensor_grid(spec.grid)
+    rng = np.random.default_rng(5)
+    tau = rng.standard_normal((m.n_cells, 6)) * 10.0 ** rng.integers(-12, 6, (m.n_cells, 1))
+    patches = []
+    for name, p in zip(m.patch_names, m.patches):
+        if p.type == abi.PATCH_EMPTY:
+            patches.append((name, "empty", None))
+        elif p.type == abi.PATCH_WALL:
+            patches.append((name, "linearExtrapolation", rng.standard_normal((p.size, 6))))
+        elif name == m.patch_names[0]:
+            patches.append((name, "fixedValue", rng.standard_normal((p.size, 6))))
+        else:
+            patches.append((name, "zeroGradient", None))
+    for gz in (False, True):
+        path = tmp_path / ("gz" if gz else "plain") / "tau"
+        foamio.write_field(path, "tau", tau, patches, "[1 -1 -2 0 0 0 0]", gz=gz)
+        f = foamio.FoamField(path)
+        assert (f.cls, f.object, f.n_comp, f.internal_uniform, f.n_internal) == ("volSymmTensorField", "tau", 6, False, m.n_cells)
+        assert np.array_equal(f.internal(m.n_cells), tau)
+        for name, ty, vals in patches:
+            size = 0 if vals is None else len(vals)
+            t2, v2 = f.patch(name, size)
+            assert t2 == ty and (vals is None) == (v2 is None)
+            if vals is not None:
+                assert np.array_equal(v2, vals)
+        with pytest.raises(KeyError):
+            f.patch("noSuchPatch")
+        f.apply_bcs(m, "tau")
+        for (name, ty, _), p in zip(patches, m.patches):
+            assert p.tau_bc == {"empty": abi.BC_EMPTY, "linearExtrapolation": abi.BC_LINEAR_EXTRAPOLATION, "fixedValue": abi.BC_FIXED_VALUE,
+                                "zeroGradient": abi.BC_ZERO_GRADIENT}[ty]
+
+
+def test_regular_expression_keys_follow_openfoam_lookup_rules(tmp_path):
+    """exact keyword first; otherwise the LAST matching pattern (of90/tutorials/rheoFoam/Cylinder/Oldroyd-BLog/0/theta:33 style)."""
+    (tmp_path / "theta").write_text("""
+FoamFile { version 2.0; format ascii; class volSymmTensorField; object theta; }
+dimensions [0 0 0 0 0 0 0];
+internalField uniform (1 2 3 4 5 6);   // comment
+boundaryField
+{
+    ".*"                { type zeroGradient; }
+    "(walls|cylinder)"  { type fixedValue; value uniform (0 0 0 0 0 0); }
+    inlet               { type fixedValue; value nonuniform List<symmTensor> 2 ((1 0 0 1 0 1) (2 0 0 2 0 2)); }
+    /* block comment */
+    frontAndBack        { type empty; }
+}
+""")
+    f = foamio.FoamField(tmp_path / "theta")
+    assert f.internal_uniform and np.array_equal(f.internal(2), np.tile([1, 2, 3, 4, 5, 6.0], (2, 1)))
+    assert f.patch("outlet")[0] == "zeroGradient"
+    ty, v = f.patch("cylinder", 3)
+    assert ty == "fixedValue" and np.array_equal(v, np.zeros((3, 6)))
+    ty, v = f.patch("inlet", 2)
+    assert ty == "fixedValue" and np.array_equal(v, [[1, 0, 0, 1, 0, 1], [2, 0, 0, 2, 0, 2.0]])
+    assert f.patch("frontAndBack")[0] == "empty"
+    with pytest.raises(foamio.FoamError):
+        f.patch("inlet", 3)            # value list does not match the patch size
+
+
+def test_errors_name_the_file_and_the_problem(tmp_path):
+    with pytest.raises(foamio.FoamError, match="cannot read"):
+        foamio.read_polymesh(tmp_path / "nothing")
+    (tmp_path / "bad").write_text("FoamFile { class volSymmTensorField; object x; } internalField uniform (1 2 3); boundaryField { }")
+    with pytest.raises(foamio.FoamError, match="components"):
+        foamio.FoamField(tmp_path / "bad")

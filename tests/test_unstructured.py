@@ -1,0 +1,94 @@
+"""The stress step on an UNSTRUCTURED polyhedral mesh: a 3,000-cell piece of the polyMesh the reference ships
+(tests/golden/aneurysm_patch, cut by tools/make_fixture_aneurysm_patch.py around a snappyHexMesh refinement transition and
+read through rheo_io_read_polymesh).
+Tensor grids only ever have 4 or 6 slots per cell and 2 colours; this mesh drives the generic paths: run-time slot
+count (KT = 0 kernels), more than two DILU colours, cells with different numbers of faces, zero-size patches."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import rel_l2, tight
+from oracle import mesh_ref
+from oracle import oracle as orc
+from rheotool_b200 import abi, cases, foamio
+
+FIXTURE = Path(__file__).parent / "golden" / "aneurysm_patch"
+
+
+def _case():
+    m = foamio.read_polymesh(FIXTURE)
+    # BCs as in the reference's viscoelastic tutorials: walls zeroGradient theta / linearExtrapolation tau; the cut surface
+    # (in- and outflow) holds fixedValue theta
+    bc = {"walls": (abi.BC_ZERO_GRADIENT, abi.BC_LINEAR_EXTRAPOLATION), "cut": (abi.BC_FIXED_VALUE, abi.BC_ZERO_GRADIENT)}
+    for name, p in zip(m.patch_names, m.desc.patches[: m.desc.n_patches]):
+        p.theta_bc, p.tau_bc = bc.get(name, (abi.BC_ZERO_GRADIENT, abi.BC_ZERO_GRADIENT))
+    c0, L = m.C.mean(0), np.ptp(m.C, axis=0).max()
+
+    def vel(x):
+        s = (x - c0) / L * 3.0
+        return np.stack([0.8 + 0.3 * np.sin(s[:, 1]), 0.4 * np.cos(s[:, 0] + s[:, 2]), 0.5 * np.sin(s[:, 0]) * np.cos(s[:, 1])], axis=1)
+
+    U, Ub = vel(m.C), vel(m.Cf[m.n_internal:])
+    phi = (vel(m.Cf) * m.Sf).sum(1)
+    s = (m.C - c0) / L * 4.0
+    S = np.stack([0.4 * np.sin(s[:, 0]), 0.2 * np.cos(s[:, 1]), 0.1 * np.sin(s[:, 2]), -0.3 * np.cos(s[:, 0] + s[:, 1]), 0.15 * np.sin(s[:, 1] - s[:, 2]),
+                  0.25 * np.cos(s[:, 2])], axis=1)
+    rng = np.random.default_rng(12345)
+    theta0 = S + 0.05 * (rng.random(S.shape) - 0.5)
+    sb = (m.Cf[m.n_internal:] - c0) / L * 4.0
+    thetaB = np.stack([0.4 * np.sin(sb[:, 0]), 0.2 * np.cos(sb[:, 1]), 0.1 * np.sin(sb[:, 2]), -0.3 * np.cos(sb[:, 0] + sb[:, 1]),
+                       0.15 * np.sin(sb[:, 1] - sb[:, 2]), 0.25 * np.cos(sb[:, 2])], axis=1)
+    dt = 0.2 / m.max_courant_rate(phi)
+    models = [cases.model_desc("GiesekusLog", rho=1.0, etaS=0.01, etaP=0.99, lambda_=200 * dt, alpha=0.2)]
+    return m, models, U, Ub, phi, theta0, thetaB, dt
+
+
+def _oracle(m, models, sc, U, Ub, phi, theta0, thetaB):
+    oc = orc.OracleCase([m.desc], models, sc)
+    vals, vecs = orc.calc_eig(theta0)
+    oc.set_state(0, 0, theta0, np.zeros_like(theta0), vals, vecs, theta_b=thetaB)
+    oc.set_velocity(0, U, Ub, phi)
+    return oc, vals, vecs
+
+
+def test_fixture_is_an_unstructured_mesh_and_the_oracle_runs_on_it():
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
+    assert (m.n_cells, m.n_internal) == (3000, 8375)
+    assert m.patch_names == ["walls", "out1", "in1", "out2", "cut"] and [p.size for p in m.patches] == [60, 0, 0, 0, 2069]
+    acc = np.zeros((m.n_cells, 3))
+    np.add.at(acc, m.owner, m.Sf); np.subtract.at(acc, m.neighbour, m.Sf[: m.n_internal])
+    assert np.abs(acc).max() < 1e-12 * np.linalg.norm(m.Sf, axis=1).max() and m.V.min() > 0
+    faces_per_cell = np.bincount(m.owner, minlength=m.n_cells) + np.bincount(m.neighbour, minlength=m.n_cells)
+    assert len(set(faces_per_cell.tolist())) >= 5 and faces_per_cell.max() == 21   # hexahedra and 9..21-faced transition polyhedra
+    perm, colour, cstart = mesh_ref.colour_renumber(m.n_cells, m.owner[: m.n_internal], m.neighbour)
+    assert len(cstart) - 1 > 2
+    sc = tight(cases.scheme_ctl("cubista", "PBiCGStab", 1e-10))
+    oc, _, _ = _oracle(m, models, sc, U, Ub, phi, theta0, thetaB)
+    for _ in range(3):
+        oc.store_old_time(); oc.step(dt)
+    th = oc.get(0, 0, abi.FIELD_THETA)
+    assert np.isfinite(th).all() and 1e-4 < rel_l2(th, theta0) < 0.5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("limiter", ["cubista", "upwind"])
+def test_gpu_matches_oracle_on_the_unstructured_mesh(limiter):
+    from rheotool_b200.stress import GpuStressModel
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
+    sc = tight(cases.scheme_ctl(limiter, "PBiCGStab", 1e-10))
+    oc, vals, vecs = _oracle(m, models, sc, U, Ub, phi, theta0, thetaB)
+    g = GpuStressModel(m, models, sc)
+    g.upload_state(0, theta0, np.zeros_like(theta0), vals, vecs, theta_b=thetaB)
+    g.upload_velocity(U, Ub, phi)
+    _, cstart = g.renumbering()
+    assert len(cstart) - 1 > 2
+    for n in range(5):
+        oc.store_old_time(); oc.step(dt)
+        g.store_old_time(); g.correct(dt)
+        if n == 0:
+            assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-10
+            assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-10
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-8
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
+    assert rel_l2(g.download(abi.FIELD_TAU_B), oc.get(0, 0, abi.FIELD_TAU_B)) <= 1e-8
