@@ -1059,13 +1059,13 @@ int orc_set_state(void* h, int rank, int mode, const double* theta, const double
     if (tau) mo.tau.assign(tau, tau + 6 * n);
     if (eigvals) mo.eigVals.assign(eigvals, eigvals + 9 * n);
     if (eigvecs) mo.eigVecs.assign(eigvecs, eigvecs + 9 * n);
+    // EXT-OF9 zeroGradientFvPatchField(p, iF, dict): the constructor evaluates (value = patchInternalField), whatever the
+    // file's `value` entry says — so a zeroGradient patch never keeps caller-supplied boundary values
     if (theta_b) mo.thetaB.assign(theta_b, theta_b + 6 * nb);
-    else {
-        for (const Patch& p : rk.mesh.patches)
-            if (p.theta_bc == RHEO_BC_ZERO_GRADIENT && p.type != RHEO_PATCH_EMPTY)
-                for (int f = p.start; f < p.start + p.size; ++f)
-                    for (int q = 0; q < 6; ++q) mo.thetaB[6 * (size_t)(f - rk.mesh.nInt) + q] = mo.theta[6 * (size_t)rk.mesh.own[f] + q];
-    }
+    for (const Patch& p : rk.mesh.patches)
+        if (p.theta_bc == RHEO_BC_ZERO_GRADIENT && p.type != RHEO_PATCH_EMPTY)
+            for (int f = p.start; f < p.start + p.size; ++f)
+                for (int q = 0; q < 6; ++q) mo.thetaB[6 * (size_t)(f - rk.mesh.nInt) + q] = mo.theta[6 * (size_t)rk.mesh.own[f] + q];
     if (tau_b) mo.tauB.assign(tau_b, tau_b + 6 * nb);
     else {
         for (const Patch& p : rk.mesh.patches)

@@ -339,18 +339,20 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, Sourc
     if (threadIdx.x == 0) *a.counter = 0;
 }
 
-// theta.correctBoundaryConditions() and the zeroGradient part of tau.correctBoundaryConditions() in one launch:
-// zeroGradient patch value = internal value
+// theta.correctBoundaryConditions() (theta != nullptr: every zeroGradient face) and the zeroGradient faces of tau in the
+// boundary-face range [t0, t1) in one launch: zeroGradient patch value = internal value.  tau's patches are evaluated in
+// patch order (EXT-OF9 GeometricBoundaryField::evaluate), so zeroGradient patches that FOLLOW a linearExtrapolation patch
+// are updated after it — the caller passes the ranges accordingly.
 __global__ void k_bc_zero_gradient2(MeshView m, const double* __restrict__ theta, double* __restrict__ thetaB, const double* __restrict__ tau,
-                                    double* __restrict__ tauB) {
+                                    double* __restrict__ tauB, int t0, int t1) {
     pdl_sync();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= m.nB) return;
     if (m.bkind[b] == RHEO_PATCH_EMPTY) return;
     const int c = m.bcell[b];
-    if (m.bthetaBC[b] == RHEO_BC_ZERO_GRADIENT)
+    if (theta != nullptr && m.bthetaBC[b] == RHEO_BC_ZERO_GRADIENT)
         for (int k = 0; k < 6; ++k) thetaB[(size_t)k * m.nB + b] = theta[(size_t)k * m.NP + c];
-    if (m.btauBC[b] == RHEO_BC_ZERO_GRADIENT)
+    if (b >= t0 && b < t1 && m.btauBC[b] == RHEO_BC_ZERO_GRADIENT)
         for (int k = 0; k < 6; ++k) tauB[(size_t)k * m.nB + b] = tau[(size_t)k * m.NP + c];
 }
 

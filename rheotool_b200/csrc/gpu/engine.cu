@@ -907,12 +907,33 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     // ---- theta BCs; tau.correctBoundaryConditions(): processor values first, then physical patches in order
     for (ModeDev& md : h->modes) {
         if (h->H && halo_planes(h, md.tau.as<double>(), 6)) return 1;
-        if (h->nB) LAUNCH(h, k_bc_zero_gradient2, cdiv(h->nB, BLOCK), BLOCK, h->mv, md.theta.as<double>(), md.thetaB.as<double>(), md.tau.as<double>(), md.tauB.as<double>());
-        for (const RheoPatchDesc& p : h->patches) {
-            if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR || p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION || p.size == 0) continue;
-            const int b0 = p.start - h->nInt;
-            LAUNCH(h, k_tau_bc_linext, cdiv(p.size, 128), 128, h->mv, b0, p.size, md.tau.as<double>(), md.tauB.as<double>(), h->d_tmpB.as<double>());
-            LAUNCH(h, k_tau_bc_commit, cdiv(p.size, 128), 128, h->nB, b0, p.size, h->d_tmpB.as<double>(), md.tauB.as<double>());
+        // patches in patch (= face) order, as EXT-OF9 GeometricBoundaryField::evaluate visits them: a linearExtrapolation
+        // patch sees the values of the patches before it already updated and of those after it still old.  Consecutive
+        // non-linearExtrapolation patches are one launch; the first launch also refreshes theta's zeroGradient faces.
+        if (h->nB) {
+            std::vector<const RheoPatchDesc*> ordered;
+            for (const RheoPatchDesc& p : h->patches) ordered.push_back(&p);
+            std::sort(ordered.begin(), ordered.end(), [](const RheoPatchDesc* a, const RheoPatchDesc* b) { return a->start < b->start; });
+            bool thetaDone = false, pending = false;   // pending: a zeroGradient tau patch lies in [z0, current)
+            int z0 = 0;   // first boundary face whose zeroGradient tau value has not been refreshed yet
+            auto flush = [&](int z1) {
+                if (pending || !thetaDone)
+                    LAUNCH(h, k_bc_zero_gradient2, cdiv(h->nB, BLOCK), BLOCK, h->mv, thetaDone ? (const double*)nullptr : md.theta.as<double>(), md.thetaB.as<double>(),
+                           md.tau.as<double>(), md.tauB.as<double>(), z0, z1);
+                thetaDone = true; pending = false;
+                z0 = z1;
+            };
+            for (const RheoPatchDesc* pp : ordered) {
+                const RheoPatchDesc& p = *pp;
+                if (p.type != RHEO_PATCH_EMPTY && p.type != RHEO_PATCH_PROCESSOR && p.tau_bc == RHEO_BC_ZERO_GRADIENT && p.size > 0) pending = true;
+                if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR || p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION || p.size == 0) continue;
+                const int b0 = p.start - h->nInt;
+                flush(b0);
+                LAUNCH(h, k_tau_bc_linext, cdiv(p.size, 128), 128, h->mv, b0, p.size, md.tau.as<double>(), md.tauB.as<double>(), h->d_tmpB.as<double>());
+                LAUNCH(h, k_tau_bc_commit, cdiv(p.size, 128), 128, h->nB, b0, p.size, h->d_tmpB.as<double>(), md.tauB.as<double>());
+                z0 = b0 + p.size;
+            }
+            flush(h->nB);
         }
     }
     if (h->timing) {
