@@ -119,7 +119,7 @@ struct RheoGpu {
     std::vector<std::pair<int, int>> ubRanges, phiBRanges;
     // device mesh
     DevBuf d_perm, d_faceOld, d_nbr, d_nbrA, d_fidx, d_Sf, d_w, d_C, d_V, d_rV, d_bcell, d_bkind, d_bthetaBC, d_btauBC, d_CfB;
-    DevBuf d_haloCell, d_segStart, d_segLen, d_send, d_recv;
+    DevBuf d_haloCell, d_send, d_recv;
     DevBuf d_tileRec;              // per-tile mesh records streamed by k_flux_assemble (assembly.cuh)
     int nTiles = 0;
     MeshView mv;
@@ -293,7 +293,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     for (int f = nInt; f < nF; ++f) { h->faceOld[f] = f + 1; newOwn[f] = iperm[d->owner[f]]; }
 
     // ---- ghosts: one per processor face, in patch order
-    std::vector<int> ghostOfB(nB, -1), haloCell, segStart, segLen;
+    std::vector<int> ghostOfB(nB, -1), haloCell;
     std::vector<int> bkind(nB, RHEO_PATCH_EMPTY), bthetaBC(nB, RHEO_BC_EMPTY), btauBC(nB, RHEO_BC_EMPTY), bcell(nB);
     int H = 0;
     for (const RheoPatchDesc& p : h->patches) {
@@ -305,8 +305,6 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
             if (p.type == RHEO_PATCH_PROCESSOR) {
                 ghostOfB[b] = H;
                 haloCell.push_back(newOwn[f]);
-                segStart.push_back(h->segs.back().h0);
-                segLen.push_back(p.size);
                 ++H;
             } else if (p.type != RHEO_PATCH_EMPTY) {
                 if (p.theta_bc != RHEO_BC_FIXED_VALUE && p.theta_bc != RHEO_BC_ZERO_GRADIENT)
@@ -460,8 +458,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     if (upload(h->d_perm, h->perm) || upload(h->d_faceOld, h->faceOld) || upload(h->d_nbr, h->h_nbr) || upload(h->d_nbrA, nbrA) ||
         upload(h->d_fidx, h->h_fidx) || upload(h->d_Sf, Sf) || upload(h->d_w, w) || upload(h->d_C, C) || upload(h->d_V, V) ||
         upload(h->d_rV, rV) || upload(h->d_bcell, bcell) || upload(h->d_bkind, bkind) || upload(h->d_bthetaBC, bthetaBC) ||
-        upload(h->d_btauBC, btauBC) || upload(h->d_CfB, CfB) || upload(h->d_haloCell, haloCell) || upload(h->d_segStart, segStart) ||
-        upload(h->d_segLen, segLen))
+        upload(h->d_btauBC, btauBC) || upload(h->d_CfB, CfB) || upload(h->d_haloCell, haloCell))
         return 1;
     MeshView& m = h->mv;
     m.N = N; m.H = H; m.NT = h->NT; m.NS = h->NS; m.NP = h->NP; m.K = K; m.nInt = nInt; m.nF = nF; m.nB = nB;
@@ -1012,7 +1009,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
     for (int r = 0; r < MAX_RANKS; ++r) if (r != h->rank && h->peerBase[r]) cudaIpcCloseMemHandle(h->peerBase[r]);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
-                      &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_segStart, &h->d_segLen, &h->d_send, &h->d_recv,
+                      &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})

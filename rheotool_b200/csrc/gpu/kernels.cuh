@@ -77,28 +77,6 @@ __device__ __forceinline__ void block_reduce_to_partials(double (&v)[NV], double
     __syncthreads();
 }
 
-__device__ __forceinline__ void finalize_partials(const double* partials, int nSlots, double* out, unsigned* counter) {
-    __shared__ bool isLast;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned t = atomicAdd(counter, 1u);
-        isLast = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!isLast) return;
-    __threadfence();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int s = warp; s < nSlots; s += BLOCK / 32) {
-        double x = 0;
-        for (unsigned b = lane; b < gridDim.x; b += 32) x += partials[(size_t)b * nSlots + s];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) out[s] = x;
-    }
-    if (threadIdx.x == 0) *counter = 0;
-}
-
 // ---------------------------------------------------------------- layout transforms (upload / download)
 // AoS in the caller's numbering -> SoA planes in device numbering
 __global__ void k_aos_to_soa(int n, int nc, const int* __restrict__ perm, const double* __restrict__ aos, double* __restrict__ soa, int stride) {
@@ -151,12 +129,6 @@ __global__ void k_fill(size_t n, double* p, double v) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
-__global__ void k_copy(size_t n, const double* __restrict__ s, double* __restrict__ d) {
-    pdl_sync();
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) d[i] = s[i];
-}
-
 // ---------------------------------------------------------------- halo pack / unpack
 // record layout: buf[h * n + p] for ghost h and plane p (a neighbour's segment is a contiguous range of h)
 struct PlaneList { int n; double* p[MAX_RHS]; };

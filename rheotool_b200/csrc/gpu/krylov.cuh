@@ -230,26 +230,8 @@ __device__ __forceinline__ void finalize_ctl(const double* partials, int nBlocks
 // All kernels below are persistent-style: a bounded grid (a few CTAs per SM) strides over the cells, so the
 // block reduction / last-block epilogue is paid once per CTA instead of once per 256 cells.
 
-// ---------------------------------------------------------------- sum(psi) for gAverage
-template <int NR>
-__global__ void __launch_bounds__(BLOCK) k_sum_psi(int N, int nModes, RhsPtrs rp, double* partials, double* out, unsigned* counter) {
-    pdl_sync();
-    const int stride = gridDim.x * BLOCK;
-    for (int md = 0; md < nModes; ++md) {
-        double v[NR];
-#pragma unroll
-        for (int j = 0; j < NR; ++j) v[j] = 0.0;
-        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < N; c += stride) {
-#pragma unroll
-            for (int j = 0; j < NR; ++j) v[j] += rp.psi[md * NR + j][c];
-        }
-        block_reduce_to_partials<NR>(v, partials, md * NR, nModes * NR);
-    }
-    SolveCtl sc{};
-    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, CTL_NONE, nullptr, 0, sc);
-}
-
 // ---------------------------------------------------------------- initial residual
+// gAverage(psi): the per-component sums of theta arrive in sumPsi (accumulated by k_cell_source2, assembly.cuh)
 // v = A psi (ghost columns included: psi halos are exchanged before), r = b - v, r0 = r
 // sums per RHS: [0] |v - xRef rowsum| + |b - xRef rowsum|, [1] |r|, [2] r.r
 template <int NR, int KT>
