@@ -110,3 +110,96 @@ def write_field(path, obj: str, internal: np.ndarray, patches: list, dimensions:
     if abi.lib().rheo_io_write_field(str(path).encode(), CLASS_OF_NCOMP[nc].encode(), obj.encode(), dimensions.encode(), nc, len(a),
                                      a.ctypes.data_as(C.c_void_p), len(patches), names, types, sizes, vals, 1 if gz else 0):
         raise FoamError(_err())
+
+
+# ---------------------------------------------------------------- whole cases (constant/polyMesh + a time directory)
+BC_WORD = {abi.BC_FIXED_VALUE: "fixedValue", abi.BC_ZERO_GRADIENT: "zeroGradient", abi.BC_LINEAR_EXTRAPOLATION: "linearExtrapolation",
+           abi.BC_EMPTY: "empty", abi.BC_PROCESSOR: "processor"}
+DIMENSIONS = {"tau": "[1 -1 -2 0 0 0 0]", "U": "[0 1 -1 0 0 0 0]"}
+
+
+def surface_flux(m: HostMesh, U: np.ndarray, U_b: np.ndarray) -> np.ndarray:
+    """phi = linearInterpolate(U) & Sf  (what createPhi.H computes for an incompressible solver: EXT-OF9
+    surfaceInterpolationScheme::interpolate, w U_P + (1 - w) U_N on internal faces, patch values on the boundary)."""
+    n = m.n_internal
+    w = m.weights[:n, None]
+    Uf = w * (U[m.owner[:n]] - U[m.neighbour]) + U[m.neighbour]
+    return np.concatenate([(Uf * m.Sf[:n]).sum(1), (U_b * m.Sf[n:]).sum(1)])
+
+
+def write_case(case_dir, m: HostMesh, time: str, theta, tau, U, U_b, theta_b=None, tau_b=None, eigvals=None, eigvecs=None, name: str = "", gz: bool = False):
+    """constant/polyMesh + <time>/{U, theta<name>, tau<name>[, eigVals<name>, eigVecs<name>]} as rheoFoam reads / writes them
+    (CE/Oldroyd-B/Oldroyd-BLog/Oldroyd_BLog.C:52-113).  Boundary types come from the mesh's patch kinds and theta/tau BCs."""
+    case_dir = Path(case_dir)
+    write_polymesh(m, case_dir / "constant" / "polyMesh", gz=gz)
+    nint = m.n_internal
+
+    def patches(bc_of, values, fixed_word="fixedValue"):
+        out = []
+        for pname, p in zip(m.patch_names, m.patches):
+            sl = slice(p.start - nint, p.start - nint + p.size)
+            if p.type == abi.PATCH_EMPTY:
+                out.append((pname, "empty", None))
+            elif p.type == abi.PATCH_PROCESSOR:
+                out.append((pname, "processor", None if values is None else values[sl]))
+            else:
+                word = BC_WORD[bc_of(p)] if bc_of else fixed_word
+                has_value = word in ("fixedValue", "linearExtrapolation")
+                out.append((pname, word, values[sl] if (has_value and values is not None) else None))
+        return out
+
+    tdir = case_dir / time
+    write_field(tdir / "U", "U", U, patches(None, U_b), DIMENSIONS["U"], gz=gz)
+    nb = m.n_boundary
+    write_field(tdir / f"theta{name}", f"theta{name}", theta, patches(lambda p: p.theta_bc, theta_b if theta_b is not None else np.zeros((nb, 6))), gz=gz)
+    write_field(tdir / f"tau{name}", f"tau{name}", tau, patches(lambda p: p.tau_bc, tau_b if tau_b is not None else np.zeros((nb, 6))), DIMENSIONS["tau"], gz=gz)
+    calc = [(pname, "empty" if p.type == abi.PATCH_EMPTY else "zeroGradient", None) for pname, p in zip(m.patch_names, m.patches)]
+    if eigvals is not None:
+        write_field(tdir / f"eigVals{name}", f"eigVals{name}", eigvals, calc, gz=gz)
+    if eigvecs is not None:
+        write_field(tdir / f"eigVecs{name}", f"eigVecs{name}", eigvecs, calc, gz=gz)
+
+
+def read_case(case_dir, time: str, name: str = ""):
+    """-> (mesh with theta/tau BCs set from the field files, dict of arrays: U, U_b, phi, theta, theta_b, tau, tau_b, eigvals, eigvecs).
+    eigVals/eigVecs are READ_IF_PRESENT (None when absent: the model then starts from the identity, Oldroyd_BLog.C:76-113)."""
+    case_dir = Path(case_dir)
+    m = read_polymesh(case_dir / "constant" / "polyMesh")
+    tdir = case_dir / time
+    nint, nb = m.n_internal, m.n_boundary
+
+    def load(fname, ncomp, required=True):
+        path = tdir / fname
+        if not (path.exists() or Path(str(path) + ".gz").exists()):
+            if required:
+                raise FoamError(f"{path}: MUST_READ field is missing")
+            return None, None, None
+        f = FoamField(path)
+        if f.n_comp != ncomp:
+            raise FoamError(f"{path}: class {f.cls} where {CLASS_OF_NCOMP[ncomp]} is expected")
+        internal = f.internal(m.n_cells)
+        bvals = np.zeros((nb, ncomp))
+        for pname, p in zip(m.patch_names, m.patches):
+            if p.type == abi.PATCH_EMPTY or p.size == 0:
+                continue
+            _, v = f.patch(pname, p.size)
+            if v is not None:
+                bvals[p.start - nint: p.start - nint + p.size] = v
+        return f, internal, bvals
+
+    fU, U, U_b = load("U", 3)
+    fth, theta, theta_b = load(f"theta{name}", 6)
+    fta, tau, tau_b = load(f"tau{name}", 6)
+    fth.apply_bcs(m, "theta")
+    fta.apply_bcs(m, "tau")
+    _, eigvals, _ = load(f"eigVals{name}", 9, required=False)
+    _, eigvecs, _ = load(f"eigVecs{name}", 9, required=False)
+    # velocity on patches without a value entry (zeroGradient outlets): the internal value
+    for pname, p in zip(m.patch_names, m.patches):
+        if p.type == abi.PATCH_EMPTY or p.size == 0:
+            continue
+        ty, v = fU.patch(pname, p.size)
+        if v is None:
+            U_b[p.start - nint: p.start - nint + p.size] = U[m.owner[p.start: p.start + p.size]]
+    return m, {"U": U, "U_b": U_b, "phi": surface_flux(m, U, U_b), "theta": theta, "theta_b": theta_b, "tau": tau, "tau_b": tau_b,
+               "eigvals": eigvals, "eigvecs": eigvecs}
