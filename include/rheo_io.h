@@ -31,6 +31,9 @@ RheoHostMesh* rheo_io_read_polymesh(const char* dir);
 int rheo_io_write_polymesh(const RheoHostMesh* m, const char* dir, int32_t gz);
 /* nPoints / nFaces-with-points of the mesh (0 when the mesh carries no points), patch names */
 int rheo_io_mesh_counts(const RheoHostMesh* m, int64_t* n_points, int64_t* n_face_points);
+/* processor patches of a mesh read from a processorN directory: the cell centres across the patch (what the neighbour rank
+ * would send at start-up) — also recomputes the patch's interpolation weights (EXT-OF9 makeWeights on coupled patches) */
+int rheo_io_set_nbr_centres(RheoHostMesh* m, int32_t patch, const double* centres3);
 int rheo_io_patch_name(const RheoHostMesh* m, int32_t patch, char* buf, int32_t buflen);
 int rheo_io_set_patch_name(RheoHostMesh* m, int32_t patch, const char* name);
 

@@ -131,6 +131,7 @@ IO_SYMBOLS = {
     "rheo_io_read_polymesh": (_P, [C.c_char_p]),
     "rheo_io_write_polymesh": (C.c_int, [_P, C.c_char_p, _I]),
     "rheo_io_mesh_counts": (C.c_int, [_P, _P, _P]),
+    "rheo_io_set_nbr_centres": (C.c_int, [_P, _I, _P]),
     "rheo_io_patch_name": (C.c_int, [_P, _I, _P, _I]),
     "rheo_io_set_patch_name": (C.c_int, [_P, _I, C.c_char_p]),
     "rheo_io_read_field": (_P, [C.c_char_p]),

@@ -123,6 +123,23 @@ RheoHostMesh* rheo_mesh_decompose(const RheoHostMesh* m, const int32_t* c2r, int
     }
     s->n_faces = (int32_t)s->owner.size();
     s->nbr_C = nbrC_tmp;
+    s->my_rank = rank;
+    for (size_t p = 0; p < m->patches.size() && p < m->patch_names.size(); ++p) s->patch_names.push_back(m->patch_names[p]);
+    if (!m->points.empty()) {   // polyMesh provenance: the sub-mesh's faces are the parent's (reversed where this side is the neighbour)
+        std::vector<int32_t> pid(m->points.size() / 3, -1);
+        s->face_start.assign(1, 0);
+        for (int32_t fa : s->face_addr) {
+            const int32_t gf = (fa > 0 ? fa : -fa) - 1;
+            const int32_t b = m->face_start[gf], e = m->face_start[gf + 1];
+            for (int32_t q = 0; q < e - b; ++q) {
+                // a flipped face keeps its first point and reverses the rest (EXT-OF9 face::reverseFace)
+                const int32_t gp = m->face_pts[fa > 0 ? b + q : (q == 0 ? b : e - q)];
+                if (pid[gp] < 0) { pid[gp] = (int32_t)(s->points.size() / 3); for (int c = 0; c < 3; ++c) s->points.push_back(m->points[3 * (size_t)gp + c]); }
+                s->face_pts.push_back(pid[gp]);
+            }
+            s->face_start.push_back((int32_t)s->face_pts.size());
+        }
+    }
     s->C.resize(3 * (size_t)s->n_cells);
     s->V.resize((size_t)s->n_cells);
     for (int32_t c = 0; c < s->n_cells; ++c) {

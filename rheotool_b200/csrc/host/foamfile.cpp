@@ -247,6 +247,8 @@ bool patch_bc_code(const std::string& type, int32_t& code) {
 
 std::string patch_name_of(const RheoHostMesh* m, int p) {
     if (p < (int)m->patch_names.size() && !m->patch_names[p].empty()) return m->patch_names[p];
+    if (m->patches[p].type == RHEO_PATCH_PROCESSOR)   // EXT-OF9 processorPolyPatch::newName
+        return "procBoundary" + std::to_string(std::max(m->my_rank, 0)) + "to" + std::to_string(m->patches[p].nbr_rank);
     return "patch" + std::to_string(p);
 }
 
@@ -332,6 +334,9 @@ RheoHostMesh* rheo_io_read_polymesh(const char* dir) {
     if (!read_labels("owner", m->owner)) return fail("cannot read owner");
     if (!read_labels("neighbour", m->neighbour)) return fail("cannot read neighbour");
     if ((int)m->owner.size() != m->n_faces) return fail("owner and faces differ in length");
+    if (file_exists(d + "/cellProcAddressing") || file_exists(d + "/cellProcAddressing.gz")) {   // processor mesh written by decomposePar
+        if (!read_labels("cellProcAddressing", m->cell_addr) || !read_labels("faceProcAddressing", m->face_addr)) return fail("cannot read the ProcAddressing files");
+    }
     m->n_internal = (int32_t)m->neighbour.size();
     m->n_cells = 0;
     for (int32_t o : m->owner) m->n_cells = std::max(m->n_cells, o + 1);
@@ -360,7 +365,12 @@ RheoHostMesh* rheo_io_read_polymesh(const char* dir) {
             long nf, sf;
             if (!to_long(word("nFaces"), nf) || !to_long(word("startFace"), sf)) return fail("patch " + name + ": nFaces/startFace missing");
             p.size = (int32_t)nf; p.start = (int32_t)sf; p.nbr_rank = -1;
-            if (p.type == RHEO_PATCH_PROCESSOR) { long r; if (!to_long(word("neighbProcNo"), r)) return fail("processor patch " + name + ": neighbProcNo missing"); p.nbr_rank = (int32_t)r; }
+            if (p.type == RHEO_PATCH_PROCESSOR) {
+                long r;
+                if (!to_long(word("neighbProcNo"), r)) return fail("processor patch " + name + ": neighbProcNo missing");
+                p.nbr_rank = (int32_t)r;
+                if (to_long(word("myProcNo"), r)) m->my_rank = (int32_t)r;
+            }
             p.theta_bc = p.tau_bc = p.type == RHEO_PATCH_EMPTY ? RHEO_BC_EMPTY : (p.type == RHEO_PATCH_PROCESSOR ? RHEO_BC_PROCESSOR : RHEO_BC_ZERO_GRADIENT);
             m->patches.push_back(p);
             m->patch_names.push_back(name);
@@ -428,11 +438,42 @@ int rheo_io_write_polymesh(const RheoHostMesh* m, const char* dir, int32_t gz) {
         const RheoPatchDesc& pd = m->patches[p];
         const char* type = pd.type == RHEO_PATCH_WALL ? "wall" : pd.type == RHEO_PATCH_EMPTY ? "empty" : pd.type == RHEO_PATCH_PROCESSOR ? "processor" : "patch";
         s += "    " + patch_name_of(m, (int)p) + "\n    {\n        type            " + type + ";\n";
-        if (pd.type == RHEO_PATCH_PROCESSOR) s += "        neighbProcNo    " + std::to_string(pd.nbr_rank) + ";\n";
+        if (pd.type == RHEO_PATCH_PROCESSOR)
+            s += "        myProcNo        " + std::to_string(std::max(m->my_rank, 0)) + ";\n        neighbProcNo    " + std::to_string(pd.nbr_rank) + ";\n";
         s += "        nFaces          " + std::to_string(pd.size) + ";\n        startFace       " + std::to_string(pd.start) + ";\n    }\n";
     }
     s += ")\n";
     if (!spit(d + "/boundary", s, false)) { rheo::set_error("rheo_io_write_polymesh: cannot write boundary"); return 1; }   // the boundary file is never compressed
+    if (!m->face_addr.empty() && !m->cell_addr.empty()) {   // decomposePar's addressing of a processor mesh into the undecomposed one
+        std::vector<int32_t> bpa;
+        int phys = 0;
+        for (const RheoPatchDesc& pd : m->patches) bpa.push_back(pd.type == RHEO_PATCH_PROCESSOR ? -1 : phys++);
+        if (!labels("cellProcAddressing", m->cell_addr) || !labels("faceProcAddressing", m->face_addr) || !labels("boundaryProcAddressing", bpa)) {
+            rheo::set_error("rheo_io_write_polymesh: cannot write the ProcAddressing files");
+            return 1;
+        }
+    }
+    return 0;
+}
+
+int rheo_io_set_nbr_centres(RheoHostMesh* m, int32_t patch, const double* centres) {
+    if (!m || !centres || patch < 0 || patch >= (int)m->patches.size() || m->patches[patch].type != RHEO_PATCH_PROCESSOR) {
+        rheo::set_error("rheo_io_set_nbr_centres: not a processor patch");
+        return 1;
+    }
+    const RheoPatchDesc& p = m->patches[patch];
+    std::copy(centres, centres + 3 * (size_t)p.size, m->nbr_C.begin() + 3 * (size_t)(p.start - m->n_internal));
+    // EXT-OF9 surfaceInterpolation::makeWeights on a coupled patch: w = |Sf.(Cn - Cf)| / (|Sf.(Cf - Cp)| + |Sf.(Cn - Cf)|)
+    for (int32_t f = p.start; f < p.start + p.size; ++f) {
+        const double* S = &m->Sf[3 * (size_t)f];
+        const double* Cf = &m->Cf[3 * (size_t)f];
+        const double* Cp = &m->C[3 * (size_t)m->owner[f]];
+        const double* Cn = &m->nbr_C[3 * (size_t)(f - m->n_internal)];
+        double so = 0, sn = 0;
+        for (int c = 0; c < 3; ++c) { so += S[c] * (Cf[c] - Cp[c]); sn += S[c] * (Cn[c] - Cf[c]); }
+        so = std::fabs(so); sn = std::fabs(sn);
+        m->weights[f] = sn / (so + sn);
+    }
     return 0;
 }
 

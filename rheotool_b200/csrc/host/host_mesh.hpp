@@ -26,6 +26,7 @@ struct RheoHostMesh {
     std::vector<int32_t> face_start;       // n_faces + 1 offsets into face_pts
     std::vector<int32_t> face_pts;
     std::vector<std::string> patch_names;  // may be shorter than patches (unnamed: patch<i>)
+    int32_t my_rank = -1;                  // processor sub-meshes: myProcNo
 
     // --- decomposition provenance (EXT-OF9 cellProcAddressing / faceProcAddressing) ---
     std::vector<int32_t> cell_addr, face_addr;

@@ -203,3 +203,69 @@ def read_case(case_dir, time: str, name: str = ""):
             U_b[p.start - nint: p.start - nint + p.size] = U[m.owner[p.start: p.start + p.size]]
     return m, {"U": U, "U_b": U_b, "phi": surface_flux(m, U, U_b), "theta": theta, "theta_b": theta_b, "tau": tau, "tau_b": tau_b,
                "eigvals": eigvals, "eigvecs": eigvecs}
+
+
+# ---------------------------------------------------------------- decomposed cases (processorN/ directories, decomposePar layout)
+def write_decomposed_case(case_dir, m: HostMesh, cell_to_rank: np.ndarray, time: str, fields: dict, name: str = "", gz: bool = False):
+    """processor<r>/constant/polyMesh (+ cell/face/boundaryProcAddressing) and processor<r>/<time>/ fields for every rank of
+    `cell_to_rank` — what `decomposePar` leaves for `mpirun -np N rheoFoam -parallel`.
+    fields: theta, tau, U, U_b (+ optional theta_b, tau_b, eigvals, eigvecs) of the undecomposed mesh."""
+    case_dir = Path(case_dir)
+    n_ranks = int(np.max(cell_to_rank)) + 1
+    nint = m.n_internal
+    subs = []
+    for r in range(n_ranks):
+        sub = m.decompose(cell_to_rank, n_ranks, r)
+        ca, fa = sub.proc_addressing()
+        gb = (np.abs(fa) - 1)[sub.n_internal:] - nint       # undecomposed boundary face of each local boundary face (< 0: processor face)
+
+        def bnd(key, ncomp):
+            v = fields.get(key)
+            if v is None:
+                return None
+            out = np.zeros((sub.n_boundary, ncomp))
+            out[gb >= 0] = v[gb[gb >= 0]]
+            return out
+
+        def cells(key):
+            v = fields.get(key)
+            return None if v is None else v[ca]
+
+        write_case(case_dir / f"processor{r}", sub, time, cells("theta"), cells("tau"), cells("U"), bnd("U_b", 3), theta_b=bnd("theta_b", 6),
+                   tau_b=bnd("tau_b", 6), eigvals=cells("eigvals"), eigvecs=cells("eigvecs"), name=name, gz=gz)
+        subs.append(sub)
+    return subs
+
+
+def read_decomposed_case(case_dir, time: str, name: str = ""):
+    """-> [(mesh, fields)] per rank, processor patches completed with the cell centres across them (read from the
+    neighbour's directory — inside an MPI run each rank would receive them from its neighbour at start-up), and phi taken
+    consistently on both sides of every processor face."""
+    case_dir = Path(case_dir)
+    n_ranks = len([p for p in case_dir.iterdir() if p.is_dir() and p.name.startswith("processor")])
+    ranks = [read_case(case_dir / f"processor{r}", time, name) for r in range(n_ranks)]
+    for r, (m, f) in enumerate(ranks):
+        for pi, p in enumerate(m.patches):
+            if p.type != abi.PATCH_PROCESSOR:
+                continue
+            om, of = ranks[p.nbr_rank]
+            q = next(x for x in om.patches if x.type == abi.PATCH_PROCESSOR and x.nbr_rank == r)
+            if q.size != p.size:
+                raise FoamError(f"processor patches {r}<->{p.nbr_rank} differ in size")
+            centres = np.ascontiguousarray(om.C[om.owner[q.start: q.start + q.size]])
+            if abi.lib().rheo_io_set_nbr_centres(m.handle, pi, centres.ctypes.data_as(C.c_void_p)):
+                raise FoamError(_err())
+    # weights changed on the processor patches: flux through them = linear interpolation of the two cell values
+    for r, (m, f) in enumerate(ranks):
+        nint = m.n_internal
+        for p in m.patches:
+            if p.type != abi.PATCH_PROCESSOR:
+                continue
+            om, of = ranks[p.nbr_rank]
+            q = next(x for x in om.patches if x.type == abi.PATCH_PROCESSOR and x.nbr_rank == r)
+            sl = slice(p.start, p.start + p.size)
+            w = m.weights[sl, None]
+            Uf = w * f["U"][m.owner[sl]] + (1 - w) * of["U"][om.owner[q.start: q.start + q.size]]
+            f["phi"][sl] = (Uf * m.Sf[sl]).sum(1)
+            f["U_b"][p.start - nint: p.start - nint + p.size] = Uf
+    return ranks
