@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Advance the stress of an OpenFOAM case on the GPU with the velocity field frozen (what rheoFoam does with the momentum
+balance switched off): read constant/polyMesh and <time>/{U, theta, tau[, eigVals, eigVecs]}, run n steps of
+constitutiveEq::correct() on cuda:0, write the new time directory (theta, tau, eigVals, eigVecs) for restart / ParaView.
+
+    python tools/run_case.py CASE --time 0 --model Oldroyd-BLog --etaS 0.59 --etaP 0.41 --lambda 0.7 --dt 0.02 --steps 50
+
+The flux is createPhi's (linear interpolation of U dotted with Sf).  Needs a CUDA device: there is no CPU path."""
+import argparse
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from rheotool_b200 import abi, cases, foamio  # noqa: E402
+from rheotool_b200.stress import GpuStressModel  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    ap.add_argument("case")
+    ap.add_argument("--time", default="0")
+    ap.add_argument("--name", default="", help="field name suffix (multi-region / multi-phase cases)")
+    ap.add_argument("--model", default="Oldroyd-BLog", choices=sorted(abi.MODEL_NAMES))
+    ap.add_argument("--etaS", type=float, default=0.0)
+    ap.add_argument("--etaP", type=float, default=1.0)
+    ap.add_argument("--lambda", dest="lambda_", type=float, default=1.0)
+    ap.add_argument("--param", action="append", default=[], metavar="KEY=VALUE", help="further model_desc parameters (alpha, epsilon, zeta, L2, ...)")
+    ap.add_argument("--limiter", default="cubista", choices=sorted(abi.LIMITER))
+    ap.add_argument("--ddt", default="Euler", choices=["Euler", "backward"])
+    ap.add_argument("--tolerance", type=float, default=1e-10)
+    ap.add_argument("--dt", type=float, required=True)
+    ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--gz", action="store_true")
+    a = ap.parse_args()
+
+    m, f = foamio.read_case(a.case, a.time, a.name)
+    extra = {k: (v if k == "ptt_function" else float(v)) for k, v in (kv.split("=", 1) for kv in a.param)}
+    model = cases.model_desc(a.model, etaS=a.etaS, etaP=a.etaP, lambda_=a.lambda_, **extra)
+    schemes = cases.scheme_ctl(a.limiter, "PBiCGStab", a.tolerance, ddt=a.ddt)
+    g = GpuStressModel(m, [model], schemes, 0)
+    g.upload_state(0, f["theta"], f["tau"], f["eigvals"], f["eigvecs"], theta_b=f["theta_b"])
+    g.upload_velocity(f["U"], f["U_b"], f["phi"])
+    for n in range(a.steps):
+        g.store_old_time()
+        g.correct(a.dt)
+        print(f"step {n + 1}: Krylov iterations {g.last_iterations()}")
+    t_new = f"{float(a.time) + a.steps * a.dt:g}"
+    foamio.write_case(a.case, m, t_new, g.theta(), g.tau(0), f["U"], f["U_b"], theta_b=g.download(abi.FIELD_THETA_B), tau_b=g.download(abi.FIELD_TAU_B),
+                      eigvals=g.download(abi.FIELD_EIGVALS), eigvecs=g.download(abi.FIELD_EIGVECS), name=a.name, gz=a.gz)
+    print(f"wrote {Path(a.case) / t_new}")
+
+
+if __name__ == "__main__":
+    main()
