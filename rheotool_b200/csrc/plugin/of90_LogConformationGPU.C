@@ -162,6 +162,11 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     const dictionary& sol = mesh.solverDict(thetaName);
     const word solver(sol.lookup("solver"));
     // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs PBiCGStab
+    if (solver != "PBiCGStab")
+    {
+        WarningInFunction << "fvSolution selects " << solver << " for " << thetaName
+            << "; the GPU path solves with PBiCGStab + DILU (same tolerance, relTol, minIter, maxIter)" << endl;
+    }
     ctl_.solver    = RHEO_SOLVER_PBICGSTAB;
     ctl_.tolerance = sol.lookupOrDefault<scalar>("tolerance", 1e-6);
     ctl_.rel_tol   = sol.lookupOrDefault<scalar>("relTol", 0);
