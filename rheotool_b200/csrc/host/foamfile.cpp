@@ -65,6 +65,12 @@ bool tokenize(const std::string& in, std::vector<Tok>& out) {
             if (e == std::string::npos) return false;
             i = e + 2; continue;
         }
+        if (c == '#' && i + 1 < n && in[i + 1] == '{') {   // verbatim code block of a coded boundary condition: #{ ... #}
+            const size_t e = in.find("#}", i + 2);
+            if (e == std::string::npos) return false;
+            out.push_back({Tok::Str, in.substr(i + 2, e - i - 2)});
+            i = e + 2; continue;
+        }
         if (c == '(' || c == ')' || c == '{' || c == '}' || c == ';') { out.push_back({Tok::Punct, std::string(1, c)}); ++i; continue; }
         if (c == '"') {
             size_t e = i + 1;
@@ -75,6 +81,12 @@ bool tokenize(const std::string& in, std::vector<Tok>& out) {
         }
         size_t e = i;
         int depth = 0;   // words may contain balanced <> (List<symmTensor>) and [] is handled as word characters
+        if (c == '$' && i + 1 < n && in[i + 1] == '{') {   // ${name}
+            const size_t close = in.find('}', i + 2);
+            if (close == std::string::npos) return false;
+            out.push_back({Tok::Word, in.substr(i, close - i + 1)});
+            i = close + 1; continue;
+        }
         while (e < n) {
             const char d = in[e];
             if (d == '<') ++depth;
@@ -117,6 +129,10 @@ bool parse_dict(const std::vector<Tok>& t, size_t& i, Dict& d, bool top) {
     while (i < t.size()) {
         if (t[i].kind == Tok::Punct && t[i].s == "}") { if (top) return false; ++i; return true; }
         if (t[i].kind == Tok::Punct) return false;
+        if (t[i].kind == Tok::Word && t[i].s[0] == '#') {   // #include "file", #includeEtc "...", #inputMode merge: not followed, not needed for the values
+            i += 2;
+            continue;
+        }
         Entry e;
         e.key = t[i].s; e.pattern = t[i].kind == Tok::Str;
         ++i;
@@ -142,6 +158,22 @@ bool parse_dict(const std::vector<Tok>& t, size_t& i, Dict& d, bool top) {
         d.entries.push_back(std::move(e));
     }
     return top;
+}
+
+// $name -> the tokens of entry `name`, looked up from the innermost scope outwards (EXT-OF9 dictionary variable expansion)
+std::vector<Tok> expand(const std::vector<Tok>& v, const std::vector<const Dict*>& scopes, int depth = 0) {
+    std::vector<Tok> out;
+    for (const Tok& t : v) {
+        if (t.kind == Tok::Word && t.s.size() > 1 && t.s[0] == '$' && depth < 8) {
+            std::string name = t.s.substr(1);
+            if (!name.empty() && name[0] == '{' && name.back() == '}') name = name.substr(1, name.size() - 2);
+            const Entry* e = nullptr;
+            for (auto it = scopes.rbegin(); it != scopes.rend() && !e; ++it) e = (*it)->find_exact(name);
+            if (e && !e->sub) { const std::vector<Tok> x = expand(e->value, scopes, depth + 1); out.insert(out.end(), x.begin(), x.end()); continue; }
+        }
+        out.push_back(t);
+    }
+    return out;
 }
 
 bool to_double(const std::string& s, double& v) { char* e = nullptr; v = std::strtod(s.c_str(), &e); return e && *e == 0 && !s.empty(); }
@@ -230,6 +262,7 @@ struct RheoFoamField {
     std::string cls, object;
     int ncomp = 0;
     FieldValue internal;
+    Dict body;        // the whole file (scope of $variables)
     Dict boundary;
 };
 
@@ -509,10 +542,10 @@ RheoFoamField* rheo_io_read_field(const char* path) {
     if (!skip_header(t, i, &f->cls, &f->object, nullptr)) return fail("no FoamFile header");
     f->ncomp = ncomp_of_class(f->cls);
     if (!f->ncomp) return fail("class " + f->cls + " is not a vol<Type>Field this library knows");
-    Dict body;
+    Dict& body = f->body;
     if (!parse_dict(t, i, body, true)) return fail("syntax error in the dictionary");
     const Entry* in = body.find_exact("internalField");
-    if (!in || !parse_value(in->value, f->internal)) return fail("bad or missing internalField");
+    if (!in || !parse_value(expand(in->value, {&body}), f->internal)) return fail("bad or missing internalField");
     if (f->internal.ncomp != f->ncomp && !(f->internal.count == 0)) return fail("internalField has " + std::to_string(f->internal.ncomp) + " components, class " + f->cls + " needs " + std::to_string(f->ncomp));
     const Entry* bf = body.find_exact("boundaryField");
     if (!bf || !bf->sub) return fail("no boundaryField dictionary");
@@ -555,7 +588,7 @@ int rheo_io_field_patch(const RheoFoamField* f, const char* patch_name, int32_t 
     if (has_value) *has_value = v ? 1 : 0;
     if (v && values) {
         FieldValue fv;
-        if (!parse_value(v->value, fv)) { rheo::set_error(std::string("rheo_io_field_patch: bad value entry on patch ") + patch_name); return 1; }
+        if (!parse_value(expand(v->value, {&f->body, &f->boundary, e->sub.get()}), fv)) { rheo::set_error(std::string("rheo_io_field_patch: bad value entry on patch ") + patch_name); return 1; }
         if (fv.uniform) {
             if (fv.ncomp != f->ncomp) { rheo::set_error("rheo_io_field_patch: value has the wrong number of components"); return 1; }
             for (int32_t q = 0; q < n_faces; ++q) for (int k = 0; k < f->ncomp; ++k) values[(size_t)q * f->ncomp + k] = fv.data[(size_t)k];

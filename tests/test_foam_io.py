@@ -249,3 +249,35 @@ def test_decomposed_case_round_trip_runs_like_the_undecomposed_one(tmp_path):
         ca, _fa = mm.proc_addressing()
         got[ca] = many.get(r, 0, abi.FIELD_TAU)
     assert rel_l2(got, ref) < 1e-10
+
+
+def test_dictionary_variables_directives_and_code_blocks(tmp_path):
+    """$variables (innermost scope first), #include-style directives (skipped) and #{ ... #} code blocks, as they occur in the
+    reference's 0/U files (e.g. `value uniform ($uStart 0 0);`, `value $internalField;`, `#includeEtc "caseDicts/setConstraintTypes"`)."""
+    (tmp_path / "U").write_text("""
+FoamFile { version 2.0; format ascii; class volVectorField; object U; }
+uStart 1.5;
+dimensions [0 1 -1 0 0 0 0];
+internalField uniform ($uStart 0 0);
+boundaryField
+{
+    #includeEtc "caseDicts/setConstraintTypes"
+    inlet   { type fixedValue; value uniform (${uStart} 0 0); }
+    outlet  { type fixedValue; value $internalField; }
+    coded   { type codedFixedValue; value uniform (0 0 0); name ramp; code #{ operator==(vector(1, 0, 0)); // not parsed ; { ( #}; }
+}
+""")
+    f = foamio.FoamField(tmp_path / "U")
+    assert np.array_equal(f.internal(2), [[1.5, 0, 0], [1.5, 0, 0]])
+    assert np.array_equal(f.patch("inlet", 1)[1], [[1.5, 0, 0]])
+    assert np.array_equal(f.patch("outlet", 2)[1], [[1.5, 0, 0], [1.5, 0, 0]])
+    assert f.patch("coded", 1)[0] == "codedFixedValue"
+
+
+@needs_ref
+def test_every_velocity_file_of_the_reference_tutorials_parses():
+    files = sorted(p for p in REF.rglob("U") if p.is_file() and p.parent.name in ("0", "fluid", "0.orig"))
+    assert len(files) >= 60
+    for p in files:
+        f = foamio.FoamField(p)
+        assert f.cls == "volVectorField" and f.internal(2).shape == (2, 3), p
