@@ -62,6 +62,16 @@ int rheo_io_write_field(const char* path, const char* cls, const char* object, c
                         const double* internal, int32_t n_patches, const char* const* patch_names, const char* const* patch_types,
                         const int32_t* patch_sizes, const double* const* patch_values, int32_t gz);
 
+/* ---- plain dictionaries (constant/constitutiveProperties, system/fvSchemes, system/fvSolution) ------------------ */
+typedef struct RheoFoamDict RheoFoamDict;
+RheoFoamDict* rheo_io_dict_open(const char* path);
+void rheo_io_dict_free(RheoFoamDict* d);
+/* Entry at a '/'-separated path of keywords (regular-expression keys honoured at every level; a list of named
+ * dictionaries such as multiMode's `models ( M1 {..} M2 {..} )` is descended like a dictionary).  Returns 0 and the
+ * value's tokens joined by blanks ($variables expanded), 3 and the keys of the sub-dictionary, or 2 when there is no
+ * such entry. */
+int rheo_io_dict_lookup(const RheoFoamDict* d, const char* path, char* buf, int32_t buflen);
+
 #ifdef __cplusplus
 }
 #endif

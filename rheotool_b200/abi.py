@@ -140,6 +140,9 @@ IO_SYMBOLS = {
     "rheo_io_field_internal": (C.c_int, [_P, C.c_int64, _P]),
     "rheo_io_field_patch": (C.c_int, [_P, C.c_char_p, _I, _P, _I, _P, _P]),
     "rheo_io_apply_field_bcs": (C.c_int, [_P, _P, _I]),
+    "rheo_io_dict_open": (_P, [C.c_char_p]),
+    "rheo_io_dict_free": (None, [_P]),
+    "rheo_io_dict_lookup": (C.c_int, [_P, C.c_char_p, _P, _I]),
     "rheo_io_write_field": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _I, C.c_int64, _P, _I, _P, _P, _P, _P, _I]),
 }
 

@@ -87,11 +87,18 @@ bool tokenize(const std::string& in, std::vector<Tok>& out) {
             out.push_back({Tok::Word, in.substr(i, close - i + 1)});
             i = close + 1; continue;
         }
+        // a word that starts with a letter may hold balanced parentheses: div(phi,theta), ddt(theta), grad(U)
+        // (EXT-OF9 ISstream::readWordToken); numbers never do: "4(0 1 2 3)" is the label 4 followed by a list
+        const bool alpha = std::isalpha((unsigned char)c) || c == '_';
+        int pdepth = 0;
         while (e < n) {
             const char d = in[e];
             if (d == '<') ++depth;
             if (d == '>') --depth;
-            if (depth == 0 && (std::isspace((unsigned char)d) || d == '(' || d == ')' || d == '{' || d == '}' || d == ';' || d == '"')) break;
+            if (alpha && d == '(' && e > i) { ++pdepth; ++e; continue; }
+            if (pdepth > 0 && d == ')') { --pdepth; ++e; continue; }
+            if (depth == 0 && pdepth == 0 && (std::isspace((unsigned char)d) || d == '(' || d == ')' || d == '{' || d == '}' || d == ';' || d == '"')) break;
+            if (pdepth > 0 && (d == ';' || d == '{' || d == '}')) break;   // unbalanced: give up on the parenthesis
             ++e;
         }
         out.push_back({Tok::Word, in.substr(i, e - i)});
@@ -257,6 +264,8 @@ bool skip_header(const std::vector<Tok>& t, size_t& i, std::string* cls, std::st
 }
 
 }  // namespace
+
+struct RheoFoamDict { Dict root; };
 
 struct RheoFoamField {
     std::string cls, object;
@@ -554,6 +563,67 @@ RheoFoamField* rheo_io_read_field(const char* path) {
 }
 
 void rheo_io_field_free(RheoFoamField* f) { delete f; }
+
+RheoFoamDict* rheo_io_dict_open(const char* path) {
+    if (!path) { rheo::set_error("rheo_io_dict_open: null path"); return nullptr; }
+    std::string txt;
+    if (!slurp(path, txt)) { rheo::set_error(std::string("rheo_io_dict_open(") + path + "): cannot read file"); return nullptr; }
+    std::vector<Tok> t;
+    if (!tokenize(txt, t)) { rheo::set_error(std::string("rheo_io_dict_open(") + path + "): unterminated comment or string"); return nullptr; }
+    size_t i = 0;
+    if (!t.empty() && t[0].s == "FoamFile") { if (!skip_header(t, i, nullptr, nullptr, nullptr)) { rheo::set_error(std::string("rheo_io_dict_open(") + path + "): bad FoamFile header"); return nullptr; } }
+    auto d = std::make_unique<RheoFoamDict>();
+    if (!parse_dict(t, i, d->root, true)) { rheo::set_error(std::string("rheo_io_dict_open(") + path + "): syntax error"); return nullptr; }
+    return d.release();
+}
+
+void rheo_io_dict_free(RheoFoamDict* d) { delete d; }
+
+int rheo_io_dict_lookup(const RheoFoamDict* d, const char* path, char* buf, int32_t buflen) {
+    if (!d || !path || !buf || buflen < 1) { rheo::set_error("rheo_io_dict_lookup: null argument"); return 1; }
+    std::vector<std::shared_ptr<Dict>> keep;          // dictionaries parsed on the way (lists of named dictionaries)
+    std::vector<const Dict*> scopes{&d->root};
+    const Dict* cur = &d->root;
+    const Entry* e = nullptr;
+    std::string p(path);
+    size_t pos = 0;
+    while (pos <= p.size()) {
+        const size_t nx = p.find('/', pos);
+        const std::string key = p.substr(pos, nx == std::string::npos ? std::string::npos : nx - pos);
+        e = cur->lookup(key);
+        if (!e) { rheo::set_error(std::string("rheo_io_dict_lookup: no entry ") + path); return 2; }
+        if (nx == std::string::npos) break;
+        if (e->sub) cur = e->sub.get();
+        else {   // "( name { ... } name { ... } )": a list of named dictionaries (multiMode's `models`)
+            const std::vector<Tok>& v = e->value;
+            if (v.size() < 2 || v.front().s != "(" || v.back().s != ")") { rheo::set_error(std::string("rheo_io_dict_lookup: ") + key + " is not a dictionary"); return 2; }
+            std::vector<Tok> inner(v.begin() + 1, v.end() - 1);
+            auto sub = std::make_shared<Dict>();
+            size_t j = 0;
+            if (!parse_dict(inner, j, *sub, true)) { rheo::set_error(std::string("rheo_io_dict_lookup: ") + key + " is not a list of dictionaries"); return 2; }
+            keep.push_back(sub);
+            cur = sub.get();
+        }
+        scopes.push_back(cur);
+        pos = nx + 1;
+    }
+    std::string out;
+    int rc = 0;
+    if (e->sub) { for (const Entry& x : e->sub->entries) { if (!out.empty()) out += ' '; out += x.key; } rc = 3; }
+    else {
+        const std::vector<Tok> v = expand(e->value, scopes);
+        // a list of named dictionaries reports its names, like a dictionary
+        bool listOfDicts = v.size() >= 2 && v.front().s == "(" && v.back().s == ")" && std::any_of(v.begin(), v.end(), [](const Tok& t) { return t.kind == Tok::Punct && t.s == "{"; });
+        if (listOfDicts) {
+            std::vector<Tok> inner(v.begin() + 1, v.end() - 1);
+            Dict sub; size_t j = 0;
+            if (parse_dict(inner, j, sub, true)) { for (const Entry& x : sub.entries) { if (!out.empty()) out += ' '; out += x.key; } rc = 3; }
+        }
+        if (rc == 0) for (const Tok& t : v) { if (!out.empty()) out += ' '; out += t.s; }
+    }
+    snprintf(buf, (size_t)buflen, "%s", out.c_str());
+    return rc;
+}
 
 int rheo_io_field_info(const RheoFoamField* f, char* cls, int32_t cls_len, char* object, int32_t object_len, int32_t* n_comp, int32_t* internal_uniform,
                        int64_t* n_internal) {

@@ -269,3 +269,128 @@ def read_decomposed_case(case_dir, time: str, name: str = ""):
             f["phi"][sl] = (Uf * m.Sf[sl]).sum(1)
             f["U_b"][p.start - nint: p.start - nint + p.size] = Uf
     return ranks
+
+
+# ---------------------------------------------------------------- case dictionaries: constitutiveProperties, fvSchemes, fvSolution
+class FoamDict:
+    """A plain OpenFOAM dictionary file; entries are addressed by '/'-separated keyword paths."""
+
+    def __init__(self, path):
+        self.path = str(path)
+        self._h = abi.lib().rheo_io_dict_open(self.path.encode())
+        if not self._h:
+            raise FoamError(_err())
+
+    def __del__(self):
+        try:
+            if self._h:
+                abi.lib().rheo_io_dict_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _lookup(self, key):
+        buf = C.create_string_buffer(1 << 16)
+        rc = abi.lib().rheo_io_dict_lookup(self._h, key.encode(), buf, len(buf))
+        return rc, buf.value.decode()
+
+    def get(self, key, default=None):
+        """Value tokens of a primitive entry joined by blanks; `default` when there is no such entry."""
+        rc, s = self._lookup(key)
+        if rc == 2:
+            return default
+        if rc == 3:
+            raise FoamError(f"{self.path}: {key} is a dictionary, not a value")
+        if rc:
+            raise FoamError(_err())
+        return s
+
+    def keys(self, key):
+        rc, s = self._lookup(key)
+        if rc != 3:
+            raise FoamError(f"{self.path}: {key} is not a dictionary")
+        return s.split()
+
+    def scalar(self, key, default=None) -> float:
+        """`name [dims] value` (dimensionedScalar) or a bare number: the last token."""
+        s = self.get(key)
+        if s is None:
+            if default is None:
+                raise FoamError(f"{self.path}: keyword {key} is undefined")
+            return default
+        return float(s.split()[-1])
+
+
+def _read_one_model(d: FoamDict, at: str):
+    from . import cases
+    ty = d.get(f"{at}/type")
+    if ty is None:
+        raise FoamError(f"{d.path}: {at} has no type")
+    if ty not in abi.MODEL_NAMES:
+        raise FoamError(f"{d.path}: constitutiveEq type {ty} is not a log-conformation model of this library (valid: {sorted(abi.MODEL_NAMES)})")
+    sc = lambda k, default=None: d.scalar(f"{at}/{k}", default)   # noqa: E731
+    kw = dict(rho=sc("rho"), etaS=sc("etaS"), etaP=sc("etaP"))
+    if ty == "Rolie-PolyLog":      # RoliePolyLog.C:114-121
+        kw.update(lambda_=sc("lambdaD"), rp_lambdaR=sc("lambdaR"), rp_beta=sc("beta"), rp_delta=sc("delta"), rp_chiMax=sc("chiMax"))
+    elif ty == "XPomPomLog":       # XPomPomLog.C:115-122
+        kw.update(lambda_=sc("lambdaB"), xpp_lambdaS=sc("lambdaS"), alpha=sc("alpha"), xpp_q=sc("q"), xpp_n=sc("n"))
+    else:
+        kw.update(lambda_=sc("lambda"))
+    if ty == "GiesekusLog":
+        kw.update(alpha=sc("alpha"))
+    elif ty == "PTTLog":           # PTTLog.C:41-50, 129-170
+        fn = d.get(f"{at}/destructionFunctionType")
+        if fn not in ("linear", "exponential", "generalized"):
+            raise FoamError(f"{d.path}: destructionFunctionType {fn}: valid are linear exponential generalized")
+        kw.update(epsilon=sc("epsilon"), zeta=sc("zeta"), ptt_function=fn)
+        if fn == "generalized":
+            kw.update(ml_alpha=sc("alpha"), ml_beta=sc("beta"))
+    elif ty in ("FENE-PLog", "FENE-CRLog"):
+        kw.update(L2=sc("L2"))
+    elif ty == "WhiteMetznerCYLog":   # WhiteMetznerCYLog.C:132-140
+        K, L, n, m_, a, b = (sc(k) for k in ("K", "L", "n", "m", "a", "b"))
+        if m_ != n or K != L or a != b:
+            raise FoamError("The Log version of the WhiteMetznerCY model can only be used if:  m=n   and   K=L   and   a=b")
+        kw.update(wm_K=K, wm_n=n, wm_a=a)
+    return cases.model_desc(ty, **kw)
+
+
+def read_models(constitutive_properties, section: str = "parameters"):
+    """constant/constitutiveProperties -> [RheoModelDesc]: one model, or the modes of a multiMode entry (multiMode.C:41-92)."""
+    d = FoamDict(constitutive_properties)
+    if d.get(f"{section}/type") == "multiMode":
+        return [_read_one_model(d, f"{section}/models/{k}") for k in d.keys(f"{section}/models")]
+    return [_read_one_model(d, section)]
+
+
+def mode_names(constitutive_properties, section: str = "parameters"):
+    """Field-name suffixes of the modes: [""] for a single model, the keys of `models` for multiMode (theta<name>, tau<name>:
+    multiMode.C:73-87)."""
+    d = FoamDict(constitutive_properties)
+    return d.keys(f"{section}/models") if d.get(f"{section}/type") == "multiMode" else [""]
+
+
+def read_schemes(case_dir, theta_name: str = "theta"):
+    """system/fvSchemes + system/fvSolution -> RheoSchemeCtl, as the OpenFOAM shim reads them (of90_LogConformationGPU.C):
+    div(phi,theta) must be `GaussDefCmpw <limiter>`, ddt Euler or backward; the solver entry may select PBiCG (the device
+    runs PBiCGStab: reported in the second return value)."""
+    from . import cases
+    case_dir = Path(case_dir)
+    fs, sol = FoamDict(case_dir / "system" / "fvSchemes"), FoamDict(case_dir / "system" / "fvSolution")
+    div = fs.get(f"divSchemes/div(phi,{theta_name})") or fs.get("divSchemes/default")
+    if div is None:
+        raise FoamError(f"{fs.path}: no div(phi,{theta_name}) scheme")
+    tok = div.split()
+    if len(tok) != 2 or tok[0] != "GaussDefCmpw" or tok[1] not in abi.LIMITER:
+        raise FoamError(f"{fs.path}: div(phi,{theta_name}) is `{div}`; the stress step needs `GaussDefCmpw <limiter>` with one of {sorted(abi.LIMITER)}")
+    ddt = fs.get(f"ddtSchemes/ddt({theta_name})") or fs.get("ddtSchemes/default")
+    if ddt not in ("Euler", "backward"):
+        raise FoamError(f"{fs.path}: ddtSchemes Euler and backward are available, not {ddt}")
+    at = f"solvers/{theta_name}"
+    solver = sol.get(f"{at}/solver")
+    if solver is None:
+        raise FoamError(f"{sol.path}: no solver entry for {theta_name}")
+    relax = sol.scalar(f"relaxationFactors/equations/{theta_name}", 0.0)
+    ctl = cases.scheme_ctl(tok[1], "PBiCGStab", sol.scalar(f"{at}/tolerance", 1e-6), sol.scalar(f"{at}/relTol", 0.0), int(sol.scalar(f"{at}/minIter", 0)),
+                           int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt)
+    return ctl, solver

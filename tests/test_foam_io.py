@@ -281,3 +281,51 @@ def test_every_velocity_file_of_the_reference_tutorials_parses():
     for p in files:
         f = foamio.FoamField(p)
         assert f.cls == "volVectorField" and f.internal(2).shape == (2, 3), p
+
+
+@needs_ref
+def test_case_dictionaries_of_the_reference_tutorials_give_models_and_schemes():
+    """constant/constitutiveProperties + system/fvSchemes + system/fvSolution of every reference tutorial that selects one of the
+    log-conformation models of this library (or a multiMode of them): models and schemes come out as the shim would read them."""
+    import re
+    seen, n_multi, n_schemes, n_refused = {}, 0, 0, 0
+    for cp in sorted(REF.rglob("constitutiveProperties")):
+        txt = cp.read_text()
+        types = re.findall(r"^\s*type\s+([\w-]+)\s*;", txt, flags=re.M)
+        if not types:
+            continue
+        try:   # single-phase layout only: a top-level `parameters` dictionary (two-phase cases nest it per phase: out of scope)
+            foamio.FoamDict(cp).keys("parameters")
+        except foamio.FoamError:
+            continue
+        first = types[0]
+        wanted = first in abi.MODEL_NAMES or (first == "multiMode" and all(t in abi.MODEL_NAMES for t in types[1:] if t.endswith("Log")) and
+                                                 all(t.endswith("Log") for t in types[1:len(types)]))
+        if not wanted:
+            with pytest.raises(foamio.FoamError):
+                foamio.read_models(cp)
+            continue
+        models = foamio.read_models(cp)
+        if first == "multiMode":
+            n_multi += 1
+            assert len(models) >= 2
+        for md in models:
+            assert md.etaP > 0 and md.lambda_ > 0 and md.rho > 0
+        seen[first] = seen.get(first, 0) + 1
+        case = cp.parent.parent
+        if (case / "system" / "fvSchemes").exists() and "theta" in (case / "system" / "fvSchemes").read_text():
+            try:
+                ctl, solver = foamio.read_schemes(case, "theta" + foamio.mode_names(cp)[0])
+            except foamio.FoamError as e:   # refused loudly: a time scheme the stress step does not have (CrankNicolson, steadyState)
+                assert "ddtSchemes" in str(e) and re.search(r"CrankNicolson|steadyState", (case / "system" / "fvSchemes").read_text())
+                n_refused += 1
+                continue
+            n_schemes += 1
+            assert solver in ("PBiCG", "PBiCGStab") and ctl.tolerance > 0 and ctl.ddt in (abi.DDT_EULER, abi.DDT_BACKWARD)
+    assert seen.get("Oldroyd-BLog", 0) >= 5 and n_multi >= 1 and len(seen) >= 4, seen
+    assert n_schemes >= 10 and n_refused >= 1, (n_schemes, n_refused)
+    # a spot value: the Cylinder tutorial (SURVEY.md §8d C1)
+    (m,) = foamio.read_models(REF / "rheoFoam/Cylinder/Oldroyd-BLog/constant/constitutiveProperties")
+    assert (m.model, m.rho, m.etaS, m.etaP, m.lambda_) == (abi.MODEL_OLDROYD_B_LOG, 1.0, 0.59, 0.41, 0.7)
+    ctl, solver = foamio.read_schemes(REF / "rheoFoam/Cylinder/Oldroyd-BLog")
+    assert ctl.limiter == abi.LIMITER["cubista"] and solver == "PBiCG" and ctl.ddt == abi.DDT_EULER

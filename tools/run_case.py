@@ -3,9 +3,11 @@
 balance switched off): read constant/polyMesh and <time>/{U, theta, tau[, eigVals, eigVecs]}, run n steps of
 constitutiveEq::correct() on cuda:0, write the new time directory (theta, tau, eigVals, eigVecs) for restart / ParaView.
 
-    python tools/run_case.py CASE --time 0 --model Oldroyd-BLog --etaS 0.59 --etaP 0.41 --lambda 0.7 --dt 0.02 --steps 50
+    python tools/run_case.py CASE --time 0 --dt 0.02 --steps 50
 
-The flux is createPhi's (linear interpolation of U dotted with Sf).  Needs a CUDA device: there is no CPU path."""
+The model(s) come from constant/constitutiveProperties (one log-conformation model or a multiMode of them), the convection
+limiter, time scheme and solver controls from system/fvSchemes and system/fvSolution — like rheoFoam reads them; --model and
+the flags after it replace the dictionaries.  The flux is createPhi's (linear interpolation of U dotted with Sf).  Needs a CUDA device: there is no CPU path."""
 import argparse
 import sys
 from pathlib import Path
@@ -23,7 +25,7 @@ def main():
     ap.add_argument("case")
     ap.add_argument("--time", default="0")
     ap.add_argument("--name", default="", help="field name suffix (multi-region / multi-phase cases)")
-    ap.add_argument("--model", default="Oldroyd-BLog", choices=sorted(abi.MODEL_NAMES))
+    ap.add_argument("--model", default=None, choices=sorted(abi.MODEL_NAMES), help="override constant/constitutiveProperties")
     ap.add_argument("--etaS", type=float, default=0.0)
     ap.add_argument("--etaP", type=float, default=1.0)
     ap.add_argument("--lambda", dest="lambda_", type=float, default=1.0)
@@ -36,20 +38,31 @@ def main():
     ap.add_argument("--gz", action="store_true")
     a = ap.parse_args()
 
-    m, f = foamio.read_case(a.case, a.time, a.name)
-    extra = {k: (v if k == "ptt_function" else float(v)) for k, v in (kv.split("=", 1) for kv in a.param)}
-    model = cases.model_desc(a.model, etaS=a.etaS, etaP=a.etaP, lambda_=a.lambda_, **extra)
-    schemes = cases.scheme_ctl(a.limiter, "PBiCGStab", a.tolerance, ddt=a.ddt)
-    g = GpuStressModel(m, [model], schemes, 0)
-    g.upload_state(0, f["theta"], f["tau"], f["eigvals"], f["eigvecs"], theta_b=f["theta_b"])
+    case = Path(a.case)
+    if a.model:
+        extra = {k: (v if k == "ptt_function" else float(v)) for k, v in (kv.split("=", 1) for kv in a.param)}
+        models, names = [cases.model_desc(a.model, etaS=a.etaS, etaP=a.etaP, lambda_=a.lambda_, **extra)], [a.name]
+        schemes = cases.scheme_ctl(a.limiter, "PBiCGStab", a.tolerance, ddt=a.ddt)
+    else:
+        cp = case / "constant" / "constitutiveProperties"
+        models, names = foamio.read_models(cp), [a.name + n for n in foamio.mode_names(cp)]
+        schemes, solver = foamio.read_schemes(case, "theta" + names[0])
+        if solver != "PBiCGStab":
+            print(f"fvSolution selects {solver}; the GPU path solves with PBiCGStab + DILU (same controls)")
+    m, f = foamio.read_case(case, a.time, names[0])
+    per_mode = [f] + [foamio.read_case(case, a.time, n)[1] for n in names[1:]]
+    g = GpuStressModel(m, models, schemes, 0)
+    for mi, fm in enumerate(per_mode):
+        g.upload_state(mi, fm["theta"], fm["tau"], fm["eigvals"], fm["eigvecs"], theta_b=fm["theta_b"])
     g.upload_velocity(f["U"], f["U_b"], f["phi"])
     for n in range(a.steps):
         g.store_old_time()
         g.correct(a.dt)
         print(f"step {n + 1}: Krylov iterations {g.last_iterations()}")
     t_new = f"{float(a.time) + a.steps * a.dt:g}"
-    foamio.write_case(a.case, m, t_new, g.theta(), g.tau(0), f["U"], f["U_b"], theta_b=g.download(abi.FIELD_THETA_B), tau_b=g.download(abi.FIELD_TAU_B),
-                      eigvals=g.download(abi.FIELD_EIGVALS), eigvecs=g.download(abi.FIELD_EIGVECS), name=a.name, gz=a.gz)
+    for mi, n in enumerate(names):
+        foamio.write_case(case, m, t_new, g.theta(mi), g.tau(mi), f["U"], f["U_b"], theta_b=g.download(abi.FIELD_THETA_B, mi), tau_b=g.download(abi.FIELD_TAU_B, mi),
+                          eigvals=g.download(abi.FIELD_EIGVALS, mi), eigvecs=g.download(abi.FIELD_EIGVECS, mi), name=n, gz=a.gz)
     print(f"wrote {Path(a.case) / t_new}")
 
 
