@@ -7,7 +7,10 @@
 // PARITY UNPINNED: the reference cannot be built here (needs OpenFOAM-9, Eigen 3.2.9, MPI; none is
 // installed, no network) and ships no golden vectors for this path.  The oracle
 // is therefore pinned only (a) line-by-line against the reference sources cited at each function,
-// (b) against analytic material functions and algebraic identities (tests/test_oracle_*.py).
+// (b) against analytic material functions and algebraic identities (tests/test_oracle_*.py), (c) across reference files:
+// the steady state reached by the LOG models must satisfy the reference's NON-log conformation / stress equations
+// (RoliePoly.C, XPomPom.C; tests/test_oracle_analytic.py), (d) by partition invariance on tensor grids and on a piece of the
+// polyhedral polyMesh the reference ships (tests/test_unstructured.py).
 //
 // Conventions follow OpenFOAM: symmTensor = (xx,xy,xz,yy,yz,zz); tensor row-major; fields AoS;
 // face loops in face order; one scalar Krylov solve per valid component (segregated).
