@@ -1,0 +1,21 @@
+// ref_model.cpp — one translation unit per Log model (TEST INFRASTRUCTURE ONLY, see ref_ce.H).
+// Compiled with -DREF_MODEL_<name>; the function body is the reference's text, cut by oracle/Makefile from
+// constitutiveEqs/<family>/<name>/<name>.C ("void Foam::constitutiveEqs::<name>::correct" to end of file)
+// into oracle/_ref/gen/<name>_correct.inc.  boilerLog.H (included by that text) is the reference's file and
+// switches on PTTLog_H exactly as it does when PTTLog.C includes PTTLog.H.
+#if defined(REF_MODEL_PTTLog)
+#define PTTLog_H
+#endif
+#include "ref_ce.H"
+
+#if defined(REF_MODEL_Oldroyd_BLog)
+#include "Oldroyd_BLog_correct.inc"
+#elif defined(REF_MODEL_GiesekusLog)
+#include "GiesekusLog_correct.inc"
+#elif defined(REF_MODEL_PTTLog)
+#include "PTTLog_correct.inc"
+#elif defined(REF_MODEL_FENE_PLog)
+#include "FENE_PLog_correct.inc"
+#else
+#error "define REF_MODEL_<name>"
+#endif

@@ -1,0 +1,52 @@
+"""The cases on which the oracle (and the GPU path) are pinned against rheoTool's OWN stress-step text
+(oracle/_ref, built by `make -C oracle ref` where /root/reference exists).  Shared by
+tools/make_golden_reference.py (which writes tests/golden/reference_correct.npz) and tests/test_reference_pin.py.
+Small meshes on purpose: the fixture travels with the repo."""
+from __future__ import annotations
+
+import hashlib
+
+import numpy as np
+
+from rheotool_b200 import abi, cases
+
+
+def _with(spec, models, limiter):
+    spec.models = models
+    spec.schemes = cases.scheme_ctl(limiter, "PBiCGStab", 1e-15, relax=0.0)
+    return spec
+
+
+def _fixed_theta_walls(spec):
+    """theta fixedValue (0) on every wall instead of zeroGradient.  superbee's first row (alpha, beta) = (1/2, 1/2) does
+    not vanish at phi~ = 0 (limiters.H:77-82), and a wall-adjacent cell with zeroGradient theta and flow away from the wall
+    has phi~ = 1 - (tN - tP)/(2 grad.d + 1e-18) = 0 up to the rounding of its Gauss gradient: the reference algorithm itself
+    picks `upwind` or `row 0` by the last bit there (measured: ~40 faces of a 729-cell cavity differ between two builds of
+    the same text), so that combination is not a parity case for any implementation."""
+    for p in spec.grid.patches:
+        if p.theta_bc == abi.BC_ZERO_GRADIENT:
+            p.theta_bc = abi.BC_FIXED_VALUE
+    return spec
+
+
+# name -> (spec factory, limiter).  Every model whose correct() the reference harness compiles, every limiter row,
+# 2-D (empty patches, fixedValue inlet, zeroGradient outlet, linearExtrapolation walls) and 3-D meshes.
+REFERENCE_CASES = {
+    "OldroydBLog-2D-cubista": lambda: _with(cases.channel_2d(30, 12), [cases.model_desc("Oldroyd-BLog", 1.0, 0.59, 0.41, 0.7)], "cubista"),
+    "PTTLog-linear-zeta-2D-minmod": lambda: _with(cases.channel_2d(30, 12), [cases.model_desc("PTTLog", 1.0, 0.1, 0.9, 0.6, epsilon=0.25, zeta=0.1)], "minmod"),
+    "PTTLog-exponential-2D-smart": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("PTTLog", 1.0, 0.1, 0.9, 0.6, epsilon=0.25, zeta=0.05, ptt_function="exponential")], "smart"),
+    "PTTLog-generalized-2D-waceb": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("PTTLog", 1.0, 0.1, 0.9, 0.6, epsilon=0.25, zeta=0.0, ptt_function="generalized", ml_alpha=0.8, ml_beta=1.2)], "waceb"),
+    "GiesekusLog-3D-contraction-cubista": lambda: _with(cases.by_name("C3", 1 / 19), [cases.model_desc("GiesekusLog", 1.0, 0.01, 0.99, 0.1, alpha=0.2)], "cubista"),
+    "FENEPLog-3D-cavity-cubista": lambda: _with(cases.cube(9, "cavity", 1, "FENE-PLog"), [cases.model_desc("FENE-PLog", 1.0, 0.01, 0.99, 0.1, L2=100.0)], "cubista"),
+    "FENEPLog-3D-box-superbee": lambda: _with(_fixed_theta_walls(cases.cube(8, "box", 1, "FENE-PLog")), [cases.model_desc("FENE-PLog", 1.0, 0.01, 0.99, 0.1, L2=100.0)], "superbee"),
+    "OldroydBLog-3D-cavity-upwind": lambda: _with(cases.cube(8, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("Oldroyd-BLog", 1.0, 0.01, 0.99, 0.1)], "upwind"),
+}
+
+N_STEPS = 3   # correct() calls chained in the fixture (each is the first correct() of a new time step)
+
+
+def digest(*arrays) -> str:
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return h.hexdigest()[:16]
