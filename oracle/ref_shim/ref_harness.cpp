@@ -329,6 +329,18 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
         model.epsilon_ = dimensionedScalar("epsilon", mm->epsilon);
         model.zeta_ = dimensionedScalar("zeta", mm->zeta);
         model.L2_ = dimensionedScalar("L2", mm->L2);
+        // WhiteMetznerCYLog requires m = n, L = K, b = a (WhiteMetznerCYLog.C:132-140); the descriptor carries one set
+        model.K_ = model.L_ = dimensionedScalar("K", mm->wm_K);
+        model.n_ = model.m_ = dimensionedScalar("n", mm->model == RHEO_MODEL_XPOMPOM_LOG ? mm->xpp_n : mm->wm_n);
+        model.a_ = model.b_ = dimensionedScalar("a", mm->wm_a);
+        model.lambdaR_ = dimensionedScalar("lambdaR", mm->rp_lambdaR);
+        model.lambdaD_ = dimensionedScalar("lambdaD", mm->lambda);
+        model.chiMax_ = dimensionedScalar("chiMax", mm->rp_chiMax);
+        model.delta_ = dimensionedScalar("delta", mm->rp_delta);
+        if (mm->model == RHEO_MODEL_ROLIE_POLY_LOG) model.beta_ = dimensionedScalar("beta", mm->rp_beta);
+        model.lambdaS_ = dimensionedScalar("lambdaS", mm->xpp_lambdaS);
+        model.lambdaB_ = dimensionedScalar("lambdaB", mm->lambda);
+        model.q_ = dimensionedScalar("q", mm->xpp_q);
         model.correct();
     };
     switch (mm->model)
@@ -336,6 +348,10 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
         case RHEO_MODEL_OLDROYD_B_LOG: { constitutiveEqs::Oldroyd_BLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_GIESEKUS_LOG: { constitutiveEqs::GiesekusLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_FENE_P_LOG: { constitutiveEqs::FENE_PLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
+        case RHEO_MODEL_FENE_CR_LOG: { constitutiveEqs::FENE_CRLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
+        case RHEO_MODEL_WM_CY_LOG: { constitutiveEqs::WhiteMetznerCYLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
+        case RHEO_MODEL_ROLIE_POLY_LOG: { constitutiveEqs::RoliePolyLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
+        case RHEO_MODEL_XPOMPOM_LOG: { constitutiveEqs::XPomPomLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_PTT_LOG:
         {
             constitutiveEqs::PTTLog m(Uf, phif, tauf, thetaf, valsf, vecsf);

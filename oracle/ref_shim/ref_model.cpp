@@ -16,6 +16,14 @@
 #include "PTTLog_correct.inc"
 #elif defined(REF_MODEL_FENE_PLog)
 #include "FENE_PLog_correct.inc"
+#elif defined(REF_MODEL_FENE_CRLog)
+#include "FENE_CRLog_correct.inc"
+#elif defined(REF_MODEL_WhiteMetznerCYLog)
+#include "WhiteMetznerCYLog_correct.inc"
+#elif defined(REF_MODEL_RoliePolyLog)
+#include "RoliePolyLog_correct.inc"
+#elif defined(REF_MODEL_XPomPomLog)
+#include "XPomPomLog_correct.inc"
 #else
 #error "define REF_MODEL_<name>"
 #endif

@@ -39,10 +39,18 @@ REFERENCE_CASES = {
     "GiesekusLog-3D-contraction-cubista": lambda: _with(cases.by_name("C3", 1 / 19), [cases.model_desc("GiesekusLog", 1.0, 0.01, 0.99, 0.1, alpha=0.2)], "cubista"),
     "FENEPLog-3D-cavity-cubista": lambda: _with(cases.cube(9, "cavity", 1, "FENE-PLog"), [cases.model_desc("FENE-PLog", 1.0, 0.01, 0.99, 0.1, L2=100.0)], "cubista"),
     "FENEPLog-3D-box-superbee": lambda: _with(_fixed_theta_walls(cases.cube(8, "box", 1, "FENE-PLog")), [cases.model_desc("FENE-PLog", 1.0, 0.01, 0.99, 0.1, L2=100.0)], "superbee"),
+    "FENECRLog-3D-cavity-cubista": lambda: _with(cases.cube(7, "cavity", 1, "FENE-CRLog"), [cases.model_desc("FENE-CRLog", 1.0, 0.01, 0.99, 0.1, L2=50.0)], "cubista"),
+    "WhiteMetznerCYLog-2D-cubista": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("WhiteMetznerCYLog", 1.0, 0.01, 0.99, 0.1, wm_K=0.5, wm_n=0.6, wm_a=1.7)], "cubista"),
+    "RoliePolyLog-3D-cavity-minmod": lambda: _with(cases.cube(7, "cavity", 1, "Rolie-PolyLog"), [cases.model_desc("Rolie-PolyLog", 1.0, 0.01, 0.99, 0.1, rp_lambdaR=0.05, rp_beta=0.5, rp_delta=-0.5, rp_chiMax=0.0)], "minmod"),
+    "RoliePolyLog-chiMax-2D-cubista": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("Rolie-PolyLog", 1.0, 0.01, 0.99, 0.1, rp_lambdaR=0.2, rp_beta=0.5, rp_delta=-0.5, rp_chiMax=10.0)], "cubista"),
+    "XPomPomLog-n0-3D-cavity-cubista": lambda: _with(cases.cube(7, "cavity", 1, "XPomPomLog"), [cases.model_desc("XPomPomLog", 1.0, 0.01, 0.99, 0.1, alpha=0.15, xpp_lambdaS=0.04, xpp_q=3.0, xpp_n=0.0)], "cubista"),
+    "XPomPomLog-n1-2D-smart": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("XPomPomLog", 1.0, 0.01, 0.99, 0.5, alpha=0.1, xpp_lambdaS=0.3, xpp_q=2.0, xpp_n=1.0)], "smart"),
     "OldroydBLog-3D-cavity-upwind": lambda: _with(cases.cube(8, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("Oldroyd-BLog", 1.0, 0.01, 0.99, 0.1)], "upwind"),
 }
 
 N_STEPS = 3   # correct() calls chained in the fixture (each is the first correct() of a new time step)
+STORED_STEPS = (1, 3)          # steps whose fields the fixture holds
+MATRIX_CASE = "GiesekusLog-3D-contraction-cubista"   # the case whose assembled thetaEqn the fixture holds
 
 
 def digest(*arrays) -> str:

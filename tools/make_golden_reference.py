@@ -12,7 +12,7 @@ sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
 
 import helpers  # noqa: E402
 from oracle import ref  # noqa: E402
-from reference_cases import N_STEPS, REFERENCE_CASES, digest  # noqa: E402
+from reference_cases import MATRIX_CASE, N_STEPS, REFERENCE_CASES, STORED_STEPS, digest  # noqa: E402
 from rheotool_b200 import abi  # noqa: E402
 
 
@@ -40,11 +40,11 @@ def main():
         out[f"{name}/inputs"] = np.frombuffer(digest(s.U, s.Ub, s.phi, s.theta0, st["theta_b"], s.eigvals, s.eigvecs, [s.dt]).encode(), dtype=np.uint8)
         for k in range(N_STEPS):
             st = ref.correct(s.mesh.desc, spec.models[0], spec.schemes.limiter, s.dt, s.U, s.Ub, s.phi, st["theta"], st["theta_b"],
-                             st["tau"], st["tau_b"], st["eigvals"], st["eigvecs"], want_matrix=(k == 0))
-            if k == 0:
+                             st["tau"], st["tau_b"], st["eigvals"], st["eigvecs"], want_matrix=(k == 0 and name == MATRIX_CASE))
+            if k == 0 and name == MATRIX_CASE:
                 for f in ("lower", "upper", "diag", "source", "internalCoeffs", "boundaryCoeffs"):
                     out[f"{name}/matrix/{f}"] = st[f]
-            for f in ("theta", "tau", "theta_b", "tau_b"):
+            for f in ("theta", "tau", "theta_b", "tau_b") if k + 1 in STORED_STEPS else ():
                 out[f"{name}/step{k + 1}/{f}"] = st[f]
         print(name, s.mesh.n_cells, "cells")
     np.savez_compressed(ROOT / "tests" / "golden" / "reference_correct.npz", **out)
