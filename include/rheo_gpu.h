@@ -49,6 +49,8 @@ extern "C" {
 #define RHEO_MODEL_ROLIE_POLY_LOG 6  /* Rolie-Poly/Rolie-PolyLog/RoliePolyLog.C:130-215 (lambda = lambdaD) */
 #define RHEO_MODEL_XPOMPOM_LOG   7   /* XPomPom/XPomPomLog/XPomPomLog.C:130-198 (lambda = lambdaB, alpha = anisotropy) */
 
+#define RHEO_MODEL_SARAMITO_LOG  8   /* otherModels/Saramito/SaramitoLog/SaramitoLog.C:143-245 (elasto-viscoplastic: the relaxation
+                                        term is switched by max(0, (|tau_d| - tau0)/(k |tau_d|^n))^(1/n) of the CURRENT tau) */
 /* PTTLog destructionFunctionType (PTT/PTTLog/PTTLog.C:41-50,190-237) */
 #define RHEO_PTT_LINEAR      0
 #define RHEO_PTT_EXPONENTIAL 1
@@ -82,6 +84,10 @@ typedef struct RheoModelDesc {
                                m = n, L = K, b = a (WhiteMetznerCYLog.C:132-140: the caller checks and passes one set) */
     double  rp_lambdaR, rp_beta, rp_delta, rp_chiMax;   /* Rolie-PolyLog (RoliePolyLog.C:114-121)            */
     double  xpp_lambdaS, xpp_q, xpp_n;                  /* XPomPomLog   (XPomPomLog.C:115-122)               */
+    double  sar_tau0, sar_k, sar_n;   /* SaramitoLog yield stress, consistency (viscosity units; = etaP when n == 1, SaramitoLog.C:116),
+                                         index; epsilon / zeta / ptt_function (linear | exponential, only with n == 1) as for PTTLog */
+    double  sar_dims[3];              /* SaramitoLog `dims` (1 = valid geometric direction, SaramitoLog.C:117-119,128-130)           */
+    int32_t sar_ptt;                  /* SaramitoLog PTTfunction: 0 none, 1 linear, 2 exponential (SaramitoLog.C:133-165)            */
 } RheoModelDesc;
 
 typedef struct RheoSchemeCtl {

@@ -305,10 +305,12 @@ double mittag_leffler(const Model& mo, double zi) {
 
 // right-hand side of the theta equation for one cell; returns the FENE-P / FENE-CR f (else 0)
 //   Oldroyd_BLog.C:146-163, GiesekusLog.C:142-157, PTTLog.C:190-251, FENE_PLog.C:142-163, FENE_CRLog.C:141-163
-double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const T9& R, const T9& Lam, double* rhs6) {
+//   SaramitoLog.C:150-238 (tau6 = the model's CURRENT tau of the cell; unused by the other models)
+double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const T9& R, const T9& Lam, double* rhs6, const double* tau6 = nullptr) {
     const RheoModelDesc& d = mo.d;
     T9 omega, B;
-    decompose_gradU_cell(L, R, Lam, d.zeta, d.model == RHEO_MODEL_PTT_LOG, omega, B);
+    // boilerLog.H:26: the zeta-branch is compiled for PTTLog and SaramitoLog
+    decompose_gradU_cell(L, R, Lam, d.zeta, d.model == RHEO_MODEL_PTT_LOG || d.model == RHEO_MODEL_SARAMITO_LOG, omega, B);
     const T9 I = identity();
     const T9 th = from_sym(theta6);
     T9 acc = add(sub(mul(omega, th), mul(th, omega)), scale(2.0, B));
@@ -384,6 +386,30 @@ double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const 
             acc = add(acc, scale((1.0 / d.lambda) * f, mul(mul(R, sub(inv(Lam), I)), transpose(R))));
             break;
         }
+        case RHEO_MODEL_SARAMITO_LOG: {   // SaramitoLog.C:153-238
+            // 2nd invariant of the deviatoric stress: mag(tau - ItensorCorr*tr(tau)/nDims)/sqrt(2), ItensorCorr = diag(dims)
+            static const double zero6[6] = {0, 0, 0, 0, 0, 0};
+            if (!tau6) tau6 = zero6;   // stand-alone per-cell entry point (orc_model_rhs) without a stress state
+            const double nDims = d.sar_dims[0] + d.sar_dims[1] + d.sar_dims[2];
+            const double trT = tau6[0] + tau6[3] + tau6[5];
+            const double t6[6] = {tau6[0] - d.sar_dims[0] * trT / nDims, tau6[1], tau6[2], tau6[3] - d.sar_dims[1] * trT / nDims, tau6[4],
+                                  tau6[5] - d.sar_dims[2] * trT / nDims};
+            const double tauDMag = std::sqrt(t6[0] * t6[0] + t6[3] * t6[3] + t6[5] * t6[5] + 2.0 * (t6[1] * t6[1] + t6[2] * t6[2] + t6[4] * t6[4])) / std::sqrt(2.);
+            double fac;
+            if (d.sar_n == 1.) fac = std::max(0., (tauDMag - d.sar_tau0) / (d.sar_k * tauDMag + 1e-16));
+            else fac = std::pow(std::max(0., (tauDMag - d.sar_tau0) / (d.sar_k * std::pow(tauDMag, d.sar_n) + 1e-16)), 1. / d.sar_n);
+            double Y = 1.;   // PTT function (only with n == 1, SaramitoLog.C:133-165)
+            if (d.sar_n == 1. && d.sar_ptt != 0) {
+                const double z = (d.epsilon / (1 - d.zeta)) * (tr(mul(mul(R, Lam), transpose(R))) - 3.);
+                Y = d.sar_ptt == 1 ? 1. + z : std::exp(z);
+            }
+            // thetaEqn -= symm(...)  ->  source += V * symm(...): the term joins the right-hand side with a plus sign
+            double g6[6], a6[6];
+            symm(acc, a6);
+            symm(scale((fac * d.etaP / d.lambda) * Y, mul(mul(R, sub(inv(Lam), I)), transpose(R))), g6);
+            for (int q = 0; q < 6; ++q) rhs6[q] = a6[q] + g6[q];
+            return 0.;
+        }
     }
     symm(acc, rhs6);
     return f;
@@ -400,7 +426,7 @@ void tau_cell(const Model& mo, const T9& R, const T9& Lam, double fOld, double* 
         const double a = d.L2 / (d.L2 - 3.);
         symm(sub(scale(fOld, A), scale(a, I)), s);
     } else {
-        if (d.model == RHEO_MODEL_PTT_LOG) coef = d.etaP / (d.lambda * (1 - d.zeta));
+        if (d.model == RHEO_MODEL_PTT_LOG || d.model == RHEO_MODEL_SARAMITO_LOG) coef = d.etaP / (d.lambda * (1 - d.zeta));   // SaramitoLog.C:242
         if (d.model == RHEO_MODEL_FENE_CR_LOG) coef = (d.etaP / d.lambda) * fOld;   // FENE_CRLog.C:174 (f of before the solve)
         if (d.model == RHEO_MODEL_WM_CY_LOG) coef = fOld;                            // WhiteMetznerCYLog.C:207
         if (d.model == RHEO_MODEL_ROLIE_POLY_LOG && d.rp_chiMax > 1.) {              // RoliePolyLog.C:203-212 (updated tr A)
@@ -724,7 +750,7 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             std::memcpy(L.v, &rk.L[(size_t)9 * c], 72);
             std::memcpy(Rm.v, &mo.eigVecs[(size_t)9 * c], 72);
             std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
-            rk.fFene[c] = model_rhs_cell(mo.model, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c]);
+            rk.fFene[c] = model_rhs_cell(mo.model, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c], &mo.tau[(size_t)6 * c]);
         }
     });
 

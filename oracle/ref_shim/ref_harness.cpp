@@ -341,6 +341,19 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
         model.lambdaS_ = dimensionedScalar("lambdaS", mm->xpp_lambdaS);
         model.lambdaB_ = dimensionedScalar("lambdaB", mm->lambda);
         model.q_ = dimensionedScalar("q", mm->xpp_q);
+        if (mm->model == RHEO_MODEL_SARAMITO_LOG)
+        {
+            // SaramitoLog.C:113-130 (constructor)
+            model.tau0_ = dimensionedScalar("tau0", mm->sar_tau0);
+            model.n_ = dimensionedScalar("n", mm->sar_n);
+            model.k_ = dimensionedScalar("k", mm->sar_k);
+            model.nDims = scalar(mm->sar_dims[0] + mm->sar_dims[1] + mm->sar_dims[2]);
+            model.ItensorCorr = dimensionedSymmTensor("Identity", symm(tensor::I));
+            model.ItensorCorr.value().xx() = mm->sar_dims[0];
+            model.ItensorCorr.value().yy() = mm->sar_dims[1];
+            model.ItensorCorr.value().zz() = mm->sar_dims[2];
+            model.funcPTT = mm->sar_ptt;
+        }
         model.correct();
     };
     switch (mm->model)
@@ -352,6 +365,7 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
         case RHEO_MODEL_WM_CY_LOG: { constitutiveEqs::WhiteMetznerCYLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_ROLIE_POLY_LOG: { constitutiveEqs::RoliePolyLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_XPOMPOM_LOG: { constitutiveEqs::XPomPomLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
+        case RHEO_MODEL_SARAMITO_LOG: { constitutiveEqs::SaramitoLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_PTT_LOG:
         {
             constitutiveEqs::PTTLog m(Uf, phif, tauf, thetaf, valsf, vecsf);

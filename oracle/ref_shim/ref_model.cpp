@@ -6,6 +6,9 @@
 #if defined(REF_MODEL_PTTLog)
 #define PTTLog_H
 #endif
+#if defined(REF_MODEL_SaramitoLog)
+#define SaramitoLog_H
+#endif
 #include "ref_ce.H"
 
 #if defined(REF_MODEL_Oldroyd_BLog)
@@ -24,6 +27,8 @@
 #include "RoliePolyLog_correct.inc"
 #elif defined(REF_MODEL_XPomPomLog)
 #include "XPomPomLog_correct.inc"
+#elif defined(REF_MODEL_SaramitoLog)
+#include "SaramitoLog_correct.inc"
 #else
 #error "define REF_MODEL_<name>"
 #endif

@@ -13,7 +13,7 @@ _LIB_PATH = Path(__file__).resolve().parent / "librheo_b200.so"
 # ---- constants (keep in sync with include/*.h) ---------------------------------------------------
 PATCH_PATCH, PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2, 3
 BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSOR = 0, 1, 2, 3, 4
-MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG = 0, 1, 2, 3, 4, 5, 6, 7
+MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG, MODEL_SARAMITO_LOG = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
 LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}
 DDT_EULER, DDT_BACKWARD = 0, 1
@@ -30,6 +30,7 @@ MODEL_NAMES = {
     "WhiteMetznerCYLog": MODEL_WM_CY_LOG,
     "Rolie-PolyLog": MODEL_ROLIE_POLY_LOG,
     "XPomPomLog": MODEL_XPOMPOM_LOG,
+    "SaramitoLog": MODEL_SARAMITO_LOG,
 }
 
 
@@ -66,7 +67,9 @@ class RheoModelDesc(C.Structure):
                 ("ml_max_iter", C.c_int32), ("L2", C.c_double),
                 ("wm_K", C.c_double), ("wm_n", C.c_double), ("wm_a", C.c_double),
                 ("rp_lambdaR", C.c_double), ("rp_beta", C.c_double), ("rp_delta", C.c_double), ("rp_chiMax", C.c_double),
-                ("xpp_lambdaS", C.c_double), ("xpp_q", C.c_double), ("xpp_n", C.c_double)]
+                ("xpp_lambdaS", C.c_double), ("xpp_q", C.c_double), ("xpp_n", C.c_double),
+                ("sar_tau0", C.c_double), ("sar_k", C.c_double), ("sar_n", C.c_double), ("sar_dims", C.c_double * 3),
+                ("sar_ptt", C.c_int32)]
 
 
 class RheoSchemeCtl(C.Structure):

@@ -263,6 +263,7 @@ struct SourceArgs {
     int solvedIdx[6];       // component -> index among the solved components, -1 if not solved (2-D: xz, yz)
     const double* gradU; const double* theta; const double* thetaOld; const double* lam; const double* R;
     double* bsrc; double* fFene;
+    const double* tau;      // the model's current tau planes (read by SaramitoLog only)
     // EXT-OF9 backwardDdtScheme: source = (1/dt) V (c0 theta_old - c00 theta_oldold); Euler: (1/dt) theta_old V
     int backward; double c0, c00; const double* thetaOldOld;
     // sum of theta over the cells per solved component (gAverage(psi) of the solver's normFactor): theta is in registers
@@ -294,7 +295,15 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, Sourc
         const double V = m.V[c];
         // g[3k+d] = d_d U_k  ->  L_ij = d_i U_j = g[3j+i]
         const double L[9] = {g[0], g[3], g[6], g[1], g[4], g[7], g[2], g[5], g[8]};
-        const double f = model_rhs<MODEL>(a.mp, L, th, Rm, lm, rhs);
+        double f;
+        if constexpr (MODEL == RHEO_MODEL_SARAMITO_LOG) {
+            double tc[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) tc[k] = a.tau[(size_t)k * m.NP + c];
+            f = model_rhs<MODEL>(a.mp, L, th, Rm, lm, rhs, tc);
+        } else {
+            f = model_rhs<MODEL>(a.mp, L, th, Rm, lm, rhs);
+        }
         a.fFene[c] = f;
 #pragma unroll
         for (int k = 0; k < 6; ++k) {

@@ -16,7 +16,9 @@ namespace rk {
 struct ModelParams {
     int model, ptt_function, ml_max_iter;
     double etaP, lambda, alpha, epsilon, zeta, L2, ml_rtol, gamma_beta, wmK, wmN, wmA,
-        rpLambdaR, rpBeta, rpDelta, rpChiMax, xppLambdaS, xppQ, xppN;
+        rpLambdaR, rpBeta, rpDelta, rpChiMax, xppLambdaS, xppQ, xppN,
+        sarTau0, sarK, sarN, sarD0, sarD1, sarD2;   // SaramitoLog.C:113-130
+    int sarPtt;                                     // 0 none, 1 linear, 2 exponential (n == 1 only)
     const double* gamma_vals;   // device table Gamma(alpha k + beta), PTTLog.C:143-170
 };
 
@@ -69,12 +71,13 @@ __device__ __forceinline__ double mittag_leffler(const ModelParams& mp, double z
 // rhs6 = symm(Omega.theta - theta.Omega + 2B + G);  returns the FENE-P / FENE-CR f (0 otherwise).
 // MODEL is a compile-time constant: every model gets its own instance of the source kernel (no dead code, fewer registers).
 // L: grad(U), L_ij = d_i U_j.  R: eigenvectors in columns.  lam: exp(eigenvalues).
+// tau6: the model's current tau of the cell (SaramitoLog only; nullptr otherwise).
 template <int MODEL>
 __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double* L, const double* th6, const double* R,
-                                            const double* lam, double* rhs6) {
-    // X = L^T (- zeta symm(L) for PTT)          boilerLog.H:26-32
+                                            const double* lam, double* rhs6, const double* tau6 = nullptr) {
+    // X = L^T (- zeta symm(L) for PTT and Saramito)          boilerLog.H:26-32
     double X[9] = {L[0], L[3], L[6], L[1], L[4], L[7], L[2], L[5], L[8]};
-    if (MODEL == RHEO_MODEL_PTT_LOG) {
+    if (MODEL == RHEO_MODEL_PTT_LOG || MODEL == RHEO_MODEL_SARAMITO_LOG) {
         const double z = mp.zeta;
         const double sxy = 0.5 * (L[1] + L[3]), sxz = 0.5 * (L[2] + L[6]), syz = 0.5 * (L[5] + L[7]);
         X[0] -= z * L[0]; X[4] -= z * L[4]; X[8] -= z * L[8];
@@ -132,6 +135,26 @@ __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double*
         else if (mp.ptt_function == RHEO_PTT_EXPONENTIAL) Y = exp(z);
         else Y = mp.gamma_beta * mittag_leffler(mp, z);
         g0 = il * (i0 - 1.0) * Y; g1 = il * (i1 - 1.0) * Y; g2 = il * (i2 - 1.0) * Y;
+        rdrt_sym(R, g0, g1, g2, G6);
+    } else if (MODEL == RHEO_MODEL_SARAMITO_LOG) {
+        // SaramitoLog.C:153-238: `thetaEqn -= symm((fac etaP/lambda) Y R (1/Lambda - I) R^T)` adds the term to the right-hand
+        // side; fac = max(0, (|tau_d| - tau0)/(k |tau_d|^n + 1e-16))^(1/n) of the CURRENT tau, |tau_d| = mag(dev tau)/sqrt(2)
+        const double nDims = mp.sarD0 + mp.sarD1 + mp.sarD2;
+        const double trT = tau6[0] + tau6[3] + tau6[5];
+        const double d0 = tau6[0] - mp.sarD0 * trT / nDims, d3 = tau6[3] - mp.sarD1 * trT / nDims, d5 = tau6[5] - mp.sarD2 * trT / nDims;
+        const double tauDMag = sqrt(d0 * d0 + d3 * d3 + d5 * d5 + 2.0 * (tau6[1] * tau6[1] + tau6[2] * tau6[2] + tau6[4] * tau6[4])) / sqrt(2.0);
+        double fac;
+        if (mp.sarN == 1.0) fac = fmax(0.0, (tauDMag - mp.sarTau0) / (mp.sarK * tauDMag + 1e-16));
+        else fac = pow(fmax(0.0, (tauDMag - mp.sarTau0) / (mp.sarK * pow(tauDMag, mp.sarN) + 1e-16)), 1.0 / mp.sarN);
+        double Y = 1.0;
+        if (mp.sarN == 1.0 && mp.sarPtt != 0) {
+            double A6[6];
+            rdrt_sym(R, lx, ly, lz, A6);
+            const double z = (mp.epsilon / (1.0 - mp.zeta)) * ((A6[0] + A6[3] + A6[5]) - 3.0);
+            Y = mp.sarPtt == 1 ? 1.0 + z : exp(z);
+        }
+        const double cf = (fac * mp.etaP / mp.lambda) * Y;
+        g0 = cf * (i0 - 1.0); g1 = cf * (i1 - 1.0); g2 = cf * (i2 - 1.0);
         rdrt_sym(R, g0, g1, g2, G6);
     } else if (MODEL == RHEO_MODEL_FENE_CR_LOG) {   // FENE_CRLog.C:143-163: (f/lambda) R (1/Lambda - I) R^T
         double A6[6];
@@ -257,7 +280,7 @@ __device__ __forceinline__ void tau_from_eig(const ModelParams& mp, const double
         tau6[0] = coef * (fOld * A6[0] - a); tau6[1] = coef * (fOld * A6[1]); tau6[2] = coef * (fOld * A6[2]);
         tau6[3] = coef * (fOld * A6[3] - a); tau6[4] = coef * (fOld * A6[4]); tau6[5] = coef * (fOld * A6[5] - a);
     } else {
-        if (MODEL == RHEO_MODEL_PTT_LOG) coef = mp.etaP / (mp.lambda * (1.0 - mp.zeta));
+        if (MODEL == RHEO_MODEL_PTT_LOG || MODEL == RHEO_MODEL_SARAMITO_LOG) coef = mp.etaP / (mp.lambda * (1.0 - mp.zeta));   // SaramitoLog.C:242
         if (MODEL == RHEO_MODEL_FENE_CR_LOG) coef = (mp.etaP / mp.lambda) * fOld;   // FENE_CRLog.C:174: f of BEFORE the solve
         if (MODEL == RHEO_MODEL_WM_CY_LOG) coef = fOld;                              // WhiteMetznerCYLog.C:207: etaP/lambda of BEFORE the solve
         if (MODEL == RHEO_MODEL_ROLIE_POLY_LOG && mp.rpChiMax > 1.0) {               // RoliePolyLog.C:203-212: finite extensibility, NEW tr(A)

@@ -492,7 +492,7 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         ModeDev& md = h->modes[mi];
         md.desc = modes[mi];
         const RheoModelDesc& q = modes[mi];
-        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_XPOMPOM_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
+        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_SARAMITO_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
         if (!(q.lambda > 0)) return fail("rheo_gpu_create: lambda must be positive");
         ModelParams& mp = md.mp;
         mp.model = q.model; mp.ptt_function = q.ptt_function; mp.ml_max_iter = q.ml_max_iter;
@@ -501,6 +501,13 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         mp.wmK = q.wm_K; mp.wmN = q.wm_n; mp.wmA = q.wm_a;
         mp.rpLambdaR = q.rp_lambdaR; mp.rpBeta = q.rp_beta; mp.rpDelta = q.rp_delta; mp.rpChiMax = q.rp_chiMax;
         mp.xppLambdaS = q.xpp_lambdaS; mp.xppQ = q.xpp_q; mp.xppN = q.xpp_n;
+        mp.sarTau0 = q.sar_tau0; mp.sarK = q.sar_k; mp.sarN = q.sar_n; mp.sarD0 = q.sar_dims[0]; mp.sarD1 = q.sar_dims[1]; mp.sarD2 = q.sar_dims[2];
+        mp.sarPtt = q.sar_n == 1.0 ? q.sar_ptt : 0;   // SaramitoLog.C:161-165: no PTT function when n != 1
+        if (q.model == RHEO_MODEL_SARAMITO_LOG) {
+            if (!(q.sar_n > 0 && q.sar_k > 0 && q.sar_tau0 >= 0)) return fail("rheo_gpu_create: SaramitoLog needs n > 0, k > 0 and tau0 >= 0");
+            if (!(q.sar_dims[0] + q.sar_dims[1] + q.sar_dims[2] > 0)) return fail("rheo_gpu_create: SaramitoLog needs at least one valid direction in dims");
+            if (q.sar_ptt < 0 || q.sar_ptt > 2) return fail("The PTT function specified does not exist. Available PTT functions are: none linear exponential");
+        }
         if (q.model == RHEO_MODEL_ROLIE_POLY_LOG && !(q.rp_lambdaR > 0)) return fail("rheo_gpu_create: Rolie-PolyLog needs lambdaR > 0");
         if (q.model == RHEO_MODEL_XPOMPOM_LOG && !(q.xpp_lambdaS > 0 && q.xpp_q > 0)) return fail("rheo_gpu_create: XPomPomLog needs lambdaS > 0 and q > 0");
         if (q.model == RHEO_MODEL_WM_CY_LOG && !(q.wm_a > 0)) return fail("rheo_gpu_create: WhiteMetznerCYLog needs a > 0");
@@ -819,7 +826,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
                 sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
                 sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
-                sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>();
+                sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>(); sa.tau = md.tau.as<double>();
                 sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
                 const int srcGrid = std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms);
                 switch (md.mp.model) {
@@ -830,6 +837,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                     case RHEO_MODEL_FENE_CR_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_CR_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                     case RHEO_MODEL_WM_CY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                     case RHEO_MODEL_ROLIE_POLY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_ROLIE_POLY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                    case RHEO_MODEL_SARAMITO_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_SARAMITO_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                     default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_XPOMPOM_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                 }
             }
@@ -896,6 +904,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             case RHEO_MODEL_FENE_CR_LOG: RK_EIG(RHEO_MODEL_FENE_CR_LOG); break;
             case RHEO_MODEL_WM_CY_LOG: RK_EIG(RHEO_MODEL_WM_CY_LOG); break;
             case RHEO_MODEL_ROLIE_POLY_LOG: RK_EIG(RHEO_MODEL_ROLIE_POLY_LOG); break;
+            case RHEO_MODEL_SARAMITO_LOG: RK_EIG(RHEO_MODEL_SARAMITO_LOG); break;
             default: RK_EIG(RHEO_MODEL_XPOMPOM_LOG); break;
         }
 #undef RK_EIG

@@ -3,7 +3,7 @@
 
   Registered type names (constant/constitutiveProperties -> parameters -> type):
       Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  FENE-CRLogGPU
-      WhiteMetznerCYLogGPU  Rolie-PolyLogGPU  XPomPomLogGPU  multiModeLogGPU
+      WhiteMetznerCYLogGPU  Rolie-PolyLogGPU  XPomPomLogGPU  SaramitoLogGPU  multiModeLogGPU
   Dictionary keys are those of the CPU models (Oldroyd_BLog.C:114-119,
   GiesekusLog.C:117, PTTLog.C:129-139, FENE_PLog.C:114-119, multiMode.C:73-92);
   fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler or backward,
@@ -46,6 +46,7 @@ namespace constitutiveEqs
     RHEO_GPU_REGISTER(WhiteMetznerCYLogGPU, "WhiteMetznerCYLogGPU")
     RHEO_GPU_REGISTER(RoliePolyLogGPU, "Rolie-PolyLogGPU")
     RHEO_GPU_REGISTER(XPomPomLogGPU, "XPomPomLogGPU")
+    RHEO_GPU_REGISTER(SaramitoLogGPU, "SaramitoLogGPU")
     RHEO_GPU_REGISTER(multiModeLogGPU, "multiModeLogGPU")
 }
 }
@@ -131,6 +132,30 @@ void LogConformationGPU::readMode(const word& type, const dictionary& dict, Rheo
         m.alpha       = dimensionedScalar(dict.lookup("alpha")).value();
         m.xpp_q       = dimensionedScalar(dict.lookup("q")).value();
         m.xpp_n       = dimensionedScalar(dict.lookup("n")).value();
+    }
+    else if (type == "SaramitoLogGPU" || type == "SaramitoLog")          // SaramitoLog.C:108-165
+    {
+        m.model    = RHEO_MODEL_SARAMITO_LOG;
+        m.epsilon  = dimensionedScalar(dict.lookup("epsilon")).value();
+        m.zeta     = dimensionedScalar(dict.lookup("zeta")).value();
+        m.sar_tau0 = dimensionedScalar(dict.lookup("tau0")).value();
+        m.sar_n    = dimensionedScalar(dict.lookup("n")).value();
+        m.sar_k    = (m.sar_n == 1) ? m.etaP : dimensionedScalar(dict.lookup("k")).value();   // :116
+        const vector dims(dict.lookup("dims"));
+        m.sar_dims[0] = dims.x(); m.sar_dims[1] = dims.y(); m.sar_dims[2] = dims.z();
+        m.sar_ptt = 0;
+        if (m.sar_n == 1)                                                 // :133-165 (no PTT function when n != 1)
+        {
+            const word f(dict.lookup("PTTfunction"));
+            if (f == "none") m.sar_ptt = 0;
+            else if (f == "linear") m.sar_ptt = 1;
+            else if (f == "exponential") m.sar_ptt = 2;
+            else
+            {
+                FatalErrorInFunction << "\nThe PTT function specified does not exist.\n" << "\nAvailable PTT functions are:\n"
+                    << "\n. none" << "\n. linear" << "\n. exponential" << abort(FatalError);
+            }
+        }
     }
     else
     {

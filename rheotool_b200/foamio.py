@@ -352,6 +352,18 @@ def _read_one_model(d: FoamDict, at: str):
         if m_ != n or K != L or a != b:
             raise FoamError("The Log version of the WhiteMetznerCY model can only be used if:  m=n   and   K=L   and   a=b")
         kw.update(wm_K=K, wm_n=n, wm_a=a)
+    elif ty == "SaramitoLog":         # SaramitoLog.C:108-165
+        n = sc("n")
+        dims = d.get(f"{at}/dims")
+        if dims is None:
+            raise FoamError(f"{d.path}: keyword {at}/dims is undefined")
+        kw.update(epsilon=sc("epsilon"), zeta=sc("zeta"), sar_tau0=sc("tau0"), sar_n=n, sar_k=None if n == 1.0 else sc("k"),
+                  sar_dims=tuple(float(t) for t in dims.replace("(", " ").replace(")", " ").split()))
+        if n == 1.0:
+            fn = d.get(f"{at}/PTTfunction")
+            if fn not in ("none", "linear", "exponential"):
+                raise FoamError(f"{d.path}: The PTT function specified does not exist. Available PTT functions are: none linear exponential")
+            kw.update(sar_ptt=fn)
     return cases.model_desc(ty, **kw)
 
 

@@ -45,8 +45,23 @@ REFERENCE_CASES = {
     "RoliePolyLog-chiMax-2D-cubista": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("Rolie-PolyLog", 1.0, 0.01, 0.99, 0.1, rp_lambdaR=0.2, rp_beta=0.5, rp_delta=-0.5, rp_chiMax=10.0)], "cubista"),
     "XPomPomLog-n0-3D-cavity-cubista": lambda: _with(cases.cube(7, "cavity", 1, "XPomPomLog"), [cases.model_desc("XPomPomLog", 1.0, 0.01, 0.99, 0.1, alpha=0.15, xpp_lambdaS=0.04, xpp_q=3.0, xpp_n=0.0)], "cubista"),
     "XPomPomLog-n1-2D-smart": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("XPomPomLog", 1.0, 0.01, 0.99, 0.5, alpha=0.1, xpp_lambdaS=0.3, xpp_q=2.0, xpp_n=1.0)], "smart"),
+    "SaramitoLog-n075-2D-cubista": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("SaramitoLog", 1.0, 0.01, 0.99, 0.1, sar_tau0=2.5, sar_k=1.5, sar_n=0.75, sar_dims=(1, 1, 0))], "cubista"),
+    "SaramitoLog-n1-linearPTT-3D-minmod": lambda: _with(cases.cube(7, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("SaramitoLog", 1.0, 0.01, 0.99, 0.1, epsilon=0.1, zeta=0.1, sar_tau0=1.0, sar_n=1.0, sar_ptt="linear")], "minmod"),
+    "SaramitoLog-n1-expPTT-3D-cubista": lambda: _with(cases.cube(7, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("SaramitoLog", 1.0, 0.01, 0.99, 0.1, epsilon=0.1, zeta=0.05, sar_tau0=1.0, sar_n=1.0, sar_ptt="exponential")], "cubista"),
     "OldroydBLog-3D-cavity-upwind": lambda: _with(cases.cube(8, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("Oldroyd-BLog", 1.0, 0.01, 0.99, 0.1)], "upwind"),
 }
+
+def make_setup(name):
+    """(spec, Setup) of a case.  SaramitoLog reads its CURRENT tau (yield criterion), so those cases start from the stress
+    of the initial conformation tensor instead of tau = 0 (which would switch the relaxation term off in the first call)."""
+    from helpers import Setup
+    from oracle import oracle as orc
+    spec = REFERENCE_CASES[name]()
+    s = Setup(spec)
+    if spec.models[0].model == abi.MODEL_SARAMITO_LOG:
+        s.tau0 = orc.tau_from_eig(spec.models[0], s.eigvecs, s.eigvals)
+    return spec, s
+
 
 N_STEPS = 3   # correct() calls chained in the fixture (each is the first correct() of a new time step)
 STORED_STEPS = (1, 3)          # steps whose fields the fixture holds

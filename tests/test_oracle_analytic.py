@@ -209,3 +209,40 @@ def test_ptt_generalized_reduces_to_exponential_for_alpha_beta_one():
     r1, _ = orc.model_rhs(m_exp, L, th, vecs, vals)
     r2, _ = orc.model_rhs(m_gen, L, th, vecs, vals)
     assert np.abs(r1 - r2).max() < 1e-10 * np.abs(r1).max()
+
+
+@pytest.mark.parametrize("n,k,tau0", [(1.0, None, 0.3), (0.75, 1.5, 0.4)])
+def test_saramito_log_steady_state_satisfies_the_stress_form(n, k, tau0):
+    """Cross-file pin for SaramitoLog (otherModels/Saramito/SaramitoLog/SaramitoLog.C:143-245): above the yield stress the
+    steady tau of the LOG oracle must satisfy the reference's NON-log stress equation (otherModels/Saramito/Saramito.C:
+    174-192, zeta = 0, no PTT function):  tau.L + L^T.tau + (etaP/lambda) 2D - fac (etaP/lambda) tau = 0,
+    fac = max(0, (|tau_d| - tau0)/(k |tau_d|^n))^(1/n), |tau_d| = mag(dev tau)/sqrt(2)  (Saramito.C:143,160-171)."""
+    etaP, lam, gd = 1.0, 0.5, 2.0
+    model = cases.model_desc("SaramitoLog", etaS=0.1, etaP=etaP, lambda_=lam, sar_tau0=tau0, sar_n=n, sar_k=k, sar_dims=(1, 1, 1))
+    kappa = np.zeros((3, 3)); kappa[0, 1] = gd
+    oc, _ = homogeneous_case(model, kappa, n_steps=6000)
+    tau = sym6(oc.get(0, 0, abi.FIELD_TAU)[0])
+    L = kappa.T                                   # L_ij = d_i U_j
+    dev = tau - np.eye(3) * np.trace(tau) / 3.0
+    tauDMag = np.sqrt((dev * dev).sum()) / np.sqrt(2.0)
+    assert tauDMag > tau0                         # yielded: the relaxation term is active
+    kk = model.sar_k
+    fac = max(0.0, (tauDMag - tau0) / (kk * tauDMag ** n)) ** (1.0 / n)
+    res = tau @ L + L.T @ tau + (etaP / lam) * (L + L.T) - fac * (etaP / lam) * tau
+    assert np.abs(res).max() <= 1e-7 * np.abs(tau).max() * gd
+
+
+def test_saramito_log_below_yield_is_elastic():
+    """Below the yield stress fac = 0 (SaramitoLog.C:160-171): no relaxation, the conformation tensor follows the
+    upper-convected kinematics exactly: simple shear from rest gives A_xy = gd t, A_xx = 1 + (gd t)^2 (first order in time
+    for the Euler scheme: the bar is the time-step error)."""
+    etaP, lam, gd = 1.0, 0.5, 0.2
+    model = cases.model_desc("SaramitoLog", etaS=0.1, etaP=etaP, lambda_=lam, sar_tau0=50.0, sar_n=1.0, sar_dims=(1, 1, 1))
+    kappa = np.zeros((3, 3)); kappa[0, 1] = gd
+    steps, dtl = 400, 0.005
+    oc, _ = homogeneous_case(model, kappa, n_steps=steps, dt_over_lambda=dtl)
+    t = steps * dtl * lam
+    A = conformation(oc)
+    assert A[0, 1] == pytest.approx(gd * t, rel=2e-2)
+    assert A[0, 0] - 1.0 == pytest.approx((gd * t) ** 2, rel=5e-2)
+    assert A[1, 1] == pytest.approx(1.0, abs=1e-3)
