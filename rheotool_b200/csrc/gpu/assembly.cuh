@@ -37,6 +37,7 @@ struct FluxArgs {
     const double* U; const double* Ub;
     double* bsrc;         // [6*NP] own part of the source (ddt and model terms are added by k_cell_source)
     double* diag; double* rD; double* Fs;   // Fs = A, tile-major (ell_t)
+    double* FsT;          // A^T in the same layout: A[nb][c] = min(-F, 0) (PBiCG only, pbicg.cuh); null otherwise
     double* corr;         // [nComp][K*NS] face values handed to the downwind cell
     double* ghostCorr;    // send buffer: [(h * ghostStride) + ghostOffset + comp]
     int ghostStride, ghostOffset;
@@ -108,6 +109,9 @@ __global__ void __launch_bounds__(TILE * 9, 4) k_flux_assemble(MeshView m, FluxA
             if (a.writeMatrix)   // row coefficients A[c][nb] = min(F,0), slot-major for the Krylov kernels
                 for (int s = grp; s < K; s += nGrp)
                     a.Fs[ell_t(m.K, s, c)] = ((pMeta[s * TILE] & SLOT_CELL) && !a.noConv) ? fmin(pF[s * TILE], 0.0) : 0.0;
+            if (a.writeMatrix && a.FsT)
+                for (int s = grp; s < K; s += nGrp)
+                    a.FsT[ell_t(m.K, s, c)] = ((pMeta[s * TILE] & SLOT_CELL) && !a.noConv) ? fmin(-pF[s * TILE], 0.0) : 0.0;
             if (grp >= a.cl.n) {   // ---------------- velocity warp: grad(U_u)
                 const int u = grp - a.cl.n;
                 const double* fk = a.U + (size_t)u * m.NP;

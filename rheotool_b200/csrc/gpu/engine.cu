@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "krylov.cuh"
+#include "pbicg.cuh"
 #include "assembly.cuh"
 #include "peer.cuh"
 #include "rheo_gpu.h"
@@ -124,7 +125,7 @@ struct RheoGpu {
     int nTiles = 0;
     MeshView mv;
     // fields
-    DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_stage, d_tmpB;
+    DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_FsT, d_stage, d_tmpB;   // d_FsT: A^T coefficients, allocated when fvSolution selects PBiCG
     DevBuf d_Fell, d_gradU, d_sumPsi;   // d_sumPsi: sum of theta per (mode, solved component), written by k_cell_source2
     std::vector<ModeDev> modes;
     // Krylov
@@ -765,7 +766,15 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         c0 = coefft + c00;
         ddtDiag = coefft * (1.0 / dt);
     }
-    if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB) return fail("rheo_gpu_step: only PBiCGStab is implemented on the device (fvSolution solver PBiCGStab)");
+    if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB && h->ctl.solver != RHEO_SOLVER_PBICG) return fail("rheo_gpu_step: unknown solver (fvSolution solver PBiCGStab or PBiCG)");
+    const bool pbicg = h->ctl.solver == RHEO_SOLVER_PBICG;
+    if (pbicg) {
+        if (h->nRanks > 1) return fail("rheo_gpu_step: PBiCG on the device runs on one rank (pbicg.cuh); decomposed cases use PBiCGStab");
+        if (!h->d_FsT.p) {
+            if (h->d_FsT.alloc((size_t)h->K * h->NS * sizeof(double))) return 1;
+            if (zero(h, h->d_FsT)) return 1;
+        }
+    }
     const int N = h->N, NP = h->NP, grid = cdiv(N, BLOCK);
     const int nModes = (int)h->modes.size();
     const double rDeltaT = 1.0 / dt;
@@ -809,7 +818,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 fa.writeMatrix = mi == 0 ? 1 : 0;
                 fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
                 fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
-                fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>();
+                fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>(); fa.FsT = pbicg ? h->d_FsT.as<double>() : nullptr;
                 fa.corr = md.corr.as<double>(); fa.ghostCorr = h->d_send.as<double>(); fa.ghostStride = stride; fa.ghostOffset = (mi - g0) * h->nComp;
                 fa.gradU = h->d_gradU.as<double>();
                 const int threads = TILE * (cl.n + fa.nU);
@@ -869,7 +878,10 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             }
         int iters = 0;
         int rc;
-        if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m0, m1 - m0, &iters) : solve_batch<6, 0>(h, rp, m0, m1 - m0, &iters);
+        if (pbicg) {
+            if (h->nComp == 6) rc = (h->K == 6) ? solve_batch_pbicg<6, 6>(h, rp, m0, m1 - m0, &iters) : solve_batch_pbicg<6, 0>(h, rp, m0, m1 - m0, &iters);
+            else rc = (h->K == 4) ? solve_batch_pbicg<4, 4>(h, rp, m0, m1 - m0, &iters) : solve_batch_pbicg<4, 0>(h, rp, m0, m1 - m0, &iters);
+        } else if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m0, m1 - m0, &iters) : solve_batch<6, 0>(h, rp, m0, m1 - m0, &iters);
         else rc = (h->K == 4) ? solve_batch<4, 4>(h, rp, m0, m1 - m0, &iters) : solve_batch<4, 0>(h, rp, m0, m1 - m0, &iters);
         if (rc) return rc;
         h->specIters = std::max(1, iters);
@@ -1020,7 +1032,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
     for (DevBuf* b : {&h->d_perm, &h->d_faceOld, &h->d_nbr, &h->d_nbrA, &h->d_fidx, &h->d_Sf, &h->d_w, &h->d_C, &h->d_V, &h->d_rV, &h->d_bcell,
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
-                      &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
+                      &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_FsT, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
     for (ModeDev& md : h->modes)

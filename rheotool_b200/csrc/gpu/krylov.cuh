@@ -168,7 +168,26 @@ __device__ __forceinline__ void ctl_end_one(KrylovCtl& k, double sumR, double r0
         else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);
     }
 }
-enum { CTL_NONE = 0, CTL_INIT = 1, CTL_ALPHA = 2, CTL_HALF = 3, CTL_OMEGA = 4, CTL_END = 5, CTL_HALF_OMEGA = 6 };
+// ---- PBiCG (pbicg.cuh; EXT-OF9 PBiCG.C): rho holds wArT
+__device__ __forceinline__ void ctl_pb_beta_one(KrylovCtl& k, double wArT) {
+    if (k.state != 0) return;
+    k.rhoOld = k.rho;
+    k.rho = wArT;
+    k.beta = k.iters == 0 ? 0.0 : k.rho / k.rhoOld;
+}
+__device__ __forceinline__ void ctl_pb_alpha_one(KrylovCtl& k, double wApT) {
+    if (k.state != 0) return;
+    if (!(fabs(wApT) / k.normFactor > 1e-300)) { k.state = 2; k.singular = 1; return; }   // solverPerf.checkSingularity: break
+    k.alpha = k.rho / wApT;
+}
+__device__ __forceinline__ void ctl_pb_end_one(KrylovCtl& k, double sumR, const SolveCtl& sc) {
+    if (k.state != 0) return;
+    k.finRes = sumR / k.normFactor;
+    const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
+    if (!cont) k.state = 2;
+}
+enum { CTL_NONE = 0, CTL_INIT = 1, CTL_ALPHA = 2, CTL_HALF = 3, CTL_OMEGA = 4, CTL_END = 5, CTL_HALF_OMEGA = 6,
+       CTL_PB_BETA = 7, CTL_PB_ALPHA = 8, CTL_PB_END = 9 };
 // CTL_HALF_OMEGA: red = [t.t, t.s per RHS (2 nrhs) | sum|s| per RHS (nrhs)] — the half-step check deferred to the end of the
 // second preconditioned product (peer-memory path)
 __device__ __noinline__ void ctl_dispatch(int what, KrylovShared* ks, int nrhs, const double* red, const SolveCtl& sc) {
@@ -183,13 +202,16 @@ __device__ __noinline__ void ctl_dispatch(int what, KrylovShared* ks, int nrhs, 
             case CTL_OMEGA: ctl_omega_one(k, red[2 * q], red[2 * q + 1]); break;
             case CTL_HALF_OMEGA: ctl_half_one(k, red[2 * nrhs + q], sc); ctl_omega_one(k, red[2 * q], red[2 * q + 1]); break;
             case CTL_END: ctl_end_one(k, red[2 * q], red[2 * q + 1], sc); break;
+            case CTL_PB_BETA: ctl_pb_beta_one(k, red[q]); break;
+            case CTL_PB_ALPHA: ctl_pb_alpha_one(k, red[q]); break;
+            case CTL_PB_END: ctl_pb_end_one(k, red[q], sc); break;
             default: break;
         }
         ks->ctl[q] = k;
         active = k.state == 0;
     }
     const unsigned m = __ballot_sync(0xffffffffu, active);
-    if (q == 0 && (what == CTL_INIT || what == CTL_END)) ks->nActive = __popc(m);
+    if (q == 0 && (what == CTL_INIT || what == CTL_END || what == CTL_PB_ALPHA || what == CTL_PB_END)) ks->nActive = __popc(m);
 }
 __global__ void k_ctl(int what, KrylovShared* ks, int nrhs, const double* red, SolveCtl sc) {
     pdl_sync();

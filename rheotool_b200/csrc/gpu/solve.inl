@@ -1,4 +1,4 @@
-// solve.inl — host orchestration of the batched PBiCGStab/DILU solve (included by engine.cu).
+// solve.inl — host orchestration of the batched PBiCGStab/DILU solve, and of PBiCG/DILU (included by engine.cu).
 //
 // One call solves the NR valid components of `nModes` modes on the shared LDU matrix.  Iterations are
 // launched in speculative batches (as many as the previous step needed) with no host synchronisation
@@ -169,6 +169,60 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* i
         CK(cudaMemcpyAsync(h->h_ks, ks, sizeof(KrylovShared), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         if (h->h_ks->pad[0]) return fail("peer-memory wait expired: a neighbour rank did not reach the halo swap / reduction (peer.cuh)");
+        if (h->h_ks->nActive == 0 || launched > h->ctl.max_iter + 2) break;
+        spec = 1;
+    }
+    int iters = 0;
+    for (int q = 0; q < nrhs; ++q) iters = std::max(iters, h->h_ks->ctl[q].iters);
+    *itersOut = iters;
+    return 0;
+}
+
+// PBiCG + DILU (pbicg.cuh): correctness-first, one rank.  Vectors: rA = r, rT = r0, pA = p, pT = y, wA = v, wT = t.
+template <int NR, int KT>
+int solve_batch_pbicg(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* itersOut) {
+    const int nrhs = nModes * NR, N = h->N, NP = h->NP;
+    KrylovShared* ks = h->d_ks.as<KrylovShared>();
+    double* part = h->d_partials.as<double>();
+    double* red = h->d_red.as<double>();
+    double* redB = red + MAX_RED;
+    unsigned* counter = h->d_counter.as<unsigned>();
+    double *rA = h->d_r.as<double>(), *rT = h->d_r0.as<double>(), *pA = h->d_p.as<double>(), *pT = h->d_y.as<double>(),
+           *wA = h->d_v.as<double>(), *wT = h->d_t.as<double>();
+    const SolveCtl sc{h->ctl.tolerance, h->ctl.rel_tol, h->ctl.min_iter, h->ctl.max_iter};
+    const double* diag = h->d_diag.as<double>();
+    const double* rD = h->d_rD.as<double>();
+    const double* A = h->d_Fs.as<double>();
+    const double* AT = h->d_FsT.as<double>();
+    const int nc = h->nColours;
+
+    // gAverage(psi), rA = b - A psi, rT = rA, normFactor, initial residual: the same kernel as PBiCGStab (r0 = r)
+    double* sumPsi = h->d_sumPsi.as<double>() + (size_t)firstMode * NR;
+    if (all_reduce(h, sumPsi, nrhs)) return 1;
+    LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, rA, rT, part, redB, counter,
+           CTL_INIT, ks, sc);
+    int launched = 0;
+    int spec = std::max(1, h->specIters);
+    for (;;) {
+        for (int it = 0; it < spec; ++it) {
+            // wA = M^-1 rA, wT = M^-T rT: forward substitution colour by colour, backward in reverse (the last colour has no
+            // higher-numbered neighbour)
+            for (int k = 0; k < nc; ++k) {
+                const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
+                if (c1 > c0) LAUNCH(h, (k_pb_sweep<NR, 1>), GRID(h, (k_pb_sweep<NR, 1>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, AT, rA, rT, wA, wT);
+            }
+            for (int k = nc - 2; k >= 0; --k) {
+                const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
+                if (c1 > c0) LAUNCH(h, (k_pb_sweep<NR, 0>), GRID(h, (k_pb_sweep<NR, 0>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, AT, rA, rT, wA, wT);
+            }
+            LAUNCH(h, (k_pb_dot<NR>), GRID(h, (k_pb_dot<NR>), N), BLOCK, N, NP, nModes, ks, wA, rT, part, red, counter, sc);
+            LAUNCH(h, (k_pb_update_p<NR>), GRID(h, (k_pb_update_p<NR>), N), BLOCK, N, NP, nModes, ks, wA, wT, pA, pT);
+            LAUNCH(h, (k_pb_spmv<NR>), GRID(h, (k_pb_spmv<NR>), N), BLOCK, h->mv, nModes, ks, diag, A, AT, pA, pT, wA, wT, part, red, counter, sc);
+            LAUNCH(h, (k_pb_update_x_r<NR>), GRID(h, (k_pb_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, pA, wA, wT, rA, rT, part, red, counter, sc);
+            ++launched;
+        }
+        CK(cudaMemcpyAsync(h->h_ks, ks, sizeof(KrylovShared), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
         if (h->h_ks->nActive == 0 || launched > h->ctl.max_iter + 2) break;
         spec = 1;
     }
