@@ -68,6 +68,8 @@ extern "C" {
 #define RHEO_DDT_EULER    0
 #define RHEO_DDT_BACKWARD 1   /* EXT-OF9 backwardDdtScheme: Euler until the field has two old times, variable-step coefficients after */
 
+#define RHEO_DDT_CRANK_NICOLSON 2   /* EXT-OF9 CrankNicolsonDdtScheme `CrankNicolson <psi>` (tutorial Cavity/Oldroyd-BLog/system/fvSchemes:
+                                      `CrankNicolson 1`): ddt0-field formulation on a fresh start (first step Euler), cn_psi = off-centring */
 #define RHEO_SOLVER_PBICGSTAB 0
 #define RHEO_SOLVER_PBICG     1
 
@@ -99,6 +101,7 @@ typedef struct RheoSchemeCtl {
     int32_t min_iter;
     int32_t max_iter;
     double  relax;          /* relaxationFactors.equations.theta; <= 0 : relax() is a no-op */
+    double  cn_psi;         /* CrankNicolson off-centring coefficient psi in [0,1] (1 = Crank-Nicolson, 0 = Euler); other ddt: unused */
 } RheoSchemeCtl;
 
 /* mirrors OpenFOAM SolverPerformance<symmTensor> per mode */

@@ -104,6 +104,8 @@ struct Model {
 struct Mode {
     Model model;
     dvec theta, thetaOld, thetaOldOld, tau, eigVals, eigVecs, thetaB, tauB;
+    dvec ddt0;                // CrankNicolson: the scheme's ddt0 field (EXT-OF9 CrankNicolsonDdtScheme::ddt0_)
+    int ddt0TimeIndex = 0;    //                 time step at which ddt0 was last evaluated
 };
 
 struct Rank {
@@ -718,7 +720,7 @@ Perf pbicg(Ldu& A, DVec& psi, const DVec& source, const RheoSchemeCtl& ctl) {
 int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
     const int R = (int)cs.ranks.size();
     const RheoSchemeCtl& ctl = cs.ctl;
-    if (ctl.ddt != RHEO_DDT_EULER && ctl.ddt != RHEO_DDT_BACKWARD) { g_err = "oracle: only the Euler and backward ddt schemes are restated"; return 3; }
+    if (ctl.ddt != RHEO_DDT_EULER && ctl.ddt != RHEO_DDT_BACKWARD && ctl.ddt != RHEO_DDT_CRANK_NICOLSON) { g_err = "oracle: only the Euler, backward and CrankNicolson ddt schemes are restated"; return 3; }
     double aL[3] = {1, 1, 1}, bL[3] = {0, 0, 0}, bnd[2] = {1, 1};
     const bool hrs = limiter_table(ctl.limiter, aL, bL, bnd);
     const bool noConv = (ctl.limiter == RHEO_LIMITER_NONE);
@@ -778,6 +780,30 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
                 rk.diag[c] = (coefft * rDeltaT) * m.V[c];
                 for (int q = 0; q < 6; ++q)
                     rk.source[(size_t)6 * c + q] = rDeltaT * m.V[c] * (coefft0 * mo.thetaOld[(size_t)6 * c + q] - coefft00 * oo[(size_t)6 * c + q]);
+            }
+        } else if (ctl.ddt == RHEO_DDT_CRANK_NICOLSON) {
+            // EXT-OF9 CrankNicolsonDdtScheme<Type>::fvmDdt (static mesh), fresh start (the ddt0 field is created by the first
+            // call, so its startTimeIndex is the first step's time index): k = time steps since the state was set,
+            //   coef_  = (k > 1) ? 1 + psi : 1        rDtCoef  = coef_/deltaT          (first step: Euler)
+            //   coef0_ = (k > 2) ? 1 + psi : 1        rDtCoef0 = coef0_/deltaT0
+            //   once per time index:  ddt0 = rDtCoef0 (theta_old - theta_oldold) - offCentre(ddt0)
+            //   diag = rDtCoef V;   source = (rDtCoef theta_old + offCentre(ddt0)) V;   offCentre(x) = psi < 1 ? psi x : x
+            const double psi = ctl.cn_psi;
+            const int k = std::max(1, cs.nOldTimes);
+            const double off = psi < 1 ? psi : 1.0;
+            if (mo.ddt0.size() != (size_t)6 * n) { mo.ddt0.assign((size_t)6 * n, 0.0); mo.ddt0TimeIndex = 0; }
+            if (k > mo.ddt0TimeIndex) {
+                if (k > 1) {
+                    const double rDtCoef0 = (k > 2 ? 1 + psi : 1.0) / cs.dt0;
+                    for (size_t i = 0; i < mo.ddt0.size(); ++i) mo.ddt0[i] = rDtCoef0 * (mo.thetaOld[i] - mo.thetaOldOld[i]) - off * mo.ddt0[i];
+                }
+                mo.ddt0TimeIndex = k;
+            }
+            const double rDtCoef = (k > 1 ? 1 + psi : 1.0) / dt;
+            for (int c = 0; c < n; ++c) {
+                rk.diag[c] = rDtCoef * m.V[c];
+                for (int q = 0; q < 6; ++q)
+                    rk.source[(size_t)6 * c + q] = (rDtCoef * mo.thetaOld[(size_t)6 * c + q] + off * mo.ddt0[(size_t)6 * c + q]) * m.V[c];
             }
         } else
         for (int c = 0; c < n; ++c) {
@@ -1095,7 +1121,7 @@ int orc_set_state(void* h, int rank, int mode, const double* theta, const double
     Rank& rk = cs.ranks[rank];
     Mode& mo = rk.modes[mode];
     const size_t n = rk.mesh.nCells, nb = rk.mesh.nB();
-    if (theta) { mo.theta.assign(theta, theta + 6 * n); mo.thetaOld = mo.theta; mo.thetaOldOld = mo.theta; cs.nOldTimes = 0; }
+    if (theta) { mo.theta.assign(theta, theta + 6 * n); mo.thetaOld = mo.theta; mo.thetaOldOld = mo.theta; cs.nOldTimes = 0; mo.ddt0.clear(); mo.ddt0TimeIndex = 0; }
     if (tau) mo.tau.assign(tau, tau + 6 * n);
     if (eigvals) mo.eigVals.assign(eigvals, eigvals + 9 * n);
     if (eigvecs) mo.eigVecs.assign(eigvecs, eigvecs + 9 * n);

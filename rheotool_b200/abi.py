@@ -16,7 +16,7 @@ BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSO
 MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG, MODEL_SARAMITO_LOG = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
 LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}
-DDT_EULER, DDT_BACKWARD = 0, 1
+DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON = 0, 1, 2
 SOLVER = {"PBiCGStab": 0, "PBiCG": 1}
 FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD = range(8)
 FLOW_CONTRACTION_2D, FLOW_VORTEX, FLOW_CONTRACTION_3D = 0, 1, 2
@@ -74,7 +74,8 @@ class RheoModelDesc(C.Structure):
 
 class RheoSchemeCtl(C.Structure):
     _fields_ = [("limiter", C.c_int32), ("ddt", C.c_int32), ("solver", C.c_int32), ("tolerance", C.c_double),
-                ("rel_tol", C.c_double), ("min_iter", C.c_int32), ("max_iter", C.c_int32), ("relax", C.c_double)]
+                ("rel_tol", C.c_double), ("min_iter", C.c_int32), ("max_iter", C.c_int32), ("relax", C.c_double),
+                ("cn_psi", C.c_double)]
 
 
 class RheoStepStats(C.Structure):

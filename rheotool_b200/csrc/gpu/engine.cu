@@ -89,7 +89,9 @@ struct DevBuf {
 struct ModeDev {
     RheoModelDesc desc;
     ModelParams mp;
-    DevBuf theta, thetaOld, thetaOldOld, tau, lam, R, fFene, bsrc, thetaB, tauB, gammaVals;   // thetaOldOld: backward ddt only
+    DevBuf theta, thetaOld, thetaOldOld, tau, lam, R, fFene, bsrc, thetaB, tauB, gammaVals;   // thetaOldOld: backward and CrankNicolson ddt only
+    DevBuf ddt0;              // CrankNicolson: the scheme's ddt0 field (6 planes)
+    int ddt0TimeIndex = 0;    //                 time step at which ddt0 was last evaluated
     DevBuf corr;   // [nComp][K*NS] deferred face values received from the upwind neighbours (assembly.cuh)
 };
 
@@ -524,9 +526,10 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         }
         if (md.theta.alloc(6 * NP * d8) || md.thetaOld.alloc(6 * NP * d8) || md.tau.alloc(6 * NP * d8) || md.lam.alloc(3 * NP * d8) ||
             md.R.alloc(9 * NP * d8) || md.fFene.alloc(NP * d8) || md.bsrc.alloc(6 * NP * d8) || md.thetaB.alloc(6 * nB * d8) || md.tauB.alloc(6 * nB * d8) ||
-            md.corr.alloc((size_t)h->nComp * h->K * h->NS * d8) || md.thetaOldOld.alloc(h->ctl.ddt == RHEO_DDT_BACKWARD ? 6 * NP * d8 : 0))
+            md.corr.alloc((size_t)h->nComp * h->K * h->NS * d8) || md.thetaOldOld.alloc(h->ctl.ddt != RHEO_DDT_EULER ? 6 * NP * d8 : 0) ||
+            md.ddt0.alloc(h->ctl.ddt == RHEO_DDT_CRANK_NICOLSON ? 6 * NP * d8 : 0))
             return 1;
-        zero(h, md.corr); zero(h, md.thetaOldOld);
+        zero(h, md.corr); zero(h, md.thetaOldOld); zero(h, md.ddt0);
         zero(h, md.theta); zero(h, md.thetaOld); zero(h, md.tau); zero(h, md.fFene); zero(h, md.bsrc); zero(h, md.thetaB); zero(h, md.tauB); zero(h, md.R);
         // READ_IF_PRESENT defaults: eigVals = eigVecs = I (Oldroyd_BLog.C:76-113)
         LAUNCH(h, k_fill, cdiv(3 * NP, BLOCK), BLOCK, 3 * NP, md.lam.as<double>(), 1.0);
@@ -754,7 +757,9 @@ template <class Kern> int flux_grid(RheoGpu* h, Kern kern, int threads, size_t s
 
 int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
-    if (h->ctl.ddt != RHEO_DDT_EULER && h->ctl.ddt != RHEO_DDT_BACKWARD) return fail("rheo_gpu_step: only the Euler and backward ddt schemes are implemented");
+    if (h->ctl.ddt != RHEO_DDT_EULER && h->ctl.ddt != RHEO_DDT_BACKWARD && h->ctl.ddt != RHEO_DDT_CRANK_NICOLSON)
+        return fail("rheo_gpu_step: only the Euler, backward and CrankNicolson ddt schemes are implemented");
+    if (h->ctl.ddt == RHEO_DDT_CRANK_NICOLSON && !(h->ctl.cn_psi >= 0 && h->ctl.cn_psi <= 1)) return fail("CrankNicolson coefficient should be >= 0 and <= 1");
     // EXT-OF9 backwardDdtScheme::fvmDdt: deltaT0 = great while the field has < 2 old times (first step = Euler)
     h->dtNow = dt;
     double ddtDiag = 1.0 / dt, c0 = 1.0, c00 = 0.0;
@@ -765,6 +770,28 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         c00 = dt * dt / (deltaT0 * (dt + deltaT0));
         c0 = coefft + c00;
         ddtDiag = coefft * (1.0 / dt);
+    }
+    // EXT-OF9 CrankNicolsonDdtScheme::fvmDdt, fresh start (see oracle.cpp): once per time index
+    //   ddt0 = (coef0/deltaT0)(theta_old - theta_oldold) - offCentre(ddt0);   diag = (coef/dt) V;
+    //   source = ((coef/dt) theta_old + offCentre(ddt0)) V  — the backward slots of the source kernel with c0 = coef,
+    //   c00 = -dt*off and ddt0 in place of theta_oldold:  (1/dt) V (c0 theta_old - c00 ddt0)
+    const bool crankNicolson = h->ctl.ddt == RHEO_DDT_CRANK_NICOLSON;
+    if (crankNicolson) {
+        const double psi = h->ctl.cn_psi, off = psi < 1 ? psi : 1.0;
+        const int k = std::max(1, h->nOldTimes);
+        for (ModeDev& md : h->modes) {
+            if (k > md.ddt0TimeIndex) {
+                if (k > 1) {
+                    const double rDtCoef0 = (k > 2 ? 1 + psi : 1.0) / h->dt0;
+                    const size_t n6 = (size_t)6 * h->NP;
+                    LAUNCH(h, k_cn_ddt0, cdiv((long)n6, BLOCK), BLOCK, n6, rDtCoef0, off, md.thetaOld.as<double>(), md.thetaOldOld.as<double>(), md.ddt0.as<double>());
+                }
+                md.ddt0TimeIndex = k;
+            }
+        }
+        const double coef = k > 1 ? 1 + psi : 1.0;
+        c0 = coef; c00 = -dt * off;
+        ddtDiag = coef / dt;
     }
     if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB && h->ctl.solver != RHEO_SOLVER_PBICG) return fail("rheo_gpu_step: unknown solver (fvSolution solver PBiCGStab or PBiCG)");
     const bool pbicg = h->ctl.solver == RHEO_SOLVER_PBICG;
@@ -829,8 +856,8 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                     default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
                 }
                 SourceArgs sa;
-                sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.backward = backward ? 1 : 0; sa.c0 = c0; sa.c00 = c00;
-                sa.thetaOldOld = backward ? md.thetaOldOld.as<double>() : md.thetaOld.as<double>();
+                sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.backward = (backward || crankNicolson) ? 1 : 0; sa.c0 = c0; sa.c00 = c00;
+                sa.thetaOldOld = backward ? md.thetaOldOld.as<double>() : crankNicolson ? md.ddt0.as<double>() : md.thetaOld.as<double>();
                 for (int q = 0; q < 6; ++q) sa.solvedIdx[q] = -1;
                 for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
                 sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
@@ -1036,7 +1063,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
         b->release();
     for (ModeDev& md : h->modes)
-        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld}) b->release();
+        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0}) b->release();
     if (h->h_ks) cudaFreeHost(h->h_ks);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1081,6 +1108,8 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
         if (put_cells(h, theta, 6, md.theta.as<double>())) return 1;
         CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
         if (md.thetaOldOld.p) CK(cudaMemcpyAsync(md.thetaOldOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+        if (md.ddt0.p) { if (zero(h, md.ddt0)) return 1; }
+        md.ddt0TimeIndex = 0;
         h->nOldTimes = 0;
     }
     if (tau && put_cells(h, tau, 6, md.tau.as<double>())) return 1;

@@ -124,6 +124,12 @@ __global__ void k_phi_in(int nF, const int* __restrict__ faceOld, const double* 
     const int o = faceOld[f];   // old face + 1, negative if flipped
     dst[f] = o > 0 ? src[o - 1] : -src[-o - 1];
 }
+// CrankNicolson ddt0 update (EXT-OF9 CrankNicolsonDdtScheme::fvmDdt): ddt0 = a (theta_old - theta_oldold) - off ddt0
+__global__ void k_cn_ddt0(size_t n, double a, double off, const double* __restrict__ thOld, const double* __restrict__ thOldOld, double* __restrict__ ddt0) {
+    pdl_sync();
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ddt0[i] = a * (thOld[i] - thOldOld[i]) - off * ddt0[i];
+}
 __global__ void k_fill(size_t n, double* p, double v) {
     pdl_sync();
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -183,7 +183,16 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     const word ddtName(mesh.ddtScheme("ddt(" + thetaName + ")"));
     if (ddtName == "Euler") ctl_.ddt = RHEO_DDT_EULER;
     else if (ddtName == "backward") ctl_.ddt = RHEO_DDT_BACKWARD;
-    else FatalErrorInFunction << "ddtSchemes Euler and backward are available on the GPU path, not " << ddtName << exit(FatalError);
+    else if (ddtName == "CrankNicolson")
+    {
+        // `CrankNicolson <psi>`: the stream returned by ddtScheme() still holds the off-centring coefficient
+        ITstream& is = mesh.ddtScheme("ddt(" + thetaName + ")");
+        const word again(is);
+        ctl_.ddt = RHEO_DDT_CRANK_NICOLSON;
+        ctl_.cn_psi = is.eof() ? 1 : readScalar(is);
+        if (ctl_.cn_psi < 0 || ctl_.cn_psi > 1) FatalErrorInFunction << "CrankNicolson coefficient = " << ctl_.cn_psi << " should be >= 0 and <= 1" << exit(FatalError);
+    }
+    else FatalErrorInFunction << "ddtSchemes Euler, backward and CrankNicolson are available on the GPU path, not " << ddtName << exit(FatalError);
     const dictionary& sol = mesh.solverDict(thetaName);
     const word solver(sol.lookup("solver"));
     // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs PBiCGStab

@@ -396,13 +396,20 @@ def read_schemes(case_dir, theta_name: str = "theta"):
     if len(tok) != 2 or tok[0] != "GaussDefCmpw" or tok[1] not in abi.LIMITER:
         raise FoamError(f"{fs.path}: div(phi,{theta_name}) is `{div}`; the stress step needs `GaussDefCmpw <limiter>` with one of {sorted(abi.LIMITER)}")
     ddt = fs.get(f"ddtSchemes/ddt({theta_name})") or fs.get("ddtSchemes/default")
-    if ddt not in ("Euler", "backward"):
-        raise FoamError(f"{fs.path}: ddtSchemes Euler and backward are available, not {ddt}")
+    cn_psi = 1.0
+    if ddt is not None and ddt.split()[0] == "CrankNicolson":      # `CrankNicolson <psi>` (Cavity/Oldroyd-BLog/system/fvSchemes)
+        tokd = ddt.split()
+        cn_psi = float(tokd[1]) if len(tokd) > 1 else 1.0
+        if not 0.0 <= cn_psi <= 1.0:
+            raise FoamError(f"{fs.path}: CrankNicolson off-centring coefficient {cn_psi} is outside [0, 1]")
+        ddt = "CrankNicolson"
+    if ddt not in ("Euler", "backward", "CrankNicolson"):
+        raise FoamError(f"{fs.path}: ddtSchemes Euler, backward and CrankNicolson are available, not {ddt}")
     at = f"solvers/{theta_name}"
     solver = sol.get(f"{at}/solver")
     if solver is None:
         raise FoamError(f"{sol.path}: no solver entry for {theta_name}")
     relax = sol.scalar(f"relaxationFactors/equations/{theta_name}", 0.0)
     ctl = cases.scheme_ctl(tok[1], "PBiCGStab", sol.scalar(f"{at}/tolerance", 1e-6), sol.scalar(f"{at}/relTol", 0.0), int(sol.scalar(f"{at}/minIter", 0)),
-                           int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt)
+                           int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt, cn_psi=cn_psi)
     return ctl, solver

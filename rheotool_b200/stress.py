@@ -225,10 +225,12 @@ def constitutive_model(mesh: HostMesh, constitutive_properties: dict, fv_schemes
         raise RheoError("bounded GaussDefCmpw is not implemented on the GPU path")
     if div[0] != "GaussDefCmpw":
         raise RheoError(f"div(phi,theta) must use GaussDefCmpw, got {div[0]}")
-    if fv_schemes.get("ddt", "Euler") != "Euler":
-        raise RheoError("only ddtSchemes Euler is implemented on the GPU path")
+    ddt_tok = str(fv_schemes.get("ddt", "Euler")).split()
+    if ddt_tok[0] not in ("Euler", "backward", "CrankNicolson"):
+        raise RheoError(f"ddtSchemes Euler, backward and CrankNicolson are implemented on the GPU path, not {ddt_tok[0]}")
+    cn_psi = float(ddt_tok[1]) if (ddt_tok[0] == "CrankNicolson" and len(ddt_tok) > 1) else 1.0
     sol = fv_solution.get("theta", {})
     ctl = scheme_ctl(limiter=div[1], solver=sol.get("solver", "PBiCGStab"), tolerance=float(sol.get("tolerance", 1e-10)),
                      rel_tol=float(sol.get("relTol", 0.0)), min_iter=int(sol.get("minIter", 0)), max_iter=int(sol.get("maxIter", 1000)),
-                     relax=float(fv_solution.get("relaxationFactors", {}).get("theta", 0.0)))
+                     relax=float(fv_solution.get("relaxationFactors", {}).get("theta", 0.0)), ddt=ddt_tok[0], cn_psi=cn_psi)
     return GpuStressModel(mesh, models, ctl, device)

@@ -288,7 +288,7 @@ def test_case_dictionaries_of_the_reference_tutorials_give_models_and_schemes():
     """constant/constitutiveProperties + system/fvSchemes + system/fvSolution of every reference tutorial that selects one of the
     log-conformation models of this library (or a multiMode of them): models and schemes come out as the shim would read them."""
     import re
-    seen, n_multi, n_schemes, n_refused = {}, 0, 0, 0
+    seen, n_multi, n_schemes, n_refused, n_cn = {}, 0, 0, 0, 0
     for cp in sorted(REF.rglob("constitutiveProperties")):
         txt = cp.read_text()
         types = re.findall(r"^\s*type\s+([\w-]+)\s*;", txt, flags=re.M)
@@ -316,14 +316,18 @@ def test_case_dictionaries_of_the_reference_tutorials_give_models_and_schemes():
         if (case / "system" / "fvSchemes").exists() and "theta" in (case / "system" / "fvSchemes").read_text():
             try:
                 ctl, solver = foamio.read_schemes(case, "theta" + foamio.mode_names(cp)[0])
-            except foamio.FoamError as e:   # refused loudly: a time scheme the stress step does not have (CrankNicolson, steadyState)
-                assert "ddtSchemes" in str(e) and re.search(r"CrankNicolson|steadyState", (case / "system" / "fvSchemes").read_text())
+            except foamio.FoamError as e:   # refused loudly: a time scheme the stress step does not have (steadyState)
+                assert "ddtSchemes" in str(e) and re.search(r"steadyState", (case / "system" / "fvSchemes").read_text())
                 n_refused += 1
                 continue
             n_schemes += 1
-            assert solver in ("PBiCG", "PBiCGStab") and ctl.tolerance > 0 and ctl.ddt in (abi.DDT_EULER, abi.DDT_BACKWARD)
+            assert solver in ("PBiCG", "PBiCGStab") and ctl.tolerance > 0 and ctl.ddt in (abi.DDT_EULER, abi.DDT_BACKWARD, abi.DDT_CRANK_NICOLSON)
+            n_cn += ctl.ddt == abi.DDT_CRANK_NICOLSON
     assert seen.get("Oldroyd-BLog", 0) >= 5 and n_multi >= 1 and len(seen) >= 4, seen
-    assert n_schemes >= 10 and n_refused >= 1, (n_schemes, n_refused)
+    assert n_schemes >= 10 and n_cn >= 1, (n_schemes, n_refused, n_cn)
+    # the Cavity tutorial: `CrankNicolson 1`
+    ctl, _ = foamio.read_schemes(REF / "rheoFoam/Cavity/Oldroyd-BLog")
+    assert ctl.ddt == abi.DDT_CRANK_NICOLSON and ctl.cn_psi == 1.0
     # a spot value: the Cylinder tutorial
     (m,) = foamio.read_models(REF / "rheoFoam/Cylinder/Oldroyd-BLog/constant/constitutiveProperties")
     assert (m.model, m.rho, m.etaS, m.etaP, m.lambda_) == (abi.MODEL_OLDROYD_B_LOG, 1.0, 0.59, 0.41, 0.7)
