@@ -125,3 +125,71 @@ def test_partition_invariance_on_the_unstructured_mesh(n):
         for r in range(nr):
             got[addr[r]] = many.get(r, 0, fld)
         assert rel_l2(got, ref) < 1e-11, fld
+
+
+# ---- the reference's own text on the polyhedral mesh (oracle/_ref; see tests/test_reference_pin.py) -------------------------
+REF_GOLD = Path(__file__).parent / "golden" / "reference_unstructured.npz"
+
+
+def reference_on_the_unstructured_mesh(limiter, steps=2):
+    """[state after each correct()] of rheoTool's text (oracle/_ref) on the fixture; used by tools/make_golden_reference.py."""
+    from oracle import ref
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
+    sc = tight(cases.scheme_ctl(limiter, "PBiCGStab", 1e-10))
+    oc, vals, vecs = _oracle(m, models, sc, U, Ub, phi, theta0, thetaB)
+    st = {"theta": theta0, "theta_b": oc.get(0, 0, abi.FIELD_THETA_B), "tau": np.zeros_like(theta0), "tau_b": oc.get(0, 0, abi.FIELD_TAU_B),
+          "eigvals": vals, "eigvecs": vecs}
+    out = []
+    for _ in range(steps):
+        st = ref.correct(m.desc, models[0], abi.LIMITER[limiter], dt, U, Ub, phi, st["theta"], st["theta_b"], st["tau"], st["tau_b"],
+                         st["eigvals"], st["eigvecs"])
+        out.append(st)
+    return out
+
+
+@pytest.mark.parametrize("limiter", ["cubista", "upwind"])
+def test_oracle_matches_the_reference_text_on_the_unstructured_mesh(limiter):
+    """Non-orthogonal polyhedra (face area vectors not aligned with the centre-to-centre vectors, 4 to 21 faces per cell):
+    Gauss gradients, the limiter's d = C_N - C_P geometry and linearExtrapolation with C_f - C_P are exercised where a tensor
+    grid cannot.  Oracle against the committed outputs of the reference's text (tolerance 1e-12; measured 1e-15)."""
+    gold = np.load(REF_GOLD)
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
+    sc = tight(cases.scheme_ctl(limiter, "PBiCGStab", 1e-10))
+    oc, _, _ = _oracle(m, models, sc, U, Ub, phi, theta0, thetaB)
+    for k in range(2):
+        oc.store_old_time(); oc.step(dt)
+        for fld, key in ((abi.FIELD_THETA, "theta"), (abi.FIELD_TAU, "tau"), (abi.FIELD_TAU_B, "tau_b")):
+            if key == "tau_b" and k > 0:
+                continue   # see below
+            assert rel_l2(oc.get(0, 0, fld), gold[f"{limiter}/step{k + 1}/{key}"]) <= 1e-12, (limiter, k, key)
+    # KNOWN DIFFERENCE (DESIGN.md §6): this mesh lists `walls` (tau linearExtrapolation) BEFORE `cut` (tau zeroGradient).  While
+    # `walls` evaluates its Gauss gradient, the reference harness has `cut` holding the boundary value of the expression just
+    # assigned to tau_ (GeometricField::operator= assigns non-fixed patches; with eigVals_/eigVecs_ boundary values never
+    # updated after construction that value is 0), the oracle and the device have it holding the previously evaluated
+    # zeroGradient value.  Only wall faces whose cell also touches `cut` see it, from the second call on, and only in tau_b:
+    tb_o, tb_r = oc.get(0, 0, abi.FIELD_TAU_B), gold[f"{limiter}/step2/tau_b"]
+    walls = m.desc.patches[0]
+    sl = slice(walls.start - m.n_internal, walls.start - m.n_internal + walls.size)
+    rest = np.ones(len(tb_o), bool); rest[sl] = False
+    assert rel_l2(tb_o[rest], tb_r[rest]) <= 1e-12                       # every other patch agrees
+    touching = set(m.owner[m.desc.patches[4].start: m.desc.patches[4].start + m.desc.patches[4].size].tolist())
+    wall_cells = m.owner[walls.start: walls.start + walls.size]
+    differs = np.abs(tb_o[sl] - tb_r[sl]).max(axis=1) > 1e-9 * np.abs(tb_r).max()
+    assert all(int(c) in touching for c in wall_cells[differs])          # ... and so does every wall face away from `cut`
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("limiter", ["cubista", "upwind"])
+def test_gpu_matches_the_reference_text_on_the_unstructured_mesh(limiter):
+    from rheotool_b200.stress import GpuStressModel
+    gold = np.load(REF_GOLD)
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
+    sc = tight(cases.scheme_ctl(limiter, "PBiCGStab", 1e-10))
+    vals, vecs = orc.calc_eig(theta0)
+    g = GpuStressModel(m, models, sc)
+    g.upload_state(0, theta0, np.zeros_like(theta0), vals, vecs, theta_b=thetaB)
+    g.upload_velocity(U, Ub, phi)
+    g.store_old_time(); g.correct(dt)
+    assert rel_l2(g.theta(), gold[f"{limiter}/step1/theta"]) <= 1e-10
+    assert rel_l2(g.tau(0), gold[f"{limiter}/step1/tau"]) <= 1e-10
+    assert rel_l2(g.download(abi.FIELD_TAU_B, 0), gold[f"{limiter}/step1/tau_b"]) <= 1e-10

@@ -1,4 +1,4 @@
-"""Writes tests/golden/reference_correct.npz and tests/golden/reference_cell.npz: outputs of rheoTool's OWN text
+"""Writes tests/golden/reference_correct.npz, reference_unstructured.npz and reference_cell.npz: outputs of rheoTool's OWN text
 for the stress step (oracle/_ref/libref_stress.so, compiled from /root/reference by `make -C oracle ref`).
 Run in the container that has /root/reference:  python tools/make_golden_reference.py
 The GPU box has no /root/reference; tests there (and the -m gpu parity tests) read these fixtures."""
@@ -47,6 +47,14 @@ def main():
                 out[f"{name}/step{k + 1}/{f}"] = st[f]
         print(name, s.mesh.n_cells, "cells")
     np.savez_compressed(ROOT / "tests" / "golden" / "reference_correct.npz", **out)
+
+    import test_unstructured
+    un = {}
+    for limiter in ("cubista", "upwind"):
+        for k, st in enumerate(test_unstructured.reference_on_the_unstructured_mesh(limiter)):
+            for f in ("theta", "tau", "tau_b"):
+                un[f"{limiter}/step{k + 1}/{f}"] = st[f]
+    np.savez_compressed(ROOT / "tests" / "golden" / "reference_unstructured.npz", **un)
 
     th = cell_vectors()
     D, V, nrot = ref.jacobi(th)
