@@ -410,7 +410,7 @@ def main():
                 "config": {"workload": label, "cells_total": ncell, "dt": dt},
                 "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "Mcell-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "note": "restated CPU baseline (rheoTool algorithm, not the rheoTool binary: OpenFOAM-9/Eigen/MPI are not installable here)"}
+                "note": "restated CPU baseline (rheoTool algorithm, not the rheoTool binary: OpenFOAM-9/Eigen/MPI are not installable here); the restatement is pinned on rheoTool's own text compiled into oracle/_ref (tests/test_reference_pin.py), whose stand-in linear solver is not rheoTool's and is therefore not what is timed"}
         print(json.dumps(line))
         return
 
