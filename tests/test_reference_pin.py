@@ -185,18 +185,15 @@ def test_live_every_limiter_larger_mesh(limiter):
 
 
 # ---- the CUDA path against the reference's numbers ----------------------------------------------------------------
-# device code written after this round's GPU budget was spent: compiled for sm_100a, not yet run on hardware
-NOT_YET_RUN_ON_GPU = {n for n in REFERENCE_CASES if n.startswith("SaramitoLog")}
-
-
-def _gpu_cases():
-    for n in sorted(REFERENCE_CASES):
-        marks = [pytest.mark.xfail(strict=False, reason="SaramitoLog device functor has not run on a GPU yet (written without GPU access)")] if n in NOT_YET_RUN_ON_GPU else []
-        yield pytest.param(n, marks=marks)
+# These GPU tests were written after this round's GPU budget was spent and have not run on hardware yet (the device paths of
+# the eight models they cover have: tests/test_gpu_parity.py; the SaramitoLog functor has not).  Until their first run they
+# are xfail(strict=False): a pass is reported as XPASS, a failure cannot hide the rest of the suite behind `-x`.
+not_yet_run = pytest.mark.xfail(strict=False, reason="written without GPU access: not yet run on hardware")
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(_gpu_cases()))
+@not_yet_run
+@pytest.mark.parametrize("name", sorted(REFERENCE_CASES))
 def test_gpu_correct_golden(gold, name):
     spec, s = make_setup(name)
     g = s.gpu(spec.schemes)
@@ -211,6 +208,7 @@ def test_gpu_correct_golden(gold, name):
 
 
 @pytest.mark.gpu
+@not_yet_run
 def test_gpu_eig_golden(cell):
     """k_eig_tau against utils/jacobi.H: same eigenvalues (the device sorts ascending like Eigen; jacobi.H does not),
     same conformation tensor R exp(D) R^T."""

@@ -179,6 +179,7 @@ def test_oracle_matches_the_reference_text_on_the_unstructured_mesh(limiter):
 
 
 @pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written without GPU access: not yet run on hardware")
 @pytest.mark.parametrize("limiter", ["cubista", "upwind"])
 def test_gpu_matches_the_reference_text_on_the_unstructured_mesh(limiter):
     from rheotool_b200.stress import GpuStressModel
