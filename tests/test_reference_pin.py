@@ -9,8 +9,8 @@ tests/reference_cases.py are committed as tests/golden/reference_*.npz by tools/
 * `test_oracle_*_golden`: the oracle against the committed fixtures — runs everywhere.
 * `test_live_*`: the oracle against the library itself on more inputs, and the fixtures against a fresh run — only
   where the library is built or /root/reference is present (skipped on the GPU box's CPU run otherwise).
-* `test_gpu_*` (marked gpu): the CUDA path, through the C-ABI, against the same fixtures: the reference's numbers,
-  not the oracle's.
+* the CUDA path, through the C-ABI, against the same fixtures (the reference's numbers, not the oracle's) is in
+  tests/test_zz_gpu_not_yet_run.py.
 Tolerances: 1e-12 relative L2 oracle-vs-reference (measured: <= 4e-15), BASELINE's 1e-10 for the GPU after one step.
 """
 from pathlib import Path
@@ -182,42 +182,3 @@ def test_live_every_limiter_larger_mesh(limiter):
     oc.store_old_time(); oc.step(s.dt)
     for fld, key in ((abi.FIELD_THETA, "theta"), (abi.FIELD_TAU, "tau"), (abi.FIELD_TAU_B, "tau_b"), (abi.FIELD_EIGVALS, "eigvals"), (abi.FIELD_EIGVECS, "eigvecs")):
         assert rel_l2(oc.get(0, 0, fld), st[key]) <= TOL_ORACLE, key
-
-
-# ---- the CUDA path against the reference's numbers ----------------------------------------------------------------
-# These GPU tests were written after this round's GPU budget was spent and have not run on hardware yet (the device paths of
-# the eight models they cover have: tests/test_gpu_parity.py; the SaramitoLog functor has not).  Until their first run they
-# are xfail(strict=False): a pass is reported as XPASS, a failure cannot hide the rest of the suite behind `-x`.
-not_yet_run = pytest.mark.xfail(strict=False, reason="written without GPU access: not yet run on hardware")
-
-
-@pytest.mark.gpu
-@not_yet_run
-@pytest.mark.parametrize("name", sorted(REFERENCE_CASES))
-def test_gpu_correct_golden(gold, name):
-    spec, s = make_setup(name)
-    g = s.gpu(spec.schemes)
-    for k in range(N_STEPS):
-        g.store_old_time(); g.correct(s.dt)
-        if k + 1 not in STORED_STEPS:
-            continue
-        tol = TOL_GPU_1 if k == 0 else TOL_GPU_N
-        for fld, key in ((abi.FIELD_THETA, "theta"), (abi.FIELD_TAU, "tau"), (abi.FIELD_THETA_B, "theta_b"), (abi.FIELD_TAU_B, "tau_b")):
-            err = rel_l2(g.download(fld, 0), gold[f"{name}/step{k + 1}/{key}"])
-            assert err <= tol, f"{name} step {k + 1} {key}: {err:.2e}"
-
-
-@pytest.mark.gpu
-@not_yet_run
-def test_gpu_eig_golden(cell):
-    """k_eig_tau against utils/jacobi.H: same eigenvalues (the device sorts ascending like Eigen; jacobi.H does not),
-    same conformation tensor R exp(D) R^T."""
-    from rheotool_b200.stress import eig_exp
-    gv, gV = eig_exp(cell["theta"])
-    d = np.sort(cell["expD"], axis=1)
-    assert np.abs(np.stack([gv[:, 0], gv[:, 4], gv[:, 8]], 1) - d).max() <= 1e-12 * np.abs(d).max()
-    R = gV.reshape(-1, 3, 3)
-    A = R @ gv.reshape(-1, 3, 3) @ np.transpose(R, (0, 2, 1))
-    Vr = cell["V"]
-    Ar = Vr @ (cell["expD"][:, :, None] * np.transpose(Vr, (0, 2, 1)))
-    assert rel_l2(A, Ar) <= 1e-13

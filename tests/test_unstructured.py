@@ -176,21 +176,3 @@ def test_oracle_matches_the_reference_text_on_the_unstructured_mesh(limiter):
     wall_cells = m.owner[walls.start: walls.start + walls.size]
     differs = np.abs(tb_o[sl] - tb_r[sl]).max(axis=1) > 1e-9 * np.abs(tb_r).max()
     assert all(int(c) in touching for c in wall_cells[differs])          # ... and so does every wall face away from `cut`
-
-
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="written without GPU access: not yet run on hardware")
-@pytest.mark.parametrize("limiter", ["cubista", "upwind"])
-def test_gpu_matches_the_reference_text_on_the_unstructured_mesh(limiter):
-    from rheotool_b200.stress import GpuStressModel
-    gold = np.load(REF_GOLD)
-    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
-    sc = tight(cases.scheme_ctl(limiter, "PBiCGStab", 1e-10))
-    vals, vecs = orc.calc_eig(theta0)
-    g = GpuStressModel(m, models, sc)
-    g.upload_state(0, theta0, np.zeros_like(theta0), vals, vecs, theta_b=thetaB)
-    g.upload_velocity(U, Ub, phi)
-    g.store_old_time(); g.correct(dt)
-    assert rel_l2(g.theta(), gold[f"{limiter}/step1/theta"]) <= 1e-10
-    assert rel_l2(g.tau(0), gold[f"{limiter}/step1/tau"]) <= 1e-10
-    assert rel_l2(g.download(abi.FIELD_TAU_B, 0), gold[f"{limiter}/step1/tau_b"]) <= 1e-10
