@@ -195,13 +195,18 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     else FatalErrorInFunction << "ddtSchemes Euler, backward and CrankNicolson are available on the GPU path, not " << ddtName << exit(FatalError);
     const dictionary& sol = mesh.solverDict(thetaName);
     const word solver(sol.lookup("solver"));
-    // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs PBiCGStab
-    if (solver != "PBiCGStab")
+    // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs its tuned, multi-rank
+    // PBiCGStab path unless the solver dictionary asks for the device PBiCG path by name (`gpuSolver PBiCG;`, serial runs only)
+    ctl_.solver = RHEO_SOLVER_PBICGSTAB;
+    if (solver == "PBiCG" && word(sol.lookupOrDefault<word>("gpuSolver", "PBiCGStab")) == "PBiCG" && !Pstream::parRun())
+    {
+        ctl_.solver = RHEO_SOLVER_PBICG;
+    }
+    else if (solver != "PBiCGStab")
     {
         WarningInFunction << "fvSolution selects " << solver << " for " << thetaName
             << "; the GPU path solves with PBiCGStab + DILU (same tolerance, relTol, minIter, maxIter)" << endl;
     }
-    ctl_.solver    = RHEO_SOLVER_PBICGSTAB;
     ctl_.tolerance = sol.lookupOrDefault<scalar>("tolerance", 1e-6);
     ctl_.rel_tol   = sol.lookupOrDefault<scalar>("relTol", 0);
     ctl_.min_iter  = sol.lookupOrDefault<label>("minIter", 0);
