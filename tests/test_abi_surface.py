@@ -60,6 +60,10 @@ def test_constants_match_the_headers():
     assert defs["RHEO_MODEL_GIESEKUS_LOG"] == abi.MODEL_NAMES["GiesekusLog"]
     assert defs["RHEO_MODEL_PTT_LOG"] == abi.MODEL_NAMES["PTTLog"]
     assert defs["RHEO_MODEL_FENE_P_LOG"] == abi.MODEL_NAMES["FENE-PLog"]
+    for macro, name in (("FENE_CR_LOG", "FENE-CRLog"), ("WM_CY_LOG", "WhiteMetznerCYLog"), ("ROLIE_POLY_LOG", "Rolie-PolyLog"),
+                        ("XPOMPOM_LOG", "XPomPomLog"), ("SARAMITO_LOG", "SaramitoLog")):
+        assert defs["RHEO_MODEL_" + macro] == abi.MODEL_NAMES[name]
+    assert (defs["RHEO_DDT_EULER"], defs["RHEO_DDT_BACKWARD"], defs["RHEO_DDT_CRANK_NICOLSON"]) == (abi.DDT_EULER, abi.DDT_BACKWARD, abi.DDT_CRANK_NICOLSON)
     for name, val in abi.LIMITER.items():
         assert defs["RHEO_LIMITER_" + name.upper()] == val
     assert defs["RHEO_SOLVER_PBICGSTAB"] == abi.SOLVER["PBiCGStab"] and defs["RHEO_SOLVER_PBICG"] == abi.SOLVER["PBiCG"]
