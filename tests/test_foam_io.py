@@ -325,6 +325,9 @@ def test_case_dictionaries_of_the_reference_tutorials_give_models_and_schemes():
             n_cn += ctl.ddt == abi.DDT_CRANK_NICOLSON
     assert seen.get("Oldroyd-BLog", 0) >= 5 and n_multi >= 1 and len(seen) >= 4, seen
     assert n_schemes >= 10 and n_cn >= 1, (n_schemes, n_refused, n_cn)
+    # the SaramitoLog tutorial (SaramitoLog.C:108-165: k is read because n != 1, no PTT function then, dims (1 1 0))
+    (m,) = foamio.read_models(REF / "rheoFoam/OtherTests/Channel2D_VE/otherModels/SaramitoLog/constant/constitutiveProperties")
+    assert (m.model, m.sar_tau0, m.sar_k, m.sar_n, list(m.sar_dims), m.sar_ptt, m.zeta) == (abi.MODEL_SARAMITO_LOG, 2.5, 1.5, 0.75, [1.0, 1.0, 0.0], 0, 0.0)
     # the Cavity tutorial: `CrankNicolson 1`
     ctl, _ = foamio.read_schemes(REF / "rheoFoam/Cavity/Oldroyd-BLog")
     assert ctl.ddt == abi.DDT_CRANK_NICOLSON and ctl.cn_psi == 1.0
