@@ -21,7 +21,8 @@ from reference_cases import N_STEPS, REFERENCE_CASES, STORED_STEPS, make_setup
 from rheotool_b200 import abi, cases
 from test_unstructured import REF_GOLD, _case
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written without GPU access: not yet run on hardware")]
+pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="written without GPU access: not yet run on hardware"),
+              pytest.mark.timeout(900)]   # pytest-timeout: a kernel that never returns must not hold the box
 
 GOLD = Path(__file__).resolve().parent / "golden"
 TOL_GPU_1 = 1e-10
