@@ -182,3 +182,22 @@ def test_live_every_limiter_larger_mesh(limiter):
     oc.store_old_time(); oc.step(s.dt)
     for fld, key in ((abi.FIELD_THETA, "theta"), (abi.FIELD_TAU, "tau"), (abi.FIELD_TAU_B, "tau_b"), (abi.FIELD_EIGVALS, "eigvals"), (abi.FIELD_EIGVECS, "eigvecs")):
         assert rel_l2(oc.get(0, 0, fld), st[key]) <= TOL_ORACLE, key
+
+
+@live
+def test_live_hundred_chained_calls_stay_on_the_reference():
+    """BASELINE's long-run bar (<= 1e-6 after 100 steps) for the oracle against the reference's text itself: 100 chained
+    correct() calls with the tutorial Krylov tolerance scaled down to 1e-13 on the oracle side."""
+    name = "PTTLog-linear-zeta-2D-minmod"
+    spec, s = make_setup(name)
+    from rheotool_b200 import cases
+    oc = s.oracle(cases.scheme_ctl("minmod", "PBiCG", 1e-13), sort_eig=False)     # the tutorials' solver
+    st = {"theta": s.theta0, "theta_b": oc.get(0, 0, abi.FIELD_THETA_B), "tau": s.tau0, "tau_b": oc.get(0, 0, abi.FIELD_TAU_B),
+          "eigvals": s.eigvals, "eigvecs": s.eigvecs}
+    for _ in range(100):
+        st = ref.correct(s.mesh.desc, spec.models[0], spec.schemes.limiter, s.dt, s.U, s.Ub, s.phi, st["theta"], st["theta_b"],
+                         st["tau"], st["tau_b"], st["eigvals"], st["eigvecs"])
+        oc.store_old_time(); oc.step(s.dt)
+    assert rel_l2(oc.get(0, 0, abi.FIELD_THETA), st["theta"]) <= 1e-9
+    assert rel_l2(oc.get(0, 0, abi.FIELD_TAU), st["tau"]) <= 1e-9
+    assert rel_l2(oc.get(0, 0, abi.FIELD_TAU_B), st["tau_b"]) <= 1e-9
