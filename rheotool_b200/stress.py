@@ -210,6 +210,15 @@ def models_from_dict(params: dict) -> list:
             kw.pop("alpha", None)
             kw["ml_rtol"] = float(params.get("rTolMittagLeffler", 1e-12))
             kw["ml_max_iter"] = int(params.get("maxIterMittagLeffler", 200))
+    if t == "SaramitoLog":            # SaramitoLog.C:108-165
+        kw["sar_tau0"], kw["sar_n"] = float(params["tau0"]), float(params["n"])
+        kw["sar_k"] = None if kw["sar_n"] == 1.0 else float(params["k"])
+        kw["sar_dims"] = tuple(float(x) for x in params["dims"])
+        if kw["sar_n"] == 1.0:
+            fn = params.get("PTTfunction")
+            if fn not in ("none", "linear", "exponential"):
+                raise RheoError("The PTT function specified does not exist.\n\nAvailable PTT functions are:\n. none\n. linear\n. exponential")
+            kw["sar_ptt"] = fn
     return [model_desc(t, **kw)]
 
 
