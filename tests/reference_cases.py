@@ -23,6 +23,8 @@ def _fixed_theta_walls(spec):
     has phi~ = 1 - (tN - tP)/(2 grad.d + 1e-18) = 0 up to the rounding of its Gauss gradient: the reference algorithm itself
     picks `upwind` or `row 0` by the last bit there (measured: ~40 faces of a 729-cell cavity differ between two builds of
     the same text), so that combination is not a parity case for any implementation."""
+    import copy
+    spec.grid.patches = [copy.copy(p) for p in spec.grid.patches]   # cases.py shares its inlet / outlet PatchSpec objects
     for p in spec.grid.patches:
         if p.theta_bc == abi.BC_ZERO_GRADIENT:
             p.theta_bc = abi.BC_FIXED_VALUE
