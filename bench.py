@@ -187,6 +187,7 @@ def run_ours(args):
         dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local))
 
     spec, decomp, label = workload(args.config, n, args.scale)
+    spec.schemes.solver = abi.SOLVER[args.solver]
     m = build_rank_mesh(spec, decomp, rank, n)
     U, Ub, phi, theta0 = m.synth_fields(spec.synth)
     # dt for face-CFL 0.2 on the GLOBAL mesh
@@ -312,7 +313,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": label, "cells_total": n_cells_total, "cells_per_gpu": m.n_cells, "dt": dt, "cfl": spec.cfl,
                        "krylov_iterations_mean": statistics.mean(iters) if iters else None,
-                       "limiter": "cubista", "solver": "PBiCGStab+DILU", "tolerance": spec.schemes.tolerance,
+                       "limiter": "cubista", "solver": args.solver + "+DILU", "tolerance": spec.schemes.tolerance,
                        "modes": len(spec.models), "decomposition": list(decomp),
                        "l2": "working set (~1.0 kB/cell) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_value, "unit": "Mcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
@@ -396,6 +397,8 @@ def main():
     ap.add_argument("--config", default="C2", choices=["C1", "C2", "C3", "C4", "C5"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload per direction (tests only; 1.0 = the named config)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solver", default="PBiCGStab", choices=["PBiCGStab", "PBiCG"],
+                    help="Krylov method of the GPU arm (PBiCG: csrc/gpu/pbicg.cuh, one GPU; the headline configuration is PBiCGStab)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
