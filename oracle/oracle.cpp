@@ -119,6 +119,12 @@ struct Rank {
 struct Case {
     std::vector<Rank> ranks;
     RheoSchemeCtl ctl;
+    // Alternative reading of `tau_ = ...` (off by default): GeometricField::operator= assigns the boundary value of
+    // the right-hand expression to every non-fixed patch before correctBoundaryConditions(); with the boundary values of
+    // eigVals_/eigVecs_ left at their construction value I that is 0, or -etaP/lambda I where the expression goes through
+    // innerP (Oldroyd_BLog.C:176: the temporary's boundary is zero).  It is what a linearExtrapolation patch sees on a
+    // zeroGradient patch that comes LATER in the patch list.
+    bool tauAssign = false;
     bool sortEig = true;   // order eigenpairs ascending like Eigen::SelfAdjointEigenSolver (CE/constitutiveEq/constitutiveEq.C:390-414)
     int lastIters = 0;
     bool finalized = false;
@@ -999,6 +1005,16 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
         Mode& mo = rk.modes[mi];
         const Mesh& m = rk.mesh;
         dvec fb((size_t)6 * m.nB()), g((size_t)18 * m.nCells);
+        if (cs.tauAssign) {
+            const RheoModelDesc& d = mo.model.d;
+            const double e = d.model == RHEO_MODEL_OLDROYD_B_LOG ? -d.etaP / d.lambda : 0.0;
+            for (const Patch& p : m.patches)
+                if (p.type != RHEO_PATCH_EMPTY && p.type != RHEO_PATCH_PROCESSOR && p.tau_bc == RHEO_BC_ZERO_GRADIENT)
+                    for (int f = p.start; f < p.start + p.size; ++f) {
+                        double* t = &mo.tauB[(size_t)6 * (f - m.nInt)];
+                        t[0] = e; t[1] = 0; t[2] = 0; t[3] = e; t[4] = 0; t[5] = e;
+                    }
+        }
         for (const Patch& p : m.patches) {
             if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR) continue;
             if (p.tau_bc == RHEO_BC_ZERO_GRADIENT) {
@@ -1114,6 +1130,7 @@ int orc_add_mode(void* h, const RheoModelDesc* d) {
 
 int orc_set_schemes(void* h, const RheoSchemeCtl* c) { ((Case*)h)->ctl = *c; return 0; }
 int orc_set_sort_eig(void* h, int on) { ((Case*)h)->sortEig = on != 0; return 0; }
+int orc_set_tau_assignment(void* h, int on) { ((Case*)h)->tauAssign = on != 0; return 0; }
 
 int orc_set_state(void* h, int rank, int mode, const double* theta, const double* tau, const double* eigvals,
                   const double* eigvecs, const double* theta_b, const double* tau_b) {

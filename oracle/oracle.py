@@ -31,7 +31,7 @@ def lib() -> C.CDLL:
         P, I, D = C.c_void_p, C.c_int, C.c_double
         sig = {
             "orc_create": (P, [I]), "orc_destroy": (None, [P]), "orc_set_mesh": (I, [P, I, P]),
-            "orc_add_mode": (I, [P, P]), "orc_set_schemes": (I, [P, P]), "orc_set_sort_eig": (I, [P, I]),
+            "orc_add_mode": (I, [P, P]), "orc_set_schemes": (I, [P, P]), "orc_set_sort_eig": (I, [P, I]), "orc_set_tau_assignment": (I, [P, I]),
             "orc_set_state": (I, [P, I, I, P, P, P, P, P, P]), "orc_set_velocity": (I, [P, I, P, P, P]),
             "orc_store_old_time": (I, [P]), "orc_step": (I, [P, D, P]), "orc_last_iterations": (I, [P]),
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
@@ -85,6 +85,10 @@ class OracleCase:
     def set_velocity(self, rank, U, Ub, phi):
         keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (U, Ub, phi)]
         lib().orc_set_velocity(self._h, rank, *[_p(a) for a in keep])
+
+    def set_tau_assignment(self, on: bool):
+        """Alternative reading of `tau_ = ...` before tau_.correctBoundaryConditions() (oracle.cpp: Case::tauAssign)."""
+        lib().orc_set_tau_assignment(self._h, 1 if on else 0)
 
     def store_old_time(self):
         lib().orc_store_old_time(self._h)

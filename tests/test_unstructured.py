@@ -176,3 +176,10 @@ def test_oracle_matches_the_reference_text_on_the_unstructured_mesh(limiter):
     wall_cells = m.owner[walls.start: walls.start + walls.size]
     differs = np.abs(tb_o[sl] - tb_r[sl]).max(axis=1) > 1e-9 * np.abs(tb_r).max()
     assert all(int(c) in touching for c in wall_cells[differs])          # ... and so does every wall face away from `cut`
+    # and that reading of the assignment is the WHOLE difference: switched on in the oracle, tau_b agrees everywhere
+    oc2, _, _ = _oracle(m, models, sc, U, Ub, phi, theta0, thetaB)
+    oc2.set_tau_assignment(True)
+    for k in range(2):
+        oc2.store_old_time(); oc2.step(dt)
+    assert rel_l2(oc2.get(0, 0, abi.FIELD_TAU_B), tb_r) <= 1e-12
+    assert rel_l2(oc2.get(0, 0, abi.FIELD_THETA), gold[f"{limiter}/step2/theta"]) <= 1e-12
