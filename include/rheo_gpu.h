@@ -149,6 +149,11 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
 int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi);
 
 int rheo_gpu_store_old_time(RheoGpu* h);
+/* Off by default.  Alternative reading of `tau_ = ...` (Oldroyd_BLog.C:176 and the same line of the other models) before
+ * tau_.correctBoundaryConditions(): GeometricField::operator= leaves the boundary value of the right-hand expression on every
+ * non-fixed tau patch (0, or -etaP/lambda I for Oldroyd-BLog), which a linearExtrapolation patch listed EARLIER then sees
+ * (DESIGN.md section 6).  Switch on to reproduce oracle/_ref on meshes that list wall patches before zeroGradient patches. */
+int rheo_gpu_set_tau_assignment(RheoGpu* h, int32_t on);
 
 /* One constitutiveEq::correct() for all modes, inputs already resident in HBM.
  * stats: array of n_modes entries or NULL (NULL avoids the final device->host read). */

@@ -111,6 +111,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_upload_state": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P]),
     "rheo_gpu_upload_velocity": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_store_old_time": (C.c_int, [_P]),
+    "rheo_gpu_set_tau_assignment": (C.c_int, [_P, C.c_int32]),
     "rheo_gpu_step": (C.c_int, [_P, _D, _P]),
     "rheo_gpu_download": (C.c_int, [_P, _I, _I, _P]),
     "rheo_gpu_correct": (C.c_int, [_P, _P, _P, _P, _D, _I, _P, _P, _P]),

@@ -369,6 +369,17 @@ __global__ void k_bc_zero_gradient2(MeshView m, const double* __restrict__ theta
         for (int k = 0; k < 6; ++k) tauB[(size_t)k * m.nB + b] = tau[(size_t)k * m.NP + c];
 }
 
+// Optional (rheo_gpu_set_tau_assignment, off by default): what `tau_ = ...` leaves on the non-fixed tau
+// patches before correctBoundaryConditions() under the alternative reading — e on the diagonal, 0 off it
+__global__ void k_tau_b_assign(MeshView m, double e, double* __restrict__ tauB) {
+    pdl_sync();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m.nB) return;
+    if (m.bkind[b] == RHEO_PATCH_EMPTY || m.bkind[b] == RHEO_PATCH_PROCESSOR || m.btauBC[b] != RHEO_BC_ZERO_GRADIENT) return;
+    tauB[b] = e; tauB[(size_t)m.nB + b] = 0.0; tauB[(size_t)2 * m.nB + b] = 0.0;
+    tauB[(size_t)3 * m.nB + b] = e; tauB[(size_t)4 * m.nB + b] = 0.0; tauB[(size_t)5 * m.nB + b] = e;
+}
+
 // processor faces: deferred values received from the upwind side, for the cells that own ghost slots
 //   b[c] -= F * v  for inflow ghost slots;  recv layout: [(h * stride) + offset + comp]
 __global__ void k_ghost_corr(MeshView m, int nBcells, const int* __restrict__ bcells, CompList cl, const double* __restrict__ Fs,

@@ -133,6 +133,7 @@ struct RheoGpu {
     // Krylov
     DevBuf d_r, d_r0, d_p, d_y, d_v, d_s, d_z, d_t, d_ks, d_partials, d_red, d_counter, d_bcells;
     KrylovShared* h_ks = nullptr;  // pinned mirror of the device control block
+    bool tauAssign = false;        // rheo_gpu_set_tau_assignment (alternative reading of `tau_ = ...`)
     int specIters = 1;             // Krylov iterations launched speculatively per batch (= last step's count)
     int nSms = 148;                // SM count (set at create)
     std::map<const void*, int> residentBlocks;   // kernel -> SM count x resident CTAs per SM
@@ -955,6 +956,10 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         // patches in patch (= face) order, as EXT-OF9 GeometricBoundaryField::evaluate visits them: a linearExtrapolation
         // patch sees the values of the patches before it already updated and of those after it still old.  Consecutive
         // non-linearExtrapolation patches are one launch; the first launch also refreshes theta's zeroGradient faces.
+        if (h->nB && h->tauAssign) {
+            const double e = md.mp.model == RHEO_MODEL_OLDROYD_B_LOG ? -md.mp.etaP / md.mp.lambda : 0.0;   // Oldroyd_BLog.C:176 goes through innerP
+            LAUNCH(h, k_tau_b_assign, cdiv(h->nB, BLOCK), BLOCK, h->mv, e, md.tauB.as<double>());
+        }
         if (h->nB) {
             std::vector<const RheoPatchDesc*> ordered;
             for (const RheoPatchDesc& p : h->patches) ordered.push_back(&p);
@@ -1139,6 +1144,12 @@ int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, con
     }
     LAUNCH(h, k_phi_in, cdiv(h->nF, BLOCK), BLOCK, h->nF, h->d_faceOld.as<int>(), h->d_stage.as<double>(), h->d_phi.as<double>());
     LAUNCH(h, k_flux_ell, cdiv(h->N, BLOCK), BLOCK, h->mv, h->d_phi.as<double>(), h->d_Fell.as<double>());
+    return 0;
+}
+
+int rheo_gpu_set_tau_assignment(RheoGpu* h, int32_t on) {
+    if (!h) return fail("null handle");
+    h->tauAssign = on != 0;
     return 0;
 }
 

@@ -84,6 +84,10 @@ class GpuStressModel:
     def store_old_time(self):
         _check(abi.lib().rheo_gpu_store_old_time(self._h))
 
+    def set_tau_assignment(self, on: bool):
+        """Alternative reading of `tau_ = ...` before tau_.correctBoundaryConditions() (include/rheo_gpu.h; off by default)."""
+        _check(abi.lib().rheo_gpu_set_tau_assignment(self._h, 1 if on else 0))
+
     def correct(self, dt: float, want_stats: bool = False):
         """constitutiveEq::correct() with U/phi already resident on the device."""
         stats = (abi.RheoStepStats * self.n_modes)() if want_stats else None

@@ -84,6 +84,24 @@ def test_gpu_matches_the_reference_text_on_the_unstructured_mesh(limiter):
     assert rel_l2(g.download(abi.FIELD_TAU_B, 0), gold[f"{limiter}/step1/tau_b"]) <= 1e-10
 
 
+def test_gpu_tau_assignment_option_reproduces_the_reference_boundary_stress():
+    """rheo_gpu_set_tau_assignment(on): with the alternative reading of `tau_ = ...` the wall faces next to the later-listed
+    zeroGradient patch agree with the reference harness too (tests/test_unstructured.py has the CPU side of this)."""
+    from rheotool_b200.stress import GpuStressModel
+    gold = np.load(REF_GOLD)
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case()
+    sc = tight(cases.scheme_ctl("cubista", "PBiCGStab", 1e-10))
+    vals, vecs = orc.calc_eig(theta0)
+    g = GpuStressModel(m, models, sc)
+    g.set_tau_assignment(True)
+    g.upload_state(0, theta0, np.zeros_like(theta0), vals, vecs, theta_b=thetaB)
+    g.upload_velocity(U, Ub, phi)
+    for _ in range(2):
+        g.store_old_time(); g.correct(dt)
+    assert rel_l2(g.download(abi.FIELD_TAU_B, 0), gold["cubista/step2/tau_b"]) <= 1e-9
+    assert rel_l2(g.theta(), gold["cubista/step2/theta"]) <= 1e-9
+
+
 # ---- PBiCG on the device ------------------------------------------------------------------------------------------
 TOL_1 = 1e-10
 
