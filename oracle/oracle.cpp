@@ -11,12 +11,12 @@
 //   utils/jacobi.H, utils/boilerLog.H, constitutiveEq::decomposeGradU / innerP, the whole correct() bodies of
 //   Oldroyd_BLog, GiesekusLog, PTTLog (linear / exponential / generalized, zeta != 0), FENE_PLog, FENE_CRLog,
 //   WhiteMetznerCYLog, RoliePolyLog, XPomPomLog, gaussDefCmpwConvectionScheme::{fvmDiv, phifDefC, lims} with every
-//   limiter row of limiters.H, linearExtrapolationFvPatchField::updateCoeffs.  Measured agreement of theta, tau and
+//   limiter row of limiters.H incl. its coupled-patch branches on emulated ranks, linearExtrapolationFvPatchField::updateCoeffs.  Measured agreement of theta, tau and
 //   their boundary fields after one and three correct() calls: <= 4e-15 relative L2 (test bar 1e-12).
 //   NOT PINNED (not in /root/reference, restated from published OpenFOAM-9 / Eigen semantics):
 //   the OpenFOAM-9 layer under that text — gaussGrad/linear, EulerDdtScheme / backwardDdtScheme, fvMatrix::relax,
 //   solveSegregated, PBiCG / PBiCGStab / DILU iteration histories (the pin compares the SOLUTION of the assembled
-//   system, solved by the harness with a different method to round-off), processor patches — and Eigen 3.2.9's
+//   system, solved by the harness with a different method to round-off) — and Eigen 3.2.9's
 //   SelfAdjointEigenSolver (the reference's own jacobi.H alternative, constitutiveEq.C:418-426, stands in; theta
 //   and tau do not depend on the order or sign of the eigen-pairs).  Those parts stay pinned only by (a) analytic
 //   material functions and algebraic identities (tests/test_oracle_*.py), (b) cross-file steady states

@@ -47,6 +47,7 @@ def lib() -> C.CDLL:
         L.ref_decompose_gradU.restype, L.ref_decompose_gradU.argtypes = None, [I, P, P, P, P, P]
         L.ref_innerP.restype, L.ref_innerP.argtypes = None, [I, P, P, I, P]
         L.ref_correct.restype, L.ref_correct.argtypes = I, [P, P, I, D, I] + [P] * 15
+        L.ref_correct_multi.restype, L.ref_correct_multi.argtypes = I, [I, P, P, I, D, I] + [P] * 9
         _lib = L
     return _lib
 
@@ -113,3 +114,24 @@ def correct(mesh_desc, model_desc, limiter: int, dt: float, U, Ub, phi, theta, t
         raise RuntimeError("the reference harness holds no correct() text for this model")
     st.update(mats)
     return st
+
+
+def correct_multi(mesh_descs, model_desc, limiter: int, dt: float, states, use_regression=False):
+    """One XxxLog::correct() of the reference on R sub-domain meshes with processor patches (one thread per rank).
+    `states`: per rank a dict with U, Ub, phi, theta, theta_b, tau, tau_b, eigvals, eigvecs; returns the per-rank states after."""
+    R = len(mesh_descs)
+    keys_in = ("U", "Ub", "phi")
+    keys_io = ("theta", "theta_b", "tau", "tau_b", "eigvals", "eigvecs")
+    keep = [{k: _f(st[k]).copy() for k in keys_in + keys_io} for st in states]
+    ptrs = {k: (C.c_void_p * R)(*[a[k].ctypes.data for a in keep]) for k in keys_in + keys_io}
+    descs = (C.c_void_p * R)(*[C.cast(C.byref(d), C.c_void_p).value for d in mesh_descs])
+    rc = lib().ref_correct_multi(R, C.cast(descs, C.c_void_p), C.cast(C.byref(model_desc), C.c_void_p), int(limiter), float(dt),
+                                 1 if use_regression else 0, *[C.cast(ptrs[k], C.c_void_p) for k in keys_in + keys_io])
+    if rc:
+        raise RuntimeError("the reference harness holds no correct() text for this model")
+    out = []
+    for r, d in enumerate(mesh_descs):
+        n, nb = d.n_cells, d.n_faces - d.n_internal_faces
+        shapes = {"theta": (n, 6), "theta_b": (nb, 6), "tau": (n, 6), "tau_b": (nb, 6), "eigvals": (n, 9), "eigvecs": (n, 9)}
+        out.append({k: keep[r][k].reshape(shapes[k]) for k in keys_io})
+    return out

@@ -1,7 +1,8 @@
 // ref_harness.cpp — C entry points of oracle/_ref/libref_stress.so (TEST INFRASTRUCTURE ONLY).
 //
 // Runs the reference's OWN text for the stress step (see ref_ce.H for the list of files and line ranges)
-// on a mesh given as a RheoMeshDesc, so that tests/ can pin oracle/oracle.cpp against it.  What is NOT the
+// on a mesh given as a RheoMeshDesc (ref_correct), or on R decomposed meshes with processor patches, one thread per rank
+// (ref_correct_multi), so that tests/ can pin oracle/oracle.cpp against it.  What is NOT the
 // reference's here, and therefore not pinned by it: the OpenFOAM-9 layer (minifoam.H), the linear solver
 // (a Jacobi iteration to round-off — the pinned quantity is the solution of the assembled system, not an
 // iteration history) and the eigen-solver call (Eigen 3.2.9 is absent; the reference's own jacobi.H is
@@ -13,6 +14,7 @@
 #include "../../include/rheo_gpu.h"
 
 #include <cstring>
+#include <thread>
 
 namespace Foam
 {
@@ -79,6 +81,8 @@ void GeometricField<Type, PatchField, GeoMesh>::correctBoundaryConditions()
 {
     if constexpr (std::is_same<GeoMesh, volMesh>::value)
     {
+        // non-blocking processor patches: every send and receive completes before the first evaluate()
+        evaluateCoupled(*this);
         forAll(boundary_, patchi)
         {
             auto& pf = boundary_[patchi];
@@ -131,9 +135,11 @@ static void buildMesh(fvMesh& m, const RheoMeshDesc* d)
     {
         const RheoPatchDesc& pd = d->patches[p];
         fvPatch& fp = m.boundary_[p];
-        fp.bm_ = &m.boundary_; fp.index_ = p; fp.start_ = pd.start; fp.kind_ = pd.type; fp.coupled_ = false;
-        if (pd.type == RHEO_PATCH_PROCESSOR)
-            FatalError << "the reference harness runs single-rank meshes only" << abort(FatalError);
+        fp.bm_ = &m.boundary_; fp.index_ = p; fp.start_ = pd.start; fp.kind_ = pd.type;
+        fp.coupled_ = pd.type == RHEO_PATCH_PROCESSOR;
+        fp.nbrRank_ = pd.nbr_rank;
+        if (fp.coupled_ && !refHarness::world())
+            FatalError << "processor patches need ref_correct_multi (one thread per rank)" << abort(FatalError);
         if (pd.type == RHEO_PATCH_EMPTY) continue;   // emptyFvPatch::size() == 0
         for (label i = 0; i < pd.size; i++)
         {
@@ -141,7 +147,12 @@ static void buildMesh(fvMesh& m, const RheoMeshDesc* d)
             fp.faceCells_.append(d->owner[f]);
             fp.Cf_.append(m.allCf_[f]);
             fp.Sf_.append(m.allSf_[f]);
-            fp.delta_.append(m.allCf_[f] - m.C_[d->owner[f]]);
+            if (fp.coupled_)   // processorFvPatch::delta(): neighbour cell centre - own cell centre; linear weight of the owner side
+            {
+                fp.delta_.append(v3(d->nbr_C, f - d->n_internal_faces) - m.C_[d->owner[f]]);
+                fp.weights_.append(d->weights[f]);
+            }
+            else fp.delta_.append(m.allCf_[f] - m.C_[d->owner[f]]);
         }
     }
 }
@@ -154,6 +165,7 @@ static int bcKind(int bc)
         case RHEO_BC_ZERO_GRADIENT: return pfZeroGradient;
         case RHEO_BC_LINEAR_EXTRAPOLATION: return pfLinearExtrapolation;
         case RHEO_BC_EMPTY: return pfEmpty;
+        case RHEO_BC_PROCESSOR: return pfProcessor;
     }
     FatalError << "patch field kind not available in the reference harness" << abort(FatalError);
     return pfCalculated;
@@ -280,17 +292,20 @@ void ref_innerP(int n, const double* t1, const double* t2, int isFirstT, double*
 //   asm_lower/upper [n_internal_faces], asm_diag [n_cells], asm_source [6*n_cells], asm_iC/asm_bC [6*n_bfaces]:
 //   optional (NULL) — the thetaEqn the reference assembled, as handed to solve().
 // Returns 0, or -1 for a model the harness has no reference text for.
-int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, double dt, int use_regression,
-                const double* U, const double* U_b, const double* phi,
-                double* theta, double* theta_b, double* tau, double* tau_b, double* eigvals, double* eigvecs,
-                double* asm_lower, double* asm_upper, double* asm_diag, double* asm_source,
-                double* asm_iC, double* asm_bC)
+struct RankArrays
 {
-    fvMesh mesh;
-    buildMesh(mesh, md);
+    const double *U, *U_b, *phi;
+    double *theta, *theta_b, *tau, *tau_b, *eigvals, *eigvecs;
+    double *asm_lower, *asm_upper, *asm_diag, *asm_source, *asm_iC, *asm_bC;
+};
+
+static int correctOnMesh(fvMesh& mesh, const RheoMeshDesc* md, const RheoModelDesc* mm, double dt, const RankArrays& a)
+{
+    const double *U = a.U, *U_b = a.U_b, *phi = a.phi;
+    double *theta = a.theta, *theta_b = a.theta_b, *tau = a.tau, *tau_b = a.tau_b, *eigvals = a.eigvals, *eigvecs = a.eigvecs;
+    double *asm_lower = a.asm_lower, *asm_upper = a.asm_upper, *asm_diag = a.asm_diag, *asm_source = a.asm_source, *asm_iC = a.asm_iC,
+           *asm_bC = a.asm_bC;
     mesh.time_.deltaT_ = dt;
-    refHarness::limiterName = limiterWord(limiter);
-    refHarness::useRegression = use_regression != 0;
 
     volVectorField Uf(IOobject("U"), mesh, dimensionSet());
     surfaceScalarField phif(IOobject("phi"), mesh, dimensionSet());
@@ -302,7 +317,8 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
     for (label p = 0; p < md->n_patches; p++)
     {
         const bool empty = md->patches[p].type == RHEO_PATCH_EMPTY;
-        Uf.setPatchKind(p, empty ? pfEmpty : pfFixedValue);
+        const bool proc = md->patches[p].type == RHEO_PATCH_PROCESSOR;
+        Uf.setPatchKind(p, empty ? pfEmpty : proc ? pfProcessor : pfFixedValue);
         thetaf.setPatchKind(p, empty ? pfEmpty : bcKind(md->patches[p].theta_bc));
         tauf.setPatchKind(p, empty ? pfEmpty : bcKind(md->patches[p].tau_bc));
     }
@@ -314,6 +330,8 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
     forAll(phif, f) phif[f] = phi[f];
     forAll(phif.boundaryField(), p) forAll(phif.boundaryField()[p], i)
         phif.boundaryFieldRef()[p][i] = phi[md->patches[p].start + i];
+    // processor patches hold the neighbour cells' values (processorFvPatchField after evaluate())
+    evaluateCoupled(Uf); evaluateCoupled(thetaf); evaluateCoupled(tauf);
     thetaf.storeOldTime();
     tauf.store();      // linearExtrapolation looks tau up by name in the registry
     thetaf.store();
@@ -413,6 +431,67 @@ int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, do
         }
         last.reset();
     }
+    return 0;
+}
+
+
+int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, double dt, int use_regression,
+                const double* U, const double* U_b, const double* phi,
+                double* theta, double* theta_b, double* tau, double* tau_b, double* eigvals, double* eigvecs,
+                double* asm_lower, double* asm_upper, double* asm_diag, double* asm_source,
+                double* asm_iC, double* asm_bC)
+{
+    fvMesh mesh;
+    buildMesh(mesh, md);
+    refHarness::limiterName = limiterWord(limiter);
+    refHarness::useRegression = use_regression != 0;
+    const RankArrays a{U, U_b, phi, theta, theta_b, tau, tau_b, eigvals, eigvecs, asm_lower, asm_upper, asm_diag, asm_source, asm_iC, asm_bC};
+    return correctOnMesh(mesh, md, mm, dt, a);
+}
+
+// The same on R sub-domain meshes with processor patches (decomposePar layout): one thread per rank, lock-step collectives in
+// place of Pstream (minifoam.H: refHarness::World).  Arrays are given per rank: U[r], U_b[r], ... (boundary arrays indexed by
+// face - n_internal_faces of that rank's mesh; values on processor faces are ignored on input).
+int ref_correct_multi(int R, const RheoMeshDesc* const* md, const RheoModelDesc* mm, int limiter, double dt, int use_regression,
+                      const double* const* U, const double* const* U_b, const double* const* phi,
+                      double* const* theta, double* const* theta_b, double* const* tau, double* const* tau_b,
+                      double* const* eigvals, double* const* eigvecs)
+{
+    refHarness::World world;
+    world.R = R;
+    world.mail.resize(R);
+    world.red.assign(R, 0.0);
+    refHarness::world() = &world;
+    refHarness::limiterName = limiterWord(limiter);
+    refHarness::useRegression = use_regression != 0;
+    std::vector<fvMesh> meshes(R);
+    for (int r = 0; r < R; r++)
+    {
+        buildMesh(meshes[r], md[r]);
+        world.mail[r].resize(md[r]->n_patches);
+    }
+    for (int r = 0; r < R; r++)   // the patch of the neighbour rank that faces this one
+        for (fvPatch& p : meshes[r].boundary_)
+            if (p.coupled())
+            {
+                const fvBoundaryMesh& nb = meshes[p.nbrRank_].boundary_;
+                for (size_t q = 0; q < nb.size(); q++) if (nb[q].coupled() && nb[q].nbrRank_ == r) p.nbrPatch_ = label(q);
+                if (p.nbrPatch_ < 0 || nb[p.nbrPatch_].size() != p.size())
+                    FatalError << "processor patches of ranks " << r << " and " << p.nbrRank_ << " do not match" << abort(FatalError);
+            }
+    std::vector<int> rc(R, 0);
+    std::vector<std::thread> threads;
+    for (int r = 0; r < R; r++)
+        threads.emplace_back([&, r]()
+        {
+            refHarness::myRank() = r;
+            const RankArrays a{U[r], U_b[r], phi[r], theta[r], theta_b[r], tau[r], tau_b[r], eigvals[r], eigvecs[r],
+                               nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+            rc[r] = correctOnMesh(meshes[r], md[r], mm, dt, a);
+        });
+    for (auto& t : threads) t.join();
+    refHarness::world() = nullptr;
+    for (int r = 0; r < R; r++) if (rc[r]) return rc[r];
     return 0;
 }
 

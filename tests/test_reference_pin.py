@@ -235,3 +235,45 @@ def test_decomposed_oracle_reproduces_the_single_rank_reference(gold, name, n):
             for r in range(nr):
                 got[addr[r]] = many.get(r, 0, fld)
             assert rel_l2(got, gold[f"{name}/step{k + 1}/{key}"]) <= 1e-11, (name, k, key)
+
+
+@live
+@pytest.mark.parametrize("name,n", [("GiesekusLog-3D-contraction-cubista", (2, 2, 1)), ("PTTLog-linear-zeta-2D-minmod", (3, 1, 1))])
+def test_live_reference_text_on_several_ranks(gold, name, n):
+    """The reference's text itself on a decomposed mesh (one thread per rank, processor patches: the coupled branches of
+    gaussDefCmpwConvectionScheme.C:104-110, 158-167, 289-319, gradients with neighbour values, interfaces in the solve)
+    against (1) its own single-rank numbers and (2) the oracle on the same emulated ranks."""
+    spec, s = make_setup(name)
+    nr = n[0] * n[1] * n[2]
+    c2r = s.mesh.simple_decomp(*n)
+    subs = [s.mesh.decompose(c2r, nr, r) for r in range(nr)]
+    many = orc.OracleCase([x.desc for x in subs], spec.models, spec.schemes, False)
+    states, addr = [], []
+    for r, sub in enumerate(subs):
+        ca, fa = sub.proc_addressing()
+        addr.append(ca)
+        gf = np.abs(fa) - 1
+        ph = np.where(fa > 0, s.phi[gf], -s.phi[gf])
+        gb = gf[sub.n_internal:] - s.mesh.n_internal
+        Ub = np.zeros((sub.n_boundary, 3))
+        Ub[gb >= 0] = s.Ub[gb[gb >= 0]]
+        many.set_state(r, 0, s.theta0[ca], s.tau0[ca], s.eigvals[ca], s.eigvecs[ca])
+        many.set_velocity(r, s.U[ca], Ub, ph)
+        states.append({"U": s.U[ca], "Ub": Ub, "phi": ph, "theta": s.theta0[ca], "theta_b": many.get(r, 0, abi.FIELD_THETA_B),
+                       "tau": s.tau0[ca], "tau_b": many.get(r, 0, abi.FIELD_TAU_B), "eigvals": s.eigvals[ca], "eigvecs": s.eigvecs[ca]})
+    out = ref.correct_multi([x.desc for x in subs], spec.models[0], spec.schemes.limiter, s.dt, states)
+    many.store_old_time(); many.step(s.dt)
+    for key, fld in (("theta", abi.FIELD_THETA), ("tau", abi.FIELD_TAU)):
+        whole = np.empty_like(gold[f"{name}/step1/{key}"])
+        for r in range(nr):
+            whole[addr[r]] = out[r][key]
+            assert rel_l2(many.get(r, 0, fld), out[r][key]) <= TOL_ORACLE, (key, r)          # (2)
+        assert rel_l2(whole, gold[f"{name}/step1/{key}"]) <= 1e-12, key                       # (1)
+    for r in range(nr):   # boundary stresses incl. the walls next to processor faces
+        tb_o, tb_r = many.get(r, 0, abi.FIELD_TAU_B), out[r]["tau_b"]
+        phys = np.ones(len(tb_o), bool)
+        d = subs[r].desc
+        for p in range(d.n_patches):
+            if d.patches[p].type == abi.PATCH_PROCESSOR:
+                phys[d.patches[p].start - d.n_internal_faces: d.patches[p].start - d.n_internal_faces + d.patches[p].size] = False
+        assert rel_l2(tb_o[phys], tb_r[phys]) <= TOL_ORACLE, r
