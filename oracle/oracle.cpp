@@ -10,8 +10,9 @@
 //   tests/golden/reference_{cell,correct}.npz by tools/make_golden_reference.py; tests/test_reference_pin.py):
 //   utils/jacobi.H, utils/boilerLog.H, constitutiveEq::decomposeGradU / innerP, the whole correct() bodies of
 //   Oldroyd_BLog, GiesekusLog, PTTLog (linear / exponential / generalized, zeta != 0), FENE_PLog, FENE_CRLog,
-//   WhiteMetznerCYLog, RoliePolyLog, XPomPomLog, gaussDefCmpwConvectionScheme::{fvmDiv, phifDefC, lims} with every
-//   limiter row of limiters.H incl. its coupled-patch branches on emulated ranks, linearExtrapolationFvPatchField::updateCoeffs.  Measured agreement of theta, tau and
+//   WhiteMetznerCYLog, RoliePolyLog, XPomPomLog, SaramitoLog, gaussDefCmpwConvectionScheme::{fvmDiv, phifDefC, lims} with
+//   every limiter row of limiters.H (its coupled-patch branches too, on emulated ranks),
+//   linearExtrapolationFvPatchField::updateCoeffs.  Measured agreement of theta, tau and
 //   their boundary fields after one and three correct() calls: <= 4e-15 relative L2 (test bar 1e-12).
 //   NOT PINNED (not in /root/reference, restated from published OpenFOAM-9 / Eigen semantics):
 //   the OpenFOAM-9 layer under that text — gaussGrad/linear, EulerDdtScheme / backwardDdtScheme, fvMatrix::relax,
