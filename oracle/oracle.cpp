@@ -1244,6 +1244,19 @@ void orc_model_rhs(const RheoModelDesc* d, int n, const double* L9, const double
         if (f) f[c] = ff;
     }
 }
+// the same with the model's current tau of each cell (read by SaramitoLog only)
+void orc_model_rhs_tau(const RheoModelDesc* d, int n, const double* L9, const double* theta6, const double* R9, const double* Lam9, const double* tau6,
+                       double* rhs6, double* f) {
+    Model mo;
+    mo.d = *d;
+    init_model(mo);
+    for (int c = 0; c < n; ++c) {
+        T9 L, R, Lam;
+        std::memcpy(L.v, L9 + 9 * (size_t)c, 72); std::memcpy(R.v, R9 + 9 * (size_t)c, 72); std::memcpy(Lam.v, Lam9 + 9 * (size_t)c, 72);
+        double ff = model_rhs_cell(mo, L, theta6 + 6 * (size_t)c, R, Lam, rhs6 + 6 * (size_t)c, tau6 ? tau6 + 6 * (size_t)c : nullptr);
+        if (f) f[c] = ff;
+    }
+}
 void orc_tau(const RheoModelDesc* d, int n, const double* R9, const double* Lam9, const double* f, double* tau6) {
     Model mo;
     mo.d = *d;

@@ -36,7 +36,7 @@ def lib() -> C.CDLL:
             "orc_store_old_time": (I, [P]), "orc_step": (I, [P, D, P]), "orc_last_iterations": (I, [P]),
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
             "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
-            "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
+            "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_model_rhs_tau": (None, [P, I, P, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
             "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []),
         }
         for n, (r, a) in sig.items():
@@ -134,13 +134,18 @@ def decompose_gradU(L9, R9, Lam9, zeta=0.0, ptt=False):
     return om, B
 
 
-def model_rhs(model, L9, theta6, R9, Lam9):
+def model_rhs(model, L9, theta6, R9, Lam9, tau6=None):
+    """tau6: the model's current stress per cell (SaramitoLog's yield criterion); None = zero."""
     L9 = np.ascontiguousarray(L9, dtype=np.float64).reshape(-1, 9)
     th = np.ascontiguousarray(theta6, dtype=np.float64).reshape(-1, 6)
     R9 = np.ascontiguousarray(R9, dtype=np.float64).reshape(-1, 9)
     Lam9 = np.ascontiguousarray(Lam9, dtype=np.float64).reshape(-1, 9)
     rhs = np.zeros_like(th); f = np.zeros(len(th))
-    lib().orc_model_rhs(C.byref(model), len(th), _p(L9), _p(th), _p(R9), _p(Lam9), _p(rhs), _p(f))
+    if tau6 is None:
+        lib().orc_model_rhs(C.byref(model), len(th), _p(L9), _p(th), _p(R9), _p(Lam9), _p(rhs), _p(f))
+    else:
+        t6 = np.ascontiguousarray(tau6, dtype=np.float64).reshape(-1, 6)
+        lib().orc_model_rhs_tau(C.byref(model), len(th), _p(L9), _p(th), _p(R9), _p(Lam9), _p(t6), _p(rhs), _p(f))
     return rhs, f
 
 
