@@ -123,6 +123,8 @@ typedef struct RheoGpu RheoGpu;
 #define RHEO_FIELD_TAU_B      5  /* symmTensor, 6/boundary face */
 #define RHEO_FIELD_TAU_TOTAL  6  /* sum over modes of tau, 6/cell (multiMode::tau) */
 #define RHEO_FIELD_THETA_OLD  7
+#define RHEO_FIELD_TAU_B_TOTAL 8 /* sum over modes of the boundary stress, 6/boundary face: what multiMode::divTau sees on the
+                                    patches (each mode's own linearExtrapolation / zeroGradient / fixedValue values, summed) */
 
 int rheo_gpu_device_count(void);
 
@@ -162,7 +164,7 @@ int rheo_gpu_step(RheoGpu* h, double dt, RheoStepStats* stats);
 int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst);
 
 /* Host-buffer convenience = upload_velocity + store_old_time (if new_time_step) + step +
- * download(TAU_TOTAL) (+ TAU_B of mode 0 when tau_b != NULL): what the reference plugin call costs
+ * download(TAU_TOTAL) (+ TAU_B_TOTAL, the boundary stress summed over the modes, when tau_b != NULL): what the reference plugin call costs
  * when the momentum predictor stays on the CPU. */
 int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const double* phi, double dt,
                      int32_t new_time_step, double* tau_out, double* tau_b_out, RheoStepStats* stats);
@@ -170,6 +172,9 @@ int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const doubl
 /* ---- introspection used by the parity tests and bench.py ---- */
 /* renumbering actually used on the device: perm[new] = old cell, n_colours, colour_start[n_colours+1] */
 int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int32_t* colour_start);
+/* one line of text naming the cell ordering the DILU substitutions run in on this handle, e.g.
+ * "8x8x4 blocks (256 cells), natural order inside, 2 block colours" or "cell colouring, 2 colours" */
+int rheo_gpu_get_ordering(RheoGpu* h, char* buf, int32_t buflen);
 /* ELL width K and the neighbour table nbr[K*n_cells] (slot-major, in NEW numbering: >=0 cell,
  * >= n_cells ghost, -1 empty, <=-2 boundary face -(b+2)) and face table (face index, ~face when
  * the cell is the face's neighbour) */

@@ -40,6 +40,8 @@
 #include <string>
 #include <vector>
 
+#include <omp.h>
+
 #include "rheo_gpu.h"
 #include "rheo_mesh.h"
 
@@ -490,9 +492,13 @@ struct Ldu {   // one scalar system per component on the shared LDU structure
     std::vector<dvec> ifBou, ifInt;   // per boundary face (only processor faces used)
 };
 
+// threads of the rank loop; 0 = OpenMP's default (OMP_NUM_THREADS).  bench.py sets it explicitly: under torchrun the
+// environment carries OMP_NUM_THREADS=1, which would silently time the CPU arm on one core.
+int g_threads = 0;
 template <class F> void for_ranks(Case& cs, F f) {
     const int R = (int)cs.ranks.size();
-#pragma omp parallel for schedule(static) if (R > 1)
+    const int nt = g_threads > 0 ? g_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(static) num_threads(nt) if (R > 1)
     for (int r = 0; r < R; ++r) f(r);
 }
 
@@ -665,7 +671,9 @@ Perf pbicgstab(Ldu& A, DVec& psi, const DVec& source, const RheoSchemeCtl& ctl) 
                 }
             });
             perf.fin = sumMag(rA) / normFactor;
-        } while ((perf.iters++ < ctl.max_iter && !check_conv(perf, ctl.tolerance, ctl.rel_tol)) || perf.iters < ctl.min_iter);
+            // EXT-OF9 PBiCGStab.C: `(++solverPerf.nIterations() < maxIter_ && !converged) || nIterations() < minIter_` — a
+            // PRE-increment, unlike PBiCG / PCG below (`nIterations()++ < maxIter_`)
+        } while ((++perf.iters < ctl.max_iter && !check_conv(perf, ctl.tolerance, ctl.rel_tol)) || perf.iters < ctl.min_iter);
     }
     perf.conv = check_conv(perf, ctl.tolerance, ctl.rel_tol);
     return perf;
@@ -1079,6 +1087,20 @@ void init_model(Model& mo) {
 extern "C" {
 
 const char* orc_last_error(void) { return g_err.c_str(); }
+
+// number of threads the rank loop uses (0 restores OMP_NUM_THREADS); returns the count a parallel region actually gets
+int orc_set_num_threads(int n) {
+    g_threads = n > 0 ? n : 0;
+    omp_set_dynamic(0);
+    int got = 1;
+    const int nt = g_threads > 0 ? g_threads : omp_get_max_threads();
+#pragma omp parallel num_threads(nt)
+    {
+#pragma omp single
+        got = omp_get_num_threads();
+    }
+    return got;
+}
 
 void* orc_create(int n_ranks) {
     auto* cs = new Case();

@@ -37,13 +37,18 @@ def lib() -> C.CDLL:
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
             "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
             "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_model_rhs_tau": (None, [P, I, P, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
-            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []),
+            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
             f.restype, f.argtypes = r, a
         _lib = L
     return _lib
+
+
+def set_num_threads(n: int) -> int:
+    """Threads of the oracle's rank loop (one sub-domain per thread); returns how many a parallel region really gets."""
+    return int(lib().orc_set_num_threads(int(n)))
 
 
 def _p(a):

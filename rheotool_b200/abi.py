@@ -18,7 +18,7 @@ PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
 LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}
 DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON = 0, 1, 2
 SOLVER = {"PBiCGStab": 0, "PBiCG": 1}
-FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD = range(8)
+FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD, FIELD_TAU_B_TOTAL = range(9)
 FLOW_CONTRACTION_2D, FLOW_VORTEX, FLOW_CONTRACTION_3D = 0, 1, 2
 
 MODEL_NAMES = {
@@ -117,6 +117,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_correct": (C.c_int, [_P, _P, _P, _P, _D, _I, _P, _P, _P]),
     "rheo_gpu_get_renumbering": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ell": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_gpu_get_ordering": (C.c_int, [_P, _P, _I]),
     "rheo_gpu_launch_count": (C.c_int64, [_P]),
     "rheo_gpu_last_iterations": (C.c_int, [_P]),
     "rheo_gpu_transfer_bytes": (C.c_int, [_P, _P, _P]),

@@ -110,6 +110,7 @@ struct RheoGpu {
     int comps[6];                  // indices of solved components
     int nColours = 0;
     std::vector<int> colourStart;
+    std::string orderingInfo;      // rheo_gpu_get_ordering
     long nGlobalCells = 0;
     // host-side maps
     std::vector<int> perm;         // perm[new] = old
@@ -269,6 +270,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     // ---- renumbering
     h->nColours = colour_renumber(N, nInt, d->owner, d->neighbour, h->perm, h->colourStart);
     if (h->nColours < 1) return fail("rheo_gpu_create: colouring failed (more than 63 colours)");
+    h->orderingInfo = "cell colouring, " + std::to_string(h->nColours) + " colours";
     std::vector<int> iperm(N);
     for (int c = 0; c < N; ++c) iperm[h->perm[c]] = c;
 
@@ -1193,6 +1195,13 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
         case RHEO_FIELD_EIGVECS: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 9, h->d_perm.as<int>(), md.R.as<double>(), stage, NP); bytes = (size_t)N * 9; break;
         case RHEO_FIELD_THETA_B: if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, md.thetaB.as<double>(), stage, nB); bytes = (size_t)nB * 6; break;
         case RHEO_FIELD_TAU_B: if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, md.tauB.as<double>(), stage, nB); bytes = (size_t)nB * 6; break;
+        case RHEO_FIELD_TAU_B_TOTAL:   // multiMode::divTau sums each mode's divTau, i.e. sees the sum of the modes' patch values
+            for (size_t mi = 0; nB && mi < h->modes.size(); ++mi) {
+                if (mi == 0) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, h->modes[mi].tauB.as<double>(), stage, nB);
+                else LAUNCH(h, k_soa_to_aos_acc, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, h->modes[mi].tauB.as<double>(), stage, nB);
+            }
+            bytes = (size_t)nB * 6;
+            break;
         default: return fail("rheo_gpu_download: unknown field");
     }
     if (bytes) CK(cudaMemcpyAsync(dst, stage, bytes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1207,7 +1216,7 @@ int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const doubl
     if (new_time_step && rheo_gpu_store_old_time(h)) return 1;
     if (rheo_gpu_step(h, dt, stats)) return 1;
     if (tau_out && rheo_gpu_download(h, 0, RHEO_FIELD_TAU_TOTAL, tau_out)) return 1;
-    if (tau_b_out && rheo_gpu_download(h, 0, RHEO_FIELD_TAU_B, tau_b_out)) return 1;
+    if (tau_b_out && rheo_gpu_download(h, 0, RHEO_FIELD_TAU_B_TOTAL, tau_b_out)) return 1;
     return 0;
 }
 
@@ -1216,6 +1225,12 @@ int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int3
     if (perm) std::copy(h->perm.begin(), h->perm.end(), perm);
     if (n_colours) *n_colours = h->nColours;
     if (colour_start) std::copy(h->colourStart.begin(), h->colourStart.end(), colour_start);
+    return 0;
+}
+
+int rheo_gpu_get_ordering(RheoGpu* h, char* buf, int32_t buflen) {
+    if (!h || !buf || buflen < 1) return fail("rheo_gpu_get_ordering: bad argument");
+    snprintf(buf, (size_t)buflen, "%s", h->orderingInfo.c_str());
     return 0;
 }
 

@@ -162,7 +162,9 @@ __device__ __forceinline__ void ctl_end_one(KrylovCtl& k, double sumR, double r0
         k.finRes = sumR / k.normFactor;
         k.rhoOld = k.rho;
         k.rho = r0r;
-        const bool cont = ((k.iters++ < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
+        // EXT-OF9 PBiCGStab::solve: `(++nIterations() < maxIter_ && !converged) || nIterations() < minIter_` — PRE-increment
+        // (PBiCG and PCG post-increment: ctl_pb_end_one)
+        const bool cont = ((++k.iters < sc.maxIter) && !conv_check(k.finRes, k.initRes, sc)) || k.iters < sc.minIter;
         if (!cont) k.state = 2;
         else if (!(fabs(k.rho) > 1e-300) || !(fabs(k.omega) > 1e-300)) { k.state = 2; k.singular = 1; }
         else k.beta = (k.rho / k.rhoOld) * (k.alpha / k.omega);

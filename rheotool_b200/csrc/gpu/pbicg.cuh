@@ -16,7 +16,8 @@
 // separate reduction kernels with the scalar control in their last-block epilogue (same KrylovCtl block as PBiCGStab).
 // It reads each matrix row twice per product instead of streaming it through the row-tile pipeline of krylov.cuh, and
 // runs on one rank (processor-patch columns are not added): PBiCGStab remains the tuned, multi-GPU path.
-// STATUS: written after the round's GPU budget was spent — compiled for sm_100a, not yet run on hardware.
+// STATUS: run on B200 in round 2 (tests/test_gpu_pbicg.py): parity with the oracle's PBiCG, with PBiCGStab on the device and
+// with the reference fixtures; same iteration counts as the oracle on the renumbered mesh.
 #pragma once
 #include "krylov.cuh"
 
@@ -65,6 +66,35 @@ __global__ void __launch_bounds__(BLOCK) k_pb_sweep(MeshView m, int c0, int c1, 
             stv<NR>(wT, base + c, ot);
         }
     }
+}
+
+// Initial transpose residual.  EXT-OF9 PBiCG::solve starts from rT = source - A^T psi (Tmul), not from rT = rA: with
+// rA = b - A psi already formed by k_krylov_init (b includes the deferred inflow terms folded there),
+//     rT = rA + (A - A^T) psi = rA + sum_{local slots} (A[s] - AT[s]) psi[nb]     (the diagonal is shared)
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_pb_init_rT(MeshView m, int nModes, RhsPtrs rp, const double* __restrict__ A, const double* __restrict__ AT,
+                                                       const double* __restrict__ rA, double* __restrict__ rT) {
+    pdl_sync();
+    const int stride = gridDim.x * BLOCK;
+    for (int md = 0; md < nModes; ++md)
+        for (int c = blockIdx.x * BLOCK + threadIdx.x; c < m.N; c += stride) {
+            double acc[NR];
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+            for (int s = 0; s < m.K; ++s) {
+                const size_t e = ell_t(m.K, s, c);
+                const int nb = m.nbrA[e];
+                if (nb == c || nb >= m.N) continue;
+                const double d = A[e] - AT[e];
+#pragma unroll
+                for (int j = 0; j < NR; ++j) acc[j] += d * rp.psi[md * NR + j][nb];
+            }
+            double r[NR];
+            ldv<NR>(rA, (size_t)md * m.NP + c, r);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) r[j] += acc[j];
+            stv<NR>(rT, (size_t)md * m.NP + c, r);
+        }
 }
 
 // wArT = wA . rT per RHS; epilogue: beta

@@ -201,6 +201,8 @@ int solve_batch_pbicg(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, 
     if (all_reduce(h, sumPsi, nrhs)) return 1;
     LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, rA, rT, part, redB, counter,
            CTL_INIT, ks, sc);
+    // EXT-OF9 PBiCG::solve: the transpose residual starts from source - A^T psi
+    LAUNCH(h, (k_pb_init_rT<NR>), GRID(h, (k_pb_init_rT<NR>), N), BLOCK, h->mv, nModes, rp, A, AT, rA, rT);
     int launched = 0;
     int spec = std::max(1, h->specIters);
     for (;;) {

@@ -99,7 +99,7 @@ class GpuStressModel:
         _check(abi.lib().rheo_gpu_correct(self._h, U_ptr, Ub_ptr, phi_ptr, float(dt), 1 if new_time_step else 0, tau_out_ptr, tau_b_out_ptr, None))
 
     def download(self, field: int, mode: int = 0) -> np.ndarray:
-        n = self.mesh.n_boundary if field in (abi.FIELD_THETA_B, abi.FIELD_TAU_B) else self.mesh.n_cells
+        n = self.mesh.n_boundary if field in (abi.FIELD_THETA_B, abi.FIELD_TAU_B, abi.FIELD_TAU_B_TOTAL) else self.mesh.n_cells
         w = 9 if field in (abi.FIELD_EIGVALS, abi.FIELD_EIGVECS) else 6
         out = np.zeros((n, w))
         _check(abi.lib().rheo_gpu_download(self._h, mode, field, _p(out)))
@@ -127,6 +127,12 @@ class GpuStressModel:
         face = np.zeros((K.value, self.mesh.n_cells), dtype=np.int32)
         _check(abi.lib().rheo_gpu_get_ell(self._h, C.byref(K), _p(nbr), _p(face)))
         return nbr, face
+
+    def ordering(self) -> str:
+        """The cell ordering the DILU substitutions run in."""
+        buf = C.create_string_buffer(256)
+        _check(abi.lib().rheo_gpu_get_ordering(self._h, buf, len(buf)))
+        return buf.value.decode()
 
     def launch_count(self) -> int:
         return int(abi.lib().rheo_gpu_launch_count(self._h))

@@ -68,7 +68,7 @@ def test_constants_match_the_headers():
         assert defs["RHEO_LIMITER_" + name.upper()] == val
     assert defs["RHEO_SOLVER_PBICGSTAB"] == abi.SOLVER["PBiCGStab"] and defs["RHEO_SOLVER_PBICG"] == abi.SOLVER["PBiCG"]
     assert (defs["RHEO_FIELD_THETA"], defs["RHEO_FIELD_TAU"], defs["RHEO_FIELD_EIGVALS"], defs["RHEO_FIELD_EIGVECS"], defs["RHEO_FIELD_THETA_B"],
-            defs["RHEO_FIELD_TAU_B"], defs["RHEO_FIELD_TAU_TOTAL"], defs["RHEO_FIELD_THETA_OLD"]) == tuple(range(8))
+            defs["RHEO_FIELD_TAU_B"], defs["RHEO_FIELD_TAU_TOTAL"], defs["RHEO_FIELD_THETA_OLD"], defs["RHEO_FIELD_TAU_B_TOTAL"]) == tuple(range(9))
     assert (defs["RHEO_PATCH_PATCH"], defs["RHEO_PATCH_WALL"], defs["RHEO_PATCH_EMPTY"], defs["RHEO_PATCH_PROCESSOR"]) == (0, 1, 2, 3)
     assert (defs["RHEO_BC_FIXED_VALUE"], defs["RHEO_BC_ZERO_GRADIENT"], defs["RHEO_BC_LINEAR_EXTRAPOLATION"], defs["RHEO_BC_EMPTY"],
             defs["RHEO_BC_PROCESSOR"]) == (0, 1, 2, 3, 4)

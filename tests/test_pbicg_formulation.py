@@ -1,4 +1,4 @@
-"""CPU check of the FORMULATION pbicg.cuh implements (the kernels themselves need a GPU: tests/test_zz_gpu_not_yet_run.py).
+"""CPU check of the FORMULATION pbicg.cuh implements (the kernels themselves need a GPU: tests/test_gpu_pbicg.py).
 
 numpy restatement of exactly what the device does —
   * A^T without a transposed mesh structure: slot coefficient of A is min(F, 0), of A^T min(-F, 0), F = signed outflow

@@ -10,7 +10,7 @@ tests/reference_cases.py are committed as tests/golden/reference_*.npz by tools/
 * `test_live_*`: the oracle against the library itself on more inputs, and the fixtures against a fresh run — only
   where the library is built or /root/reference is present (skipped on the GPU box's CPU run otherwise).
 * the CUDA path, through the C-ABI, against the same fixtures (the reference's numbers, not the oracle's) is in
-  tests/test_zz_gpu_not_yet_run.py.
+  tests/test_gpu_reference_golden.py.
 Tolerances: 1e-12 relative L2 oracle-vs-reference (measured: <= 4e-15), BASELINE's 1e-10 for the GPU after one step.
 """
 from pathlib import Path
