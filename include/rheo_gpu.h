@@ -175,6 +175,9 @@ int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int3
 /* one line of text naming the cell ordering the DILU substitutions run in on this handle, e.g.
  * "8x8x4 blocks (256 cells), natural order inside, 2 block colours" or "cell colouring, 2 colours" */
 int rheo_gpu_get_ordering(RheoGpu* h, char* buf, int32_t buflen);
+/* block ordering only: levels of every cell (new numbering) in the dependency graph of its 256-cell chunk — longest chain of
+ * lower- (fwd) / higher-numbered (bwd) neighbours inside the chunk; the level-scheduled substitutions run in this order */
+int rheo_gpu_get_levels(RheoGpu* h, int32_t* fwd, int32_t* bwd);
 /* ELL width K and the neighbour table nbr[K*n_cells] (slot-major, in NEW numbering: >=0 cell,
  * >= n_cells ghost, -1 empty, <=-2 boundary face -(b+2)) and face table (face index, ~face when
  * the cell is the face's neighbour) */

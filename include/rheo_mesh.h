@@ -143,6 +143,14 @@ int rheo_mesh_proc_addressing(const RheoHostMesh* sub, int32_t* cell_addr, int32
 int rheo_mesh_colour_renumber(const RheoHostMesh* m, int32_t* perm, int32_t* colour,
                               int32_t* colour_start);
 
+/* Block ordering of lattice (tensor-product, blockMesh-like) meshes — what the device uses for PBiCGStab's DILU on such
+ * meshes (csrc/host/ordering.hpp): cells sorted block by block (8x8x4 lattice cells in 3-D, 16x16 in 2-D; natural order, i
+ * fastest, inside a block), the sequence cut into chunks of 256 cells, the chunk graph coloured greedily in chunk order, new
+ * numbering = colour by colour, chunk by chunk.  perm[new] = old cell; colour_start[n_colours+1] (caller: >= 65 entries);
+ * tile3 (may be NULL) receives the block shape.  Returns the number of chunk colours, 0 if the mesh is not a lattice mesh
+ * (the device then falls back to rheo_mesh_colour_renumber's ordering), < 0 on error. */
+int rheo_mesh_block_renumber(const RheoHostMesh* m, int32_t* perm, int32_t* colour_start, int32_t* tile3);
+
 /* ---- synthetic benchmark fields ------------------------------------------------ */
 #define RHEO_FLOW_CONTRACTION_2D 0  /* psi = Q g(y/h(x)), h: H_up -> H_down, no-slip/no-penetration walls */
 #define RHEO_FLOW_VORTEX         1  /* Psi_z = A sin(pi x^) sin(pi y^) (1 + 0.3 sin(pi z^)) on the bounding box */

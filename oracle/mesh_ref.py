@@ -1,5 +1,6 @@
 """numpy restatement of the INTEGER contracts of the GPU library.  TEST INFRASTRUCTURE ONLY.
 
+  * block_renumber    block ordering of lattice meshes (csrc/host/ordering.hpp): what the device uses for PBiCGStab
   * colour_renumber   greedy multi-colouring in cell order + colour-major stable sort (what
                       rheo_gpu_create applies on the device; DESIGN.md "Renumbering")
   * renumbered_mesh   the mesh after that permutation in OpenFOAM upper-triangular order — what
@@ -98,6 +99,96 @@ def colour_renumber(n_cells: int, owner: np.ndarray, neighbour: np.ndarray):
     cstart = np.zeros(ncol + 1, dtype=np.int32)
     cstart[1:] = np.cumsum(np.bincount(colour, minlength=ncol))
     return perm, colour, cstart
+
+
+CHUNK = 256
+
+
+def block_renumber(rm: "RefMesh"):
+    """Independent numpy restatement of csrc/host/ordering.hpp::block_renumber (the integer contract of the device's block
+    ordering).  Returns (perm[new]=old, colour_start, tile) or None when the mesh is not a lattice mesh."""
+    N, nint = rm.n_cells, rm.n_internal
+    ijk, dims = [], []
+    tol = 1e-10 * max(float((rm.C.max(axis=0) - rm.C.min(axis=0)).max()), 1e-300)
+    for d in range(3):
+        x = rm.C[:, d]
+        u = np.unique(x)                      # sorted; merge planes closer than tol
+        keep = np.concatenate([[True], np.diff(u) > tol])
+        planes = u[keep]
+        if len(planes) > 8192:
+            return None
+        idx = np.searchsorted(planes, x - tol)
+        idx = np.clip(idx, 0, len(planes) - 1)
+        if not np.all(np.abs(planes[idx] - x) <= tol):
+            return None
+        ijk.append(idx.astype(np.int64)); dims.append(len(planes))
+    own, nei = rm.owner[:nint].astype(np.int64), rm.neighbour.astype(np.int64)
+    dist = sum(np.abs(a[own] - a[nei]) for a in ijk)
+    if nint and not np.all(dist == 1):
+        return None
+    thick = [d > 1 for d in dims]
+    t = [1, 1, 1]
+    if sum(thick) == 3:
+        t = [8, 8, 4]
+    elif sum(thick) == 2:
+        t = [16 if th else 1 for th in thick]
+    elif sum(thick) == 1:
+        t = [256 if th else 1 for th in thick]
+    nT = [(dims[d] + t[d] - 1) // t[d] for d in range(3)]
+    i, j, k = ijk
+    tid = ((k // t[2]) * nT[1] + (j // t[1])) * nT[0] + (i // t[0])
+    local = ((k % t[2]) * t[1] + (j % t[1])) * t[0] + (i % t[0])
+    seq = np.lexsort((np.arange(N), local, tid))
+    n_chunks = (N + CHUNK - 1) // CHUNK
+    chunk_of = np.empty(N, dtype=np.int64)
+    chunk_of[seq] = np.arange(N) // CHUNK
+    a, b = chunk_of[own], chunk_of[nei]
+    cut = a != b
+    hi, lo = np.maximum(a, b)[cut], np.minimum(a, b)[cut]
+    order = np.argsort(hi, kind="stable")
+    hi, lo = hi[order], lo[order]
+    starts = np.searchsorted(hi, np.arange(n_chunks + 1))
+    colour = np.zeros(n_chunks, dtype=np.int64)
+    for q in range(n_chunks):
+        used = set(colour[lo[starts[q]:starts[q + 1]]].tolist())
+        c = 0
+        while c in used:
+            c += 1
+        if c >= 63:
+            return None
+        colour[q] = c
+    ncol = int(colour.max()) + 1
+    if N % CHUNK != 0:
+        cp, cl = int(colour[-1]), ncol - 1
+        if cp != cl:
+            was_cp, was_cl = colour == cp, colour == cl
+            colour[was_cp], colour[was_cl] = cl, cp
+    sizes = np.minimum(CHUNK, N - np.arange(n_chunks) * CHUNK)
+    cstart = np.zeros(ncol + 1, dtype=np.int32)
+    cstart[1:] = np.cumsum(np.bincount(colour, weights=sizes, minlength=ncol)).astype(np.int64)
+    chunk_order = np.argsort(colour, kind="stable")
+    perm = np.concatenate([seq[q * CHUNK:q * CHUNK + sizes[q]] for q in chunk_order]).astype(np.int32)
+    return perm, cstart, tuple(t)
+
+
+def chunk_levels(nbr: np.ndarray, n_cells: int):
+    """(fwd, bwd) levels of the in-chunk dependency graphs for the slot-major neighbour table nbr[K, N] in the NEW numbering
+    (csrc/host/ordering.hpp::chunk_levels): longest chain of lower- / higher-numbered neighbours inside the cell's chunk."""
+    K, N = nbr.shape
+    fwd = np.zeros(N, dtype=np.int64); bwd = np.zeros(N, dtype=np.int64)
+    for c in range(N):
+        base = c - c % CHUNK
+        for s in range(K):
+            nb = nbr[s, c]
+            if base <= nb < c:
+                fwd[c] = max(fwd[c], fwd[nb] + 1)
+    for c in range(N - 1, -1, -1):
+        end = min(n_cells, c - c % CHUNK + CHUNK)
+        for s in range(K):
+            nb = nbr[s, c]
+            if c < nb < end:
+                bwd[c] = max(bwd[c], bwd[nb] + 1)
+    return fwd, bwd
 
 
 def face_order(n_cells, owner, neighbour, perm):

@@ -98,6 +98,7 @@ MESH_SYMBOLS = {
     "rheo_mesh_decompose": (_P, [_P, _P, _I, _I]),
     "rheo_mesh_proc_addressing": (C.c_int, [_P, _P, _P]),
     "rheo_mesh_colour_renumber": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_mesh_block_renumber": (C.c_int, [_P, _P, _P, _P]),
     "rheo_synth_fields": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "rheo_mesh_max_courant_rate": (_D, [_P, _P]),
     "rheo_mesh_last_error": (C.c_char_p, []),
@@ -118,6 +119,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_get_renumbering": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ell": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ordering": (C.c_int, [_P, _P, _I]),
+    "rheo_gpu_get_levels": (C.c_int, [_P, _P, _P]),
     "rheo_gpu_launch_count": (C.c_int64, [_P]),
     "rheo_gpu_last_iterations": (C.c_int, [_P]),
     "rheo_gpu_transfer_bytes": (C.c_int, [_P, _P, _P]),

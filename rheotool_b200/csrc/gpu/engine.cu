@@ -22,6 +22,8 @@
 #include <vector>
 
 #include "krylov.cuh"
+#include "blocksweep.cuh"
+#include "ordering.hpp"
 #include "pbicg.cuh"
 #include "assembly.cuh"
 #include "peer.cuh"
@@ -111,6 +113,8 @@ struct RheoGpu {
     int nColours = 0;
     std::vector<int> colourStart;
     std::string orderingInfo;      // rheo_gpu_get_ordering
+    bool blockMode = false;        // block ordering (host/ordering.hpp): colourStart holds the chunk colours' cell ranges
+    DevBuf d_lev, d_chunkLev;
     long nGlobalCells = 0;
     // host-side maps
     std::vector<int> perm;         // perm[new] = old
@@ -259,18 +263,36 @@ template <class T> int upload(DevBuf& b, const std::vector<T>& v) {
     return 0;
 }
 
-int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
+int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
     const int N = d->n_cells, nF = d->n_faces, nInt = d->n_internal_faces, nB = nF - nInt;
+    h->segs.clear(); h->ubRanges.clear(); h->phiBRanges.clear(); h->blockMode = false;
     h->N = N; h->nF = nF; h->nInt = nInt; h->nB = nB;
     h->patches.assign(d->patches, d->patches + d->n_patches);
     h->nComp = 0;
     for (int q = 0; q < 6; ++q) if (d->solved_components[q]) h->comps[h->nComp++] = q;
     if (h->nComp != 6 && h->nComp != 4) return fail("rheo_gpu_create: solved_components must select 6 (3-D) or 4 (2-D) components");
 
-    // ---- renumbering
-    h->nColours = colour_renumber(N, nInt, d->owner, d->neighbour, h->perm, h->colourStart);
-    if (h->nColours < 1) return fail("rheo_gpu_create: colouring failed (more than 63 colours)");
-    h->orderingInfo = "cell colouring, " + std::to_string(h->nColours) + " colours";
+    // ---- renumbering: block ordering (natural order inside 256-cell blocks, blocks coloured: the reference's Krylov iteration
+    // counts) for lattice meshes solved with PBiCGStab; greedy cell colouring otherwise (unstructured meshes; the device PBiCG,
+    // pbicg.cuh, sweeps cell colours; RHEO_ORDERING=colour forces it)
+    {
+        const char* env = getenv("RHEO_ORDERING");
+        const bool wantBlocks = allowBlocks && h->ctl.solver == RHEO_SOLVER_PBICGSTAB && !(env && std::string(env) == "colour");
+        rk_host::BlockOrdering bo;
+        if (wantBlocks && rk_host::block_renumber(N, nInt, d->owner, d->neighbour, d->C, bo)) {
+            h->blockMode = true;
+            h->perm = std::move(bo.perm);
+            h->colourStart = std::move(bo.colourStart);
+            h->nColours = bo.nColours;
+            h->orderingInfo = std::to_string(bo.tile[0]) + "x" + std::to_string(bo.tile[1]) + "x" + std::to_string(bo.tile[2]) + " blocks of a " +
+                              std::to_string(bo.dims[0]) + "x" + std::to_string(bo.dims[1]) + "x" + std::to_string(bo.dims[2]) +
+                              " lattice, natural order inside chunks of 256 cells, " + std::to_string(bo.nColours) + " chunk colours";
+        } else {
+            h->nColours = colour_renumber(N, nInt, d->owner, d->neighbour, h->perm, h->colourStart);
+            if (h->nColours < 1) return fail("rheo_gpu_create: colouring failed (more than 63 colours)");
+            h->orderingInfo = "cell colouring, " + std::to_string(h->nColours) + " colours";
+        }
+    }
     std::vector<int> iperm(N);
     for (int c = 0; c < N; ++c) iperm[h->perm[c]] = c;
 
@@ -371,6 +393,11 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
             nbrA[ell_t(K, s, c)] = (v >= 0) ? v : std::min(c, N - 1);   // tile-major (kernels.cuh: ell_t)
         }
 
+    if (h->blockMode) {   // levels of the in-chunk dependency graphs (blocksweep.cuh)
+        std::vector<uint16_t> lev, chunkLev;
+        if (!rk_host::chunk_levels(N, h->NS, K, h->h_nbr, lev, chunkLev)) return build_mesh(h, d, false);   // a chain longer than 255: cell colouring
+        if (upload(h->d_lev, lev) || upload(h->d_chunkLev, chunkLev)) return 1;
+    }
     {   // cells owning ghost slots (k_ghost)
         std::vector<int> bc;
         for (int c = 0; c < N; ++c) {
@@ -472,6 +499,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d) {
     m.Sf = h->d_Sf.as<double>(); m.w = h->d_w.as<double>(); m.C = h->d_C.as<double>(); m.V = h->d_V.as<double>(); m.rV = h->d_rV.as<double>();
     m.bcell = h->d_bcell.as<int>(); m.bkind = h->d_bkind.as<int>(); m.bthetaBC = h->d_bthetaBC.as<int>(); m.btauBC = h->d_btauBC.as<int>();
     m.CfB = h->d_CfB.as<double>();
+    m.lev = h->d_lev.as<uint16_t>(); m.chunkLev = h->d_chunkLev.as<uint16_t>();
     h->nGlobalCells = N;
     return 0;
 }
@@ -715,6 +743,16 @@ int setup_peer(RheoGpu* h) {
     pv.blockCounter = h->d_peerMisc.as<unsigned>(); pv.err = (int*)((char*)h->d_peerMisc.p + 128); pv.stat = (unsigned long long*)((char*)h->d_peerMisc.p + 192);
     CK(cudaStreamSynchronize(h->stream));
     h->p2p = true;
+    return 0;
+}
+
+// A bounded peer-memory wait that expired leaves pv.err set (peer.cuh): halo data or reduced sums may then have been read
+// without synchronisation.  Called after the stream has been synchronised, by every entry point that hands results to the host.
+int check_peer_err(RheoGpu* h) {
+    if (!h->p2p) return 0;
+    int e = 0;
+    CK(cudaMemcpy(&e, h->pv.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e) return fail("peer-memory wait expired: a neighbour rank did not reach a halo swap / reduction within 20 s (peer.cuh); results of this handle are invalid");
     return 0;
 }
 
@@ -1067,7 +1105,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_FsT, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
-                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells})
+                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev})
         b->release();
     for (ModeDev& md : h->modes)
         for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0}) b->release();
@@ -1207,7 +1245,7 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
     if (bytes) CK(cudaMemcpyAsync(dst, stage, bytes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->d2hBytes += (long long)bytes * sizeof(double);
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_peer_err(h);
 }
 
 int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const double* phi, double dt, int32_t new_time_step, double* tau_out,
@@ -1231,6 +1269,16 @@ int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int3
 int rheo_gpu_get_ordering(RheoGpu* h, char* buf, int32_t buflen) {
     if (!h || !buf || buflen < 1) return fail("rheo_gpu_get_ordering: bad argument");
     snprintf(buf, (size_t)buflen, "%s", h->orderingInfo.c_str());
+    return 0;
+}
+
+int rheo_gpu_get_levels(RheoGpu* h, int32_t* fwd, int32_t* bwd) {
+    if (!h || !fwd || !bwd) return fail("rheo_gpu_get_levels: bad argument");
+    if (!h->blockMode) return fail("rheo_gpu_get_levels: this handle uses the cell colouring (no in-chunk levels)");
+    CK(cudaSetDevice(h->device));
+    std::vector<uint16_t> lev(h->NS);
+    CK(cudaMemcpy(lev.data(), h->d_lev.p, (size_t)h->NS * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+    for (int c = 0; c < h->N; ++c) { fwd[c] = lev[c] & 255; bwd[c] = lev[c] >> 8; }
     return 0;
 }
 
@@ -1291,7 +1339,7 @@ int rheo_gpu_synchronize(RheoGpu* h) {
     if (!h) return fail("null handle");
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->stream));
-    return 0;
+    return check_peer_err(h);
 }
 
 int rheo_gpu_eig_exp(int32_t device, int32_t n, const double* theta6, double* eigvals9, double* eigvecs9) {

@@ -44,6 +44,9 @@ struct MeshView {
     const int* bthetaBC;  // [nB]
     const int* btauBC;    // [nB]
     const double* CfB;    // [3*nB] planes
+    // block ordering only (host/ordering.hpp, blocksweep.cuh): levels of the in-chunk dependency graphs
+    const uint16_t* lev;       // [NS] forward level | backward level << 8
+    const uint16_t* chunkLev;  // [NS / 256] max forward level | max backward level << 8 of the chunk
 };
 
 struct RhsPtrs {      // one batch of right-hand sides sharing the matrix

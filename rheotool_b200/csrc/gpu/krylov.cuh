@@ -520,44 +520,67 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_spmv(MeshView m, RowSrc rs,
     finalize_ctl(partials, totalBlocks, ND * nModes * NR, out, counter, (unsigned)totalBlocks, ctlWhat, ks, nModes * NR, sc);
 }
 
-// ghost (processor-patch) columns, after the halo exchange of y: one thread per cell that owns ghost slots
-//   v[c] += sum_{ghost slots} A y[ghost]; the dots are corrected for the change of v
+// ghost (processor-patch) columns, after the halo exchange of y (NCCL fallback path; the peer-memory path does this in
+// k_peer_ghost): grid-stride over the cells that own ghost slots
+//   v[c] += sum_{ghost slots} A y[ghost]; the dots are corrected for the change of v — per-CTA partial sums, added to the
+//   dots by the last CTA in block order (deterministic: no atomics on doubles)
 template <int NR, int MODE>
 __global__ void __launch_bounds__(BLOCK) k_ghost(MeshView m, int nBcells, const int* __restrict__ bcells, int nModes, const KrylovShared* __restrict__ ks,
                                                   const double* __restrict__ A, const double* __restrict__ y, double* __restrict__ v,
-                                                  const double* __restrict__ other, double* dots) {
+                                                  const double* __restrict__ other, double* dots, double* partials, unsigned* counter) {
     pdl_sync();
     if (ks->nActive == 0) return;
     constexpr int ND = MODE == 0 ? 1 : 2;
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i0 >= nBcells) return;
-    const int c = bcells[i0];
+    const int nrhs = nModes * NR;
     for (int md = 0; md < nModes; ++md) {
-        double acc[NR];
+        double red[ND * NR];
 #pragma unroll
-        for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-        for (int s = 0; s < m.K; ++s) {
-            const int nb = m.nbrA[ell_t(m.K, s, c)];
-            if (nb < m.N) continue;
-            const double a = A[ell_t(m.K, s, c)];
-            double yn[NR];
-            ldv<NR>(y, (size_t)md * m.NP + nb, yn);
+        for (int j = 0; j < ND * NR; ++j) red[j] = 0.0;
+        for (int i0 = blockIdx.x * BLOCK + threadIdx.x; i0 < nBcells; i0 += gridDim.x * BLOCK) {
+            const int c = bcells[i0];
+            double acc[NR];
 #pragma unroll
-            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+            for (int j = 0; j < NR; ++j) acc[j] = 0.0;
+            for (int s = 0; s < m.K; ++s) {
+                const int nb = m.nbrA[ell_t(m.K, s, c)];
+                if (nb < m.N) continue;
+                const double a = A[ell_t(m.K, s, c)];
+                double yn[NR];
+                ldv<NR>(y, (size_t)md * m.NP + nb, yn);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+            }
+            const size_t i = (size_t)md * m.NP + c;
+            double vv[NR], oo[NR];
+            ldv<NR>(v, i, vv); ldv<NR>(other, i, oo);
+#pragma unroll
+            for (int j = 0; j < NR; ++j) {
+                if (ks->ctl[md * NR + j].state != 0) continue;
+                const double vn = vv[j] + acc[j];
+                if (MODE == 0) red[j] += oo[j] * acc[j];
+                else { red[2 * j] += vn * vn - vv[j] * vv[j]; red[2 * j + 1] += acc[j] * oo[j]; }
+                vv[j] = vn;
+            }
+            stv<NR>(v, i, vv);
         }
-        const size_t i = (size_t)md * m.NP + c;
-        double vv[NR], oo[NR];
-        ldv<NR>(v, i, vv); ldv<NR>(other, i, oo);
-#pragma unroll
-        for (int j = 0; j < NR; ++j) {
-            if (ks->ctl[md * NR + j].state != 0) continue;
-            const double vn = vv[j] + acc[j];
-            if (MODE == 0) atomicAdd(&dots[md * NR + j], oo[j] * acc[j]);
-            else { atomicAdd(&dots[ND * (md * NR + j)], vn * vn - vv[j] * vv[j]); atomicAdd(&dots[ND * (md * NR + j) + 1], acc[j] * oo[j]); }
-            vv[j] = vn;
-        }
-        stv<NR>(v, i, vv);
+        block_reduce_to_partials<ND * NR>(red, partials, ND * md * NR, ND * nrhs);
     }
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) isLast = atomicAdd(counter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int q = warp; q < ND * nrhs; q += BLOCK / 32) {
+        double t = 0;
+        for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&partials[(size_t)b * ND * nrhs + q]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        if (lane == 0) dots[q] += t;
+    }
+    if (threadIdx.x == 0) *counter = 0;
 }
 
 // ---------------------------------------------------------------- s = r - alpha v ; z = rD s ; sum|s|   on cells [c0, c1)

@@ -15,7 +15,9 @@
 //
 // Buffers are double-buffered on the parity of the sequence number; since every swap / reduction is symmetric (a rank
 // receives from everyone it sends to) a sender can be at most one operation ahead of a receiver, so two parities suffice.
-// Waits are bounded (PEER_SPIN_MAX polls): on expiry the kernel raises an error flag instead of hanging the GPU.
+// Waits are bounded in TIME (PEER_WAIT_NS of %globaltimer, not a poll count: a neighbour that is merely slow on the host side
+// must not trip it): on expiry the kernel raises an error flag instead of hanging the GPU; the host reads the flag at the end
+// of every solve, of every step and before every download (engine.cu: check_peer_err) and fails the call.
 #pragma once
 #include "krylov.cuh"
 
@@ -23,7 +25,7 @@ namespace rk {
 
 constexpr int MAX_RANKS = 16;
 constexpr int AR_MAX = MAX_RED;                      // doubles per all-reduce contribution
-constexpr unsigned long long PEER_SPIN_MAX = 10ull * 1000 * 1000;   // polls (~1 us each) before a wait gives up
+constexpr unsigned long long PEER_WAIT_NS = 20ull * 1000 * 1000 * 1000;   // a wait gives up after 20 s of %globaltimer time
 
 struct PeerSeg { int nbrRank, h0, len, nbrH0; };     // my ghosts [h0, h0+len) face rank nbrRank, whose matching ghosts start at nbrH0
 
@@ -64,11 +66,11 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 // kind 0: halo, 1: all-reduce (statistics only)
 __device__ __forceinline__ void peer_wait(const unsigned long long* flag, unsigned long long seq, const PeerView& pv, int kind) {
-    unsigned long long n = 0;
-    if (*(volatile int*)pv.err) return;   // a wait has already expired on this rank: do not wait again
+    unsigned n = 0;
+    if (*(volatile int*)pv.err) return;   // a wait has already expired on this rank: do not wait again (the host fails the call)
     const unsigned long long t0 = global_ns();
     while (ld_acquire_sys(flag) < seq) {
-        if (++n > PEER_SPIN_MAX) { atomicExch(pv.err, 1); break; }
+        if ((++n & 1023u) == 0 && global_ns() - t0 > PEER_WAIT_NS) { atomicExch(pv.err, 1); break; }
     }
     if (threadIdx.x == 0 && blockIdx.x == 0) { pv.stat[kind] += global_ns() - t0; pv.stat[2 + kind] += 1; }
 }
@@ -126,56 +128,74 @@ __global__ void __launch_bounds__(128) k_peer_allreduce_ctl(PeerView pv, double*
 }
 
 
-// ---------------------------------------------------------------- fused: halo swap of x + ghost columns of v = A x + all-reduce of the dots + control
-// What the processor patches add to one preconditioned product, in ONE single-CTA kernel (the launch-bound part of the
-// multi-GPU iteration at ~1 M cells per GPU):
-//   1. store the records x[boundary cell] of my processor faces into the neighbours' mailboxes, publish, wait for theirs;
-//   2. for the cells that own ghost slots:  v[c] += sum_{ghost slots} A x[ghost]  with x[ghost] read straight from my
-//      mailbox, and the change of the fused dots (MODE 0: r0.v;  MODE 1: t.t, t.s);
-//   3. all-reduce [dots | (MODE 1) sum|s| of the half step] over the ranks in rank order;
-//   4. scalar control: (MODE 1: half-step convergence, then) alpha / omega.
+// ---------------------------------------------------------------- what the processor patches add to one preconditioned product
+// Two multi-CTA kernels (round 1 had ONE single-CTA kernel here: 87 us per launch on a 5 k-face halo, 27 % of the 8-GPU step):
+//
+//   k_peer_put    launched as soon as x = M^-1 p is final (before the SpMV of the remaining cells): every CTA packs the
+//                 records x[boundary cell] of its share of my processor faces and stores them straight into the neighbours'
+//                 mailboxes (NVLink stores are posted: nothing waits here); the last CTA to finish publishes one sequence
+//                 number per neighbour (st.release.sys).  The records travel while the interior SpMV runs.
+//   k_peer_ghost  after the interior SpMV: every CTA waits for the neighbours' sequence numbers (normally already there),
+//                 adds the ghost columns  v[c] += sum_{ghost slots} A x[ghost]  for its share of the cells that own processor
+//                 faces (x[ghost] read straight from my mailbox) and the change of the fused dots (MODE 0: r0.v;  MODE 1:
+//                 t.t, t.s) as per-CTA partial sums; the LAST CTA adds the partials in block order (deterministic), then does
+//                 the all-reduce of [dots | (MODE 1) sum|s| of the half step] over the ranks in rank order and the scalar
+//                 control step (MODE 1: half-step convergence, then omega; MODE 0: alpha).
 // MODE 1 carries the half-step sums along instead of reducing them in a round of their own: a RHS that turns out to have
 // converged at the half step has had z, t computed for nothing, which update_x_r ignores (state 1) — same results.
-constexpr int PEER_CTA = 1024;
-template <int NR, int MODE>
-__global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, unsigned long long seqHalo, unsigned long long seqAr, MeshView m, int nBcells,
-                                                                 const int* __restrict__ bcells, const int* __restrict__ haloCell, int nModes, KrylovShared* ks,
-                                                                 const double* __restrict__ A, const double* __restrict__ x, double* __restrict__ v,
-                                                                 const double* __restrict__ other, double* dots, const double* half, SolveCtl sc) {
+// No early exit when every RHS has converged (speculative iterations): the sequence numbers must advance by one per executed
+// operation on every rank, or the two-parity mailboxes would lose their ordering guarantee.
+template <int NR>
+__global__ void __launch_bounds__(BLOCK) k_peer_put(PeerView pv, unsigned long long seq, int NP, const int* __restrict__ haloCell, int nModes,
+                                                     const double* __restrict__ x) {
     pdl_sync();
-    // no early exit when every RHS has converged (speculative iterations): the sequence numbers must advance by one per
-    // executed operation on every rank, or the two-parity mailboxes would lose their ordering guarantee
-    constexpr int ND = MODE == 0 ? 1 : 2;
-    const int rec = nModes * NR, nrhs = nModes * NR;
-    const int parH = (int)(seqHalo & 1ull), parA = (int)(seqAr & 1ull), R = pv.nRanks;
-    __shared__ double sRed[PEER_CTA / 32][2 * NR];
-    __shared__ double sCorr[MAX_RED];
-    // ---- 1. halo swap
-    for (int hh = threadIdx.x; hh < pv.H; hh += PEER_CTA) {
+    __shared__ bool isLast;
+    const int par = (int)(seq & 1ull), rec = nModes * NR;
+    for (int hh = blockIdx.x * BLOCK + threadIdx.x; hh < pv.H; hh += gridDim.x * BLOCK) {
         const PeerSeg sg = pv.segs[pv.segOfGhost[hh]];
-        double* dst = pv.pHaloData[sg.nbrRank] + (long)parH * pv.pHaloCap[sg.nbrRank] + (long)(sg.nbrH0 + (hh - sg.h0)) * rec;
+        double* dst = pv.pHaloData[sg.nbrRank] + (long)par * pv.pHaloCap[sg.nbrRank] + (long)(sg.nbrH0 + (hh - sg.h0)) * rec;
         const int c = haloCell[hh];
         for (int md = 0; md < nModes; ++md) {
             double t[NR];
-            ldv<NR>(x, (size_t)md * m.NP + c, t);
-#pragma unroll
-            for (int j = 0; j < NR; ++j) dst[md * NR + j] = t[j];
+            ldv<NR>(x, (size_t)md * NP + c, t);
+            stv<NR>(dst, (size_t)md, t);   // records are 16-byte aligned (rec = NR * nModes doubles, NR even)
         }
     }
     __threadfence_system();
     __syncthreads();
-    if (threadIdx.x < pv.nSegs) {
-        st_release_sys(&pv.pHaloFlag[pv.segs[threadIdx.x].nbrRank][parH * R + pv.rank], seqHalo);
-        peer_wait(&pv.haloFlag[parH * R + pv.segs[threadIdx.x].nbrRank], seqHalo, pv, 0);
-    }
+    if (threadIdx.x == 0) isLast = atomicAdd(pv.blockCounter, 1u) == gridDim.x - 1;
     __syncthreads();
-    // ---- 2. ghost columns
+    if (isLast) {   // every CTA of this rank has stored and fenced: publish
+        __threadfence_system();
+        if (threadIdx.x < pv.nSegs) st_release_sys(&pv.pHaloFlag[pv.segs[threadIdx.x].nbrRank][par * pv.nRanks + pv.rank], seq);
+        if (threadIdx.x == 0) *pv.blockCounter = 0;
+    }
+}
+
+template <int NR, int MODE>
+__global__ void __launch_bounds__(BLOCK) k_peer_ghost(PeerView pv, unsigned long long seqHalo, unsigned long long seqAr, MeshView m, int nBcells,
+                                                       const int* __restrict__ bcells, int nModes, KrylovShared* ks, const double* __restrict__ A,
+                                                       double* __restrict__ v, const double* __restrict__ other, double* dots, const double* half,
+                                                       double* partials, SolveCtl sc) {
+    pdl_sync();
+    constexpr int ND = MODE == 0 ? 1 : 2;
+    const int rec = nModes * NR, nrhs = nModes * NR;
+    const int parH = (int)(seqHalo & 1ull), parA = (int)(seqAr & 1ull), R = pv.nRanks;
+    __shared__ bool isLast;
+    __shared__ double sCorr[MAX_RED];
+    // ---- the neighbours' records of this swap
+    if (threadIdx.x < pv.nSegs) peer_wait(&pv.haloFlag[parH * R + pv.segs[threadIdx.x].nbrRank], seqHalo, pv, 0);
+    __syncthreads();
+    // ---- ghost columns of my share of the boundary cells
     const double* box = pv.haloData + (long)parH * pv.haloCap;
     for (int md = 0; md < nModes; ++md) {
         double red[ND * NR];
+        bool on[NR];
 #pragma unroll
         for (int j = 0; j < ND * NR; ++j) red[j] = 0.0;
-        for (int i0 = threadIdx.x; i0 < nBcells; i0 += PEER_CTA) {
+#pragma unroll
+        for (int j = 0; j < NR; ++j) on[j] = ks->ctl[md * NR + j].state == 0;
+        for (int i0 = blockIdx.x * BLOCK + threadIdx.x; i0 < nBcells; i0 += gridDim.x * BLOCK) {
             const int c = bcells[i0];
             double acc[NR];
 #pragma unroll
@@ -184,16 +204,16 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
                 const int nb = m.nbrA[ell_t(m.K, s, c)];
                 if (nb < m.N) continue;
                 const double a = A[ell_t(m.K, s, c)];
-                const double* yn = box + (long)(nb - m.N) * rec + md * NR;
+                const double2* yn = reinterpret_cast<const double2*>(box + (long)(nb - m.N) * rec + md * NR);
 #pragma unroll
-                for (int j = 0; j < NR; ++j) acc[j] += a * __ldcg(yn + j);
+                for (int j = 0; j < NR / 2; ++j) { const double2 t = __ldcg(yn + j); acc[2 * j] += a * t.x; acc[2 * j + 1] += a * t.y; }
             }
             const size_t i = (size_t)md * m.NP + c;
             double vv[NR], oo[NR];
             ldv<NR>(v, i, vv); ldv<NR>(other, i, oo);
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
-                if (ks->ctl[md * NR + j].state != 0) continue;
+                if (!on[j]) continue;
                 const double vn = vv[j] + acc[j];
                 if (MODE == 0) red[j] += oo[j] * acc[j];
                 else { red[2 * j] += vn * vn - vv[j] * vv[j]; red[2 * j + 1] += acc[j] * oo[j]; }
@@ -201,26 +221,29 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
             }
             stv<NR>(v, i, vv);
         }
-        // block reduction of the dot corrections of this mode
+        block_reduce_to_partials<ND * NR>(red, partials, ND * md * NR, ND * nrhs);
+    }
+    // ---- last CTA: partials in block order, all-reduce over the ranks in rank order, scalar control
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) isLast = atomicAdd(pv.blockCounter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+    const int ndDots = ND * nrhs, nd = ndDots + (MODE == 1 ? nrhs : 0);
+    {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-        for (int j = 0; j < ND * NR; ++j) {
-            double t = red[j];
+        for (int q = warp; q < ndDots; q += BLOCK / 32) {
+            double t = 0;
+            for (unsigned b = lane; b < gridDim.x; b += 32) t += __ldcg(&partials[(size_t)b * ndDots + q]);
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-            if (lane == 0) sRed[warp][j] = t;
+            if (lane == 0) sCorr[q] = t;
         }
-        __syncthreads();
-        if (threadIdx.x < ND * NR) {
-            double t = 0;
-            for (int wv = 0; wv < PEER_CTA / 32; ++wv) t += sRed[wv][threadIdx.x];
-            sCorr[ND * md * NR + threadIdx.x] = t;
-        }
-        __syncthreads();
     }
-    // ---- 3. all-reduce of [dots | half]
-    const int ndDots = ND * nrhs, nd = ndDots + (MODE == 1 ? nrhs : 0);
-    for (int q = threadIdx.x; q < nd; q += PEER_CTA) {
+    __syncthreads();
+    if (threadIdx.x == 0) *pv.blockCounter = 0;
+    for (int q = threadIdx.x; q < nd; q += BLOCK) {
         const double val = q < ndDots ? dots[q] + sCorr[q] : half[q - ndDots];
         for (int r = 0; r < R; ++r) pv.pArData[r][((long)parA * R + pv.rank) * AR_MAX + q] = val;
     }
@@ -231,13 +254,12 @@ __global__ void __launch_bounds__(PEER_CTA) k_peer_ghost_reduce(PeerView pv, uns
         peer_wait(&pv.arFlag[parA * R + threadIdx.x], seqAr, pv, 1);
     }
     __syncthreads();
-    for (int q = threadIdx.x; q < nd; q += PEER_CTA) {
+    for (int q = threadIdx.x; q < nd; q += BLOCK) {
         double t = 0.0;
         for (int r = 0; r < R; ++r) t += __ldcg(&pv.arData[((long)parA * R + r) * AR_MAX + q]);
         dots[q] = t;   // MODE 1: [t.t, t.s per RHS | reduced half-step sums]  (dots has room for 3 nrhs values)
     }
     __syncthreads();
-    // ---- 4. control (one lane per RHS)
     if (threadIdx.x == 0 && *pv.err) ks->pad[0] = 1;
     if (threadIdx.x < 32) ctl_dispatch(MODE == 0 ? CTL_ALPHA : CTL_HALF_OMEGA, ks, nrhs, dots, sc);
 }

@@ -53,6 +53,36 @@ template <class Kern> int row_grid(RheoGpu* h, Kern kern, long cells, size_t sme
     return std::max(1, std::min(cdiv(cells, RT) + 1, blocks));   // + 1: a range that starts mid-tile touches one more tile
 }
 
+// peer-memory path: x is final once the colour-0 backward substitution has run, so its boundary records leave for the
+// neighbours BEFORE the SpMV of the remaining cells and travel over NVLink while that kernel runs (k_peer_put, peer.cuh)
+template <int NR>
+unsigned long long peer_put(RheoGpu* h, int nModes, const double* x) {
+    const unsigned long long seq = ++h->haloSeq;
+    const int grid = std::max(1, std::min(cdiv(h->H, BLOCK), 2 * h->nSms));
+    LAUNCH(h, (k_peer_put<NR>), grid, BLOCK, h->pv, seq, h->NP, h->d_haloCell.as<int>(), nModes, x);
+    return seq;
+}
+// what the processor patches add after the local SpMV: ghost columns, all-reduce of the fused dots, scalar control
+template <int NR, int MODE>
+int ghost_and_reduce(RheoGpu* h, int nModes, unsigned long long seqHalo, double* x, double* w, const double* other, double* redDots, double* redHalf,
+                     const SolveCtl& sc) {
+    if (h->nRanks <= 1) return 0;
+    KrylovShared* ks = h->d_ks.as<KrylovShared>();
+    double* part = h->d_partials.as<double>();
+    if (h->p2p) {
+        const unsigned long long sa = ++h->arSeq;
+        const int grid = std::max(1, std::min(cdiv(h->nBcells, BLOCK), GRID(h, (k_peer_ghost<NR, MODE>), std::max(h->nBcells, 1))));
+        LAUNCH(h, (k_peer_ghost<NR, MODE>), grid, BLOCK, h->pv, seqHalo, sa, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks,
+               h->d_Fs.as<double>(), w, other, redDots, redHalf, part, sc);
+        return 0;
+    }
+    const int nd = (MODE == 0 ? 1 : 2) * nModes * NR;
+    if (halo_interleaved<NR>(h, nModes, x)) return 1;
+    if (h->nBcells) LAUNCH(h, (k_ghost<NR, MODE>), std::min(cdiv(h->nBcells, BLOCK), 4 * h->nSms), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks,
+                           h->d_Fs.as<double>(), x, w, other, redDots, part, h->d_counter.as<unsigned>());
+    return all_reduce_ctl(h, redDots, nd, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, nModes * NR, sc);
+}
+
 // One preconditioned product of the PBiCGStab iteration:
 //   WHICH 0 :  p = r + beta (p - omega v);  y = M^-1 p;  v = A y;  dots r0.v -> alpha            (x = y, w = v)
 //   WHICH 1 :  s = r - alpha v (sum|s| -> half-step convergence);  z = M^-1 s;  t = A z;  dots t.t, t.s -> omega   (x = z, w = t)
@@ -100,7 +130,7 @@ int precond_spmv(RheoGpu* h, int nModes, const SolveCtl& sc) {
         LAUNCH_SM(h, (k_sweep<NR, KT, 1, UPD>), grids[k], RT, smem, h->mv, rs, c0, c1, nModes, ks, x, u);
         base += grids[k];
     }
-    // (peer-memory path: the half-step sums are reduced together with the dots of this product, see k_peer_ghost_reduce)
+    // (peer-memory path: the half-step sums are reduced together with the dots of this product, see k_peer_ghost)
     if (WHICH == 1 && multi && !h->p2p && all_reduce_ctl(h, redHalf, nModes * NR, CTL_HALF, nModes * NR, sc)) return 1;
     // ---- backward substitution of the middle colours
     for (int k = nc - 2; k >= 1; --k) {
@@ -114,23 +144,91 @@ int precond_spmv(RheoGpu* h, int nModes, const SolveCtl& sc) {
     const int what = multi ? CTL_NONE : (MODE == 0 ? CTL_ALPHA : CTL_OMEGA);
     const int g0 = (nc >= 2) ? row_grid(h, (k_spmv<NR, KT, MODE, 1>), n0, smem) : row_grid(h, (k_spmv<NR, KT, MODE, 0>), n0, smem);
     const int g1 = (N > n0) ? row_grid(h, (k_spmv<NR, KT, MODE, 0>), N - n0, smem) : 0;
+    const bool peer = multi && h->p2p;
+    unsigned long long seqHalo = 0;
     if (nc >= 2) {
         LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 1>), g0, RT, smem, h->mv, rs, 0, n0, nModes, ks, x, w, other, part, redDots, counter, 0, g0 + g1, what, sc);
+        if (peer) seqHalo = peer_put<NR>(h, nModes, x);
         if (g1) LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g1, RT, smem, h->mv, rs, n0, N, nModes, ks, x, w, other, part, redDots, counter, g0, g0 + g1, what, sc);
     } else {
+        if (peer) seqHalo = peer_put<NR>(h, nModes, x);
         LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g0, RT, smem, h->mv, rs, 0, N, nModes, ks, x, w, other, part, redDots, counter, 0, g0, what, sc);
     }
-    if (multi && h->p2p) {
-        const unsigned long long sh = ++h->haloSeq, sa = ++h->arSeq;
-        LAUNCH(h, (k_peer_ghost_reduce<NR, MODE>), 1, PEER_CTA, h->pv, sh, sa, h->mv, h->nBcells, h->d_bcells.as<int>(), h->d_haloCell.as<int>(), nModes, ks,
-               h->d_Fs.as<double>(), x, w, other, redDots, redHalf, sc);
-    } else if (multi) {
-        const int nd = (MODE == 0 ? 1 : 2) * nModes * NR;
-        if (halo_interleaved<NR>(h, nModes, x)) return 1;
-        if (h->nBcells) LAUNCH(h, (k_ghost<NR, MODE>), cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, h->d_Fs.as<double>(), x, w, other, redDots);
-        if (all_reduce_ctl(h, redDots, nd, MODE == 0 ? CTL_ALPHA : CTL_OMEGA, nModes * NR, sc)) return 1;
+    return ghost_and_reduce<NR, MODE>(h, nModes, seqHalo, x, w, other, redDots, redHalf, sc);
+}
+
+// The same preconditioned product in the BLOCK ordering (host/ordering.hpp, blocksweep.cuh): chunks of 256 cells in natural
+// order, coloured; colour k's chunks are independent of each other.
+template <int NR, int KT, int WHICH>
+int precond_spmv_blocks(RheoGpu* h, int nModes, const SolveCtl& sc) {
+    KrylovShared* ks = h->d_ks.as<KrylovShared>();
+    const double* rD = h->d_rD.as<double>();
+    const RowSrc rs{h->d_nbrA.as<int>(), h->d_Fs.as<double>(), rD, h->d_diag.as<double>()};
+    double* part = h->d_partials.as<double>();
+    double* red = h->d_red.as<double>();
+    unsigned* counter = h->d_counter.as<unsigned>();
+    double *r = h->d_r.as<double>(), *r0 = h->d_r0.as<double>(), *p = h->d_p.as<double>(), *y = h->d_y.as<double>(), *v = h->d_v.as<double>(),
+           *sv = h->d_s.as<double>(), *z = h->d_z.as<double>(), *t = h->d_t.as<double>();
+    double* x = WHICH == 0 ? y : z;
+    double* w = WHICH == 0 ? v : t;
+    const double* other = WHICH == 0 ? r0 : sv;
+    double* redDots = WHICH == 0 ? red : red + 2 * MAX_RED;
+    double* redHalf = red + MAX_RED;
+    const int nc = h->nColours, N = h->N;
+    const bool multi = h->nRanks > 1;
+    const bool peer = multi && h->p2p;
+    const size_t smem = 2 * row_stage_bytes(h->K);
+    constexpr int UPD = WHICH == 0 ? 1 : 2;
+    constexpr int MODE = WHICH;
+    const std::vector<int>& cs = h->colourStart;
+
+    // ---- (vector update +) forward substitution, colour by colour; the last colour runs its backward substitution too
+    std::vector<int> grids(nc, 0);
+    int totalBlocks = 0;
+    for (int k = 0; k < nc; ++k) {
+        const int cells = cs[k + 1] - cs[k];
+        if (cells <= 0) continue;
+        if (k == nc - 1) grids[k] = k == 0 ? row_grid(h, (k_bsweep<NR, KT, 1, UPD, 1>), cells, smem) : row_grid(h, (k_bsweep<NR, KT, 1, UPD, 0>), cells, smem);
+        else grids[k] = k == 0 ? row_grid(h, (k_bsweep<NR, KT, 0, UPD, 1>), cells, smem) : row_grid(h, (k_bsweep<NR, KT, 0, UPD, 0>), cells, smem);
+        totalBlocks += grids[k];
     }
-    return 0;
+    const int halfWhat = multi ? CTL_NONE : CTL_HALF;
+    int base = 0;
+    for (int k = 0; k < nc; ++k) {
+        if (!grids[k]) continue;
+        SweepUpd u{r, v, p, sv, part, redHalf, counter, base, totalBlocks, halfWhat, sc};
+        if (k == nc - 1) {
+            if (k == 0) LAUNCH_SM(h, (k_bsweep<NR, KT, 1, UPD, 1>), grids[k], RT, smem, h->mv, rs, cs[k], cs[k + 1], nModes, ks, x, u);
+            else LAUNCH_SM(h, (k_bsweep<NR, KT, 1, UPD, 0>), grids[k], RT, smem, h->mv, rs, cs[k], cs[k + 1], nModes, ks, x, u);
+        } else {
+            if (k == 0) LAUNCH_SM(h, (k_bsweep<NR, KT, 0, UPD, 1>), grids[k], RT, smem, h->mv, rs, cs[k], cs[k + 1], nModes, ks, x, u);
+            else LAUNCH_SM(h, (k_bsweep<NR, KT, 0, UPD, 0>), grids[k], RT, smem, h->mv, rs, cs[k], cs[k + 1], nModes, ks, x, u);
+        }
+        base += grids[k];
+    }
+    if (WHICH == 1 && multi && !peer && all_reduce_ctl(h, redHalf, nModes * NR, CTL_HALF, nModes * NR, sc)) return 1;
+    // ---- backward substitution of the middle colours
+    for (int k = nc - 2; k >= 1; --k) {
+        if (cs[k + 1] <= cs[k]) continue;
+        SweepUpd u{};
+        LAUNCH_SM(h, (k_bsweep<NR, KT, 2, 0, 0>), row_grid(h, (k_bsweep<NR, KT, 2, 0, 0>), cs[k + 1] - cs[k], smem), RT, smem, h->mv, rs, cs[k], cs[k + 1], nModes, ks, x, u);
+    }
+    // ---- colour 0: backward substitution + SpMV; the other colours: SpMV
+    const int what = multi ? CTL_NONE : (MODE == 0 ? CTL_ALPHA : CTL_OMEGA);
+    unsigned long long seqHalo = 0;
+    if (nc >= 2) {
+        const int n0 = cs[1];
+        const int g0 = row_grid(h, (k_bspmv0<NR, KT, MODE>), n0, smem);
+        const int g1 = (N > n0) ? row_grid(h, (k_spmv<NR, KT, MODE, 0>), N - n0, smem) : 0;
+        LAUNCH_SM(h, (k_bspmv0<NR, KT, MODE>), g0, RT, smem, h->mv, rs, 0, n0, nModes, ks, x, w, other, part, redDots, counter, 0, g0 + g1, what, sc);
+        if (peer) seqHalo = peer_put<NR>(h, nModes, x);
+        if (g1) LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g1, RT, smem, h->mv, rs, n0, N, nModes, ks, x, w, other, part, redDots, counter, g0, g0 + g1, what, sc);
+    } else {
+        const int g0 = row_grid(h, (k_spmv<NR, KT, MODE, 0>), N, smem);
+        if (peer) seqHalo = peer_put<NR>(h, nModes, x);
+        LAUNCH_SM(h, (k_spmv<NR, KT, MODE, 0>), g0, RT, smem, h->mv, rs, 0, N, nModes, ks, x, w, other, part, redDots, counter, 0, g0, what, sc);
+    }
+    return ghost_and_reduce<NR, MODE>(h, nModes, seqHalo, x, w, other, redDots, redHalf, sc);
 }
 
 template <int NR, int KT>
@@ -160,8 +258,13 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* i
     int spec = std::max(1, h->specIters);
     for (;;) {
         for (int it = 0; it < spec; ++it) {
-            if (precond_spmv<NR, KT, 0>(h, nModes, sc)) return 1;
-            if (precond_spmv<NR, KT, 1>(h, nModes, sc)) return 1;
+            if (h->blockMode) {
+                if (precond_spmv_blocks<NR, KT, 0>(h, nModes, sc)) return 1;
+                if (precond_spmv_blocks<NR, KT, 1>(h, nModes, sc)) return 1;
+            } else {
+                if (precond_spmv<NR, KT, 0>(h, nModes, sc)) return 1;
+                if (precond_spmv<NR, KT, 1>(h, nModes, sc)) return 1;
+            }
             LAUNCH(h, (k_update_x_r<NR>), GRID(h, (k_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, y, z, sv, t, r0, r, part, redD, counter, multi ? CTL_NONE : CTL_END, sc);
             if (multi && all_reduce_ctl(h, redD, 2 * nrhs, CTL_END, nrhs, sc)) return 1;
             ++launched;

@@ -5,6 +5,7 @@
 // then processor patches by neighbour rank, faces in global order, flipped when the local cell is
 // the global neighbour).  Reference use: `decomposePar` + `mpirun -np N rheoFoam -parallel`
 // (of90/tutorials/rheoHeatFoam/channel/PTTLog/Allrun:16-20; .../Cylinder/Oldroyd-BLog/system/decomposeParDict:16-31).
+#include "ordering.hpp"
 #include <algorithm>
 #include <cmath>
 #include <numeric>
@@ -147,6 +148,16 @@ RheoHostMesh* rheo_mesh_decompose(const RheoHostMesh* m, const int32_t* c2r, int
         s->V[c] = m->V[s->cell_addr[c]];
     }
     return s;
+}
+
+int rheo_mesh_block_renumber(const RheoHostMesh* m, int32_t* perm, int32_t* colour_start, int32_t* tile3) {
+    if (!m || !perm || !colour_start) { rheo::set_error("rheo_mesh_block_renumber: null argument"); return -1; }
+    rk_host::BlockOrdering bo;
+    if (!rk_host::block_renumber(m->n_cells, m->n_internal, m->owner.data(), m->neighbour.data(), m->C.data(), bo)) return 0;
+    std::copy(bo.perm.begin(), bo.perm.end(), perm);
+    std::copy(bo.colourStart.begin(), bo.colourStart.end(), colour_start);
+    if (tile3) { tile3[0] = bo.tile[0]; tile3[1] = bo.tile[1]; tile3[2] = bo.tile[2]; }
+    return bo.nColours;
 }
 
 int rheo_mesh_colour_renumber(const RheoHostMesh* m, int32_t* perm, int32_t* colour, int32_t* colour_start) {

@@ -132,6 +132,18 @@ class HostMesh:
             raise RuntimeError(abi.lib().rheo_mesh_last_error().decode())
         return perm, colour, cstart[: nc + 1].copy()
 
+    def block_renumber(self):
+        """(perm, colour_start, tile) of the block ordering, or None when the mesh is not a lattice mesh."""
+        perm = np.zeros(self.n_cells, dtype=np.int32)
+        cstart = np.zeros(65, dtype=np.int32)
+        tile = np.zeros(3, dtype=np.int32)
+        nc = abi.lib().rheo_mesh_block_renumber(self._h, _ptr(perm), _ptr(cstart), _ptr(tile))
+        if nc < 0:
+            raise RuntimeError(abi.lib().rheo_mesh_last_error().decode())
+        if nc == 0:
+            return None
+        return perm, cstart[: nc + 1].copy(), tuple(int(t) for t in tile)
+
     # ---- synthetic fields ------------------------------------------------------------------------
     def synth_fields(self, spec: abi.RheoSynthSpec):
         U = np.zeros((self.n_cells, 3))

@@ -134,6 +134,13 @@ class GpuStressModel:
         _check(abi.lib().rheo_gpu_get_ordering(self._h, buf, len(buf)))
         return buf.value.decode()
 
+    def levels(self):
+        """(fwd, bwd) in-chunk levels per cell in device numbering (block ordering only)."""
+        fwd = np.zeros(self.mesh.n_cells, dtype=np.int32)
+        bwd = np.zeros(self.mesh.n_cells, dtype=np.int32)
+        _check(abi.lib().rheo_gpu_get_levels(self._h, _p(fwd), _p(bwd)))
+        return fwd, bwd
+
     def launch_count(self) -> int:
         return int(abi.lib().rheo_gpu_launch_count(self._h))
 

@@ -185,10 +185,30 @@ def test_relax_factor_one_is_folded():
 
 
 def test_renumbering_and_ell_bit_exact():
-    """integer mesh renumbering / addressing must be bit-exact (BASELINE.json)."""
+    """integer mesh renumbering / addressing must be bit-exact (BASELINE.json): the block ordering PBiCGStab uses on
+    lattice meshes (permutation, chunk-colour offsets, ELL tables, in-chunk levels) against oracle/mesh_ref.py."""
     spec = cases.by_name("C2", 1 / 9)
     s = Setup(spec)
     g = s.gpu()
+    assert "chunk colours" in g.ordering()
+    perm, cstart = g.renumbering()
+    rm = mesh_ref.from_host_mesh(s.mesh)
+    perm_ref, cstart_ref, _ = mesh_ref.block_renumber(rm)
+    assert np.array_equal(perm, perm_ref) and np.array_equal(cstart, cstart_ref)
+    nbr, face = g.ell()
+    nbr_ref, face_ref = mesh_ref.ell_tables(rm, perm_ref)
+    assert np.array_equal(nbr, nbr_ref) and np.array_equal(face, face_ref)
+    fwd, bwd = g.levels()
+    fwd_ref, bwd_ref = mesh_ref.chunk_levels(nbr_ref, rm.n_cells)
+    assert np.array_equal(fwd, fwd_ref) and np.array_equal(bwd, bwd_ref)
+
+
+def test_cell_colouring_renumbering_bit_exact():
+    """... and the greedy cell colouring the device PBiCG (pbicg.cuh) and unstructured meshes run in."""
+    spec = cases.by_name("C2", 1 / 9)
+    s = Setup(spec)
+    g = s.gpu(tight(spec.schemes, 1e-10, solver="PBiCG"))
+    assert "cell colouring" in g.ordering()
     perm, cstart = g.renumbering()
     rm = mesh_ref.from_host_mesh(s.mesh)
     perm_ref, colour_ref, cstart_ref = mesh_ref.colour_renumber(rm.n_cells, rm.owner, rm.neighbour)
@@ -198,97 +218,40 @@ def test_renumbering_and_ell_bit_exact():
     assert np.array_equal(nbr, nbr_ref) and np.array_equal(face, face_ref)
 
 
-def test_upload_download_round_trip_is_exact():
-    spec = cases.by_name("C3", 2 / 19)
-    s = Setup(spec)
+@pytest.mark.parametrize("name,scale,cfl", [("C5", 32 / 400, 2.0), ("C3", 4 / 19, 2.0), ("C2", 2 / 9, 4.0)])
+def test_block_ordering_same_iterations_as_sequential_oracle(name, scale, cfl):
+    """The level-scheduled in-chunk substitutions + chunk colours ARE the sequential DILU of the oracle on the renumbered
+    mesh: same iteration counts per component (two chunk colours on C5's box of whole blocks, several on C3 / C2)."""
+    spec = cases.by_name(name, scale)
+    s = Setup(spec, cfl=cfl)
     g = s.gpu()
-    assert np.array_equal(g.theta(), s.theta0)
-    assert np.array_equal(g.download(abi.FIELD_EIGVECS), s.eigvecs)
-    assert np.array_equal(g.download(abi.FIELD_EIGVALS), s.eigvals)
+    perm, cstart = g.renumbering()
+    rm = mesh_ref.renumbered_mesh(mesh_ref.from_host_mesh(s.mesh), perm)
+    oc = orc.OracleCase([mesh_ref.to_desc(rm, abi)], spec.models, spec.schemes)
+    oc.set_state(0, 0, s.theta0[perm], s.tau0[perm], s.eigvals[perm], s.eigvecs[perm])
+    fa = rm.face_addr
+    oc.set_velocity(0, s.U[perm], s.Ub, np.where(fa > 0, s.phi[np.abs(fa) - 1], -s.phi[np.abs(fa) - 1]))
+    so = (abi.RheoStepStats * 1)()
+    for _ in range(2):
+        oc.store_old_time(); oc.step(s.dt, so)
+        g.store_old_time(); sg = g.correct(s.dt, want_stats=True)
+        assert list(sg[0].n_iterations) == list(so[0].n_iterations)
+    assert max(so[0].n_iterations) >= 2
+    th_o = np.empty_like(s.theta0); th_o[perm] = oc.get(0, 0, abi.FIELD_THETA)
+    assert rel_l2(g.theta(), th_o) <= 1e-11
 
 
-def test_errors_are_reported_not_swallowed():
-    from rheotool_b200.stress import GpuStressModel, RheoError
-    spec = cases.by_name("C3", 2 / 19)
-    s = Setup(spec)
-    bad = tight(spec.schemes); bad.limiter = 99
-    with pytest.raises(RheoError, match="deferred limited scheme"):
-        GpuStressModel(s.mesh, spec.models, bad)
-    g = s.gpu()
-    with pytest.raises(RheoError):
-        g.correct(-1.0)
-
-
-def test_host_buffer_call_matches_resident_call_and_skips_empty_patches():
-    """rheo_gpu_correct (host buffers: what the OpenFOAM shim calls) == upload + store_old_time + step + download; the
-    values a caller leaves on the faces of `empty` patches are never read (OpenFOAM's emptyFvPatchField has size 0), and
-    the bytes the library reports are the bytes it copied."""
-    spec = cases.by_name("C2", 1 / 9)   # 2-D: the front/back patches are `empty`
-    s = Setup(spec)
-    sc = tight(spec.schemes)
-    g1, g2 = s.gpu(sc), s.gpu(sc)
-    g1.store_old_time(); g1.correct(s.dt)
-    # poison everything that belongs to an empty patch
-    Ub, phi = s.Ub.copy(), s.phi.copy()
-    nint = s.mesh.n_internal
-    n_empty = 0
-    for p in s.mesh.patches:
-        if p.type == abi.PATCH_EMPTY:
-            Ub[p.start - nint:p.start - nint + p.size] = np.nan
-            phi[p.start:p.start + p.size] = np.nan
-            n_empty += p.size
-    assert n_empty > 0
-    U = np.ascontiguousarray(s.U)
-    tau = np.zeros((s.mesh.n_cells, 6))
-    h0, d0 = g2.transfer_bytes()
-    g2.correct_host(U.ctypes.data, Ub.ctypes.data, phi.ctypes.data, s.dt, True, tau.ctypes.data)
-    h1, d1 = g2.transfer_bytes()
-    assert np.array_equal(tau, g1.tau(0))
-    assert np.array_equal(g2.theta(), g1.theta())
-    n_faces = s.mesh.n_internal + s.mesh.n_boundary
-    assert h1 - h0 == 8 * (3 * s.mesh.n_cells + 3 * (s.mesh.n_boundary - n_empty) + (n_faces - n_empty))
-    assert d1 - d0 == 8 * 6 * s.mesh.n_cells
-    assert g2.comm_stats()["mode"] == "single"
-
-
-def test_fene_cr_log_one_step_and_ten_steps():
-    """FENE-CRLog (FENE_CRLog.C:128-182): same kernels, its own source / theta->tau functor."""
-    spec = cases.by_name("C5", 16 / 400)
-    spec.models[:] = [cases.model_desc("FENE-CRLog", rho=1.0, etaS=0.01, etaP=0.99, lambda_=0.1, L2=100.0)]
-    s, oc, g = _one_step(spec)
-    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
-    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
-    for _ in range(9):
-        oc.store_old_time(); oc.step(s.dt)
-        g.store_old_time(); g.correct(s.dt)
-    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
-
-
-def test_white_metzner_cy_log_one_step_and_ten_steps():
-    """WhiteMetznerCYLog (WhiteMetznerCYLog.C:145-211): shear-rate dependent eta_p, lambda per cell."""
+@pytest.mark.parametrize("max_iter", [1, 2])
+def test_max_iter_cap_counts_like_openfoam(max_iter):
+    """EXT-OF9 PBiCGStab: `++nIterations() < maxIter_` (pre-increment): capped at maxIter the solver has run exactly maxIter
+    iterations and reports that number; device and oracle agree on count, residuals and the (unconverged) field."""
     spec = cases.by_name("C3", 3 / 19)
-    spec.models[:] = [cases.model_desc("WhiteMetznerCYLog", rho=1.0, etaS=0.01, etaP=0.99, lambda_=0.1, wm_K=0.8, wm_n=0.5, wm_a=2.0)]
-    s, oc, g = _one_step(spec)
-    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
-    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
-    for _ in range(9):
-        oc.store_old_time(); oc.step(s.dt)
-        g.store_old_time(); g.correct(s.dt)
-    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
-
-
-@pytest.mark.parametrize("mname,kw", [
-    ("Rolie-PolyLog", dict(lambda_=0.1, rp_lambdaR=0.03, rp_beta=0.3, rp_delta=-0.5, rp_chiMax=5.0)),
-    ("XPomPomLog", dict(lambda_=0.1, alpha=0.1, xpp_lambdaS=0.04, xpp_q=3.0, xpp_n=1.0)),
-])
-def test_tube_models_one_step_and_ten_steps(mname, kw):
-    """Rolie-PolyLog / XPomPomLog (RoliePolyLog.C:130-215, XPomPomLog.C:130-198)."""
-    spec = cases.by_name("C3", 3 / 19)
-    spec.models[:] = [cases.model_desc(mname, rho=1.0, etaS=0.01, etaP=0.99, **kw)]
-    s, oc, g = _one_step(spec)
-    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= TOL_1
-    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= TOL_1
-    for _ in range(9):
-        oc.store_old_time(); oc.step(s.dt)
-        g.store_old_time(); g.correct(s.dt)
-    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
+    s = Setup(spec, cfl=3.0)
+    sc = tight(spec.schemes, 1e-14)
+    sc.max_iter = max_iter
+    oc, g = s.oracle(sc), s.gpu(sc)
+    so = (abi.RheoStepStats * 1)()
+    oc.store_old_time(); oc.step(s.dt, so)
+    g.store_old_time(); sg = g.correct(s.dt, want_stats=True)
+    assert max(so[0].n_iterations) == max_iter and list(sg[0].n_iterations) == list(so[0].n_iterations)
+    assert not any(sg[0].converged[c] for c in range(6)) and not any(so[0].converged[c] for c in range(6))

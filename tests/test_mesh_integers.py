@@ -154,6 +154,42 @@ def test_colour_renumbering_bit_exact(name):
     assert (np.diff(key) > 0).all()
 
 
+@pytest.mark.parametrize("name,scale", [("C1", 0.3), ("C2", 2 / 9), ("C3", 5 / 19), ("C4", 30 / 252), ("C5", 32 / 400), ("C5", 0.1)])
+def test_block_renumbering_bit_exact(name, scale):
+    """The device's block ordering for PBiCGStab on lattice meshes (csrc/host/ordering.hpp) against its numpy restatement:
+    permutation and chunk-colour offsets bit-exact; chunks of one colour share no face; natural order inside a chunk's blocks."""
+    from rheotool_b200 import cases
+    m = mesh.tensor_grid(cases.by_name(name, scale).grid)
+    got = m.block_renumber()
+    assert got is not None, "tensor grids are lattice meshes"
+    perm, cstart, tile = got
+    rm = mesh_ref.from_host_mesh(m)
+    rperm, rcstart, rtile = mesh_ref.block_renumber(rm)
+    assert np.array_equal(perm, rperm) and np.array_equal(cstart, rcstart) and tile == rtile
+    assert np.array_equal(np.sort(perm), np.arange(m.n_cells))
+    assert all(int(c) % 256 == 0 for c in cstart[:-1]) and cstart[-1] == m.n_cells
+    # chunks of one colour are pairwise non-adjacent
+    iperm = np.empty(m.n_cells, dtype=np.int64); iperm[perm] = np.arange(m.n_cells)
+    o, n = iperm[m.owner[: m.n_internal]], iperm[m.neighbour]
+    colour_of = np.searchsorted(cstart, np.arange(m.n_cells), side="right") - 1
+    cut = (o >> 8) != (n >> 8)
+    assert (colour_of[o[cut]] != colour_of[n[cut]]).all()
+    if name == "C5" and scale == 32 / 400:
+        assert len(cstart) - 1 == 2 and tile == (8, 8, 4), "a box of whole 8x8x4 blocks is two-colourable"
+    # levels of the in-chunk dependency graphs: a chain can only grow by one per neighbour
+    nbr, _ = mesh_ref.ell_tables(rm, perm)
+    fwd, bwd = mesh_ref.chunk_levels(nbr, m.n_cells)
+    assert fwd.max() <= 255 and bwd.max() <= 255
+    if tile == (8, 8, 4) and len(cstart) - 1 == 2:
+        assert fwd.max() == 7 + 7 + 3 and bwd.max() == 7 + 7 + 3
+
+
+def test_block_renumbering_declines_unstructured_meshes():
+    ncell, own, nei = _prism_like_mesh()
+    m, _ = _mesh_from_addressing(ncell, own, nei)
+    assert m.block_renumber() is None
+
+
 def _prism_like_mesh(nx=7, ny=6, nz=3, seed=3):
     """An unstructured, NOT two-colourable addressing: a hex grid with the squares of every z-layer split
     into two triangular prisms (odd cycles), cells randomly renumbered.  Geometry is irrelevant here."""

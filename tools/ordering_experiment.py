@@ -50,6 +50,9 @@ def perms(m):
         out[f"tileRB{bx}x{by}x{bz}"] = np.lexsort((nat, tid, col)).astype(np.int32)
     col = (j + k) & 1
     out["lineRB"] = np.lexsort((nat, col)).astype(np.int32)
+    br = m.block_renumber()   # what the device uses (csrc/host/ordering.hpp)
+    if br is not None:
+        out["device-blocks"] = br[0]
     return out
 
 
