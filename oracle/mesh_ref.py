@@ -101,7 +101,7 @@ def colour_renumber(n_cells: int, owner: np.ndarray, neighbour: np.ndarray):
     return perm, colour, cstart
 
 
-CHUNK = 256
+CHUNK = 32
 
 
 def block_renumber(rm: "RefMesh"):
@@ -129,11 +129,12 @@ def block_renumber(rm: "RefMesh"):
     thick = [d > 1 for d in dims]
     t = [1, 1, 1]
     if sum(thick) == 3:
-        t = [8, 8, 4]
+        t = [4, 4, 2]
     elif sum(thick) == 2:
-        t = [16 if th else 1 for th in thick]
+        w = [8, 4]
+        t = [w.pop(0) if th else 1 for th in thick]
     elif sum(thick) == 1:
-        t = [256 if th else 1 for th in thick]
+        t = [CHUNK if th else 1 for th in thick]
     nT = [(dims[d] + t[d] - 1) // t[d] for d in range(3)]
     i, j, k = ijk
     tid = ((k // t[2]) * nT[1] + (j // t[1])) * nT[0] + (i // t[0])

@@ -49,7 +49,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; the B200 stress-step library cannot be built")
     OBJ.mkdir(parents=True, exist_ok=True)
-    headers = list((ROOT / "include").glob("*.h")) + list(CSRC.rglob("*.hpp")) + list(CSRC.rglob("*.cuh"))
+    headers = list((ROOT / "include").glob("*.h")) + list(CSRC.rglob("*.hpp")) + list(CSRC.rglob("*.cuh")) + list(CSRC.rglob("*.inl"))
     inc = ["-I", str(ROOT / "include"), "-I", str(CSRC / "host"), "-I", str(CSRC / "gpu")]
     objs = []
     for src in sorted(CSRC.rglob("*.cpp")) + sorted(CSRC.rglob("*.cu")):

@@ -1,15 +1,18 @@
-// blocksweep.cuh — DILU substitutions in the BLOCK ordering (host/ordering.hpp): natural cell order inside chunks of 256
-// cells, chunks coloured so that chunks of one colour are pairwise non-adjacent.
+// blocksweep.cuh — DILU substitutions in the BLOCK ordering (host/ordering.hpp): natural cell order inside chunks of 32
+// cells (4x4x2 lattice cells in 3-D, 8x4 in 2-D), chunks coloured so that chunks of one colour are pairwise non-adjacent.
 //
-// EXT-OF9 DILUPreconditioner::precondition restated for that numbering.  One CTA owns one chunk (= one row tile of the
-// matrix, streamed by the same cp.async.bulk pipeline as krylov.cuh), one thread one cell:
+// EXT-OF9 DILUPreconditioner::precondition restated for that numbering.  One WARP owns one chunk, one thread one cell; the
+// CTA still walks row tiles of 256 cells (8 chunks) whose matrix rows arrive through the cp.async.bulk pipeline of krylov.cuh:
 //   * neighbours in OTHER chunks belong to another colour; the kernels run colour by colour, so those values are final in
-//     HBM and are gathered as before;
+//     HBM and are gathered as before (outflow faces have A = min(F, 0) = 0 and are not gathered at all);
 //   * neighbours INSIDE the chunk are resolved in shared memory by a level-scheduled sweep: a cell of level l (longest chain
-//     of lower-numbered in-chunk neighbours, precomputed on the host) is updated in round l, after a __syncthreads; an
-//     8x8x4 block has 18 levels, a 16x16 block 31.  The arithmetic is the sequential substitution's (same operands, the
-//     in-chunk and out-of-chunk sums are formed separately) — tests hold the iteration history to the oracle's on the
-//     renumbered mesh.
+//     of lower-numbered in-chunk neighbours, precomputed on the host) is updated in round l, after a __syncwarp — no CTA-wide
+//     barrier, so the 16-24 resident warps of an SM hide each other's latency chains (a 4x4x2 block has 8 levels, an 8x4
+//     block 11).  The slot classification (in-chunk lower / higher, shared-memory index, coefficient) is done once per cell,
+//     before the rounds.  The arithmetic is the sequential substitution's (same operands; in-chunk and out-of-chunk sums
+//     are formed separately) — tests hold the iteration history to the oracle's on the renumbered mesh.
+//   (The first version of this round used 256-cell chunks swept by the whole CTA with __syncthreads between 18 + 18 levels:
+//    same iteration counts, but every round was an exposed latency chain — 4x the memory time; profiles/r2_ordering.md.)
 // Per preconditioned product x = M^-1 rhs, w = A x with nc chunk colours:
 //   k_bsweep<DIR 0>   colours 0 .. nc-2 : (vector update of the cell) + forward substitution
 //   k_bsweep<DIR 1>   colour nc-1       : forward AND backward substitution in one pass (no higher colour exists)
@@ -24,88 +27,111 @@
 
 namespace rk {
 
-// slot classification for cell c of row tile `tile` (nbrA holds c itself for unused / boundary slots, >= N for ghosts)
-__device__ __forceinline__ bool in_chunk(int nb, int c, int tile, int N) { return (nb >> 8) == tile && nb < N && nb != c; }
+constexpr int CH = 32;        // cells per chunk (== rk_host::CHUNK)
+constexpr int CH_SHIFT = 5;
 
-// acc[j] = sum over the slots selected by `sel(nb)` of A[s] * y[nb][j], neighbour values from HBM
-//   WHICH 0: out-of-chunk lower (nb < c)    1: out-of-chunk higher (c < nb < N)    2: every out-of-chunk local column
+// nbrA holds c itself for unused / boundary slots and indices >= N for ghosts (which may share c's chunk index range)
+__device__ __forceinline__ bool in_chunk(int nb, int c, int N) { return (nb >> CH_SHIFT) == (c >> CH_SHIFT) && nb < N && nb != c; }
+
+// this cell's matrix row, classified once: out-of-chunk neighbours (gathered from HBM) and in-chunk ones (shared memory)
+template <int KT> struct RowSplit {
+    int nb[KT > 0 ? KT : 1];      // neighbour (global index)
+    double aLow[KT > 0 ? KT : 1], aHigh[KT > 0 ? KT : 1];   // coefficient if the slot is an IN-chunk lower / higher neighbour, else 0
+    double aRem[KT > 0 ? KT : 1]; // coefficient if the slot is an OUT-of-chunk local column (nb < N), else 0
+};
+template <int KT>
+__device__ __forceinline__ void split_row(const RowView& rv, int c, int N, RowSplit<KT>& r) {
+#pragma unroll
+    for (int s = 0; s < KT; ++s) {
+        const int nb = rv.nb[s * RT];
+        const double a = rv.a[s * RT];
+        const bool loc = in_chunk(nb, c, N);
+        const bool rem = !loc && nb != c && nb < N;
+        r.nb[s] = nb;
+        r.aLow[s] = (loc && nb < c) ? a : 0.0;
+        r.aHigh[s] = (loc && nb > c) ? a : 0.0;
+        r.aRem[s] = rem ? a : 0.0;
+    }
+}
+
+// acc[j] = sum over out-of-chunk slots of A[s] * y[nb][j]   WHICH 0: lower (nb < c)   1: higher (nb > c)   2: all
 template <int NR, int KT, int WHICH>
-__device__ __forceinline__ void gather_remote(const RowView& rv, int K, int c, int tile, int N, const double* __restrict__ y, size_t base, double (&acc)[NR]) {
+__device__ __forceinline__ void gather_remote(const RowSplit<KT>& r, const RowView& rv, int K, int c, int N, const double* __restrict__ y, size_t base,
+                                              double (&acc)[NR]) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-    auto selected = [&](int nb) {
-        if (nb == c || nb >= N || (nb >> 8) == tile) return false;
-        return WHICH == 0 ? nb < c : (WHICH == 1 ? nb > c : true);
-    };
     if constexpr (KT == 0) {
         for (int s = 0; s < K; ++s) {
             const int nb = rv.nb[s * RT];
-            if (!selected(nb)) continue;
+            if (nb == c || nb >= N || in_chunk(nb, c, N)) continue;
+            if ((WHICH == 0 && nb > c) || (WHICH == 1 && nb < c)) continue;
             const double a = rv.a[s * RT];
+            if (a == 0.0) continue;
             double yn[NR];
             ldv<NR>(y, base + nb, yn);
 #pragma unroll
             for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
         }
     } else {
-        int nb[KT];
-        double a[KT];
-#pragma unroll
-        for (int s = 0; s < KT; ++s) { nb[s] = rv.nb[s * RT]; a[s] = rv.a[s * RT]; }
-#pragma unroll
-        for (int s = 0; s < KT; ++s)
-            if (!selected(nb[s])) a[s] = 0.0;
 #pragma unroll
         for (int s = 0; s < KT; ++s) {
-            // unselected slot, or an outflow face (A = min(F, 0) = 0: half of the faces of an upwind matrix): nothing to add.
-            // Interior cells of a block have no out-of-chunk neighbour at all and issue no gather.
-            if (a[s] == 0.0) continue;
+            // not selected, or an outflow face (A = min(F, 0) = 0: half of the faces of an upwind matrix): nothing to add
+            const double a = ((WHICH == 0 && r.nb[s] > c) || (WHICH == 1 && r.nb[s] < c)) ? 0.0 : r.aRem[s];
+            if (a == 0.0) continue;
             double yn[NR];
-            ldv<NR>(y, base + nb[s], yn);
+            ldv<NR>(y, base + r.nb[s], yn);
 #pragma unroll
-            for (int j = 0; j < NR; ++j) acc[j] += a[s] * yn[j];
+            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
         }
     }
 }
 
-// acc[j] = sum over in-chunk slots (LOWER: nb < c, else nb > c; BOTH: all) of A[s] * ys[nb - tileBase][j], values from shared memory
-template <int NR, int KT, int WHICH>   // WHICH 0 lower, 1 higher, 2 both
-__device__ __forceinline__ void gather_local(const RowView& rv, int K, int c, int tile, int N, const double* ys, double (&acc)[NR]) {
+// acc[j] = sum over in-chunk slots of A[s] * ys[nb & 255][j] (shared memory)   WHICH 0: lower   1: higher   2: both
+template <int NR, int KT, int WHICH>
+__device__ __forceinline__ void gather_local(const RowSplit<KT>& r, const RowView& rv, int K, int c, int N, const double* ys, double (&acc)[NR]) {
 #pragma unroll
     for (int j = 0; j < NR; ++j) acc[j] = 0.0;
-    const int KK = KT > 0 ? KT : K;
+    if constexpr (KT == 0) {
+        for (int s = 0; s < K; ++s) {
+            const int nb = rv.nb[s * RT];
+            if (!in_chunk(nb, c, N)) continue;
+            if ((WHICH == 0 && nb > c) || (WHICH == 1 && nb < c)) continue;
+            const double a = rv.a[s * RT];
+            const double* yn = ys + (size_t)(nb & (RT - 1)) * NR;
 #pragma unroll
-    for (int s = 0; s < KK; ++s) {
-        const int nb = rv.nb[s * RT];
-        if (!in_chunk(nb, c, tile, N)) continue;
-        if (WHICH == 0 && nb > c) continue;
-        if (WHICH == 1 && nb < c) continue;
-        const double a = rv.a[s * RT];
-        const double* yn = ys + (size_t)(nb & (RT - 1)) * NR;
+            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+        }
+    } else {
 #pragma unroll
-        for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+        for (int s = 0; s < KT; ++s) {
+            const double a = WHICH == 0 ? r.aLow[s] : (WHICH == 1 ? r.aHigh[s] : r.aLow[s] + r.aHigh[s]);
+            if (a == 0.0) continue;
+            const double* yn = ys + (size_t)(r.nb[s] & (RT - 1)) * NR;
+#pragma unroll
+            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+        }
     }
 }
 
-// level-scheduled in-chunk substitution: after round l every cell of level <= l holds its final value in ys
-//   BWD 0: forward (levels of lower neighbours), BWD 1: backward (levels of higher neighbours)
+// level-scheduled in-chunk substitution of one warp: after round l every cell of level <= l holds its final value in ys
+//   BWD 0: forward (levels of lower neighbours), BWD 1: backward (levels of higher neighbours).  Called by whole warps.
 template <int NR, int KT, int BWD>
-__device__ __forceinline__ void chunk_sweep(const RowView& rv, int K, int c, int tile, int N, bool valid, int myLev, int maxLev, const bool (&on)[NR], double* ys,
-                                            double (&yy)[NR]) {
+__device__ __forceinline__ void chunk_sweep(const RowSplit<KT>& r, const RowView& rv, int K, int c, int N, bool valid, int myLev, int maxLev, double rd,
+                                            const bool (&on)[NR], double* ys, double (&yy)[NR]) {
     for (int l = 1; l <= maxLev; ++l) {
-        __syncthreads();
+        __syncwarp();
         if (valid && myLev == l) {
             double acc[NR];
-            gather_local<NR, KT, BWD>(rv, K, c, tile, N, ys, acc);
+            gather_local<NR, KT, BWD>(r, rv, K, c, N, ys, acc);
             double* mine = ys + (size_t)threadIdx.x * NR;
 #pragma unroll
             for (int j = 0; j < NR; ++j) {
-                if (on[j]) yy[j] -= rv.rd * acc[j];
+                if (on[j]) yy[j] -= rd * acc[j];
                 mine[j] = yy[j];
             }
         }
     }
-    __syncthreads();
+    __syncwarp();
 }
 
 // DIR 0: forward   1: forward + backward (last colour)   2: backward (middle colours; UPD must be 0)
@@ -144,18 +170,20 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bsweep(MeshView m, RowSrc r
             const int st = it & 1, next = tile + gridDim.x;
             if (threadIdx.x == 0 && next <= tEnd) row_issue(smemRaw + (size_t)(st ^ 1) * stageBytes, &full[st ^ 1], rs, K, next);
             const int c = tile * RT + threadIdx.x;
-            const bool valid = c >= c0 && c < c1;
+            const bool valid = c >= c0 && c < c1;   // colour ranges are chunk-aligned: a warp is in range or out of it as a whole
             const size_t i = (size_t)md * m.NP + c;
             double yy[NR], rr[NR], vv[NR], pp[NR];
-            int myLev = 0;
+            int myLev = 0, chunkLev = 0;
             if (valid) {
                 if (UPD == 0) ldv<NR>(y, i, yy);
                 else { ldv<NR>(u.r, i, rr); ldv<NR>(u.v, i, vv); if (UPD == 1) ldv<NR>(u.p, i, pp); }
                 myLev = m.lev[c];
+                chunkLev = m.chunkLev[c >> CH_SHIFT];
             }
-            const int chunkLev = m.chunkLev[tile];
             mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
             const RowView rv = row_view(smemRaw + (size_t)st * stageBytes, K);
+            RowSplit<KT> sp;
+            if constexpr (KT > 0) split_row<KT>(rv, c, m.N, sp);
             if (valid) {
                 if (UPD == 1) {
 #pragma unroll
@@ -180,7 +208,7 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bsweep(MeshView m, RowSrc r
                 }
                 if (!(FIRST && DIR != 2)) {   // out-of-chunk neighbours of the direction being substituted (final in HBM)
                     double acc[NR];
-                    gather_remote<NR, KT, DIR == 2 ? 1 : 0>(rv, K, c, tile, m.N, y, (size_t)md * m.NP, acc);
+                    gather_remote<NR, KT, DIR == 2 ? 1 : 0>(sp, rv, K, c, m.N, y, (size_t)md * m.NP, acc);
 #pragma unroll
                     for (int j = 0; j < NR; ++j)
                         if (on[j]) yy[j] -= rv.rd * acc[j];
@@ -189,10 +217,11 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bsweep(MeshView m, RowSrc r
 #pragma unroll
                 for (int j = 0; j < NR; ++j) mine[j] = yy[j];
             }
-            if (DIR != 2) chunk_sweep<NR, KT, 0>(rv, K, c, tile, m.N, valid, myLev & 255, chunkLev & 255, on, ys, yy);
-            if (DIR != 0) chunk_sweep<NR, KT, 1>(rv, K, c, tile, m.N, valid, myLev >> 8, chunkLev >> 8, on, ys, yy);
+            chunkLev = __shfl_sync(0xffffffffu, chunkLev, 0);   // warp-uniform round count (lane 0 is valid whenever any lane is)
+            if (DIR != 2) chunk_sweep<NR, KT, 0>(sp, rv, K, c, m.N, valid, myLev & 255, chunkLev & 255, rv.rd, on, ys, yy);
+            if (DIR != 0) chunk_sweep<NR, KT, 1>(sp, rv, K, c, m.N, valid, myLev >> 8, chunkLev >> 8, rv.rd, on, ys, yy);
             if (valid) stv<NR>(y, i, yy);
-            __syncthreads();   // stage st and ys are free for the next tile
+            __syncthreads();   // stage st is free for the prefetch issued in the next iteration (ys is per warp)
         }
         if constexpr (UPD == 2) block_reduce_to_partials<NR>(red, u.partials + (size_t)u.blockBase * nModes * NR, md * NR, nModes * NR);
     }
@@ -233,13 +262,14 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bspmv0(MeshView m, RowSrc r
             const bool valid = c >= c0 && c < c1;
             const size_t i = (size_t)md * m.NP + c;
             double yy[NR], oo[NR], accR[NR];
-            int myLev = 0;
-            if (valid) { ldv<NR>(y, i, yy); ldv<NR>(other, i, oo); myLev = m.lev[c]; }
-            const int chunkLev = m.chunkLev[tile];
+            int myLev = 0, chunkLev = 0;
+            if (valid) { ldv<NR>(y, i, yy); ldv<NR>(other, i, oo); myLev = m.lev[c]; chunkLev = m.chunkLev[c >> CH_SHIFT]; }
             mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
             const RowView rv = row_view(smemRaw + (size_t)st * stageBytes, K);
+            RowSplit<KT> sp;
+            if constexpr (KT > 0) split_row<KT>(rv, c, m.N, sp);
             if (valid) {
-                gather_remote<NR, KT, 2>(rv, K, c, tile, m.N, y, (size_t)md * m.NP, accR);
+                gather_remote<NR, KT, 2>(sp, rv, K, c, m.N, y, (size_t)md * m.NP, accR);
                 double* mine = ys + (size_t)threadIdx.x * NR;
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
@@ -247,10 +277,11 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bspmv0(MeshView m, RowSrc r
                     mine[j] = yy[j];
                 }
             }
-            chunk_sweep<NR, KT, 1>(rv, K, c, tile, m.N, valid, myLev >> 8, chunkLev >> 8, on, ys, yy);   // ends with a barrier: ys is final
+            chunkLev = __shfl_sync(0xffffffffu, chunkLev, 0);   // warp-uniform round count (lane 0 is valid whenever any lane is)
+            chunk_sweep<NR, KT, 1>(sp, rv, K, c, m.N, valid, myLev >> 8, chunkLev >> 8, rv.rd, on, ys, yy);   // ends with __syncwarp: the chunk's ys is final
             if (valid) {
                 double accL[NR], vv[NR];
-                gather_local<NR, KT, 2>(rv, K, c, tile, m.N, ys, accL);
+                gather_local<NR, KT, 2>(sp, rv, K, c, m.N, ys, accL);
 #pragma unroll
                 for (int j = 0; j < NR; ++j) {
                     vv[j] = 0.0;

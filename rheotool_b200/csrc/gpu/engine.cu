@@ -158,6 +158,7 @@ struct RheoGpu {
     int nOldTimes = 0;
     double dtNow = 0, dt0 = 0;
     long launches = 0;
+    std::string launchErr;         // first kernel whose launch left an error behind (diagnostics of rheo_gpu_step's message)
     long long h2dBytes = 0, d2hBytes = 0;   // host<->device bytes copied by the upload/download entry points
     int lastIters = 0;
     bool timing = false;
@@ -188,6 +189,7 @@ inline void launch_pdl(cudaStream_t stream, int grid, int block, size_t smem, vo
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
         launch_pdl((h)->stream, (grid), (block), 0, kern, __VA_ARGS__);       \
         (h)->launches++;                                                       \
+        if ((h)->launchErr.empty() && cudaPeekAtLastError() != cudaSuccess) (h)->launchErr = #kern; \
         if ((h)->ktiming) {                                                    \
             cudaEventRecord((h)->kev1, (h)->stream);                           \
             cudaEventSynchronize((h)->kev1);                                   \
@@ -204,6 +206,7 @@ inline void launch_pdl(cudaStream_t stream, int grid, int block, size_t smem, vo
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
         launch_pdl((h)->stream, (grid), (block), (smem), kern, __VA_ARGS__);  \
         (h)->launches++;                                                       \
+        if ((h)->launchErr.empty() && cudaPeekAtLastError() != cudaSuccess) (h)->launchErr = #kern; \
         if ((h)->ktiming) {                                                    \
             cudaEventRecord((h)->kev1, (h)->stream);                           \
             cudaEventSynchronize((h)->kev1);                                   \
@@ -1038,7 +1041,11 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->phaseMs[6] = ms;
     }
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(std::string("rheo_gpu_step: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        const std::string where = h->launchErr.empty() ? std::string() : " (first failing launch: " + h->launchErr + ")";
+        h->launchErr.clear();
+        return fail(std::string("rheo_gpu_step: ") + cudaGetErrorString(e) + where);
+    }
     return 0;
 }
 

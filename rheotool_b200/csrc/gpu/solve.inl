@@ -44,7 +44,9 @@ template <class Kern> int row_grid(RheoGpu* h, Kern kern, long cells, size_t sme
     auto it = h->residentBlocks.find((const void*)kern);
     int blocks;
     if (it == h->residentBlocks.end()) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncAttributes fa{};   // static + dynamic shared memory above 48 KB needs the opt-in (blocksweep.cuh keeps 12 KB static)
+        if (cudaFuncGetAttributes(&fa, kern) != cudaSuccess) cudaGetLastError();
+        if (smem + fa.sharedSizeBytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int perSm = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kern, RT, smem) != cudaSuccess || perSm < 1) { cudaGetLastError(); perSm = 1; }
         blocks = perSm * h->nSms;

@@ -5,19 +5,21 @@
 // how much of the matrix the forward substitution solves exactly.  The reference runs in blockMesh's natural order (i
 // fastest); round 1's cell-wise red-black order made every substitution parallel but cost one extra Krylov iteration on
 // every configuration (C2 1 -> 2, C3/C5 2 -> 3, i.e. 25-30 % of the step).  This ordering keeps the natural
-// order INSIDE blocks of 256 cells (8x8x4 cells in 3-D, 16x16 in 2-D) and colours the BLOCKS:
+// order INSIDE blocks of 32 cells (4x4x2 cells in 3-D, 8x4 in 2-D: one warp) and colours the BLOCKS:
 //
 //   1. lattice indices (i,j,k) of every cell from its centre coordinates; every internal face must join lattice neighbours;
 //   2. cells sorted block by block (blocks in lexicographic order, natural order inside), the sequence cut into chunks of
-//      exactly 256 cells (= the row tiles of the Krylov kernels; for box sizes that are multiples of the block a chunk IS a
-//      block, otherwise chunk boundaries drift across clipped blocks);
+//      exactly 32 cells (for box sizes that are multiples of the block a chunk IS a block, otherwise chunk boundaries drift
+//      across clipped blocks);
 //   3. greedy colouring of the chunk graph in chunk order (2 colours on a box of whole blocks), chunks of one colour are
-//      pairwise non-adjacent => independent in the substitutions; the only partial chunk (N mod 256 cells) goes last;
+//      pairwise non-adjacent => independent in the substitutions; the only partial chunk (N mod 32 cells) goes last;
 //   4. new numbering = colour by colour, chunk by chunk.
 //
-// On the device one CTA owns one chunk: neighbours in other chunks are gathered from HBM (they belong to another colour and
-// are final), neighbours inside the chunk are resolved in shared memory by a level-scheduled sweep — the per-cell levels of
-// the in-chunk dependency graph are computed here.  With the oracle's sequential DILU on the same numbering the arithmetic is
+// On the device one WARP owns one chunk: neighbours in other chunks are gathered from HBM (they belong to another colour and
+// are final), neighbours inside the chunk are resolved in shared memory by a level-scheduled sweep synchronised with
+// __syncwarp only — the per-cell levels of the in-chunk dependency graph are computed here (a 4x4x2 block has 8 levels).
+// (First version of this round: 256-cell chunks = 8x8x4 blocks swept by a whole CTA with __syncthreads between the 18 + 18
+// levels: right iteration counts, but the barrier-separated latency chains made the sweeps 4x slower than the memory time.)  With the oracle's sequential DILU on the same numbering the arithmetic is
 // the same (tests/test_gpu_parity.py: same iteration counts), and the iteration counts are those of the reference's order
 // (tools/ordering_experiment.py; profiles/r2_ordering.md).
 //
@@ -31,11 +33,11 @@
 
 namespace rk_host {
 
-constexpr int CHUNK = 256;   // == RT of the Krylov row tiles (kernels.cuh)
+constexpr int CHUNK = 32;   // one warp; the row tiles of the Krylov kernels (RT = 256, kernels.cuh) hold 8 chunks
 
 struct BlockOrdering {
     std::vector<int> perm;          // perm[new] = old
-    std::vector<int> colourStart;   // [nColours + 1], in cells; every entry but the last is a multiple of CHUNK
+    std::vector<int> colourStart;   // [nColours + 1], in cells; every entry but the last is a multiple of CHUNK (32)
     int nColours = 0;
     int tile[3] = {0, 0, 0};        // block shape in lattice cells
     int dims[3] = {0, 0, 0};        // lattice extents
@@ -92,14 +94,14 @@ inline bool block_renumber(int N, int nInt, const int32_t* own, const int32_t* n
         const int dist = std::abs(ijk[0][o] - ijk[0][n]) + std::abs(ijk[1][o] - ijk[1][n]) + std::abs(ijk[2][o] - ijk[2][n]);
         if (dist != 1) return false;
     }
-    // block shape: 256 cells over the axes that have more than one layer
+    // block shape: 32 cells over the axes that have more than one layer
     int thick[3], nThick = 0;
     for (int d = 0; d < 3; ++d) { thick[d] = out.dims[d] > 1; nThick += thick[d]; }
     int* t = out.tile;
     t[0] = t[1] = t[2] = 1;
-    if (nThick == 3) { t[0] = 8; t[1] = 8; t[2] = 4; }
-    else if (nThick == 2) { for (int d = 0; d < 3; ++d) if (thick[d]) t[d] = 16; }
-    else if (nThick == 1) { for (int d = 0; d < 3; ++d) if (thick[d]) t[d] = 256; }
+    if (nThick == 3) { t[0] = 4; t[1] = 4; t[2] = 2; }
+    else if (nThick == 2) { int w = 8; for (int d = 0; d < 3; ++d) if (thick[d]) { t[d] = w; w = 4; } }
+    else if (nThick == 1) { for (int d = 0; d < 3; ++d) if (thick[d]) t[d] = CHUNK; }
     const long nT[3] = {(out.dims[0] + t[0] - 1) / t[0], (out.dims[1] + t[1] - 1) / t[1], (out.dims[2] + t[2] - 1) / t[2]};
     const long nTiles = nT[0] * nT[1] * nT[2];
     if (nTiles >= (1L << 31)) return false;
@@ -145,7 +147,7 @@ inline bool block_renumber(int N, int nInt, const int32_t* own, const int32_t* n
         nCol = std::max(nCol, col + 1);
     }
     // the partial chunk (if any) is the last chunk of the sequence: its colour goes last, so that every other chunk keeps a
-    // 256-aligned position in the new numbering
+    // 32-aligned position in the new numbering
     if (N % CHUNK != 0) {
         const int cp = colour[nChunks - 1], cl = nCol - 1;
         if (cp != cl)
@@ -169,7 +171,7 @@ inline bool block_renumber(int N, int nInt, const int32_t* own, const int32_t* n
 
 // Levels of the in-chunk dependency graphs in the NEW numbering (nbr: slot-major neighbour table with row stride NS, >= 0
 // cell / ghost, negative otherwise): fwd[c] = longest chain of lower-numbered neighbours inside c's chunk, bwd[c] the same
-// over higher-numbered ones.  lev[c] = fwd | bwd << 8; chunkLev[q] = max fwd | max bwd << 8.  False if a level exceeds 255.
+// over higher-numbered ones (at most 31).  lev[c] = fwd | bwd << 8; chunkLev[q] = max fwd | max bwd << 8 per chunk.
 inline bool chunk_levels(int N, int NS, int K, const std::vector<int>& nbr, std::vector<uint16_t>& lev, std::vector<uint16_t>& chunkLev) {
     std::vector<int> fwd(N, 0), bwd(N, 0);
     for (int c = 0; c < N; ++c) {

@@ -167,21 +167,21 @@ def test_block_renumbering_bit_exact(name, scale):
     rperm, rcstart, rtile = mesh_ref.block_renumber(rm)
     assert np.array_equal(perm, rperm) and np.array_equal(cstart, rcstart) and tile == rtile
     assert np.array_equal(np.sort(perm), np.arange(m.n_cells))
-    assert all(int(c) % 256 == 0 for c in cstart[:-1]) and cstart[-1] == m.n_cells
+    assert all(int(c) % 32 == 0 for c in cstart[:-1]) and cstart[-1] == m.n_cells
     # chunks of one colour are pairwise non-adjacent
     iperm = np.empty(m.n_cells, dtype=np.int64); iperm[perm] = np.arange(m.n_cells)
     o, n = iperm[m.owner[: m.n_internal]], iperm[m.neighbour]
     colour_of = np.searchsorted(cstart, np.arange(m.n_cells), side="right") - 1
-    cut = (o >> 8) != (n >> 8)
+    cut = (o >> 5) != (n >> 5)
     assert (colour_of[o[cut]] != colour_of[n[cut]]).all()
     if name == "C5" and scale == 32 / 400:
-        assert len(cstart) - 1 == 2 and tile == (8, 8, 4), "a box of whole 8x8x4 blocks is two-colourable"
+        assert len(cstart) - 1 == 2 and tile == (4, 4, 2), "a box of whole 4x4x2 blocks is two-colourable"
     # levels of the in-chunk dependency graphs: a chain can only grow by one per neighbour
     nbr, _ = mesh_ref.ell_tables(rm, perm)
     fwd, bwd = mesh_ref.chunk_levels(nbr, m.n_cells)
-    assert fwd.max() <= 255 and bwd.max() <= 255
-    if tile == (8, 8, 4) and len(cstart) - 1 == 2:
-        assert fwd.max() == 7 + 7 + 3 and bwd.max() == 7 + 7 + 3
+    assert fwd.max() <= 31 and bwd.max() <= 31
+    if tile == (4, 4, 2) and len(cstart) - 1 == 2:
+        assert fwd.max() == 3 + 3 + 1 and bwd.max() == 3 + 3 + 1
 
 
 def test_block_renumbering_declines_unstructured_meshes():

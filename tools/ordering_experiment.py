@@ -32,7 +32,7 @@ def ijk_of(m):
     return out
 
 
-TILES = [(8, 8, 4), (4, 4, 4), (16, 16, 1), (8, 8, 1)]
+TILES = [(4, 4, 2), (8, 4, 1), (8, 2, 2)]
 
 
 def perms(m):
