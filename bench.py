@@ -109,6 +109,16 @@ def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int):
         # diag, rD, row, gathered y, y own, other | v (+ y when the backward substitution is fused: colour 0)
         fuse = k.rstrip(">").rstrip().endswith("1")
         return 16 + row + c * 8 * 4 + (c * 8 if fuse else 0), half
+    if base == "k_bsweep":
+        # block ordering (blocksweep.cuh): k_bsweep<NR, KT, DIR, UPD, FIRST> over one chunk colour
+        # rD, row, in/out-of-chunk gathers (one record per distinct out-of-chunk neighbour: ~0.5/cell) | UPD 1: r, p, v -> p, y;  UPD 2: r, v -> s, z
+        # (average 4.5 vectors);  DIR 2 (backward only): y -> y
+        args = [a.strip() for a in k[k.index("<") + 1:k.rindex(">")].split(",")]
+        backward_only = len(args) >= 3 and args[2] == "2"
+        return 8 + row + 0.5 * c * 8 + (2 if backward_only else 4.5) * c * 8, half
+    if base == "k_bspmv0":
+        # diag, rD, row, out-of-chunk gathers, y own, other | y, v
+        return 16 + row + 0.5 * c * 8 + 4 * c * 8, half
     if base == "k_update_p":
         return 8 + 5 * c * 8, half
     if base == "k_make_s":

@@ -8,7 +8,9 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "librheo_b200.so"
+import os as _os
+# RHEO_LIB_PATH: load another build of the same library (kernel tuning experiments with RHEO_NVCC_EXTRA variants)
+_LIB_PATH = Path(_os.environ.get("RHEO_LIB_PATH") or (Path(__file__).resolve().parent / "librheo_b200.so"))
 
 # ---- constants (keep in sync with include/*.h) ---------------------------------------------------
 PATCH_PATCH, PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2, 3

@@ -24,7 +24,7 @@ HOST_CXX = "/usr/bin/g++"   # the image's default CXX (/opt/gcc) has no OpenMP s
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-ccbin", HOST_CXX,
-] + (["-Xptxas", "-v"] if os.environ.get("RHEO_PTXAS_V") else [])
+] + (["-Xptxas", "-v"] if os.environ.get("RHEO_PTXAS_V") else []) + os.environ.get("RHEO_NVCC_EXTRA", "").split()
 CXX_FLAGS = ["-O2", "-fPIC", "-std=c++17", "-Wall"]
 
 

@@ -28,19 +28,30 @@
 namespace rk {
 
 constexpr int CH = 32;        // cells per chunk (== rk_host::CHUNK)
+#ifndef RK_BLK_MINB
+#define RK_BLK_MINB 2         // resident CTAs per SM the chunk kernels are compiled for
+#endif
 constexpr int CH_SHIFT = 5;
 
 // nbrA holds c itself for unused / boundary slots and indices >= N for ghosts (which may share c's chunk index range)
 __device__ __forceinline__ bool in_chunk(int nb, int c, int N) { return (nb >> CH_SHIFT) == (c >> CH_SHIFT) && nb < N && nb != c; }
 
-// this cell's matrix row, classified once: out-of-chunk neighbours (gathered from HBM) and in-chunk ones (shared memory)
+// this cell's matrix row, classified once: out-of-chunk neighbours (gathered from HBM) and in-chunk ones (shared memory).
+// A lattice cell has at most 3 lower and 3 higher neighbours, so the in-chunk ones are compacted into 3 + 3 fixed registers
+// (shared-memory offset of the neighbour's record, coefficient); empty entries point at the cell's own record with
+// coefficient 0.  The rounds of chunk_sweep then cost 3 x (3 LDS.128 + 6 DFMA) instead of a 6-slot loop with branches.
 template <int KT> struct RowSplit {
     int nb[KT > 0 ? KT : 1];      // neighbour (global index)
-    double aLow[KT > 0 ? KT : 1], aHigh[KT > 0 ? KT : 1];   // coefficient if the slot is an IN-chunk lower / higher neighbour, else 0
     double aRem[KT > 0 ? KT : 1]; // coefficient if the slot is an OUT-of-chunk local column (nb < N), else 0
+    int lo[3], hi[3];             // shared-memory record index (cell & 255) of the in-chunk lower / higher neighbours, slot order
+    double aLo[3], aHi[3];
 };
 template <int KT>
 __device__ __forceinline__ void split_row(const RowView& rv, int c, int N, RowSplit<KT>& r) {
+    const int self = c & (RT - 1);
+    int nl = 0, nh = 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { r.lo[i] = self; r.hi[i] = self; r.aLo[i] = 0.0; r.aHi[i] = 0.0; }
 #pragma unroll
     for (int s = 0; s < KT; ++s) {
         const int nb = rv.nb[s * RT];
@@ -48,9 +59,16 @@ __device__ __forceinline__ void split_row(const RowView& rv, int c, int N, RowSp
         const bool loc = in_chunk(nb, c, N);
         const bool rem = !loc && nb != c && nb < N;
         r.nb[s] = nb;
-        r.aLow[s] = (loc && nb < c) ? a : 0.0;
-        r.aHigh[s] = (loc && nb > c) ? a : 0.0;
         r.aRem[s] = rem ? a : 0.0;
+        const bool low = loc && nb < c, high = loc && nb > c;
+        const int idx = nb & (RT - 1);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            if (low && nl == i) { r.lo[i] = idx; r.aLo[i] = a; }
+            if (high && nh == i) { r.hi[i] = idx; r.aHi[i] = a; }
+        }
+        nl += low ? 1 : 0;
+        nh += high ? 1 : 0;
     }
 }
 
@@ -86,7 +104,7 @@ __device__ __forceinline__ void gather_remote(const RowSplit<KT>& r, const RowVi
     }
 }
 
-// acc[j] = sum over in-chunk slots of A[s] * ys[nb & 255][j] (shared memory)   WHICH 0: lower   1: higher   2: both
+// acc[j] = sum over in-chunk slots of A[s] * ys[record][j] (shared memory)   WHICH 0: lower   1: higher   2: both
 template <int NR, int KT, int WHICH>
 __device__ __forceinline__ void gather_local(const RowSplit<KT>& r, const RowView& rv, int K, int c, int N, const double* ys, double (&acc)[NR]) {
 #pragma unroll
@@ -102,19 +120,30 @@ __device__ __forceinline__ void gather_local(const RowSplit<KT>& r, const RowVie
             for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
         }
     } else {
+        if (WHICH != 1) {
 #pragma unroll
-        for (int s = 0; s < KT; ++s) {
-            const double a = WHICH == 0 ? r.aLow[s] : (WHICH == 1 ? r.aHigh[s] : r.aLow[s] + r.aHigh[s]);
-            if (a == 0.0) continue;
-            const double* yn = ys + (size_t)(r.nb[s] & (RT - 1)) * NR;
+            for (int i = 0; i < 3; ++i) {
+                double yn[NR];
+                ldv<NR>(ys, (size_t)r.lo[i], yn);
 #pragma unroll
-            for (int j = 0; j < NR; ++j) acc[j] += a * yn[j];
+                for (int j = 0; j < NR; ++j) acc[j] += r.aLo[i] * yn[j];
+            }
+        }
+        if (WHICH != 0) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                double yn[NR];
+                ldv<NR>(ys, (size_t)r.hi[i], yn);
+#pragma unroll
+                for (int j = 0; j < NR; ++j) acc[j] += r.aHi[i] * yn[j];
+            }
         }
     }
 }
 
 // level-scheduled in-chunk substitution of one warp: after round l every cell of level <= l holds its final value in ys
 //   BWD 0: forward (levels of lower neighbours), BWD 1: backward (levels of higher neighbours).  Called by whole warps.
+// (A right-hand side that is no longer active holds zeros in every cell, so its rounds add 0 * 0: no predicate per RHS.)
 template <int NR, int KT, int BWD>
 __device__ __forceinline__ void chunk_sweep(const RowSplit<KT>& r, const RowView& rv, int K, int c, int N, bool valid, int myLev, int maxLev, double rd,
                                             const bool (&on)[NR], double* ys, double (&yy)[NR]) {
@@ -123,12 +152,9 @@ __device__ __forceinline__ void chunk_sweep(const RowSplit<KT>& r, const RowView
         if (valid && myLev == l) {
             double acc[NR];
             gather_local<NR, KT, BWD>(r, rv, K, c, N, ys, acc);
-            double* mine = ys + (size_t)threadIdx.x * NR;
 #pragma unroll
-            for (int j = 0; j < NR; ++j) {
-                if (on[j]) yy[j] -= rd * acc[j];
-                mine[j] = yy[j];
-            }
+            for (int j = 0; j < NR; ++j) yy[j] -= rd * acc[j];
+            stv<NR>(ys, (size_t)threadIdx.x, yy);
         }
     }
     __syncwarp();
@@ -138,7 +164,7 @@ __device__ __forceinline__ void chunk_sweep(const RowSplit<KT>& r, const RowView
 // FIRST: colour 0 — no out-of-chunk lower neighbour exists (forward), nothing is gathered from HBM
 // UPD as in k_sweep (krylov.cuh): 0 none, 1 p = r + beta (p - omega v) / y = rD p, 2 s = r - alpha v / z = rD s / sum|s|
 template <int NR, int KT, int DIR, int UPD, int FIRST>
-__global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bsweep(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, SweepUpd u) {
+__global__ void __launch_bounds__(RT, RK_BLK_MINB) k_bsweep(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, SweepUpd u) {
     pdl_sync();
     if (ks->nActive == 0) return;
     extern __shared__ __align__(128) unsigned char smemRaw[];
@@ -232,7 +258,7 @@ __global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bsweep(MeshView m, RowSrc r
 // dots as in k_spmv (MODE 0: other . v;  MODE 1: v . v, v . other); shares partials / counter with the k_spmv launch over
 // the other colours (blockBase / totalBlocks)
 template <int NR, int KT, int MODE>
-__global__ void __launch_bounds__(RT, RK_ROW_MINB) k_bspmv0(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, double* __restrict__ v,
+__global__ void __launch_bounds__(RT, RK_BLK_MINB) k_bspmv0(MeshView m, RowSrc rs, int c0, int c1, int nModes, KrylovShared* ks, double* __restrict__ y, double* __restrict__ v,
                                                 const double* __restrict__ other, double* partials, double* out, unsigned* counter, int blockBase,
                                                 int totalBlocks, int ctlWhat, SolveCtl sc) {
     pdl_sync();
