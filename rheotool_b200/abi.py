@@ -11,6 +11,7 @@ from pathlib import Path
 import os as _os
 # RHEO_LIB_PATH: load another build of the same library (kernel tuning experiments with RHEO_NVCC_EXTRA variants)
 _LIB_PATH = Path(_os.environ.get("RHEO_LIB_PATH") or (Path(__file__).resolve().parent / "librheo_b200.so"))
+_HOST_LIB_PATH = Path(__file__).resolve().parent / "librheo_host.so"
 
 # ---- constants (keep in sync with include/*.h) ---------------------------------------------------
 PATCH_PATCH, PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2, 3
@@ -156,25 +157,60 @@ IO_SYMBOLS = {
     "rheo_io_write_field": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _I, C.c_int64, _P, _I, _P, _P, _P, _P, _I]),
 }
 
-_lib = None
+_gpu = None
+_host = None
 
 
-def lib() -> C.CDLL:
-    """Load librheo_b200.so (building is the job of __graft_entry__.build / rheotool_b200.build)."""
-    global _lib
-    if _lib is None:
+def _bind(L, table):
+    for name, (res, args) in table.items():
+        fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    return L
+
+
+def host_lib() -> C.CDLL:
+    """librheo_host.so: mesh generator, decomposition, synthetic fields, OpenFOAM file formats.  No CUDA."""
+    global _host
+    if _host is None:
+        if not _HOST_LIB_PATH.exists():
+            raise RuntimeError(f"{_HOST_LIB_PATH} is missing: run `python -m rheotool_b200.build` (or __graft_entry__.build()).")
+        _host = _bind(C.CDLL(str(_HOST_LIB_PATH)), {**MESH_SYMBOLS, **IO_SYMBOLS})
+    return _host
+
+
+def gpu_lib() -> C.CDLL:
+    """librheo_b200.so: the CUDA stress step (include/rheo_gpu.h)."""
+    global _gpu
+    if _gpu is None:
         if not _LIB_PATH.exists():
             raise RuntimeError(
                 f"{_LIB_PATH} is missing: run `python -m rheotool_b200.build` (or __graft_entry__.build()). "
                 "There is no CPU fallback for the stress step.")
-        L = C.CDLL(str(_LIB_PATH))
-        for name, (res, args) in {**MESH_SYMBOLS, **GPU_SYMBOLS, **IO_SYMBOLS}.items():
-            fn = getattr(L, name)   # AttributeError if the library does not export a declared symbol
-            fn.restype = res
-            fn.argtypes = args
-        _lib = L
-    return _lib
+        _gpu = _bind(C.CDLL(str(_LIB_PATH)), GPU_SYMBOLS)
+    return _gpu
+
+
+class _Libs:
+    """One namespace over both libraries; the CUDA library is loaded on the first use of a rheo_gpu_* entry point, so a
+    process that only builds meshes or reads files (bench.py --impl reference, the oracle-only tests) never maps it."""
+
+    def __getattr__(self, name):
+        if name in GPU_SYMBOLS:
+            return getattr(gpu_lib(), name)
+        return getattr(host_lib(), name)
+
+
+_libs = _Libs()
+
+
+def lib() -> _Libs:
+    return _libs
 
 
 def lib_path() -> Path:
     return _LIB_PATH
+
+
+def host_lib_path() -> Path:
+    return _HOST_LIB_PATH

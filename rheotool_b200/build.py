@@ -1,8 +1,12 @@
-"""In-tree build of librheo_b200.so (host C++ + sm_100a CUDA) with plain nvcc/g++.
+"""In-tree build of the two shared libraries with plain nvcc/g++:
 
-The library is built next to this file so that it travels to the GPU box with the repo snapshot
-(git-ignored, not gpurun-ignored).  No JIT cache, no torch.utils.cpp_extension: the C-ABI has no
-torch types.
+  librheo_b200.so   the product: the sm_100a CUDA stress step behind include/rheo_gpu.h (csrc/gpu/*.cu) — needs a CUDA device
+  librheo_host.so   host services (csrc/host/*.cpp): blockMesh-lite mesh generator, decomposePar-style decomposition,
+                    synthetic fields, OpenFOAM file formats (include/rheo_mesh.h, include/rheo_io.h) — no CUDA in it, so the
+                    CPU reference arm of bench.py and the oracle-only tests never map the CUDA library
+
+Both are built next to this file so that they travel to the GPU box with the repo snapshot (git-ignored, not
+gpurun-ignored).  No JIT cache, no torch.utils.cpp_extension: the C-ABI has no torch types.
 """
 from __future__ import annotations
 
@@ -17,6 +21,7 @@ PKG = ROOT / "rheotool_b200"
 CSRC = PKG / "csrc"
 OBJ = ROOT / "build" / "obj"
 LIB = PKG / "librheo_b200.so"
+HOST_LIB = PKG / "librheo_host.so"
 
 NVCC = os.environ.get("RHEO_NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"   # the image's default CXX (/opt/gcc) has no OpenMP spec; system g++ 13 is complete
@@ -45,7 +50,7 @@ def _run(cmd: list[str]) -> None:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every source under csrc/ and link librheo_b200.so.  Returns the library path."""
+    """Compile every source under csrc/ and link librheo_b200.so and librheo_host.so.  Returns the path of the CUDA library."""
     if not Path(NVCC).exists():
         raise RuntimeError(f"nvcc not found at {NVCC}; the B200 stress-step library cannot be built")
     OBJ.mkdir(parents=True, exist_ok=True)
@@ -65,8 +70,15 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
             if verbose:
                 print(" ".join(cmd))
             _run(cmd)
-    if force or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in objs):
-        cmd = [NVCC, "-shared", "-ccbin", HOST_CXX, "-o", str(LIB), *map(str, objs), "-lcudart", "-ldl", "-lpthread", "-lz"]
+    gpu_objs = [o for o in objs if o.name.startswith("gpu__")]
+    host_objs = [o for o in objs if not o.name.startswith("gpu__")]
+    if force or not HOST_LIB.exists() or any(o.stat().st_mtime > HOST_LIB.stat().st_mtime for o in host_objs):
+        cmd = [HOST_CXX, "-shared", "-o", str(HOST_LIB), *map(str, host_objs), "-lpthread", "-lz"]
+        if verbose:
+            print(" ".join(cmd))
+        _run(cmd)
+    if force or not LIB.exists() or any(o.stat().st_mtime > LIB.stat().st_mtime for o in gpu_objs):
+        cmd = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOST_CXX, "-o", str(LIB), *map(str, gpu_objs), "-lcudart", "-ldl", "-lpthread"]
         if verbose:
             print(" ".join(cmd))
         _run(cmd)

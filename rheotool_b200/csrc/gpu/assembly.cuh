@@ -62,8 +62,11 @@ __host__ __device__ constexpr size_t tile_flux_bytes(int K) { return (size_t)K *
 //             velocity warp u: Gauss gradient of U_u;  warp g also writes A = min(F,0) of slot g.
 // KT = compile-time slot count (neighbour values stay in registers between the gradient and the face pass); KT = 0:
 // run-time K, the face pass re-reads the neighbour value (L1 hit).
+#ifndef RK_FLUX_MINB
+#define RK_FLUX_MINB 4   // resident CTAs per SM k_flux_assemble is compiled for (register cap 65536 / (288 * MINB))
+#endif
 template <int KT>
-__global__ void __launch_bounds__(TILE * 9, 4) k_flux_assemble(MeshView m, FluxArgs a, const unsigned char* __restrict__ tileRec, int nTiles) {
+__global__ void __launch_bounds__(TILE * 9, RK_FLUX_MINB) k_flux_assemble(MeshView m, FluxArgs a, const unsigned char* __restrict__ tileRec, int nTiles) {
     pdl_sync();
     extern __shared__ __align__(128) unsigned char smemRaw[];
     const int K = KT > 0 ? KT : m.K;

@@ -258,8 +258,11 @@ __device__ __forceinline__ void finalize_ctl(const double* partials, int nBlocks
 // gAverage(psi): the per-component sums of theta arrive in sumPsi (accumulated by k_cell_source2, assembly.cuh)
 // v = A psi (ghost columns included: psi halos are exchanged before), r = b - v, r0 = r
 // sums per RHS: [0] |v - xRef rowsum| + |b - xRef rowsum|, [1] |r|, [2] r.r
+#ifndef RK_INIT_MINB
+#define RK_INIT_MINB 2   // resident CTAs per SM k_krylov_init is compiled for
+#endif
 template <int NR, int KT>
-__global__ void __launch_bounds__(BLOCK) k_krylov_init(MeshView m, int nModes, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ A,
+__global__ void __launch_bounds__(BLOCK, RK_INIT_MINB) k_krylov_init(MeshView m, int nModes, RhsPtrs rp, const double* __restrict__ diag, const double* __restrict__ A,
                                                         const double* __restrict__ sumPsi, double nGlobal, double* __restrict__ r, double* __restrict__ r0v,
                                                         double* partials, double* out, unsigned* counter, int ctlWhat, KrylovShared* ks, SolveCtl sc) {
     pdl_sync();

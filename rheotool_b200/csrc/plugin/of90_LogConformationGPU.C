@@ -193,19 +193,40 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
         if (ctl_.cn_psi < 0 || ctl_.cn_psi > 1) FatalErrorInFunction << "CrankNicolson coefficient = " << ctl_.cn_psi << " should be >= 0 and <= 1" << exit(FatalError);
     }
     else FatalErrorInFunction << "ddtSchemes Euler, backward and CrankNicolson are available on the GPU path, not " << ddtName << exit(FatalError);
+    // the device hard-codes Gauss linear for grad(U) (boilerLog.H:1), for the per-component grad(theta) of phifDefC
+    // (gaussDefCmpwConvectionScheme.C:254) and for `linExtrapGrad` (linearExtrapolationFvPatchField.C:128)
+    {
+        const char* grads[] = {"grad(U)", "linExtrapGrad", "grad(theta)"};
+        for (const char* gname : grads)
+        {
+            ITstream& gs = mesh.gradScheme(gname);
+            const word g0(gs);
+            const word g1(gs.eof() ? word("") : word(gs));
+            if (g0 != "Gauss" || g1 != "linear")
+            {
+                FatalErrorInFunction << "gradSchemes entry for " << gname << " is `" << g0 << ' ' << g1
+                    << "`; the GPU stress step implements `Gauss linear` gradients only" << exit(FatalError);
+            }
+        }
+    }
     const dictionary& sol = mesh.solverDict(thetaName);
     const word solver(sol.lookup("solver"));
-    // PBiCG (what the tutorials select) and PBiCGStab converge to the same field; the device runs its tuned, multi-rank
-    // PBiCGStab path unless the solver dictionary asks for the device PBiCG path by name (`gpuSolver PBiCG;`, serial runs only)
-    ctl_.solver = RHEO_SOLVER_PBICGSTAB;
-    if (solver == "PBiCG" && word(sol.lookupOrDefault<word>("gpuSolver", "PBiCGStab")) == "PBiCG" && !Pstream::parRun())
+    // the solver fvSolution names is the solver that runs: PBiCG (what every Log tutorial selects) on one rank (pbicg.cuh),
+    // PBiCGStab on any number of ranks.  A decomposed PBiCG case is refused here instead of being solved differently.
+    if (solver == "PBiCGStab") ctl_.solver = RHEO_SOLVER_PBICGSTAB;
+    else if (solver == "PBiCG")
     {
+        if (Pstream::parRun())
+        {
+            FatalErrorInFunction << "fvSolution selects PBiCG for " << thetaName << "; on several ranks the GPU path implements "
+                << "PBiCGStab + DILU only (select `solver PBiCGStab;`)" << exit(FatalError);
+        }
         ctl_.solver = RHEO_SOLVER_PBICG;
     }
-    else if (solver != "PBiCGStab")
+    else
     {
-        WarningInFunction << "fvSolution selects " << solver << " for " << thetaName
-            << "; the GPU path solves with PBiCGStab + DILU (same tolerance, relTol, minIter, maxIter)" << endl;
+        FatalErrorInFunction << "fvSolution selects " << solver << " for " << thetaName
+            << "; the GPU path implements PBiCG and PBiCGStab (+ DILU)" << exit(FatalError);
     }
     ctl_.tolerance = sol.lookupOrDefault<scalar>("tolerance", 1e-6);
     ctl_.rel_tol   = sol.lookupOrDefault<scalar>("relTol", 0);
@@ -254,6 +275,25 @@ void LogConformationGPU::buildMeshDesc
             q.theta_bc = isA<zeroGradientFvPatchSymmTensorField>(tb) ? RHEO_BC_ZERO_GRADIENT : RHEO_BC_FIXED_VALUE;
             q.tau_bc = isA<linearExtrapolationFvPatchField<symmTensor>>(ub) ? RHEO_BC_LINEAR_EXTRAPOLATION
                      : isA<zeroGradientFvPatchSymmTensorField>(ub) ? RHEO_BC_ZERO_GRADIENT : RHEO_BC_FIXED_VALUE;
+            if (q.tau_bc == RHEO_BC_LINEAR_EXTRAPOLATION)
+            {
+                // useReg_ is private (linearExtrapolationFvPatchField.H:82) but write() prints it (.C:230): the device has
+                // the gradient branch (.C:101-151) only, so the regression branch (.C:152-219) is refused
+                OStringStream os;
+                ub.write(os);
+                const string txt(os.str());
+                const auto at = txt.find("useRegression");
+                if (at != string::npos)
+                {
+                    IStringStream is(txt.substr(at + 13));
+                    const Switch sw(is);
+                    if (sw)
+                    {
+                        FatalErrorInFunction << "patch " << p.name() << " of " << ta.name() << " sets useRegression true; the GPU stress "
+                            << "step implements the gradient branch of linearExtrapolation only" << exit(FatalError);
+                    }
+                }
+            }
         }
     }
     d.n_cells = mesh.nCells(); d.n_faces = nF; d.n_internal_faces = nI; d.n_patches = patches.size();
@@ -321,7 +361,21 @@ LogConformationGPU::LogConformationGPU
                                            mesh, dimensionedTensor("I", dimless, pTraits<tensor>::I), extrapolatedCalculatedFvPatchField<tensor>::typeName));
     }
     checkForStab(dict);                                                     // constitutiveEq.C:430-439
+    // the modes are batched on ONE matrix with ONE set of controls: every mode's schemes and solver entry must be identical
+    // (checked, not assumed: the reference lets thetaM1, thetaM2, ... have their own fvSchemes / fvSolution entries)
     readSchemes(mesh, "theta" + suffix[0]);
+    {
+        const RheoSchemeCtl first = ctl_;
+        for (label i = 1; i < suffix.size(); ++i)
+        {
+            readSchemes(mesh, "theta" + suffix[i]);
+            if (std::memcmp(&first, &ctl_, sizeof(RheoSchemeCtl)) != 0)
+            {
+                FatalErrorInFunction << "schemes / solver controls of theta" << suffix[i] << " differ from those of theta" << suffix[0]
+                    << "; the batched multiMode solve of the GPU path needs identical controls" << exit(FatalError);
+            }
+        }
+    }
 
     List<int32_t> owner, neighbour; List<RheoPatchDesc> patches; vectorField nbrC; scalarField weights;
     RheoMeshDesc d;
@@ -428,23 +482,23 @@ void LogConformationGPU::correct(const volScalarField* alpha, const volTensorFie
     // OpenFOAM-style solver report (SolverPerformance<symmTensor>)
     static const char* cmpt[6] = {"XX", "XY", "XZ", "YY", "YZ", "ZZ"};
     forAll(stats, i) for (int c = 0; c < 6; ++c) if (stats[i].n_iterations[c] || stats[i].initial_residual[c] > 0)
-        Info<< "B200-PBiCGStab:  Solving for " << theta_[i].name() << cmpt[c] << ", Initial residual = " << stats[i].initial_residual[c]
+        Info<< (ctl_.solver == RHEO_SOLVER_PBICG ? "B200-PBiCG:  Solving for " : "B200-PBiCGStab:  Solving for ") << theta_[i].name() << cmpt[c] << ", Initial residual = " << stats[i].initial_residual[c]
             << ", Final residual = " << stats[i].final_residual[c] << ", No Iterations " << stats[i].n_iterations[c] << endl;
 
-    // boundary values of tau for the momentum predictor (single mode: patch values from the device;
-    // multi-mode: extrapolated, as multiMode::tau() rebuilds them from the sum)
+    // boundary values of tau for the momentum predictor: the device returns the patch values SUMMED OVER THE MODES
+    // (RHEO_FIELD_TAU_B_TOTAL) — multiMode::divTau (multiMode.C) sums each mode's divTau, i.e. uses each mode's own
+    // linearExtrapolation / zeroGradient / fixedValue patch values
+    forAll(tauTotal_.boundaryField(), pI)
+    {
+        fvPatchSymmTensorField& pf = tauTotal_.boundaryFieldRef()[pI];
+        if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
+        forAll(pf, i) pf[i] = tauB[pf.patch().start() - nI + i];
+    }
     if (modes_.size() == 1)
     {
-        forAll(tauTotal_.boundaryField(), pI)
-        {
-            fvPatchSymmTensorField& pf = tauTotal_.boundaryFieldRef()[pI];
-            if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
-            forAll(pf, i) pf[i] = tauB[pf.patch().start() - nI + i];
-        }
         tau_[0].primitiveFieldRef() = tauTotal_.primitiveField();
         tau_[0].boundaryFieldRef() = tauTotal_.boundaryField();
     }
-    else tauTotal_.correctBoundaryConditions();
 
     if (U().time().writeTime())
     {

@@ -384,8 +384,8 @@ def mode_names(constitutive_properties, section: str = "parameters"):
 
 def read_schemes(case_dir, theta_name: str = "theta"):
     """system/fvSchemes + system/fvSolution -> RheoSchemeCtl, as the OpenFOAM shim reads them (of90_LogConformationGPU.C):
-    div(phi,theta) must be `GaussDefCmpw <limiter>`, ddt Euler or backward; the solver entry may select PBiCG (the device
-    runs PBiCGStab: reported in the second return value)."""
+    div(phi,theta) must be `GaussDefCmpw <limiter>`, ddt Euler / backward / CrankNicolson, gradSchemes Gauss linear; the solver
+    entry (PBiCG or PBiCGStab) is the solver that runs."""
     from . import cases
     case_dir = Path(case_dir)
     fs, sol = FoamDict(case_dir / "system" / "fvSchemes"), FoamDict(case_dir / "system" / "fvSolution")
@@ -405,11 +405,38 @@ def read_schemes(case_dir, theta_name: str = "theta"):
         ddt = "CrankNicolson"
     if ddt not in ("Euler", "backward", "CrankNicolson"):
         raise FoamError(f"{fs.path}: ddtSchemes Euler, backward and CrankNicolson are available, not {ddt}")
+    # the device hard-codes Gauss linear for grad(U) (boilerLog.H:1), for the per-component grad(theta) of phifDefC
+    # (gaussDefCmpwConvectionScheme.C:254) and for `linExtrapGrad` (linearExtrapolationFvPatchField.C:128): anything else in
+    # gradSchemes would silently differ from the reference
+    for key in ("gradSchemes/default", "gradSchemes/grad(U)", "gradSchemes/linExtrapGrad"):
+        g = fs.get(key)
+        if g is not None and g.split() != ["Gauss", "linear"]:
+            raise FoamError(f"{fs.path}: {key} is `{g}`; the stress step implements `Gauss linear` gradients only")
+    if fs.get("gradSchemes/default") is None and (fs.get("gradSchemes/grad(U)") is None or fs.get("gradSchemes/linExtrapGrad") is None):
+        raise FoamError(f"{fs.path}: gradSchemes needs `default Gauss linear` (or grad(U) and linExtrapGrad entries)")
     at = f"solvers/{theta_name}"
     solver = sol.get(f"{at}/solver")
     if solver is None:
         raise FoamError(f"{sol.path}: no solver entry for {theta_name}")
+    if solver not in abi.SOLVER:
+        raise FoamError(f"{sol.path}: solver {solver} for {theta_name}; the stress step implements {sorted(abi.SOLVER)} (+ DILU)")
     relax = sol.scalar(f"relaxationFactors/equations/{theta_name}", 0.0)
-    ctl = cases.scheme_ctl(tok[1], "PBiCGStab", sol.scalar(f"{at}/tolerance", 1e-6), sol.scalar(f"{at}/relTol", 0.0), int(sol.scalar(f"{at}/minIter", 0)),
+    # the solver the file names is the solver that runs: PBiCG (what the Log tutorials select) on one rank (pbicg.cuh),
+    # PBiCGStab on any number of ranks; a decomposed PBiCG case fails loudly at the first step instead of being substituted
+    ctl = cases.scheme_ctl(tok[1], solver, sol.scalar(f"{at}/tolerance", 1e-6), sol.scalar(f"{at}/relTol", 0.0), int(sol.scalar(f"{at}/minIter", 0)),
                            int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt, cn_psi=cn_psi)
     return ctl, solver
+
+
+def read_schemes_modes(case_dir, theta_names):
+    """multiMode: the modes are batched on ONE matrix with ONE set of controls, so every mode's schemes and solver entry
+    (thetaM1, thetaM2, ...) must be identical — checked here instead of applying the first mode's to all."""
+    first = None
+    for name in theta_names:
+        ctl, solver = read_schemes(case_dir, name)
+        key = tuple(getattr(ctl, f) for f, _ in abi.RheoSchemeCtl._fields_)
+        if first is None:
+            first = (key, ctl, solver, name)
+        elif key != first[0]:
+            raise FoamError(f"{case_dir}: schemes / solver controls of {name} differ from those of {first[3]}; the batched multiMode solve needs identical controls")
+    return first[1], first[2]

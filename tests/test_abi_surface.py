@@ -25,9 +25,14 @@ def declared_functions():
 def test_every_declared_symbol_is_exported_and_bound():
     decl = declared_functions()
     assert len(decl) >= 35
-    out = subprocess.run(["nm", "-D", "--defined-only", str(abi.lib_path())], capture_output=True, text=True, check=True).stdout
-    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
-    assert decl <= exported, f"declared but not exported: {sorted(decl - exported)}"
+    exported = {}
+    for path in (abi.lib_path(), abi.host_lib_path()):
+        out = subprocess.run(["nm", "-D", "--defined-only", str(path)], capture_output=True, text=True, check=True).stdout
+        exported[path.name] = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    gpu_decl = {n for n in decl if n.startswith("rheo_gpu_")}
+    assert gpu_decl <= exported["librheo_b200.so"], f"declared but not exported: {sorted(gpu_decl - exported['librheo_b200.so'])}"
+    assert decl - gpu_decl <= exported["librheo_host.so"], f"declared but not exported: {sorted(decl - gpu_decl - exported['librheo_host.so'])}"
+    assert not any(n.startswith("rheo_gpu_") for n in exported["librheo_host.so"]), "the host library holds no compute entry point"
     bound = set(abi.MESH_SYMBOLS) | set(abi.GPU_SYMBOLS) | set(abi.IO_SYMBOLS)
     assert decl == bound, f"header / ctypes mismatch: {sorted(decl ^ bound)}"
     lib = abi.lib()
@@ -39,6 +44,8 @@ def test_no_oracle_or_torch_in_the_product_library():
     """The product never links or loads the oracle (test infrastructure) nor torch."""
     out = subprocess.run(["ldd", str(abi.lib_path())], capture_output=True, text=True).stdout
     assert "liboracle" not in out and "torch" not in out and "libc10" not in out
+    host = subprocess.run(["ldd", str(abi.host_lib_path())], capture_output=True, text=True).stdout
+    assert "liboracle" not in host and "cudart" not in host and "libcuda" not in host, "librheo_host.so must not depend on CUDA"
     for src in (ROOT / "rheotool_b200").rglob("*"):
         if src.suffix in (".py", ".cu", ".cuh", ".cpp", ".hpp", ".inl") and src.is_file():
             txt = src.read_text()

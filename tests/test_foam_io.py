@@ -316,8 +316,9 @@ def test_case_dictionaries_of_the_reference_tutorials_give_models_and_schemes():
         if (case / "system" / "fvSchemes").exists() and "theta" in (case / "system" / "fvSchemes").read_text():
             try:
                 ctl, solver = foamio.read_schemes(case, "theta" + foamio.mode_names(cp)[0])
-            except foamio.FoamError as e:   # refused loudly: a time scheme the stress step does not have (steadyState)
-                assert "ddtSchemes" in str(e) and re.search(r"steadyState", (case / "system" / "fvSchemes").read_text())
+            except foamio.FoamError as e:   # refused loudly: a time scheme (steadyState) or a gradient scheme the stress step does not have
+                txt = (case / "system" / "fvSchemes").read_text()
+                assert ("ddtSchemes" in str(e) and re.search(r"steadyState", txt)) or ("gradSchemes" in str(e) and not re.search(r"default\s+Gauss linear;", txt)), str(e)
                 n_refused += 1
                 continue
             n_schemes += 1
@@ -335,4 +336,59 @@ def test_case_dictionaries_of_the_reference_tutorials_give_models_and_schemes():
     (m,) = foamio.read_models(REF / "rheoFoam/Cylinder/Oldroyd-BLog/constant/constitutiveProperties")
     assert (m.model, m.rho, m.etaS, m.etaP, m.lambda_) == (abi.MODEL_OLDROYD_B_LOG, 1.0, 0.59, 0.41, 0.7)
     ctl, solver = foamio.read_schemes(REF / "rheoFoam/Cylinder/Oldroyd-BLog")
-    assert ctl.limiter == abi.LIMITER["cubista"] and solver == "PBiCG" and ctl.ddt == abi.DDT_EULER
+    assert ctl.limiter == abi.LIMITER["cubista"] and solver == "PBiCG" and ctl.solver == abi.SOLVER["PBiCG"] and ctl.ddt == abi.DDT_EULER
+
+
+# ---- configurations the stress step does not implement are refused loudly, not run differently ------------------------
+_FOAM_HEAD = 'FoamFile\n{\n    version 2.0;\n    format ascii;\n    class %s;\n    object %s;\n}\n'
+
+
+def _write_case_dicts(case, grad_default="Gauss linear", solver="PBiCG", extra_theta=None):
+    (case / "system").mkdir(parents=True, exist_ok=True)
+    names = ["theta"] + (extra_theta or [])
+    div = "".join(f"    div(phi,{n}) GaussDefCmpw cubista;\n" for n in names)
+    (case / "system" / "fvSchemes").write_text(
+        _FOAM_HEAD % ("dictionary", "fvSchemes") + "ddtSchemes { default Euler; }\n" + f"gradSchemes {{ default {grad_default}; }}\n" + "divSchemes\n{\n" + div + "}\n")
+    sol = "".join(f"    {n} {{ solver {solver if n == 'theta' else 'PBiCGStab'}; preconditioner DILU; tolerance 1e-10; relTol 0; }}\n" for n in names)
+    (case / "system" / "fvSolution").write_text(_FOAM_HEAD % ("dictionary", "fvSolution") + "solvers\n{\n" + sol + "}\n")
+
+
+def test_schemes_the_device_does_not_implement_are_refused(tmp_path):
+    """gradSchemes other than Gauss linear, per-mode controls that differ, unknown solvers — an error naming the
+    entry, never a silent substitution; the solver named in fvSolution (PBiCG in every Log tutorial) is the solver that runs."""
+    _write_case_dicts(tmp_path / "ok")
+    ctl, solver = foamio.read_schemes(tmp_path / "ok")
+    assert solver == "PBiCG" and ctl.solver == abi.SOLVER["PBiCG"]
+    _write_case_dicts(tmp_path / "lsq", grad_default="leastSquares")
+    with pytest.raises(foamio.FoamError, match="gradSchemes/default is `leastSquares`"):
+        foamio.read_schemes(tmp_path / "lsq")
+    _write_case_dicts(tmp_path / "gamg", solver="GAMG")
+    with pytest.raises(foamio.FoamError, match="solver GAMG"):
+        foamio.read_schemes(tmp_path / "gamg")
+    _write_case_dicts(tmp_path / "mm", extra_theta=["thetaM2"])
+    with pytest.raises(foamio.FoamError, match="differ from those of theta"):
+        foamio.read_schemes_modes(tmp_path / "mm", ["theta", "thetaM2"])
+    _write_case_dicts(tmp_path / "mm2", solver="PBiCGStab", extra_theta=["thetaM2"])
+    ctl, solver = foamio.read_schemes_modes(tmp_path / "mm2", ["theta", "thetaM2"])
+    assert solver == "PBiCGStab"
+
+
+def test_linear_extrapolation_with_regression_is_refused(tmp_path):
+    """linearExtrapolationFvPatchField.C:72,118,152-219: `useRegression true` selects the least-squares branch, which the
+    device does not have — the case reader says so instead of extrapolating with the gradient branch."""
+    spec = cases.by_name("C3", 2 / 19)
+    m = mesh.tensor_grid(spec.grid)
+    n = m.n_cells
+    zeros6 = np.zeros((n, 6))
+    U, Ub, phi, th = m.synth_fields(spec.synth)
+    foamio.write_case(tmp_path, m, "0", th, zeros6, U, Ub)
+    f = foamio.FoamField(tmp_path / "0" / "tau")
+    f.apply_bcs(m, "tau")   # as written: plain linearExtrapolation on the walls
+    txt = (tmp_path / "0" / "tau").read_text()
+    assert "linearExtrapolation" in txt
+    (tmp_path / "0" / "tau").write_text(txt.replace("type linearExtrapolation;", "type linearExtrapolation; useRegression true;", 1)
+                                        if "type linearExtrapolation;" in txt else
+                                        txt.replace("linearExtrapolation;", "linearExtrapolation;\n        useRegression   true;", 1))
+    f2 = foamio.FoamField(tmp_path / "0" / "tau")
+    with pytest.raises(foamio.FoamError, match="useRegression true"):
+        f2.apply_bcs(m, "tau")

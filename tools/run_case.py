@@ -46,9 +46,8 @@ def main():
     else:
         cp = case / "constant" / "constitutiveProperties"
         models, names = foamio.read_models(cp), [a.name + n for n in foamio.mode_names(cp)]
-        schemes, solver = foamio.read_schemes(case, "theta" + names[0])
-        if solver != "PBiCGStab":
-            print(f"fvSolution selects {solver}; the GPU path solves with PBiCGStab + DILU (same controls)")
+        schemes, solver = foamio.read_schemes_modes(case, ["theta" + n[len(a.name):] if a.name else "theta" + n for n in names])
+        print(f"fvSolution selects {solver} + DILU for theta: that is the solver the device runs")
     m, f = foamio.read_case(case, a.time, names[0])
     per_mode = [f] + [foamio.read_case(case, a.time, n)[1] for n in names[1:]]
     g = GpuStressModel(m, models, schemes, 0)
