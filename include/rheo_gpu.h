@@ -70,6 +70,8 @@ extern "C" {
 
 #define RHEO_DDT_CRANK_NICOLSON 2   /* EXT-OF9 CrankNicolsonDdtScheme `CrankNicolson <psi>` (tutorial Cavity/Oldroyd-BLog/system/fvSchemes:
                                       `CrankNicolson 1`): ddt0-field formulation on a fresh start (first step Euler), cn_psi = off-centring */
+#define RHEO_DDT_STEADY_STATE 3      /* EXT-OF9 steadyStateDdtScheme: fvm::ddt contributes nothing (tutorials rheoFilmFoam/UCM/system/fvSchemes:
+                                      `default steadyState`); used with relaxationFactors.equations.theta < 1 and `bounded` convection */
 #define RHEO_SOLVER_PBICGSTAB 0
 #define RHEO_SOLVER_PBICG     1
 
@@ -102,6 +104,9 @@ typedef struct RheoSchemeCtl {
     int32_t max_iter;
     double  relax;          /* relaxationFactors.equations.theta; <= 0 : relax() is a no-op */
     double  cn_psi;         /* CrankNicolson off-centring coefficient psi in [0,1] (1 = Crank-Nicolson, 0 = Euler); other ddt: unused */
+    int32_t bounded;        /* divSchemes `bounded GaussDefCmpw <limiter>` (EXT-OF9 boundedConvectionScheme: fvmDiv - fvm::Sp(div(phi)),
+                               rheoFilmFoam/UCM/system/fvSchemes:35): the net outflow of the cell is taken off the diagonal */
+    int32_t pad_;
 } RheoSchemeCtl;
 
 /* mirrors OpenFOAM SolverPerformance<symmTensor> per mode */
@@ -149,6 +154,13 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
  * phi [n_faces] (internal then boundary; faces of empty patches are neither read nor copied — OpenFOAM's
  * emptyFvPatchField has size 0, so the shim has nothing to put there).  Pageable or pinned host memory. */
 int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi);
+
+/* Temperature-dependent relaxation time and polymer viscosity (Oldroyd_BLog.C:133-135 and the same lines of GiesekusLog,
+ * PTTLog, FENE-PLog, FENE-CRLog, WhiteMetznerCYLog: `lambda = thermoLambdaPtr_->createField(lambda_)`): per-cell values
+ * lambda_cell[n_cells], etaP_cell[n_cells] in the caller's numbering replace the scalars of RheoModelDesc for `mode`; the caller
+ * evaluates the thermoFunction (include/rheo_mesh.h: rheo_thermo_factor restates Arrhenius / ArrheniusModified / WLF / VFT).
+ * NULL, NULL restores the scalar parameters.  Call again whenever T has changed. */
+int rheo_gpu_upload_thermo(RheoGpu* h, int32_t mode, const double* lambda_cell, const double* etaP_cell);
 
 int rheo_gpu_store_old_time(RheoGpu* h);
 /* Off by default.  Alternative reading of `tau_ = ...` (Oldroyd_BLog.C:176 and the same line of the other models) before

@@ -151,6 +151,15 @@ int rheo_mesh_colour_renumber(const RheoHostMesh* m, int32_t* perm, int32_t* col
  * (the device then falls back to rheo_mesh_colour_renumber's ordering), < 0 on error. */
 int rheo_mesh_block_renumber(const RheoHostMesh* m, int32_t* perm, int32_t* colour_start, int32_t* tile3);
 
+/* ---- thermoFunctions (of90/src/libs/thermo/thermoFunctions/): factor a_T(T) that multiplies lambda / etaP --------- */
+#define RHEO_THERMO_CONSTANT           0   /* Constant: 1                                                         */
+#define RHEO_THERMO_ARRHENIUS          1   /* Arrhenius.C:67:          exp(alpha (1/T - 1/T0));     p = {alpha, T0}   */
+#define RHEO_THERMO_ARRHENIUS_MODIFIED 2   /* ArrheniusModified.C:67:  exp(-alpha (T - T0));        p = {alpha, T0}   */
+#define RHEO_THERMO_WLF                3   /* WLF.C:67:                10^(-c1 (T - T0) / (c2 + (T - T0))); p = {c1, c2, T0} */
+#define RHEO_THERMO_VFT                4   /* VFT.C:68:                10^(B + A / (T - T0));       p = {A, B, T0}    */
+/* out[i] = a_T(T[i]) for n cells; returns non-zero for an unknown kind */
+int rheo_thermo_factor(int32_t kind, const double* params3, int64_t n, const double* T, double* out);
+
 /* ---- synthetic benchmark fields ------------------------------------------------ */
 #define RHEO_FLOW_CONTRACTION_2D 0  /* psi = Q g(y/h(x)), h: H_up -> H_down, no-slip/no-penetration walls */
 #define RHEO_FLOW_VORTEX         1  /* Psi_z = A sin(pi x^) sin(pi y^) (1 + 0.3 sin(pi z^)) on the bounding box */

@@ -109,6 +109,14 @@ struct Mode {
     dvec theta, thetaOld, thetaOldOld, tau, eigVals, eigVecs, thetaB, tauB;
     dvec ddt0;                // CrankNicolson: the scheme's ddt0 field (EXT-OF9 CrankNicolsonDdtScheme::ddt0_)
     int ddt0TimeIndex = 0;    //                 time step at which ddt0 was last evaluated
+    dvec lambdaCell, etaPCell;   // thermo-dependent lambda / etaP per cell (Oldroyd_BLog.C:133-135: createField); empty = the scalars
+    // the model with this cell's lambda / etaP
+    Model at(int c) const {
+        if (lambdaCell.empty()) return model;
+        Model q = model;
+        q.d.lambda = lambdaCell[c]; q.d.etaP = etaPCell[c];
+        return q;
+    }
 };
 
 struct Rank {
@@ -735,7 +743,7 @@ Perf pbicg(Ldu& A, DVec& psi, const DVec& source, const RheoSchemeCtl& ctl) {
 int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
     const int R = (int)cs.ranks.size();
     const RheoSchemeCtl& ctl = cs.ctl;
-    if (ctl.ddt != RHEO_DDT_EULER && ctl.ddt != RHEO_DDT_BACKWARD && ctl.ddt != RHEO_DDT_CRANK_NICOLSON) { g_err = "oracle: only the Euler, backward and CrankNicolson ddt schemes are restated"; return 3; }
+    if (ctl.ddt != RHEO_DDT_EULER && ctl.ddt != RHEO_DDT_BACKWARD && ctl.ddt != RHEO_DDT_CRANK_NICOLSON && ctl.ddt != RHEO_DDT_STEADY_STATE) { g_err = "oracle: only the Euler, backward, CrankNicolson and steadyState ddt schemes are restated"; return 3; }
     double aL[3] = {1, 1, 1}, bL[3] = {0, 0, 0}, bnd[2] = {1, 1};
     const bool hrs = limiter_table(ctl.limiter, aL, bL, bnd);
     const bool noConv = (ctl.limiter == RHEO_LIMITER_NONE);
@@ -767,7 +775,10 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             std::memcpy(L.v, &rk.L[(size_t)9 * c], 72);
             std::memcpy(Rm.v, &mo.eigVecs[(size_t)9 * c], 72);
             std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
-            rk.fFene[c] = model_rhs_cell(mo.model, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c], &mo.tau[(size_t)6 * c]);
+            Model tmp;
+            const Model* pm = &mo.model;
+            if (!mo.lambdaCell.empty()) { tmp = mo.at(c); pm = &tmp; }
+            rk.fFene[c] = model_rhs_cell(*pm, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c], &mo.tau[(size_t)6 * c]);
         }
     });
 
@@ -820,6 +831,8 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
                 for (int q = 0; q < 6; ++q)
                     rk.source[(size_t)6 * c + q] = (rDtCoef * mo.thetaOld[(size_t)6 * c + q] + off * mo.ddt0[(size_t)6 * c + q]) * m.V[c];
             }
+        } else if (ctl.ddt == RHEO_DDT_STEADY_STATE) {
+            // EXT-OF9 steadyStateDdtScheme<Type>::fvmDdt: an empty matrix (diag 0, source 0)
         } else
         for (int c = 0; c < n; ++c) {
             rk.diag[c] = rDeltaT * m.V[c];
@@ -834,6 +847,18 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             }
             for (int f = 0; f < m.nInt; ++f) { ddiag[m.own[f]] -= rk.lower[f]; ddiag[m.nei[f]] -= rk.upper[f]; }   // negSumDiag
             for (int c = 0; c < n; ++c) rk.diag[c] += ddiag[c];
+            if (ctl.bounded) {
+                // EXT-OF9 boundedConvectionScheme<Type>::fvmDiv: scheme.fvmDiv(phi, vf) - fvm::Sp(fvc::surfaceIntegrate(phi), vf);
+                // fvm::Sp(sp, vf): diag += V sp, and V surfaceIntegrate(phi) = sum of the outward face fluxes of the cell
+                // (internal faces in face order, then the patches: EXT-OF9 fvc::surfaceIntegrate; empty patches hold no faces)
+                dvec net(n, 0.0);
+                for (int f = 0; f < m.nInt; ++f) { net[m.own[f]] += rk.phi[f]; net[m.nei[f]] -= rk.phi[f]; }
+                for (const Patch& p : m.patches) {
+                    if (p.type == RHEO_PATCH_EMPTY) continue;
+                    for (int f = p.start; f < p.start + p.size; ++f) net[m.own[f]] += rk.phi[f];
+                }
+                for (int c = 0; c < n; ++c) rk.diag[c] -= net[c];
+            }
             for (const Patch& p : m.patches) {
                 if (p.type == RHEO_PATCH_EMPTY) continue;
                 for (int f = p.start; f < p.start + p.size; ++f) {
@@ -1003,7 +1028,10 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             T9 Rm, Lam;
             std::memcpy(Rm.v, &mo.eigVecs[(size_t)9 * c], 72);
             std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
-            tau_cell(mo.model, Rm, Lam, rk.fFene[c], &mo.tau[(size_t)6 * c]);
+            Model tmp;
+            const Model* pm = &mo.model;
+            if (!mo.lambdaCell.empty()) { tmp = mo.at(c); pm = &tmp; }
+            tau_cell(*pm, Rm, Lam, rk.fFene[c], &mo.tau[(size_t)6 * c]);
         }
     });
     // tau BCs: processor values first (all sends complete before any evaluate), then the physical
@@ -1179,6 +1207,18 @@ int orc_set_state(void* h, int rank, int mode, const double* theta, const double
                 for (int f = p.start; f < p.start + p.size; ++f)
                     for (int q = 0; q < 6; ++q) mo.tauB[6 * (size_t)(f - rk.mesh.nInt) + q] = mo.tau[6 * (size_t)rk.mesh.own[f] + q];
     }
+    return 0;
+}
+
+// thermo-dependent lambda / etaP per cell (NULL, NULL: back to the scalars of the model)
+int orc_set_thermo(void* h, int rank, int mode, const double* lambdaCell, const double* etaPCell) {
+    Case& cs = *(Case*)h;
+    if (rank < 0 || rank >= (int)cs.ranks.size() || mode < 0 || mode >= (int)cs.ranks[rank].modes.size()) { g_err = "orc_set_thermo: bad rank/mode"; return 1; }
+    Mode& mo = cs.ranks[rank].modes[mode];
+    const int n = cs.ranks[rank].mesh.nCells;
+    if (!lambdaCell || !etaPCell) { mo.lambdaCell.clear(); mo.etaPCell.clear(); return 0; }
+    mo.lambdaCell.assign(lambdaCell, lambdaCell + n);
+    mo.etaPCell.assign(etaPCell, etaPCell + n);
     return 0;
 }
 

@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
             "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
             "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_model_rhs_tau": (None, [P, I, P, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
-            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]),
+            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -90,6 +90,12 @@ class OracleCase:
     def set_velocity(self, rank, U, Ub, phi):
         keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (U, Ub, phi)]
         lib().orc_set_velocity(self._h, rank, *[_p(a) for a in keep])
+
+    def set_thermo(self, rank, mode, lambda_cell=None, etaP_cell=None):
+        """Per-cell lambda / etaP (thermo-dependent parameters, Oldroyd_BLog.C:133-135); None restores the scalars."""
+        keep = [None if a is None else np.ascontiguousarray(a, dtype=np.float64) for a in (lambda_cell, etaP_cell)]
+        if lib().orc_set_thermo(self._h, rank, mode, _p(keep[0]), _p(keep[1])):
+            raise RuntimeError(lib().orc_last_error().decode())
 
     def set_tau_assignment(self, on: bool):
         """Alternative reading of `tau_ = ...` before tau_.correctBoundaryConditions() (oracle.cpp: Case::tauAssign)."""

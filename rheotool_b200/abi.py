@@ -19,7 +19,8 @@ BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSO
 MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG, MODEL_SARAMITO_LOG = 0, 1, 2, 3, 4, 5, 6, 7, 8
 PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
 LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}
-DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON = 0, 1, 2
+DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON, DDT_STEADY_STATE = 0, 1, 2, 3
+THERMO = {"Constant": 0, "Arrhenius": 1, "ArrheniusModified": 2, "WLF": 3, "VFT": 4}   # thermoFunctions/* type names
 SOLVER = {"PBiCGStab": 0, "PBiCG": 1}
 FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD, FIELD_TAU_B_TOTAL = range(9)
 FLOW_CONTRACTION_2D, FLOW_VORTEX, FLOW_CONTRACTION_3D = 0, 1, 2
@@ -78,7 +79,7 @@ class RheoModelDesc(C.Structure):
 class RheoSchemeCtl(C.Structure):
     _fields_ = [("limiter", C.c_int32), ("ddt", C.c_int32), ("solver", C.c_int32), ("tolerance", C.c_double),
                 ("rel_tol", C.c_double), ("min_iter", C.c_int32), ("max_iter", C.c_int32), ("relax", C.c_double),
-                ("cn_psi", C.c_double)]
+                ("cn_psi", C.c_double), ("bounded", C.c_int32), ("pad_", C.c_int32)]
 
 
 class RheoStepStats(C.Structure):
@@ -103,6 +104,7 @@ MESH_SYMBOLS = {
     "rheo_mesh_colour_renumber": (C.c_int, [_P, _P, _P, _P]),
     "rheo_mesh_block_renumber": (C.c_int, [_P, _P, _P, _P]),
     "rheo_synth_fields": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "rheo_thermo_factor": (C.c_int, [_I, _P, C.c_int64, _P, _P]),
     "rheo_mesh_max_courant_rate": (_D, [_P, _P]),
     "rheo_mesh_last_error": (C.c_char_p, []),
 }
@@ -114,6 +116,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_comm_init": (C.c_int, [_P, _I, _I, _P]),
     "rheo_gpu_upload_state": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P]),
     "rheo_gpu_upload_velocity": (C.c_int, [_P, _P, _P, _P]),
+    "rheo_gpu_upload_thermo": (C.c_int, [_P, _I, _P, _P]),
     "rheo_gpu_store_old_time": (C.c_int, [_P]),
     "rheo_gpu_set_tau_assignment": (C.c_int, [_P, C.c_int32]),
     "rheo_gpu_step": (C.c_int, [_P, _D, _P]),

@@ -95,6 +95,7 @@ struct ModeDev {
     DevBuf ddt0;              // CrankNicolson: the scheme's ddt0 field (6 planes)
     int ddt0TimeIndex = 0;    //                 time step at which ddt0 was last evaluated
     DevBuf corr;   // [nComp][K*NS] deferred face values received from the upwind neighbours (assembly.cuh)
+    DevBuf lamCell, etaCell;   // thermo-dependent lambda / etaP per cell (rheo_gpu_upload_thermo); unallocated: the scalars of desc
 };
 
 struct HaloSeg { int nbrRank, h0, len; };
@@ -801,12 +802,13 @@ template <class Kern> int flux_grid(RheoGpu* h, Kern kern, int threads, size_t s
 
 int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
-    if (h->ctl.ddt != RHEO_DDT_EULER && h->ctl.ddt != RHEO_DDT_BACKWARD && h->ctl.ddt != RHEO_DDT_CRANK_NICOLSON)
-        return fail("rheo_gpu_step: only the Euler, backward and CrankNicolson ddt schemes are implemented");
+    if (h->ctl.ddt != RHEO_DDT_EULER && h->ctl.ddt != RHEO_DDT_BACKWARD && h->ctl.ddt != RHEO_DDT_CRANK_NICOLSON && h->ctl.ddt != RHEO_DDT_STEADY_STATE)
+        return fail("rheo_gpu_step: the Euler, backward, CrankNicolson and steadyState ddt schemes are implemented");
+    const bool steady = h->ctl.ddt == RHEO_DDT_STEADY_STATE;   // EXT-OF9 steadyStateDdtScheme::fvmDdt: no diagonal, no source
     if (h->ctl.ddt == RHEO_DDT_CRANK_NICOLSON && !(h->ctl.cn_psi >= 0 && h->ctl.cn_psi <= 1)) return fail("CrankNicolson coefficient should be >= 0 and <= 1");
     // EXT-OF9 backwardDdtScheme::fvmDdt: deltaT0 = great while the field has < 2 old times (first step = Euler)
     h->dtNow = dt;
-    double ddtDiag = 1.0 / dt, c0 = 1.0, c00 = 0.0;
+    double ddtDiag = steady ? 0.0 : 1.0 / dt, c0 = 1.0, c00 = 0.0;
     const bool backward = h->ctl.ddt == RHEO_DDT_BACKWARD;
     if (backward) {
         const double deltaT0 = h->nOldTimes < 2 ? 1e15 : h->dt0;
@@ -848,7 +850,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     }
     const int N = h->N, NP = h->NP, grid = cdiv(N, BLOCK);
     const int nModes = (int)h->modes.size();
-    const double rDeltaT = 1.0 / dt;
+    const double rDeltaT = steady ? 0.0 : 1.0 / dt;
     const int noConv = h->ctl.limiter == RHEO_LIMITER_NONE;
     CompList cl;
     cl.n = h->nComp;
@@ -887,6 +889,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 FluxArgs fa;
                 fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = ddtDiag; fa.relax = h->ctl.relax;
                 fa.writeMatrix = mi == 0 ? 1 : 0;
+                fa.bounded = h->ctl.bounded ? 1 : 0;
                 fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
                 fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
                 fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>(); fa.FsT = pbicg ? h->d_FsT.as<double>() : nullptr;
@@ -894,10 +897,20 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 fa.gradU = h->d_gradU.as<double>();
                 const int threads = TILE * (cl.n + fa.nU);
                 const unsigned char* rec = h->d_tileRec.as<unsigned char>();
-                switch (h->K) {
-                    case 4: LAUNCH_SM(h, (k_flux_assemble<4>), flux_grid(h, k_flux_assemble<4>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
-                    case 6: LAUNCH_SM(h, (k_flux_assemble<6>), flux_grid(h, k_flux_assemble<6>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
-                    default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                static const bool oldFlux = !(getenv("RHEO_FLUX") && getenv("RHEO_FLUX")[0] == '2');   // RHEO_FLUX=2: the phase-split mapping (k_flux_assemble2: measured 13 % slower, kept for A/B runs)
+                if (oldFlux) {
+                    switch (h->K) {
+                        case 4: LAUNCH_SM(h, (k_flux_assemble<4>), flux_grid(h, k_flux_assemble<4>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                        case 6: LAUNCH_SM(h, (k_flux_assemble<6>), flux_grid(h, k_flux_assemble<6>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                        default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                    }
+                } else {
+                    const size_t sm2 = fluxSmem + flux2_extra_bytes<0>(h->K, cl.n);
+                    switch (h->K) {
+                        case 4: LAUNCH_SM(h, (k_flux_assemble2<4>), flux_grid(h, k_flux_assemble2<4>, threads, sm2), threads, sm2, h->mv, fa, rec, h->nTiles); break;
+                        case 6: LAUNCH_SM(h, (k_flux_assemble2<6>), flux_grid(h, k_flux_assemble2<6>, threads, sm2), threads, sm2, h->mv, fa, rec, h->nTiles); break;
+                        default: LAUNCH_SM(h, (k_flux_assemble2<0>), flux_grid(h, k_flux_assemble2<0>, threads, sm2), threads, sm2, h->mv, fa, rec, h->nTiles); break;
+                    }
                 }
                 SourceArgs sa;
                 sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.backward = (backward || crankNicolson) ? 1 : 0; sa.c0 = c0; sa.c00 = c00;
@@ -907,6 +920,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
                 sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
                 sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>(); sa.tau = md.tau.as<double>();
+                sa.lamCell = md.lamCell.as<double>(); sa.etaCell = md.etaCell.as<double>();
                 sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
                 const int srcGrid = std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms);
                 switch (md.mp.model) {
@@ -978,7 +992,8 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     // ---- eig + exp + tau
     for (ModeDev& md : h->modes)
     {
-#define RK_EIG(M) LAUNCH(h, (k_eig_tau<M>), grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>())
+#define RK_EIG(M) LAUNCH(h, (k_eig_tau<M>), grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>(), \
+                         md.lamCell.as<double>(), md.etaCell.as<double>())
         switch (md.mp.model) {
             case RHEO_MODEL_OLDROYD_B_LOG: RK_EIG(RHEO_MODEL_OLDROYD_B_LOG); break;
             case RHEO_MODEL_GIESEKUS_LOG: RK_EIG(RHEO_MODEL_GIESEKUS_LOG); break;
@@ -1115,7 +1130,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev})
         b->release();
     for (ModeDev& md : h->modes)
-        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0}) b->release();
+        for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0, &md.lamCell, &md.etaCell}) b->release();
     if (h->h_ks) cudaFreeHost(h->h_ks);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -1191,6 +1206,24 @@ int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, con
     }
     LAUNCH(h, k_phi_in, cdiv(h->nF, BLOCK), BLOCK, h->nF, h->d_faceOld.as<int>(), h->d_stage.as<double>(), h->d_phi.as<double>());
     LAUNCH(h, k_flux_ell, cdiv(h->N, BLOCK), BLOCK, h->mv, h->d_phi.as<double>(), h->d_Fell.as<double>());
+    return 0;
+}
+
+int rheo_gpu_upload_thermo(RheoGpu* h, int32_t mode, const double* lambda_cell, const double* etaP_cell) {
+    if (!h || mode < 0 || mode >= (int)h->modes.size()) return fail("rheo_gpu_upload_thermo: bad handle/mode");
+    if ((lambda_cell == nullptr) != (etaP_cell == nullptr)) return fail("rheo_gpu_upload_thermo: pass both lambda and etaP per cell, or neither");
+    CK(cudaSetDevice(h->device));
+    ModeDev& md = h->modes[mode];
+    if (!lambda_cell) {
+        CK(cudaStreamSynchronize(h->stream));
+        md.lamCell.release(); md.etaCell.release();
+        return 0;
+    }
+    if (!md.lamCell.p && (md.lamCell.alloc((size_t)h->NP * sizeof(double)) || md.etaCell.alloc((size_t)h->NP * sizeof(double)))) return 1;
+    if (put_cells(h, lambda_cell, 1, md.lamCell.as<double>())) return 1;
+    CK(cudaStreamSynchronize(h->stream));   // the staging buffer is reused by the next copy
+    if (put_cells(h, etaP_cell, 1, md.etaCell.as<double>())) return 1;
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
 }
 

@@ -296,10 +296,12 @@ struct KrylovCtl {   // one per RHS, device resident
 // ---------------------------------------------------------------- eig + exp + tau
 template <int MODEL>
 __global__ void __launch_bounds__(BLOCK) k_eig_tau(int N, int NP, ModelParams mp, const double* __restrict__ theta, const double* __restrict__ fFene,
-                                                    double* __restrict__ lam, double* __restrict__ R, double* __restrict__ tau) {
+                                                    double* __restrict__ lam, double* __restrict__ R, double* __restrict__ tau,
+                                                    const double* __restrict__ lamCell, const double* __restrict__ etaCell) {
     pdl_sync();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
+    if (lamCell) { mp.lambda = lamCell[c]; mp.etaP = etaCell[c]; }   // thermo-dependent parameters (Oldroyd_BLog.C:133-135)
     double th[6], d[3], V[9], l[3], t6[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) th[k] = theta[(size_t)k * NP + c];

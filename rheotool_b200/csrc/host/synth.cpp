@@ -139,3 +139,21 @@ extern "C" int rheo_synth_fields(const RheoHostMesh* m, const RheoSynthSpec* spe
     }
     return 0;
 }
+
+// thermoFunctions of the reference (of90/src/libs/thermo/thermoFunctions/{Arrhenius,ArrheniusModified,WLF,VFT,Constant}): the
+// factor that createField() / multiply() apply to lambda and etaP
+extern "C" int rheo_thermo_factor(int32_t kind, const double* p, int64_t n, const double* T, double* out) {
+    if (!out || (n > 0 && !T && kind != RHEO_THERMO_CONSTANT) || (kind != RHEO_THERMO_CONSTANT && !p)) return 1;
+    for (int64_t i = 0; i < n; ++i) {
+        switch (kind) {
+            case RHEO_THERMO_CONSTANT: out[i] = 1.0; break;
+            case RHEO_THERMO_ARRHENIUS: out[i] = std::exp(p[0] * (1. / T[i] - 1. / p[1])); break;
+            case RHEO_THERMO_ARRHENIUS_MODIFIED: out[i] = std::exp(-p[0] * (T[i] - p[1])); break;
+            case RHEO_THERMO_WLF: out[i] = std::pow(10.0, -p[0] * (T[i] - p[2]) / (p[1] + (T[i] - p[2]))); break;
+            case RHEO_THERMO_VFT: out[i] = std::pow(10.0, p[1] + p[0] / (T[i] - p[2])); break;
+            default: return 2;
+        }
+    }
+    return 0;
+}
+

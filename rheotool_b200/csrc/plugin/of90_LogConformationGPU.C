@@ -161,12 +161,11 @@ void LogConformationGPU::readMode(const word& type, const dictionary& dict, Rheo
     {
         FatalErrorInFunction << "Unknown GPU constitutiveEq type " << type << exit(FatalError);
     }
-    // thermoLambda / thermoEta sub-dictionaries: only the Constant function (the default when absent,
-    // thermo/thermoFunctions/thermoFunction/newThermoFunction.C:39-41) is supported on the device
-    if (dict.found("thermoLambda") || dict.found("thermoEta"))
-    {
-        FatalErrorInFunction << "temperature-dependent lambda/etaP are not available on the GPU path" << exit(FatalError);
-    }
+    // thermoLambda / thermoEta sub-dictionaries (Oldroyd_BLog.C:118-119): the thermoFunction objects stay on the host — they
+    // need the T field — and correct() uploads lambda(T), etaP(T) per cell (rheo_gpu_upload_thermo)
+    thermoLambda_.append(thermoFunction::New("thermoLambda", U().mesh(), dict).ptr());
+    thermoEta_.append(thermoFunction::New("thermoEta", U().mesh(), dict).ptr());
+    if (dict.found("thermoLambda") || dict.found("thermoEta")) hasThermo_ = true;
 }
 
 void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
@@ -174,7 +173,7 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     std::memset(&ctl_, 0, sizeof(ctl_));
     ITstream& div = mesh.divScheme("div(phi," + thetaName + ")");
     word w(div);
-    if (w == "bounded") FatalErrorInFunction << "bounded GaussDefCmpw is not available on the GPU path" << exit(FatalError);
+    if (w == "bounded") { ctl_.bounded = 1; w = word(div); }   // EXT-OF9 boundedConvectionScheme: fvmDiv - fvm::Sp(div(phi))
     if (w != "GaussDefCmpw") FatalErrorInFunction << "div(phi," << thetaName << ") must be GaussDefCmpw" << exit(FatalError);
     const word lim(div);
     const char* names[] = {"upwind", "cubista", "minmod", "smart", "waceb", "superbee", "none"};   // limiters.H:48-98
@@ -183,6 +182,7 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     const word ddtName(mesh.ddtScheme("ddt(" + thetaName + ")"));
     if (ddtName == "Euler") ctl_.ddt = RHEO_DDT_EULER;
     else if (ddtName == "backward") ctl_.ddt = RHEO_DDT_BACKWARD;
+    else if (ddtName == "steadyState") ctl_.ddt = RHEO_DDT_STEADY_STATE;
     else if (ddtName == "CrankNicolson")
     {
         // `CrankNicolson <psi>`: the stream returned by ddtScheme() still holds the off-centring coefficient
@@ -192,7 +192,7 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
         ctl_.cn_psi = is.eof() ? 1 : readScalar(is);
         if (ctl_.cn_psi < 0 || ctl_.cn_psi > 1) FatalErrorInFunction << "CrankNicolson coefficient = " << ctl_.cn_psi << " should be >= 0 and <= 1" << exit(FatalError);
     }
-    else FatalErrorInFunction << "ddtSchemes Euler, backward and CrankNicolson are available on the GPU path, not " << ddtName << exit(FatalError);
+    else FatalErrorInFunction << "ddtSchemes Euler, backward, CrankNicolson and steadyState are available on the GPU path, not " << ddtName << exit(FatalError);
     // the device hard-codes Gauss linear for grad(U) (boilerLog.H:1), for the per-component grad(theta) of phifDefC
     // (gaussDefCmpwConvectionScheme.C:254) and for `linExtrapGrad` (linearExtrapolationFvPatchField.C:128)
     {
@@ -470,6 +470,18 @@ void LogConformationGPU::correct(const volScalarField* alpha, const volTensorFie
     // theta_.oldTime() bookkeeping of fvm::ddt (Oldroyd_BLog.C:143): once per time step, not per inner iteration
     const bool newStep = U().time().timeIndex() != lastTimeIndex_;
     lastTimeIndex_ = U().time().timeIndex();
+
+    // temperature-dependent lambda / etaP (Oldroyd_BLog.C:133-135): evaluated here with the reference's own thermoFunction
+    // objects, one scalar per cell and mode to the device
+    if (hasThermo_)
+    {
+        forAll(modes_, i)
+        {
+            const volScalarField lam(thermoLambda_[i].createField(dimensionedScalar("lambda", dimTime, modes_[i].lambda)));
+            const volScalarField eta(thermoEta_[i].createField(dimensionedScalar("etaP", dimMass/(dimLength*dimTime), modes_[i].etaP)));
+            check(rheo_gpu_upload_thermo(gpu_, i, lam.primitiveField().begin(), eta.primitiveField().begin()), "rheo_gpu_upload_thermo");
+        }
+    }
 
     symmTensorField tauB(mesh.nFaces() - nI);
     List<RheoStepStats> stats(modes_.size());

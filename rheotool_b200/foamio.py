@@ -393,8 +393,11 @@ def read_schemes(case_dir, theta_name: str = "theta"):
     if div is None:
         raise FoamError(f"{fs.path}: no div(phi,{theta_name}) scheme")
     tok = div.split()
+    bounded = bool(tok) and tok[0] == "bounded"   # EXT-OF9 boundedConvectionScheme (rheoFilmFoam/UCM/system/fvSchemes:35)
+    if bounded:
+        tok = tok[1:]
     if len(tok) != 2 or tok[0] != "GaussDefCmpw" or tok[1] not in abi.LIMITER:
-        raise FoamError(f"{fs.path}: div(phi,{theta_name}) is `{div}`; the stress step needs `GaussDefCmpw <limiter>` with one of {sorted(abi.LIMITER)}")
+        raise FoamError(f"{fs.path}: div(phi,{theta_name}) is `{div}`; the stress step needs `[bounded] GaussDefCmpw <limiter>` with one of {sorted(abi.LIMITER)}")
     ddt = fs.get(f"ddtSchemes/ddt({theta_name})") or fs.get("ddtSchemes/default")
     cn_psi = 1.0
     if ddt is not None and ddt.split()[0] == "CrankNicolson":      # `CrankNicolson <psi>` (Cavity/Oldroyd-BLog/system/fvSchemes)
@@ -403,8 +406,8 @@ def read_schemes(case_dir, theta_name: str = "theta"):
         if not 0.0 <= cn_psi <= 1.0:
             raise FoamError(f"{fs.path}: CrankNicolson off-centring coefficient {cn_psi} is outside [0, 1]")
         ddt = "CrankNicolson"
-    if ddt not in ("Euler", "backward", "CrankNicolson"):
-        raise FoamError(f"{fs.path}: ddtSchemes Euler, backward and CrankNicolson are available, not {ddt}")
+    if ddt not in ("Euler", "backward", "CrankNicolson", "steadyState"):
+        raise FoamError(f"{fs.path}: ddtSchemes Euler, backward, CrankNicolson and steadyState are available, not {ddt}")
     # the device hard-codes Gauss linear for grad(U) (boilerLog.H:1), for the per-component grad(theta) of phifDefC
     # (gaussDefCmpwConvectionScheme.C:254) and for `linExtrapGrad` (linearExtrapolationFvPatchField.C:128): anything else in
     # gradSchemes would silently differ from the reference
@@ -424,7 +427,7 @@ def read_schemes(case_dir, theta_name: str = "theta"):
     # the solver the file names is the solver that runs: PBiCG (what the Log tutorials select) on one rank (pbicg.cuh),
     # PBiCGStab on any number of ranks; a decomposed PBiCG case fails loudly at the first step instead of being substituted
     ctl = cases.scheme_ctl(tok[1], solver, sol.scalar(f"{at}/tolerance", 1e-6), sol.scalar(f"{at}/relTol", 0.0), int(sol.scalar(f"{at}/minIter", 0)),
-                           int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt, cn_psi=cn_psi)
+                           int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt, cn_psi=cn_psi, bounded=bounded)
     return ctl, solver
 
 

@@ -81,6 +81,12 @@ class GpuStressModel:
         """Raw host pointers (e.g. pinned torch tensors); asynchronous on the model's stream."""
         _check(abi.lib().rheo_gpu_upload_velocity(self._h, U_ptr, Ub_ptr, phi_ptr))
 
+    def upload_thermo(self, mode=0, lambda_cell=None, etaP_cell=None):
+        """Thermo-dependent lambda / etaP per cell (Oldroyd_BLog.C:133-135: thermoLambdaPtr_->createField(lambda_)); None, None
+        restores the scalars.  `thermo_factor` evaluates the reference's thermoFunctions."""
+        a, b = _c(lambda_cell), _c(etaP_cell)
+        _check(abi.lib().rheo_gpu_upload_thermo(self._h, mode, _p(a), _p(b)))
+
     def store_old_time(self):
         _check(abi.lib().rheo_gpu_store_old_time(self._h))
 
@@ -192,6 +198,18 @@ class GpuStressModel:
         _check(abi.lib().rheo_gpu_synchronize(self._h))
 
 
+def thermo_factor(kind: str, params, T) -> np.ndarray:
+    """a_T(T) of the reference's thermoFunctions (of90/src/libs/thermo/thermoFunctions): kind in Constant | Arrhenius (alpha, T0) |
+    ArrheniusModified (alpha, T0) | WLF (c1, c2, T0) | VFT (A, B, T0); lambda(T) = lambda a_T, etaP(T) = etaP a_T."""
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    p = np.zeros(3)
+    p[: len(params)] = params
+    out = np.zeros_like(T)
+    if abi.lib().rheo_thermo_factor(abi.THERMO[kind], _p(p), T.size, _p(T), _p(out)):
+        raise RheoError(f"unknown thermoFunction {kind}")
+    return out
+
+
 def eig_exp(theta6: np.ndarray, device: int = 0):
     """calcEig on the GPU for an AoS symmTensor array (constitutiveEq.C:360-416)."""
     t = np.ascontiguousarray(theta6, dtype=np.float64).reshape(-1, 6)
@@ -247,16 +265,17 @@ def constitutive_model(mesh: HostMesh, constitutive_properties: dict, fv_schemes
     fv_schemes = fv_schemes or {}
     fv_solution = fv_solution or {}
     div = fv_schemes.get("div(phi,theta)", "GaussDefCmpw cubista").split()
-    if div[0] == "bounded":
-        raise RheoError("bounded GaussDefCmpw is not implemented on the GPU path")
+    bounded = div[0] == "bounded"   # EXT-OF9 boundedConvectionScheme (rheoFilmFoam/UCM/system/fvSchemes:35)
+    if bounded:
+        div = div[1:]
     if div[0] != "GaussDefCmpw":
         raise RheoError(f"div(phi,theta) must use GaussDefCmpw, got {div[0]}")
     ddt_tok = str(fv_schemes.get("ddt", "Euler")).split()
-    if ddt_tok[0] not in ("Euler", "backward", "CrankNicolson"):
-        raise RheoError(f"ddtSchemes Euler, backward and CrankNicolson are implemented on the GPU path, not {ddt_tok[0]}")
+    if ddt_tok[0] not in ("Euler", "backward", "CrankNicolson", "steadyState"):
+        raise RheoError(f"ddtSchemes Euler, backward, CrankNicolson and steadyState are implemented on the GPU path, not {ddt_tok[0]}")
     cn_psi = float(ddt_tok[1]) if (ddt_tok[0] == "CrankNicolson" and len(ddt_tok) > 1) else 1.0
     sol = fv_solution.get("theta", {})
     ctl = scheme_ctl(limiter=div[1], solver=sol.get("solver", "PBiCGStab"), tolerance=float(sol.get("tolerance", 1e-10)),
                      rel_tol=float(sol.get("relTol", 0.0)), min_iter=int(sol.get("minIter", 0)), max_iter=int(sol.get("maxIter", 1000)),
-                     relax=float(fv_solution.get("relaxationFactors", {}).get("theta", 0.0)), ddt=ddt_tok[0], cn_psi=cn_psi)
+                     relax=float(fv_solution.get("relaxationFactors", {}).get("theta", 0.0)), ddt=ddt_tok[0], cn_psi=cn_psi, bounded=bounded)
     return GpuStressModel(mesh, models, ctl, device)
