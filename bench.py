@@ -93,6 +93,13 @@ def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int):
     if base == "k_flux_assemble":
         # theta, U, tile record (nbr, meta, S, W, D, rV, V), flux tile | A, diag+rD, bsrc, corr (one value per face and component), gradU
         return (c1 + 3) * 8 + K * (4 + 4 + 7 * 8) + 16 + K * 8 + K * 8 + 16 + c1 * 8 + f * c1 * 8 + 72, 1.0
+    if base == "k_flux3":
+        # assembly3.cuh: theta, U, tile record v3 (nbr, meta, G, D, G0, V), flux tile | A, diag+rD, rowsum, inflow mask, bsrc, A theta,
+        # corr (one value per face and component), gradU
+        return (c1 + 3) * 8 + K * (4 + 4 + 6 * 8) + 32 + K * 8 + K * 8 + 16 + 8 + 4 + c1 * 8 + c1 * 8 + f * c1 * 8 + 72, 1.0
+    if base == "k_source_init":
+        # gradU, theta, thetaOld, lam, R, V, bsrc, A theta, rowsum, inflow mask, corr (inflow faces) | fFene, r, r0   (one mode per launch)
+        return (9 + 6 + 6 + 3 + 9 + 1) * 8 + c1 * 8 + c1 * 8 + 8 + 4 + f * c1 * 8 + 8 + 2 * c1 * 8, 1.0
     if base == "k_cell_source2":
         # gradU, theta, thetaOld, lam, R, V, bsrc read | bsrc, fFene
         return (9 + 6 + 6 + 3 + 9 + 1) * 8 + c1 * 8 + 6 * 8 + 8, 1.0

@@ -43,6 +43,12 @@ struct FluxArgs {
     double* ghostCorr;    // send buffer: [(h * ghostStride) + ghostOffset + comp]
     int ghostStride, ghostOffset;
     double* gradU;        // [9*NP] g[3k+d] = d_d U_k
+    // k_flux3 only (assembly3.cuh): what the fused source + first-residual kernel needs instead of gathers
+    double* acc;          // [nComp][NP] A theta (diag theta_P + sum_s A_s theta_N), this mode
+    double* rowsum;       // [N] diag + sum_s A_s           (written with the matrix)
+    unsigned* inflow;     // [N] bit s: A_s < 0             (written with the matrix)
+    double* sumPartials; double* sumOut; unsigned* counter;   // sum(theta) per solved component -> sumOut[nComp]
+    const int* tileOrder; // [nTiles] tiles in geometric (super-block) order, or null: the tiles a wave of CTAs works on share their neighbours in L2
 };
 
 // Tile record of the mesh (static, built once per mesh; one contiguous block per 32 consecutive cells so that ONE bulk copy
@@ -259,290 +265,6 @@ __global__ void __launch_bounds__(TILE * 9, RK_FLUX_MINB) k_flux_assemble(MeshVi
             }
         }
         __syncthreads();   // every warp is done with stage st before the next iteration's prefetch overwrites it
-    }
-}
-
-// ---------------------------------------------------------------- the same assembly, work re-mapped (round 2)
-// k_flux_assemble above maps one thread to one (cell, component): every theta warp re-reads the tile's geometry, re-derives
-// the slot flags and runs the limiter body for every slot on which ANY of its 32 cells is the upwind cell — ncu (profiles/
-// r1_final_C3_full.md, r2): 250 warp-instructions per cell of which 21 % FP64 math, issue slots 64 % busy, DRAM 44 %.
-// k_flux_assemble2 splits the tile's work into phases with different thread mappings (same arithmetic, same outputs):
-//   1. (cell, component)  theta_P, the K neighbour values and the Gauss gradient of the component -> shared memory;
-//                         velocity warps: grad(U) as before; warp 0: the component-independent diagonal terms, once;
-//   2. (cell, slot)       which (cell, slot) pairs is this cell the upwind cell of (or a processor face)?  The pairs are
-//                         COMPACTED (ballot + prefix) so that phase 3 runs on full warps;
-//   3. one thread per compacted pair, loop over the components: geometry and flags read once per face instead of once
-//                         per face and component, limiter body only for upwind faces; v F left in shared memory, v handed
-//                         to the downwind cell (corr) or to the halo send buffer;
-//   4. (cell, component)  sum of the cell's v F in slot order, boundary source, relax, store.
-template <int KT> __host__ __device__ constexpr size_t flux2_extra_bytes(int K, int nComp) {
-    return (size_t)TILE * sizeof(double) * ((size_t)nComp + 3 * nComp + (size_t)nComp * K + 5) + (size_t)K * TILE * sizeof(unsigned short) + 64;
-}
-template <int KT>
-__global__ void __launch_bounds__(TILE * 9, RK_FLUX_MINB) k_flux_assemble2(MeshView m, FluxArgs a, const unsigned char* __restrict__ tileRec, int nTiles) {
-    pdl_sync();
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    const int K = KT > 0 ? KT : m.K;
-    const int KTL = K * TILE;
-    const int nC = a.cl.n;
-    const size_t recBytes = tile_record_bytes(K), fluxBytes = tile_flux_bytes(K), stageBytes = recBytes + fluxBytes;
-    __shared__ uint64_t full[2];
-    double* sTheta = (double*)(smemRaw + 2 * stageBytes);   // [nC][TILE]
-    double* sGrad = sTheta + nC * TILE;                      // [nC][3][TILE]
-    double* sVn = sGrad + 3 * nC * TILE;                     // [nC][K][TILE]: neighbour value, then v F of the pairs processed in phase 3
-    double* sDiag = sVn + (size_t)nC * KTL;                  // [5][TILE]: D, sumOff, iCcoupled, iCplainAbs, iCplain
-    unsigned short* sPairs = (unsigned short*)(sDiag + 5 * TILE);   // [K * TILE] compacted pair ids (slot * TILE + cell)
-    int* sCnt = (int*)(sPairs + KTL);                        // [<= 15] per-warp pair counts, [15] total
-    const int lane = threadIdx.x & (TILE - 1), grp = threadIdx.x / TILE, nGrp = blockDim.x / TILE;
-    const bool hrs = a.lim.hrs && !a.noConv;
-    const bool needDiag = a.relax > 0 || a.writeMatrix;
-    if (threadIdx.x == 0) {
-        mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && (int)blockIdx.x < nTiles) {
-        mbar_expect_tx(&full[0], (uint32_t)stageBytes);
-        bulk_g2s(smemRaw, tileRec + (size_t)blockIdx.x * recBytes, (uint32_t)recBytes, &full[0]);
-        bulk_g2s(smemRaw + recBytes, (const unsigned char*)a.Fell + (size_t)blockIdx.x * fluxBytes, (uint32_t)fluxBytes, &full[0]);
-    }
-    int it = 0;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x, ++it) {
-        const int st = it & 1;
-        const int next = tile + gridDim.x;
-        if (threadIdx.x == 0 && next < nTiles) {   // stage st^1 was released by the __syncthreads that ended the previous iteration
-            unsigned char* dst = smemRaw + (size_t)(st ^ 1) * stageBytes;
-            mbar_expect_tx(&full[st ^ 1], (uint32_t)stageBytes);
-            bulk_g2s(dst, tileRec + (size_t)next * recBytes, (uint32_t)recBytes, &full[st ^ 1]);
-            bulk_g2s(dst + recBytes, (const unsigned char*)a.Fell + (size_t)next * fluxBytes, (uint32_t)fluxBytes, &full[st ^ 1]);
-        }
-        const unsigned char* base = smemRaw + (size_t)st * stageBytes;
-        const int* bNb = (const int*)base;                                                  // [K][TILE]
-        const int* bMeta = bNb + KTL;
-        const double* bS = (const double*)(base + (size_t)2 * KTL * sizeof(int));         // [3][K][TILE]
-        const double* bW = bS + 3 * KTL;
-        const double* bD = bW + KTL;                                                        // [3][K][TILE]
-        const double* bRV = bD + 3 * KTL;                                                   // rV[32], V[32]
-        const double* bF = (const double*)(base + recBytes);
-        const int* pNb = bNb + lane;
-        const int* pMeta = bMeta + lane;
-        const double* pS = bS + lane;
-        const double* pW = bW + lane;
-        const double* pF = bF + lane;
-        const int c = tile * TILE + lane;
-        const bool active = c < m.N;
-        mbar_wait(&full[st], (uint32_t)((it >> 1) & 1));
-
-        // ---------------------------------------------------------------- phase 1
-        if (active) {
-            if (a.writeMatrix)   // row coefficients A[c][nb] = min(F,0), slot-major for the Krylov kernels
-                for (int s = grp; s < K; s += nGrp)
-                    a.Fs[ell_t(m.K, s, c)] = ((pMeta[s * TILE] & SLOT_CELL) && !a.noConv) ? fmin(pF[s * TILE], 0.0) : 0.0;
-            if (a.writeMatrix && a.FsT)
-                for (int s = grp; s < K; s += nGrp)
-                    a.FsT[ell_t(m.K, s, c)] = ((pMeta[s * TILE] & SLOT_CELL) && !a.noConv) ? fmin(-pF[s * TILE], 0.0) : 0.0;
-            if (grp >= nC) {   // ---------------- velocity warp: grad(U_u)
-                const int u = grp - nC;
-                const double* fk = a.U + (size_t)u * m.NP;
-                const double own = fk[c];
-                const double* uB = a.Ub + (size_t)u * m.nB;
-                double gx = 0, gy = 0, gz = 0;
-                double un[KT > 0 ? KT : 1];
-                if constexpr (KT > 0) {
-#pragma unroll
-                    for (int s = 0; s < KT; ++s) {
-                        const int nb = pNb[s * TILE];
-                        const double* src = nb >= 0 ? fk + nb : (nb == -1 ? fk + c : uB + (-nb - 2));
-                        un[s] = *src;
-                    }
-                }
-#pragma unroll
-                for (int s = 0; s < K; ++s) {
-                    const int nb = pNb[s * TILE];
-                    if (nb == -1) continue;
-                    double v;
-                    if constexpr (KT > 0) v = un[s];
-                    else v = nb >= 0 ? fk[nb] : uB[-nb - 2];
-                    double vf = v;
-                    if (nb >= 0) {
-                        const double w = pW[s * TILE];
-                        if (nb >= m.N) vf = w * own + (1.0 - w) * v;
-                        else vf = nb > c ? w * (own - v) + v : w * (v - own) + own;
-                    }
-                    gx += pS[s * TILE] * vf; gy += pS[KTL + s * TILE] * vf; gz += pS[2 * KTL + s * TILE] * vf;
-                }
-                const double rv = bRV[lane];
-                a.gradU[(size_t)(3 * u) * m.NP + c] = gx * rv;
-                a.gradU[(size_t)(3 * u + 1) * m.NP + c] = gy * rv;
-                a.gradU[(size_t)(3 * u + 2) * m.NP + c] = gz * rv;
-            } else {               // ---------------- theta warp: theta_P, neighbour values, Gauss gradient -> shared memory
-                const int k = a.cl.c[grp];
-                const double* tk = a.theta + (size_t)k * m.NP;
-                const double* tB = a.thetaB + (size_t)k * m.nB;
-                const double tP = tk[c];
-                sTheta[grp * TILE + lane] = tP;
-                if (hrs) {
-                    double* myVn = sVn + (size_t)grp * KTL + lane;
-                    double vn[KT > 0 ? KT : 1];
-                    if constexpr (KT > 0) {
-#pragma unroll
-                        for (int s = 0; s < KT; ++s) {   // K independent gathers in flight
-                            const int nb = pNb[s * TILE];
-                            const double* src = nb >= 0 ? tk + nb : (nb == -1 ? tk + c : tB + (-nb - 2));
-                            vn[s] = *src;
-                        }
-                    }
-                    double gx = 0, gy = 0, gz = 0;
-#pragma unroll
-                    for (int s = 0; s < K; ++s) {
-                        const int nb = pNb[s * TILE];
-                        if (nb == -1) continue;
-                        double v;
-                        if constexpr (KT > 0) v = vn[s];
-                        else v = nb >= 0 ? tk[nb] : tB[-nb - 2];
-                        myVn[s * TILE] = v;
-                        double vf = v;
-                        if (nb >= 0) {
-                            const double w = pW[s * TILE];
-                            if (nb >= m.N) vf = w * tP + (1.0 - w) * v;
-                            else vf = nb > c ? w * (tP - v) + v : w * (v - tP) + tP;
-                        }
-                        gx += pS[s * TILE] * vf; gy += pS[KTL + s * TILE] * vf; gz += pS[2 * KTL + s * TILE] * vf;
-                    }
-                    const double rv = bRV[lane];
-                    sGrad[(grp * 3 + 0) * TILE + lane] = gx * rv;
-                    sGrad[(grp * 3 + 1) * TILE + lane] = gy * rv;
-                    sGrad[(grp * 3 + 2) * TILE + lane] = gz * rv;
-                }
-                if (grp == 0 && needDiag) {   // component-independent diagonal terms, once per cell
-                    double D = a.rDeltaT * bRV[TILE + lane], sumOff = 0, iCcoupled = 0, iCplainAbs = 0, iCplain = 0;
-                    for (int s = 0; s < K; ++s) {
-                        const int meta = pMeta[s * TILE];
-                        const double F = a.noConv ? 0.0 : pF[s * TILE];
-                        if (a.bounded) D -= F;
-                        if (meta & SLOT_CELL) {
-                            if (!(meta & SLOT_GHOST)) { D += fmax(F, 0.0); sumOff += fmax(-F, 0.0); }
-                            else { iCcoupled += (F >= 0 ? F : 0.0); sumOff += fmax(-F, 0.0); }
-                        } else if (meta & SLOT_PATCH_ZG) { iCplain += F; iCplainAbs += fabs(F); }
-                    }
-                    sDiag[lane] = D; sDiag[TILE + lane] = sumOff; sDiag[2 * TILE + lane] = iCcoupled; sDiag[3 * TILE + lane] = iCplainAbs;
-                    sDiag[4 * TILE + lane] = iCplain;
-                }
-            }
-        }
-        __syncthreads();
-        if (hrs) {
-            // ---------------------------------------------------------------- phase 2: pairs (cell, slot) this cell is upwind of, or processor faces
-            const int nPairsAll = KTL;
-            int nUp = 0;
-            auto pair_kind = [&](int p, int& meta, double& F) -> int {   // 0 none, 1 upwind, 2 processor face where the other side is upwind
-                const int l = p & (TILE - 1);
-                if (tile * TILE + l >= m.N) return 0;
-                meta = bMeta[p];
-                if (!(meta & SLOT_CELL)) return 0;
-                F = bF[p];
-                const bool own = meta & SLOT_OWNER;
-                const bool upwFace = own ? (F >= 0) : (-F >= 0);   // pos(phi), phi = own ? F : -F
-                if (own == upwFace) return 1;
-                return (meta & SLOT_GHOST) ? 2 : 0;
-            };
-            auto do_pair = [&](int p, int kind, int meta, double F) {   // phase 3 body: every component of one face
-                const int l = p & (TILE - 1), s = p / TILE;
-                const int cc = tile * TILE + l;
-                const int nb = bNb[p];
-                const bool own = meta & SLOT_OWNER;
-                const bool upwFace = own ? (F >= 0) : (-F >= 0);
-                const double d0 = bD[p], d1 = bD[KTL + p], d2 = bD[2 * KTL + p];
-                const Limiter L = a.lim;
-                for (int g = 0; g < nC; ++g) {
-                    double v = 0.0;
-                    double* slot = sVn + (size_t)g * KTL + p;
-                    if (kind == 1) {
-                        const double tP = sTheta[g * TILE + l], tn = *slot;
-                        const double gd = sGrad[(g * 3 + 0) * TILE + l] * d0 + sGrad[(g * 3 + 1) * TILE + l] * d1 + sGrad[(g * 3 + 2) * TILE + l] * d2;
-                        v = phif_defc(own ? tP : tn, own ? tn : tP, gd, gd, upwFace, L);
-                        *slot = v * F;   // souT[own] += v*phi ; souT[nei] -= v*phi  (summed per cell in phase 4)
-                        if (!(meta & SLOT_GHOST)) a.corr[(size_t)g * m.K * m.NS + (size_t)(unsigned)(meta >> 8) * (unsigned)m.NS + (unsigned)nb] = v;
-                    }
-                    if (meta & SLOT_GHOST) {
-                        // processor face: the value travels with the halo exchange (0 where the other side is upwind, so
-                        // that the receiver never reads an unwritten word); my own ghost slot of `corr` is cleared
-                        a.ghostCorr[(size_t)(nb - m.N) * a.ghostStride + a.ghostOffset + g] = v;
-                        a.corr[(size_t)g * m.K * m.NS + (size_t)(unsigned)s * (unsigned)m.NS + (unsigned)cc] = 0.0;
-                    }
-                }
-            };
-            if (KT > 0 && nPairsAll <= (int)blockDim.x) {
-                int meta = 0, kind = 0;
-                double F = 0;
-                const int p = threadIdx.x;
-                if (p < nPairsAll) kind = pair_kind(p, meta, F);
-                const unsigned bal = __ballot_sync(0xffffffffu, kind != 0);
-                if (lane == 0) sCnt[grp] = __popc(bal);
-                __syncthreads();
-                int off = 0;
-                for (int w = 0; w < nGrp; ++w) { const int n = sCnt[w]; if (w < grp) off += n; nUp += n; }
-                if (kind != 0) sPairs[off + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)p;
-                __syncthreads();
-                // ------------------------------------------------------------ phase 3 on full warps
-                for (int q = threadIdx.x; q < nUp; q += blockDim.x) {
-                    const int pp = sPairs[q];
-                    int meta2 = 0;
-                    double F2 = 0;
-                    const int kind2 = pair_kind(pp, meta2, F2);
-                    do_pair(pp, kind2, meta2, F2);
-                }
-            } else {   // run-time K (unstructured meshes): no compaction
-                for (int p = threadIdx.x; p < nPairsAll; p += blockDim.x) {
-                    int meta = 0;
-                    double F = 0;
-                    const int kind = pair_kind(p, meta, F);
-                    if (kind) do_pair(p, kind, meta, F);
-                }
-            }
-            __syncthreads();
-        }
-        // ---------------------------------------------------------------- phase 4: per (cell, component)
-        if (active && grp < nC) {
-            const int k = a.cl.c[grp];
-            const double* tB = a.thetaB + (size_t)k * m.nB;
-            const double tP = sTheta[grp * TILE + lane];
-            const double* myVF = sVn + (size_t)grp * KTL + lane;
-            double sou = 0, bnd = 0;
-            for (int s = 0; s < K; ++s) {
-                const int meta = pMeta[s * TILE];
-                if (meta & SLOT_CELL) {
-                    if (hrs) {
-                        const double F = pF[s * TILE];
-                        const bool own = meta & SLOT_OWNER;
-                        const bool upwFace = own ? (F >= 0) : (-F >= 0);
-                        if (own == upwFace) sou += myVF[s * TILE];
-                    }
-                } else if ((meta & (SLOT_PATCH | SLOT_PATCH_ZG)) == SLOT_PATCH) {
-                    bnd += -(a.noConv ? 0.0 : pF[s * TILE]) * tB[-pNb[s * TILE] - 2];
-                }
-            }
-            double D = 0, iCcoupled = 0, iCplain = 0, add = 0;
-            if (needDiag) { D = sDiag[lane]; iCcoupled = sDiag[2 * TILE + lane]; iCplain = sDiag[4 * TILE + lane]; }
-            if (a.relax > 0) {   // EXT-OF9 fvMatrix::relax
-                const double D0 = D, sumOff = sDiag[TILE + lane], iCplainAbs = sDiag[3 * TILE + lane];
-                double Dn = D + iCcoupled + iCplainAbs;
-                Dn = fmax(fabs(Dn), sumOff);
-                Dn /= a.relax;
-                Dn -= iCcoupled;
-                Dn -= iCplain;
-                add = (Dn - D0) * tP;
-                D = Dn;
-            }
-            a.bsrc[(size_t)k * m.NP + c] = (-sou + add) + bnd;
-            if (a.writeMatrix && grp == 0) {
-                const double Dfull = D + iCcoupled + iCplain;   // addBoundaryDiag
-                a.diag[c] = Dfull;
-                a.rD[c] = 1.0 / Dfull;   // DILU: upper*lower == 0 on every face of an upwind matrix
-            }
-        }
-        __syncthreads();   // every warp is done with stage st and the phase buffers before the next tile
     }
 }
 

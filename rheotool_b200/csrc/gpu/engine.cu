@@ -26,6 +26,7 @@
 #include "ordering.hpp"
 #include "pbicg.cuh"
 #include "assembly.cuh"
+#include "assembly3.cuh"
 #include "peer.cuh"
 #include "rheo_gpu.h"
 
@@ -129,8 +130,12 @@ struct RheoGpu {
     // device mesh
     DevBuf d_perm, d_faceOld, d_nbr, d_nbrA, d_fidx, d_Sf, d_w, d_C, d_V, d_rV, d_bcell, d_bkind, d_bthetaBC, d_btauBC, d_CfB;
     DevBuf d_haloCell, d_send, d_recv;
-    DevBuf d_tileRec;              // per-tile mesh records streamed by k_flux_assemble (assembly.cuh)
+    DevBuf d_tileRec;              // per-tile mesh records streamed by k_flux_assemble (assembly.cuh) / k_flux3 (assembly3.cuh)
     int nTiles = 0;
+    bool rec3 = false;             // d_tileRec holds version-3 records: k_flux3 + k_source_init run instead of k_flux_assemble + k_cell_source2 + k_krylov_init
+    std::vector<int> sweepOrder;   // block ordering: chunks in geometric order (host/ordering.hpp)
+    DevBuf d_tileOrder;            // rec3: the assembly's tile walk (sweepOrder padded to nTiles); RHEO_TILE_ORDER=0 walks in index order
+    DevBuf d_rowsum, d_inflow;     // rec3: row sums of the matrix and inflow-slot masks (written by k_flux3 with the matrix)
     MeshView mv;
     // fields
     DevBuf d_U, d_Ub, d_phi, d_diag, d_rD, d_Fs, d_FsT, d_stage, d_tmpB;   // d_FsT: A^T coefficients, allocated when fvSolution selects PBiCG
@@ -286,6 +291,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
         if (wantBlocks && rk_host::block_renumber(N, nInt, d->owner, d->neighbour, d->C, bo)) {
             h->blockMode = true;
             h->perm = std::move(bo.perm);
+            h->sweepOrder = std::move(bo.sweepOrder);
             h->colourStart = std::move(bo.colourStart);
             h->nColours = bo.nColours;
             h->orderingInfo = std::to_string(bo.tile[0]) + "x" + std::to_string(bo.tile[1]) + "x" + std::to_string(bo.tile[2]) + " blocks of a " +
@@ -434,9 +440,13 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
             for (int e = 0; e < 3; ++e) C[(size_t)e * h->NP + N + ghostOfB[b]] = d->nbr_C[3 * (size_t)b + e];
         }
     }
-    {   // tile records streamed by k_flux_assemble (layout: assembly.cuh, tile_record_bytes)
+    {   // tile records streamed by the assembly kernel
+        // version 3 (assembly3.cuh: k_flux3, one thread per cell) for lattice-sized rows solved with PBiCGStab; version 1
+        // (assembly.cuh: k_flux_assemble, run-time K) for unstructured meshes and for the device PBiCG.  RHEO_FLUX=1 forces version 1.
+        const char* fenv = getenv("RHEO_FLUX");
+        h->rec3 = h->ctl.solver == RHEO_SOLVER_PBICGSTAB && ((K == 6 && h->nComp == 6) || (K == 4 && h->nComp == 4)) && !(fenv && fenv[0] == '1');
         const int nTiles = h->NS / TILE;
-        const size_t recBytes = tile_record_bytes(K);
+        const size_t recBytes = h->rec3 ? tile_record3_bytes(K) : tile_record_bytes(K);
         std::vector<unsigned char> rec((size_t)nTiles * recBytes, 0);
         std::vector<int> slotOfOwner(nInt, 0);
         for (int s = 0; s < K; ++s)
@@ -449,14 +459,19 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
             unsigned char* base = rec.data() + (size_t)t * recBytes;
             int* rNb = (int*)base;
             int* rMeta = rNb + K * TILE;
-            double* rS = (double*)(base + (size_t)2 * K * TILE * sizeof(int));
-            double* rW = rS + 3 * K * TILE;
-            double* rD = rW + K * TILE;
-            double* rRV = rD + 3 * K * TILE;
+            double* dbl = (double*)(base + (size_t)2 * K * TILE * sizeof(int));
+            // version 1: S[3][K][T], W[K][T], D[3][K][T], rV[T], V[T];   version 3: G[3][K][T], D[3][K][T], G0[3][T], V[T]
+            double* rS = dbl;
+            double* rW = h->rec3 ? nullptr : rS + 3 * K * TILE;
+            double* rD = h->rec3 ? rS + 3 * K * TILE : rW + K * TILE;
+            double* rG0 = h->rec3 ? rD + 3 * K * TILE : nullptr;
+            double* rRV = h->rec3 ? nullptr : rD + 3 * K * TILE;
+            double* rVol = h->rec3 ? rG0 + 3 * TILE : rRV + TILE;
             for (int l = 0; l < TILE; ++l) {
                 const int c = t * TILE + l;
-                rRV[l] = c < N ? rV[c] : 0.0;
-                rRV[TILE + l] = c < N ? V[c] : 0.0;
+                if (rRV) rRV[l] = c < N ? rV[c] : 0.0;
+                rVol[l] = c < N ? V[c] : 0.0;
+                double g0[3] = {0, 0, 0};
                 for (int s = 0; s < K; ++s) {
                     const int i = s * TILE + l;
                     rNb[i] = -1; rMeta[i] = 0;
@@ -468,10 +483,22 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
                     const int fi = h->h_fidx[e];
                     const int f = fi >= 0 ? fi : ~fi;
                     const double sg = fi >= 0 ? 1.0 : -1.0;
-                    for (int x = 0; x < 3; ++x) rS[x * K * TILE + i] = sg * Sf[(size_t)x * nF + f];
-                    rW[i] = nb >= 0 ? w[f] : 0.0;   // patch slots: w = 0 makes the branch-free face value w (P - N) + N the patch value
+                    const bool own = fi >= 0;   // == (nb > c) on internal faces: faces are in upper-triangular order
+                    if (!h->rec3) {
+                        for (int x = 0; x < 3; ++x) rS[x * K * TILE + i] = sg * Sf[(size_t)x * nF + f];
+                        rW[i] = nb >= 0 ? w[f] : 0.0;   // patch slots: w = 0 makes the branch-free face value w (P - N) + N the patch value
+                    } else {
+                        // face value = a f_P + b f_N: owner / processor side  w, 1 - w;  neighbour side  1 - w, w;  patch  0, 1
+                        const double wf = w[f];
+                        const double bN = nb < 0 ? 1.0 : ((own || nb >= N) ? 1.0 - wf : wf);
+                        const double aP = nb < 0 ? 0.0 : ((own || nb >= N) ? wf : 1.0 - wf);
+                        for (int x = 0; x < 3; ++x) {
+                            const double Sx = sg * Sf[(size_t)x * nF + f];
+                            rS[x * K * TILE + i] = (bN * Sx) * rV[c];
+                            g0[x] += aP * Sx;
+                        }
+                    }
                     if (nb >= 0) {
-                        const bool own = fi >= 0;   // == (nb > c): faces are in upper-triangular order
                         int rs = 0;
                         if (nb < N) {
                             if (own) {   // find our face in the neighbour's row
@@ -487,10 +514,18 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
                         rMeta[i] = SLOT_PATCH | (bthetaBC[-nb - 2] == RHEO_BC_ZERO_GRADIENT ? SLOT_PATCH_ZG : 0);
                     }
                 }
+                if (rG0 && c < N) for (int x = 0; x < 3; ++x) rG0[x * TILE + l] = g0[x] * rV[c];
             }
         }
         h->nTiles = nTiles;
         if (upload(h->d_tileRec, rec)) return 1;
+        const char* oenv = getenv("RHEO_TILE_ORDER");
+        if (h->rec3 && h->blockMode && !(oenv && oenv[0] == '0')) {
+            std::vector<int> order(h->sweepOrder);
+            for (int t = (int)order.size(); t < nTiles; ++t) order.push_back(t);   // padding tiles (no cells) last
+            if ((int)order.size() != nTiles) return fail("rheo_gpu_create: tile order does not cover the tiles");
+            if (upload(h->d_tileOrder, order)) return 1;
+        } else h->d_tileOrder.release();
     }
     if (upload(h->d_perm, h->perm) || upload(h->d_faceOld, h->faceOld) || upload(h->d_nbr, h->h_nbr) || upload(h->d_nbrA, nbrA) ||
         upload(h->d_fidx, h->h_fidx) || upload(h->d_Sf, Sf) || upload(h->d_w, w) || upload(h->d_C, C) || upload(h->d_V, V) ||
@@ -576,7 +611,9 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
         h->d_z.alloc(kv) || h->d_t.alloc(kv))
         return 1;
     for (DevBuf* b : {&h->d_r, &h->d_r0, &h->d_p, &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t}) zero(h, *b);
-    const int nBlocks = cdiv(h->N, BLOCK);
+    // partial sums: one row of <= MAX_RED slots per CTA of the largest reducing grid (all of them persistent: one resident wave)
+    const int nBlocks = std::max(cdiv(h->N, BLOCK), std::min(cdiv(h->N, TILE), 32 * h->nSms));
+    if (h->rec3 && (h->d_rowsum.alloc(std::max<size_t>(NP, h->NS) * d8) || h->d_inflow.alloc(std::max<size_t>(NP, h->NS) * sizeof(unsigned)))) return 1;
     if (h->d_ks.alloc(sizeof(KrylovShared)) || h->d_partials.alloc((size_t)nBlocks * MAX_RED * d8) || h->d_red.alloc(4 * MAX_RED * d8) ||
         h->d_counter.alloc(sizeof(unsigned)) || h->d_sumPsi.alloc((size_t)nModes * 6 * d8))
         return 1;
@@ -870,104 +907,139 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         if (pl.n && halo_exchange(h, pl)) return 1;
     }
     if (h->timing) cudaEventRecord(h->ev[1], h->stream);
-    // ---- assembly, mode by mode (the matrix is shared: same phi, same dt)
-    float msGrad = 0, msAsm = 0;
-    {
-        // k_flux_assemble (upwind cell computes each deferred face value once; grad(U) with the first mode) then
-        // k_cell_source2 (model source + ddt + inflow faces).  Processor faces: the face values of a group of modes
-        // travel in one message per neighbour, then k_ghost_corr adds them on the receiving side.
-        const bool hrs = h->lim.hrs && !noConv;
-        const size_t fluxSmem = 2 * (tile_record_bytes(h->K) + tile_flux_bytes(h->K));   // two stages
-        const int perGroup = std::max(1, MAX_RHS / h->nComp);
-        cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
-        if (h->timing) cudaEventRecord(e0, h->stream);
-        for (int g0 = 0; g0 < nModes; g0 += perGroup) {
-            const int g1 = std::min(nModes, g0 + perGroup);
-            const int stride = (g1 - g0) * h->nComp;
-            for (int mi = g0; mi < g1; ++mi) {
-                ModeDev& md = h->modes[mi];
-                FluxArgs fa;
-                fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = ddtDiag; fa.relax = h->ctl.relax;
-                fa.writeMatrix = mi == 0 ? 1 : 0;
-                fa.bounded = h->ctl.bounded ? 1 : 0;
-                fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
-                fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
-                fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>(); fa.FsT = pbicg ? h->d_FsT.as<double>() : nullptr;
-                fa.corr = md.corr.as<double>(); fa.ghostCorr = h->d_send.as<double>(); fa.ghostStride = stride; fa.ghostOffset = (mi - g0) * h->nComp;
-                fa.gradU = h->d_gradU.as<double>();
-                const int threads = TILE * (cl.n + fa.nU);
-                const unsigned char* rec = h->d_tileRec.as<unsigned char>();
-                static const bool oldFlux = !(getenv("RHEO_FLUX") && getenv("RHEO_FLUX")[0] == '2');   // RHEO_FLUX=2: the phase-split mapping (k_flux_assemble2: measured 13 % slower, kept for A/B runs)
-                if (oldFlux) {
-                    switch (h->K) {
-                        case 4: LAUNCH_SM(h, (k_flux_assemble<4>), flux_grid(h, k_flux_assemble<4>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
-                        case 6: LAUNCH_SM(h, (k_flux_assemble<6>), flux_grid(h, k_flux_assemble<6>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
-                        default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
-                    }
-                } else {
-                    const size_t sm2 = fluxSmem + flux2_extra_bytes<0>(h->K, cl.n);
-                    switch (h->K) {
-                        case 4: LAUNCH_SM(h, (k_flux_assemble2<4>), flux_grid(h, k_flux_assemble2<4>, threads, sm2), threads, sm2, h->mv, fa, rec, h->nTiles); break;
-                        case 6: LAUNCH_SM(h, (k_flux_assemble2<6>), flux_grid(h, k_flux_assemble2<6>, threads, sm2), threads, sm2, h->mv, fa, rec, h->nTiles); break;
-                        default: LAUNCH_SM(h, (k_flux_assemble2<0>), flux_grid(h, k_flux_assemble2<0>, threads, sm2), threads, sm2, h->mv, fa, rec, h->nTiles); break;
-                    }
-                }
-                SourceArgs sa;
-                sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.backward = (backward || crankNicolson) ? 1 : 0; sa.c0 = c0; sa.c00 = c00;
-                sa.thetaOldOld = backward ? md.thetaOldOld.as<double>() : crankNicolson ? md.ddt0.as<double>() : md.thetaOld.as<double>();
-                for (int q = 0; q < 6; ++q) sa.solvedIdx[q] = -1;
-                for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
-                sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
-                sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
-                sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>(); sa.tau = md.tau.as<double>();
-                sa.lamCell = md.lamCell.as<double>(); sa.etaCell = md.etaCell.as<double>();
-                sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
-                const int srcGrid = std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms);
-                switch (md.mp.model) {
-                    case RHEO_MODEL_OLDROYD_B_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_OLDROYD_B_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_GIESEKUS_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_GIESEKUS_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_PTT_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_PTT_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_FENE_P_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_P_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_FENE_CR_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_CR_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_WM_CY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_ROLIE_POLY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_ROLIE_POLY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    case RHEO_MODEL_SARAMITO_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_SARAMITO_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                    default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_XPOMPOM_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
-                }
-            }
-            if (h->H && hrs) {
-                const double* recv;
-                if (halo_sendrecv(h, stride, &recv)) return 1;
-                for (int mi = g0; mi < g1; ++mi)
-                    if (h->nBcells) LAUNCH(h, k_ghost_corr, cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), cl, h->d_Fs.as<double>(),
-                                           recv, stride, (mi - g0) * h->nComp, h->modes[mi].bsrc.as<double>());
-            }
-        }
-        if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
-    }
-    if (h->timing) cudaEventRecord(h->ev[2], h->stream);
-
-    // ---- segregated solve: all valid components of all modes batched on the shared matrix
+    // ---- assembly + segregated solve, batch by batch (the matrix is shared by all modes: same phi, same dt; a batch = as many
+    // modes as fit MAX_RHS right-hand sides — the Krylov vectors are sized for one batch)
+    float msGrad = 0, msAsm = 0, msSolve = 0;
     h->lastIters = 0;
+    const bool hrs = h->lim.hrs && !noConv;
     const int perBatch = std::max(1, MAX_RHS / h->nComp);
     for (int m0 = 0; m0 < nModes; m0 += perBatch) {
         const int m1 = std::min(nModes, m0 + perBatch);
+        const int nrhs = (m1 - m0) * h->nComp;
+        cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
+        if (h->timing) cudaEventRecord(e0, h->stream);
+        // k_flux3 / k_flux_assemble: the upwind cell computes each deferred face value once (grad(U) and the matrix with the
+        // first mode).  Processor faces: the face values of the batch travel in one message per neighbour, then k_ghost_corr
+        // adds them on the receiving side.  Then the per-cell source (model term + ddt) and the first residual.
+        for (int mi = m0; mi < m1; ++mi) {
+            ModeDev& md = h->modes[mi];
+            FluxArgs fa{};
+            fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = ddtDiag; fa.relax = h->ctl.relax;
+            fa.writeMatrix = mi == 0 ? 1 : 0;
+            fa.bounded = h->ctl.bounded ? 1 : 0;
+            fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
+            fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
+            fa.diag = h->d_diag.as<double>(); fa.rD = h->d_rD.as<double>(); fa.Fs = h->d_Fs.as<double>(); fa.FsT = pbicg ? h->d_FsT.as<double>() : nullptr;
+            fa.corr = md.corr.as<double>(); fa.ghostCorr = h->d_send.as<double>(); fa.ghostStride = nrhs; fa.ghostOffset = (mi - m0) * h->nComp;
+            fa.gradU = h->d_gradU.as<double>();
+            const unsigned char* rec = h->d_tileRec.as<unsigned char>();
+            if (h->rec3) {
+                // A theta goes where the Krylov vector t will live (first written by the second product of the first iteration)
+                fa.acc = h->d_t.as<double>() + (size_t)(mi - m0) * h->nComp * NP;
+                fa.rowsum = h->d_rowsum.as<double>(); fa.inflow = h->d_inflow.as<unsigned>();
+                fa.sumPartials = h->d_partials.as<double>(); fa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; fa.counter = h->d_counter.as<unsigned>();
+                fa.tileOrder = h->d_tileOrder.as<int>();
+                const size_t sm3 = tile_record3_bytes(h->K) + tile_flux_bytes(h->K);
+                if (h->K == 6) LAUNCH_SM(h, (k_flux3<6, 6>), flux_grid(h, k_flux3<6, 6>, TILE, sm3), TILE, sm3, h->mv, fa, rec, h->nTiles);
+                else LAUNCH_SM(h, (k_flux3<4, 4>), flux_grid(h, k_flux3<4, 4>, TILE, sm3), TILE, sm3, h->mv, fa, rec, h->nTiles);
+                continue;
+            }
+            const size_t fluxSmem = 2 * (tile_record_bytes(h->K) + tile_flux_bytes(h->K));   // two stages
+            const int threads = TILE * (cl.n + fa.nU);
+            switch (h->K) {
+                case 4: LAUNCH_SM(h, (k_flux_assemble<4>), flux_grid(h, k_flux_assemble<4>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                case 6: LAUNCH_SM(h, (k_flux_assemble<6>), flux_grid(h, k_flux_assemble<6>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+                default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
+            }
+        }
+        if (h->H && hrs) {
+            const double* recv;
+            if (halo_sendrecv(h, nrhs, &recv)) return 1;
+            for (int mi = m0; mi < m1; ++mi)
+                if (h->nBcells) LAUNCH(h, k_ghost_corr, cdiv(h->nBcells, BLOCK), BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), cl, h->d_Fs.as<double>(),
+                                       recv, nrhs, (mi - m0) * h->nComp, h->modes[mi].bsrc.as<double>());
+        }
+        // gAverage(psi) of the solver's normFactor: the per-component sums of theta (k_flux3 / k_cell_source2), summed over the ranks
+        double* sumPsi = h->d_sumPsi.as<double>() + (size_t)m0 * h->nComp;
+        if (h->rec3 && all_reduce(h, sumPsi, nrhs)) return 1;
+        const SolveCtl sc{h->ctl.tolerance, h->ctl.rel_tol, h->ctl.min_iter, h->ctl.max_iter};
+        const int srcGrid = std::min(cdiv(N, SRC_BLOCK), 3 * h->nSms);
+        for (int mi = m0; mi < m1; ++mi) {
+            ModeDev& md = h->modes[mi];
+            SourceArgs sa;
+            sa.mp = md.mp; sa.rDeltaT = rDeltaT; sa.backward = (backward || crankNicolson) ? 1 : 0; sa.c0 = c0; sa.c00 = c00;
+            sa.thetaOldOld = backward ? md.thetaOldOld.as<double>() : crankNicolson ? md.ddt0.as<double>() : md.thetaOld.as<double>();
+            for (int q = 0; q < 6; ++q) sa.solvedIdx[q] = -1;
+            for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
+            sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
+            sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
+            sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>(); sa.tau = md.tau.as<double>();
+            sa.lamCell = md.lamCell.as<double>(); sa.etaCell = md.etaCell.as<double>();
+            sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
+            if (h->rec3) {
+                SrcInitArgs si;
+                si.s = sa;
+                si.corr = hrs ? md.corr.as<double>() : nullptr;
+                si.acc = h->d_t.as<double>() + (size_t)(mi - m0) * h->nComp * NP;
+                si.rowsum = h->d_rowsum.as<double>(); si.inflow = h->d_inflow.as<unsigned>();
+                si.sumPsi = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; si.nGlobal = (double)h->nGlobalCells;
+                si.r = h->d_r.as<double>() + (size_t)(mi - m0) * NP * h->nComp; si.r0 = h->d_r0.as<double>() + (size_t)(mi - m0) * NP * h->nComp;
+                si.partials = h->d_partials.as<double>(); si.out = h->d_red.as<double>() + MAX_RED; si.counter = h->d_counter.as<unsigned>();
+                si.slotBase = 3 * (mi - m0) * h->nComp; si.nSlots = 3 * nrhs; si.totalBlocks = (m1 - m0) * srcGrid;
+                si.ctlWhat = h->nRanks > 1 ? CTL_NONE : CTL_INIT; si.nrhs = nrhs;
+                si.ks = h->d_ks.as<KrylovShared>(); si.sc = sc;
+#define RK_SRC3(M)                                                                                            \
+    do {                                                                                                      \
+        if (h->K == 6) LAUNCH(h, (k_source_init<M, 6, 6>), srcGrid, SRC_BLOCK, h->mv, si);                    \
+        else LAUNCH(h, (k_source_init<M, 4, 4>), srcGrid, SRC_BLOCK, h->mv, si);                              \
+    } while (0)
+                switch (md.mp.model) {
+                    case RHEO_MODEL_OLDROYD_B_LOG: RK_SRC3(RHEO_MODEL_OLDROYD_B_LOG); break;
+                    case RHEO_MODEL_GIESEKUS_LOG: RK_SRC3(RHEO_MODEL_GIESEKUS_LOG); break;
+                    case RHEO_MODEL_PTT_LOG: RK_SRC3(RHEO_MODEL_PTT_LOG); break;
+                    case RHEO_MODEL_FENE_P_LOG: RK_SRC3(RHEO_MODEL_FENE_P_LOG); break;
+                    case RHEO_MODEL_FENE_CR_LOG: RK_SRC3(RHEO_MODEL_FENE_CR_LOG); break;
+                    case RHEO_MODEL_WM_CY_LOG: RK_SRC3(RHEO_MODEL_WM_CY_LOG); break;
+                    case RHEO_MODEL_ROLIE_POLY_LOG: RK_SRC3(RHEO_MODEL_ROLIE_POLY_LOG); break;
+                    case RHEO_MODEL_SARAMITO_LOG: RK_SRC3(RHEO_MODEL_SARAMITO_LOG); break;
+                    default: RK_SRC3(RHEO_MODEL_XPOMPOM_LOG); break;
+                }
+#undef RK_SRC3
+                continue;
+            }
+            switch (md.mp.model) {
+                case RHEO_MODEL_OLDROYD_B_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_OLDROYD_B_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_GIESEKUS_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_GIESEKUS_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_PTT_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_PTT_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_FENE_P_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_P_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_FENE_CR_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_FENE_CR_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_WM_CY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_ROLIE_POLY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_ROLIE_POLY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_SARAMITO_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_SARAMITO_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_XPOMPOM_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+            }
+        }
+        if (h->rec3 && h->nRanks > 1 && all_reduce_ctl(h, h->d_red.as<double>() + MAX_RED, 3 * nrhs, CTL_INIT, nrhs, sc)) return 1;
+        if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
+
+        // ---- segregated solve: all valid components of the batch's modes on the shared matrix
         RhsPtrs rp;
         rp.n = 0;
         for (int mi = m0; mi < m1; ++mi)
             for (int j = 0; j < h->nComp; ++j) {
                 rp.psi[rp.n] = h->modes[mi].theta.as<double>() + (size_t)h->comps[j] * NP;
                 rp.b[rp.n] = h->modes[mi].bsrc.as<double>() + (size_t)h->comps[j] * NP;
-                rp.corr[rp.n] = (h->lim.hrs && !noConv) ? h->modes[mi].corr.as<double>() + (size_t)j * h->K * h->NS : nullptr;
+                rp.corr[rp.n] = hrs ? h->modes[mi].corr.as<double>() + (size_t)j * h->K * h->NS : nullptr;
                 rp.n++;
             }
         int iters = 0;
         int rc;
+        const bool initDone = h->rec3;   // k_source_init has formed r, r0, the norm factor and the initial residual
         if (pbicg) {
             if (h->nComp == 6) rc = (h->K == 6) ? solve_batch_pbicg<6, 6>(h, rp, m0, m1 - m0, &iters) : solve_batch_pbicg<6, 0>(h, rp, m0, m1 - m0, &iters);
             else rc = (h->K == 4) ? solve_batch_pbicg<4, 4>(h, rp, m0, m1 - m0, &iters) : solve_batch_pbicg<4, 0>(h, rp, m0, m1 - m0, &iters);
-        } else if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m0, m1 - m0, &iters) : solve_batch<6, 0>(h, rp, m0, m1 - m0, &iters);
-        else rc = (h->K == 4) ? solve_batch<4, 4>(h, rp, m0, m1 - m0, &iters) : solve_batch<4, 0>(h, rp, m0, m1 - m0, &iters);
+        } else if (h->nComp == 6) rc = (h->K == 6) ? solve_batch<6, 6>(h, rp, m0, m1 - m0, &iters, initDone) : solve_batch<6, 0>(h, rp, m0, m1 - m0, &iters, false);
+        else rc = (h->K == 4) ? solve_batch<4, 4>(h, rp, m0, m1 - m0, &iters, initDone) : solve_batch<4, 0>(h, rp, m0, m1 - m0, &iters, false);
         if (rc) return rc;
         h->specIters = std::max(1, iters);
         int q = 0;
@@ -986,6 +1058,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             }
             if (stats) for (int cmp = 0; cmp < 6; ++cmp) if (std::find(h->comps, h->comps + h->nComp, cmp) == h->comps + h->nComp) stats[mi].converged[cmp] = 1;
         }
+        if (h->timing) { cudaEventRecord(e0, h->stream); cudaEventSynchronize(e0); float ms; cudaEventElapsedTime(&ms, e1, e0); msSolve += ms; }
     }
     if (h->timing) cudaEventRecord(h->ev[3], h->stream);
 
@@ -1050,7 +1123,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         float ms;
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->phaseMs[0] = ms;
         h->phaseMs[1] = msGrad; h->phaseMs[2] = msAsm;
-        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); h->phaseMs[3] = ms;
+        h->phaseMs[3] = msSolve;
         cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->phaseMs[4] = ms;
         cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); h->phaseMs[5] = ms;
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[5]); h->phaseMs[6] = ms;
@@ -1127,7 +1200,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_FsT, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
-                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev})
+                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev, &h->d_rowsum, &h->d_inflow, &h->d_tileOrder})
         b->release();
     for (ModeDev& md : h->modes)
         for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0, &md.lamCell, &md.etaCell}) b->release();

@@ -234,7 +234,7 @@ int precond_spmv_blocks(RheoGpu* h, int nModes, const SolveCtl& sc) {
 }
 
 template <int NR, int KT>
-int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* itersOut) {
+int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* itersOut, bool initDone) {
     const int nrhs = nModes * NR, N = h->N, NP = h->NP;
     KrylovShared* ks = h->d_ks.as<KrylovShared>();
     double* part = h->d_partials.as<double>();
@@ -251,11 +251,14 @@ int solve_batch(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, int* i
     // gAverage(psi), initial residual + normFactor.  (psi = theta: its processor-patch values were swapped at the start of
     // the step and nothing has written theta since, so the ghost cells are current.)
     // gAverage(psi): the per-component sums were accumulated by k_cell_source2 while it had theta in registers
-    double* sumPsi = h->d_sumPsi.as<double>() + (size_t)firstMode * NR;
-    if (all_reduce(h, sumPsi, nrhs)) return 1;
-    LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, r, r0, part, redB, counter,
-           multi ? CTL_NONE : CTL_INIT, ks, sc);
-    if (multi && all_reduce_ctl(h, redB, 3 * nrhs, CTL_INIT, nrhs, sc)) return 1;
+    // initDone: k_source_init (assembly3.cuh) has done all of this, fused with the per-cell source
+    if (!initDone) {
+        double* sumPsi = h->d_sumPsi.as<double>() + (size_t)firstMode * NR;
+        if (all_reduce(h, sumPsi, nrhs)) return 1;
+        LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, r, r0, part, redB, counter,
+               multi ? CTL_NONE : CTL_INIT, ks, sc);
+        if (multi && all_reduce_ctl(h, redB, 3 * nrhs, CTL_INIT, nrhs, sc)) return 1;
+    }
     int launched = 0;
     int spec = std::max(1, h->specIters);
     for (;;) {

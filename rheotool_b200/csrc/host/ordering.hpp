@@ -41,6 +41,11 @@ struct BlockOrdering {
     int nColours = 0;
     int tile[3] = {0, 0, 0};        // block shape in lattice cells
     int dims[3] = {0, 0, 0};        // lattice extents
+    std::vector<int> sweepOrder;    // [nChunks] chunk positions (new cell number / CHUNK) in geometric order: super-blocks of 8x8x8 blocks in
+                                    // lexicographic order, blocks in lexicographic order inside.  Kernels without an ordering constraint
+                                    // (the assembly) walk the chunks in this order, so that the chunks in flight at any time are
+                                    // neighbours in space and find each other's values in L2 — the numbering itself puts every
+                                    // neighbour of a chunk into ANOTHER colour, i.e. (with 2 colours) half the mesh away in memory.
 };
 
 // lattice index of every cell along axis d (sorted unique centre coordinates within tol), or false if there are more than
@@ -122,6 +127,16 @@ inline bool block_renumber(int N, int nInt, const int32_t* own, const int32_t* n
         std::sort(seq.begin() + start[q], seq.begin() + start[q + 1], [&](int a, int b) { return local[a] < local[b] || (local[a] == local[b] && a < b); });
     // ---- chunks of CHUNK consecutive cells of that sequence; chunk graph; greedy colouring in chunk order
     const int nChunks = (N + CHUNK - 1) / CHUNK;
+    std::vector<long> chunkKey(nChunks);   // geometric key of the chunk = that of the block its first cell lies in
+    {
+        constexpr long SB = 8;
+        const long nS[2] = {(nT[0] + SB - 1) / SB, (nT[1] + SB - 1) / SB};
+        for (int q = 0; q < nChunks; ++q) {
+            const long tid = tileOf[seq[(size_t)q * CHUNK]];
+            const long bi = tid % nT[0], bj = (tid / nT[0]) % nT[1], bk = tid / (nT[0] * nT[1]);
+            chunkKey[q] = ((((bk / SB) * nS[1] + bj / SB) * nS[0] + bi / SB) * SB * SB * SB) + ((bk % SB) * SB + bj % SB) * SB + bi % SB;
+        }
+    }
     std::vector<int>& chunkOf = tileOf;   // reuse
     for (int p = 0; p < N; ++p) chunkOf[seq[p]] = p / CHUNK;
     std::vector<int> adjStart((size_t)nChunks + 1, 0);
@@ -160,12 +175,19 @@ inline bool block_renumber(int N, int nInt, const int32_t* own, const int32_t* n
     for (int c = 0; c < nCol; ++c) out.colourStart[c + 1] += out.colourStart[c];
     std::vector<int> pos(out.colourStart.begin(), out.colourStart.end() - 1);
     out.perm.resize(N);
+    std::vector<int> newChunk(nChunks);
     for (int q = 0; q < nChunks; ++q) {
         const int n = std::min(CHUNK, N - q * CHUNK);
         int& p = pos[colour[q]];
         for (int e = 0; e < n; ++e) out.perm[p + e] = seq[(size_t)q * CHUNK + e];
+        newChunk[q] = p / CHUNK;
         p += n;
     }
+    std::vector<int> byKey(nChunks);
+    for (int q = 0; q < nChunks; ++q) byKey[q] = q;
+    std::stable_sort(byKey.begin(), byKey.end(), [&](int a, int b) { return chunkKey[a] < chunkKey[b]; });
+    out.sweepOrder.resize(nChunks);
+    for (int q = 0; q < nChunks; ++q) out.sweepOrder[q] = newChunk[byKey[q]];
     return true;
 }
 
