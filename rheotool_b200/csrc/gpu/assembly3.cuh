@@ -42,10 +42,10 @@ namespace rk {
 __host__ __device__ constexpr size_t tile_record3_bytes(int K) { return (size_t)K * TILE * (2 * sizeof(int) + 6 * sizeof(double)) + 4 * TILE * sizeof(double); }
 
 #ifndef RK_FLUX3_DEPTH
-#define RK_FLUX3_DEPTH 2   // fields gathered ahead of the one being worked on
+#define RK_FLUX3_DEPTH 1   // fields gathered ahead of the one being worked on (2 with 12 warps per SM measured the same: r3d/r3f)
 #endif
 #ifndef RK_FLUX3_MINB
-#define RK_FLUX3_MINB 12   // resident single-warp CTAs per SM k_flux3 is compiled for (register cap 65536 / (32 * MINB); 13.3 KB of shared memory each)
+#define RK_FLUX3_MINB 16   // resident single-warp CTAs per SM k_flux3 is compiled for (register cap 65536 / (32 * MINB); 13.3 KB of shared memory each)
 #endif
 
 // The per-slot vectors G and D stay in the shared-memory stage for the whole tile (the first version copied them to registers:
@@ -81,9 +81,7 @@ __global__ void __launch_bounds__(TILE, RK_FLUX3_MINB) k_flux3(MeshView m, FluxA
     const double* sD = sG + 3 * KTL;                                                      // [3][K][TILE]
     const double* sG0 = sD + 3 * KTL;                                                     // [3][TILE], then V[TILE]
     const double* sF = (const double*)(smemRaw + recBytes) + lane;
-    double sumTh[NC];
-#pragma unroll
-    for (int g = 0; g < NC; ++g) sumTh[g] = 0.0;
+    double sumTh = 0.0;   // lane g < NC: this warp's running sum of theta component g (warp-reduced tile by tile: 2 registers instead of 2 NC)
 
     int it = 0;
     for (int t = blockIdx.x; t < nTiles; t += gridDim.x, ++it) {
@@ -96,6 +94,7 @@ __global__ void __launch_bounds__(TILE, RK_FLUX3_MINB) k_flux3(MeshView m, FluxA
         }
         mbar_wait(&full, (uint32_t)(it & 1));
         const int c = tile * TILE + lane;
+        const unsigned vmask = __ballot_sync(0xffffffffu, c < m.N);
         if (c < m.N) {
             // ---- per-slot quantities shared by every field, packed: bit s + base of `fl`; reverse slots 3 bits each in `rev`
             enum : unsigned { UP = 0, GHOST = 6, FIXEDB = 12, GB = 18, CELL = 24 };
@@ -195,7 +194,19 @@ __global__ void __launch_bounds__(TILE, RK_FLUX3_MINB) k_flux3(MeshView m, FluxA
                 // ---- theta component g
                 const int g = f - 3 < NC ? f - 3 : 0;
                 const int k = a.cl.c[g];
-                sumTh[g] += tP;
+                {
+                    double x = tP;
+                    if (vmask == 0xffffffffu) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+                    } else {   // the mesh's one partial tile
+                        double tot = 0.0;
+                        for (int l = 0; l < 32; ++l)
+                            if ((vmask >> l) & 1u) tot += __shfl_sync(vmask, x, l);
+                        x = tot;
+                    }
+                    if (lane == g) sumTh += x;
+                }
                 // A theta of the first residual (lduMatrix::Amul incl. the processor interfaces; slot order as k_krylov_init)
                 double ac = Dfull * tP;
 #pragma unroll
@@ -244,13 +255,7 @@ __global__ void __launch_bounds__(TILE, RK_FLUX3_MINB) k_flux3(MeshView m, FluxA
 
     // ---- sum(theta) per solved component (gAverage(psi) of the solver's normFactor): warp sums, the last CTA adds them in CTA order
     if (a.sumOut == nullptr) return;
-#pragma unroll
-    for (int g = 0; g < NC; ++g) {
-        double x = sumTh[g];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if (lane == 0) a.sumPartials[(size_t)blockIdx.x * NC + g] = x;
-    }
+    if (lane < NC) a.sumPartials[(size_t)blockIdx.x * NC + lane] = sumTh;
     __threadfence();
     unsigned last = 0;
     if (lane == 0) last = atomicAdd(a.counter, 1u) == gridDim.x - 1 ? 1u : 0u;
