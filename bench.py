@@ -10,8 +10,9 @@ Contract (see the task statement): `python bench.py --gpus N --steps K --warmup 
     the other BASELINE configurations; `--config C2 --weak` is round 1's weak-scaling family (~971k cells per GPU);
   * every run first solves a shrunk replica of the workload on the same ranks and compares it with the CPU oracle on ONE rank
     (`parity`), and prints a checksum of the full-size state after the timed steps (`state_check`: equal across N);
-  * `e2e` = the same metric through rheo_gpu_correct() with pinned HOST buffers (U, U_b, phi up; tau
-    down every step);
+  * `e2e` = the same metric through the C-ABI with pinned HOST buffers: U, U_b, phi up, rheo_gpu_correct(), then the explicit
+    part of constitutiveEq::divTau down (rheo_gpu_div_tau: 3 doubles per cell); `e2e_tau_download` = round 1's variant (tau
+    itself, 6 doubles per cell, comes back);
   * `--impl reference` times the CPU restatement of the reference algorithm (oracle/, OpenMP over sub-domains = one per
     host core, thread count set explicitly) on a bounded sample of the same workload (the same model, schemes and CFL on the
     1/8 sub-cube a rank of the 8-GPU run owns) — the reference binary itself cannot be built without OpenFOAM-9/Eigen/MPI
@@ -383,28 +384,45 @@ def run_ours(args):
     state_check = {"after_steps": args.warmup + args.steps, "theta_abs_sum": chk[0], "theta_sum": chk[1], "tau_abs_sum": chk[2],
                    "finite": finite, "note": "mode 0, summed over all ranks; equal across N for the same --config/--steps/--warmup"}
 
-    # ---- e2e through the C-ABI with pinned HOST buffers (upload U,U_b,phi; download tau) every step
+    # ---- e2e through the C-ABI with pinned HOST buffers, every step: upload U, U_b, phi; correct(); download what the CPU
+    # momentum predictor needs.  Two variants of that last leg:
+    #   e2e                the explicit part of constitutiveEq::divTau evaluated on the device (rheo_gpu_div_tau, stabilization
+    #                      coupling — 47 of the 52 tutorials), 3 doubles per cell come back; tau stays in HBM
+    #   e2e_tau_download   round 1's call: tau itself (6 doubles per cell) comes back and the host evaluates divTau
     hU = torch.from_numpy(U).pin_memory(); hUb = torch.from_numpy(Ub).pin_memory(); hphi = torch.from_numpy(phi).pin_memory()
     htau = torch.zeros((m.n_cells, 6), dtype=torch.float64).pin_memory()
+    hdiv = torch.zeros((m.n_cells, 3), dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
+
+    def e2e_tau():
         g.correct_host(hU.data_ptr(), hUb.data_ptr(), hphi.data_ptr(), dt, True, htau.data_ptr())
-    barrier()
-    tb0 = g.transfer_bytes()
-    t0 = time.perf_counter()
-    e0.record(ext)
-    for _ in range(e2e_steps):
-        g.correct_host(hU.data_ptr(), hUb.data_ptr(), hphi.data_ptr(), dt, True, htau.data_ptr())
-    e1.record(ext)
-    barrier()
-    wall = time.perf_counter() - t0
-    ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device="cuda")
-    if n > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = n_cells_total * e2e_steps / (float(ms2.item()) * 1e-3) / 1e6
-    tb1 = g.transfer_bytes()
-    h2d = (tb1[0] - tb0[0]) // e2e_steps   # counted inside the library from the copies it issued
-    d2h = (tb1[1] - tb0[1]) // e2e_steps
+
+    def e2e_div():
+        g.correct_host(hU.data_ptr(), hUb.data_ptr(), hphi.data_ptr(), dt, True, None)
+        g.div_tau_host(abi.STAB_COUPLING, hdiv.data_ptr())
+
+    def time_e2e(call):
+        for _ in range(2):
+            call()
+        barrier()
+        tb0 = g.transfer_bytes()
+        t0 = time.perf_counter()
+        e0.record(ext)
+        for _ in range(e2e_steps):
+            call()
+        e1.record(ext)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms2 = torch.tensor([max(e0.elapsed_time(e1), wall * 1e3)], dtype=torch.float64, device="cuda")
+        if n > 1:
+            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+        tb1 = g.transfer_bytes()
+        # bytes counted inside the library from the copies it issued
+        return n_cells_total * e2e_steps / (float(ms2.item()) * 1e-3) / 1e6, (tb1[0] - tb0[0]) // e2e_steps, (tb1[1] - tb0[1]) // e2e_steps
+
+    e2e_tau_value, h2d_tau, d2h_tau = time_e2e(e2e_tau)
+    e2e_value, h2d, d2h = time_e2e(e2e_div)
+    e2e_div_finite = bool(np.isfinite(hdiv.numpy()).all())
 
     # ---- roofline of the dominant kernel: per-kernel CUDA-event timing pass (serialised launches)
     roof = None
@@ -454,7 +472,10 @@ def run_ours(args):
                        "limiter": "cubista", "solver": args.solver + "+DILU", "tolerance": spec.schemes.tolerance,
                        "modes": len(spec.models), "decomposition": list(decomp),
                        "l2": "working set (~1.7 kB/cell) exceeds the 126 MB L2; no explicit flush"},
-            "e2e": {"value": e2e_value, "unit": "Mcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "Mcell-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "call": "rheo_gpu_correct(U, U_b, phi -> device) + rheo_gpu_div_tau(coupling -> host): 3 doubles per cell back", "finite": e2e_div_finite},
+            "e2e_tau_download": {"value": e2e_tau_value, "unit": "Mcell-steps/s", "h2d_bytes_per_step": h2d_tau, "d2h_bytes_per_step": d2h_tau, "steps": e2e_steps,
+                                 "call": "rheo_gpu_correct(U, U_b, phi -> device; tau -> host): 6 doubles per cell back (round 1's e2e)"},
             "gpu_launches": launches,
             "parity": parity,
             "state_check": state_check,

@@ -131,6 +131,11 @@ typedef struct RheoGpu RheoGpu;
 #define RHEO_FIELD_TAU_B_TOTAL 8 /* sum over modes of the boundary stress, 6/boundary face: what multiMode::divTau sees on the
                                     patches (each mode's own linearExtrapolation / zeroGradient / fixedValue values, summed) */
 
+/* constitutiveProperties `stabilization` (constitutiveEq/constitutiveEq.H: soNone, soBSD, soCoupling) */
+#define RHEO_STAB_NONE      0
+#define RHEO_STAB_BSD       1
+#define RHEO_STAB_COUPLING  2
+
 int rheo_gpu_device_count(void);
 
 /* Build the device-resident model.  The mesh arrays are only read during the call. */
@@ -183,6 +188,14 @@ int rheo_gpu_correct(RheoGpu* h, const double* U, const double* U_b, const doubl
 
 /* ---- introspection used by the parity tests and bench.py ---- */
 /* renumbering actually used on the device: perm[new] = old cell, n_colours, colour_start[n_colours+1] */
+/* Explicit part of constitutiveEq::divTau(U) (constitutiveEq/constitutiveEq.C:72-132, summed over the modes as
+ * multiMode/multiMode.C:143-157 does), evaluated on the device from the stress of the last step and the velocity last uploaded:
+ *   div_out[3*n_cells] = sum_modes fvc::div(tau_m/rho_m)  -  (RHEO_STAB_COUPLING only) fvc::div((etaP_m/rho_m) fvc::grad(U)),
+ * both `Gauss linear` (csrc/gpu/momentum.cuh).  The caller adds fvm::laplacian((etaP+etaS)/rho, U) (and, for RHEO_STAB_BSD,
+ * subtracts its own fvc::laplacian(etaP/rho, U)): with this call tau itself only leaves the device at write time.
+ * Collective over the ranks of a decomposed case (the velocity gradient of the ghost cells is swapped). */
+int rheo_gpu_div_tau(RheoGpu* h, int32_t stabilization, double* div_out);
+
 int rheo_gpu_get_renumbering(RheoGpu* h, int32_t* perm, int32_t* n_colours, int32_t* colour_start);
 /* one line of text naming the cell ordering the DILU substitutions run in on this handle, e.g.
  * "8x8x4 blocks (256 cells), natural order inside, 2 block colours" or "cell colouring, 2 colours" */

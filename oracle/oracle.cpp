@@ -1112,6 +1112,112 @@ void init_model(Model& mo) {
 }  // namespace
 
 // ==================================================================== C API (ctypes)
+// ------------------------------------------------------------------ explicit part of constitutiveEq::divTau
+// CE/constitutiveEq/constitutiveEq.C:72-132 (stabilization none / BSD / coupling) summed over the modes as multiMode.C:143-157
+// does; the divSchemes div(tau) and div(grad(U)) are `Gauss linear` in every tutorial.  EXT-OF9 (builder's reading, not in
+// /root/reference): gaussDivScheme::fvcDiv = fvc::surfaceIntegrate(Sf & linearInterpolate(vf)); gaussGrad::calcGrad ends with
+// correctBoundaryConditions: g_b += n (snGrad(U)_b - (n & g_b)) on non-coupled patches, g_b starting from the patch-internal
+// value; fvPatchField::snGrad = deltaCoeffs (U_b - U_c), deltaCoeffs = 1/|delta|, fvPatch::delta = n (n & (Cf - Cn)).
+// Fields here: X[9*cell + 3i + j] = X_ij with i the index contracted with Sf.
+static void gauss_div9(const Mesh& m, const double* X, const double* XfB, double sign, double* out) {
+    dvec tmp((size_t)3 * m.nCells, 0.0);
+    for (int f = 0; f < m.nInt; ++f) {
+        const int P = m.own[f], N = m.nei[f];
+        const double* S = &m.Sf[3 * (size_t)f];
+        for (int j = 0; j < 3; ++j) {
+            double v = 0;
+            for (int i = 0; i < 3; ++i) {
+                const double xf = m.w[f] * (X[(size_t)9 * P + 3 * i + j] - X[(size_t)9 * N + 3 * i + j]) + X[(size_t)9 * N + 3 * i + j];
+                v += S[i] * xf;
+            }
+            tmp[(size_t)3 * P + j] += v;
+            tmp[(size_t)3 * N + j] -= v;
+        }
+    }
+    for (const Patch& p : m.patches) {
+        if (p.type == RHEO_PATCH_EMPTY) continue;
+        for (int f = p.start; f < p.start + p.size; ++f) {
+            const int P = m.own[f];
+            const double* S = &m.Sf[3 * (size_t)f];
+            const double* xb = &XfB[(size_t)9 * (f - m.nInt)];
+            for (int j = 0; j < 3; ++j) tmp[(size_t)3 * P + j] += S[0] * xb[j] + S[1] * xb[3 + j] + S[2] * xb[6 + j];
+        }
+    }
+    for (int c = 0; c < m.nCells; ++c)
+        for (int j = 0; j < 3; ++j) out[(size_t)3 * c + j] += sign * (tmp[(size_t)3 * c + j] / m.V[c]);
+}
+
+// out[r]: [3 * nCells] per rank
+static int div_tau_explicit(Case& cs, int stab, std::vector<dvec>& out) {
+    const int R = (int)cs.ranks.size();
+    out.assign(R, dvec());
+    for (int r = 0; r < R; ++r) out[r].assign((size_t)3 * cs.ranks[r].mesh.nCells, 0.0);
+    const int nModes = (int)cs.ranks[0].modes.size();
+    std::vector<dvec> X(R), XB(R);
+    auto sym9 = [](const double* t, double s, double* x) {
+        x[0] = s * t[0]; x[1] = s * t[1]; x[2] = s * t[2]; x[3] = s * t[1]; x[4] = s * t[3]; x[5] = s * t[4]; x[6] = s * t[2]; x[7] = s * t[4]; x[8] = s * t[5];
+    };
+    for (int mi = 0; mi < nModes; ++mi) {
+        // ---- fvc::div(tau/rho)
+        for_ranks(cs, [&](int r) {
+            const Rank& rk = cs.ranks[r];
+            const Mode& mo = rk.modes[mi];
+            const double rr = 1.0 / mo.model.d.rho;
+            X[r].resize((size_t)9 * rk.mesh.nCells); XB[r].resize((size_t)9 * rk.mesh.nB());
+            for (int c = 0; c < rk.mesh.nCells; ++c) sym9(&mo.tau[(size_t)6 * c], rr, &X[r][(size_t)9 * c]);
+            for (int b = 0; b < rk.mesh.nB(); ++b) sym9(&mo.tauB[(size_t)6 * b], rr, &XB[r][(size_t)9 * b]);
+        });
+        for_ranks(cs, [&](int r) {
+            const Mesh& m = cs.ranks[r].mesh;
+            dvec fb((size_t)9 * m.nB(), 0.0);
+            face_values_boundary(cs, r, 9, [&](int q) { return X[q].data(); }, XB[r].data(), fb.data());
+            gauss_div9(m, X[r].data(), fb.data(), 1.0, out[r].data());
+        });
+        if (stab != RHEO_STAB_COUPLING) continue;
+        // ---- - fvc::div((etaP/rho) fvc::grad(U))
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            const Mesh& m = rk.mesh;
+            const Mode& mo = rk.modes[mi];
+            const double coef = mo.model.d.etaP / mo.model.d.rho;
+            dvec fb((size_t)3 * m.nB(), 0.0), g((size_t)9 * m.nCells);
+            face_values_boundary(cs, r, 3, [&](int q) { return cs.ranks[q].U.data(); }, rk.Ub.data(), fb.data());
+            gauss_grad(m, 3, rk.U.data(), fb.data(), g.data());   // g[9c + 3k + d] = d_d U_k
+            X[r].resize((size_t)9 * m.nCells); XB[r].assign((size_t)9 * m.nB(), 0.0);
+            for (int c = 0; c < m.nCells; ++c)
+                for (int i = 0; i < 3; ++i)
+                    for (int j = 0; j < 3; ++j) X[r][(size_t)9 * c + 3 * i + j] = g[(size_t)9 * c + 3 * j + i];   // (grad U)_ij = d_i U_j, not yet scaled
+            for (const Patch& p : m.patches) {
+                if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR) continue;
+                for (int f = p.start; f < p.start + p.size; ++f) {
+                    const int c = m.own[f], b = f - m.nInt;
+                    const double* S = &m.Sf[3 * (size_t)f];
+                    const double magS = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+                    const double n[3] = {S[0] / magS, S[1] / magS, S[2] / magS};
+                    double nd = 0;
+                    for (int d = 0; d < 3; ++d) nd += n[d] * (m.Cf[3 * (size_t)f + d] - m.C[3 * (size_t)c + d]);
+                    const double deltaCoeff = 1.0 / std::fabs(nd);
+                    for (int j = 0; j < 3; ++j) {
+                        const double sn = deltaCoeff * (rk.Ub[(size_t)3 * b + j] - rk.U[(size_t)3 * c + j]);
+                        double ng = 0;
+                        for (int k = 0; k < 3; ++k) ng += n[k] * X[r][(size_t)9 * c + 3 * k + j];
+                        for (int i = 0; i < 3; ++i) XB[r][(size_t)9 * b + 3 * i + j] = X[r][(size_t)9 * c + 3 * i + j] + n[i] * (sn - ng);
+                    }
+                }
+            }
+            for (double& x : X[r]) x *= coef;
+            for (double& x : XB[r]) x *= coef;
+        });
+        for_ranks(cs, [&](int r) {
+            const Mesh& m = cs.ranks[r].mesh;
+            dvec fb((size_t)9 * m.nB(), 0.0);
+            face_values_boundary(cs, r, 9, [&](int q) { return X[q].data(); }, XB[r].data(), fb.data());
+            gauss_div9(m, X[r].data(), fb.data(), -1.0, out[r].data());
+        });
+    }
+    return 0;
+}
+
 extern "C" {
 
 const char* orc_last_error(void) { return g_err.c_str(); }
@@ -1330,6 +1436,16 @@ void orc_tau(const RheoModelDesc* d, int n, const double* R9, const double* Lam9
     }
 }
 // Gauss-linear gradient of a scalar cell field on rank 0's mesh with given boundary face values
+// explicit part of divTau for `rank` (3 per cell); every rank is evaluated (the processor faces need the neighbours)
+int orc_div_tau(void* h, int rank, int stabilization, double* out) {
+    Case& cs = *(Case*)h;
+    if (stabilization != RHEO_STAB_NONE && stabilization != RHEO_STAB_BSD && stabilization != RHEO_STAB_COUPLING) { g_err = "orc_div_tau: unknown stabilization"; return 3; }
+    std::vector<dvec> all;
+    if (div_tau_explicit(cs, stabilization, all)) return 3;
+    std::copy(all[rank].begin(), all[rank].end(), out);
+    return 0;
+}
+
 int orc_gauss_grad(void* h, int rank, int nc, const double* psi, const double* faceB, double* out) {
     Case& cs = *(Case*)h;
     gauss_grad(cs.ranks[rank].mesh, nc, psi, faceB, out);

@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
             "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
             "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_model_rhs_tau": (None, [P, I, P, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
-            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
+            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_div_tau": (I, [P, I, I, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -117,6 +117,14 @@ class OracleCase:
         rows = nb if field in (4, 5) else n
         out = np.zeros((rows, FIELD_WIDTH[field]))
         if lib().orc_get(self._h, rank, mode, field, _p(out)):
+            raise RuntimeError(lib().orc_last_error().decode())
+        return out
+
+    def div_tau(self, rank, stabilization):
+        """explicit part of constitutiveEq::divTau (constitutiveEq.C:72-132; multiMode.C:143-157), 3 per cell of `rank`"""
+        n, _ = self.sizes[rank]
+        out = np.zeros((n, 3))
+        if lib().orc_div_tau(self._h, rank, int(stabilization), _p(out)):
             raise RuntimeError(lib().orc_last_error().decode())
         return out
 

@@ -22,6 +22,7 @@ LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "supe
 DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON, DDT_STEADY_STATE = 0, 1, 2, 3
 THERMO = {"Constant": 0, "Arrhenius": 1, "ArrheniusModified": 2, "WLF": 3, "VFT": 4}   # thermoFunctions/* type names
 SOLVER = {"PBiCGStab": 0, "PBiCG": 1}
+STAB_NONE, STAB_BSD, STAB_COUPLING = range(3)   # constitutiveProperties `stabilization`
 FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD, FIELD_TAU_B_TOTAL = range(9)
 FLOW_CONTRACTION_2D, FLOW_VORTEX, FLOW_CONTRACTION_3D = 0, 1, 2
 
@@ -122,6 +123,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_step": (C.c_int, [_P, _D, _P]),
     "rheo_gpu_download": (C.c_int, [_P, _I, _I, _P]),
     "rheo_gpu_correct": (C.c_int, [_P, _P, _P, _P, _D, _I, _P, _P, _P]),
+    "rheo_gpu_div_tau": (C.c_int, [_P, _I, _P]),
     "rheo_gpu_get_renumbering": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ell": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ordering": (C.c_int, [_P, _P, _I]),

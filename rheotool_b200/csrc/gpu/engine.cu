@@ -27,6 +27,7 @@
 #include "pbicg.cuh"
 #include "assembly.cuh"
 #include "assembly3.cuh"
+#include "momentum.cuh"
 #include "peer.cuh"
 #include "rheo_gpu.h"
 
@@ -135,6 +136,7 @@ struct RheoGpu {
     bool rec3 = false;             // d_tileRec holds version-3 records: k_flux3 + k_source_init run instead of k_flux_assemble + k_cell_source2 + k_krylov_init
     std::vector<int> sweepOrder;   // block ordering: chunks in geometric order (host/ordering.hpp)
     DevBuf d_tileOrder;            // rec3: the assembly's tile walk (sweepOrder padded to nTiles); RHEO_TILE_ORDER=0 walks in index order
+    DevBuf d_gradUb;               // [9][nB] patch values of fvc::grad(U) (rheo_gpu_div_tau, allocated on first use)
     DevBuf d_rowsum, d_inflow;     // rec3: row sums of the matrix and inflow-slot masks (written by k_flux3 with the matrix)
     MeshView mv;
     // fields
@@ -1200,7 +1202,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_FsT, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
-                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev, &h->d_rowsum, &h->d_inflow, &h->d_tileOrder})
+                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev, &h->d_rowsum, &h->d_inflow, &h->d_tileOrder, &h->d_gradUb})
         b->release();
     for (ModeDev& md : h->modes)
         for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0, &md.lamCell, &md.etaCell}) b->release();
@@ -1357,6 +1359,39 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
     }
     if (bytes) CK(cudaMemcpyAsync(dst, stage, bytes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->d2hBytes += (long long)bytes * sizeof(double);
+    CK(cudaStreamSynchronize(h->stream));
+    return check_peer_err(h);
+}
+
+// constitutiveEq::divTau, explicit part (momentum.cuh)
+int rheo_gpu_div_tau(RheoGpu* h, int32_t stabilization, double* div_out) {
+    if (!h || !div_out) return fail("rheo_gpu_div_tau: null argument");
+    if (stabilization != RHEO_STAB_NONE && stabilization != RHEO_STAB_BSD && stabilization != RHEO_STAB_COUPLING) return fail("rheo_gpu_div_tau: unknown stabilization");
+    if ((int)h->modes.size() > MAX_MODES_DIV) return fail("rheo_gpu_div_tau: more than 8 modes");
+    CK(cudaSetDevice(h->device));
+    const bool coupling = stabilization == RHEO_STAB_COUPLING;
+    DivTauArgs a{};
+    a.nModes = (int)h->modes.size();
+    for (int mi = 0; mi < a.nModes; ++mi) {
+        ModeDev& md = h->modes[mi];
+        if (coupling && md.etaCell.p) return fail("rheo_gpu_div_tau: stabilization coupling with a temperature-dependent etaP is not implemented (download tau instead)");
+        a.tau[mi] = md.tau.as<double>(); a.tauB[mi] = md.tauB.as<double>();
+        a.rRho[mi] = 1.0 / md.desc.rho;
+        if (coupling) a.coefGrad += md.desc.etaP / md.desc.rho;
+    }
+    a.gradU = h->d_gradU.as<double>(); a.U = h->d_U.as<double>(); a.Ub = h->d_Ub.as<double>();
+    a.perm = h->d_perm.as<int>(); a.out = h->d_stage.as<double>();
+    if (coupling) {
+        if (h->H && halo_planes(h, h->d_gradU.as<double>(), 9)) return 1;
+        if (h->nB) {
+            if (!h->d_gradUb.p && h->d_gradUb.alloc((size_t)9 * h->nB * sizeof(double))) return 1;
+            LAUNCH(h, k_gradU_patch, cdiv(h->nB, BLOCK), BLOCK, h->mv, a.gradU, a.U, a.Ub, h->d_gradUb.as<double>());
+        }
+        a.gradUb = h->d_gradUb.as<double>();
+    }
+    LAUNCH(h, k_div_tau, cdiv(h->N, BLOCK), BLOCK, h->mv, a);
+    CK(cudaMemcpyAsync(div_out, h->d_stage.p, (size_t)h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    h->d2hBytes += (long long)h->N * 3 * sizeof(double);
     CK(cudaStreamSynchronize(h->stream));
     return check_peer_err(h);
 }

@@ -104,6 +104,18 @@ class GpuStressModel:
         """upload + correct + tau download through the one-call C entry point (host buffers)."""
         _check(abi.lib().rheo_gpu_correct(self._h, U_ptr, Ub_ptr, phi_ptr, float(dt), 1 if new_time_step else 0, tau_out_ptr, tau_b_out_ptr, None))
 
+    def div_tau(self, stabilization: int = abi.STAB_COUPLING, out: np.ndarray | None = None) -> np.ndarray:
+        """Explicit part of constitutiveEq::divTau(U) (constitutiveEq.C:72-132; multiMode.C:143-157), evaluated on the device:
+        sum over modes of fvc::div(tau/rho) [- fvc::div((etaP/rho) grad(U)) with stabilization coupling], 3 per cell."""
+        if out is None:
+            out = np.zeros((self.mesh.n_cells, 3))
+        _check(abi.lib().rheo_gpu_div_tau(self._h, int(stabilization), _p(out)))
+        return out
+
+    def div_tau_host(self, stabilization: int, out_ptr):
+        """div_tau into a caller-owned (pinned) host buffer."""
+        _check(abi.lib().rheo_gpu_div_tau(self._h, int(stabilization), out_ptr))
+
     def download(self, field: int, mode: int = 0) -> np.ndarray:
         n = self.mesh.n_boundary if field in (abi.FIELD_THETA_B, abi.FIELD_TAU_B, abi.FIELD_TAU_B_TOTAL) else self.mesh.n_cells
         w = 9 if field in (abi.FIELD_EIGVALS, abi.FIELD_EIGVECS) else 6

@@ -96,7 +96,8 @@ def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol):
             g.store_old_time()
             g.correct(dt)
             iters.append(g.last_iterations())
-        np.savez(Path(out_dir) / f"gpu_rank{rank}.npz", cells=part.global_cells(), dt=dt, iters=np.array(iters),
+        div_tau = g.div_tau(abi.STAB_COUPLING)   # collective: swaps the velocity gradient of the ghost cells
+        np.savez(Path(out_dir) / f"gpu_rank{rank}.npz", cells=part.global_cells(), dt=dt, iters=np.array(iters), div_tau=div_tau,
                  **{f"theta{mi}": g.theta(mi) for mi in range(len(spec.models))},
                  **{f"tau{mi}": g.tau(mi) for mi in range(len(spec.models))})
         g.close()

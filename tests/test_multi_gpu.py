@@ -55,3 +55,10 @@ def test_decomposed_gpu_run_matches_single_rank_oracle(case, scale, decomp, step
                 got[d["cells"]] = d[f"{name}{mi}"]
             err = rel_l2(got, ref)
             assert err <= 1e-10, f"{case} {decomp} mode {mi} {name}: rel L2 {err:.3e}"
+    # explicit part of constitutiveEq::divTau across the processor patches (constitutiveEq.C:72-132, stabilization coupling)
+    ref = oc.div_tau(0, abi.STAB_COUPLING)
+    got = np.full_like(ref, np.nan)
+    for d in ranks:
+        got[d["cells"]] = d["div_tau"]
+    err = rel_l2(got, ref)
+    assert err <= 1e-10, f"{case} {decomp} divTau: rel L2 {err:.3e}"
