@@ -49,6 +49,10 @@ extern "C" {
 #define RHEO_MODEL_ROLIE_POLY_LOG 6  /* Rolie-Poly/Rolie-PolyLog/RoliePolyLog.C:130-215 (lambda = lambdaD) */
 #define RHEO_MODEL_XPOMPOM_LOG   7   /* XPomPom/XPomPomLog/XPomPomLog.C:130-198 (lambda = lambdaB, alpha = anisotropy) */
 
+#define RHEO_MODEL_BMP_LOG       9   /* otherModels/BMP/BMPLog/BMPLog.C:142-201 (thixotropic: the fluidity Phi obeys its own transport
+                                       equation, solved before theta in every correct(); single-mode only) */
+#define RHEO_MODEL_BMP_FLUIDITY  10  /* internal: the fluidity equation of a BMPLog mode (BMPLog.C:151-163), carried as component xx of
+                                       a padded symmTensor through the same assembly and solver; not selectable by the caller */
 #define RHEO_MODEL_SARAMITO_LOG  8   /* otherModels/Saramito/SaramitoLog/SaramitoLog.C:143-245 (elasto-viscoplastic: the relaxation
                                         term is switched by max(0, (|tau_d| - tau0)/(k |tau_d|^n))^(1/n) of the CURRENT tau) */
 /* PTTLog destructionFunctionType (PTT/PTTLog/PTTLog.C:41-50,190-237) */
@@ -92,6 +96,9 @@ typedef struct RheoModelDesc {
                                          index; epsilon / zeta / ptt_function (linear | exponential, only with n == 1) as for PTTLog */
     double  sar_dims[3];              /* SaramitoLog `dims` (1 = valid geometric direction, SaramitoLog.C:117-119,128-130)           */
     int32_t sar_ptt;                  /* SaramitoLog PTTfunction: 0 none, 1 linear, 2 exponential (SaramitoLog.C:133-165)            */
+    double  bmp_G0, bmp_k, bmp_Phi0, bmp_PhiInf;   /* BMPLog (BMPLog.C:129-136): elastic modulus, structure break-down constant, zero- and
+                                                      infinite-shear fluidities; lambda = structure build-up time; etaP only enters divTau */
+    double  bmp_relax;                /* relaxationFactors.equations.Phi (PhiEqn.relax(), BMPLog.C:165); <= 0 : no-op                */
 } RheoModelDesc;
 
 typedef struct RheoSchemeCtl {
@@ -128,6 +135,8 @@ typedef struct RheoGpu RheoGpu;
 #define RHEO_FIELD_TAU_B      5  /* symmTensor, 6/boundary face */
 #define RHEO_FIELD_TAU_TOTAL  6  /* sum over modes of tau, 6/cell (multiMode::tau) */
 #define RHEO_FIELD_THETA_OLD  7
+#define RHEO_FIELD_FLUIDITY    9  /* BMPLog: Phi, 1/cell      */
+#define RHEO_FIELD_FLUIDITY_B  10 /* BMPLog: Phi, 1/boundary face */
 #define RHEO_FIELD_TAU_B_TOTAL 8 /* sum over modes of the boundary stress, 6/boundary face: what multiMode::divTau sees on the
                                     patches (each mode's own linearExtrapolation / zeroGradient / fixedValue values, summed) */
 
@@ -154,6 +163,10 @@ int rheo_gpu_comm_init(RheoGpu* h, int32_t rank, int32_t n_ranks, const void* id
 int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const double* tau,
                           const double* eigvals, const double* eigvecs,
                           const double* theta_b, const double* tau_b);
+
+/* BMPLog: the fluidity field Phi (MUST_READ in BMPLog.C:112-122) of `mode`: Phi[n_cells], Phi_b[n_boundary_faces] or NULL (boundary
+ * values derived from the BC kinds, which are those of theta: fixedValue patches then hold 0). */
+int rheo_gpu_upload_fluidity(RheoGpu* h, int32_t mode, const double* Phi, const double* Phi_b);
 
 /* U [3*n_cells], U_b [3*n_boundary_faces] (faces of processor/empty patches are neither read nor copied),
  * phi [n_faces] (internal then boundary; faces of empty patches are neither read nor copied — OpenFOAM's

@@ -100,6 +100,7 @@ struct Mesh {
 
 struct Model {
     RheoModelDesc d;
+    double phiCell = 0;   // BMPLog: this cell's fluidity (set by Mode::at)
     dvec gammaVals;   // CE/PTT/PTTLog/PTTLog.C:143-170
     int mlMaxIter = 0;
 };
@@ -110,11 +111,19 @@ struct Mode {
     dvec ddt0;                // CrankNicolson: the scheme's ddt0 field (EXT-OF9 CrankNicolsonDdtScheme::ddt0_)
     int ddt0TimeIndex = 0;    //                 time step at which ddt0 was last evaluated
     dvec lambdaCell, etaPCell;   // thermo-dependent lambda / etaP per cell (Oldroyd_BLog.C:133-135: createField); empty = the scalars
-    // the model with this cell's lambda / etaP
+    // BMPLog (BMPLog.C:142-201).  The fluidity equation is a scalar transport equation with theta's convection scheme and
+    // solver; EXT-OF9 solves a symmTensor matrix component by component with the very algorithm it applies to a scalar one, so
+    // Phi is carried as component xx of a hidden mode (model RHEO_MODEL_BMP_FLUIDITY) whose other components are identically 0
+    // (zero source, zero initial residual, no iterations): its theta = [Phi, 0, 0, 0, 0, 0].
+    int fluidityMode = -1;    // BMPLog mode: index of its hidden fluidity mode
+    int fluidityOf = -1;      // hidden fluidity mode: index of the BMPLog mode it belongs to
+    const dvec* fluidity = nullptr;   // BMPLog mode during correct(): the hidden mode's theta (Phi = [6 c])
+    bool per_cell() const { return !lambdaCell.empty() || fluidity != nullptr; }
+    // the model with this cell's lambda / etaP / fluidity
     Model at(int c) const {
-        if (lambdaCell.empty()) return model;
         Model q = model;
-        q.d.lambda = lambdaCell[c]; q.d.etaP = etaPCell[c];
+        if (!lambdaCell.empty()) { q.d.lambda = lambdaCell[c]; q.d.etaP = etaPCell[c]; }
+        if (fluidity) q.phiCell = (*fluidity)[(size_t)6 * c];
         return q;
     }
 };
@@ -327,6 +336,14 @@ double mittag_leffler(const Model& mo, double zi) {
 //   SaramitoLog.C:150-238 (tau6 = the model's CURRENT tau of the cell; unused by the other models)
 double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const T9& R, const T9& Lam, double* rhs6, const double* tau6 = nullptr) {
     const RheoModelDesc& d = mo.d;
+    if (d.model == RHEO_MODEL_BMP_FLUIDITY) {   // BMPLog.C:158-160: Phi0/lambda + k (PhiInf - Phi) (tau && symm(L)); -Sp(1/lambda) is on the diagonal
+        double s6[6];
+        symm(L, s6);
+        const double tD = tau6[0] * s6[0] + tau6[3] * s6[3] + tau6[5] * s6[5] + 2.0 * (tau6[1] * s6[1] + tau6[2] * s6[2] + tau6[4] * s6[4]);
+        rhs6[0] = d.bmp_Phi0 / d.lambda + d.bmp_k * (d.bmp_PhiInf - theta6[0]) * tD;
+        for (int q = 1; q < 6; ++q) rhs6[q] = 0.0;
+        return 0.0;
+    }
     T9 omega, B;
     // boilerLog.H:26: the zeta-branch is compiled for PTTLog and SaramitoLog
     decompose_gradU_cell(L, R, Lam, d.zeta, d.model == RHEO_MODEL_PTT_LOG || d.model == RHEO_MODEL_SARAMITO_LOG, omega, B);
@@ -347,6 +364,9 @@ double model_rhs_cell(const Model& mo, const T9& L, const double* theta6, const 
         }
         case RHEO_MODEL_OLDROYD_B_LOG:
             acc = add(acc, scale(1.0 / d.lambda, innerP(R, sub(inv(Lam), I), false)));
+            break;
+        case RHEO_MODEL_BMP_LOG:   // BMPLog.C:177-185: (Phi G0) (eigVecs & (inv(eigVals) - I) & eigVecs.T()), Phi of AFTER PhiEqn.solve()
+            acc = add(acc, scale(mo.phiCell * d.bmp_G0, mul(mul(R, sub(inv(Lam), I)), transpose(R))));
             break;
         case RHEO_MODEL_GIESEKUS_LOG: {
             const T9 trhs = mul(mul(R, sub(inv(Lam), I)), transpose(R));
@@ -441,7 +461,10 @@ void tau_cell(const Model& mo, const T9& R, const T9& Lam, double fOld, double* 
     const T9 I = identity();
     double s[6];
     double coef = d.etaP / d.lambda;
-    if (d.model == RHEO_MODEL_FENE_P_LOG) {
+    if (d.model == RHEO_MODEL_BMP_LOG) {   // BMPLog.C:196: tau = G0 symm((eigVecs & eigVals & eigVecs.T()) - I)
+        symm(sub(mul(mul(R, Lam), transpose(R)), I), s);
+        coef = d.bmp_G0;
+    } else if (d.model == RHEO_MODEL_FENE_P_LOG) {
         const double a = d.L2 / (d.L2 - 3.);
         symm(sub(scale(fOld, A), scale(a, I)), s);
     } else {
@@ -777,8 +800,10 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
             Model tmp;
             const Model* pm = &mo.model;
-            if (!mo.lambdaCell.empty()) { tmp = mo.at(c); pm = &tmp; }
-            rk.fFene[c] = model_rhs_cell(*pm, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c], &mo.tau[(size_t)6 * c]);
+            if (mo.per_cell()) { tmp = mo.at(c); pm = &tmp; }
+            // the fluidity equation's source reads the stress of the BMPLog mode it belongs to (BMPLog.C:160: tau_ && symm(L))
+            const dvec& tauSrc = mo.fluidityOf >= 0 ? rk.modes[mo.fluidityOf].tau : mo.tau;
+            rk.fFene[c] = model_rhs_cell(*pm, L, &mo.theta[(size_t)6 * c], Rm, Lam, &rk.rhs[(size_t)6 * c], &tauSrc[(size_t)6 * c]);
         }
     });
 
@@ -940,8 +965,17 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
     });
 
     // --- thetaEqn.relax()  (EXT-OF9 fvMatrix::relax; only with a relaxation factor in fvSolution)
-    if (ctl.relax > 0) {
-        const double alpha = ctl.relax;
+    const bool isFluidity = cs.ranks[0].modes[mi].model.d.model == RHEO_MODEL_BMP_FLUIDITY;
+    if (isFluidity) {   // == - fvm::Sp(1/lambda, Phi) (BMPLog.C:158): EXT-OF9 fvm::Sp adds V sp to the diagonal; `A == B` is A - B
+        for_ranks(cs, [&](int r) {
+            Rank& rk = cs.ranks[r];
+            const double rl = 1.0 / rk.modes[mi].model.d.lambda;
+            for (int c = 0; c < rk.mesh.nCells; ++c) rk.diag[c] += rl * rk.mesh.V[c];
+        });
+    }
+    const double relaxFactor = isFluidity ? cs.ranks[0].modes[mi].model.d.bmp_relax : ctl.relax;   // PhiEqn.relax() / thetaEqn.relax()
+    if (relaxFactor > 0) {
+        const double alpha = relaxFactor;
         for_ranks(cs, [&](int r) {
             Rank& rk = cs.ranks[r];
             Mode& mo = rk.modes[mi];
@@ -1023,6 +1057,7 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             if (p.theta_bc == RHEO_BC_ZERO_GRADIENT && p.type != RHEO_PATCH_EMPTY)
                 for (int f = p.start; f < p.start + p.size; ++f)
                     for (int q = 0; q < 6; ++q) mo.thetaB[(size_t)6 * (f - m.nInt) + q] = mo.theta[(size_t)6 * m.own[f] + q];
+        if (isFluidity) return;   // the fluidity has no eigen-decomposition and no stress of its own
         for (int c = 0; c < m.nCells; ++c) {
             calc_eig_cell(&mo.theta[(size_t)6 * c], &mo.eigVals[(size_t)9 * c], &mo.eigVecs[(size_t)9 * c], cs.sortEig);
             T9 Rm, Lam;
@@ -1030,13 +1065,14 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
             std::memcpy(Lam.v, &mo.eigVals[(size_t)9 * c], 72);
             Model tmp;
             const Model* pm = &mo.model;
-            if (!mo.lambdaCell.empty()) { tmp = mo.at(c); pm = &tmp; }
+            if (mo.per_cell()) { tmp = mo.at(c); pm = &tmp; }
             tau_cell(*pm, Rm, Lam, rk.fFene[c], &mo.tau[(size_t)6 * c]);
         }
     });
     // tau BCs: processor values first (all sends complete before any evaluate), then the physical
     // patches in patch order; linearExtrapolation (linearExtrapolationFvPatchField.C:101-151) uses a
     // full Gauss-linear gradient per component with the boundary values current at that moment.
+    if (isFluidity) return 0;
     for_ranks(cs, [&](int r) {
         Rank& rk = cs.ranks[r];
         Mode& mo = rk.modes[mi];
@@ -1282,7 +1318,29 @@ int orc_add_mode(void* h, const RheoModelDesc* d) {
         mo.thetaB.assign(6 * nb, 0.0); mo.tauB.assign(6 * nb, 0.0);
         rk.modes.push_back(std::move(mo));
     }
+    if (d->model == RHEO_MODEL_BMP_LOG) {   // its fluidity equation: a hidden mode behind the public ones
+        if (cs.ranks[0].modes.size() != 1) { g_err = "oracle: BMPLog is restated as a single-mode model"; return 3; }
+        RheoModelDesc f = *d;
+        f.model = RHEO_MODEL_BMP_FLUIDITY;
+        const int rc = orc_add_mode(h, &f);
+        if (rc) return rc;
+        for (Rank& rk : cs.ranks) { rk.modes[0].fluidityMode = 1; rk.modes[1].fluidityOf = 0; }
+    } else if (d->model != RHEO_MODEL_BMP_FLUIDITY && cs.ranks[0].modes[0].fluidityMode >= 0) { g_err = "oracle: BMPLog is restated as a single-mode model"; return 3; }
     return 0;
+}
+
+int orc_set_state(void* h, int rank, int mode, const double* theta, const double* tau, const double* eigvals,
+                  const double* eigvecs, const double* theta_b, const double* tau_b);
+// BMPLog: the fluidity field of `mode` (Phi, MUST_READ in BMPLog.C:112-122)
+int orc_set_fluidity(void* h, int rank, int mode, const double* Phi, const double* Phi_b) {
+    Case& cs = *(Case*)h;
+    Rank& rk = cs.ranks[rank];
+    if (mode < 0 || mode >= (int)rk.modes.size() || rk.modes[mode].fluidityMode < 0) { g_err = "orc_set_fluidity: not a BMPLog mode"; return 3; }
+    const size_t n = rk.mesh.nCells, nb = rk.mesh.nB();
+    dvec th(6 * n, 0.0), thb(6 * nb, 0.0);
+    for (size_t c = 0; c < n; ++c) th[6 * c] = Phi[c];
+    if (Phi_b) for (size_t b = 0; b < nb; ++b) thb[6 * b] = Phi_b[b];
+    return orc_set_state(h, rank, rk.modes[mode].fluidityMode, th.data(), nullptr, nullptr, nullptr, thb.data(), nullptr);
 }
 
 int orc_set_schemes(void* h, const RheoSchemeCtl* c) { ((Case*)h)->ctl = *c; return 0; }
@@ -1354,6 +1412,13 @@ int orc_step(void* h, double dt, RheoStepStats* stats) {
     cs.dtNow = dt;
     const int nm = (int)cs.ranks[0].modes.size();
     for (int mi = 0; mi < nm; ++mi) {
+        if (cs.ranks[0].modes[mi].fluidityOf >= 0) continue;   // hidden: solved with the BMPLog mode it belongs to
+        const int fm = cs.ranks[0].modes[mi].fluidityMode;
+        if (fm >= 0) {   // BMPLog.C:151-166: the fluidity equation first; theta then sees the new Phi
+            int rc = correct_mode(cs, fm, dt, nullptr);
+            if (rc) return rc;
+            for (Rank& rk : cs.ranks) rk.modes[mi].fluidity = &rk.modes[fm].theta;
+        }
         int rc = correct_mode(cs, mi, dt, stats ? &stats[mi] : nullptr);
         if (rc) return rc;
     }
@@ -1374,6 +1439,12 @@ int orc_get(void* h, int rank, int mode, int field, double* out) {
         case RHEO_FIELD_THETA_B: src = &rk.modes[mode].thetaB; break;
         case RHEO_FIELD_TAU_B: src = &rk.modes[mode].tauB; break;
         case RHEO_FIELD_THETA_OLD: src = &rk.modes[mode].thetaOld; break;
+        case RHEO_FIELD_FLUIDITY: case RHEO_FIELD_FLUIDITY_B: {
+            if (rk.modes[mode].fluidityMode < 0) { g_err = "orc_get: not a BMPLog mode"; return 3; }
+            const dvec& f = field == RHEO_FIELD_FLUIDITY ? rk.modes[rk.modes[mode].fluidityMode].theta : rk.modes[rk.modes[mode].fluidityMode].thetaB;
+            for (size_t i = 0; i < f.size() / 6; ++i) out[i] = f[6 * i];
+            return 0;
+        }
         case RHEO_FIELD_TAU_TOTAL:   // multiMode::tau(), multiMode.C:216-226
             tot.assign(rk.modes[0].tau.size(), 0.0);
             for (Mode& mo : rk.modes) for (size_t q = 0; q < tot.size(); ++q) tot[q] += mo.tau[q];

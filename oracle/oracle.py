@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
             "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
             "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_model_rhs_tau": (None, [P, I, P, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
-            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_div_tau": (I, [P, I, I, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
+            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_div_tau": (I, [P, I, I, P]), "orc_set_fluidity": (I, [P, I, I, P, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -55,7 +55,7 @@ def _p(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(C.c_void_p)
 
 
-FIELD_WIDTH = {0: 6, 1: 6, 2: 9, 3: 9, 4: 6, 5: 6, 6: 6, 7: 6}
+FIELD_WIDTH = {0: 6, 1: 6, 2: 9, 3: 9, 4: 6, 5: 6, 6: 6, 7: 6, 9: 1, 10: 1}
 
 
 class OracleCase:
@@ -72,7 +72,8 @@ class OracleCase:
                 raise RuntimeError(L.orc_last_error().decode())
             self.sizes.append((d.n_cells, d.n_faces - d.n_internal_faces))
         for m in models:
-            L.orc_add_mode(self._h, C.byref(m))
+            if L.orc_add_mode(self._h, C.byref(m)):
+                raise RuntimeError(L.orc_last_error().decode())
         self.n_modes = len(models)
         L.orc_set_schemes(self._h, C.byref(schemes))
         L.orc_set_sort_eig(self._h, 1 if sort_eig else 0)
@@ -86,6 +87,13 @@ class OracleCase:
     def set_state(self, rank, mode, theta=None, tau=None, eigvals=None, eigvecs=None, theta_b=None, tau_b=None):
         keep = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (theta, tau, eigvals, eigvecs, theta_b, tau_b)]
         lib().orc_set_state(self._h, rank, mode, *[_p(a) for a in keep])
+
+    def set_fluidity(self, rank, mode, Phi, Phi_b=None):
+        """BMPLog: the fluidity field (BMPLog.C:112-122)"""
+        a = np.ascontiguousarray(Phi, dtype=np.float64)
+        b = None if Phi_b is None else np.ascontiguousarray(Phi_b, dtype=np.float64)
+        if lib().orc_set_fluidity(self._h, rank, mode, _p(a), _p(b)):
+            raise RuntimeError(lib().orc_last_error().decode())
 
     def set_velocity(self, rank, U, Ub, phi):
         keep = [np.ascontiguousarray(a, dtype=np.float64) for a in (U, Ub, phi)]
@@ -114,11 +122,11 @@ class OracleCase:
 
     def get(self, rank, mode, field):
         n, nb = self.sizes[rank]
-        rows = nb if field in (4, 5) else n
+        rows = nb if field in (4, 5, 10) else n
         out = np.zeros((rows, FIELD_WIDTH[field]))
         if lib().orc_get(self._h, rank, mode, field, _p(out)):
             raise RuntimeError(lib().orc_last_error().decode())
-        return out
+        return out[:, 0] if FIELD_WIDTH[field] == 1 else out
 
     def div_tau(self, rank, stabilization):
         """explicit part of constitutiveEq::divTau (constitutiveEq.C:72-132; multiMode.C:143-157), 3 per cell of `rank`"""

@@ -16,14 +16,14 @@ _HOST_LIB_PATH = Path(__file__).resolve().parent / "librheo_host.so"
 # ---- constants (keep in sync with include/*.h) ---------------------------------------------------
 PATCH_PATCH, PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2, 3
 BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSOR = 0, 1, 2, 3, 4
-MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG, MODEL_SARAMITO_LOG = 0, 1, 2, 3, 4, 5, 6, 7, 8
+MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG, MODEL_SARAMITO_LOG, MODEL_BMP_LOG = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
 LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}
 DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON, DDT_STEADY_STATE = 0, 1, 2, 3
 THERMO = {"Constant": 0, "Arrhenius": 1, "ArrheniusModified": 2, "WLF": 3, "VFT": 4}   # thermoFunctions/* type names
 SOLVER = {"PBiCGStab": 0, "PBiCG": 1}
 STAB_NONE, STAB_BSD, STAB_COUPLING = range(3)   # constitutiveProperties `stabilization`
-FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD, FIELD_TAU_B_TOTAL = range(9)
+FIELD_THETA, FIELD_TAU, FIELD_EIGVALS, FIELD_EIGVECS, FIELD_THETA_B, FIELD_TAU_B, FIELD_TAU_TOTAL, FIELD_THETA_OLD, FIELD_TAU_B_TOTAL, FIELD_FLUIDITY, FIELD_FLUIDITY_B = range(11)
 FLOW_CONTRACTION_2D, FLOW_VORTEX, FLOW_CONTRACTION_3D = 0, 1, 2
 
 MODEL_NAMES = {
@@ -36,6 +36,7 @@ MODEL_NAMES = {
     "Rolie-PolyLog": MODEL_ROLIE_POLY_LOG,
     "XPomPomLog": MODEL_XPOMPOM_LOG,
     "SaramitoLog": MODEL_SARAMITO_LOG,
+    "BMPLog": MODEL_BMP_LOG,
 }
 
 
@@ -74,7 +75,8 @@ class RheoModelDesc(C.Structure):
                 ("rp_lambdaR", C.c_double), ("rp_beta", C.c_double), ("rp_delta", C.c_double), ("rp_chiMax", C.c_double),
                 ("xpp_lambdaS", C.c_double), ("xpp_q", C.c_double), ("xpp_n", C.c_double),
                 ("sar_tau0", C.c_double), ("sar_k", C.c_double), ("sar_n", C.c_double), ("sar_dims", C.c_double * 3),
-                ("sar_ptt", C.c_int32)]
+                ("sar_ptt", C.c_int32),
+                ("bmp_G0", C.c_double), ("bmp_k", C.c_double), ("bmp_Phi0", C.c_double), ("bmp_PhiInf", C.c_double), ("bmp_relax", C.c_double)]
 
 
 class RheoSchemeCtl(C.Structure):
@@ -124,6 +126,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_download": (C.c_int, [_P, _I, _I, _P]),
     "rheo_gpu_correct": (C.c_int, [_P, _P, _P, _P, _D, _I, _P, _P, _P]),
     "rheo_gpu_div_tau": (C.c_int, [_P, _I, _P]),
+    "rheo_gpu_upload_fluidity": (C.c_int, [_P, _I, _P, _P]),
     "rheo_gpu_get_renumbering": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ell": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ordering": (C.c_int, [_P, _P, _I]),

@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_cell_source2(MeshView m, Sourc
         double f;
         ModelParams mp = a.mp;
         if (a.lamCell) { mp.lambda = a.lamCell[c]; mp.etaP = a.etaCell[c]; }   // Oldroyd_BLog.C:133-135: createField(lambda_), createField(etaP_)
-        if constexpr (MODEL == RHEO_MODEL_SARAMITO_LOG) {
+        if constexpr (MODEL == RHEO_MODEL_SARAMITO_LOG || MODEL == RHEO_MODEL_BMP_FLUIDITY) {
             double tc[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) tc[k] = a.tau[(size_t)k * m.NP + c];
@@ -381,6 +381,17 @@ __global__ void k_bc_zero_gradient2(MeshView m, const double* __restrict__ theta
         for (int k = 0; k < 6; ++k) thetaB[(size_t)k * m.nB + b] = theta[(size_t)k * m.NP + c];
     if (b >= t0 && b < t1 && m.btauBC[b] == RHEO_BC_ZERO_GRADIENT)
         for (int k = 0; k < 6; ++k) tauB[(size_t)k * m.nB + b] = tau[(size_t)k * m.NP + c];
+}
+
+// BMPLog.C:177-196 with the fluidity of AFTER PhiEqn.solve(): theta relaxes at Phi G0 and tau = G0 (c - I), i.e. the Oldroyd-BLog
+// source and theta -> tau map with lambda = 1 / (Phi G0), etaP = 1 / Phi per cell (the arrays rheo_gpu_upload_thermo fills otherwise)
+__global__ void k_bmp_rates(int N, const double* __restrict__ Phi, double G0, double* __restrict__ lamCell, double* __restrict__ etaCell) {
+    pdl_sync();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= N) return;
+    const double f = Phi[c];
+    lamCell[c] = 1.0 / (f * G0);
+    etaCell[c] = 1.0 / f;
 }
 
 // Optional (rheo_gpu_set_tau_assignment, off by default): what `tau_ = ...` leaves on the non-fixed tau

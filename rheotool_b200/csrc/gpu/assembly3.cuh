@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(SRC_BLOCK, 3) k_source_init(MeshView m, SrcIni
         double f;
         ModelParams mp = a.s.mp;
         if (a.s.lamCell) { mp.lambda = a.s.lamCell[c]; mp.etaP = a.s.etaCell[c]; }   // Oldroyd_BLog.C:133-135
-        if constexpr (MODEL == RHEO_MODEL_SARAMITO_LOG) {
+        if constexpr (MODEL == RHEO_MODEL_SARAMITO_LOG || MODEL == RHEO_MODEL_BMP_FLUIDITY) {
             double tc[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) tc[k] = a.s.tau[(size_t)k * NP + c];

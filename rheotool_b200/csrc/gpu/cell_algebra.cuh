@@ -19,6 +19,7 @@ struct ModelParams {
         rpLambdaR, rpBeta, rpDelta, rpChiMax, xppLambdaS, xppQ, xppN,
         sarTau0, sarK, sarN, sarD0, sarD1, sarD2;   // SaramitoLog.C:113-130
     int sarPtt;                                     // 0 none, 1 linear, 2 exponential (n == 1 only)
+    double bmpK, bmpPhi0, bmpPhiInf;                // BMPLog.C:129-136 (the fluidity equation; theta runs as Oldroyd-BLog on per-cell rates)
     const double* gamma_vals;   // device table Gamma(alpha k + beta), PTTLog.C:143-170
 };
 
@@ -75,6 +76,16 @@ __device__ __forceinline__ double mittag_leffler(const ModelParams& mp, double z
 template <int MODEL>
 __device__ __forceinline__ double model_rhs(const ModelParams& mp, const double* L, const double* th6, const double* R,
                                             const double* lam, double* rhs6, const double* tau6 = nullptr) {
+    if (MODEL == RHEO_MODEL_BMP_FLUIDITY) {
+        // BMPLog.C:158-160: Phi0/lambda + k (PhiInf - Phi) (tau && symm(L)); th6[0] = Phi, tau6 = the BMPLog mode's stress.
+        // (-Sp(1/lambda, Phi) is on the diagonal: the assembly gets 1/dt + 1/lambda.)
+        const double sxy = 0.5 * (L[1] + L[3]), sxz = 0.5 * (L[2] + L[6]), syz = 0.5 * (L[5] + L[7]);
+        const double tD = tau6[0] * L[0] + tau6[3] * L[4] + tau6[5] * L[8] + 2.0 * (tau6[1] * sxy + tau6[2] * sxz + tau6[4] * syz);
+        rhs6[0] = mp.bmpPhi0 / mp.lambda + mp.bmpK * (mp.bmpPhiInf - th6[0]) * tD;
+#pragma unroll
+        for (int q = 1; q < 6; ++q) rhs6[q] = 0.0;
+        return 0.0;
+    }
     // X = L^T (- zeta symm(L) for PTT and Saramito)          boilerLog.H:26-32
     double X[9] = {L[0], L[3], L[6], L[1], L[4], L[7], L[2], L[5], L[8]};
     if (MODEL == RHEO_MODEL_PTT_LOG || MODEL == RHEO_MODEL_SARAMITO_LOG) {

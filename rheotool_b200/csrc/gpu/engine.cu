@@ -36,7 +36,17 @@ using namespace rk;
 namespace {
 
 thread_local std::string g_err;
-const bool g_pdl = !(getenv("RHEO_PDL") && getenv("RHEO_PDL")[0] == '0');   // programmatic dependent launch (RHEO_PDL=0 disables)
+// Programmatic dependent launch (kernels.cuh: pdl_sync) lets the next kernel's CTAs become resident under the tail of the
+// running one.  Measured (profiles/r2_pdl.md): +4 % on 1 M cells (27 launches of 20-170 us per step), neutral at 8-32 M, and
+// -10 % on 64 M cells per GPU, where the early-resident CTAs of the dependent kernels cost more than the ramp they hide.
+// So it is on for meshes up to RK_PDL_MAX_CELLS cells per rank; RHEO_PDL=0 / 1 forces it off / on.
+constexpr int RK_PDL_MAX_CELLS = 4 * 1000 * 1000;
+inline bool pdl_policy(int nCells) {
+    const char* e = getenv("RHEO_PDL");
+    if (e && e[0] == '0') return false;
+    if (e && e[0] == '1') return true;
+    return nCells <= RK_PDL_MAX_CELLS;
+}
 int fail(const std::string& m) { g_err = m; return 1; }
 
 #define CK(call)                                                                                     \
@@ -136,6 +146,8 @@ struct RheoGpu {
     bool rec3 = false;             // d_tileRec holds version-3 records: k_flux3 + k_source_init run instead of k_flux_assemble + k_cell_source2 + k_krylov_init
     std::vector<int> sweepOrder;   // block ordering: chunks in geometric order (host/ordering.hpp)
     DevBuf d_tileOrder;            // rec3: the assembly's tile walk (sweepOrder padded to nTiles); RHEO_TILE_ORDER=0 walks in index order
+    bool pdl = true;               // programmatic dependent launch on this handle's kernels (pdl_policy)
+    int nHidden = 0;               // BMPLog: its fluidity equation is modes[0] (RHEO_MODEL_BMP_FLUIDITY), the caller's mode 0 is modes[1]
     DevBuf d_gradUb;               // [9][nB] patch values of fvc::grad(U) (rheo_gpu_div_tau, allocated on first use)
     DevBuf d_rowsum, d_inflow;     // rec3: row sums of the matrix and inflow-slot masks (written by k_flux3 with the matrix)
     MeshView mv;
@@ -182,12 +194,12 @@ namespace {
 
 // kernel launch with programmatic dependent launch enabled (kernels.cuh: pdl_sync)
 template <class... KArgs, class... Args>
-inline void launch_pdl(cudaStream_t stream, int grid, int block, size_t smem, void (*kern)(KArgs...), Args&&... args) {
+inline void launch_pdl(bool pdl, cudaStream_t stream, int grid, int block, size_t smem, void (*kern)(KArgs...), Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)block); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
 }
@@ -195,7 +207,7 @@ inline void launch_pdl(cudaStream_t stream, int grid, int block, size_t smem, vo
 #define LAUNCH(h, kern, grid, block, ...)                                      \
     do {                                                                       \
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
-        launch_pdl((h)->stream, (grid), (block), 0, kern, __VA_ARGS__);       \
+        launch_pdl((h)->pdl, (h)->stream, (grid), (block), 0, kern, __VA_ARGS__); \
         (h)->launches++;                                                       \
         if ((h)->launchErr.empty() && cudaPeekAtLastError() != cudaSuccess) (h)->launchErr = #kern; \
         if ((h)->ktiming) {                                                    \
@@ -212,7 +224,7 @@ inline void launch_pdl(cudaStream_t stream, int grid, int block, size_t smem, vo
 #define LAUNCH_SM(h, kern, grid, block, smem, ...)                             \
     do {                                                                       \
         if ((h)->ktiming) cudaEventRecord((h)->kev0, (h)->stream);             \
-        launch_pdl((h)->stream, (grid), (block), (smem), kern, __VA_ARGS__);  \
+        launch_pdl((h)->pdl, (h)->stream, (grid), (block), (smem), kern, __VA_ARGS__); \
         (h)->launches++;                                                       \
         if ((h)->launchErr.empty() && cudaPeekAtLastError() != cudaSuccess) (h)->launchErr = #kern; \
         if ((h)->ktiming) {                                                    \
@@ -278,6 +290,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
     const int N = d->n_cells, nF = d->n_faces, nInt = d->n_internal_faces, nB = nF - nInt;
     h->segs.clear(); h->ubRanges.clear(); h->phiBRanges.clear(); h->blockMode = false;
     h->N = N; h->nF = nF; h->nInt = nInt; h->nB = nB;
+    h->pdl = pdl_policy(N);
     h->patches.assign(d->patches, d->patches + d->n_patches);
     h->nComp = 0;
     for (int q = 0; q < 6; ++q) if (d->solved_components[q]) h->comps[h->nComp++] = q;
@@ -550,7 +563,7 @@ int zero(RheoGpu* h, DevBuf& b) {
     return 0;
 }
 
-int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
+int alloc_fields(RheoGpu* h, const RheoModelDesc* callerModes, int nCallerModes) {
     const size_t NP = h->NP, nB = std::max(h->nB, 1);
     const size_t d8 = sizeof(double);
     if (h->d_U.alloc(3 * NP * d8) || h->d_Ub.alloc(3 * nB * d8) || h->d_phi.alloc((size_t)std::max(h->nF, 1) * d8) ||
@@ -562,15 +575,35 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
     zero(h, h->d_Fell); zero(h, h->d_gradU);
     h->stageBytes = std::max<size_t>(9 * (size_t)h->N, std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;
     if (h->d_stage.alloc(h->stageBytes)) return 1;
+    // BMPLog (BMPLog.C:142-201): the fluidity equation is solved before theta in every correct().  It runs through the same
+    // assembly and solver as component xx of a padded symmTensor (the other components have a zero source and a zero initial
+    // residual: no iterations), as a hidden mode IN FRONT of the caller's — do_step then meets it first.
+    std::vector<RheoModelDesc> list(callerModes, callerModes + nCallerModes);
+    h->nHidden = 0;
+    for (int mi = 0; mi < nCallerModes; ++mi) {
+        if (callerModes[mi].model == RHEO_MODEL_BMP_FLUIDITY) return fail("rheo_gpu_create: unknown constitutiveEq model");
+        if (callerModes[mi].model != RHEO_MODEL_BMP_LOG) continue;
+        if (nCallerModes != 1) return fail("rheo_gpu_create: BMPLog runs as a single-mode model (not inside multiMode)");
+        const RheoModelDesc& q = callerModes[mi];
+        if (!(q.bmp_G0 > 0 && q.bmp_Phi0 > 0 && q.bmp_PhiInf > 0)) return fail("rheo_gpu_create: BMPLog needs G0 > 0, Phi0 > 0 and PhiInf > 0");
+        RheoModelDesc f = q;
+        f.model = RHEO_MODEL_BMP_FLUIDITY;
+        list.insert(list.begin(), f);
+        h->nHidden = 1;
+    }
+    const RheoModelDesc* modes = list.data();
+    const int nModes = (int)list.size();
     h->modes.resize(nModes);
     for (int mi = 0; mi < nModes; ++mi) {
         ModeDev& md = h->modes[mi];
         md.desc = modes[mi];
         const RheoModelDesc& q = modes[mi];
-        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_SARAMITO_LOG) return fail("rheo_gpu_create: unknown constitutiveEq model");
+        if (q.model < RHEO_MODEL_OLDROYD_B_LOG || q.model > RHEO_MODEL_BMP_FLUIDITY) return fail("rheo_gpu_create: unknown constitutiveEq model");
         if (!(q.lambda > 0)) return fail("rheo_gpu_create: lambda must be positive");
         ModelParams& mp = md.mp;
-        mp.model = q.model; mp.ptt_function = q.ptt_function; mp.ml_max_iter = q.ml_max_iter;
+        mp.model = q.model == RHEO_MODEL_BMP_LOG ? RHEO_MODEL_OLDROYD_B_LOG : q.model;   // theta of BMPLog: Oldroyd-BLog on per-cell rates (k_bmp_rates)
+        mp.bmpK = q.bmp_k; mp.bmpPhi0 = q.bmp_Phi0; mp.bmpPhiInf = q.bmp_PhiInf;
+        mp.ptt_function = q.ptt_function; mp.ml_max_iter = q.ml_max_iter;
         mp.etaP = q.etaP; mp.lambda = q.lambda; mp.alpha = q.alpha; mp.epsilon = q.epsilon; mp.zeta = q.zeta; mp.L2 = q.L2;
         mp.ml_rtol = q.ml_rtol; mp.gamma_beta = 1.0; mp.gamma_vals = nullptr;
         mp.wmK = q.wm_K; mp.wmN = q.wm_n; mp.wmA = q.wm_a;
@@ -601,6 +634,11 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* modes, int nModes) {
             md.corr.alloc((size_t)h->nComp * h->K * h->NS * d8) || md.thetaOldOld.alloc(h->ctl.ddt != RHEO_DDT_EULER ? 6 * NP * d8 : 0) ||
             md.ddt0.alloc(h->ctl.ddt == RHEO_DDT_CRANK_NICOLSON ? 6 * NP * d8 : 0))
             return 1;
+        if (q.model == RHEO_MODEL_BMP_LOG) {
+            if (md.lamCell.alloc(NP * d8) || md.etaCell.alloc(NP * d8)) return 1;
+            LAUNCH(h, k_fill, cdiv(NP, BLOCK), BLOCK, NP, md.lamCell.as<double>(), 1.0);
+            LAUNCH(h, k_fill, cdiv(NP, BLOCK), BLOCK, NP, md.etaCell.as<double>(), 1.0);
+        }
         zero(h, md.corr); zero(h, md.thetaOldOld); zero(h, md.ddt0);
         zero(h, md.theta); zero(h, md.thetaOld); zero(h, md.tau); zero(h, md.fFene); zero(h, md.bsrc); zero(h, md.thetaB); zero(h, md.tauB); zero(h, md.R);
         // READ_IF_PRESENT defaults: eigVals = eigVecs = I (Oldroyd_BLog.C:76-113)
@@ -839,7 +877,7 @@ template <class Kern> int flux_grid(RheoGpu* h, Kern kern, int threads, size_t s
 
 #include "solve.inl"
 
-int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
+int do_step(RheoGpu* h, double dt, RheoStepStats* statsOut) {
     if (!(dt > 0)) return fail("rheo_gpu_step: dt must be positive");
     if (h->ctl.ddt != RHEO_DDT_EULER && h->ctl.ddt != RHEO_DDT_BACKWARD && h->ctl.ddt != RHEO_DDT_CRANK_NICOLSON && h->ctl.ddt != RHEO_DDT_STEADY_STATE)
         return fail("rheo_gpu_step: the Euler, backward, CrankNicolson and steadyState ddt schemes are implemented");
@@ -914,11 +952,12 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     float msGrad = 0, msAsm = 0, msSolve = 0;
     h->lastIters = 0;
     const bool hrs = h->lim.hrs && !noConv;
-    const int perBatch = std::max(1, MAX_RHS / h->nComp);
+    const int perBatch = h->nHidden ? 1 : std::max(1, MAX_RHS / h->nComp);   // BMPLog: the fluidity matrix has its own diagonal
     for (int m0 = 0; m0 < nModes; m0 += perBatch) {
         const int m1 = std::min(nModes, m0 + perBatch);
         const int nrhs = (m1 - m0) * h->nComp;
         cudaEvent_t e0 = h->ev[6], e1 = h->ev[7];
+        const bool oneBatch = nModes <= perBatch;   // phase events are then only recorded, never waited for, inside the step
         if (h->timing) cudaEventRecord(e0, h->stream);
         // k_flux3 / k_flux_assemble: the upwind cell computes each deferred face value once (grad(U) and the matrix with the
         // first mode).  Processor faces: the face values of the batch travel in one message per neighbour, then k_ghost_corr
@@ -926,8 +965,12 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         for (int mi = m0; mi < m1; ++mi) {
             ModeDev& md = h->modes[mi];
             FluxArgs fa{};
-            fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv; fa.rDeltaT = ddtDiag; fa.relax = h->ctl.relax;
-            fa.writeMatrix = mi == 0 ? 1 : 0;
+            const bool fluidity = md.mp.model == RHEO_MODEL_BMP_FLUIDITY;
+            fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv;
+            // BMPLog.C:158: `== - fvm::Sp(1/lambda, Phi)` puts V/lambda on the diagonal next to the ddt coefficient; PhiEqn.relax() has its own factor
+            fa.rDeltaT = fluidity ? ddtDiag + 1.0 / md.mp.lambda : ddtDiag;
+            fa.relax = fluidity ? md.desc.bmp_relax : h->ctl.relax;
+            fa.writeMatrix = (mi == 0 || h->nHidden) ? 1 : 0;
             fa.bounded = h->ctl.bounded ? 1 : 0;
             fa.Fell = h->d_Fell.as<double>(); fa.theta = md.theta.as<double>(); fa.thetaB = md.thetaB.as<double>();
             fa.U = h->d_U.as<double>(); fa.Ub = h->d_Ub.as<double>(); fa.bsrc = md.bsrc.as<double>();
@@ -954,6 +997,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 default: LAUNCH_SM(h, (k_flux_assemble<0>), flux_grid(h, k_flux_assemble<0>, threads, fluxSmem), threads, fluxSmem, h->mv, fa, rec, h->nTiles); break;
             }
         }
+        if (h->timing && oneBatch) cudaEventRecord(h->ev[2], h->stream);   // end of the flux / matrix kernels
         if (h->H && hrs) {
             const double* recv;
             if (halo_sendrecv(h, nrhs, &recv)) return 1;
@@ -975,7 +1019,8 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             for (int j = 0; j < h->nComp; ++j) sa.solvedIdx[h->comps[j]] = j;
             sa.gradU = h->d_gradU.as<double>(); sa.theta = md.theta.as<double>(); sa.thetaOld = md.thetaOld.as<double>();
             sa.lam = md.lam.as<double>(); sa.R = md.R.as<double>();
-            sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>(); sa.tau = md.tau.as<double>();
+            sa.bsrc = md.bsrc.as<double>(); sa.fFene = md.fFene.as<double>();
+            sa.tau = md.mp.model == RHEO_MODEL_BMP_FLUIDITY ? h->modes[mi + 1].tau.as<double>() : md.tau.as<double>();   // BMPLog.C:160: tau_ && symm(L)
             sa.lamCell = md.lamCell.as<double>(); sa.etaCell = md.etaCell.as<double>();
             sa.sumPartials = h->d_partials.as<double>(); sa.sumOut = h->d_sumPsi.as<double>() + (size_t)mi * h->nComp; sa.counter = h->d_counter.as<unsigned>();
             if (h->rec3) {
@@ -1004,6 +1049,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                     case RHEO_MODEL_WM_CY_LOG: RK_SRC3(RHEO_MODEL_WM_CY_LOG); break;
                     case RHEO_MODEL_ROLIE_POLY_LOG: RK_SRC3(RHEO_MODEL_ROLIE_POLY_LOG); break;
                     case RHEO_MODEL_SARAMITO_LOG: RK_SRC3(RHEO_MODEL_SARAMITO_LOG); break;
+                    case RHEO_MODEL_BMP_FLUIDITY: RK_SRC3(RHEO_MODEL_BMP_FLUIDITY); break;
                     default: RK_SRC3(RHEO_MODEL_XPOMPOM_LOG); break;
                 }
 #undef RK_SRC3
@@ -1018,11 +1064,12 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
                 case RHEO_MODEL_WM_CY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_WM_CY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                 case RHEO_MODEL_ROLIE_POLY_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_ROLIE_POLY_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                 case RHEO_MODEL_SARAMITO_LOG: LAUNCH(h, (k_cell_source2<RHEO_MODEL_SARAMITO_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
+                case RHEO_MODEL_BMP_FLUIDITY: LAUNCH(h, (k_cell_source2<RHEO_MODEL_BMP_FLUIDITY>), srcGrid, SRC_BLOCK, h->mv, sa); break;
                 default: LAUNCH(h, (k_cell_source2<RHEO_MODEL_XPOMPOM_LOG>), srcGrid, SRC_BLOCK, h->mv, sa); break;
             }
         }
         if (h->rec3 && h->nRanks > 1 && all_reduce_ctl(h, h->d_red.as<double>() + MAX_RED, 3 * nrhs, CTL_INIT, nrhs, sc)) return 1;
-        if (h->timing) { cudaEventRecord(e1, h->stream); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; }
+        if (h->timing) { cudaEventRecord(e1, h->stream); if (!oneBatch) { cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); msAsm += ms; } }
 
         // ---- segregated solve: all valid components of the batch's modes on the shared matrix
         RhsPtrs rp;
@@ -1046,6 +1093,15 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         h->specIters = std::max(1, iters);
         int q = 0;
         for (int mi = m0; mi < m1; ++mi) {
+            if (h->modes[mi].mp.model == RHEO_MODEL_BMP_FLUIDITY) {
+                // theta of the BMPLog mode sees the fluidity of AFTER PhiEqn.solve() (BMPLog.C:177-196)
+                ModeDev& T = h->modes[mi + 1];
+                LAUNCH(h, k_bmp_rates, grid, BLOCK, N, h->modes[mi].theta.as<double>(), T.desc.bmp_G0, T.lamCell.as<double>(), T.etaCell.as<double>());
+                h->lastIters = std::max(h->lastIters, h->h_ks->ctl[0].iters);
+                q += h->nComp;
+                continue;
+            }
+            RheoStepStats* stats = statsOut ? statsOut - h->nHidden : nullptr;   // the caller's array starts at its own mode 0
             if (stats) std::memset(&stats[mi], 0, sizeof(RheoStepStats));
             for (int j = 0; j < h->nComp; ++j, ++q) {
                 const KrylovCtl& k = h->h_ks->ctl[q];
@@ -1060,13 +1116,14 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
             }
             if (stats) for (int cmp = 0; cmp < 6; ++cmp) if (std::find(h->comps, h->comps + h->nComp, cmp) == h->comps + h->nComp) stats[mi].converged[cmp] = 1;
         }
-        if (h->timing) { cudaEventRecord(e0, h->stream); cudaEventSynchronize(e0); float ms; cudaEventElapsedTime(&ms, e1, e0); msSolve += ms; }
+        if (h->timing && !oneBatch) { cudaEventRecord(e0, h->stream); cudaEventSynchronize(e0); float ms; cudaEventElapsedTime(&ms, e1, e0); msSolve += ms; }
     }
     if (h->timing) cudaEventRecord(h->ev[3], h->stream);
 
     // ---- eig + exp + tau
     for (ModeDev& md : h->modes)
     {
+        if (md.mp.model == RHEO_MODEL_BMP_FLUIDITY) continue;   // the fluidity has no eigen-decomposition and no stress of its own
 #define RK_EIG(M) LAUNCH(h, (k_eig_tau<M>), grid, BLOCK, N, NP, md.mp, md.theta.as<double>(), md.fFene.as<double>(), md.lam.as<double>(), md.R.as<double>(), md.tau.as<double>(), \
                          md.lamCell.as<double>(), md.etaCell.as<double>())
         switch (md.mp.model) {
@@ -1085,12 +1142,16 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
     if (h->timing) cudaEventRecord(h->ev[4], h->stream);
     // ---- theta BCs; tau.correctBoundaryConditions(): processor values first, then physical patches in order
     for (ModeDev& md : h->modes) {
+        if (md.mp.model == RHEO_MODEL_BMP_FLUIDITY) {   // Phi.correctBoundaryConditions(): zeroGradient faces follow their cells
+            if (h->nB) LAUNCH(h, k_bc_zero_gradient2, cdiv(h->nB, BLOCK), BLOCK, h->mv, (const double*)md.theta.as<double>(), md.thetaB.as<double>(), (const double*)nullptr, (double*)nullptr, 0, 0);
+            continue;
+        }
         if (h->H && halo_planes(h, md.tau.as<double>(), 6)) return 1;
         // patches in patch (= face) order, as EXT-OF9 GeometricBoundaryField::evaluate visits them: a linearExtrapolation
         // patch sees the values of the patches before it already updated and of those after it still old.  Consecutive
         // non-linearExtrapolation patches are one launch; the first launch also refreshes theta's zeroGradient faces.
         if (h->nB && h->tauAssign) {
-            const double e = md.mp.model == RHEO_MODEL_OLDROYD_B_LOG ? -md.mp.etaP / md.mp.lambda : 0.0;   // Oldroyd_BLog.C:176 goes through innerP
+            const double e = md.desc.model == RHEO_MODEL_OLDROYD_B_LOG ? -md.mp.etaP / md.mp.lambda : 0.0;   // Oldroyd_BLog.C:176 goes through innerP
             LAUNCH(h, k_tau_b_assign, cdiv(h->nB, BLOCK), BLOCK, h->mv, e, md.tauB.as<double>());
         }
         if (h->nB) {
@@ -1124,6 +1185,11 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* stats) {
         cudaEventSynchronize(h->ev[5]);
         float ms;
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); h->phaseMs[0] = ms;
+        if (nModes <= perBatch) {   // one batch: free-running phases (events recorded in stream order, read here)
+            cudaEventElapsedTime(&msGrad, h->ev[6], h->ev[2]);
+            cudaEventElapsedTime(&msAsm, h->ev[6], h->ev[7]);
+            cudaEventElapsedTime(&msSolve, h->ev[7], h->ev[3]);
+        }
         h->phaseMs[1] = msGrad; h->phaseMs[2] = msAsm;
         h->phaseMs[3] = msSolve;
         cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); h->phaseMs[4] = ms;
@@ -1243,9 +1309,9 @@ int rheo_gpu_comm_init(RheoGpu* h, int32_t rank, int32_t n_ranks, const void* id
 
 int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const double* tau, const double* eigvals, const double* eigvecs,
                           const double* theta_b, const double* tau_b) {
-    if (!h || mode < 0 || mode >= (int)h->modes.size()) return fail("rheo_gpu_upload_state: bad handle/mode");
+    if (!h || mode < 0 || mode + h->nHidden >= (int)h->modes.size()) return fail("rheo_gpu_upload_state: bad handle/mode");
     CK(cudaSetDevice(h->device));
-    ModeDev& md = h->modes[mode];
+    ModeDev& md = h->modes[mode + h->nHidden];
     if (theta) {
         if (put_cells(h, theta, 6, md.theta.as<double>())) return 1;
         CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
@@ -1268,6 +1334,26 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
     return 0;
 }
 
+// BMPLog: the fluidity field (component xx of the hidden mode; the other components stay 0)
+int rheo_gpu_upload_fluidity(RheoGpu* h, int32_t mode, const double* Phi, const double* Phi_b) {
+    if (!h || !Phi) return fail("rheo_gpu_upload_fluidity: null argument");
+    if (!h->nHidden || mode != 0) return fail("rheo_gpu_upload_fluidity: not a BMPLog mode");
+    CK(cudaSetDevice(h->device));
+    ModeDev& md = h->modes[0];
+    if (zero(h, md.theta) || zero(h, md.thetaB)) return 1;
+    if (put_cells(h, Phi, 1, md.theta.as<double>())) return 1;
+    CK(cudaMemcpyAsync(md.thetaOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (md.thetaOldOld.p) CK(cudaMemcpyAsync(md.thetaOldOld.p, md.theta.p, md.theta.bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (md.ddt0.p) { if (zero(h, md.ddt0)) return 1; }
+    md.ddt0TimeIndex = 0;
+    h->nOldTimes = 0;
+    CK(cudaStreamSynchronize(h->stream));   // the staging buffer is reused by the next copy
+    if (Phi_b && put_bfaces(h, Phi_b, 1, md.thetaB.as<double>())) return 1;
+    if (h->nB) LAUNCH(h, k_bc_zero_gradient, cdiv(h->nB, BLOCK), BLOCK, h->mv, h->d_bthetaBC.as<int>(), md.theta.as<double>(), md.thetaB.as<double>(), 6);
+    CK(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi) {
     if (!h || !U || !phi) return fail("rheo_gpu_upload_velocity: null argument");
     CK(cudaSetDevice(h->device));
@@ -1285,7 +1371,8 @@ int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, con
 }
 
 int rheo_gpu_upload_thermo(RheoGpu* h, int32_t mode, const double* lambda_cell, const double* etaP_cell) {
-    if (!h || mode < 0 || mode >= (int)h->modes.size()) return fail("rheo_gpu_upload_thermo: bad handle/mode");
+    if (!h || mode < 0 || mode + h->nHidden >= (int)h->modes.size()) return fail("rheo_gpu_upload_thermo: bad handle/mode");
+    if (h->nHidden) return fail("rheo_gpu_upload_thermo: BMPLog has no thermo-dependent parameters (the per-cell rates come from its fluidity)");
     if ((lambda_cell == nullptr) != (etaP_cell == nullptr)) return fail("rheo_gpu_upload_thermo: pass both lambda and etaP per cell, or neither");
     CK(cudaSetDevice(h->device));
     ModeDev& md = h->modes[mode];
@@ -1327,9 +1414,9 @@ int rheo_gpu_step(RheoGpu* h, double dt, RheoStepStats* stats) {
 }
 
 int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
-    if (!h || !dst || mode < 0 || mode >= (int)h->modes.size()) return fail("rheo_gpu_download: bad argument");
+    if (!h || !dst || mode < 0 || mode + h->nHidden >= (int)h->modes.size()) return fail("rheo_gpu_download: bad argument");
     CK(cudaSetDevice(h->device));
-    ModeDev& md = h->modes[mode];
+    ModeDev& md = h->modes[mode + h->nHidden];
     const int N = h->N, NP = h->NP, nB = h->nB;
     double* stage = h->d_stage.as<double>();
     size_t bytes = 0;
@@ -1338,8 +1425,8 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
         case RHEO_FIELD_THETA_OLD: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), md.thetaOld.as<double>(), stage, NP); bytes = (size_t)N * 6; break;
         case RHEO_FIELD_TAU: LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), md.tau.as<double>(), stage, NP); bytes = (size_t)N * 6; break;
         case RHEO_FIELD_TAU_TOTAL:
-            for (size_t mi = 0; mi < h->modes.size(); ++mi) {
-                if (mi == 0) LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), h->modes[mi].tau.as<double>(), stage, NP);
+            for (size_t mi = h->nHidden; mi < h->modes.size(); ++mi) {
+                if ((int)mi == h->nHidden) LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), h->modes[mi].tau.as<double>(), stage, NP);
                 else LAUNCH(h, k_soa_to_aos_acc, cdiv(N, BLOCK), BLOCK, N, 6, h->d_perm.as<int>(), h->modes[mi].tau.as<double>(), stage, NP);
             }
             bytes = (size_t)N * 6;
@@ -1349,12 +1436,18 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
         case RHEO_FIELD_THETA_B: if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, md.thetaB.as<double>(), stage, nB); bytes = (size_t)nB * 6; break;
         case RHEO_FIELD_TAU_B: if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, md.tauB.as<double>(), stage, nB); bytes = (size_t)nB * 6; break;
         case RHEO_FIELD_TAU_B_TOTAL:   // multiMode::divTau sums each mode's divTau, i.e. sees the sum of the modes' patch values
-            for (size_t mi = 0; nB && mi < h->modes.size(); ++mi) {
-                if (mi == 0) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, h->modes[mi].tauB.as<double>(), stage, nB);
+            for (size_t mi = h->nHidden; nB && mi < h->modes.size(); ++mi) {
+                if ((int)mi == h->nHidden) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, h->modes[mi].tauB.as<double>(), stage, nB);
                 else LAUNCH(h, k_soa_to_aos_acc, cdiv(nB, BLOCK), BLOCK, nB, 6, (const int*)nullptr, h->modes[mi].tauB.as<double>(), stage, nB);
             }
             bytes = (size_t)nB * 6;
             break;
+        case RHEO_FIELD_FLUIDITY:
+            if (!h->nHidden) return fail("rheo_gpu_download: not a BMPLog model");
+            LAUNCH(h, k_soa_to_aos, cdiv(N, BLOCK), BLOCK, N, 1, h->d_perm.as<int>(), h->modes[0].theta.as<double>(), stage, NP); bytes = (size_t)N; break;
+        case RHEO_FIELD_FLUIDITY_B:
+            if (!h->nHidden) return fail("rheo_gpu_download: not a BMPLog model");
+            if (nB) LAUNCH(h, k_soa_to_aos, cdiv(nB, BLOCK), BLOCK, nB, 1, (const int*)nullptr, h->modes[0].thetaB.as<double>(), stage, nB); bytes = (size_t)nB; break;
         default: return fail("rheo_gpu_download: unknown field");
     }
     if (bytes) CK(cudaMemcpyAsync(dst, stage, bytes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -1367,14 +1460,14 @@ int rheo_gpu_download(RheoGpu* h, int32_t mode, int32_t field, double* dst) {
 int rheo_gpu_div_tau(RheoGpu* h, int32_t stabilization, double* div_out) {
     if (!h || !div_out) return fail("rheo_gpu_div_tau: null argument");
     if (stabilization != RHEO_STAB_NONE && stabilization != RHEO_STAB_BSD && stabilization != RHEO_STAB_COUPLING) return fail("rheo_gpu_div_tau: unknown stabilization");
-    if ((int)h->modes.size() > MAX_MODES_DIV) return fail("rheo_gpu_div_tau: more than 8 modes");
+    if ((int)h->modes.size() - h->nHidden > MAX_MODES_DIV) return fail("rheo_gpu_div_tau: more than 8 modes");
     CK(cudaSetDevice(h->device));
     const bool coupling = stabilization == RHEO_STAB_COUPLING;
     DivTauArgs a{};
-    a.nModes = (int)h->modes.size();
+    a.nModes = (int)h->modes.size() - h->nHidden;
     for (int mi = 0; mi < a.nModes; ++mi) {
-        ModeDev& md = h->modes[mi];
-        if (coupling && md.etaCell.p) return fail("rheo_gpu_div_tau: stabilization coupling with a temperature-dependent etaP is not implemented (download tau instead)");
+        ModeDev& md = h->modes[mi + h->nHidden];
+        if (coupling && md.etaCell.p && !h->nHidden) return fail("rheo_gpu_div_tau: stabilization coupling with a temperature-dependent etaP is not implemented (download tau instead)");
         a.tau[mi] = md.tau.as<double>(); a.tauB[mi] = md.tauB.as<double>();
         a.rRho[mi] = 1.0 / md.desc.rho;
         if (coupling) a.coefGrad += md.desc.etaP / md.desc.rho;

@@ -3,7 +3,7 @@
 
   Registered type names (constant/constitutiveProperties -> parameters -> type):
       Oldroyd-BLogGPU  GiesekusLogGPU  PTTLogGPU  FENE-PLogGPU  FENE-CRLogGPU
-      WhiteMetznerCYLogGPU  Rolie-PolyLogGPU  XPomPomLogGPU  SaramitoLogGPU  multiModeLogGPU
+      WhiteMetznerCYLogGPU  Rolie-PolyLogGPU  XPomPomLogGPU  SaramitoLogGPU  BMPLogGPU  multiModeLogGPU
   Dictionary keys are those of the CPU models (Oldroyd_BLog.C:114-119,
   GiesekusLog.C:117, PTTLog.C:129-139, FENE_PLog.C:114-119, multiMode.C:73-92);
   fvSchemes div(phi,theta<name>) must be `GaussDefCmpw <limiter>`, ddtSchemes Euler or backward,
@@ -47,6 +47,7 @@ namespace constitutiveEqs
     RHEO_GPU_REGISTER(RoliePolyLogGPU, "Rolie-PolyLogGPU")
     RHEO_GPU_REGISTER(XPomPomLogGPU, "XPomPomLogGPU")
     RHEO_GPU_REGISTER(SaramitoLogGPU, "SaramitoLogGPU")
+    RHEO_GPU_REGISTER(BMPLogGPU, "BMPLogGPU")
     RHEO_GPU_REGISTER(multiModeLogGPU, "multiModeLogGPU")
 }
 }
@@ -133,6 +134,17 @@ void LogConformationGPU::readMode(const word& type, const dictionary& dict, Rheo
         m.xpp_q       = dimensionedScalar(dict.lookup("q")).value();
         m.xpp_n       = dimensionedScalar(dict.lookup("n")).value();
     }
+    else if (type == "BMPLogGPU" || type == "BMPLog")                    // BMPLog.C:129-136
+    {
+        m.model      = RHEO_MODEL_BMP_LOG;
+        m.bmp_G0     = dimensionedScalar(dict.lookup("G0")).value();
+        m.bmp_k      = dimensionedScalar(dict.lookup("k")).value();
+        m.bmp_Phi0   = dimensionedScalar(dict.lookup("Phi0")).value();
+        m.bmp_PhiInf = dimensionedScalar(dict.lookup("PhiInf")).value();
+        // PhiEqn.relax() (BMPLog.C:165): relaxationFactors.equations.Phi<name>; its solver entry must equal theta's (the tutorial's
+        // fvSolution groups "(theta|tau|C|A|Phi)"), and so must its convection scheme (div(phi,Phi): readSchemes checks both)
+        m.bmp_relax  = 0;
+    }
     else if (type == "SaramitoLogGPU" || type == "SaramitoLog")          // SaramitoLog.C:108-165
     {
         m.model    = RHEO_MODEL_SARAMITO_LOG;
@@ -206,6 +218,23 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
             {
                 FatalErrorInFunction << "gradSchemes entry for " << gname << " is `" << g0 << ' ' << g1
                     << "`; the GPU stress step implements `Gauss linear` gradients only" << exit(FatalError);
+            }
+        }
+    }
+    // deviceDivTau: div(tau) and div(grad(U)) (constitutiveEq.C:100-126) are evaluated on the device as `Gauss linear`
+    if (deviceDivTau_)
+    {
+        const char* divs[] = {"div(tau)", "div(grad(U))"};
+        for (const char* dname : divs)
+        {
+            if (word(dname) == "div(grad(U))" && stabOption_ != soCoupling) continue;
+            ITstream& ds = mesh.divScheme(dname);
+            const word d0(ds);
+            const word d1(ds.eof() ? word("") : word(ds));
+            if (d0 != "Gauss" || d1 != "linear")
+            {
+                FatalErrorInFunction << "divSchemes entry for " << dname << " is `" << d0 << ' ' << d1
+                    << "`; the device divTau implements `Gauss linear` only (set deviceDivTau false)" << exit(FatalError);
             }
         }
     }
@@ -332,7 +361,8 @@ LogConformationGPU::LogConformationGPU
     ),
     rho_("rho", dimDensity, 0), etaS_("etaS", dimPressure*dimTime, 0), etaP_("etaP", dimPressure*dimTime, 0),
     gpu_(nullptr),
-    lastTimeIndex_(-1)
+    lastTimeIndex_(-1),
+    deviceDivTau_(dict.lookupOrDefault<Switch>("deviceDivTau", true))
 {
     const fvMesh& mesh = U.mesh();
     const word type(dict.lookup("type"));
@@ -373,6 +403,35 @@ LogConformationGPU::LogConformationGPU
             {
                 FatalErrorInFunction << "schemes / solver controls of theta" << suffix[i] << " differ from those of theta" << suffix[0]
                     << "; the batched multiMode solve of the GPU path needs identical controls" << exit(FatalError);
+            }
+        }
+    }
+
+    if (modes_[0].model == RHEO_MODEL_BMP_LOG)                              // BMPLog.C:112-136
+    {
+        if (modes_.size() != 1) FatalErrorInFunction << "BMPLog runs as a single-mode model on the GPU path" << exit(FatalError);
+        Phi_.reset(new volScalarField(IOobject("Phi" + name, U.time().timeName(), mesh, IOobject::MUST_READ, IOobject::AUTO_WRITE), mesh));
+        // the fluidity equation shares theta's assembly and solver: same convection scheme, same solver entry, same patch kinds
+        {
+            const RheoSchemeCtl first = ctl_;
+            readSchemes(mesh, "Phi" + name);   // reads div(phi,Phi<name>), solvers.Phi<name>, relaxationFactors.equations.Phi<name>
+            modes_[0].bmp_relax = ctl_.relax;
+            ctl_.relax = first.relax;
+            if (std::memcmp(&first, &ctl_, sizeof(RheoSchemeCtl)) != 0)
+            {
+                FatalErrorInFunction << "schemes / solver controls of Phi" << name << " differ from those of theta" << name
+                    << "; the GPU path solves both with one set of controls" << exit(FatalError);
+            }
+        }
+        forAll(Phi_().boundaryField(), pI)
+        {
+            const fvPatchScalarField& pf = Phi_().boundaryField()[pI];
+            if (pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
+            const bool fixedPhi = isA<fixedValueFvPatchScalarField>(pf), fixedTheta = isA<fixedValueFvPatchSymmTensorField>(theta_[0].boundaryField()[pI]);
+            if (fixedPhi != fixedTheta || (!fixedPhi && !isA<zeroGradientFvPatchScalarField>(pf)))
+            {
+                FatalErrorInFunction << "patch " << pf.patch().name() << ": Phi" << name << " must be fixedValue where theta" << name
+                    << " is fixedValue and zeroGradient elsewhere (the fluidity is carried through theta's assembly)" << exit(FatalError);
             }
         }
     }
@@ -429,6 +488,17 @@ void LogConformationGPU::uploadState()
               reinterpret_cast<const double*>(thB.begin()), reinterpret_cast<const double*>(tauB.begin())),
               "rheo_gpu_upload_state");
     }
+    if (Phi_.valid())   // BMPLog's fluidity (BMPLog.C:112-122)
+    {
+        scalarField PhiB(U().mesh().nFaces() - nI, 0.0);
+        forAll(Phi_().boundaryField(), pI)
+        {
+            const fvPatchScalarField& pf = Phi_().boundaryField()[pI];
+            if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
+            forAll(pf, i) PhiB[pf.patch().start() - nI + i] = pf[i];
+        }
+        check(rheo_gpu_upload_fluidity(gpu_, 0, Phi_().primitiveField().begin(), PhiB.begin()), "rheo_gpu_upload_fluidity");
+    }
 }
 
 void LogConformationGPU::downloadAll()
@@ -441,6 +511,11 @@ void LogConformationGPU::downloadAll()
         theta_[i].correctBoundaryConditions();
         eigVals_[i].correctBoundaryConditions();
         eigVecs_[i].correctBoundaryConditions();
+    }
+    if (Phi_.valid())
+    {
+        check(rheo_gpu_download(gpu_, 0, RHEO_FIELD_FLUIDITY, Phi_().primitiveFieldRef().begin()), "download Phi");
+        Phi_().correctBoundaryConditions();
     }
 }
 
@@ -485,11 +560,15 @@ void LogConformationGPU::correct(const volScalarField* alpha, const volTensorFie
 
     symmTensorField tauB(mesh.nFaces() - nI);
     List<RheoStepStats> stats(modes_.size());
+    // deviceDivTau: the momentum predictor takes div(tau) from the device (divTau below), so tau only comes back at write time
+    const bool wantTau = !deviceDivTau_ || U().time().writeTime();
     check(rheo_gpu_correct(gpu_,
           reinterpret_cast<const double*>(U().primitiveField().begin()), reinterpret_cast<const double*>(Ub.begin()), ph.begin(),
           U().time().deltaTValue(), newStep ? 1 : 0,
-          reinterpret_cast<double*>(tauTotal_.primitiveFieldRef().begin()), reinterpret_cast<double*>(tauB.begin()), stats.begin()),
+          wantTau ? reinterpret_cast<double*>(tauTotal_.primitiveFieldRef().begin()) : nullptr,
+          wantTau ? reinterpret_cast<double*>(tauB.begin()) : nullptr, stats.begin()),
           "rheo_gpu_correct");
+    tauOnHost_ = wantTau;
 
     // OpenFOAM-style solver report (SolverPerformance<symmTensor>)
     static const char* cmpt[6] = {"XX", "XY", "XZ", "YY", "YZ", "ZZ"};
@@ -500,13 +579,13 @@ void LogConformationGPU::correct(const volScalarField* alpha, const volTensorFie
     // boundary values of tau for the momentum predictor: the device returns the patch values SUMMED OVER THE MODES
     // (RHEO_FIELD_TAU_B_TOTAL) — multiMode::divTau (multiMode.C) sums each mode's divTau, i.e. uses each mode's own
     // linearExtrapolation / zeroGradient / fixedValue patch values
-    forAll(tauTotal_.boundaryField(), pI)
+    if (wantTau) forAll(tauTotal_.boundaryField(), pI)
     {
         fvPatchSymmTensorField& pf = tauTotal_.boundaryFieldRef()[pI];
         if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
         forAll(pf, i) pf[i] = tauB[pf.patch().start() - nI + i];
     }
-    if (modes_.size() == 1)
+    if (wantTau && modes_.size() == 1)
     {
         tau_[0].primitiveFieldRef() = tauTotal_.primitiveField();
         tau_[0].boundaryFieldRef() = tauTotal_.boundaryField();
@@ -517,5 +596,54 @@ void LogConformationGPU::correct(const volScalarField* alpha, const volTensorFie
         downloadAll();
         if (modes_.size() > 1) forAll(tau_, i)
             check(rheo_gpu_download(gpu_, i, RHEO_FIELD_TAU, reinterpret_cast<double*>(tau_[i].primitiveFieldRef().begin())), "download tau");
+    }
+}
+
+
+// tau() (constitutiveEq.H:314; multiMode.C:216-226).  With deviceDivTau the host copy is stale between write times: a caller
+// that still asks for it (post-processing function objects) gets a fresh download.
+Foam::tmp<Foam::volSymmTensorField> Foam::constitutiveEqs::LogConformationGPU::tau() const
+{
+    if (!tauOnHost_)
+    {
+        const label nI = U().mesh().nInternalFaces();
+        symmTensorField tauB(U().mesh().nFaces() - nI);
+        check(rheo_gpu_download(gpu_, 0, RHEO_FIELD_TAU_TOTAL, reinterpret_cast<double*>(tauTotal_.primitiveFieldRef().begin())), "download tau");
+        check(rheo_gpu_download(gpu_, 0, RHEO_FIELD_TAU_B_TOTAL, reinterpret_cast<double*>(tauB.begin())), "download tau_b");
+        forAll(tauTotal_.boundaryField(), pI)
+        {
+            fvPatchSymmTensorField& pf = tauTotal_.boundaryFieldRef()[pI];
+            if (!pf.size() || pf.patch().coupled() || isA<emptyFvPatch>(pf.patch())) continue;
+            forAll(pf, i) pf[i] = tauB[pf.patch().start() - nI + i];
+        }
+        tauOnHost_ = true;
+    }
+    return tauTotal_;
+}
+
+// constitutiveEq::divTau (constitutiveEq.C:72-132): the fvc::div terms come from the device (rheo_gpu_div_tau: Gauss linear,
+// which readSchemes has checked for div(tau) and div(grad(U))), the implicit laplacian and BSD's explicit laplacian are
+// OpenFOAM's.  multiMode (multiMode.C:143-157) sums the modes' matrices: the device sums tau_m/rho_m and etaP_m/rho_m, the
+// implicit part uses the summed etaP_ (constructor) like the single-mode classes.
+Foam::tmp<Foam::fvVectorMatrix> Foam::constitutiveEqs::LogConformationGPU::divTau(const volVectorField& U) const
+{
+    if (!deviceDivTau_ || solveCoupled_) return constitutiveEq::divTau(U);
+    const int32_t stab = stabOption_ == soNone ? RHEO_STAB_NONE : (stabOption_ == soBSD ? RHEO_STAB_BSD : RHEO_STAB_COUPLING);
+    volVectorField divExplicit
+    (
+        IOobject("divTauExplicit", U.time().timeName(), U.mesh(), IOobject::NO_READ, IOobject::NO_WRITE),
+        U.mesh(),
+        dimensionedVector("zero", dimensionSet(0, 1, -2, 0, 0, 0, 0), vector::zero)   // div(tau/rho)
+    );
+    check(rheo_gpu_div_tau(gpu_, stab, reinterpret_cast<double*>(divExplicit.primitiveFieldRef().begin())), "rheo_gpu_div_tau");
+    switch (stabOption_)
+    {
+        case soNone:
+            return divExplicit + fvm::laplacian(etaS()/rho(), U, "laplacian(eta,U)");
+        case soBSD:
+            return divExplicit - fvc::laplacian(etaP()/rho(), U, "laplacian(eta,U)")
+                 + fvm::laplacian((etaP() + etaS())/rho(), U, "laplacian(eta,U)");
+        default:
+            return divExplicit + fvm::laplacian((etaP() + etaS())/rho(), U, "laplacian(eta,U)");
     }
 }

@@ -127,7 +127,8 @@ def surface_flux(m: HostMesh, U: np.ndarray, U_b: np.ndarray) -> np.ndarray:
     return np.concatenate([(Uf * m.Sf[:n]).sum(1), (U_b * m.Sf[n:]).sum(1)])
 
 
-def write_case(case_dir, m: HostMesh, time: str, theta, tau, U, U_b, theta_b=None, tau_b=None, eigvals=None, eigvecs=None, name: str = "", gz: bool = False):
+def write_case(case_dir, m: HostMesh, time: str, theta, tau, U, U_b, theta_b=None, tau_b=None, eigvals=None, eigvecs=None, name: str = "", gz: bool = False,
+               Phi=None, Phi_b=None):
     """constant/polyMesh + <time>/{U, theta<name>, tau<name>[, eigVals<name>, eigVecs<name>]} as rheoFoam reads / writes them
     (CE/Oldroyd-B/Oldroyd-BLog/Oldroyd_BLog.C:52-113).  Boundary types come from the mesh's patch kinds and theta/tau BCs."""
     case_dir = Path(case_dir)
@@ -158,6 +159,9 @@ def write_case(case_dir, m: HostMesh, time: str, theta, tau, U, U_b, theta_b=Non
         write_field(tdir / f"eigVals{name}", f"eigVals{name}", eigvals, calc, gz=gz)
     if eigvecs is not None:
         write_field(tdir / f"eigVecs{name}", f"eigVecs{name}", eigvecs, calc, gz=gz)
+    if Phi is not None:   # BMPLog's fluidity (BMPLog.C:112-122): the BC kinds are theta's
+        write_field(tdir / f"Phi{name}", f"Phi{name}", np.asarray(Phi).reshape(-1, 1),
+                    patches(lambda p: p.theta_bc, np.asarray(Phi_b).reshape(-1, 1) if Phi_b is not None else np.zeros((nb, 1))), "[-1 1 1 0 0 0 0]", gz=gz)
 
 
 def read_case(case_dir, time: str, name: str = ""):
@@ -194,6 +198,7 @@ def read_case(case_dir, time: str, name: str = ""):
     fta.apply_bcs(m, "tau")
     _, eigvals, _ = load(f"eigVals{name}", 9, required=False)
     _, eigvecs, _ = load(f"eigVecs{name}", 9, required=False)
+    _, Phi, Phi_b = load(f"Phi{name}", 1, required=False)   # BMPLog's fluidity (MUST_READ there: the caller checks)
     # velocity on patches without a value entry (zeroGradient outlets): the internal value
     for pname, p in zip(m.patch_names, m.patches):
         if p.type == abi.PATCH_EMPTY or p.size == 0:
@@ -202,7 +207,7 @@ def read_case(case_dir, time: str, name: str = ""):
         if v is None:
             U_b[p.start - nint: p.start - nint + p.size] = U[m.owner[p.start: p.start + p.size]]
     return m, {"U": U, "U_b": U_b, "phi": surface_flux(m, U, U_b), "theta": theta, "theta_b": theta_b, "tau": tau, "tau_b": tau_b,
-               "eigvals": eigvals, "eigvecs": eigvecs}
+               "eigvals": eigvals, "eigvecs": eigvecs, "Phi": None if Phi is None else Phi[:, 0], "Phi_b": None if Phi_b is None else Phi_b[:, 0]}
 
 
 # ---------------------------------------------------------------- decomposed cases (processorN/ directories, decomposePar layout)

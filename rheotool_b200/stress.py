@@ -72,6 +72,21 @@ class GpuStressModel:
         arrs = [_c(a) for a in (theta, tau, eigvals, eigvecs, theta_b, tau_b)]
         _check(abi.lib().rheo_gpu_upload_state(self._h, mode, *[_p(a) for a in arrs]))
 
+    def upload_fluidity(self, mode=0, Phi=None, Phi_b=None):
+        """BMPLog: the fluidity field Phi (MUST_READ, BMPLog.C:112-122), cell values and (fixedValue patches) boundary values."""
+        a, b = _c(Phi), _c(Phi_b)
+        _check(abi.lib().rheo_gpu_upload_fluidity(self._h, mode, _p(a), _p(b)))
+
+    def fluidity(self, mode=0) -> np.ndarray:
+        out = np.zeros(self.mesh.n_cells)
+        _check(abi.lib().rheo_gpu_download(self._h, mode, abi.FIELD_FLUIDITY, _p(out)))
+        return out
+
+    def fluidity_b(self, mode=0) -> np.ndarray:
+        out = np.zeros(self.mesh.n_boundary)
+        _check(abi.lib().rheo_gpu_download(self._h, mode, abi.FIELD_FLUIDITY_B, _p(out)))
+        return out
+
     def upload_velocity(self, U, U_b, phi):
         U, U_b, phi = _c(U), _c(U_b), _c(phi)
         _check(abi.lib().rheo_gpu_upload_velocity(self._h, _p(U), _p(U_b), _p(phi)))
@@ -186,7 +201,7 @@ class GpuStressModel:
     def phase_times(self):
         out = np.zeros(7)
         _check(abi.lib().rheo_gpu_get_phase_times(self._h, _p(out)))
-        return dict(zip(["halo_bc", "grad_theta", "assemble", "solve", "eig_tau", "tau_bc", "total"], out.tolist()))
+        return dict(zip(["halo_bc", "flux_matrix", "assemble", "solve", "eig_tau", "tau_bc", "total"], out.tolist()))
 
     def set_kernel_timing(self, on: bool):
         _check(abi.lib().rheo_gpu_set_kernel_timing(self._h, 1 if on else 0))
@@ -257,6 +272,9 @@ def models_from_dict(params: dict) -> list:
             kw.pop("alpha", None)
             kw["ml_rtol"] = float(params.get("rTolMittagLeffler", 1e-12))
             kw["ml_max_iter"] = int(params.get("maxIterMittagLeffler", 200))
+    if t == "BMPLog":                 # BMPLog.C:129-136
+        for src in ("G0", "k", "Phi0", "PhiInf"):
+            kw["bmp_" + src] = float(params[src])
     if t == "SaramitoLog":            # SaramitoLog.C:108-165
         kw["sar_tau0"], kw["sar_n"] = float(params["tau0"]), float(params["n"])
         kw["sar_k"] = None if kw["sar_n"] == 1.0 else float(params["k"])

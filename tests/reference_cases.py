@@ -71,6 +71,8 @@ MATRIX_CASE = "GiesekusLog-3D-contraction-cubista"   # the case whose assembled 
 
 
 def digest(*arrays) -> str:
+    """sha256 of the inputs of a fixture case.  The SaramitoLog cases start from a stress the ORACLE computes (make_setup): its
+    last bit follows the compiler's FMA contraction choices, so callers pass that one array rounded to 9 decimals."""
     h = hashlib.sha256()
     for a in arrays:
         h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())

@@ -1,0 +1,121 @@
+"""SURVEY.md §8f rank 2, the last Log model: BMPLog (otherModels/BMP/BMPLog/BMPLog.C:142-201) — a thixotropic model whose
+fluidity Phi obeys its own transport equation (ddt + GaussDefCmpw convection == -Sp(1/lambda) + Phi0/lambda +
+k (PhiInf - Phi) (tau && symm(grad U))), solved before theta in every correct(); theta then relaxes at the rate Phi G0 and
+tau = G0 (c - I).  CPU tests hold the oracle to limits with known answers; GPU tests hold the device to the oracle."""
+import numpy as np
+import pytest
+
+from helpers import Setup, rel_l2, tight
+from oracle import oracle as orc
+from rheotool_b200 import abi, cases
+
+G0, PHI0 = 0.8, 2.5
+
+
+def _bmp(**kw):
+    base = dict(rho=1.0, etaS=0.01, etaP=0.01, lambda_=0.7, bmp_G0=G0, bmp_k=0.0, bmp_Phi0=PHI0, bmp_PhiInf=40.0)
+    base.update(kw)
+    return cases.model_desc("BMPLog", **base)
+
+
+def _spec(name, scale, model):
+    spec = cases.by_name(name, scale)
+    spec.models = [model]
+    return spec
+
+
+def _phi0(s, value=PHI0, vary=0.0):
+    Phi = np.full(s.mesh.n_cells, value) * (1.0 + vary * np.sin(5 * s.mesh.C[:, 0]) * np.cos(3 * s.mesh.C[:, 1]))
+    own_b = s.mesh.owner[s.mesh.n_internal:]
+    return Phi, Phi[own_b].copy()   # boundary values: those of the adjacent cells (fixedValue patches keep them)
+
+
+def test_without_structure_kinetics_bmp_is_oldroyd_b_with_lambda_from_the_fluidity():
+    """k = 0 and Phi = Phi0 everywhere (inlet included): Phi stays Phi0, so theta relaxes at Phi0 G0 = 1/lambda_OB and
+    tau = G0 (c - I) = (etaP_OB/lambda_OB)(c - I) with lambda_OB = 1/(Phi0 G0), etaP_OB = 1/Phi0."""
+    spec = _spec("C3", 3 / 19, _bmp())
+    s = Setup(spec)
+    a = s.oracle(tight(spec.schemes))
+    Phi, Phi_b = _phi0(s)
+    a.set_fluidity(0, 0, Phi, Phi_b)
+    spec_ob = _spec("C3", 3 / 19, cases.model_desc("Oldroyd-BLog", rho=1.0, etaS=0.01, etaP=1.0 / PHI0, lambda_=1.0 / (PHI0 * G0)))
+    b = Setup(spec_ob).oracle(tight(spec.schemes))
+    for oc in (a, b):
+        for _ in range(2):
+            oc.store_old_time(); oc.step(s.dt)
+    assert np.abs(a.get(0, 0, abi.FIELD_FLUIDITY) - PHI0).max() <= 1e-12 * PHI0
+    assert rel_l2(a.get(0, 0, abi.FIELD_THETA), b.get(0, 0, abi.FIELD_THETA)) <= 1e-12
+    assert rel_l2(a.get(0, 0, abi.FIELD_TAU), b.get(0, 0, abi.FIELD_TAU)) <= 1e-12
+
+
+def test_fluidity_of_a_fluid_at_rest_relaxes_to_phi0_at_the_rate_one_over_lambda():
+    """U = 0: (Phi1 - Phi_old)/dt = (Phi0 - Phi1)/lambda for the Euler scheme, cell by cell"""
+    spec = _spec("C5", 10 / 400, _bmp(bmp_k=3.0))
+    s = Setup(spec)
+    oc = s.oracle(tight(spec.schemes))
+    Phi, Phi_b = _phi0(s, value=7.0)
+    oc.set_fluidity(0, 0, Phi, Phi_b)
+    oc.set_velocity(0, np.zeros_like(s.U), np.zeros_like(s.Ub), np.zeros_like(s.phi))
+    dt, lam = 0.05, 0.7
+    oc.store_old_time(); oc.step(dt)
+    exact = (7.0 / dt + PHI0 / lam) / (1.0 / dt + 1.0 / lam)
+    assert np.abs(oc.get(0, 0, abi.FIELD_FLUIDITY) - exact).max() <= 1e-12 * exact
+
+
+def test_shear_breaks_the_structure_down():
+    """k > 0 in a flow with tau && D > 0 somewhere: the fluidity rises above the value the k = 0 model reaches"""
+    out = []
+    for k in (0.0, 2.0):
+        spec = _spec("C3", 3 / 19, _bmp(bmp_k=k))
+        s = Setup(spec)
+        oc = s.oracle(tight(spec.schemes))
+        Phi, Phi_b = _phi0(s, vary=0.05)
+        oc.set_fluidity(0, 0, Phi, Phi_b)
+        for _ in range(3):
+            oc.store_old_time(); oc.step(s.dt)
+        out.append((oc.get(0, 0, abi.FIELD_FLUIDITY), oc.get(0, 0, abi.FIELD_THETA)))
+    assert np.isfinite(out[1][0]).all() and np.isfinite(out[1][1]).all()
+    assert np.abs(out[1][0] - out[0][0]).max() > 1e-6 * PHI0
+    assert rel_l2(out[1][1], out[0][1]) > 1e-9
+
+
+def test_bmp_is_single_mode_only():
+    spec = _spec("C3", 3 / 19, _bmp())
+    spec.models = [_bmp(), _bmp()]
+    with pytest.raises(RuntimeError):
+        Setup(spec).oracle(tight(spec.schemes))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,scale,ddt", [("C3", 4 / 19, "Euler"), ("C2", 1 / 9, "Euler"), ("C5", 16 / 400, "backward")])
+def test_gpu_bmp_log_matches_oracle(name, scale, ddt):
+    spec = _spec(name, scale, _bmp(bmp_k=2.0, bmp_relax=0.0))
+    sc = tight(spec.schemes)
+    sc.ddt = {"Euler": abi.DDT_EULER, "backward": abi.DDT_BACKWARD}[ddt]
+    s = Setup(spec)
+    oc, g = s.oracle(sc), s.gpu(sc)
+    Phi, Phi_b = _phi0(s, vary=0.05)
+    oc.set_fluidity(0, 0, Phi, Phi_b); g.upload_fluidity(0, Phi, Phi_b)
+    for _ in range(3):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    assert rel_l2(g.fluidity(0), oc.get(0, 0, abi.FIELD_FLUIDITY)) <= 1e-10
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-10
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-10
+
+
+@pytest.mark.gpu
+def test_gpu_bmp_log_relaxed_equations_match_oracle():
+    """PhiEqn.relax() and thetaEqn.relax() with their own factors (BMPLog.C:165,189)"""
+    spec = _spec("C3", 3 / 19, _bmp(bmp_k=1.0, bmp_relax=0.6))
+    sc = tight(spec.schemes)
+    sc.relax = 0.8
+    s = Setup(spec)
+    oc, g = s.oracle(sc), s.gpu(sc)
+    Phi, Phi_b = _phi0(s, vary=0.05)
+    oc.set_fluidity(0, 0, Phi, Phi_b); g.upload_fluidity(0, Phi, Phi_b)
+    for _ in range(2):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    assert rel_l2(g.fluidity(0), oc.get(0, 0, abi.FIELD_FLUIDITY)) <= 1e-10
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-10

@@ -36,7 +36,7 @@ def main():
         oc = s.oracle(spec.schemes, sort_eig=False)     # only used to evaluate the initial boundary values
         st = {"theta": s.theta0, "theta_b": oc.get(0, 0, abi.FIELD_THETA_B), "tau": s.tau0, "tau_b": oc.get(0, 0, abi.FIELD_TAU_B),
               "eigvals": s.eigvals, "eigvecs": s.eigvecs}
-        out[f"{name}/inputs"] = np.frombuffer(digest(s.U, s.Ub, s.phi, s.theta0, st["theta_b"], s.eigvals, s.eigvecs, [s.dt], s.tau0).encode(), dtype=np.uint8)
+        out[f"{name}/inputs"] = np.frombuffer(digest(s.U, s.Ub, s.phi, s.theta0, st["theta_b"], s.eigvals, s.eigvecs, [s.dt], np.round(s.tau0, 9)).encode(), dtype=np.uint8)
         for k in range(N_STEPS):
             st = ref.correct(s.mesh.desc, spec.models[0], spec.schemes.limiter, s.dt, s.U, s.Ub, s.phi, st["theta"], st["theta_b"],
                              st["tau"], st["tau_b"], st["eigvals"], st["eigvecs"], want_matrix=(k == 0 and name == MATRIX_CASE))

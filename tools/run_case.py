@@ -53,6 +53,10 @@ def main():
     g = GpuStressModel(m, models, schemes, 0)
     for mi, fm in enumerate(per_mode):
         g.upload_state(mi, fm["theta"], fm["tau"], fm["eigvals"], fm["eigvecs"], theta_b=fm["theta_b"])
+        if models[mi].model == abi.MODEL_BMP_LOG:   # BMPLog.C:112-122: Phi is MUST_READ
+            if fm["Phi"] is None:
+                raise SystemExit(f"{case / a.time / ('Phi' + names[mi])}: MUST_READ field is missing (BMPLog)")
+            g.upload_fluidity(mi, fm["Phi"], fm["Phi_b"])
     g.upload_velocity(f["U"], f["U_b"], f["phi"])
     for n in range(a.steps):
         g.store_old_time()
@@ -61,7 +65,9 @@ def main():
     t_new = f"{float(a.time) + a.steps * a.dt:g}"
     for mi, n in enumerate(names):
         foamio.write_case(case, m, t_new, g.theta(mi), g.tau(mi), f["U"], f["U_b"], theta_b=g.download(abi.FIELD_THETA_B, mi), tau_b=g.download(abi.FIELD_TAU_B, mi),
-                          eigvals=g.download(abi.FIELD_EIGVALS, mi), eigvecs=g.download(abi.FIELD_EIGVECS, mi), name=n, gz=a.gz)
+                          eigvals=g.download(abi.FIELD_EIGVALS, mi), eigvecs=g.download(abi.FIELD_EIGVECS, mi), name=n, gz=a.gz,
+                          Phi=g.fluidity(mi) if models[mi].model == abi.MODEL_BMP_LOG else None,
+                          Phi_b=g.fluidity_b(mi) if models[mi].model == abi.MODEL_BMP_LOG else None)
     print(f"wrote {Path(a.case) / t_new}")
 
 
