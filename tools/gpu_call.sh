@@ -1,9 +1,10 @@
-# scratch GPU call (tag r3l): whole GPU suite with the PDL policy + BMPLog, C5 N = 1 default bench line
-python -m pytest tests -m gpu -q 2>&1 | tail -8 > gpurun_out/r3l_pytest.log; cat gpurun_out/r3l_pytest.log
-(time python bench.py --steps 10 --warmup 3) > gpurun_out/r3l_bench_C5.json 2> gpurun_out/r3l_bench_C5.err; tail -4 gpurun_out/r3l_bench_C5.err
-python - <<PYEOF
-import json
-d=json.load(open('gpurun_out/r3l_bench_C5.json'))
-print('C5', round(d['value'],1), 'Mcs/s', round(d['ms_per_step'],3), 'ms; step_frac', round(d['roofline']['step_frac'],3), d['config']['ms_per_timed_step'], 'e2e', d['e2e']['value'], 'e2e_tau', d['e2e_tau_download']['value'], 'cpu', d['cpu_baseline'] and d['cpu_baseline']['value'], 'parity', d['parity'] and d['parity']['ok'])
-print(d['roofline']['kernels_ms_per_step']); print(d['phase_ms'])
-PYEOF
+# GPU evidence call (tag r2f): (1) ncu launch list of the default bench command (C5, N = 1) with the DRAM byte counters of every
+# launch in the same pass; (2) ncu --set full of one whole step of the half-scale C5 mesh (8 M cells, same kernels / colours)
+KR='k_flux3|k_source_init|k_bsweep|k_bspmv0|k_spmv|k_update_x_r|k_eig_tau'
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2f_launches_C5.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r2f_ncu_l_C5.log 2>&1
+tail -2 gpurun_out/r2f_ncu_l_C5.log | cut -c1-300; wc -l gpurun_out/r2f_launches_C5.csv
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"$KR" -s 70 -c 30 -f -o gpurun_out/r2f_full_C5h \
+  python bench.py --config C5 --scale 0.5 --steps 2 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/r2f_ncu_f_C5h.log 2>&1
+ncu -i gpurun_out/r2f_full_C5h.ncu-rep --page raw --csv > gpurun_out/r2f_full_C5h_raw.csv 2>/dev/null
+ls -la gpurun_out/r2f_*
