@@ -39,6 +39,8 @@ extern "C" {
 #define RHEO_BC_LINEAR_EXTRAPOLATION 2   /* rheoTool's wall BC for tau (fixedValue-derived)  */
 #define RHEO_BC_EMPTY                3
 #define RHEO_BC_PROCESSOR            4
+#define RHEO_BC_LINEAR_EXTRAPOLATION_REG 5   /* the same patch type with `useRegression true`: least-squares line through the wall
+                                              cell's face and centre values (linearExtrapolationFvPatchField.C:72,152-219)        */
 
 typedef struct RheoPatchDesc {
     int32_t type;      /* RHEO_PATCH_*                                              */

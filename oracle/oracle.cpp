@@ -38,6 +38,7 @@
 #include <cstdint>
 #include <cstring>
 #include <string>
+#include <array>
 #include <vector>
 
 #include <omp.h>
@@ -1107,6 +1108,68 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
                     }
                 }
                 std::copy(varp.begin(), varp.end(), mo.tauB.begin() + (size_t)6 * (p.start - m.nInt));
+            } else if (p.tau_bc == RHEO_BC_LINEAR_EXTRAPOLATION_REG) {
+                // linearExtrapolationFvPatchField.C:152-219 (useRegression true): least-squares line y(x) through the values linearly
+                // interpolated to the wall cell's INTERNAL faces (coupled faces are skipped, :181-183) and the cell value, x = wall
+                // distance of the face / cell centre along the patch-face normal; wall value = y(0) = yav - xav num/den.
+                // Faces in the order of EXT-OF9 primitiveMesh::cells(): the cell's owner faces, then its neighbour faces, ascending.
+                std::vector<int> listOf(m.nCells, -1);
+                std::vector<std::vector<int>> cellFaces;
+                for (int i = 0; i < p.size; ++i) {
+                    const int c = m.own[p.start + i];
+                    if (listOf[c] < 0) { listOf[c] = (int)cellFaces.size(); cellFaces.emplace_back(); }
+                }
+                for (int f = 0; f < m.nInt; ++f) if (listOf[m.own[f]] >= 0) cellFaces[listOf[m.own[f]]].push_back(f);
+                for (int f = 0; f < m.nInt; ++f) if (listOf[m.nei[f]] >= 0) cellFaces[listOf[m.nei[f]]].push_back(f);
+                for (int i = 0; i < p.size; ++i) {
+                    const int fp = p.start + i, cellA = m.own[fp];
+                    const double* Sp = &m.Sf[3 * (size_t)fp];
+                    const double magSp = std::sqrt(Sp[0] * Sp[0] + Sp[1] * Sp[1] + Sp[2] * Sp[2]);
+                    const double n[3] = {Sp[0] / magSp, Sp[1] / magSp, Sp[2] / magSp};
+                    const double* fx = &m.Cf[3 * (size_t)fp];
+                    std::vector<double> x;
+                    std::vector<std::array<double, 6>> y;
+                    double xav = 0;
+                    std::array<double, 6> yav{};
+                    auto add_face = [&](int f) {
+                        const int P = m.own[f], N = m.nei[f];
+                        const double* S = &m.Sf[3 * (size_t)f];
+                        const double* cf = &m.Cf[3 * (size_t)f];
+                        double so = 0, sn = 0, xd = 0;
+                        for (int d = 0; d < 3; ++d) {
+                            so += S[d] * (cf[d] - m.C[3 * (size_t)P + d]);
+                            sn += S[d] * (m.C[3 * (size_t)N + d] - cf[d]);
+                            xd += n[d] * (fx[d] - cf[d]);
+                        }
+                        const double SfdOwn = std::fabs(so), SfdNei = std::fabs(sn);
+                        const double w = SfdOwn / (SfdOwn + SfdNei);
+                        std::array<double, 6> yy;
+                        for (int q = 0; q < 6; ++q) { yy[q] = w * mo.tau[(size_t)6 * N + q] + (1. - w) * mo.tau[(size_t)6 * P + q]; yav[q] += yy[q]; }
+                        y.push_back(yy);
+                        x.push_back(std::fabs(xd));
+                        xav += x.back();
+                    };
+                    for (int f : cellFaces[listOf[cellA]]) add_face(f);
+                    {   // last pair: the cell itself
+                        std::array<double, 6> yy;
+                        double xd = 0;
+                        for (int q = 0; q < 6; ++q) { yy[q] = mo.tau[(size_t)6 * cellA + q]; yav[q] += yy[q]; }
+                        for (int d = 0; d < 3; ++d) xd += n[d] * (fx[d] - m.C[3 * (size_t)cellA + d]);
+                        y.push_back(yy);
+                        x.push_back(std::fabs(xd));
+                        xav += x.back();
+                    }
+                    const int id = (int)x.size();
+                    for (int q = 0; q < 6; ++q) yav[q] /= id;
+                    xav /= id;
+                    double den = 0;
+                    std::array<double, 6> num{};
+                    for (int k = 0; k < id; ++k) {
+                        for (int q = 0; q < 6; ++q) num[q] += (x[k] - xav) * (y[k][q] - yav[q]);
+                        den += (x[k] - xav) * (x[k] - xav);
+                    }
+                    for (int q = 0; q < 6; ++q) mo.tauB[(size_t)6 * (fp - m.nInt) + q] = yav[q] - xav * num[q] / den;
+                }
             }   // fixedValue: unchanged
         }
     });

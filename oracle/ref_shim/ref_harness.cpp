@@ -90,11 +90,12 @@ void GeometricField<Type, PatchField, GeoMesh>::correctBoundaryConditions()
             {
                 static_cast<Field<Type>&>(pf) = pf.patchInternalField();
             }
-            else if (pf.kind_ == pfLinearExtrapolation)
+            else if (pf.kind_ == pfLinearExtrapolation || pf.kind_ == pfLinearExtrapolationReg)
             {
                 if constexpr (std::is_same<Type, symmTensor>::value)
                 {
-                    linearExtrapolationFvPatchField<Type> bc(*this, patchi, refHarness::useRegression);
+                    // useRegression (linearExtrapolationFvPatchField.C:72): per patch (RHEO_BC_LINEAR_EXTRAPOLATION_REG) or for the whole call
+                    linearExtrapolationFvPatchField<Type> bc(*this, patchi, refHarness::useRegression || pf.kind_ == pfLinearExtrapolationReg);
                     bc.updateCoeffs();
                 }
             }
@@ -164,6 +165,7 @@ static int bcKind(int bc)
         case RHEO_BC_FIXED_VALUE: return pfFixedValue;
         case RHEO_BC_ZERO_GRADIENT: return pfZeroGradient;
         case RHEO_BC_LINEAR_EXTRAPOLATION: return pfLinearExtrapolation;
+        case RHEO_BC_LINEAR_EXTRAPOLATION_REG: return pfLinearExtrapolationReg;
         case RHEO_BC_EMPTY: return pfEmpty;
         case RHEO_BC_PROCESSOR: return pfProcessor;
     }

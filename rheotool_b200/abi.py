@@ -15,7 +15,7 @@ _HOST_LIB_PATH = Path(__file__).resolve().parent / "librheo_host.so"
 
 # ---- constants (keep in sync with include/*.h) ---------------------------------------------------
 PATCH_PATCH, PATCH_WALL, PATCH_EMPTY, PATCH_PROCESSOR = 0, 1, 2, 3
-BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSOR = 0, 1, 2, 3, 4
+BC_FIXED_VALUE, BC_ZERO_GRADIENT, BC_LINEAR_EXTRAPOLATION, BC_EMPTY, BC_PROCESSOR, BC_LINEAR_EXTRAPOLATION_REG = 0, 1, 2, 3, 4, 5
 MODEL_OLDROYD_B_LOG, MODEL_GIESEKUS_LOG, MODEL_PTT_LOG, MODEL_FENE_P_LOG, MODEL_FENE_CR_LOG, MODEL_WM_CY_LOG, MODEL_ROLIE_POLY_LOG, MODEL_XPOMPOM_LOG, MODEL_SARAMITO_LOG, MODEL_BMP_LOG = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 PTT_LINEAR, PTT_EXPONENTIAL, PTT_GENERALIZED = 0, 1, 2
 LIMITER = {"upwind": 0, "cubista": 1, "minmod": 2, "smart": 3, "waceb": 4, "superbee": 5, "none": 6}

@@ -148,6 +148,7 @@ struct RheoGpu {
     DevBuf d_tileOrder;            // rec3: the assembly's tile walk (sweepOrder padded to nTiles); RHEO_TILE_ORDER=0 walks in index order
     bool pdl = true;               // programmatic dependent launch on this handle's kernels (pdl_policy)
     int nHidden = 0;               // BMPLog: its fluidity equation is modes[0] (RHEO_MODEL_BMP_FLUIDITY), the caller's mode 0 is modes[1]
+    DevBuf d_CfI;                  // [3][nInt] internal face centres, only when a patch uses linearExtrapolation with useRegression
     DevBuf d_gradUb;               // [9][nB] patch values of fvc::grad(U) (rheo_gpu_div_tau, allocated on first use)
     DevBuf d_rowsum, d_inflow;     // rec3: row sums of the matrix and inflow-slot masks (written by k_flux3 with the matrix)
     MeshView mv;
@@ -349,6 +350,7 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
     std::vector<int> ghostOfB(nB, -1), haloCell;
     std::vector<int> bkind(nB, RHEO_PATCH_EMPTY), bthetaBC(nB, RHEO_BC_EMPTY), btauBC(nB, RHEO_BC_EMPTY), bcell(nB);
     int H = 0;
+    bool needCfI = false;
     for (const RheoPatchDesc& p : h->patches) {
         if (p.start < nInt || p.start + p.size > nF) return fail("rheo_gpu_create: patch range outside the boundary faces");
         if (p.type == RHEO_PATCH_PROCESSOR) h->segs.push_back({p.nbr_rank, H, p.size});
@@ -362,8 +364,10 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
             } else if (p.type != RHEO_PATCH_EMPTY) {
                 if (p.theta_bc != RHEO_BC_FIXED_VALUE && p.theta_bc != RHEO_BC_ZERO_GRADIENT)
                     return fail("rheo_gpu_create: theta BC must be fixedValue or zeroGradient on physical patches");
-                if (p.tau_bc != RHEO_BC_FIXED_VALUE && p.tau_bc != RHEO_BC_ZERO_GRADIENT && p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION)
+                if (p.tau_bc != RHEO_BC_FIXED_VALUE && p.tau_bc != RHEO_BC_ZERO_GRADIENT && p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION &&
+                    p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION_REG)
                     return fail("rheo_gpu_create: tau BC must be fixedValue, zeroGradient or linearExtrapolation on physical patches");
+                if (p.tau_bc == RHEO_BC_LINEAR_EXTRAPOLATION_REG) needCfI = true;
             }
         }
     }
@@ -434,6 +438,15 @@ int build_mesh(RheoGpu* h, const RheoMeshDesc* d, bool allowBlocks = true) {
         if (upload(h->d_bcells, bc)) return 1;
     }
     // ---- geometry in device order
+    if (needCfI) {   // internal face centres: only the regression flavour of linearExtrapolation reads them (k_tau_bc_regress)
+        std::vector<double> CfI(3 * (size_t)std::max(nInt, 1));
+        for (int q = 0; q < nInt; ++q) {
+            const int o = h->faceOld[q];
+            const int f = (o > 0 ? o : -o) - 1;
+            for (int e = 0; e < 3; ++e) CfI[(size_t)e * nInt + q] = d->Cf[3 * (size_t)f + e];
+        }
+        if (upload(h->d_CfI, CfI)) return 1;
+    } else h->d_CfI.release();
     std::vector<double> Sf(3 * (size_t)nF), w(nF), C(3 * (size_t)h->NP, 0.0), V(N), rV(N), CfB(3 * (size_t)nB);
     for (int q = 0; q < nF; ++q) {
         const int o = h->faceOld[q];
@@ -1170,6 +1183,11 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* statsOut) {
             for (const RheoPatchDesc* pp : ordered) {
                 const RheoPatchDesc& p = *pp;
                 if (p.type != RHEO_PATCH_EMPTY && p.type != RHEO_PATCH_PROCESSOR && p.tau_bc == RHEO_BC_ZERO_GRADIENT && p.size > 0) pending = true;
+                if (p.type != RHEO_PATCH_EMPTY && p.type != RHEO_PATCH_PROCESSOR && p.tau_bc == RHEO_BC_LINEAR_EXTRAPOLATION_REG && p.size > 0) {
+                    // useRegression true: cell values only, independent of the other patches' boundary values
+                    LAUNCH(h, k_tau_bc_regress, cdiv(p.size, 128), 128, h->mv, h->d_CfI.as<double>(), p.start - h->nInt, p.size, md.tau.as<double>(), md.tauB.as<double>());
+                    continue;
+                }
                 if (p.type == RHEO_PATCH_EMPTY || p.type == RHEO_PATCH_PROCESSOR || p.tau_bc != RHEO_BC_LINEAR_EXTRAPOLATION || p.size == 0) continue;
                 const int b0 = p.start - h->nInt;
                 flush(b0);
@@ -1268,7 +1286,7 @@ void rheo_gpu_destroy(RheoGpu* h) {
                       &h->d_bkind, &h->d_bthetaBC, &h->d_btauBC, &h->d_CfB, &h->d_haloCell, &h->d_send, &h->d_recv,
                       &h->d_tileRec, &h->d_Fell, &h->d_gradU, &h->d_sumPsi, &h->d_mailbox, &h->d_peerSegs, &h->d_segOfGhost, &h->d_peerMisc,
                       &h->d_U, &h->d_Ub, &h->d_phi, &h->d_diag, &h->d_rD, &h->d_Fs, &h->d_FsT, &h->d_stage, &h->d_tmpB, &h->d_r, &h->d_r0, &h->d_p,
-                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev, &h->d_rowsum, &h->d_inflow, &h->d_tileOrder, &h->d_gradUb})
+                      &h->d_y, &h->d_v, &h->d_s, &h->d_z, &h->d_t, &h->d_ks, &h->d_partials, &h->d_red, &h->d_counter, &h->d_bcells, &h->d_lev, &h->d_chunkLev, &h->d_rowsum, &h->d_inflow, &h->d_tileOrder, &h->d_gradUb, &h->d_CfI})
         b->release();
     for (ModeDev& md : h->modes)
         for (DevBuf* b : {&md.theta, &md.thetaOld, &md.tau, &md.lam, &md.R, &md.fFene, &md.bsrc, &md.thetaB, &md.tauB, &md.gammaVals, &md.corr, &md.thetaOldOld, &md.ddt0, &md.lamCell, &md.etaCell}) b->release();

@@ -345,6 +345,82 @@ __global__ void k_tau_bc_linext(MeshView m, int start, int size, const double* _
 #pragma unroll
     for (int k = 0; k < 6; ++k) tmp[(size_t)k * size + i] = own[k] + (g[3 * k] * dx + g[3 * k + 1] * dy + g[3 * k + 2] * dz);
 }
+// linearExtrapolation with `useRegression true` (linearExtrapolationFvPatchField.C:152-219): per patch face the least-squares
+// line through (wall distance, value) of the wall cell's internal faces (values linearly interpolated with weights recomputed
+// from the face centres, :186-190; faces on coupled patches are skipped, :181-183) and of the cell centre; wall value =
+// yav - xav num/den.  Two passes over the cell's slots (averages, then the sums) instead of the reference's lists; reads cell
+// values only, so the patch order does not matter.  CfI: [3][nInt] internal face centres in device face order.
+__global__ void k_tau_bc_regress(MeshView m, const double* __restrict__ CfI, int start, int size, const double* __restrict__ tau, double* __restrict__ tauB) {
+    pdl_sync();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= size) return;
+    const int b = start + i;
+    const int c = m.bcell[b];
+    const size_t fp = (size_t)m.nInt + b;
+    double n[3] = {m.Sf[fp], m.Sf[(size_t)m.nF + fp], m.Sf[2 * (size_t)m.nF + fp]};
+    const double magS = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+    double fx[3], Cc[3], own[6];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) { n[d] /= magS; fx[d] = m.CfB[(size_t)d * m.nB + b]; Cc[d] = m.C[(size_t)d * m.NP + c]; }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) own[q] = tau[(size_t)q * m.NP + c];
+    double xav = 0, yav[6], den = 0, num[6];
+    int id = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            xav /= id;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) { yav[q] /= id; num[q] = 0.0; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) yav[q] = 0.0;
+        }
+        for (int s = 0; s <= m.K; ++s) {
+            double x, y[6];
+            if (s < m.K) {
+                const int nb = m.nbr[(size_t)s * m.NS + c];
+                if (nb < 0 || nb >= m.N) continue;   // boundary / empty slot, or a processor face
+                const int fi = m.fidx[(size_t)s * m.NS + c];
+                const size_t f = fi >= 0 ? fi : ~fi;
+                const int P = fi >= 0 ? c : nb, N = fi >= 0 ? nb : c;
+                double so = 0, sn = 0, xd = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    const double S = m.Sf[(size_t)d * m.nF + f], cf = CfI[(size_t)d * m.nInt + f];
+                    so += S * (cf - m.C[(size_t)d * m.NP + P]);
+                    sn += S * (m.C[(size_t)d * m.NP + N] - cf);
+                    xd += n[d] * (fx[d] - cf);
+                }
+                const double SfdOwn = fabs(so), SfdNei = fabs(sn);
+                const double w = SfdOwn / (SfdOwn + SfdNei);
+                x = fabs(xd);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const double vn = tau[(size_t)q * m.NP + nb];
+                    y[q] = fi >= 0 ? w * vn + (1. - w) * own[q] : w * own[q] + (1. - w) * vn;   // w var[neighbour] + (1 - w) var[owner]
+                }
+            } else {   // last pair: the cell itself
+                double xd = 0;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) xd += n[d] * (fx[d] - Cc[d]);
+                x = fabs(xd);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) y[q] = own[q];
+            }
+            if (pass == 0) {
+                xav += x; ++id;
+#pragma unroll
+                for (int q = 0; q < 6; ++q) yav[q] += y[q];
+            } else {
+                den += (x - xav) * (x - xav);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) num[q] += (x - xav) * (y[q] - yav[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q) tauB[(size_t)q * m.nB + b] = yav[q] - xav * num[q] / den;
+}
 __global__ void k_tau_bc_commit(int nB, int start, int size, const double* __restrict__ tmp, double* __restrict__ tauB) {
     pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -684,16 +684,12 @@ int rheo_io_apply_field_bcs(RheoHostMesh* m, const RheoFoamField* f, int32_t whi
             return 1;
         }
         if (code == RHEO_BC_LINEAR_EXTRAPOLATION) {
-            // linearExtrapolationFvPatchField.C:72,118: `useRegression true` selects the least-squares branch (:152-219), which the
-            // device does not implement (the gradient branch :101-151 only) — fail loudly instead of extrapolating differently
+            // linearExtrapolationFvPatchField.C:72,118: `useRegression true` selects the least-squares branch (:152-219) instead of
+            // the gradient branch (:101-151); only tau patches are extrapolated
             const Entry* ur = e->sub->find_exact("useRegression");
             if (ur && !ur->value.empty()) {
                 const std::string& v = ur->value[0].s;
-                if (v == "true" || v == "on" || v == "yes" || v == "1" || v == "y" || v == "t") {
-                    rheo::set_error("rheo_io_apply_field_bcs: patch " + name + " of field " + f->object +
-                                    " sets useRegression true; the stress step implements the gradient branch of linearExtrapolation only");
-                    return 1;
-                }
+                if (v == "true" || v == "on" || v == "yes" || v == "1" || v == "y" || v == "t") code = RHEO_BC_LINEAR_EXTRAPOLATION_REG;
             }
         }
         (which == 0 ? m->patches[p].theta_bc : m->patches[p].tau_bc) = code;

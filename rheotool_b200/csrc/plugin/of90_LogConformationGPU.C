@@ -306,8 +306,8 @@ void LogConformationGPU::buildMeshDesc
                      : isA<zeroGradientFvPatchSymmTensorField>(ub) ? RHEO_BC_ZERO_GRADIENT : RHEO_BC_FIXED_VALUE;
             if (q.tau_bc == RHEO_BC_LINEAR_EXTRAPOLATION)
             {
-                // useReg_ is private (linearExtrapolationFvPatchField.H:82) but write() prints it (.C:230): the device has
-                // the gradient branch (.C:101-151) only, so the regression branch (.C:152-219) is refused
+                // useReg_ is private (linearExtrapolationFvPatchField.H:82) but write() prints it (.C:230): `useRegression true`
+                // selects the least-squares branch (.C:152-219) instead of the gradient branch (.C:101-151)
                 OStringStream os;
                 ub.write(os);
                 const string txt(os.str());
@@ -316,11 +316,7 @@ void LogConformationGPU::buildMeshDesc
                 {
                     IStringStream is(txt.substr(at + 13));
                     const Switch sw(is);
-                    if (sw)
-                    {
-                        FatalErrorInFunction << "patch " << p.name() << " of " << ta.name() << " sets useRegression true; the GPU stress "
-                            << "step implements the gradient branch of linearExtrapolation only" << exit(FatalError);
-                    }
+                    if (sw) q.tau_bc = RHEO_BC_LINEAR_EXTRAPOLATION_REG;
                 }
             }
         }

@@ -114,7 +114,9 @@ def write_field(path, obj: str, internal: np.ndarray, patches: list, dimensions:
 
 # ---------------------------------------------------------------- whole cases (constant/polyMesh + a time directory)
 BC_WORD = {abi.BC_FIXED_VALUE: "fixedValue", abi.BC_ZERO_GRADIENT: "zeroGradient", abi.BC_LINEAR_EXTRAPOLATION: "linearExtrapolation",
-           abi.BC_EMPTY: "empty", abi.BC_PROCESSOR: "processor"}
+           abi.BC_EMPTY: "empty", abi.BC_PROCESSOR: "processor",
+           # the writer prints `type <word>;`: the regression flavour carries its extra keyword along (linearExtrapolationFvPatchField.C:230)
+           abi.BC_LINEAR_EXTRAPOLATION_REG: "linearExtrapolation;\n        useRegression   true"}
 DIMENSIONS = {"tau": "[1 -1 -2 0 0 0 0]", "U": "[0 1 -1 0 0 0 0]"}
 
 
@@ -145,7 +147,7 @@ def write_case(case_dir, m: HostMesh, time: str, theta, tau, U, U_b, theta_b=Non
                 out.append((pname, "processor", None if values is None else values[sl]))
             else:
                 word = BC_WORD[bc_of(p)] if bc_of else fixed_word
-                has_value = word in ("fixedValue", "linearExtrapolation")
+                has_value = word == "fixedValue" or word.startswith("linearExtrapolation")
                 out.append((pname, word, values[sl] if (has_value and values is not None) else None))
         return out
 

@@ -31,6 +31,16 @@ def _fixed_theta_walls(spec):
     return spec
 
 
+def _regression_walls(spec):
+    """linearExtrapolation walls with `useRegression true` (linearExtrapolationFvPatchField.C:72,152-219)"""
+    import copy
+    spec.grid.patches = [copy.copy(p) for p in spec.grid.patches]
+    for p in spec.grid.patches:
+        if p.tau_bc == abi.BC_LINEAR_EXTRAPOLATION:
+            p.tau_bc = abi.BC_LINEAR_EXTRAPOLATION_REG
+    return spec
+
+
 # name -> (spec factory, limiter).  Every model whose correct() the reference harness compiles, every limiter row,
 # 2-D (empty patches, fixedValue inlet, zeroGradient outlet, linearExtrapolation walls) and 3-D meshes.
 REFERENCE_CASES = {
@@ -50,6 +60,8 @@ REFERENCE_CASES = {
     "SaramitoLog-n075-2D-cubista": lambda: _with(cases.channel_2d(24, 10), [cases.model_desc("SaramitoLog", 1.0, 0.01, 0.99, 0.1, sar_tau0=2.5, sar_k=1.5, sar_n=0.75, sar_dims=(1, 1, 0))], "cubista"),
     "SaramitoLog-n1-linearPTT-3D-minmod": lambda: _with(cases.cube(7, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("SaramitoLog", 1.0, 0.01, 0.99, 0.1, epsilon=0.1, zeta=0.1, sar_tau0=1.0, sar_n=1.0, sar_ptt="linear")], "minmod"),
     "SaramitoLog-n1-expPTT-3D-cubista": lambda: _with(cases.cube(7, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("SaramitoLog", 1.0, 0.01, 0.99, 0.1, epsilon=0.1, zeta=0.05, sar_tau0=1.0, sar_n=1.0, sar_ptt="exponential")], "cubista"),
+    "OldroydBLog-2D-cubista-regressionWalls": lambda: _with(_regression_walls(cases.channel_2d(30, 12)), [cases.model_desc("Oldroyd-BLog", 1.0, 0.59, 0.41, 0.7)], "cubista"),
+    "GiesekusLog-3D-contraction-cubista-regressionWalls": lambda: _with(_regression_walls(cases.by_name("C3", 1 / 19)), [cases.model_desc("GiesekusLog", 1.0, 0.01, 0.99, 0.1, alpha=0.2)], "cubista"),
     "OldroydBLog-3D-cavity-upwind": lambda: _with(cases.cube(8, "cavity", 1, "Oldroyd-BLog"), [cases.model_desc("Oldroyd-BLog", 1.0, 0.01, 0.99, 0.1)], "upwind"),
 }
 

@@ -373,9 +373,9 @@ def test_schemes_the_device_does_not_implement_are_refused(tmp_path):
     assert solver == "PBiCGStab"
 
 
-def test_linear_extrapolation_with_regression_is_refused(tmp_path):
-    """linearExtrapolationFvPatchField.C:72,118,152-219: `useRegression true` selects the least-squares branch, which the
-    device does not have — the case reader says so instead of extrapolating with the gradient branch."""
+def test_linear_extrapolation_with_regression_is_read_and_written(tmp_path):
+    """linearExtrapolationFvPatchField.C:72,118,152-219: `useRegression true` selects the least-squares branch — its own BC code,
+    kept through a write / read round trip."""
     spec = cases.by_name("C3", 2 / 19)
     m = mesh.tensor_grid(spec.grid)
     n = m.n_cells
@@ -384,11 +384,16 @@ def test_linear_extrapolation_with_regression_is_refused(tmp_path):
     foamio.write_case(tmp_path, m, "0", th, zeros6, U, Ub)
     f = foamio.FoamField(tmp_path / "0" / "tau")
     f.apply_bcs(m, "tau")   # as written: plain linearExtrapolation on the walls
+    walls = [i for i, p in enumerate(m.patches) if p.tau_bc == abi.BC_LINEAR_EXTRAPOLATION]
+    assert walls
     txt = (tmp_path / "0" / "tau").read_text()
     assert "linearExtrapolation" in txt
-    (tmp_path / "0" / "tau").write_text(txt.replace("type linearExtrapolation;", "type linearExtrapolation; useRegression true;", 1)
-                                        if "type linearExtrapolation;" in txt else
-                                        txt.replace("linearExtrapolation;", "linearExtrapolation;\n        useRegression   true;", 1))
+    (tmp_path / "0" / "tau").write_text(txt.replace("linearExtrapolation;", "linearExtrapolation;\n        useRegression   true;"))
     f2 = foamio.FoamField(tmp_path / "0" / "tau")
-    with pytest.raises(foamio.FoamError, match="useRegression true"):
-        f2.apply_bcs(m, "tau")
+    f2.apply_bcs(m, "tau")
+    assert all(m.patches[i].tau_bc == abi.BC_LINEAR_EXTRAPOLATION_REG for i in walls)
+    foamio.write_case(tmp_path / "again", m, "0", th, zeros6, U, Ub)
+    assert "useRegression   true" in (tmp_path / "again" / "0" / "tau").read_text()
+    m2 = mesh.tensor_grid(spec.grid)
+    foamio.FoamField(tmp_path / "again" / "0" / "tau").apply_bcs(m2, "tau")
+    assert [p.tau_bc for p in m2.patches] == [p.tau_bc for p in m.patches]

@@ -16,11 +16,11 @@ from rheotool_b200 import abi, cases, foamio
 FIXTURE = Path(__file__).parent / "golden" / "aneurysm_patch"
 
 
-def _case():
+def _case(wall_tau_bc=abi.BC_LINEAR_EXTRAPOLATION):
     m = foamio.read_polymesh(FIXTURE)
     # BCs as in the reference's viscoelastic tutorials: walls zeroGradient theta / linearExtrapolation tau; the cut surface
     # (in- and outflow) holds fixedValue theta
-    bc = {"walls": (abi.BC_ZERO_GRADIENT, abi.BC_LINEAR_EXTRAPOLATION), "cut": (abi.BC_FIXED_VALUE, abi.BC_ZERO_GRADIENT)}
+    bc = {"walls": (abi.BC_ZERO_GRADIENT, wall_tau_bc), "cut": (abi.BC_FIXED_VALUE, abi.BC_ZERO_GRADIENT)}
     for name, p in zip(m.patch_names, m.desc.patches[: m.desc.n_patches]):
         p.theta_bc, p.tau_bc = bc.get(name, (abi.BC_ZERO_GRADIENT, abi.BC_ZERO_GRADIENT))
     c0, L = m.C.mean(0), np.ptp(m.C, axis=0).max()
@@ -92,6 +92,30 @@ def test_gpu_matches_oracle_on_the_unstructured_mesh(limiter):
     assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-8
     assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-8
     assert rel_l2(g.download(abi.FIELD_TAU_B), oc.get(0, 0, abi.FIELD_TAU_B)) <= 1e-8
+
+
+@pytest.mark.gpu
+def test_gpu_regression_walls_match_oracle_on_the_unstructured_mesh():
+    """linearExtrapolation with `useRegression true` (linearExtrapolationFvPatchField.C:152-219) on polyhedral wall cells (9 to 21
+    faces: the run-time slot loop of k_tau_bc_regress); the oracle's branch is pinned on the reference's text
+    (tests/golden/reference_correct.npz: *-regressionWalls)."""
+    from rheotool_b200.stress import GpuStressModel
+    m, models, U, Ub, phi, theta0, thetaB, dt = _case(abi.BC_LINEAR_EXTRAPOLATION_REG)
+    sc = tight(cases.scheme_ctl("cubista", "PBiCGStab", 1e-10))
+    oc, vals, vecs = _oracle(m, models, sc, U, Ub, phi, theta0, thetaB)
+    g = GpuStressModel(m, models, sc)
+    g.upload_state(0, theta0, np.zeros_like(theta0), vals, vecs, theta_b=thetaB)
+    g.upload_velocity(U, Ub, phi)
+    for n in range(3):
+        oc.store_old_time(); oc.step(dt)
+        g.store_old_time(); g.correct(dt)
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-9
+    ref_b = oc.get(0, 0, abi.FIELD_TAU_B)
+    assert rel_l2(g.download(abi.FIELD_TAU_B), ref_b) <= 1e-9
+    plain = _oracle(*( _case()[:2] + (sc,) + _case()[2:7]))[0]
+    for n in range(3):
+        plain.store_old_time(); plain.step(dt)
+    assert rel_l2(plain.get(0, 0, abi.FIELD_TAU_B), ref_b) > 1e-4, "the regression branch must differ from the gradient branch"
 
 
 @pytest.mark.parametrize("n", [(2, 1, 1), (2, 2, 1)])
