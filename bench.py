@@ -67,16 +67,18 @@ def peaks():
 
 
 def measured_traffic(config: str, kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full capture of this
-    config (profiles/r1_traffic.json), or None when the capture does not hold this kernel / configuration."""
-    p = ROOT / "profiles" / "r1_traffic.json"
-    if not p.exists():
-        return None, None
-    t = json.loads(p.read_text())
-    k = t.get("configs", {}).get(config, {}).get(kernel.strip("()"))
-    if not k:
-        return None, None
-    return k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"], "profiles/r1_traffic.json (" + t.get("source", "") + ")"
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu capture of this config
+    (profiles/r2_traffic.json, else round 1's profiles/r1_traffic.json), or None when no capture holds this kernel /
+    configuration."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        p = ROOT / "profiles" / name
+        if not p.exists():
+            continue
+        t = json.loads(p.read_text())
+        k = t.get("configs", {}).get(config, {}).get(kernel.strip("()"))
+        if k:
+            return k["dram_read_bytes_per_launch"] + k["dram_write_bytes_per_launch"], f"profiles/{name} (" + t.get("source", "") + ")"
+    return None, None
 
 
 def kernel_bytes_per_cell(kernel: str, dims: int, n_modes: int, n_colours: int):

@@ -56,22 +56,40 @@ def to_unit(v, u):
     return v, u
 
 
-def launches(path):
+def launches(path, traffic_json=None, config=None):
+    """launch list (gpu__time_duration.sum per launch); when the same pass also holds dram__bytes_read.sum / dram__bytes_write.sum
+    the table gets DRAM columns and, with `traffic_json config`, the per-kernel averages are merged into that JSON file
+    (bench.py reads it for the `traffic` of its roofline object)."""
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
-        if row.get("Metric Name") != "gpu__time_duration.sum":
+        m = row.get("Metric Name")
+        if m not in ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum"):
             continue
         v, _ = to_unit(row["Metric Value"], row["Metric Unit"])
-        a = agg.setdefault(short(row["Kernel Name"]), [0, 0.0])
-        a[0] += 1
-        a[1] += v
+        a = agg.setdefault(short(row["Kernel Name"]), [0, 0.0, 0.0, 0.0])
+        if m == "gpu__time_duration.sum":
+            a[0] += 1
+            a[1] += v
+        elif m == "dram__bytes_read.sum":
+            a[2] += v
+        else:
+            a[3] += v
     tot = sum(v[1] for v in agg.values())
-    print(f"# launch list summary of `{path}` (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES)\n")
-    print("| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|")
+    has_dram = any(v[2] or v[3] for v in agg.values())
+    print(f"# launch list summary of `{path}` (ncu --metrics gpu__time_duration.sum{', dram__bytes_read.sum, dram__bytes_write.sum' if has_dram else ''} --clock-control none; cold-cache, serialised: compare SHARES)\n")
+    print("| kernel | launches | total us | avg us | share |" + (" DRAM read MB / launch | DRAM write MB / launch | DRAM GB/s |" if has_dram else "") + "\n|---|---:|---:|---:|---:|" + ("---:|---:|---:|" if has_dram else ""))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-        print(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {100 * v[1] / tot:.1f}% |")
+        extra = f" {v[2] / v[0] / 1e6:.1f} | {v[3] / v[0] / 1e6:.1f} | {(v[2] + v[3]) / v[1] / 1e3:.0f} |" if has_dram else ""
+        print(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.1f} | {100 * v[1] / tot:.1f}% |" + extra)
     print(f"\ntotal {tot:.1f} us over {sum(v[0] for v in agg.values())} launches")
+    if traffic_json and config and has_dram:
+        import json, os
+        t = json.load(open(traffic_json)) if os.path.exists(traffic_json) else {"source": "", "configs": {}}
+        t["source"] = "ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over the bench command (tools/gpu_call.sh r2f); per-launch averages"
+        t.setdefault("configs", {})[config] = {k: {"launches": v[0], "dram_read_bytes_per_launch": v[2] / v[0], "dram_write_bytes_per_launch": v[3] / v[0],
+                                                   "avg_us_under_ncu": v[1] / v[0]} for k, v in agg.items()}
+        json.dump(t, open(traffic_json, "w"), indent=1)
 
 
 def full(path):
@@ -99,4 +117,4 @@ def full(path):
 
 
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full}[sys.argv[1]](*sys.argv[2:])
