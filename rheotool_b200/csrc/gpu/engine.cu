@@ -1500,7 +1500,8 @@ int rheo_gpu_div_tau(RheoGpu* h, int32_t stabilization, double* div_out) {
         }
         a.gradUb = h->d_gradUb.as<double>();
     }
-    LAUNCH(h, k_div_tau, cdiv(h->N, BLOCK), BLOCK, h->mv, a);
+    a.tileOrder = h->d_tileOrder.as<int>(); a.nTiles = h->nTiles;
+    LAUNCH(h, k_div_tau, cdiv(a.tileOrder ? h->nTiles * TILE : h->N, BLOCK), BLOCK, h->mv, a);
     CK(cudaMemcpyAsync(div_out, h->d_stage.p, (size_t)h->N * 3 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     h->d2hBytes += (long long)h->N * 3 * sizeof(double);
     CK(cudaStreamSynchronize(h->stream));

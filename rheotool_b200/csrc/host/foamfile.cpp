@@ -438,6 +438,22 @@ RheoHostMesh* rheo_io_read_polymesh(const char* dir) {
     m->nbr_C.assign(3 * (size_t)m->n_boundary_faces(), 0.0);
     m->global_cell.resize(m->n_cells);
     for (int c = 0; c < m->n_cells; ++c) m->global_cell[c] = c;
+    // ---- solved components: EXT-OF9 polyMesh::solutionD() is -1 in the directions normal to the `empty` patches, and
+    // polyMesh::validComponents<symmTensor>() = solutionD x solutionD > 0, i.e. in a 2-D x-y case xz and yz drop out (zz stays:
+    // (-1)(-1) = +1), which is what fvMatrix::solveSegregated loops over (the tensor-grid generator applies the same rule)
+    {
+        int sd[3] = {1, 1, 1};
+        for (const RheoPatchDesc& p : m->patches) {
+            if (p.type != RHEO_PATCH_EMPTY) continue;
+            for (int f = p.start; f < p.start + p.size; ++f) {
+                const double* S = &m->Sf[3 * (size_t)f];
+                const double mag = std::sqrt(S[0] * S[0] + S[1] * S[1] + S[2] * S[2]);
+                for (int d = 0; d < 3; ++d) if (std::fabs(S[d]) > 0.999 * mag) sd[d] = -1;
+            }
+        }
+        const int ij[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        for (int q = 0; q < 6; ++q) m->solved[q] = sd[ij[q][0]] * sd[ij[q][1]] > 0 ? 1 : 0;
+    }
     return m.release();
 }
 
