@@ -42,9 +42,9 @@ WEAK_REFINE = {1: (9, 9), 2: (18, 9), 4: (18, 18), 8: (36, 18)}
 
 STRONG_DECOMP = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 # shrunk replica of each configuration for the on-box parity check (cells: C2 ~12k, C3 ~74k, C4 ~14k x 4 modes, C5 64k)
-PARITY_SCALE = {"C1": 0.25, "C2": 1 / 9, "C3": 4 / 19, "C4": 24 / 252, "C5": 40 / 400}
+PARITY_SCALE = {"C1stock": 1.0, "C1": 0.25, "C2": 1 / 9, "C3": 4 / 19, "C4": 24 / 252, "C5": 40 / 400}
 # bounded sample of the CPU arm: the workload shrunk per direction (C5: 200^3 = the sub-cube one rank of the 8-GPU run owns)
-CPU_SAMPLE_SCALE = {"C1": 1.0, "C2": 1.0, "C3": 0.5, "C4": 0.5, "C5": 0.5}
+CPU_SAMPLE_SCALE = {"C1stock": 1.0, "C1": 1.0, "C2": 1.0, "C3": 0.5, "C4": 0.5, "C5": 0.5}
 
 
 def workload(name: str, n_gpus: int, scale: float, weak: bool = False):
@@ -55,6 +55,8 @@ def workload(name: str, n_gpus: int, scale: float, weak: bool = False):
         spec = cases.contraction_2d(rx, ry)
         return spec, (n_gpus, 1, 1), f"C2 2-D 4:1 planar contraction PTTLog, Contraction41 blocks x({rx},{ry})", "weak"
     spec = cases.by_name(name, scale)
+    if spec.stock and n_gpus != 1:
+        raise SystemExit("bench.py: --config C1stock (the 24,894-cell tutorial mesh) runs on one GPU")
     decomp = STRONG_DECOMP.get(n_gpus, (n_gpus, 1, 1)) if spec.dims == 3 else (n_gpus, 1, 1)
     return spec, decomp, f"{name} {spec.note}", "strong"
 
@@ -182,7 +184,16 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def synth(spec, m):
+    """(U, U_b, phi, theta0, theta_b or None): the synthetic fields of the workload on mesh `m`"""
+    if spec.stock:
+        return cases.stock_fields(spec, m)
+    return (*m.synth_fields(spec.synth), None)
+
+
 def build_rank_mesh(spec, decomp, rank, n_ranks):
+    if spec.stock:
+        return cases.stock_mesh(spec)
     if n_ranks == 1:
         return mesh.tensor_grid(spec.grid)
     return mesh.tensor_grid_part(spec.grid, *decomp, rank)
@@ -212,7 +223,7 @@ def parity_replica(args, n, rank, local, decomp, dist, steps=2):
     spec.schemes.solver = abi.SOLVER[args.solver]
     sc = _tight(spec.schemes)
     part = build_rank_mesh(spec, decomp, rank, n)
-    U, Ub, phi, theta0 = part.synth_fields(spec.synth)
+    U, Ub, phi, theta0, theta_b = synth(spec, part)
     rate = torch.tensor([part.max_courant_rate(phi)], dtype=torch.float64, device="cuda")
     if n > 1:
         dist.all_reduce(rate, op=dist.ReduceOp.MAX)
@@ -225,7 +236,7 @@ def parity_replica(args, n, rank, local, decomp, dist, steps=2):
     for mi in range(len(spec.models)):
         th = theta0 * (1.0 + 0.1 * mi)
         vals, vecs = eig_exp(th, local)
-        g.upload_state(mi, th, np.zeros_like(th), vals, vecs)
+        g.upload_state(mi, th, np.zeros_like(th), vals, vecs, theta_b=theta_b)
     g.upload_velocity(U, Ub, phi)
     its = []
     for _ in range(steps):
@@ -242,13 +253,13 @@ def parity_replica(args, n, rank, local, decomp, dist, steps=2):
     if rank != 0:
         return None
     from oracle import oracle as orc   # the checker
-    full = mesh.tensor_grid(spec.grid)
-    Uf, Ubf, phif, th0 = full.synth_fields(spec.synth)
+    full = build_rank_mesh(spec, (1, 1, 1), 0, 1)
+    Uf, Ubf, phif, th0, thb = synth(spec, full)
     oc = orc.OracleCase([full.desc], spec.models, sc)
     for mi in range(len(spec.models)):
         th = th0 * (1.0 + 0.1 * mi)
         vals, vecs = orc.calc_eig(th)
-        oc.set_state(0, mi, th, np.zeros_like(th), vals, vecs)
+        oc.set_state(0, mi, th, np.zeros_like(th), vals, vecs, theta_b=thb)
     oc.set_velocity(0, Uf, Ubf, phif)
     for _ in range(steps):
         oc.store_old_time(); oc.step(dt)
@@ -307,7 +318,7 @@ def run_ours(args):
         print(f"bench: parity replica done at {time.perf_counter() - t_start:.1f} s: {parity}", file=sys.stderr)
 
     m = build_rank_mesh(spec, decomp, rank, n)
-    U, Ub, phi, theta0 = m.synth_fields(spec.synth)
+    U, Ub, phi, theta0, theta_b = synth(spec, m)
     # dt for face-CFL 0.2 on the GLOBAL mesh
     rate = torch.tensor([m.max_courant_rate(phi)], dtype=torch.float64, device="cuda")
     cells = torch.tensor([float(m.n_cells)], dtype=torch.float64, device="cuda")
@@ -325,7 +336,7 @@ def run_ours(args):
     for mi in range(len(spec.models)):
         th = theta0 * (1.0 + 0.1 * mi)
         vals, vecs = eig_exp(th, local)
-        g.upload_state(mi, th, np.zeros_like(th), vals, vecs)
+        g.upload_state(mi, th, np.zeros_like(th), vals, vecs, theta_b=theta_b)
         del vals, vecs, th
     g.upload_velocity(U, Ub, phi)
     del theta0
@@ -520,8 +531,8 @@ def run_cpu_reference(args, n_steps, max_seconds=25.0, warmup=1):
     full_spec, _, full_label, _ = workload(args.config, 1, args.scale, False)
     spec, _, label, _ = workload(args.config, 1, scale, False)
     spec.schemes.solver = abi.SOLVER[args.solver]
-    m = mesh.tensor_grid(spec.grid)
-    U, Ub, phi, theta0 = m.synth_fields(spec.synth)
+    m = build_rank_mesh(spec, (1, 1, 1), 0, 1)
+    U, Ub, phi, theta0, _ = synth(spec, m)
     dt = spec.cfl / m.max_courant_rate(phi)
     R = max(1, min(cores, 64))
     threads = orc.set_num_threads(R)   # explicit: torchrun exports OMP_NUM_THREADS=1
@@ -563,7 +574,7 @@ def run_cpu_reference(args, n_steps, max_seconds=25.0, warmup=1):
             "krylov_iterations": max(its)}, (full_spec, full_label, dt)
 
 
-K_SAMPLE_SCALE = {"C1": 1.0, "C2": 0.45, "C3": 0.5, "C4": 0.25, "C5": 0.25}
+K_SAMPLE_SCALE = {"C1stock": 1.0, "C1": 1.0, "C2": 0.45, "C3": 0.5, "C4": 0.25, "C5": 0.25}
 
 
 def reference_ordering_iterations(args, steps=2):
@@ -572,8 +583,8 @@ def reference_ordering_iterations(args, steps=2):
     from oracle import oracle as orc
     spec, _, label, _ = workload(args.config, 1, args.scale * K_SAMPLE_SCALE[args.config], False)
     spec.schemes.solver = abi.SOLVER[args.solver]
-    m = mesh.tensor_grid(spec.grid)
-    U, Ub, phi, theta0 = m.synth_fields(spec.synth)
+    m = build_rank_mesh(spec, (1, 1, 1), 0, 1)
+    U, Ub, phi, theta0, _ = synth(spec, m)
     dt = spec.cfl / m.max_courant_rate(phi)
     oc = orc.OracleCase([m.desc], spec.models, spec.schemes)
     for mi in range(len(spec.models)):
@@ -603,7 +614,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="C5", choices=["C1", "C2", "C3", "C4", "C5"],
+    ap.add_argument("--config", default="C5", choices=["C1", "C1stock", "C2", "C3", "C4", "C5"],
                     help="BASELINE.json configuration; default C5 (64 M cells: the mesh the scaling target names), strong scaling over --gpus")
     ap.add_argument("--weak", action="store_true", help="with --config C2: round 1's weak-scaling family (~971k cells per GPU)")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload per direction (tests only; 1.0 = the named config)")
@@ -619,7 +630,7 @@ def main():
         if rank != 0:
             return
         cb, (spec, label, dt) = run_cpu_reference(args, args.steps, max_seconds=150.0, warmup=args.warmup)
-        n_full = int(np.prod([len(a) - 1 for a in (spec.grid.xs, spec.grid.ys, spec.grid.zs)])) if len(spec.grid.boxes) == 1 else None
+        n_full = int(np.prod([len(a) - 1 for a in (spec.grid.xs, spec.grid.ys, spec.grid.zs)])) if (spec.grid is not None and len(spec.grid.boxes) == 1) else None
         _, _, _, scaling = workload(args.config, args.gpus, args.scale, args.weak)
         line = {"impl": "reference", "metric": "stress-step Mcell-steps/s (update+assembly+solve)", "value": cb["value"], "unit": "Mcell-steps/s",
                 "n_gpus": args.gpus, "steps": cb["steps"], "warmup": max(1, args.warmup), "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
@@ -643,7 +654,7 @@ def main():
             out["config"]["krylov_iterations_reference_ordering_note"] = "CPU oracle in the reference's (natural) cell order on " + ksample
             roof = out.get("roofline")
             if roof and roof.get("step_frac") is not None:
-                spec_dims = 2 if args.config in ("C1", "C2") else 3
+                spec_dims = 2 if args.config in ("C1", "C1stock", "C2") else 3
                 modes = out["config"]["modes"]
                 per_cell_ref = ((1480 + 1304 * kref) if spec_dims == 3 else (1192 + 880 * kref)) * modes
                 roof["step_bytes_per_cell_contract_reference_k"] = per_cell_ref

@@ -17,7 +17,7 @@ REF_CASE = Path("/root/reference/of90/tutorials/rheoFoam/Cylinder/Oldroyd-BLog")
 
 @pytest.fixture(scope="module")
 def cyl(tmp_path_factory):
-    return blockmesh.cylinder_stock_mesh(tmp_path_factory.mktemp("cylinder"))
+    return cases.stock_mesh(cases.cylinder_stock(), tmp_path_factory.mktemp("cylinder"))
 
 
 def test_expansion_and_arc_follow_blockmesh():
@@ -71,32 +71,11 @@ def test_parametrised_dictionary_equals_the_tutorials_own(tmp_path):
 
 
 def _case(m):
-    """the tutorial's model (constant/constitutiveProperties: Oldroyd-BLog, etaS 0.59, etaP 0.41, lambda 0.7 -> De = 0.7) and BC
-    kinds (0/theta, 0/tau: inlet fixedValue, walls + cylinder zeroGradient theta / linearExtrapolation tau, outlet zeroGradient)
-    with a smooth synthetic velocity that vanishes on the cylinder"""
-    bc = {"inlet": (abi.BC_FIXED_VALUE, abi.BC_FIXED_VALUE), "walls": (abi.BC_ZERO_GRADIENT, abi.BC_LINEAR_EXTRAPOLATION),
-          "cylinder": (abi.BC_ZERO_GRADIENT, abi.BC_LINEAR_EXTRAPOLATION), "outlet": (abi.BC_ZERO_GRADIENT, abi.BC_ZERO_GRADIENT)}
-    for name, p in zip(m.patch_names, m.desc.patches[: m.desc.n_patches]):
-        if name in bc:
-            p.theta_bc, p.tau_bc = bc[name]
-
-    def vel(x):
-        r2 = x[:, 0] ** 2 + x[:, 1] ** 2
-        par = 1.5 * (1 - (x[:, 1] / 2) ** 2)                      # Poiseuille profile of the channel
-        damp = 1 - np.exp(-(np.sqrt(r2) - 1).clip(0) * 3)          # -> 0 on the cylinder
-        return np.stack([par * damp, 0.3 * par * damp * np.sin(x[:, 0]) * (x[:, 1] / 2), np.zeros(len(x))], axis=1)
-
-    U, Ub = vel(m.C), vel(m.Cf[m.n_internal:])
-    phi = (vel(m.Cf) * m.Sf).sum(1)
-    s = m.C / 2.0
-    theta0 = np.stack([0.3 * np.sin(s[:, 0]) * np.exp(-0.05 * s[:, 0] ** 2), 0.2 * np.cos(s[:, 1]), np.zeros(len(s)), -0.2 * np.cos(s[:, 0] + s[:, 1]),
-                       np.zeros(len(s)), 0.1 * np.sin(s[:, 1])], axis=1)
-    sb = m.Cf[m.n_internal:] / 2.0
-    thetaB = np.stack([0.3 * np.sin(sb[:, 0]) * np.exp(-0.05 * sb[:, 0] ** 2), 0.2 * np.cos(sb[:, 1]), np.zeros(len(sb)), -0.2 * np.cos(sb[:, 0] + sb[:, 1]),
-                       np.zeros(len(sb)), 0.1 * np.sin(sb[:, 1])], axis=1)
-    dt = 0.5 / m.max_courant_rate(phi)
-    models = [cases.model_desc("Oldroyd-BLog", rho=1.0, etaS=0.59, etaP=0.41, lambda_=0.7)]
-    return models, U, Ub, phi, theta0, thetaB, dt
+    """the tutorial's model and BC kinds with a smooth synthetic velocity that vanishes on the cylinder (cases.cylinder_stock)"""
+    spec = cases.cylinder_stock()
+    U, Ub, phi, theta0, thetaB = cases.stock_fields(spec, m)
+    dt = spec.cfl / m.max_courant_rate(phi)
+    return spec.models, U, Ub, phi, theta0, thetaB, dt
 
 
 def test_oracle_runs_on_the_stock_cylinder_mesh(cyl):
