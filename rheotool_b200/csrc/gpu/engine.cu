@@ -932,7 +932,6 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* statsOut) {
     if (h->ctl.solver != RHEO_SOLVER_PBICGSTAB && h->ctl.solver != RHEO_SOLVER_PBICG) return fail("rheo_gpu_step: unknown solver (fvSolution solver PBiCGStab or PBiCG)");
     const bool pbicg = h->ctl.solver == RHEO_SOLVER_PBICG;
     if (pbicg) {
-        if (h->nRanks > 1) return fail("rheo_gpu_step: PBiCG on the device runs on one rank (pbicg.cuh); decomposed cases use PBiCGStab");
         if (!h->d_FsT.p) {
             if (h->d_FsT.alloc((size_t)h->K * h->NS * sizeof(double))) return 1;
             if (zero(h, h->d_FsT)) return 1;

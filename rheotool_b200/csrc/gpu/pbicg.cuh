@@ -14,8 +14,10 @@
 //
 // This is the CORRECTNESS-FIRST version: one thread per cell, run-time slot loops, one launch per colour and direction,
 // separate reduction kernels with the scalar control in their last-block epilogue (same KrylovCtl block as PBiCGStab).
-// It reads each matrix row twice per product instead of streaming it through the row-tile pipeline of krylov.cuh, and
-// runs on one rank (processor-patch columns are not added): PBiCGStab remains the tuned, multi-GPU path.
+// It reads each matrix row twice per product instead of streaming it through the row-tile pipeline of krylov.cuh: PBiCGStab
+// remains the tuned path.  Several ranks (solve.inl: solve_batch_pbicg): the products skip the ghost slots here; pA and pT are
+// halo-swapped before them and k_ghost (krylov.cuh) adds the processor-patch columns of A and of A^T afterwards (EXT-OF9
+// lduMatrix::Tmul uses interfaceIntCoeffs, which are the A^T slots); DILU / DILU^T stay rank-local; dots are all-reduced.
 // STATUS: run on B200 in round 2 (tests/test_gpu_pbicg.py): parity with the oracle's PBiCG, with PBiCGStab on the device and
 // with the reference fixtures; same iteration counts as the oracle on the renumbered mesh.
 #pragma once
@@ -84,7 +86,7 @@ __global__ void __launch_bounds__(BLOCK) k_pb_init_rT(MeshView m, int nModes, Rh
             for (int s = 0; s < m.K; ++s) {
                 const size_t e = ell_t(m.K, s, c);
                 const int nb = m.nbrA[e];
-                if (nb == c || nb >= m.N) continue;
+                if (nb == c) continue;   // ghost columns included: psi holds the neighbour ranks' values (halo swap at the start of the step)
                 const double d = A[e] - AT[e];
 #pragma unroll
                 for (int j = 0; j < NR; ++j) acc[j] += d * rp.psi[md * NR + j][nb];
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(BLOCK) k_pb_init_rT(MeshView m, int nModes, Rh
 // wArT = wA . rT per RHS; epilogue: beta
 template <int NR>
 __global__ void __launch_bounds__(BLOCK) k_pb_dot(int N, int NP, int nModes, KrylovShared* ks, const double* __restrict__ wA, const double* __restrict__ rT,
-                                                   double* partials, double* out, unsigned* counter, SolveCtl sc) {
+                                                   double* partials, double* out, unsigned* counter, int ctlWhat, SolveCtl sc) {
     pdl_sync();
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(BLOCK) k_pb_dot(int N, int NP, int nModes, Kry
         }
         block_reduce_to_partials<NR>(red, partials, md * NR, nModes * NR);
     }
-    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, CTL_PB_BETA, ks, nModes * NR, sc);
+    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);   // CTL_PB_BETA, or CTL_NONE before an all-reduce
 }
 
 // pA = wA + beta pA, pT = wT + beta pT (first iteration of a right-hand side: plain copies)
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(BLOCK) k_pb_update_p(int N, int NP, int nModes
 template <int NR>
 __global__ void __launch_bounds__(BLOCK) k_pb_spmv(MeshView m, int nModes, KrylovShared* ks, const double* __restrict__ diag, const double* __restrict__ A,
                                                     const double* __restrict__ AT, const double* __restrict__ pA, const double* __restrict__ pT,
-                                                    double* __restrict__ wA, double* __restrict__ wT, double* partials, double* out, unsigned* counter, SolveCtl sc) {
+                                                    double* __restrict__ wA, double* __restrict__ wT, double* partials, double* out, unsigned* counter, int ctlWhat, SolveCtl sc) {
     pdl_sync();
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
@@ -188,14 +190,14 @@ __global__ void __launch_bounds__(BLOCK) k_pb_spmv(MeshView m, int nModes, Krylo
         }
         block_reduce_to_partials<NR>(red, partials, md * NR, nModes * NR);
     }
-    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, CTL_PB_ALPHA, ks, nModes * NR, sc);
+    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);   // CTL_PB_ALPHA, or CTL_NONE (ghost columns + all-reduce follow)
 }
 
 // psi += alpha pA; rA -= alpha wA; rT -= alpha wT; sum|rA| per RHS; epilogue: residual, iteration count, convergence
 template <int NR>
 __global__ void __launch_bounds__(BLOCK) k_pb_update_x_r(int N, int NP, int nModes, RhsPtrs rp, KrylovShared* ks, const double* __restrict__ pA,
                                                           const double* __restrict__ wA, const double* __restrict__ wT, double* __restrict__ rA,
-                                                          double* __restrict__ rT, double* partials, double* out, unsigned* counter, SolveCtl sc) {
+                                                          double* __restrict__ rT, double* partials, double* out, unsigned* counter, int ctlWhat, SolveCtl sc) {
     pdl_sync();
     if (ks->nActive == 0) return;
     const int stride = gridDim.x * BLOCK;
@@ -224,7 +226,7 @@ __global__ void __launch_bounds__(BLOCK) k_pb_update_x_r(int N, int NP, int nMod
         }
         block_reduce_to_partials<NR>(red, partials, md * NR, nModes * NR);
     }
-    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, CTL_PB_END, ks, nModes * NR, sc);
+    finalize_ctl(partials, gridDim.x, nModes * NR, out, counter, gridDim.x, ctlWhat, ks, nModes * NR, sc);   // CTL_PB_END, or CTL_NONE before an all-reduce
 }
 
 }  // namespace rk

@@ -304,11 +304,19 @@ int solve_batch_pbicg(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, 
     const double* AT = h->d_FsT.as<double>();
     const int nc = h->nColours;
 
+    // Several ranks (EXT-OF9 lduMatrix::Amul / Tmul with processor interfaces, gSumProd / gSumMag): DILU and DILU^T stay rank-local
+    // (block-Jacobi across ranks, as in OpenFOAM); each product is preceded by the halo swap of pA and pT and followed by the
+    // ghost columns (k_ghost, twice: A with pA, A^T with pT — Tmul's interfaceIntCoeffs are exactly the A^T slots); every dot and
+    // residual sum goes through all_reduce_ctl, which also runs the scalar control step on the summed values.
+    const bool multi = h->nRanks > 1;
+    double* redScratch = red + 3 * MAX_RED;   // dot correction of the transposed ghost columns: not used by anything
+
     // gAverage(psi), rA = b - A psi, rT = rA, normFactor, initial residual: the same kernel as PBiCGStab (r0 = r)
     double* sumPsi = h->d_sumPsi.as<double>() + (size_t)firstMode * NR;
     if (all_reduce(h, sumPsi, nrhs)) return 1;
     LAUNCH(h, (k_krylov_init<NR, KT>), GRID(h, (k_krylov_init<NR, KT>), N), BLOCK, h->mv, nModes, rp, diag, A, sumPsi, (double)h->nGlobalCells, rA, rT, part, redB, counter,
-           CTL_INIT, ks, sc);
+           multi ? CTL_NONE : CTL_INIT, ks, sc);
+    if (multi && all_reduce_ctl(h, redB, 3 * nrhs, CTL_INIT, nrhs, sc)) return 1;
     // EXT-OF9 PBiCG::solve: the transpose residual starts from source - A^T psi
     LAUNCH(h, (k_pb_init_rT<NR>), GRID(h, (k_pb_init_rT<NR>), N), BLOCK, h->mv, nModes, rp, A, AT, rA, rT);
     int launched = 0;
@@ -325,14 +333,26 @@ int solve_batch_pbicg(RheoGpu* h, const RhsPtrs& rp, int firstMode, int nModes, 
                 const int c0 = h->colourStart[k], c1 = h->colourStart[k + 1];
                 if (c1 > c0) LAUNCH(h, (k_pb_sweep<NR, 0>), GRID(h, (k_pb_sweep<NR, 0>), c1 - c0), BLOCK, h->mv, c0, c1, nModes, ks, rD, A, AT, rA, rT, wA, wT);
             }
-            LAUNCH(h, (k_pb_dot<NR>), GRID(h, (k_pb_dot<NR>), N), BLOCK, N, NP, nModes, ks, wA, rT, part, red, counter, sc);
+            LAUNCH(h, (k_pb_dot<NR>), GRID(h, (k_pb_dot<NR>), N), BLOCK, N, NP, nModes, ks, wA, rT, part, red, counter, multi ? CTL_NONE : CTL_PB_BETA, sc);
+            if (multi && all_reduce_ctl(h, red, nrhs, CTL_PB_BETA, nrhs, sc)) return 1;
             LAUNCH(h, (k_pb_update_p<NR>), GRID(h, (k_pb_update_p<NR>), N), BLOCK, N, NP, nModes, ks, wA, wT, pA, pT);
-            LAUNCH(h, (k_pb_spmv<NR>), GRID(h, (k_pb_spmv<NR>), N), BLOCK, h->mv, nModes, ks, diag, A, AT, pA, pT, wA, wT, part, red, counter, sc);
-            LAUNCH(h, (k_pb_update_x_r<NR>), GRID(h, (k_pb_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, pA, wA, wT, rA, rT, part, red, counter, sc);
+            if (multi && (halo_interleaved<NR>(h, nModes, pA) || halo_interleaved<NR>(h, nModes, pT))) return 1;
+            LAUNCH(h, (k_pb_spmv<NR>), GRID(h, (k_pb_spmv<NR>), N), BLOCK, h->mv, nModes, ks, diag, A, AT, pA, pT, wA, wT, part, red, counter, multi ? CTL_NONE : CTL_PB_ALPHA, sc);
+            if (multi) {
+                if (h->nBcells) {
+                    const int gg = std::min(cdiv(h->nBcells, BLOCK), 4 * h->nSms);
+                    LAUNCH(h, (k_ghost<NR, 0>), gg, BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, A, pA, wA, pT, red, part, counter);          // wA += A_ghost pA; wA.pT corrected
+                    LAUNCH(h, (k_ghost<NR, 0>), gg, BLOCK, h->mv, h->nBcells, h->d_bcells.as<int>(), nModes, ks, AT, pT, wT, pA, redScratch, part, counter);   // wT += A^T_ghost pT
+                }
+                if (all_reduce_ctl(h, red, nrhs, CTL_PB_ALPHA, nrhs, sc)) return 1;
+            }
+            LAUNCH(h, (k_pb_update_x_r<NR>), GRID(h, (k_pb_update_x_r<NR>), N), BLOCK, N, NP, nModes, rp, ks, pA, wA, wT, rA, rT, part, red, counter, multi ? CTL_NONE : CTL_PB_END, sc);
+            if (multi && all_reduce_ctl(h, red, nrhs, CTL_PB_END, nrhs, sc)) return 1;
             ++launched;
         }
         CK(cudaMemcpyAsync(h->h_ks, ks, sizeof(KrylovShared), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
+        if (h->h_ks->pad[0]) return fail("peer-memory wait expired: a neighbour rank did not reach the halo swap / reduction (peer.cuh)");
         if (h->h_ks->nActive == 0 || launched > h->ctl.max_iter + 2) break;
         spec = 1;
     }

@@ -240,18 +240,10 @@ void LogConformationGPU::readSchemes(const fvMesh& mesh, const word& thetaName)
     }
     const dictionary& sol = mesh.solverDict(thetaName);
     const word solver(sol.lookup("solver"));
-    // the solver fvSolution names is the solver that runs: PBiCG (what every Log tutorial selects) on one rank (pbicg.cuh),
-    // PBiCGStab on any number of ranks.  A decomposed PBiCG case is refused here instead of being solved differently.
+    // the solver fvSolution names is the solver that runs: PBiCG (what every Log tutorial selects; pbicg.cuh) or PBiCGStab (the
+    // tuned path: block ordering, fused kernels), each on any number of ranks
     if (solver == "PBiCGStab") ctl_.solver = RHEO_SOLVER_PBICGSTAB;
-    else if (solver == "PBiCG")
-    {
-        if (Pstream::parRun())
-        {
-            FatalErrorInFunction << "fvSolution selects PBiCG for " << thetaName << "; on several ranks the GPU path implements "
-                << "PBiCGStab + DILU only (select `solver PBiCGStab;`)" << exit(FatalError);
-        }
-        ctl_.solver = RHEO_SOLVER_PBICG;
-    }
+    else if (solver == "PBiCG") ctl_.solver = RHEO_SOLVER_PBICG;   // one rank or several (solve.inl: solve_batch_pbicg)
     else
     {
         FatalErrorInFunction << "fvSolution selects " << solver << " for " << thetaName

@@ -431,8 +431,8 @@ def read_schemes(case_dir, theta_name: str = "theta"):
     if solver not in abi.SOLVER:
         raise FoamError(f"{sol.path}: solver {solver} for {theta_name}; the stress step implements {sorted(abi.SOLVER)} (+ DILU)")
     relax = sol.scalar(f"relaxationFactors/equations/{theta_name}", 0.0)
-    # the solver the file names is the solver that runs: PBiCG (what the Log tutorials select) on one rank (pbicg.cuh),
-    # PBiCGStab on any number of ranks; a decomposed PBiCG case fails loudly at the first step instead of being substituted
+    # the solver the file names is the solver that runs: PBiCG (what the Log tutorials select; pbicg.cuh) or PBiCGStab (the tuned
+    # path), each on any number of ranks
     ctl = cases.scheme_ctl(tok[1], solver, sol.scalar(f"{at}/tolerance", 1e-6), sol.scalar(f"{at}/relTol", 0.0), int(sol.scalar(f"{at}/minIter", 0)),
                            int(sol.scalar(f"{at}/maxIter", 1000)), relax, ddt=ddt, cn_psi=cn_psi, bounded=bounded)
     return ctl, solver

@@ -67,7 +67,7 @@ def gloo_rank(rank, world, port, case, scale, decomp, out_dir):
         raise
 
 
-def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol):
+def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol, solver="PBiCGStab"):
     """Each rank: its part of the mesh on cuda:<rank>; all ranks: the oracle on the same decomposition
     (in-process emulation) is run by rank 0 only and compared by the parent test."""
     try:
@@ -83,7 +83,7 @@ def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol):
         info = distributed.rank_info()
         dt = distributed.global_time_step(part, phi, spec.cfl)
         distributed.check_processor_patches(part, phi)
-        sc = tight(spec.schemes, tol)
+        sc = tight(spec.schemes, tol, solver=solver)
         g = GpuStressModel(part, spec.models, sc, rank)
         distributed.connect(g, info)
         for mi in range(len(spec.models)):

@@ -32,6 +32,18 @@ def _free_port():
     ("C5", 20 / 400, (2, 2, 2), 1),
 ])
 def test_decomposed_gpu_run_matches_single_rank_oracle(case, scale, decomp, steps):
+    _decomposed_run(case, scale, decomp, steps, "PBiCGStab")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,scale,decomp,steps", [("C3", 4 / 19, (2, 1, 1), 2), ("C2", 1 / 9, (2, 1, 1), 2)])
+def test_decomposed_pbicg_run_matches_single_rank_oracle(case, scale, decomp, steps):
+    """the tutorials' solver (fvSolution: PBiCG + DILU) on several ranks: Amul and Tmul with processor interfaces, DILU / DILU^T
+    rank-local, every dot all-reduced (solve.inl: solve_batch_pbicg)"""
+    _decomposed_run(case, scale, decomp, steps, "PBiCG")
+
+
+def _decomposed_run(case, scale, decomp, steps, solver):
     world = decomp[0] * decomp[1] * decomp[2]
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs, have {_n_gpus()}")
@@ -39,12 +51,12 @@ def test_decomposed_gpu_run_matches_single_rank_oracle(case, scale, decomp, step
     from mp_worker import gpu_rank
     tol = 1e-15
     with tempfile.TemporaryDirectory() as td:
-        mp.spawn(gpu_rank, args=(world, _free_port(), case, scale, decomp, steps, td, tol), nprocs=world, join=True)
+        mp.spawn(gpu_rank, args=(world, _free_port(), case, scale, decomp, steps, td, tol, solver), nprocs=world, join=True)
         ranks = [dict(np.load(Path(td) / f"gpu_rank{r}.npz")) for r in range(world)]
     spec = cases.by_name(case, scale)
     s = Setup(spec)
     assert float(ranks[0]["dt"]) == pytest.approx(s.dt, rel=1e-12)
-    oc = s.oracle(tight(spec.schemes, tol))
+    oc = s.oracle(tight(spec.schemes, tol, solver=solver))
     for _ in range(steps):
         oc.store_old_time(); oc.step(s.dt)
     for mi in range(len(spec.models)):
