@@ -173,6 +173,12 @@ int rheo_gpu_upload_fluidity(RheoGpu* h, int32_t mode, const double* Phi, const 
  * emptyFvPatchField has size 0, so the shim has nothing to put there).  Pageable or pinned host memory. */
 int rheo_gpu_upload_velocity(RheoGpu* h, const double* U, const double* U_b, const double* phi);
 
+/* Caller-supplied velocity gradient: correct(alpha, gradU) with gradU != nullptr (constitutiveEq.H:346-350; utils/boilerLog.H:1
+ * `L(gradU == nullptr ? fvc::grad(U)() : *gradU)`, as filmModel.C:408 calls it).  gradU9[9*n_cells] in OpenFOAM's tensor order
+ * (L_ij = d_i U_j at 3i+j) replaces the device's own Gauss-linear grad(U) in every following step; NULL returns to fvc::grad(U).
+ * (`alpha` needs no entry point: no *Log model reads it inside correct().) */
+int rheo_gpu_upload_grad_u(RheoGpu* h, const double* gradU9);
+
 /* Temperature-dependent relaxation time and polymer viscosity (Oldroyd_BLog.C:133-135 and the same lines of GiesekusLog,
  * PTTLog, FENE-PLog, FENE-CRLog, WhiteMetznerCYLog: `lambda = thermoLambdaPtr_->createField(lambda_)`): per-cell values
  * lambda_cell[n_cells], etaP_cell[n_cells] in the caller's numbering replace the scalars of RheoModelDesc for `mode`; the caller

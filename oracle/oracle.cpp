@@ -133,6 +133,7 @@ struct Rank {
     Mesh mesh;
     std::vector<Mode> modes;
     dvec U, Ub, phi;
+    dvec gradUext;   // caller-supplied gradU (correct(alpha, gradU), boilerLog.H:1), OpenFOAM tensor order; empty: fvc::grad(U)
     // per-step work (one mode at a time, like the reference)
     dvec L, rhs, fFene, diag, lower, upper, source, iC, bC, gradTheta;
 };
@@ -779,6 +780,7 @@ int correct_mode(Case& cs, int mi, double dt, RheoStepStats* st) {
         dvec fb((size_t)3 * m.nB(), 0.0);
         face_values_boundary(cs, r, 3, [&](int q) { return cs.ranks[q].U.data(); }, rk.Ub.data(), fb.data());
         rk.L.resize((size_t)9 * m.nCells);
+        if (!rk.gradUext.empty()) { rk.L = rk.gradUext; return; }   // boilerLog.H:1: L(gradU == nullptr ? fvc::grad(U)() : *gradU)
         gauss_grad(m, 3, rk.U.data(), fb.data(), rk.L.data());
         // gauss_grad stores, for component k of U, gradient d at [3k+d]; OpenFOAM's L_ij = d_i U_j = [3i+j]
         for (int c = 0; c < m.nCells; ++c) {
@@ -1394,6 +1396,15 @@ int orc_add_mode(void* h, const RheoModelDesc* d) {
 
 int orc_set_state(void* h, int rank, int mode, const double* theta, const double* tau, const double* eigvals,
                   const double* eigvecs, const double* theta_b, const double* tau_b);
+// correct(alpha, gradU) with a caller-supplied gradient (NULL: back to fvc::grad(U))
+int orc_set_grad_u(void* h, int rank, const double* gradU9) {
+    Case& cs = *(Case*)h;
+    Rank& rk = cs.ranks[rank];
+    if (!gradU9) rk.gradUext.clear();
+    else rk.gradUext.assign(gradU9, gradU9 + 9 * (size_t)rk.mesh.nCells);
+    return 0;
+}
+
 // BMPLog: the fluidity field of `mode` (Phi, MUST_READ in BMPLog.C:112-122)
 int orc_set_fluidity(void* h, int rank, int mode, const double* Phi, const double* Phi_b) {
     Case& cs = *(Case*)h;

@@ -37,7 +37,7 @@ def lib() -> C.CDLL:
             "orc_get": (I, [P, I, I, I, P]), "orc_jacobi": (None, [I, P, P, P]),
             "orc_calc_eig": (None, [I, P, P, P, I]), "orc_decompose_gradU": (None, [I, P, P, P, D, I, P, P]),
             "orc_model_rhs": (None, [P, I, P, P, P, P, P, P]), "orc_model_rhs_tau": (None, [P, I, P, P, P, P, P, P, P]), "orc_tau": (None, [P, I, P, P, P, P]),
-            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_div_tau": (I, [P, I, I, P]), "orc_set_fluidity": (I, [P, I, I, P, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
+            "orc_gauss_grad": (I, [P, I, I, P, P, P]), "orc_div_tau": (I, [P, I, I, P]), "orc_set_fluidity": (I, [P, I, I, P, P]), "orc_set_grad_u": (I, [P, I, P]), "orc_last_error": (C.c_char_p, []), "orc_set_num_threads": (I, [I]), "orc_set_thermo": (I, [P, I, I, P, P]),
         }
         for n, (r, a) in sig.items():
             f = getattr(L, n)
@@ -87,6 +87,11 @@ class OracleCase:
     def set_state(self, rank, mode, theta=None, tau=None, eigvals=None, eigvecs=None, theta_b=None, tau_b=None):
         keep = [np.ascontiguousarray(a, dtype=np.float64) if a is not None else None for a in (theta, tau, eigvals, eigvecs, theta_b, tau_b)]
         lib().orc_set_state(self._h, rank, mode, *[_p(a) for a in keep])
+
+    def set_grad_u(self, rank, gradU=None):
+        """correct(alpha, gradU): a caller-supplied velocity gradient instead of fvc::grad(U) (boilerLog.H:1); None resets"""
+        a = None if gradU is None else np.ascontiguousarray(gradU, dtype=np.float64)
+        lib().orc_set_grad_u(self._h, rank, _p(a))
 
     def set_fluidity(self, rank, mode, Phi, Phi_b=None):
         """BMPLog: the fluidity field (BMPLog.C:112-122)"""

@@ -127,6 +127,7 @@ GPU_SYMBOLS = {
     "rheo_gpu_correct": (C.c_int, [_P, _P, _P, _P, _D, _I, _P, _P, _P]),
     "rheo_gpu_div_tau": (C.c_int, [_P, _I, _P]),
     "rheo_gpu_upload_fluidity": (C.c_int, [_P, _I, _P, _P]),
+    "rheo_gpu_upload_grad_u": (C.c_int, [_P, _P]),
     "rheo_gpu_get_renumbering": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ell": (C.c_int, [_P, _P, _P, _P]),
     "rheo_gpu_get_ordering": (C.c_int, [_P, _P, _I]),

@@ -146,6 +146,7 @@ struct RheoGpu {
     bool rec3 = false;             // d_tileRec holds version-3 records: k_flux3 + k_source_init run instead of k_flux_assemble + k_cell_source2 + k_krylov_init
     std::vector<int> sweepOrder;   // block ordering: chunks in geometric order (host/ordering.hpp)
     DevBuf d_tileOrder;            // rec3: the assembly's tile walk (sweepOrder padded to nTiles); RHEO_TILE_ORDER=0 walks in index order
+    bool externalGradU = false;    // rheo_gpu_upload_grad_u: d_gradU holds the caller's gradient, the assembly must not overwrite it
     bool pdl = true;               // programmatic dependent launch on this handle's kernels (pdl_policy)
     int nHidden = 0;               // BMPLog: its fluidity equation is modes[0] (RHEO_MODEL_BMP_FLUIDITY), the caller's mode 0 is modes[1]
     DevBuf d_CfI;                  // [3][nInt] internal face centres, only when a patch uses linearExtrapolation with useRegression
@@ -978,7 +979,7 @@ int do_step(RheoGpu* h, double dt, RheoStepStats* statsOut) {
             ModeDev& md = h->modes[mi];
             FluxArgs fa{};
             const bool fluidity = md.mp.model == RHEO_MODEL_BMP_FLUIDITY;
-            fa.cl = cl; fa.nU = mi == 0 ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv;
+            fa.cl = cl; fa.nU = (mi == 0 && !h->externalGradU) ? 3 : 0; fa.lim = h->lim; fa.noConv = noConv;
             // BMPLog.C:158: `== - fvm::Sp(1/lambda, Phi)` puts V/lambda on the diagonal next to the ddt coefficient; PhiEqn.relax() has its own factor
             fa.rDeltaT = fluidity ? ddtDiag + 1.0 / md.mp.lambda : ddtDiag;
             fa.relax = fluidity ? md.desc.bmp_relax : h->ctl.relax;
@@ -1351,6 +1352,26 @@ int rheo_gpu_upload_state(RheoGpu* h, int32_t mode, const double* theta, const d
     return 0;
 }
 
+// correct(alpha, gradU) with gradU != nullptr (boilerLog.H:1): the caller's gradient, OpenFOAM tensor order L_ij = d_i U_j at 3i+j,
+// into the planes the source kernels read (g[3k+d] = d_d U_k: the transposed component order)
+int rheo_gpu_upload_grad_u(RheoGpu* h, const double* gradU9) {
+    if (!h) return fail("rheo_gpu_upload_grad_u: null handle");
+    CK(cudaSetDevice(h->device));
+    if (!gradU9) { h->externalGradU = false; return 0; }
+    if (put_cells(h, gradU9, 9, h->d_gradU.as<double>())) return 1;
+    // plane 3i+j holds L_ij; the kernels want d_d U_k at 3k+d = L_dk: swap the off-diagonal pairs through the staging buffer
+    const size_t pb = (size_t)h->NP * sizeof(double);
+    double* g = h->d_gradU.as<double>();
+    for (const auto& pr : {std::pair<int, int>{1, 3}, {2, 6}, {5, 7}}) {
+        CK(cudaMemcpyAsync(h->d_stage.p, g + (size_t)pr.first * h->NP, pb, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(g + (size_t)pr.first * h->NP, g + (size_t)pr.second * h->NP, pb, cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(g + (size_t)pr.second * h->NP, h->d_stage.p, pb, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->externalGradU = true;
+    return 0;
+}
+
 // BMPLog: the fluidity field (component xx of the hidden mode; the other components stay 0)
 int rheo_gpu_upload_fluidity(RheoGpu* h, int32_t mode, const double* Phi, const double* Phi_b) {
     if (!h || !Phi) return fail("rheo_gpu_upload_fluidity: null argument");
@@ -1480,6 +1501,7 @@ int rheo_gpu_div_tau(RheoGpu* h, int32_t stabilization, double* div_out) {
     if ((int)h->modes.size() - h->nHidden > MAX_MODES_DIV) return fail("rheo_gpu_div_tau: more than 8 modes");
     CK(cudaSetDevice(h->device));
     const bool coupling = stabilization == RHEO_STAB_COUPLING;
+    if (coupling && h->externalGradU) return fail("rheo_gpu_div_tau: stabilization coupling needs fvc::grad(U), but a caller-supplied gradU is in place (rheo_gpu_upload_grad_u(h, NULL) first)");
     DivTauArgs a{};
     a.nModes = (int)h->modes.size() - h->nHidden;
     for (int mi = 0; mi < a.nModes; ++mi) {

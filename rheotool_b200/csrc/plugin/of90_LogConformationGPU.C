@@ -509,9 +509,13 @@ void LogConformationGPU::downloadAll()
 
 void LogConformationGPU::correct(const volScalarField* alpha, const volTensorField* gradU)
 {
-    if (alpha || gradU)
+    // `alpha` (constitutiveTwoPhaseMixture.H:130-131) is part of the signature only: no *Log model reads it inside correct()
+    // (Oldroyd_BLog.C:127-179 and the same bodies of the other models), so it is ignored here as it is there.
+    // `gradU` (filmModel.C:408) replaces fvc::grad(U) (utils/boilerLog.H:1): hand it to the device, or return to its own gradient.
+    check(rheo_gpu_upload_grad_u(gpu_, gradU ? reinterpret_cast<const double*>(gradU->primitiveField().begin()) : nullptr), "rheo_gpu_upload_grad_u");
+    if (gradU && deviceDivTau_ && stabOption_ == soCoupling)
     {
-        FatalErrorInFunction << "two-phase (alpha) and caller-supplied gradU (filmModel.C:408) are not available on the GPU path"
+        FatalErrorInFunction << "a caller-supplied gradU with stabilization coupling needs `deviceDivTau false` (divTau uses fvc::grad(U))"
                              << exit(FatalError);
     }
     const fvMesh& mesh = U().mesh();

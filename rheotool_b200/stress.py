@@ -72,6 +72,12 @@ class GpuStressModel:
         arrs = [_c(a) for a in (theta, tau, eigvals, eigvecs, theta_b, tau_b)]
         _check(abi.lib().rheo_gpu_upload_state(self._h, mode, *[_p(a) for a in arrs]))
 
+    def upload_grad_u(self, gradU=None):
+        """correct(alpha, gradU) with a caller-supplied velocity gradient (boilerLog.H:1; filmModel.C:408): [n_cells, 9] in OpenFOAM's
+        tensor order, used instead of fvc::grad(U) from now on; None returns to the device's own gradient."""
+        a = _c(gradU)
+        _check(abi.lib().rheo_gpu_upload_grad_u(self._h, _p(a)))
+
     def upload_fluidity(self, mode=0, Phi=None, Phi_b=None):
         """BMPLog: the fluidity field Phi (MUST_READ, BMPLog.C:112-122), cell values and (fixedValue patches) boundary values."""
         a, b = _c(Phi), _c(Phi_b)
