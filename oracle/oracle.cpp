@@ -1259,6 +1259,7 @@ static int div_tau_explicit(Case& cs, int stab, std::vector<dvec>& out) {
         x[0] = s * t[0]; x[1] = s * t[1]; x[2] = s * t[2]; x[3] = s * t[1]; x[4] = s * t[3]; x[5] = s * t[4]; x[6] = s * t[2]; x[7] = s * t[4]; x[8] = s * t[5];
     };
     for (int mi = 0; mi < nModes; ++mi) {
+        if (cs.ranks[0].modes[mi].fluidityOf >= 0) continue;   // BMPLog's hidden fluidity mode has no stress and no etaP of its own
         // ---- fvc::div(tau/rho)
         for_ranks(cs, [&](int r) {
             const Rank& rk = cs.ranks[r];

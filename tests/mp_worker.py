@@ -67,7 +67,19 @@ def gloo_rank(rank, world, port, case, scale, decomp, out_dir):
         raise
 
 
-def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol, solver="PBiCGStab"):
+def bmp_model():
+    """the BMPLog model of the multi-GPU fluidity case (shared with the parent test)"""
+    from rheotool_b200 import cases
+    return cases.model_desc("BMPLog", rho=1.0, etaS=0.01, etaP=0.01, lambda_=0.7, bmp_G0=0.8, bmp_k=2.0, bmp_Phi0=2.5, bmp_PhiInf=40.0)
+
+
+def bmp_fluidity(C, owner_b):
+    """smooth initial fluidity from the cell centres; boundary values = those of the adjacent cells"""
+    Phi = 2.5 * (1.0 + 0.05 * np.sin(5 * C[:, 0]) * np.cos(3 * C[:, 1]))
+    return Phi, Phi[owner_b].copy()
+
+
+def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol, solver="PBiCGStab", bmp=False):
     """Each rank: its part of the mesh on cuda:<rank>; all ranks: the oracle on the same decomposition
     (in-process emulation) is run by rank 0 only and compared by the parent test."""
     try:
@@ -78,6 +90,8 @@ def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol, solver
         from rheotool_b200 import abi, cases, distributed, mesh
         from rheotool_b200.stress import GpuStressModel, eig_exp
         spec = cases.by_name(case, scale)
+        if bmp:
+            spec.models = [bmp_model()]
         part = mesh.tensor_grid_part(spec.grid, *decomp, rank)
         U, Ub, phi, theta0 = part.synth_fields(spec.synth)
         info = distributed.rank_info()
@@ -91,6 +105,8 @@ def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol, solver
             vals, vecs = eig_exp(th, rank)
             g.upload_state(mi, th, np.zeros_like(th), vals, vecs)
         g.upload_velocity(U, Ub, phi)
+        if bmp:
+            g.upload_fluidity(0, *bmp_fluidity(part.C, part.owner[part.n_internal:]))
         iters = []
         for _ in range(steps):
             g.store_old_time()
@@ -98,6 +114,7 @@ def gpu_rank(rank, world, port, case, scale, decomp, steps, out_dir, tol, solver
             iters.append(g.last_iterations())
         div_tau = g.div_tau(abi.STAB_COUPLING)   # collective: swaps the velocity gradient of the ghost cells
         np.savez(Path(out_dir) / f"gpu_rank{rank}.npz", cells=part.global_cells(), dt=dt, iters=np.array(iters), div_tau=div_tau,
+                 fluidity=g.fluidity(0) if bmp else np.zeros(0),
                  **{f"theta{mi}": g.theta(mi) for mi in range(len(spec.models))},
                  **{f"tau{mi}": g.tau(mi) for mi in range(len(spec.models))})
         g.close()

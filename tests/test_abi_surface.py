@@ -79,6 +79,12 @@ def test_constants_match_the_headers():
     assert (defs["RHEO_PATCH_PATCH"], defs["RHEO_PATCH_WALL"], defs["RHEO_PATCH_EMPTY"], defs["RHEO_PATCH_PROCESSOR"]) == (0, 1, 2, 3)
     assert (defs["RHEO_BC_FIXED_VALUE"], defs["RHEO_BC_ZERO_GRADIENT"], defs["RHEO_BC_LINEAR_EXTRAPOLATION"], defs["RHEO_BC_EMPTY"],
             defs["RHEO_BC_PROCESSOR"]) == (0, 1, 2, 3, 4)
+    # round 2: BMPLog, the fluidity fields, the regression flavour of linearExtrapolation, the stabilization options of divTau
+    assert defs["RHEO_MODEL_BMP_LOG"] == abi.MODEL_NAMES["BMPLog"] and defs["RHEO_MODEL_BMP_FLUIDITY"] not in abi.MODEL_NAMES.values()
+    assert (defs["RHEO_FIELD_FLUIDITY"], defs["RHEO_FIELD_FLUIDITY_B"]) == (abi.FIELD_FLUIDITY, abi.FIELD_FLUIDITY_B)
+    assert defs["RHEO_BC_LINEAR_EXTRAPOLATION_REG"] == abi.BC_LINEAR_EXTRAPOLATION_REG
+    assert (defs["RHEO_STAB_NONE"], defs["RHEO_STAB_BSD"], defs["RHEO_STAB_COUPLING"]) == (abi.STAB_NONE, abi.STAB_BSD, abi.STAB_COUPLING)
+    assert defs["RHEO_DDT_STEADY_STATE"] == abi.DDT_STEADY_STATE
 
 
 def test_compute_calls_fail_loudly_without_a_gpu():

@@ -46,6 +46,11 @@ def test_without_structure_kinetics_bmp_is_oldroyd_b_with_lambda_from_the_fluidi
     assert np.abs(a.get(0, 0, abi.FIELD_FLUIDITY) - PHI0).max() <= 1e-12 * PHI0
     assert rel_l2(a.get(0, 0, abi.FIELD_THETA), b.get(0, 0, abi.FIELD_THETA)) <= 1e-12
     assert rel_l2(a.get(0, 0, abi.FIELD_TAU), b.get(0, 0, abi.FIELD_TAU)) <= 1e-12
+    # divTau: the same stress, and a coupling term that scales with each model's own etaP (BMP: 0.01, "only used for stabilization")
+    assert rel_l2(a.div_tau(0, abi.STAB_NONE), b.div_tau(0, abi.STAB_NONE)) <= 1e-11
+    ca = a.div_tau(0, abi.STAB_COUPLING) - a.div_tau(0, abi.STAB_NONE)
+    cb = b.div_tau(0, abi.STAB_COUPLING) - b.div_tau(0, abi.STAB_NONE)
+    assert np.abs(cb).max() > 0 and rel_l2(ca * ((1.0 / PHI0) / 0.01), cb) <= 1e-9
 
 
 def test_fluidity_of_a_fluid_at_rest_relaxes_to_phi0_at_the_rate_one_over_lambda():
@@ -102,6 +107,7 @@ def test_gpu_bmp_log_matches_oracle(name, scale, ddt):
     assert rel_l2(g.fluidity(0), oc.get(0, 0, abi.FIELD_FLUIDITY)) <= 1e-10
     assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-10
     assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-10
+    assert rel_l2(g.div_tau(abi.STAB_COUPLING), oc.div_tau(0, abi.STAB_COUPLING)) <= 1e-10
 
 
 @pytest.mark.gpu
@@ -119,3 +125,40 @@ def test_gpu_bmp_log_relaxed_equations_match_oracle():
         g.store_old_time(); g.correct(s.dt)
     assert rel_l2(g.fluidity(0), oc.get(0, 0, abi.FIELD_FLUIDITY)) <= 1e-10
     assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-10
+
+
+@pytest.mark.parametrize("n", [(2, 2, 1)])
+def test_partition_invariance_of_the_bmp_oracle(n):
+    """the fluidity equation across processor patches (emulated ranks vs one rank): its hidden mode takes part in the halo copies,
+    the rank-ordered reductions and the per-rank DILU like every other right-hand side"""
+    spec = _spec("C3", 3 / 19, _bmp(bmp_k=2.0))
+    s = Setup(spec)
+    sc = tight(spec.schemes)
+    one = s.oracle(sc)
+    Phi, Phi_b = _phi0(s, vary=0.05)
+    one.set_fluidity(0, 0, Phi, Phi_b)
+    nr = n[0] * n[1] * n[2]
+    c2r = s.mesh.simple_decomp(*n)
+    subs = [s.mesh.decompose(c2r, nr, r) for r in range(nr)]
+    many = orc.OracleCase([x.desc for x in subs], spec.models, sc)
+    addr = []
+    for r, sub in enumerate(subs):
+        ca, fa = sub.proc_addressing()
+        addr.append(ca)
+        many.set_state(r, 0, s.theta_mode(0)[ca], s.tau0[ca], s.eigvals_mode(0)[ca], s.eigvecs_mode(0)[ca])
+        gf = np.abs(fa) - 1
+        ph = np.where(fa > 0, s.phi[gf], -s.phi[gf])
+        gb = gf[sub.n_internal:] - s.mesh.n_internal
+        Ub = np.zeros((sub.n_boundary, 3)); Ub[gb >= 0] = s.Ub[gb[gb >= 0]]
+        Pb = np.zeros(sub.n_boundary); Pb[gb >= 0] = Phi_b[gb[gb >= 0]]
+        many.set_velocity(r, s.U[ca], Ub, ph)
+        many.set_fluidity(r, 0, Phi[ca], Pb)
+    for _ in range(2):
+        one.store_old_time(); one.step(s.dt)
+        many.store_old_time(); many.step(s.dt)
+    for fld in (abi.FIELD_FLUIDITY, abi.FIELD_THETA, abi.FIELD_TAU):
+        ref = one.get(0, 0, fld)
+        got = np.empty_like(ref)
+        for r in range(nr):
+            got[addr[r]] = many.get(r, 0, fld)
+        assert rel_l2(got, ref) < 1e-11, fld

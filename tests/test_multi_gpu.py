@@ -43,7 +43,13 @@ def test_decomposed_pbicg_run_matches_single_rank_oracle(case, scale, decomp, st
     _decomposed_run(case, scale, decomp, steps, "PBiCG")
 
 
-def _decomposed_run(case, scale, decomp, steps, solver):
+@pytest.mark.gpu
+def test_decomposed_bmp_log_run_matches_single_rank_oracle():
+    """BMPLog on two ranks: the hidden fluidity mode takes part in the halo swaps and all-reduces like every other right-hand side"""
+    _decomposed_run("C3", 4 / 19, (2, 1, 1), 2, "PBiCGStab", bmp=True)
+
+
+def _decomposed_run(case, scale, decomp, steps, solver, bmp=False):
     world = decomp[0] * decomp[1] * decomp[2]
     if _n_gpus() < world:
         pytest.skip(f"needs {world} GPUs, have {_n_gpus()}")
@@ -51,12 +57,17 @@ def _decomposed_run(case, scale, decomp, steps, solver):
     from mp_worker import gpu_rank
     tol = 1e-15
     with tempfile.TemporaryDirectory() as td:
-        mp.spawn(gpu_rank, args=(world, _free_port(), case, scale, decomp, steps, td, tol, solver), nprocs=world, join=True)
+        mp.spawn(gpu_rank, args=(world, _free_port(), case, scale, decomp, steps, td, tol, solver, bmp), nprocs=world, join=True)
         ranks = [dict(np.load(Path(td) / f"gpu_rank{r}.npz")) for r in range(world)]
     spec = cases.by_name(case, scale)
+    if bmp:
+        from mp_worker import bmp_fluidity, bmp_model
+        spec.models = [bmp_model()]
     s = Setup(spec)
     assert float(ranks[0]["dt"]) == pytest.approx(s.dt, rel=1e-12)
     oc = s.oracle(tight(spec.schemes, tol, solver=solver))
+    if bmp:
+        oc.set_fluidity(0, 0, *bmp_fluidity(s.mesh.C, s.mesh.owner[s.mesh.n_internal:]))
     for _ in range(steps):
         oc.store_old_time(); oc.step(s.dt)
     for mi in range(len(spec.models)):
@@ -67,6 +78,12 @@ def _decomposed_run(case, scale, decomp, steps, solver):
                 got[d["cells"]] = d[f"{name}{mi}"]
             err = rel_l2(got, ref)
             assert err <= 1e-10, f"{case} {decomp} mode {mi} {name}: rel L2 {err:.3e}"
+    if bmp:
+        ref = oc.get(0, 0, abi.FIELD_FLUIDITY)
+        got = np.full_like(ref, np.nan)
+        for d in ranks:
+            got[d["cells"]] = d["fluidity"]
+        assert rel_l2(got, ref) <= 1e-10, f"BMPLog fluidity on {decomp}: rel L2 {rel_l2(got, ref):.3e}"
     # explicit part of constitutiveEq::divTau across the processor patches (constitutiveEq.C:72-132, stabilization coupling)
     ref = oc.div_tau(0, abi.STAB_COUPLING)
     got = np.full_like(ref, np.nan)
