@@ -12,14 +12,20 @@
 //   Oldroyd_BLog, GiesekusLog, PTTLog (linear / exponential / generalized, zeta != 0), FENE_PLog, FENE_CRLog,
 //   WhiteMetznerCYLog, RoliePolyLog, XPomPomLog, SaramitoLog, gaussDefCmpwConvectionScheme::{fvmDiv, phifDefC, lims} with
 //   every limiter row of limiters.H (its coupled-patch branches too, on emulated ranks),
-//   linearExtrapolationFvPatchField::updateCoeffs.  Measured agreement of theta, tau and
-//   their boundary fields after one and three correct() calls: <= 4e-15 relative L2 (test bar 1e-12).
+//   linearExtrapolationFvPatchField::updateCoeffs (the gradient branch and, round 2, the useRegression branch: two fixture
+//   cases, 6e-16).  Measured agreement of theta, tau and their boundary fields after one and three correct() calls:
+//   <= 4e-15 relative L2 (test bar 1e-12).
 //   NOT PINNED (not in /root/reference, restated from published OpenFOAM-9 / Eigen semantics):
 //   the OpenFOAM-9 layer under that text — gaussGrad/linear, EulerDdtScheme / backwardDdtScheme, fvMatrix::relax,
 //   solveSegregated, PBiCG / PBiCGStab / DILU iteration histories (the pin compares the SOLUTION of the assembled
 //   system, solved by the harness with a different method to round-off) — and Eigen 3.2.9's
 //   SelfAdjointEigenSolver (the reference's own jacobi.H alternative, constitutiveEq.C:418-426, stands in; theta
-//   and tau do not depend on the order or sign of the eigen-pairs).  Those parts stay pinned only by (a) analytic
+//   and tau do not depend on the order or sign of the eigen-pairs).  Round 2 added, equally UNPINNED: BMPLog (BMPLog.C:142-201 is
+//   reference text, but the harness does not compile it: its fluidity equation is restated here and held to the k = 0
+//   Oldroyd-B limit and the fluid-at-rest solution, tests/test_bmp_log.py), the explicit part of constitutiveEq::divTau
+//   (constitutiveEq.C:72-132 over EXT-OF9 fvc::div / gaussGrad boundary values; analytic identities, tests/test_div_tau.py),
+//   steadyState / bounded / CrankNicolson (tests/test_ddt_schemes.py, test_steady_bounded_thermo.py) and the caller-supplied
+//   gradU of correct(alpha, gradU).  Those parts stay pinned only by (a) analytic
 //   material functions and algebraic identities (tests/test_oracle_*.py), (b) cross-file steady states
 //   (RoliePoly.C, XPomPom.C; tests/test_oracle_analytic.py), (c) partition invariance on tensor grids and on a piece
 //   of the polyhedral polyMesh the reference ships (tests/test_unstructured.py).
