@@ -162,3 +162,28 @@ def test_partition_invariance_of_the_bmp_oracle(n):
         for r in range(nr):
             got[addr[r]] = many.get(r, 0, fld)
         assert rel_l2(got, ref) < 1e-11, fld
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["PBiCG", "RHEO_FLUX=1", "CrankNicolson"])
+def test_gpu_bmp_log_on_the_other_code_paths(variant, monkeypatch):
+    """the fluidity equation through the round-1 assembly kernels (PBiCG selects them, RHEO_FLUX=1 forces them) and with the ddt0
+    field of CrankNicolson"""
+    spec = _spec("C3", 3 / 19, _bmp(bmp_k=1.5))
+    sc = tight(spec.schemes, solver="PBiCG" if variant == "PBiCG" else None)
+    if variant == "CrankNicolson":
+        sc.ddt, sc.cn_psi = abi.DDT_CRANK_NICOLSON, 0.9
+    if variant == "RHEO_FLUX=1":
+        monkeypatch.setenv("RHEO_FLUX", "1")
+    s = Setup(spec)
+    oc, g = s.oracle(sc), s.gpu(sc)
+    Phi, Phi_b = _phi0(s, vary=0.05)
+    oc.set_fluidity(0, 0, Phi, Phi_b); g.upload_fluidity(0, Phi, Phi_b)
+    for _ in range(3):
+        oc.store_old_time(); oc.step(s.dt)
+        g.store_old_time(); g.correct(s.dt)
+    ref = oc.get(0, 0, abi.FIELD_FLUIDITY)
+    assert np.isfinite(ref).all()
+    assert rel_l2(g.fluidity(0), ref) <= 1e-9
+    assert rel_l2(g.theta(), oc.get(0, 0, abi.FIELD_THETA)) <= 1e-9
+    assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-9
