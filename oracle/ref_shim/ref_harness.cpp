@@ -73,7 +73,7 @@ public:
 
 #include "linearExtrapolation_updateCoeffs.inc"
 
-namespace refHarness { bool useRegression = false; }
+namespace refHarness { bool useRegression = false; thread_local const double* fluidity = nullptr; /* BMPLog: Phi after PhiEqn.solve(), per cell */ }
 
 // GeometricField::Boundary::evaluate (EXT-OF9): patches in order, each patch field's evaluate()
 template<class Type, template<class> class PatchField, class GeoMesh>
@@ -386,6 +386,18 @@ static int correctOnMesh(fvMesh& mesh, const RheoMeshDesc* md, const RheoModelDe
         case RHEO_MODEL_ROLIE_POLY_LOG: { constitutiveEqs::RoliePolyLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_XPOMPOM_LOG: { constitutiveEqs::XPomPomLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
         case RHEO_MODEL_SARAMITO_LOG: { constitutiveEqs::SaramitoLog m(Uf, phif, tauf, thetaf, valsf, vecsf); run(m); break; }
+        case RHEO_MODEL_BMP_LOG:
+        {
+            // the theta equation and theta -> tau of BMPLog::correct (BMPLog.C:168-199) with the fluidity handed in (ref_set_fluidity)
+            if (!refHarness::fluidity) return -1;
+            volScalarField Phif(IOobject("Phi"), mesh, dimensionedScalar("Phi", 0.0));
+            forAll(Phif, c) Phif[c] = refHarness::fluidity[c];
+            constitutiveEqs::BMPLog m(Uf, phif, tauf, thetaf, valsf, vecsf);
+            m.PhiPtr_ = &Phif;
+            m.G0_ = dimensionedScalar("G0", mm->bmp_G0);
+            run(m);
+            break;
+        }
         case RHEO_MODEL_PTT_LOG:
         {
             constitutiveEqs::PTTLog m(Uf, phif, tauf, thetaf, valsf, vecsf);
@@ -436,6 +448,9 @@ static int correctOnMesh(fvMesh& mesh, const RheoMeshDesc* md, const RheoModelDe
     return 0;
 }
 
+
+// BMPLog: the fluidity field (after PhiEqn.solve()) the next ref_correct of this thread uses; NULL clears it
+void ref_set_fluidity(const double* Phi) { refHarness::fluidity = Phi; }
 
 int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, double dt, int use_regression,
                 const double* U, const double* U_b, const double* phi,

@@ -64,6 +64,13 @@ def main():
     lims = {f"lims/{l}/{k}": v for l in range(6) for k, v in zip(("alpha", "beta", "bounds"), ref.lims(l))}
     np.savez_compressed(ROOT / "tests" / "golden" / "reference_cell.npz", theta=th, expD=D, V=V, nrot=nrot, M=M, omega=om, B=B,
                         innerP_T=ref.innerP(V.reshape(-1, 9), M, True), innerP=ref.innerP(V.reshape(-1, 9), M, False), **lims)
+    # BMPLog: the theta equation and theta -> tau of the reference text, fed with the fluidity of the oracle's PhiEqn
+    import test_bmp_log
+    bmp = {}
+    for name, scale in test_bmp_log.BMP_FIXTURE_CASES:
+        for k, (fl, th, ta, tab) in enumerate(test_bmp_log.bmp_reference_run(name, scale)):
+            bmp[f"{name}/step{k + 1}/fluidity"], bmp[f"{name}/step{k + 1}/theta"], bmp[f"{name}/step{k + 1}/tau"], bmp[f"{name}/step{k + 1}/tau_b"] = fl, th, ta, tab
+    np.savez_compressed(ROOT / "tests" / "golden" / "reference_bmp.npz", **bmp)
     print("written")
 
 
