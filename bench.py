@@ -462,7 +462,9 @@ def run_ours(args):
             bpc, frac_cells = kernel_bytes_per_cell(name, spec.dims, len(spec.models), len(cstart) - 1)
             cells_per_launch = m.n_cells * frac_cells
             achieved = (bpc * cells_per_launch / (tms / cnt * 1e-3) / 1e9) if bpc else None
-            traffic, traffic_src = measured_traffic(args.config, name)
+            # the committed ncu capture is of the N = 1 run at full size: its bytes per launch say nothing about a rank's share of a
+            # decomposed or shrunk mesh
+            traffic, traffic_src = measured_traffic(args.config, name) if (n == 1 and args.scale == 1.0) else (None, None)
             roof = {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                     "algorithmic_bytes_per_launch": (bpc * cells_per_launch) if bpc else None, "peak_source": peak_src,
