@@ -20,11 +20,10 @@
 //   solveSegregated, PBiCG / PBiCGStab / DILU iteration histories (the pin compares the SOLUTION of the assembled
 //   system, solved by the harness with a different method to round-off) — and Eigen 3.2.9's
 //   SelfAdjointEigenSolver (the reference's own jacobi.H alternative, constitutiveEq.C:418-426, stands in; theta
-//   and tau do not depend on the order or sign of the eigen-pairs).  Round 2 added: BMPLog — its theta equation and theta -> tau
-//   (BMPLog.C:168-199) ARE pinned on the reference text (oracle/_ref compiles correct() without the fluidity equation and takes
-//   the fluidity as an input: 2e-15, tests/golden/reference_bmp.npz); its fluidity equation (BMPLog.C:151-166, a scalar fvMatrix
-//   the stand-in types do not cover) is UNPINNED: restated here and held to the k = 0 Oldroyd-B limit, the fluid-at-rest
-//   solution and partition invariance (tests/test_bmp_log.py).  Equally unpinned: the explicit part of constitutiveEq::divTau
+//   and tau do not depend on the order or sign of the eigen-pairs).  Round 2 added: BMPLog — PINNED: oracle/_ref compiles the whole
+//   BMPLog::correct (BMPLog.C:142-201, fluidity equation included: PhiEqn is a scalar fvMatrix of the stand-in types, its
+//   convection term the reference's own scheme instantiated for a scalar); fluidity 4e-16, theta / tau 4e-15 after three chained
+//   calls (tests/test_bmp_log.py, tests/golden/reference_bmp.npz).  Equally unpinned: the explicit part of constitutiveEq::divTau
 //   (constitutiveEq.C:72-132 over EXT-OF9 fvc::div / gaussGrad boundary values; analytic identities, tests/test_div_tau.py),
 //   steadyState / bounded / CrankNicolson (tests/test_ddt_schemes.py, test_steady_bounded_thermo.py) and the caller-supplied
 //   gradU of correct(alpha, gradU).  Those parts stay pinned only by (a) analytic

@@ -48,7 +48,7 @@ def lib() -> C.CDLL:
         L.ref_innerP.restype, L.ref_innerP.argtypes = None, [I, P, P, I, P]
         L.ref_correct.restype, L.ref_correct.argtypes = I, [P, P, I, D, I] + [P] * 15
         L.ref_correct_multi.restype, L.ref_correct_multi.argtypes = I, [I, P, P, I, D, I] + [P] * 9
-        L.ref_set_fluidity.restype, L.ref_set_fluidity.argtypes = None, [P]
+        L.ref_set_fluidity.restype, L.ref_set_fluidity.argtypes = None, [P, P, I]
         _lib = L
     return _lib
 
@@ -92,10 +92,12 @@ def innerP(t1, t2, is_first_T: bool):
 
 
 def correct(mesh_desc, model_desc, limiter: int, dt: float, U, Ub, phi, theta, theta_b, tau, tau_b, eigvals, eigvecs,
-            use_regression=False, want_matrix=False, fluidity=None):
+            use_regression=False, want_matrix=False, fluidity=None, fluidity_b=None, solve_fluidity=False):
     """One XxxLog::correct() of the reference.  Returns a dict of the state after the call (+ the assembled thetaEqn).
-    BMPLog: `fluidity` = Phi per cell AFTER PhiEqn.solve() — the harness compiles BMPLog::correct without its fluidity equation
-    (BMPLog.C:168-199: the theta equation and theta -> tau)."""
+    BMPLog, solve_fluidity False: `fluidity` = Phi per cell AFTER PhiEqn.solve() — BMPLog::correct without its fluidity equation
+    (BMPLog.C:168-199: the theta equation and theta -> tau).  solve_fluidity True: `fluidity`, `fluidity_b` = Phi BEFORE the call;
+    the whole BMPLog::correct runs (BMPLog.C:142-201, PhiEqn as a scalar fvMatrix of the stand-in types) and the state returned
+    holds the new "fluidity" / "fluidity_b"."""
     n, nb = mesh_desc.n_cells, mesh_desc.n_faces - mesh_desc.n_internal_faces
     st = {
         "theta": _f(theta, (n, 6)).copy(), "theta_b": _f(theta_b, (nb, 6)).copy(),
@@ -108,14 +110,19 @@ def correct(mesh_desc, model_desc, limiter: int, dt: float, U, Ub, phi, theta, t
         mats = {"lower": np.zeros(nif), "upper": np.zeros(nif), "diag": np.zeros(n), "source": np.zeros((n, 6)),
                 "internalCoeffs": np.zeros((nb, 6)), "boundaryCoeffs": np.zeros((nb, 6))}
     U, Ub, phi = _f(U), _f(Ub), _f(phi)
-    fl = None if fluidity is None else _f(fluidity)
-    lib().ref_set_fluidity(_p(fl))
+    fl = None if fluidity is None else _f(fluidity).copy()
+    flb = None if fluidity_b is None else _f(fluidity_b).copy()
+    if solve_fluidity and flb is None:
+        flb = np.zeros(nb)
+    lib().ref_set_fluidity(_p(fl), _p(flb), 1 if solve_fluidity else 0)
     rc = lib().ref_correct(C.cast(C.byref(mesh_desc), C.c_void_p), C.cast(C.byref(model_desc), C.c_void_p), int(limiter),
                            float(dt), 1 if use_regression else 0, _p(U), _p(Ub), _p(phi),
                            _p(st["theta"]), _p(st["theta_b"]), _p(st["tau"]), _p(st["tau_b"]), _p(st["eigvals"]), _p(st["eigvecs"]),
                            _p(mats.get("lower")), _p(mats.get("upper")), _p(mats.get("diag")), _p(mats.get("source")),
                            _p(mats.get("internalCoeffs")), _p(mats.get("boundaryCoeffs")))
-    lib().ref_set_fluidity(None)
+    lib().ref_set_fluidity(None, None, 0)
+    if fl is not None:
+        st["fluidity"], st["fluidity_b"] = fl, flb
     if rc:
         raise RuntimeError("the reference harness holds no correct() text for this model")
     st.update(mats)

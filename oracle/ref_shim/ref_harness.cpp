@@ -43,6 +43,13 @@ tmp<fvSymmTensorMatrix> fvm::div(const surfaceScalarField& phi, const volSymmTen
     return scheme.fvmDiv(phi, vf);
 }
 
+tmp<fvScalarMatrix> fvm::div(const surfaceScalarField& phi, const volScalarField& vf)
+{
+    Istream is(refHarness::limiterName);
+    fv::gaussDefCmpwConvectionScheme<scalar> scheme(vf.mesh(), phi, is);
+    return scheme.fvmDiv(phi, vf);
+}
+
 // ---- linearExtrapolation: class shells + the reference's updateCoeffs() text ------------------------
 template<class Type>
 class fixedValueFvPatchField
@@ -73,7 +80,16 @@ public:
 
 #include "linearExtrapolation_updateCoeffs.inc"
 
-namespace refHarness { bool useRegression = false; thread_local const double* fluidity = nullptr; /* BMPLog: Phi after PhiEqn.solve(), per cell */ }
+namespace refHarness
+{
+bool useRegression = false;
+// BMPLog: fluidity per cell (+ per boundary face).  fluiditySolve == 0: Phi AFTER PhiEqn.solve() is handed in and the text without
+// the fluidity equation runs (BMPLog); != 0: Phi BEFORE the call is handed in, the whole correct() runs (BMPLogFull) and the
+// new fluidity is written back into the same arrays
+thread_local double* fluidity = nullptr;
+thread_local double* fluidityB = nullptr;
+thread_local int fluiditySolve = 0;
+}
 
 // GeometricField::Boundary::evaluate (EXT-OF9): patches in order, each patch field's evaluate()
 template<class Type, template<class> class PatchField, class GeoMesh>
@@ -104,6 +120,7 @@ void GeometricField<Type, PatchField, GeoMesh>::correctBoundaryConditions()
 }
 
 template void GeometricField<symmTensor, fvPatchField, volMesh>::correctBoundaryConditions();
+template void GeometricField<scalar, fvPatchField, volMesh>::correctBoundaryConditions();
 
 // ---- RheoMeshDesc -> fvMesh ---------------------------------------------------------------------------
 static inline vector v3(const double* p, label i) { return vector(p[3*i], p[3*i + 1], p[3*i + 2]); }
@@ -390,12 +407,30 @@ static int correctOnMesh(fvMesh& mesh, const RheoMeshDesc* md, const RheoModelDe
         {
             // the theta equation and theta -> tau of BMPLog::correct (BMPLog.C:168-199) with the fluidity handed in (ref_set_fluidity)
             if (!refHarness::fluidity) return -1;
-            volScalarField Phif(IOobject("Phi"), mesh, dimensionedScalar("Phi", 0.0));
-            forAll(Phif, c) Phif[c] = refHarness::fluidity[c];
-            constitutiveEqs::BMPLog m(Uf, phif, tauf, thetaf, valsf, vecsf);
+            volScalarField Phif(IOobject("Phi"), mesh, dimensionSet());
+            if (!refHarness::fluiditySolve)
+            {
+                forAll(Phif, c) Phif[c] = refHarness::fluidity[c];
+                constitutiveEqs::BMPLog m(Uf, phif, tauf, thetaf, valsf, vecsf);
+                m.PhiPtr_ = &Phif;
+                m.G0_ = dimensionedScalar("G0", mm->bmp_G0);
+                run(m);
+                break;
+            }
+            // the whole BMPLog::correct (BMPLog.C:142-201): Phi carries theta's patch kinds (fixedValue inlet, zeroGradient elsewhere)
+            for (label p = 0; p < md->n_patches; p++)
+                Phif.setPatchKind(p, md->patches[p].type == RHEO_PATCH_EMPTY ? pfEmpty : bcKind(md->patches[p].theta_bc));
+            loadField(Phif, refHarness::fluidity, (const double*) refHarness::fluidityB, md);
+            evaluateCoupled(Phif);
+            Phif.storeOldTime();
+            constitutiveEqs::BMPLogFull m(Uf, phif, tauf, thetaf, valsf, vecsf);
             m.PhiPtr_ = &Phif;
             m.G0_ = dimensionedScalar("G0", mm->bmp_G0);
+            m.Phi0_ = dimensionedScalar("Phi0", mm->bmp_Phi0);
+            m.PhiInf_ = dimensionedScalar("PhiInf", mm->bmp_PhiInf);
+            m.k_ = dimensionedScalar("k", mm->bmp_k);
             run(m);
+            storeField(Phif, refHarness::fluidity, refHarness::fluidityB, md);
             break;
         }
         case RHEO_MODEL_PTT_LOG:
@@ -450,7 +485,7 @@ static int correctOnMesh(fvMesh& mesh, const RheoMeshDesc* md, const RheoModelDe
 
 
 // BMPLog: the fluidity field (after PhiEqn.solve()) the next ref_correct of this thread uses; NULL clears it
-void ref_set_fluidity(const double* Phi) { refHarness::fluidity = Phi; }
+void ref_set_fluidity(double* Phi, double* Phi_b, int solve) { refHarness::fluidity = Phi; refHarness::fluidityB = Phi_b; refHarness::fluiditySolve = solve; }
 
 int ref_correct(const RheoMeshDesc* md, const RheoModelDesc* mm, int limiter, double dt, int use_regression,
                 const double* U, const double* U_b, const double* phi,

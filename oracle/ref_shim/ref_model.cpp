@@ -29,6 +29,9 @@
 #include "XPomPomLog_correct.inc"
 #elif defined(REF_MODEL_SaramitoLog)
 #include "SaramitoLog_correct.inc"
+#elif defined(REF_MODEL_BMPLogFull)
+#define Phi_ (*PhiPtr_)
+#include "BMPLogFull_correct.inc"
 #elif defined(REF_MODEL_BMPLog)
 #define Phi_ (*PhiPtr_)   // BMPLog.H: volScalarField Phi_; here a field the harness fills with the fluidity of after PhiEqn.solve()
 #include "BMPLog_correct.inc"

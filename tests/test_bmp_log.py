@@ -191,11 +191,12 @@ def test_gpu_bmp_log_on_the_other_code_paths(variant, monkeypatch):
     assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-9
 
 
-# ---- BMPLog's theta equation and theta -> tau against the reference's own text --------------------------------------------------
-# oracle/_ref compiles BMPLog::correct WITHOUT its fluidity equation (BMPLog.C:168-199; oracle/Makefile cuts the text, the scalar
-# fvMatrix of PhiEqn is not covered by the stand-in types) and takes the fluidity of after PhiEqn.solve() as an input.
-def bmp_reference_run(name, scale, steps=2):
-    """-> per step: (fluidity handed to the reference, theta, tau, tau_b of the reference); the oracle case it was chained with"""
+# ---- BMPLog::correct against the reference's own text -----------------------------------------------------------------------------
+# oracle/_ref compiles the WHOLE function (BMPLog.C:142-201): boilerLog.H, the fluidity equation (a scalar fvMatrix of the stand-in
+# types: fvm::ddt, the reference's GaussDefCmpw scheme instantiated for a scalar, fvm::Sp, the explicit source with tau && symm(L)),
+# the theta equation with the new fluidity, calcEig, theta -> tau, the tau boundary conditions.
+def bmp_reference_run(name, scale, steps=3):
+    """chained reference calls next to the oracle; -> per step (fluidity, theta, tau, tau_b) of the REFERENCE"""
     from oracle import ref
     spec = _spec(name, scale, _bmp(bmp_k=2.0))
     spec.schemes = cases.scheme_ctl("cubista", "PBiCGStab", 1e-15, relax=0.0)
@@ -204,14 +205,14 @@ def bmp_reference_run(name, scale, steps=2):
     Phi, Phi_b = _phi0(s, vary=0.05)
     oc.set_fluidity(0, 0, Phi, Phi_b)
     st = {"theta": s.theta0, "theta_b": oc.get(0, 0, abi.FIELD_THETA_B), "tau": s.tau0, "tau_b": oc.get(0, 0, abi.FIELD_TAU_B),
-          "eigvals": s.eigvals, "eigvecs": s.eigvecs}
+          "eigvals": s.eigvals, "eigvecs": s.eigvecs, "fluidity": Phi, "fluidity_b": oc.get(0, 0, abi.FIELD_FLUIDITY_B)}
     out = []
     for _ in range(steps):
         oc.store_old_time(); oc.step(s.dt)
-        phi_new = oc.get(0, 0, abi.FIELD_FLUIDITY)
         st = ref.correct(s.mesh.desc, spec.models[0], spec.schemes.limiter, s.dt, s.U, s.Ub, s.phi, st["theta"], st["theta_b"], st["tau"],
-                         st["tau_b"], st["eigvals"], st["eigvecs"], fluidity=phi_new)
-        out.append((phi_new, st["theta"], st["tau"], st["tau_b"]))
+                         st["tau_b"], st["eigvals"], st["eigvecs"], fluidity=st["fluidity"], fluidity_b=st["fluidity_b"], solve_fluidity=True)
+        out.append((st["fluidity"].copy(), st["theta"], st["tau"], st["tau_b"]))
+        assert rel_l2(oc.get(0, 0, abi.FIELD_FLUIDITY), st["fluidity"]) <= 1e-12, (name, "fluidity")
         for key, fld in (("theta", abi.FIELD_THETA), ("tau", abi.FIELD_TAU), ("tau_b", abi.FIELD_TAU_B)):
             assert rel_l2(oc.get(0, 0, fld), st[key]) <= 1e-12, (name, key)
     return out
@@ -224,15 +225,14 @@ def _ref_available():
 
 @pytest.mark.skipif(not _ref_available(), reason="oracle/_ref not built and /root/reference not present")
 @pytest.mark.parametrize("name,scale", BMP_PIN_CASES)
-def test_live_bmp_theta_equation_matches_the_reference_text(name, scale):
+def test_live_bmp_correct_matches_the_reference_text(name, scale):
     bmp_reference_run(name, scale)
 
 
 @pytest.mark.parametrize("name,scale", BMP_FIXTURE_CASES)
 def test_oracle_bmp_golden(name, scale):
-    """tests/golden/reference_bmp.npz (tools/make_golden_reference.py): the reference's theta / tau after two chained correct() calls
-    fed with the fluidity the oracle's own PhiEqn produced — the oracle must reproduce both the fluidity it handed over then and
-    the reference's answer"""
+    """tests/golden/reference_bmp.npz (tools/make_golden_reference.py): fluidity, theta, tau and tau_b of the reference's
+    BMPLog::correct after one, two and three chained calls"""
     from pathlib import Path
     gold = np.load(Path(__file__).parent / "golden" / "reference_bmp.npz")
     spec = _spec(name, scale, _bmp(bmp_k=2.0))
@@ -241,7 +241,7 @@ def test_oracle_bmp_golden(name, scale):
     oc = s.oracle(spec.schemes, sort_eig=False)
     Phi, Phi_b = _phi0(s, vary=0.05)
     oc.set_fluidity(0, 0, Phi, Phi_b)
-    for k in range(2):
+    for k in range(3):
         oc.store_old_time(); oc.step(s.dt)
         assert rel_l2(oc.get(0, 0, abi.FIELD_FLUIDITY), gold[f"{name}/step{k + 1}/fluidity"]) <= 1e-12
         for key, fld in (("theta", abi.FIELD_THETA), ("tau", abi.FIELD_TAU), ("tau_b", abi.FIELD_TAU_B)):
@@ -260,8 +260,8 @@ def test_gpu_bmp_matches_the_reference_fixture(name, scale):
     g = s.gpu(spec.schemes)
     Phi, Phi_b = _phi0(s, vary=0.05)
     g.upload_fluidity(0, Phi, Phi_b)
-    for k in range(2):
+    for k in range(3):
         g.store_old_time(); g.correct(s.dt)
-        assert rel_l2(g.fluidity(0), gold[f"{name}/step{k + 1}/fluidity"]) <= 1e-10
+        assert rel_l2(g.fluidity(0), gold[f"{name}/step{k + 1}/fluidity"]) <= 1e-10 * (10 ** k)
         assert rel_l2(g.theta(), gold[f"{name}/step{k + 1}/theta"]) <= 1e-10 * (10 ** k)
         assert rel_l2(g.tau(0), gold[f"{name}/step{k + 1}/tau"]) <= 1e-10 * (10 ** k)
