@@ -120,3 +120,26 @@ def test_gpu_matches_oracle_on_the_stock_cylinder_mesh(cyl, solver):
     assert rel_l2(g.tau(0), oc.get(0, 0, abi.FIELD_TAU)) <= 1e-9
     assert rel_l2(g.download(abi.FIELD_TAU_B), oc.get(0, 0, abi.FIELD_TAU_B)) <= 1e-9
     assert rel_l2(g.div_tau(abi.STAB_COUPLING), oc.div_tau(0, abi.STAB_COUPLING)) <= 1e-9
+
+
+REF_CONTRACTION = Path("/root/reference/of90/tutorials/rheoFoam/Contraction41/Oldroyd-BLog/system/blockMeshDict")
+
+
+@pytest.mark.skipif(not REF_CONTRACTION.exists(), reason="needs /root/reference (the builder's container)")
+def test_contraction41_tutorial_dictionary_gives_the_mesh_config_2_refines(tmp_path):
+    """two independent generators on BASELINE config 2's base mesh: the tutorial's own blockMeshDict (24 graded blocks) through
+    blockmesh.py, and cases.contraction_2d(1, 1) (the tensor-grid generator behind C2, which refines every block x9): the same 11,991
+    cells — centres and volumes to rounding — and the same boundary (the tutorial splits the walls into five patches)"""
+    from rheotool_b200 import foamio, mesh
+    P, faces, owner, nei, patches = blockmesh.generate(REF_CONTRACTION)
+    blockmesh.write_polymesh(tmp_path / "constant" / "polyMesh", P, faces, owner, nei, patches)
+    a = foamio.read_polymesh(tmp_path / "constant" / "polyMesh")
+    b = mesh.tensor_grid(cases.contraction_2d(1, 1).grid)
+    assert a.n_cells == b.n_cells == 11991 and a.n_internal == b.n_internal
+    ka = np.lexsort((np.round(a.C[:, 1], 9), np.round(a.C[:, 0], 9)))
+    kb = np.lexsort((np.round(b.C[:, 1], 9), np.round(b.C[:, 0], 9)))
+    assert np.abs(a.C[ka] - b.C[kb]).max() <= 1e-11 and np.abs(a.V[ka] - b.V[kb]).max() <= 1e-12
+    size = {n: p.size for n, p in zip(a.patch_names, a.patches)}
+    sizeb = {n: p.size for n, p in zip(b.patch_names, b.patches)}
+    assert size["inlet"] == sizeb["inlet"] and size["outlet"] == sizeb["outlet"] and size["frontAndBack"] == sizeb["frontAndBack"]
+    assert sum(v for n, v in size.items() if n.startswith("wall")) == sizeb["walls"]
