@@ -1,2 +1,3 @@
-# scratch GPU call (tag r3t): the CUDA path against the reference's BMPLog numbers (fluidity equation from the reference text)
-python -m pytest tests/test_bmp_log.py -m gpu -q --timeout 300 -k "fixture" 2>&1 | tail -12 | cut -c1-300
+# last GPU call of the round (tag r2zz): smoke() and the whole GPU suite on the committed state
+python __graft_entry__.py --smoke 2>&1 | tail -2
+python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/r2zz_pytest.log; cat gpurun_out/r2zz_pytest.log
