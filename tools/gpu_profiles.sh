@@ -1,8 +1,9 @@
 #!/bin/bash
+# (round 1's evidence script, kernel list updated; round 2's evidence call is tools/gpu_call.sh tag r2f, see profiles/README.md)
 # evidence for profiles/: bench lines (C2 with cpu_baseline, C3), ncu launch lists of the same commands, one ncu --set full
 # capture per config of one launch of every hot kernel (tag = $1).  Keeps gpurun_out small (raw CSV pages, no big reps).
 tag=${1:-x}
-KR='k_flux_assemble|k_cell_source2|k_eig_tau|k_krylov_init|k_update_p|k_sweep|k_spmv|k_make_s|k_update_x_r'
+KR='k_flux3|k_source_init|k_flux_assemble|k_cell_source2|k_eig_tau|k_krylov_init|k_bsweep|k_bspmv0|k_update_p|k_sweep|k_spmv|k_make_s|k_update_x_r'
 /usr/local/graft/bin/gpurun --timeout 1500 -- "python bench.py --steps 20 --warmup 3 > gpurun_out/${tag}_bench_C2.json 2> gpurun_out/${tag}_bench_C2.err
 python bench.py --config C3 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench_C3.json 2> gpurun_out/${tag}_bench_C3.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_bench_C2_reference.json 2> gpurun_out/${tag}_bench_C2_reference.err
