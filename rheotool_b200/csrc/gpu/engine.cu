@@ -587,7 +587,7 @@ int alloc_fields(RheoGpu* h, const RheoModelDesc* callerModes, int nCallerModes)
         return 1;
     zero(h, h->d_U); zero(h, h->d_Ub); zero(h, h->d_phi); zero(h, h->d_Fs); zero(h, h->d_diag); zero(h, h->d_rD);
     zero(h, h->d_Fell); zero(h, h->d_gradU);
-    h->stageBytes = std::max<size_t>(9 * (size_t)h->N, std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;
+    h->stageBytes = std::max<size_t>(std::max<size_t>(9 * (size_t)h->N, NP), std::max<size_t>(6 * nB, (size_t)h->nF)) * d8;   // NP: one padded plane (rheo_gpu_upload_grad_u)
     if (h->d_stage.alloc(h->stageBytes)) return 1;
     // BMPLog (BMPLog.C:142-201): the fluidity equation is solved before theta in every correct().  It runs through the same
     // assembly and solver as component xx of a padded symmTensor (the other components have a zero source and a zero initial
