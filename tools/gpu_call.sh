@@ -1,3 +1,3 @@
-# last GPU call of the round (tag r2zz): smoke() and the whole GPU suite on the committed state
-python __graft_entry__.py --smoke 2>&1 | tail -2
-python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/r2zz_pytest.log; cat gpurun_out/r2zz_pytest.log
+# last GPU call of the round (tag r2zzz): smoke() and the quick GPU tests on the rebuilt library
+python __graft_entry__.py --smoke 2>&1 | tail -1
+python -m pytest tests/test_grad_u.py tests/test_gpu_parity.py -m gpu -q -x 2>&1 | tail -3
